@@ -1,0 +1,166 @@
+/* vitok_b200.h -- C ABI of libvitok_b200.so: the drop-in boundary for the ViTok-v2 AE hot path.
+ *
+ * The reference (Na-VAE/vitok-release) has no FFI; its boundary for this path is the Python surface of
+ * vitok/models/ae.py and vitok/pp.  Each entry point below names the reference call site it replaces
+ * (paths relative to the reference repo root).  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); no hidden syncs or
+ *     allocations on the data path, so every call is CUDA-graph capturable;
+ *   - every function returns 0 on success or a negative vtk_status; the message for the calling thread
+ *     is available from vtk_last_error();
+ *   - bf16 tensors are row-major; row strides are in elements and must be multiples of 8; base pointers
+ *     16-byte aligned;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with VTK_ERR_CUDA.
+ */
+#ifndef VITOK_B200_H_
+#define VITOK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define VTK_ABI_VERSION 1
+
+typedef enum {
+  VTK_OK = 0,
+  VTK_ERR_CUDA = -1,        /* CUDA runtime / driver error, text in vtk_last_error()          -> RuntimeError */
+  VTK_ERR_BAD_ARG = -2,     /* shape / alignment / null-pointer violation                      -> ValueError   */
+  VTK_ERR_UNSUPPORTED = -3  /* valid in the reference but not implemented here (e.g. head_dim) -> NotImplementedError */
+} vtk_status;
+
+const char* vtk_last_error(void);
+int vtk_abi_version(void);
+int vtk_sm_count(void); /* <0 when no CUDA device is usable */
+
+/* ------------------------------------------------------------------------------------------------
+ * NaFlex pre/post-processing                                   vitok/pp/ops.py, vitok/pp/io.py
+ * ---------------------------------------------------------------------------------------------- */
+
+/* patchify + patch_collate_fn for a whole batch.           vitok/pp/ops.py:217-285, vitok/data.py:77-94
+ * images     : packed image buffer; img_table [B,3] int64 = {element offset, H, W} per image.
+ * in_dtype   : 0 = float32 CHW already normalised; 1 = uint8 HWC (fuses to_tensor|normalize(minus_one_to_one),
+ *              vitok/pp/ops.py:140-155).
+ * out_dtype  : 0 = float32 (what the reference returns), 1 = bfloat16.
+ * outputs    : patches [B,T,3p^2], patch_mask [B,T] (bool bytes), row/col/time_idx [B,T] int64,
+ *              meta [4,B] int64 = orig_height, orig_width, grid_rows, grid_cols.
+ * status     : optional device int, set to 1 if an image's grid exceeds max_tokens (the reference raises at :260). */
+int vtk_patchify(const void* images, const int64_t* img_table, int in_dtype, int B, int patch, int max_tokens,
+                 int out_dtype, void* patches, uint8_t* patch_mask, int64_t* row_idx, int64_t* col_idx,
+                 int64_t* time_idx, int64_t* meta, int* status, void* stream);
+
+/* max(row)+1, max(col)+1 over valid tokens -> out2[2] (device).        vitok/pp/ops.py:319-321 */
+int vtk_grid_extent(const uint8_t* patch_mask, const int64_t* row_idx, const int64_t* col_idx, int B, int N, int* out2,
+                    void* stream);
+
+/* unpatchify (+ optional fused _convert_format).          vitok/pp/ops.py:295-335, vitok/pp/io.py:91-121
+ * dtype      : 0 = float32, 1 = bfloat16 (patches and, unless out_format==1, the canvas).
+ * cell_map   : workspace, B*gy*gx int32.
+ * out        : [B,3,gy*p,gx*p].  out_format 0 = as is; 1 = uint8 "0_255"; 2 = "zero_to_one" (input is minus_one_to_one).
+ * status     : optional device int, set to 1 if a valid token lies outside the canvas (reference: index error). */
+int vtk_unpatchify(const void* patches, int dtype, const uint8_t* patch_mask, const int64_t* row_idx,
+                   const int64_t* col_idx, int B, int N, int patch, int gy, int gx, int* cell_map, void* out,
+                   int out_format, int* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernel-level entry points (used by the parity tests and by vtk_ae_* internally)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* y = bf16(rms(x) * w), fp32 math, eps inside the rsqrt.                 vitok/models/modules/norm.py:17-25 */
+int vtk_rmsnorm_bf16(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int M, int D, float eps,
+                     void* stream);
+
+/* table [M,d] bf16 = cos | sin of the 2-D RoPE angles.     vitok/models/modules/rotary_embedding.py:46-75,118-119
+ * inv_freq [d/4] float32 (device). */
+int vtk_rope_table(const int64_t* row_idx, const int64_t* col_idx, const float* inv_freq, void* table, int M, int d,
+                   void* stream);
+
+int vtk_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+int vtk_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream);
+
+/* kv_len[b] = 1 + last valid index, is_prefix[b] = mask is contiguous from 0.   vitok/models/ae.py:173-187 */
+int vtk_kv_len(const uint8_t* patch_mask, int* kv_len, int* is_prefix, int B, int N, void* stream);
+
+/* out = bf16(A W^T + bias); bias may be null.                      nn.Linear: vitok/models/ae.py:191,220,242 */
+int vtk_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                    int M, int N, int K, void* stream);
+
+/* out = LayerNorm_noaffine(bf16(A W^T + bias)), N = channels_per_token <= 256.   vitok/models/ae.py:207 */
+int vtk_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                       int M, int N, int K, float eps, void* stream);
+
+/* Fused first half of Block.forward after norm1 (vitok/models/ae.py:61-63):
+ *   qkv_proj -> norm_q/norm_k -> 2-D RoPE (modules/attention.py:95-107) and fc1 -> silu(g)*v (modules/mlp.py:21-22).
+ * Wp [w_rows, K=D] is the packed weight [Wq; Wk; Wv; 0-pad to qp; interleave16(W1_v, W1_g)]; qp = 3D rounded up to 256.
+ * qkv [M,3D] receives roped q, roped k, v; act [M,Hf] receives silu(g)*v. */
+int vtk_qkv_swiglu_bf16(const void* h, int64_t ldh, const void* Wp, int64_t ldw, int64_t w_rows, int M, int D, int d,
+                        int Hf, int qp, const void* norm_q, const void* norm_k, const void* rope_table, float eps,
+                        void* qkv, int64_t ld_qkv, void* act, int64_t ld_act, void* stream);
+
+/* Fused second half: x = bf16(x + bf16(bf16(A W^T) * gamma)) with A = [attn | act], W = [Wout | Wfc2]
+ * (modules/attention.py:129, modules/mlp.py:22, modules/layerscale.py:23, vitok/models/ae.py:64-65). */
+int vtk_proj_residual_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* gamma, void* x,
+                           int64_t ldx, int M, int N, int K, void* stream);
+
+/* softmax(q k^T / sqrt(d)) v per (image, head); q,k,v,out rows = tokens, heads along columns.
+ * kv_len/key_mask/is_prefix null = no masking (reference flash backend, modules/attention.py:109-117);
+ * otherwise the sdpa backend's key masking (modules/attention.py:118-127). */
+int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
+                       const int* kv_len, const uint8_t* key_mask, const int* is_prefix, int B, int N, int heads, int d,
+                       int zero_invalid_rows, void* stream);
+
+/* test-only: D[128,N] fp32 = A[128,K] * op(B) through one tcgen05 tile with explicit descriptor fields */
+int vtk_umma_probe(const void* A, const void* B, float* D, int N, int K, int b_mn_major, uint32_t lbo_bytes,
+                   uint32_t sbo_bytes, uint32_t kstep_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-model entry points                                       vitok/models/ae.py:68-251 (class AE)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vtk_ae_s* vtk_ae_t;
+
+typedef struct {
+  int32_t pixels_per_token, channels_per_token;
+  int32_t enc_width, enc_depth, enc_heads, enc_hidden; /* hidden = SwiGLU Hf; depth 0 = side absent */
+  int32_t dec_width, dec_depth, dec_heads, dec_hidden;
+  float norm_eps;                                       /* 1e-6 */
+} vtk_ae_config;
+
+typedef struct {
+  const void* w_in;   /* packed [qp + 2*Hf, D]: see vtk_qkv_swiglu_bf16 */
+  const void* w_out;  /* packed [D, D + Hf] = [out_proj | fc2] */
+  const void* norm1;  /* [D] */
+  const void* norm_q; /* [d] */
+  const void* norm_k; /* [d] */
+  const void* gamma;  /* [D] (ones when use_layer_scale=False) */
+} vtk_block_weights;
+
+/* The handle stores pointers only (weights stay owned by the caller) plus a small device table of RoPE
+ * inverse frequencies it allocates itself. */
+int vtk_ae_create(const vtk_ae_config* cfg, vtk_ae_t* out);
+int vtk_ae_destroy(vtk_ae_t h);
+/* side 0 = encoder (w_a = patch_embed, w_b = to_code), 1 = decoder (w_a = decoder_embed, w_b = to_pixels) */
+int vtk_ae_set_weights(vtk_ae_t h, int side, const void* w_a, const void* b_a, const void* w_b, const void* b_b,
+                       const vtk_block_weights* blocks, int nblocks, const float* inv_freq_host, int n_inv_freq);
+size_t vtk_ae_workspace_bytes(vtk_ae_t h, int side, int B, int N);
+/* AE.encode (vitok/models/ae.py:189-216): patches [B,N,P] bf16 -> z [B,N,C] bf16.  patch_mask null = flash semantics. */
+int vtk_ae_encode(vtk_ae_t h, const void* patches, const int64_t* row_idx, const int64_t* col_idx,
+                  const uint8_t* patch_mask, int B, int N, void* z_out, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* AE.decode (vitok/models/ae.py:218-243): z [B,N,C] bf16 -> patches [B,N,P] bf16. */
+int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64_t* col_idx, const uint8_t* patch_mask,
+                  int B, int N, void* patches_out, void* workspace, size_t workspace_bytes, void* stream);
+/* number of kernels launched by the last vtk_ae_encode/decode on this handle (for gpu_launches accounting) */
+int vtk_ae_last_launch_count(vtk_ae_t h);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITOK_B200_H_ */

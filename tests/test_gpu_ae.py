@@ -1,0 +1,160 @@
+"""GPU parity: AE.encode / AE.decode (one C-ABI call each) vs the CPU oracle and the reference golden vectors.
+
+Tolerances (calibrated on the reference itself):
+  default init : z max-abs <= 5e-2 and rel-Frobenius <= 1e-2 vs the fp32 oracle; patches likewise;
+                 reconstruction PSNR delta <= 0.05 dB.
+  stress init  : our error vs fp32 <= 2x the reference-bf16's own error vs fp32 (stored in the fixture).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _util import report
+from oracle import ae_oracle, pp_oracle
+from oracle.make_golden import SMALL
+from oracle.weights import make_state_dict, state_dict_shapes, synth_images
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(sizes, patch, T, seed):
+    b = pp_oracle.collate([pp_oracle.patchify(i, patch, T) for i in synth_images(sizes, seed=seed)])
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in b.items()}
+
+
+def _model(variant, sd, backend):
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(variant)
+    m = vb.AE(**cfg, attn_backend=backend).eval()
+    m.load_state_dict(sd, strict=True)
+    return m.to(device="cuda", dtype=torch.bfloat16), cfg
+
+
+def _to_cuda(batch, dtype=torch.bfloat16):
+    return {k: (v.cuda().to(dtype) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+
+
+@pytest.mark.parametrize("init", ["default", "stress"])
+@pytest.mark.parametrize("backend", ["sdpa", "flash"])
+def test_small_variant_vs_reference_golden(init, backend, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ae_small.npz"))
+    stress = init == "stress"
+    cfg0 = ae_oracle.decode_variant(SMALL)
+    sd = make_state_dict(cfg0, seed=1 if stress else 0, stress=stress)
+    model, cfg = _model(SMALL, sd, backend)
+    batch = _batch([(128, 128), (96, 64), (50, 120)], 16, 64, seed=5)
+    with torch.no_grad():
+        enc = model.encode(_to_cuda(batch))
+        dec = model.decode(enc)
+    valid = batch["patch_mask"] if backend == "sdpa" else torch.ones_like(batch["patch_mask"])
+    z_ref = torch.from_numpy(g[f"{init}_{backend}_z"])
+    p_ref = torch.from_numpy(g[f"{init}_{backend}_patches"])
+    # the reference-bf16's own error on this case, from the bf16-mode oracle
+    sdb = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    bb = {k: (v.to(torch.bfloat16) if v.dtype == torch.float32 else v) for k, v in batch.items()}
+    e_b = ae_oracle.encode(sdb, bb, cfg["encoder_heads"], attn_backend=backend)
+    d_b = ae_oracle.decode(sdb, e_b, cfg["decoder_heads"], attn_backend=backend)
+    own_z = (e_b["z"].float() - z_ref)[valid].abs().max().item()
+    own_p = (d_b["patches"].float() - p_ref)[valid].abs().max().item()
+    ma_z, _ = report(f"small {init}/{backend} z", enc["z"].cpu().float()[valid], z_ref[valid])
+    ma_p, _ = report(f"small {init}/{backend} patches", dec["patches"].cpu().float()[valid], p_ref[valid])
+    print(f"[parity] reference-bf16 own error: z {own_z:.3e} patches {own_p:.3e}")
+    assert ma_z <= max(2 * own_z, 5e-2) and ma_p <= max(2 * own_p, 5e-2)
+    # dict contract (ae.py:209-216, 236-243)
+    cb = _to_cuda(batch)
+    e2 = model.encode(cb)
+    assert e2["row_idx"] is cb["row_idx"] and e2["patch_mask"] is cb["patch_mask"] and "patches" not in e2
+    d2 = model.decode(e2)
+    assert d2["col_idx"] is cb["col_idx"] and "z" not in d2 and d2["patches"].shape == cb["patches"].shape
+
+
+@pytest.mark.parametrize("init", ["default", "stress"])
+def test_c1_350M_vs_oracle(init, golden_dir):
+    """BASELINE.json configs[0]/[1] model (350M-f16x64) on 4 x 256x256: bf16 GPU vs fp32 CPU oracle."""
+    g = np.load(os.path.join(golden_dir, "ae_c1.npz"))
+    stress = init == "stress"
+    variant = "Ld4-Ld24/1x16x64"
+    cfg0 = ae_oracle.decode_variant(variant)
+    sd = make_state_dict(cfg0, seed=1 if stress else 0, stress=stress)
+    model, cfg = _model(variant, sd, "sdpa")
+    batch = _batch([(256, 256)] * 4, 16, 256, seed=1234)
+    with torch.no_grad():
+        enc = model.encode(_to_cuda(batch))
+        dec = model.decode(enc)
+    z = enc["z"].cpu().float()
+    p = dec["patches"].cpu().float()
+    z_ref = torch.from_numpy(g[f"{init}_z"])
+    ma_z, rf_z = report(f"c1 {init} z vs reference fp32 golden", z, z_ref)
+    ma_ps, rf_ps = report(f"c1 {init} patches(sub) vs golden", p[:, ::4, ::16], torch.from_numpy(g[f"{init}_patches_sub"]))
+    own = {k: float(g[f"{init}_bf16_{k}"]) for k in ("z_maxabs", "z_relfro", "p_maxabs", "p_relfro")}
+    print(f"[parity] reference-bf16 own error vs fp32: {own}")
+    if stress:
+        assert ma_z <= 2 * own["z_maxabs"] and rf_z <= 2 * own["z_relfro"]
+        assert ma_ps <= 2 * own["p_maxabs"] and rf_ps <= 2 * own["p_relfro"]
+    else:
+        assert ma_z <= 5e-2 and rf_z <= 1e-2
+        assert ma_ps <= 5e-2 and rf_ps <= 1e-2
+    # full oracle run for the PSNR criterion (<= 0.05 dB delta on the reconstruction)
+    torch.set_num_threads(os.cpu_count() or 1)
+    e_o = ae_oracle.encode(sd, batch, cfg["encoder_heads"])
+    d_o = ae_oracle.decode(sd, e_o, cfg["decoder_heads"])
+    tgt = batch["patches"]
+    psnr_ref = ae_oracle.psnr(d_o["patches"], tgt)
+    psnr_ours = ae_oracle.psnr(p, tgt)
+    print(f"[parity] PSNR(recon, input): oracle {psnr_ref:.4f} dB, ours {psnr_ours:.4f} dB, delta {abs(psnr_ref - psnr_ours):.5f}")
+    assert abs(psnr_ref - psnr_ours) <= 0.05
+    assert abs(z.mean(-1)).max() < 2e-2 and abs(z.var(-1, unbiased=False) - 1).max() < 5e-2   # LN bottleneck property
+
+
+def test_state_dict_contract_and_halves():
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(SMALL)
+    m = vb.AE(**cfg)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in state_dict_shapes(cfg)]
+    sd = make_state_dict(cfg, seed=0)
+    enc_only = vb.AE(**cfg, encoder=True, decoder=False, attn_backend="sdpa").eval()
+    dec_only = vb.AE(**cfg, encoder=False, decoder=True, attn_backend="sdpa").eval()
+    enc_only.load_state_dict({k: v for k, v in sd.items() if k in enc_only.state_dict()}, strict=True)
+    dec_only.load_state_dict({k: v for k, v in sd.items() if k in dec_only.state_dict()}, strict=True)
+    full, _ = _model(SMALL, sd, "sdpa")
+    enc_only, dec_only = enc_only.to("cuda", torch.bfloat16), dec_only.to("cuda", torch.bfloat16)
+    batch = _to_cuda(_batch([(128, 128), (64, 96)], 16, 64, seed=9))
+    with torch.no_grad():
+        a = full(batch)
+        b = dec_only.decode(enc_only.encode(batch))
+    assert torch.equal(a["patches"], b["patches"])
+    # weights are re-packed after load_state_dict
+    sd2 = make_state_dict(cfg, seed=3)
+    full.load_state_dict({k: v.to(torch.bfloat16) for k, v in sd2.items()})
+    with torch.no_grad():
+        c = full(batch)
+    assert not torch.equal(a["patches"], c["patches"])
+    # fp32 patches are accepted (cast in-kernel), same result as bf16-cast input
+    fb = dict(batch)
+    fb["patches"] = batch["patches"].float()
+    with torch.no_grad():
+        assert torch.equal(full(fb)["patches"], c["patches"])
+    with pytest.raises(NotImplementedError):
+        full.quantize()
+    with pytest.raises(KeyError):
+        full.encode({"patches": batch["patches"]})
+
+
+def test_preprocess_encode_decode_postprocess_pipeline():
+    """README-style user flow on PIL images (reference README.md:62-65)."""
+    from PIL import Image
+    import vitok_b200 as vb
+    rng = np.random.default_rng(1)
+    imgs = [Image.fromarray(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)) for h, w in [(256, 256), (200, 120)]]
+    cfg = vb.decode_variant(SMALL)
+    model = vb.AE(**cfg, attn_backend="sdpa").eval().to("cuda", torch.bfloat16)
+    d = vb.preprocess(imgs, pp="to_tensor|normalize(minus_one_to_one)|patchify(16, 256)", device="cuda")
+    assert d["patches"].dtype == torch.float32 and d["patches"].shape == (2, 256, 768)
+    want = pp_oracle.collate([pp_oracle.patchify(pp_oracle.normalize_u8(np.asarray(i)), 16, 256) for i in imgs])
+    assert np.array_equal(d["patches"].cpu().numpy(), want["patches"])
+    with torch.no_grad():
+        out = model.decode(model.encode(d))
+    recon = vb.postprocess(out, output_format="0_255", do_unpack=True, patch=16)
+    assert [tuple(r.shape) for r in recon] == [(3, 256, 256), (3, 200, 120)] and recon[0].dtype == torch.uint8

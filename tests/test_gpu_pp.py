@@ -1,0 +1,97 @@
+"""GPU parity (bit-exact): patchify / unpatchify / index packing / format conversion vs oracle + golden."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pp_oracle
+from oracle.make_golden import PP_CASES
+from oracle.weights import C3_SIZES, synth_images
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ppmeta(golden_dir):
+    with open(os.path.join(golden_dir, "pp.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("ci", range(len(PP_CASES)))
+def test_patchify_matches_reference_golden(ci, ppmeta):
+    import vitok_b200 as vb
+    H, W, p, T = PP_CASES[ci]
+    m = ppmeta[f"case{ci}"]
+    img = synth_images([(H, W)], seed=100 + ci)[0]
+    d = vb.patchify_batch([torch.from_numpy(img)], p, T)
+    for k in ("patches", "patch_mask", "row_idx", "col_idx", "time_idx", "orig_height", "orig_width", "grid_rows", "grid_cols"):
+        assert sha(d[k][0].cpu().numpy()) == m[k], (ci, k)
+    canvas = vb.unpatchify(d, patch=p)
+    assert list(canvas.shape) == m["unpatchify_shape"]
+    assert sha(canvas.cpu().numpy()) == m["unpatchify_sha"]
+    assert sha(vb.postprocess(d, output_format="0_255", do_unpack=False, patch=p).cpu().numpy()) == m["u8_sha"]
+    assert sha(vb.postprocess(d, output_format="zero_to_one", do_unpack=False, patch=p).cpu().numpy()) == m["zero_to_one_sha"]
+    assert np.array_equal(canvas[0, :, :H, :W].cpu().numpy(), img)          # round trip
+    # per-image OPS entry point (DSL "patchify(p, T)")
+    d1 = vb.OPS["patchify"](p, T)(torch.from_numpy(img))
+    assert sha(d1["patches"].cpu().numpy()) == m["patches"] and d1["orig_height"].item() == H
+
+
+def test_ragged_batch_matches_reference_golden(ppmeta):
+    import vitok_b200 as vb
+    m = ppmeta["ragged"]
+    imgs = [torch.from_numpy(i) for i in synth_images(C3_SIZES[:6], seed=77)]
+    batch = vb.patchify_batch(imgs, 16, 1024)
+    for k, v in batch.items():
+        assert sha(v.cpu().numpy()) == m[k + "_sha"], k
+    canvas = vb.unpatchify(batch, 16)
+    assert list(canvas.shape) == m["canvas_shape"] and sha(canvas.cpu().numpy()) == m["canvas_sha"]
+    assert sha(vb.unpatchify(batch, 16, max_grid_size=32).cpu().numpy()) == m["canvas32_sha"]
+    crops = vb.postprocess(batch, output_format="0_255", do_unpack=True, patch=16)
+    assert [list(c.shape) for c in crops] == m["crops_shape"]
+    assert [sha(c.contiguous().cpu().numpy()) for c in crops] == m["crops_sha"]
+
+
+def test_uint8_fused_frontend_bit_exact():
+    """N1: uint8 HWC -> to_tensor|normalize|patchify in one kernel == oracle on the same pixels."""
+    import vitok_b200 as vb
+    rng = np.random.default_rng(0)
+    sizes = [(256, 256), (130, 131), (37, 300)]
+    u8 = [rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8) for h, w in sizes]
+    got = vb.patchify_batch(u8, 16, 512)
+    want = pp_oracle.collate([pp_oracle.patchify(pp_oracle.normalize_u8(a), 16, 512) for a in u8])
+    for k in want:
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+
+
+def test_full_size_roundtrip_and_bf16():
+    """BASELINE config sizes: 64 x 256^2 (c2) and 8 x 512^2 (c4): patchify -> unpatchify is the identity."""
+    import vitok_b200 as vb
+    for B, S, T in [(64, 256, 256), (8, 512, 1024)]:
+        g = torch.Generator().manual_seed(7)
+        imgs = (torch.rand(B, 3, S, S, generator=g) * 2 - 1).cuda()
+        d = vb.patchify_batch(imgs, 16, T)
+        assert bool(d["patch_mask"].all())
+        assert torch.equal(vb.unpatchify(d, 16), imgs)
+        db = vb.patchify_batch(imgs, 16, T, out_dtype=torch.bfloat16)
+        assert torch.equal(db["patches"], d["patches"].to(torch.bfloat16))
+        assert torch.equal(vb.unpatchify(db, 16), imgs.to(torch.bfloat16))
+
+
+def test_errors():
+    import vitok_b200 as vb
+    with pytest.raises(RuntimeError):
+        vb.patchify_batch([torch.zeros(3, 640, 480)], 16, 256)      # grid exceeds the budget (ops.py:260)
+    d = vb.patchify_batch([torch.zeros(3, 64, 64)], 16, 16)
+    d2 = {k: v for k, v in d.items() if k not in ("orig_height", "orig_width")}
+    with pytest.raises(ValueError):
+        vb.postprocess(d2, do_unpack=True)                           # io.py:84-85
+    with pytest.raises(RuntimeError):
+        vb.unpatchify({k: v.cpu() for k, v in d.items()})            # no CPU path

@@ -1,0 +1,433 @@
+// vtk_api.cu -- the exported C ABI (include/vitok_b200.h): argument checking, error plumbing,
+// tensor-map encoding, and the AE encode/decode layer loops.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/vitok_b200.h"
+#include "vtk_kernels.h"
+
+namespace vtk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return VTK_ERR_CUDA;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms > 0) return sms;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  sms = n;
+  return sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
+                           uint64_t row_stride_elems, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return VTK_ERR_CUDA;
+  cuuint64_t gdim[2] = {inner_elems, rows};
+  cuuint64_t gstride[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) base=%p inner=%llu rows=%llu stride=%llu box_rows=%u", (int)r,
+              base, (unsigned long long)inner_elems, (unsigned long long)rows, (unsigned long long)row_stride_elems, box_rows);
+    return VTK_ERR_CUDA;
+  }
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// AE handle
+// -------------------------------------------------------------------------------------------------
+struct Side {
+  int width = 0, depth = 0, heads = 0, hidden = 0;
+  const bf16 *w_a = nullptr, *b_a = nullptr, *w_b = nullptr, *b_b = nullptr;
+  std::vector<vtk_block_weights> blocks;
+  float* inv_freq = nullptr;  // device, d/4 floats
+  int head_dim() const { return heads ? width / heads : 0; }
+  int qp() const { return ((3 * width + 255) / 256) * 256; }
+};
+
+struct Workspace {
+  bf16 *x, *h, *qkv, *a2, *rope;
+  int *kv_len, *is_prefix;
+  size_t bytes;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static Workspace carve(const Side& s, void* base, long long M, int B) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += align_up(nbytes, 1024);
+    return p;
+  };
+  const long long D = s.width, Hf = s.hidden, d = s.head_dim();
+  w.x = static_cast<bf16*>(take((size_t)M * D * 2));
+  w.h = static_cast<bf16*>(take((size_t)M * D * 2));
+  w.qkv = static_cast<bf16*>(take((size_t)M * 3 * D * 2));
+  w.a2 = static_cast<bf16*>(take((size_t)M * (D + Hf) * 2));
+  w.rope = static_cast<bf16*>(take((size_t)M * d * 2));
+  w.kv_len = static_cast<int*>(take((size_t)B * 4));
+  w.is_prefix = static_cast<int*>(take((size_t)B * 4));
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace vtk
+
+struct vtk_ae_s {
+  vtk_ae_config cfg;
+  vtk::Side side[2];
+  int last_launches = 0;
+};
+
+using namespace vtk;
+
+#define VTK_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      set_error(__VA_ARGS__);         \
+      return VTK_ERR_BAD_ARG;         \
+    }                                 \
+  } while (0)
+
+extern "C" {
+
+const char* vtk_last_error(void) { return g_err; }
+int vtk_abi_version(void) { return VTK_ABI_VERSION; }
+int vtk_sm_count(void) { return num_sms(); }
+
+int vtk_patchify(const void* images, const int64_t* img_table, int in_dtype, int B, int patch, int max_tokens,
+                 int out_dtype, void* patches, uint8_t* patch_mask, int64_t* row_idx, int64_t* col_idx,
+                 int64_t* time_idx, int64_t* meta, int* status, void* stream) {
+  VTK_REQUIRE(images && img_table && patches && patch_mask && row_idx && col_idx && time_idx && meta,
+              "vtk_patchify: null pointer");
+  VTK_REQUIRE(in_dtype == 0 || in_dtype == 1, "vtk_patchify: in_dtype must be 0 (f32 CHW) or 1 (u8 HWC)");
+  VTK_REQUIRE(out_dtype == 0 || out_dtype == 1, "vtk_patchify: out_dtype must be 0 (f32) or 1 (bf16)");
+  VTK_REQUIRE(B >= 0 && max_tokens >= 0, "vtk_patchify: negative size");
+  PatchifyArgs a;
+  a.images = images; a.img_table = img_table; a.in_dtype = in_dtype; a.B = B; a.patch = patch; a.max_tokens = max_tokens;
+  a.out_dtype = out_dtype; a.patches = patches; a.patch_mask = patch_mask; a.row_idx = row_idx; a.col_idx = col_idx;
+  a.time_idx = time_idx; a.meta = meta; a.status = status;
+  return launch_patchify(a, (cudaStream_t)stream);
+}
+
+int vtk_grid_extent(const uint8_t* patch_mask, const int64_t* row_idx, const int64_t* col_idx, int B, int N, int* out2,
+                    void* stream) {
+  VTK_REQUIRE(patch_mask && row_idx && col_idx && out2, "vtk_grid_extent: null pointer");
+  return launch_grid_extent(patch_mask, row_idx, col_idx, B, N, out2, (cudaStream_t)stream);
+}
+
+int vtk_unpatchify(const void* patches, int dtype, const uint8_t* patch_mask, const int64_t* row_idx,
+                   const int64_t* col_idx, int B, int N, int patch, int gy, int gx, int* cell_map, void* out,
+                   int out_format, int* status, void* stream) {
+  VTK_REQUIRE(patches && patch_mask && row_idx && col_idx && cell_map && out, "vtk_unpatchify: null pointer");
+  VTK_REQUIRE(dtype == 0 || dtype == 1, "vtk_unpatchify: dtype must be 0 (f32) or 1 (bf16)");
+  VTK_REQUIRE(out_format >= 0 && out_format <= 2, "vtk_unpatchify: out_format must be 0, 1 or 2");
+  UnpatchifyArgs a;
+  a.patches = patches; a.dtype = dtype; a.patch_mask = patch_mask; a.row_idx = row_idx; a.col_idx = col_idx;
+  a.B = B; a.N = N; a.patch = patch; a.gy = gy; a.gx = gx; a.cell_map = cell_map; a.out = out; a.out_format = out_format;
+  a.status = status;
+  return launch_unpatchify(a, (cudaStream_t)stream);
+}
+
+int vtk_rmsnorm_bf16(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int M, int D, float eps,
+                     void* stream) {
+  VTK_REQUIRE(x && w && y, "vtk_rmsnorm_bf16: null pointer");
+  return launch_rmsnorm((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, M, D, eps, (cudaStream_t)stream);
+}
+
+int vtk_rope_table(const int64_t* row_idx, const int64_t* col_idx, const float* inv_freq, void* table, int M, int d,
+                   void* stream) {
+  VTK_REQUIRE(row_idx && col_idx && inv_freq && table, "vtk_rope_table: null pointer");
+  return launch_rope_table(row_idx, col_idx, inv_freq, (bf16*)table, M, d, (cudaStream_t)stream);
+}
+
+int vtk_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
+  VTK_REQUIRE(in && out, "vtk_cast_f32_to_bf16: null pointer");
+  return launch_cast_f32_bf16(in, (bf16*)out, n, (cudaStream_t)stream);
+}
+int vtk_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream) {
+  VTK_REQUIRE(in && out, "vtk_cast_bf16_to_f32: null pointer");
+  return launch_cast_bf16_f32((const bf16*)in, out, n, (cudaStream_t)stream);
+}
+
+int vtk_kv_len(const uint8_t* patch_mask, int* kv_len, int* is_prefix, int B, int N, void* stream) {
+  VTK_REQUIRE(patch_mask && kv_len, "vtk_kv_len: null pointer");
+  return launch_kv_len(patch_mask, kv_len, is_prefix, B, N, (cudaStream_t)stream);
+}
+
+static GemmArgs base_args(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t w_rows, int M, int N, int K) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = (const bf16*)A; g.lda = lda; g.B = (const bf16*)W; g.ldb = ldw; g.b_rows = w_rows; g.M = M; g.N = N; g.K = K;
+  g.epi.eps = 1e-6f;
+  return g;
+}
+
+int vtk_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                    int M, int N, int K, void* stream) {
+  VTK_REQUIRE(A && W && out, "vtk_linear_bf16: null pointer");
+  VTK_REQUIRE(ldo % 8 == 0, "vtk_linear_bf16: ldo must be a multiple of 8");
+  GemmArgs g = base_args(A, lda, W, ldw, N, M, N, K);
+  g.epi.out = (bf16*)out; g.epi.ldo = ldo; g.epi.bias = (const bf16*)bias;
+  return launch_gemm(EPI_BIAS, g, (cudaStream_t)stream);
+}
+
+int vtk_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                       int M, int N, int K, float eps, void* stream) {
+  VTK_REQUIRE(A && W && out && bias, "vtk_linear_ln_bf16: null pointer");
+  VTK_REQUIRE(ldo % 8 == 0, "vtk_linear_ln_bf16: ldo must be a multiple of 8");
+  GemmArgs g = base_args(A, lda, W, ldw, N, M, N, K);
+  g.epi.out = (bf16*)out; g.epi.ldo = ldo; g.epi.bias = (const bf16*)bias; g.epi.eps = eps;
+  return launch_gemm(EPI_BIAS_LN, g, (cudaStream_t)stream);
+}
+
+int vtk_qkv_swiglu_bf16(const void* h, int64_t ldh, const void* Wp, int64_t ldw, int64_t w_rows, int M, int D, int d,
+                        int Hf, int qp, const void* norm_q, const void* norm_k, const void* rope_table, float eps,
+                        void* qkv, int64_t ld_qkv, void* act, int64_t ld_act, void* stream) {
+  VTK_REQUIRE(h && Wp && norm_q && norm_k && rope_table && qkv && act, "vtk_qkv_swiglu_bf16: null pointer");
+  VTK_REQUIRE(qp >= 3 * D && w_rows == (int64_t)qp + 2 * Hf, "vtk_qkv_swiglu_bf16: packed weight must have qp + 2*Hf rows");
+  VTK_REQUIRE(ld_qkv % 8 == 0 && ld_act % 8 == 0, "vtk_qkv_swiglu_bf16: output strides must be multiples of 8");
+  GemmArgs g = base_args(h, ldh, Wp, ldw, w_rows, M, qp + 2 * Hf, D);
+  g.epi.qkv = (bf16*)qkv; g.epi.ld_qkv = ld_qkv; g.epi.act = (bf16*)act; g.epi.ld_act = ld_act;
+  g.epi.normq = (const bf16*)norm_q; g.epi.normk = (const bf16*)norm_k; g.epi.rope = (const bf16*)rope_table;
+  g.epi.D = D; g.epi.d = d; g.epi.Hf = Hf; g.epi.qp = qp; g.epi.eps = eps;
+  return launch_gemm(EPI_QKV_SWIGLU, g, (cudaStream_t)stream);
+}
+
+int vtk_proj_residual_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* gamma, void* x,
+                           int64_t ldx, int M, int N, int K, void* stream) {
+  VTK_REQUIRE(A && W && gamma && x, "vtk_proj_residual_bf16: null pointer");
+  VTK_REQUIRE(ldx % 8 == 0, "vtk_proj_residual_bf16: ldx must be a multiple of 8");
+  GemmArgs g = base_args(A, lda, W, ldw, N, M, N, K);
+  g.epi.out = (bf16*)x; g.epi.ldo = ldx; g.epi.gamma = (const bf16*)gamma;
+  return launch_gemm(EPI_RESID, g, (cudaStream_t)stream);
+}
+
+int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
+                       const int* kv_len, const uint8_t* key_mask, const int* is_prefix, int B, int N, int heads, int d,
+                       int zero_invalid_rows, void* stream) {
+  VTK_REQUIRE(q && k && v && out, "vtk_attention_bf16: null pointer");
+  AttnArgs a;
+  a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.ld_qkv = ld_qkv; a.out = (bf16*)out; a.ld_out = ld_out;
+  a.kv_len = kv_len; a.key_mask = key_mask; a.prefix_flag = is_prefix; a.B = B; a.N = N; a.heads = heads; a.d = d;
+  a.zero_invalid_rows = zero_invalid_rows;
+  return launch_attention(a, (cudaStream_t)stream);
+}
+
+int vtk_umma_probe(const void* A, const void* B, float* D, int N, int K, int b_mn_major, uint32_t lbo_bytes,
+                   uint32_t sbo_bytes, uint32_t kstep_bytes, void* stream) {
+  VTK_REQUIRE(A && B && D, "vtk_umma_probe: null pointer");
+  return launch_umma_probe((const bf16*)A, (const bf16*)B, D, N, K, b_mn_major, lbo_bytes, sbo_bytes, kstep_bytes,
+                           (cudaStream_t)stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// AE
+// -------------------------------------------------------------------------------------------------
+int vtk_ae_create(const vtk_ae_config* cfg, vtk_ae_t* out) {
+  VTK_REQUIRE(cfg && out, "vtk_ae_create: null pointer");
+  VTK_REQUIRE(cfg->enc_depth > 0 || cfg->dec_depth > 0 || cfg->enc_width > 0 || cfg->dec_width > 0,
+              "At least one of encoder or decoder must be True");
+  vtk_ae_s* h = new vtk_ae_s();
+  h->cfg = *cfg;
+  Side& e = h->side[0];
+  e.width = cfg->enc_width; e.depth = cfg->enc_depth; e.heads = cfg->enc_heads; e.hidden = cfg->enc_hidden;
+  Side& d = h->side[1];
+  d.width = cfg->dec_width; d.depth = cfg->dec_depth; d.heads = cfg->dec_heads; d.hidden = cfg->dec_hidden;
+  for (int s = 0; s < 2; ++s) {
+    Side& sd = h->side[s];
+    if (sd.width <= 0) continue;
+    if (sd.heads <= 0 || sd.width % sd.heads) {
+      set_error("vtk_ae_create: width %d not divisible by heads %d", sd.width, sd.heads);
+      delete h;
+      return VTK_ERR_BAD_ARG;
+    }
+    const int hd = sd.head_dim();
+    if (sd.depth > 0 && !(hd == 64 || hd == 128)) {
+      set_error("vtk_ae_create: head_dim %d unsupported by the sm_100a attention kernel (64 or 128)", hd);
+      delete h;
+      return VTK_ERR_UNSUPPORTED;
+    }
+    if (sd.width % 8 || sd.hidden % 16) {
+      set_error("vtk_ae_create: width must be a multiple of 8 and hidden of 16 (width=%d hidden=%d)", sd.width, sd.hidden);
+      delete h;
+      return VTK_ERR_BAD_ARG;
+    }
+  }
+  *out = h;
+  return VTK_OK;
+}
+
+int vtk_ae_destroy(vtk_ae_t h) {
+  if (!h) return VTK_OK;
+  for (int s = 0; s < 2; ++s)
+    if (h->side[s].inv_freq) cudaFree(h->side[s].inv_freq);
+  delete h;
+  return VTK_OK;
+}
+
+int vtk_ae_set_weights(vtk_ae_t h, int side, const void* w_a, const void* b_a, const void* w_b, const void* b_b,
+                       const vtk_block_weights* blocks, int nblocks, const float* inv_freq_host, int n_inv_freq) {
+  VTK_REQUIRE(h && (side == 0 || side == 1), "vtk_ae_set_weights: bad handle/side");
+  Side& s = h->side[side];
+  VTK_REQUIRE(s.width > 0, "vtk_ae_set_weights: side %d is absent from this model", side);
+  VTK_REQUIRE(w_a && b_a && w_b && b_b, "vtk_ae_set_weights: null projection weights");
+  VTK_REQUIRE(nblocks == s.depth, "vtk_ae_set_weights: expected %d blocks, got %d", s.depth, nblocks);
+  VTK_REQUIRE(nblocks == 0 || blocks, "vtk_ae_set_weights: null blocks");
+  VTK_REQUIRE(n_inv_freq == s.head_dim() / 4 && inv_freq_host, "vtk_ae_set_weights: inv_freq must have head_dim/4 entries");
+  s.w_a = (const bf16*)w_a; s.b_a = (const bf16*)b_a; s.w_b = (const bf16*)w_b; s.b_b = (const bf16*)b_b;
+  s.blocks.assign(blocks, blocks + nblocks);
+  for (int i = 0; i < nblocks; ++i) {
+    const vtk_block_weights& b = s.blocks[i];
+    VTK_REQUIRE(b.w_in && b.w_out && b.norm1 && b.norm_q && b.norm_k && b.gamma, "vtk_ae_set_weights: null pointer in block %d", i);
+  }
+  if (!s.inv_freq) {
+    int r = check_cuda(cudaMalloc(&s.inv_freq, sizeof(float) * n_inv_freq), "cudaMalloc(inv_freq)");
+    if (r) return r;
+  }
+  return check_cuda(cudaMemcpy(s.inv_freq, inv_freq_host, sizeof(float) * n_inv_freq, cudaMemcpyHostToDevice), "cudaMemcpy(inv_freq)");
+}
+
+size_t vtk_ae_workspace_bytes(vtk_ae_t h, int side, int B, int N) {
+  if (!h || side < 0 || side > 1 || B <= 0 || N <= 0) return 0;
+  return carve(h->side[side], nullptr, (long long)B * N, B).bytes;
+}
+
+static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int64_t* row_idx, const int64_t* col_idx,
+                      const uint8_t* patch_mask, int B, int N, cudaStream_t st, int& launches) {
+  const int M = B * N, D = s.width, d = s.head_dim(), Hf = s.hidden, qp = s.qp();
+  const float eps = h->cfg.norm_eps;
+  int r;
+  if (s.depth > 0) {
+    if ((r = launch_rope_table(row_idx, col_idx, s.inv_freq, w.rope, M, d, st))) return r;
+    ++launches;
+    if (patch_mask) {
+      if ((r = launch_kv_len(patch_mask, w.kv_len, w.is_prefix, B, N, st))) return r;
+      ++launches;
+    }
+  }
+  for (int i = 0; i < s.depth; ++i) {
+    const vtk_block_weights& b = s.blocks[i];
+    if ((r = launch_rmsnorm(w.x, D, (const bf16*)b.norm1, w.h, D, M, D, eps, st))) return r;
+    GemmArgs g1 = base_args(w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
+    g1.epi.qkv = w.qkv; g1.epi.ld_qkv = 3 * D; g1.epi.act = w.a2 + D; g1.epi.ld_act = D + Hf;
+    g1.epi.normq = (const bf16*)b.norm_q; g1.epi.normk = (const bf16*)b.norm_k; g1.epi.rope = w.rope;
+    g1.epi.D = D; g1.epi.d = d; g1.epi.Hf = Hf; g1.epi.qp = qp; g1.epi.eps = eps;
+    if ((r = launch_gemm(EPI_QKV_SWIGLU, g1, st))) return r;
+    AttnArgs a;
+    a.q = w.qkv; a.k = w.qkv + D; a.v = w.qkv + 2 * D; a.ld_qkv = 3 * D; a.out = w.a2; a.ld_out = D + Hf;
+    a.kv_len = patch_mask ? w.kv_len : nullptr; a.key_mask = patch_mask; a.prefix_flag = patch_mask ? w.is_prefix : nullptr;
+    a.B = B; a.N = N; a.heads = s.heads; a.d = d; a.zero_invalid_rows = patch_mask ? 1 : 0;
+    if ((r = launch_attention(a, st))) return r;
+    GemmArgs g2 = base_args(w.a2, D + Hf, b.w_out, D + Hf, D, M, D, D + Hf);
+    g2.epi.out = w.x; g2.epi.ldo = D; g2.epi.gamma = (const bf16*)b.gamma;
+    if ((r = launch_gemm(EPI_RESID, g2, st))) return r;
+    launches += 4;
+  }
+  return 0;
+}
+
+static int check_io(vtk_ae_t h, int side, const void* in, const int64_t* row_idx, const int64_t* col_idx, int B, int N,
+                    void* out, void* workspace, size_t workspace_bytes, const char* fn) {
+  VTK_REQUIRE(h, "%s: null handle", fn);
+  const Side& s = h->side[side];
+  VTK_REQUIRE(s.width > 0 && s.w_a, "%s: this model has no %s weights set", fn, side ? "decoder" : "encoder");
+  VTK_REQUIRE(in && row_idx && col_idx && out && workspace, "%s: null pointer", fn);
+  VTK_REQUIRE(B > 0 && N > 0, "%s: empty batch (B=%d N=%d)", fn, B, N);
+  VTK_REQUIRE((long long)B * N < (1ll << 31), "%s: B*N too large", fn);
+  VTK_REQUIRE(workspace_bytes >= vtk_ae_workspace_bytes(h, side, B, N), "%s: workspace too small (%zu < %zu)", fn,
+              workspace_bytes, vtk_ae_workspace_bytes(h, side, B, N));
+  VTK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "%s: workspace must be 1024-byte aligned", fn);
+  return 0;
+}
+
+int vtk_ae_encode(vtk_ae_t h, const void* patches, const int64_t* row_idx, const int64_t* col_idx,
+                  const uint8_t* patch_mask, int B, int N, void* z_out, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  int r = check_io(h, 0, patches, row_idx, col_idx, B, N, z_out, workspace, workspace_bytes, "vtk_ae_encode");
+  if (r) return r;
+  const Side& s = h->side[0];
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = B * N, P = h->cfg.pixels_per_token, C = h->cfg.channels_per_token, D = s.width;
+  Workspace w = carve(s, workspace, M, B);
+  int launches = 0;
+  GemmArgs g = base_args(patches, P, s.w_a, P, D, M, D, P);           // patch_embed, ae.py:191
+  g.epi.out = w.x; g.epi.ldo = D; g.epi.bias = s.b_a;
+  if ((r = launch_gemm(EPI_BIAS, g, st))) return r;
+  ++launches;
+  if ((r = run_blocks(h, s, w, row_idx, col_idx, patch_mask, B, N, st, launches))) return r;
+  GemmArgs gz = base_args(w.x, D, s.w_b, D, C, M, C, D);               // to_code + output_fn, ae.py:207
+  gz.epi.out = (bf16*)z_out; gz.epi.ldo = C; gz.epi.bias = s.b_b; gz.epi.eps = h->cfg.norm_eps;
+  if ((r = launch_gemm(EPI_BIAS_LN, gz, st))) return r;
+  ++launches;
+  h->last_launches = launches;
+  return VTK_OK;
+}
+
+int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64_t* col_idx, const uint8_t* patch_mask,
+                  int B, int N, void* patches_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int r = check_io(h, 1, z, row_idx, col_idx, B, N, patches_out, workspace, workspace_bytes, "vtk_ae_decode");
+  if (r) return r;
+  const Side& s = h->side[1];
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = B * N, P = h->cfg.pixels_per_token, C = h->cfg.channels_per_token, D = s.width;
+  Workspace w = carve(s, workspace, M, B);
+  int launches = 0;
+  GemmArgs g = base_args(z, C, s.w_a, C, D, M, D, C);                  // decoder_embed, ae.py:220
+  g.epi.out = w.x; g.epi.ldo = D; g.epi.bias = s.b_a;
+  if ((r = launch_gemm(EPI_BIAS, g, st))) return r;
+  ++launches;
+  if ((r = run_blocks(h, s, w, row_idx, col_idx, patch_mask, B, N, st, launches))) return r;
+  GemmArgs gp = base_args(w.x, D, s.w_b, D, P, M, P, D);               // to_pixels, ae.py:242
+  gp.epi.out = (bf16*)patches_out; gp.epi.ldo = P; gp.epi.bias = s.b_b;
+  if ((r = launch_gemm(EPI_BIAS, gp, st))) return r;
+  ++launches;
+  h->last_launches = launches;
+  return VTK_OK;
+}
+
+int vtk_ae_last_launch_count(vtk_ae_t h) { return h ? h->last_launches : 0; }
+
+}  // extern "C"

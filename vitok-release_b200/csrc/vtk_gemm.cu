@@ -1,0 +1,580 @@
+// vtk_gemm.cu -- persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   out = epilogue( A[M,K] (bf16, K-major) x B[N,K]^T (bf16, K-major) ), fp32 accumulation in TMEM.
+//
+// Roles (one CTA per SM, 128 + 32*NEPI threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 128B-swizzled boxes into a smem ring
+//   warp 1   : MMA issuer    -- one lane issues tcgen05.mma (128 x {256|128} x 16), commits to mbarriers
+//   warp 2   : TMEM allocator (2 accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warp 3   : idle
+//   warps 4..: epilogue      -- tcgen05.ld (32x32b: one accumulator row per thread), fused math, 16-byte stores
+//
+// Tile scheduler: static persistent, m fastest (concurrent CTAs share the same weight rows in L2).  When the
+// last wave would be less than half full, its tiles are split into half-width tiles (UMMA N = BN/2) so the
+// tail costs half a wave instead of a full one.
+//
+// Fused epilogues replace these reference call sites (/root/reference):
+//   EPI_BIAS        nn.Linear + bias                      vitok/models/ae.py:191,220,242
+//   EPI_BIAS_LN     to_code + LayerNorm(no affine)        vitok/models/ae.py:207, modules/norm.py:28-39
+//   EPI_QKV_SWIGLU  qkv_proj -> norm_q/norm_k -> RoPE     modules/attention.py:95-107, rotary_embedding.py:102-129
+//                   fc1 -> chunk -> silu(g) * v           modules/mlp.py:21-22
+//   EPI_RESID       out_proj + fc2 -> LayerScale -> +x    vitok/models/ae.py:62-65, modules/layerscale.py:23
+#include <stdio.h>
+
+#include "vtk_common.cuh"
+#include "vtk_kernels.h"
+
+namespace vtk {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;                        // 64 bf16 = one 128-byte swizzle atom
+static constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB
+static constexpr int SMEM_BUDGET = 192 * 1024;
+
+template <int BN> struct GemmShape {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileSched {
+  int num_m, full_tiles, total_tiles, bn;
+  // full_tiles big tiles, then (total_tiles - full_tiles) half-width tiles
+  __device__ __forceinline__ void decode(int t, int& m0, int& n0, int& width) const {
+    if (t < full_tiles) {
+      m0 = (t % num_m) * BM;
+      n0 = (t / num_m) * bn;
+      width = bn;
+    } else {
+      int u = t - full_tiles;
+      int bt = full_tiles + (u >> 1);
+      m0 = (bt % num_m) * BM;
+      n0 = (bt / num_m) * bn + (u & 1) * (bn >> 1);
+      width = bn >> 1;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// epilogue bodies: one "unit" = U consecutive accumulator columns of this thread's row
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_bf16x8(const bf16* p, float (&f)[8]) {
+  uint4 v = ld_global_nc_v4(p);
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+// out = bf16(acc + bias)
+__device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
+                                              int ucols) {
+  for (int cc = 0; cc < ucols; cc += 32) {
+    if (n + cc >= N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(taddr + cc, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = n + cc + 8 * g;
+      if (col < N && row_ok) {
+        float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (p.bias) load_bf16x8(p.bias + col, b);
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          o[i] = pack_bf16x2(__uint_as_float(r[8 * g + 2 * i]) + b[2 * i], __uint_as_float(r[8 * g + 2 * i + 1]) + b[2 * i + 1]);
+        st_global_v4(p.out + (long long)row * p.ldo + col, o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// x = bf16(x + bf16(bf16(acc) * gamma)), in place
+__device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
+                                               int ucols) {
+  for (int cc = 0; cc < ucols; cc += 32) {
+    if (n + cc >= N) break;
+    uint4 xv[4];
+    bf16* xp = p.out + (long long)row * p.ldo + n + cc;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      xv[g] = make_uint4(0, 0, 0, 0);
+      if (row_ok && n + cc + 8 * g < N) xv[g] = ld_global_v4(xp + 8 * g);
+    }
+    uint32_t r[32];
+    tmem_ld32(taddr + cc, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = n + cc + 8 * g;
+      if (col < N && row_ok) {
+        float gm[8];
+        load_bf16x8(p.gamma + col, gm);
+        const uint32_t xin[4] = {xv[g].x, xv[g].y, xv[g].z, xv[g].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float a0 = bf16r(bf16r(__uint_as_float(r[8 * g + 2 * i])) * gm[2 * i]);
+          float a1 = bf16r(bf16r(__uint_as_float(r[8 * g + 2 * i + 1])) * gm[2 * i + 1]);
+          o[i] = pack_bf16x2(bf16_lo(xin[i]) + a0, bf16_hi(xin[i]) + a1);
+        }
+        st_global_v4(xp + 8 * g, o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// LayerNorm without affine over all N (= C) columns of the row; the reference rounds the Linear output to
+// bf16 first (nn.Linear in bf16), normalises in fp32 and rounds again (norm.py:39).
+__device__ __forceinline__ void epi_bias_ln_row(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int N) {
+  float sum = 0.f;
+  for (int c = 0; c < N; c += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + c, r);
+    tmem_wait_ld();
+    float b[16];
+    load_bf16x8(p.bias + c, *reinterpret_cast<float(*)[8]>(&b[0]));
+    load_bf16x8(p.bias + c + 8, *reinterpret_cast<float(*)[8]>(&b[8]));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sum += bf16r(__uint_as_float(r[i]) + b[i]);
+  }
+  const float mean = sum / (float)N;
+  float var = 0.f;
+  for (int c = 0; c < N; c += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + c, r);
+    tmem_wait_ld();
+    float b[16];
+    load_bf16x8(p.bias + c, *reinterpret_cast<float(*)[8]>(&b[0]));
+    load_bf16x8(p.bias + c + 8, *reinterpret_cast<float(*)[8]>(&b[8]));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float dv = bf16r(__uint_as_float(r[i]) + b[i]) - mean;
+      var += dv * dv;
+    }
+  }
+  const float rstd = rsqrtf(var / (float)N + p.eps);
+  for (int c = 0; c < N; c += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + c, r);
+    tmem_wait_ld();
+    float b[16];
+    load_bf16x8(p.bias + c, *reinterpret_cast<float(*)[8]>(&b[0]));
+    load_bf16x8(p.bias + c + 8, *reinterpret_cast<float(*)[8]>(&b[8]));
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v0 = (bf16r(__uint_as_float(r[2 * i]) + b[2 * i]) - mean) * rstd;
+      float v1 = (bf16r(__uint_as_float(r[2 * i + 1]) + b[2 * i + 1]) - mean) * rstd;
+      o[i] = pack_bf16x2(v0, v1);
+    }
+    if (row_ok) {
+      bf16* op = p.out + (long long)row * p.ldo + c;
+      st_global_v4(op, o[0], o[1], o[2], o[3]);
+      st_global_v4(op + 8, o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// One q or k head: per-head RMSNorm over d (fp32, eps inside rsqrt) then interleaved-pair 2D RoPE with
+// bf16 rounding at every eager-op boundary of the reference.
+__device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, int row, int rrow, bool row_ok,
+                                            int ncol, const bf16* w) {
+  const int d = p.d;
+  float ss = 0.f;
+  for (int cc = 0; cc < d; cc += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + cc, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float t = bf16r(__uint_as_float(r[i]));
+      ss += t * t;
+    }
+  }
+  const float rstd = rsqrtf(ss / (float)d + p.eps);
+  const bf16* rope = p.rope + (long long)rrow * d;
+  for (int cc = 0; cc < d; cc += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + cc, r);
+    tmem_wait_ld();
+    float cs[16], sn[16];
+    load_bf16x8(rope + (cc >> 1), *reinterpret_cast<float(*)[8]>(&cs[0]));
+    load_bf16x8(rope + (cc >> 1) + 8, *reinterpret_cast<float(*)[8]>(&cs[8]));
+    load_bf16x8(rope + (d >> 1) + (cc >> 1), *reinterpret_cast<float(*)[8]>(&sn[0]));
+    load_bf16x8(rope + (d >> 1) + (cc >> 1) + 8, *reinterpret_cast<float(*)[8]>(&sn[8]));
+    uint32_t o[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float wv[8];
+      load_bf16x8(w + cc + 8 * g, wv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = 8 * g + 2 * i;   // even column of the pair within this 32-chunk
+        const int pi = e >> 1;         // pair index within chunk
+        float y0 = bf16r(bf16r(__uint_as_float(r[e])) * rstd * wv[2 * i]);
+        float y1 = bf16r(bf16r(__uint_as_float(r[e + 1])) * rstd * wv[2 * i + 1]);
+        float o0 = bf16r(y0 * cs[pi]) - bf16r(y1 * sn[pi]);
+        float o1 = bf16r(y0 * sn[pi]) + bf16r(y1 * cs[pi]);
+        o[pi] = pack_bf16x2(o0, o1);
+      }
+    }
+    if (row_ok) {
+      bf16* op = p.qkv + (long long)row * p.ld_qkv + ncol + cc;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) st_global_v4(op + 8 * g, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t taddr, int row, int rrow, bool row_ok,
+                                                    int n, int ucols) {
+  if (n < p.qp) {
+    const int threeD = 3 * p.D;
+    for (int hc = 0; hc < ucols; hc += p.d) {
+      const int ncol = n + hc;
+      if (ncol >= threeD) break;  // zero-padded columns between 3D and qp
+      const int seg = ncol / p.D;
+      if (seg == 2) {  // V: plain bf16 copy
+        for (int cc = 0; cc < p.d; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + hc + cc, r);
+          tmem_wait_ld();
+          if (row_ok) {
+            bf16* op = p.qkv + (long long)row * p.ld_qkv + ncol + cc;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                o[i] = pack_bf16x2(__uint_as_float(r[8 * g + 2 * i]), __uint_as_float(r[8 * g + 2 * i + 1]));
+              st_global_v4(op + 8 * g, o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      } else {
+        epi_qk_head(p, taddr + hc, row, rrow, row_ok, ncol, seg == 0 ? p.normq : p.normk);
+      }
+    }
+  } else {
+    // SwiGLU: 32 packed columns = [v(16) | g(16)] -> 16 outputs; mlp.py:21-22 with bf16 rounding of
+    // fc1's output, of silu(g) and of the product.
+    for (int cc = 0; cc < ucols; cc += 32) {
+      const int j = (n + cc - p.qp) >> 5;
+      if (16 * j >= p.Hf) break;
+      uint32_t r[32];
+      tmem_ld32(taddr + cc, r);
+      tmem_wait_ld();
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v0 = bf16r(__uint_as_float(r[2 * i])), v1 = bf16r(__uint_as_float(r[2 * i + 1]));
+        float g0 = bf16r(__uint_as_float(r[16 + 2 * i])), g1 = bf16r(__uint_as_float(r[16 + 2 * i + 1]));
+        float s0 = bf16r(__fdividef(g0, 1.f + __expf(-g0)));
+        float s1 = bf16r(__fdividef(g1, 1.f + __expf(-g1)));
+        o[i] = pack_bf16x2(s0 * v0, s1 * v1);
+      }
+      if (row_ok) {
+        bf16* op = p.act + (long long)row * p.ld_act + 16 * j;
+        st_global_v4(op, o[0], o[1], o[2], o[3]);
+        st_global_v4(op + 8, o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int EPI, int NEPI>
+__global__ void __launch_bounds__(128 + 32 * NEPI, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const int M, const int N,
+            const int K, const TileSched sched, const EpiParams epi) {
+  using S = GemmShape<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + S::STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S::STAGES;
+  uint64_t* tfull = bars + 2 * S::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], NEPI);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < sched.total_tiles; t += gridDim.x) {
+        int m0, n0, width;
+        sched.decode(t, m0, n0, width);
+        const uint32_t tx = A_STAGE_BYTES + (uint32_t)width * BK * 2;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], tx);
+          tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, m0);
+          // B is fetched as 128-row boxes so that full and half-width tiles share one tensor map
+          for (int nb = 0; nb < width; nb += 128)
+            tma_load_2d(sB + s * S::B_STAGE_BYTES + nb * (BK * 2), &tmB, &full[s], kb * BK, n0 + nb);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int t = blockIdx.x; t < sched.total_tiles; t += gridDim.x) {
+        int m0, n0, width;
+        sched.decode(t, m0, n0, width);
+        const uint32_t idesc = make_idesc_bf16(BM, width, 0, 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b0 = smem_u32(sB + s * S::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16_ss(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // smem slot reusable once these MMAs have read it
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int ew = warp - 4;
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = ew >> 2;               // 0 or 1 when NEPI == 8
+    constexpr int NHALF = NEPI / 4;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int t = blockIdx.x; t < sched.total_tiles; t += gridDim.x) {
+      int m0, n0, width;
+      sched.decode(t, m0, n0, width);
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < M;
+      const int rrow = row_ok ? row : (M - 1);
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_base + (uint32_t)(acc * BN);
+      if (EPI == EPI_BIAS_LN) {
+        epi_bias_ln_row(epi, taddr, row, row_ok, N);
+      } else {
+        const int U = (EPI == EPI_QKV_SWIGLU && epi.d > 64) ? epi.d : 64;
+        for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
+          if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
+          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
+          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, row, rrow, row_ok, n0 + c0, U);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, int EPI, int NEPI>
+static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t stream) {
+  using S = GemmShape<BN>;
+  CUtensorMap tmA, tmB;
+  if (encode_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BM)) return -1;
+  if (encode_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.b_rows, (uint64_t)a.ldb, BN < 128 ? BN : 128))
+    return -1;
+  TileSched sc;
+  sc.bn = BN;
+  sc.num_m = (a.M + BM - 1) / BM;
+  const int num_n = (a.N + BN - 1) / BN;
+  const int big = sc.num_m * num_n;
+  const int sms = num_sms();
+  const int grid = big < sms ? big : sms;
+  int rem = big % grid;
+  sc.full_tiles = big;
+  sc.total_tiles = big;
+  if (allow_split && BN >= 256 && rem > 0 && 2 * rem <= grid) {
+    sc.full_tiles = big - rem;
+    sc.total_tiles = sc.full_tiles + 2 * rem;
+  }
+  auto kern = gemm_kernel<BN, EPI, NEPI>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES),
+                   "cudaFuncSetAttribute(gemm)"))
+      return -1;
+    attr_set = true;
+  }
+  kern<<<grid, 128 + 32 * NEPI, S::SMEM_BYTES, stream>>>(tmA, tmB, a.M, a.N, a.K, sc, a.epi);
+  return check_cuda(cudaGetLastError(), "gemm launch");
+}
+
+int launch_gemm(EpiKind kind, const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) { set_error("gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K); return -2; }
+  if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.N % 8)) {
+    set_error("gemm: K, N and the row strides must be multiples of 8 (K=%d N=%d lda=%lld ldb=%lld)", a.K, a.N, a.lda, a.ldb);
+    return -2;
+  }
+  if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) {
+    set_error("gemm: operand pointers must be 16-byte aligned");
+    return -2;
+  }
+  switch (kind) {
+    case EPI_BIAS:
+      if (a.N <= 64) return launch_gemm_t<64, EPI_BIAS, 8>(a, false, stream);
+      if (a.N <= 128) return launch_gemm_t<128, EPI_BIAS, 8>(a, false, stream);
+      return launch_gemm_t<256, EPI_BIAS, 8>(a, true, stream);
+    case EPI_BIAS_LN:
+      if (a.N % 16 || a.N > 256 || !a.epi.bias) { set_error("gemm: LN epilogue needs N%%16==0, N<=256 and a bias (N=%d)", a.N); return -2; }
+      if (a.N <= 64) return launch_gemm_t<64, EPI_BIAS_LN, 4>(a, false, stream);
+      if (a.N <= 128) return launch_gemm_t<128, EPI_BIAS_LN, 4>(a, false, stream);
+      return launch_gemm_t<256, EPI_BIAS_LN, 4>(a, false, stream);
+    case EPI_QKV_SWIGLU:
+      if (!(a.epi.d == 32 || a.epi.d == 64 || a.epi.d == 128) || a.epi.qp % 256 || a.epi.D % a.epi.d || a.epi.Hf % 16) {
+        set_error("gemm: unsupported attention geometry D=%d d=%d Hf=%d qp=%d (head_dim must be 32/64/128)", a.epi.D,
+                  a.epi.d, a.epi.Hf, a.epi.qp);
+        return -3;
+      }
+      return launch_gemm_t<256, EPI_QKV_SWIGLU, 8>(a, true, stream);
+    case EPI_RESID:
+      return launch_gemm_t<256, EPI_RESID, 8>(a, true, stream);
+  }
+  set_error("gemm: unknown epilogue %d", (int)kind);
+  return -2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// descriptor probe: one CTA, one 128 x N tile, no pipelining.  Lets a test sweep the shared-memory
+// descriptor fields (LBO / SBO / per-UMMA_K start-address step) for the MN-major B operand that the
+// attention kernel uses for V, and sanity-check the K-major path in isolation.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* D, int N,
+                  int K, int b_mn_major, uint32_t lbo, uint32_t sbo, uint32_t kstep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // A: K/64 blocks of [128 x 64] (16 KB each).  B K-major: K/64 blocks of [N x 64]; B MN-major: N/64 blocks of [K x 64].
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (K / 64) * 16384;
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) {
+    uint32_t bytes = (uint32_t)(128 * K * 2 + N * K * 2);
+    mbar_expect_tx(&bar_load, bytes);
+    for (int kb = 0; kb < K / 64; ++kb) tma_load_2d(sA + kb * 16384, &tmA, &bar_load, kb * 64, 0);
+    if (!b_mn_major) {
+      for (int kb = 0; kb < K / 64; ++kb) tma_load_2d(sB + kb * (N * 128), &tmB, &bar_load, kb * 64, 0);
+    } else {
+      for (int nb = 0; nb < N / 64; ++nb) tma_load_2d(sB + nb * (K * 128), &tmB, &bar_load, nb * 64, 0);
+    }
+    mbar_wait(&bar_load, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, b_mn_major);
+    for (int k = 0; k < K / 16; ++k) {
+      const uint32_t aaddr = smem_u32(sA) + (k / 4) * 16384 + (k % 4) * 32;
+      uint64_t bdesc;
+      if (!b_mn_major) {
+        bdesc = make_desc_kmajor_sw128(smem_u32(sB) + (k / 4) * (N * 128) + (k % 4) * 32);
+      } else {
+        bdesc = make_smem_desc(smem_u32(sB) + k * kstep, lbo, sbo, 2);
+      }
+      umma_bf16_ss(tmem_base, make_desc_kmajor_sw128(aaddr), bdesc, idesc, k != 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < N; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_wait_ld();
+    for (int i = 0; i < 32; ++i) D[row * N + c + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+int launch_umma_probe(const bf16* A, const bf16* B, float* D, int N, int K, int b_mn_major, uint32_t lbo_bytes,
+                      uint32_t sbo_bytes, uint32_t kstep_bytes, cudaStream_t stream) {
+  if (N % 64 || N > 256 || K % 64 || K > 256) { set_error("probe: N, K must be multiples of 64 and <= 256"); return -2; }
+  CUtensorMap tmA, tmB;
+  if (encode_tmap_bf16_sw128(&tmA, A, K, 128, K, 128)) return -1;
+  if (!b_mn_major) {
+    if (encode_tmap_bf16_sw128(&tmB, B, K, N, K, N)) return -1;   // B [N, K]
+  } else {
+    if (encode_tmap_bf16_sw128(&tmB, B, N, K, N, K)) return -1;   // B [K, N]: box = 64 (n) x K rows
+  }
+  const int smem = 128 * K * 2 + N * K * 2 + 1024;
+  if (check_cuda(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "probe attr"))
+    return -1;
+  umma_probe_kernel<<<1, 128, smem, stream>>>(tmA, tmB, D, N, K, b_mn_major, lbo_bytes, sbo_bytes, kstep_bytes);
+  return check_cuda(cudaGetLastError(), "probe launch");
+}
+
+}  // namespace vtk

@@ -1,0 +1,124 @@
+// vtk_kernels.h -- internal (C++) launch interface between the C-ABI layer (vtk_api.cu) and the
+// kernels.  Nothing here is exported; the exported surface is include/vitok_b200.h.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vtk {
+
+typedef __nv_bfloat16 bf16;
+
+// error plumbing (vtk_api.cu)
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int num_sms();
+
+// Encode a 2-D bf16 row-major tensor map with 128-byte swizzle: inner box = 64 elements.
+int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
+                           uint64_t row_stride_elems, uint32_t box_rows);
+
+// ---------------------------------------------------------------------------------------------
+// GEMM  out = epilogue(A[M,K] * B[N,K]^T), bf16 in, fp32 accumulate in TMEM (vtk_gemm.cu)
+// ---------------------------------------------------------------------------------------------
+enum EpiKind {
+  EPI_BIAS = 0,        // out = bf16(acc + bias)            (bias may be null)
+  EPI_BIAS_LN = 1,     // out = LN_noaffine(bf16(acc+bias)) over the N (= C <= 256) columns
+  EPI_QKV_SWIGLU = 2,  // packed [q|k|v|pad|(v16,g16)*] columns: QK-RMSNorm + 2D RoPE, V copy, SwiGLU gate
+  EPI_RESID = 3,       // x = bf16(x + bf16(bf16(acc) * gamma))   (in place on out)
+};
+
+struct EpiParams {
+  bf16* out;            // EPI_BIAS / EPI_BIAS_LN: [M, N]; EPI_RESID: x (read + written)
+  long long ldo;        // row stride of out (elements)
+  const bf16* bias;     // [N] or null
+  float eps;
+  // EPI_QKV_SWIGLU
+  bf16* qkv;            // [M, 3D]
+  long long ld_qkv;
+  bf16* act;            // [M, Hf] view (row stride ld_act)
+  long long ld_act;
+  const bf16* normq;    // [d]
+  const bf16* normk;    // [d]
+  const bf16* rope;     // [M, d]: cos[d/2] | sin[d/2], bf16-rounded
+  int D, d, Hf, qp;     // qp = 3D rounded up to the tile width (start of the SwiGLU columns)
+  // EPI_RESID
+  const bf16* gamma;    // [N]
+};
+
+struct GemmArgs {
+  const bf16* A; long long lda;   // [M, K], row stride lda
+  const bf16* B; long long ldb;   // [N_rows, K], row stride ldb (N_rows may be < N: OOB rows read as 0)
+  long long b_rows;
+  int M, N, K;                    // N = number of output (packed) columns to cover
+  EpiParams epi;
+};
+
+int launch_gemm(EpiKind kind, const GemmArgs& a, cudaStream_t stream);
+
+// descriptor probe (tests only): D[128, N] fp32 = A[128,K] * op(B); b_mn_major selects B = [K, N] row-major.
+int launch_umma_probe(const bf16* A, const bf16* B, float* D, int N, int K, int b_mn_major, uint32_t lbo_bytes,
+                      uint32_t sbo_bytes, uint32_t kstep_bytes, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// attention (vtk_attention.cu): softmax(q k^T / sqrt(d)) v per (image, head); q/k/v rows are
+// [B*N, ld] with heads along columns.  kv_len[b] = number of leading key rows to visit
+// (null = N); key_mask [B, N] bytes (null = none) masks individual keys inside kv_len.
+// ---------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const bf16* q; const bf16* k; const bf16* v; long long ld_qkv;  // row stride (elements)
+  bf16* out; long long ld_out;
+  const int* kv_len;            // [B] or null
+  const uint8_t* key_mask;      // [B, N] or null
+  const int* prefix_flag;       // [B] or null: 1 = key_mask[b] is a pure prefix (kv_len alone describes it)
+  int B, N, heads, d;
+  int zero_invalid_rows;        // 1: rows >= kv_len[b] (or with key_mask 0) are written as 0
+};
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// elementwise / HBM-bound kernels (vtk_elementwise.cu)
+// ---------------------------------------------------------------------------------------------
+int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, int M, int D, float eps,
+                   cudaStream_t stream);
+int launch_rope_table(const int64_t* row_idx, const int64_t* col_idx, const float* inv_freq, bf16* table, int M, int d,
+                      cudaStream_t stream);
+int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
+int launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t stream);
+int launch_kv_len(const uint8_t* mask, int* kv_len, int* is_prefix, int B, int N, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// NaFlex pre/post-processing (vtk_pp.cu)
+// ---------------------------------------------------------------------------------------------
+struct PatchifyArgs {
+  const void* images;          // base pointer of the packed image buffer
+  const int64_t* img_table;    // device [B, 3] = {element offset, H, W}
+  int in_dtype;                // 0 = fp32 CHW (already normalised), 1 = uint8 HWC (to_tensor|normalize fused)
+  int B, patch, max_tokens;
+  int out_dtype;               // 0 = fp32, 1 = bf16
+  void* patches;               // [B, T, 3 p^2]
+  uint8_t* patch_mask;         // [B, T]
+  int64_t* row_idx; int64_t* col_idx; int64_t* time_idx;  // [B, T]
+  int64_t* meta;               // [4, B] = orig_height, orig_width, grid_rows, grid_cols
+  int* status;                 // device int: set to 1 if any grid exceeds max_tokens
+};
+int launch_patchify(const PatchifyArgs& a, cudaStream_t stream);
+
+struct UnpatchifyArgs {
+  const void* patches;         // [B, N, 3 p^2]
+  int dtype;                   // 0 fp32, 1 bf16
+  const uint8_t* patch_mask; const int64_t* row_idx; const int64_t* col_idx;  // [B, N]
+  int B, N, patch, gy, gx;
+  int* cell_map;               // workspace [B, gy*gx] int32
+  void* out;                   // [B, 3, gy*p, gx*p], same dtype unless out_u8
+  int out_format;              // 0 = same dtype, no conversion; 1 = uint8 "0_255" from minus_one_to_one;
+                               // 2 = zero_to_one from minus_one_to_one (same dtype)
+  int* status;                 // set to 1 when a valid token falls outside the canvas
+};
+int launch_unpatchify(const UnpatchifyArgs& a, cudaStream_t stream);
+int launch_grid_extent(const uint8_t* mask, const int64_t* row, const int64_t* col, int B, int N, int* out2,
+                       cudaStream_t stream);
+
+}  // namespace vtk

@@ -1,0 +1,14 @@
+"""vitok_b200 -- B200-native drop-in for the ViTok-v2 AE encode/decode hot path.
+
+Mirrors the hot-path surface of the reference package ``vitok`` (vitok/__init__.py:3-28):
+``AE``, ``decode_variant``, ``preprocess``, ``postprocess``, ``unpatchify``, ``unpack``,
+``patchify``, ``patch_collate_fn``, ``build_transform``, ``OPS``.  All tensor work runs in
+libvitok_b200.so (hand-written sm_100a kernels); there is no CPU fallback.
+"""
+from .models.ae import AE, Model, decode_variant
+from .pp import OPS, build_transform, parse_op, patchify_batch, postprocess, preprocess, unpack, unpatchify
+from .data import patch_collate_fn
+
+__version__ = "0.1.0"
+__all__ = ["AE", "Model", "decode_variant", "build_transform", "parse_op", "OPS", "patch_collate_fn", "preprocess",
+           "postprocess", "unpatchify", "unpack", "patchify_batch"]

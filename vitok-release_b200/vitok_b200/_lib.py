@@ -1,0 +1,219 @@
+"""ctypes binding of libvitok_b200.so (the C ABI declared in include/vitok_b200.h).
+
+There is NO fallback: if the shared library is missing or a tensor is not on a
+CUDA device the call raises.  torch is used only for device memory and the
+current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvitok_b200.so")
+
+VTK_OK, VTK_ERR_CUDA, VTK_ERR_BAD_ARG, VTK_ERR_UNSUPPORTED = 0, -1, -2, -3
+
+c_int, c_i64, c_f32, c_vp, c_u32, c_sz = (ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p,
+                                          ctypes.c_uint32, ctypes.c_size_t)
+
+
+class AEConfig(ctypes.Structure):
+    _fields_ = [("pixels_per_token", ctypes.c_int32), ("channels_per_token", ctypes.c_int32),
+                ("enc_width", ctypes.c_int32), ("enc_depth", ctypes.c_int32), ("enc_heads", ctypes.c_int32),
+                ("enc_hidden", ctypes.c_int32),
+                ("dec_width", ctypes.c_int32), ("dec_depth", ctypes.c_int32), ("dec_heads", ctypes.c_int32),
+                ("dec_hidden", ctypes.c_int32),
+                ("norm_eps", ctypes.c_float)]
+
+
+class BlockWeights(ctypes.Structure):
+    _fields_ = [("w_in", c_vp), ("w_out", c_vp), ("norm1", c_vp), ("norm_q", c_vp), ("norm_k", c_vp), ("gamma", c_vp)]
+
+
+# name -> (restype, argtypes); must list every symbol include/vitok_b200.h declares
+SIGNATURES = {
+    "vtk_last_error": (ctypes.c_char_p, []),
+    "vtk_abi_version": (c_int, []),
+    "vtk_sm_count": (c_int, []),
+    "vtk_patchify": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vtk_grid_extent": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "vtk_unpatchify": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "vtk_rmsnorm_bf16": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_f32, c_vp]),
+    "vtk_rope_table": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "vtk_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "vtk_cast_bf16_to_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "vtk_kv_len": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "vtk_linear_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    "vtk_linear_ln_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
+    "vtk_qkv_swiglu_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                    c_f32, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "vtk_proj_residual_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    "vtk_attention_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                   c_int, c_vp]),
+    "vtk_umma_probe": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u32, c_u32, c_u32, c_vp]),
+    "vtk_ae_create": (c_int, [ctypes.POINTER(AEConfig), ctypes.POINTER(c_vp)]),
+    "vtk_ae_destroy": (c_int, [c_vp]),
+    "vtk_ae_set_weights": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(BlockWeights), c_int,
+                                   ctypes.POINTER(c_f32), c_int]),
+    "vtk_ae_workspace_bytes": (c_sz, [c_vp, c_int, c_int, c_int]),
+    "vtk_ae_encode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "vtk_ae_decode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "vtk_ae_last_launch_count": (c_int, [c_vp]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library and type every export.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+            "(run `python vitok-release_b200/build.py`).  vitok_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load().vtk_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc == VTK_OK:
+        return
+    msg = last_error()
+    if rc == VTK_ERR_BAD_ARG:
+        raise ValueError(msg)
+    if rc == VTK_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("vitok_b200: tensors must live on a CUDA device (there is no CPU path)")
+    return t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"vitok_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"vitok_b200: {name} must have dtype {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise ValueError(f"vitok_b200: {name} must be contiguous in its last dimension")
+    return t
+
+
+# ---------------------------------------------------------------------------
+# thin kernel-level wrappers (used by the parity tests; the model path goes
+# through vtk_ae_encode / vtk_ae_decode)
+# ---------------------------------------------------------------------------
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    check(load().vtk_linear_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), M, N, K,
+                                 stream_ptr()))
+    return out
+
+
+def linear_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(bias, torch.bfloat16, "bias")
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    check(load().vtk_linear_ln_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), M, N, K,
+                                    eps, stream_ptr()))
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x"); _req(w, torch.bfloat16, "w")
+    M, D = x.shape
+    y = torch.empty_like(x)
+    check(load().vtk_rmsnorm_bf16(ptr(x), x.stride(0), ptr(w), ptr(y), y.stride(0), M, D, eps, stream_ptr()))
+    return y
+
+
+def rope_table(row_idx: torch.Tensor, col_idx: torch.Tensor, inv_freq: torch.Tensor, head_dim: int) -> torch.Tensor:
+    _req(row_idx, torch.int64, "row_idx"); _req(col_idx, torch.int64, "col_idx"); _req(inv_freq, torch.float32, "inv_freq")
+    M = row_idx.numel()
+    table = torch.empty(M, head_dim, dtype=torch.bfloat16, device=row_idx.device)
+    check(load().vtk_rope_table(ptr(row_idx.contiguous()), ptr(col_idx.contiguous()), ptr(inv_freq), ptr(table), M,
+                                head_dim, stream_ptr()))
+    return table
+
+
+def cast_to_bf16(x: torch.Tensor) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(load().vtk_cast_f32_to_bf16(ptr(x), ptr(out), x.numel(), stream_ptr()))
+    return out
+
+
+def kv_len(mask: torch.Tensor):
+    B, N = mask.shape
+    m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
+    kl = torch.empty(B, dtype=torch.int32, device=mask.device)
+    pf = torch.empty(B, dtype=torch.int32, device=mask.device)
+    check(load().vtk_kv_len(ptr(m), ptr(kl), ptr(pf), B, N, stream_ptr()))
+    return kl, pf
+
+
+def qkv_swiglu(h, w_packed, D, d, Hf, qp, norm_q, norm_k, table, eps=1e-6):
+    M = h.shape[0]
+    qkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=h.device)
+    act = torch.empty(M, Hf, dtype=torch.bfloat16, device=h.device)
+    check(load().vtk_qkv_swiglu_bf16(ptr(h), h.stride(0), ptr(w_packed), w_packed.stride(0), w_packed.shape[0], M, D, d,
+                                     Hf, qp, ptr(norm_q), ptr(norm_k), ptr(table), eps, ptr(qkv), qkv.stride(0),
+                                     ptr(act), act.stride(0), stream_ptr()))
+    return qkv, act
+
+
+def proj_residual(a, w, gamma, x):
+    M, K = a.shape
+    N = w.shape[0]
+    check(load().vtk_proj_residual_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(gamma), ptr(x), x.stride(0), M, N, K,
+                                        stream_ptr()))
+    return x
+
+
+def attention(qkv: torch.Tensor, B: int, N: int, heads: int, d: int, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv [B*N, 3*heads*d] (q | k | v).  mask [B,N] bool -> sdpa semantics; None -> flash semantics."""
+    D = heads * d
+    out = torch.empty(B * N, D, dtype=torch.bfloat16, device=qkv.device)
+    kl = pf = m8 = None
+    if mask is not None:
+        m8 = mask.contiguous().view(torch.uint8)
+        kl, pf = kv_len(mask)
+    base = qkv.data_ptr()
+    check(load().vtk_attention_bf16(base, base + 2 * D, base + 4 * D, qkv.stride(0), ptr(out), out.stride(0), ptr(kl),
+                                    ptr(m8), ptr(pf), B, N, heads, d, 1 if mask is not None else 0, stream_ptr()))
+    return out
+
+
+def umma_probe(a: torch.Tensor, b: torch.Tensor, n: int, k: int, b_mn_major: bool, lbo: int, sbo: int, kstep: int):
+    d = torch.zeros(128, n, dtype=torch.float32, device=a.device)
+    check(load().vtk_umma_probe(ptr(a), ptr(b), ptr(d), n, k, 1 if b_mn_major else 0, lbo, sbo, kstep, stream_ptr()))
+    return d

@@ -1,0 +1,371 @@
+"""B200-native drop-in for ``vitok.models.ae`` (reference: /root/reference/vitok/models/ae.py).
+
+Same public surface -- ``AE(**decode_variant(v))``, ``.encode(d)['z']``, ``.decode(d)['patches']``,
+``.forward``, ``.quantize``, identical parameter names/shapes so ``load_state_dict`` of reference or
+Hub weights works -- but no tensor math happens in PyTorch: ``encode``/``decode`` each make ONE call
+into libvitok_b200.so (``vtk_ae_encode`` / ``vtk_ae_decode``), which runs the whole layer stack as
+hand-written sm_100a kernels on the current CUDA stream.  The nn.Module tree below only *holds*
+parameters.  There is no CPU / eager fallback.
+
+Semantics kept from the reference (file:line in the reference tree):
+  * dict contract: pass-through of patch_mask/row_idx/col_idx/orig_height/orig_width as the same
+    tensor objects, 'patches' dropped by encode, 'z' dropped by decode (ae.py:209-216, 236-243);
+  * ``attn_backend="flash"``: attention over all N tokens, patch_mask ignored (attention.py:109-117);
+    ``attn_backend="sdpa"``: keys masked by patch_mask (ae.py:173-187, attention.py:118-127).  Both
+    run on the same tcgen05 attention kernel; padded keys are skipped, not masked after the fact;
+  * unknown kwargs ignored (ae.py:92); ``sw <= 0`` -> None (ae.py:99).
+Not implemented yet (raise): sliding-window attention ``sw``, FP8 ``quantize()``, autograd/backward.
+"""
+from __future__ import annotations
+
+import ctypes
+import re
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+__all__ = ["AE", "Model", "decode_variant", "pack_w_in", "pack_w_out"]
+
+# --------------------------------------------------------------------------------------
+# variant strings:  "{enc}-{dec}/{T}x{S}x{C}"                      (ae.py:280-346)
+# --------------------------------------------------------------------------------------
+_PRESETS = {  # letter: (width, depth, heads)
+    "B": (768, 12, 12), "L": (1024, 24, 16), "G": (1728, 32, 24), "T": (3072, 40, 24), "E": (4096, 48, 32),
+}
+_DEFAULT_MLP = 2.67
+_MOD = {"w": r"w(\d+)", "d": r"d(\d+)", "h": r"h(\d+)", "m": r"m(\d+(?:\.\d+)?)"}
+
+
+def _side_config(name: str) -> Dict[str, Any]:
+    """One side of a variant: preset letter with inline w/d/h/m overrides, or ``w{W}_d{D}_h{H}[_m{M}]``."""
+    if name.startswith("w") and "_d" in name and "_h" in name:
+        f = name.split("_")
+        mlp = float(f[3][1:]) if len(f) > 3 and f[3].startswith("m") else _DEFAULT_MLP
+        return {"width": int(f[0][1:]), "depth": int(f[1][1:]), "heads": int(f[2][1:]), "mlp_factor": mlp}
+    found = {k: re.search(rx, name) for k, rx in _MOD.items()}
+    base = re.sub("|".join(_MOD[k] for k in ("w", "d", "h", "m")), "", name)
+    if base and base not in _PRESETS:
+        raise ValueError(f"Unknown base variant: {base}. Available: {list(_PRESETS.keys())}")
+    pw, pd, ph = _PRESETS.get(base, (768, 12, 12))
+    return {
+        "width": int(found["w"].group(1)) if found["w"] else pw,
+        "depth": int(found["d"].group(1)) if found["d"] else pd,
+        "heads": int(found["h"].group(1)) if found["h"] else ph,
+        "mlp_factor": float(found["m"].group(1)) if found["m"] else _DEFAULT_MLP,
+    }
+
+
+def decode_variant(variant: str) -> Dict[str, Any]:
+    """Variant string -> AE kwargs; same keys/values as the reference's ``decode_variant`` (ae.py:318-346)."""
+    arch, geom = variant.split("/")
+    enc_name, dec_name = arch.split("-") if "-" in arch else (arch, arch)
+    dims = [int(t) for t in geom.split("x")]
+    if len(dims) == 2:
+        dims = [1] + dims
+    if len(dims) != 3:
+        raise ValueError(f"Invalid variant format: {variant}")
+    t_stride, s_stride, channels = dims
+    enc, dec = _side_config(enc_name), _side_config(dec_name)
+    return {
+        "encoder_width": enc["width"], "decoder_width": dec["width"],
+        "encoder_depth": enc["depth"], "decoder_depth": dec["depth"],
+        "encoder_heads": enc["heads"], "decoder_heads": dec["heads"],
+        "mlp_factor": max(enc["mlp_factor"], dec["mlp_factor"]),
+        "temporal_stride": t_stride, "spatial_stride": s_stride, "channels_per_token": channels,
+        "pixels_per_token": 3 * s_stride * s_stride * t_stride,
+    }
+
+
+def _ffn_hidden(width: int, mlp_factor: float) -> int:
+    """SwiGLU hidden size: int(width*mlp_factor) (ae.py:128) rounded to a multiple of 16 (mlp.py:14)."""
+    return ((int(width * mlp_factor) + 8) // 16) * 16
+
+
+def pack_w_in(qkv_w: torch.Tensor, fc1_w: torch.Tensor) -> torch.Tensor:
+    """[Wq; Wk; Wv; zeros up to qp = roundup(3D, 256); fc1 value/gate halves interleaved in 16-row groups].
+
+    The interleave puts value column j and gate column j in the same 32-column accumulator chunk so the
+    GEMM epilogue can apply silu(g)*v without leaving registers.
+    """
+    three_d, width = qkv_w.shape
+    hf = fc1_w.shape[0] // 2
+    qp = ((three_d + 255) // 256) * 256
+    w_in = torch.zeros(qp + 2 * hf, width, dtype=qkv_w.dtype, device=qkv_w.device)
+    w_in[:three_d] = qkv_w
+    w_in[qp:] = fc1_w.view(2, hf // 16, 16, width).permute(1, 0, 2, 3).reshape(2 * hf, width)
+    return w_in
+
+
+def pack_w_out(out_w: torch.Tensor, fc2_w: torch.Tensor) -> torch.Tensor:
+    """[out_proj | fc2] along K: attn_out + mlp_out becomes one GEMM over the concatenated activations."""
+    return torch.cat([out_w, fc2_w], dim=1).contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# parameter holders (names = the reference's state_dict keys; no forward math here)
+# --------------------------------------------------------------------------------------
+class _NoTorchPath(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("vitok_b200 modules hold parameters only; the math runs in libvitok_b200.so "
+                           "via AE.encode / AE.decode (there is no PyTorch fallback)")
+
+
+class _Scale(_NoTorchPath):
+    def __init__(self, dim: int, init: float, name: str):
+        super().__init__()
+        self.register_parameter(name, nn.Parameter(torch.full((dim,), float(init))))
+
+
+class _Attn(_NoTorchPath):
+    def __init__(self, dim: int, heads: int):
+        super().__init__()
+        self.dim, self.num_heads, self.head_dim = dim, heads, dim // heads
+        self.norm_q = _Scale(self.head_dim, 1.0, "weight")
+        self.norm_k = _Scale(self.head_dim, 1.0, "weight")
+        self.qkv_proj = nn.Linear(dim, 3 * dim, bias=False)
+        self.out_proj = nn.Linear(dim, dim, bias=False)
+
+
+class _Ffn(_NoTorchPath):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, 2 * hidden, bias=False)
+        self.fc2 = nn.Linear(hidden, dim, bias=False)
+
+
+class Block(_NoTorchPath):
+    """Parallel attention + SwiGLU block with LayerScale (reference Block, ae.py:33-65) -- parameters only."""
+
+    def __init__(self, dim: int, ffn_dim: int, num_heads: int, use_layer_scale: bool = True,
+                 layer_scale_init: float = 1e-6, drop_path: float = 0.0, sliding_window: Optional[int] = None,
+                 attn_backend: str = "flash"):
+        super().__init__()
+        self.sliding_window = sliding_window
+        self.drop_path_rate = drop_path
+        self.norm1 = _Scale(dim, 1.0, "weight")
+        self.attn = _Attn(dim, num_heads)
+        self.ffn = _Ffn(dim, ((ffn_dim + 8) // 16) * 16)
+        self.layer_scale = _Scale(dim, layer_scale_init, "gamma") if use_layer_scale else nn.Identity()
+
+
+class _OutputNorm(_NoTorchPath):
+    """LayerNorm without affine parameters (no state_dict entries), fused into the to_code GEMM epilogue."""
+
+
+class AE(nn.Module):
+    """ViTok-v2 autoencoder; see module docstring."""
+
+    def __init__(self, pixels_per_token=768, channels_per_token=32, encoder_width=1024, decoder_width=1024,
+                 encoder_depth=4, decoder_depth=24, encoder_heads=12, decoder_heads=12, mlp_factor=2.67,
+                 checkpoint: int = 0, spatial_stride: int = 16, temporal_stride: int = 1, use_layer_scale: bool = True,
+                 layer_scale_init: float = 1e-4, drop_path_rate: float = 0.0, encoder: bool = True, decoder: bool = True,
+                 sw: Optional[int] = None, attn_backend: str = "flash", **kwargs):
+        super().__init__()
+        if not encoder and not decoder:
+            raise ValueError("At least one of encoder or decoder must be True")
+        if attn_backend not in ("flash", "sdpa"):
+            raise ValueError(f"attn_backend must be 'flash' or 'sdpa', got {attn_backend!r}")
+        sw = sw if (sw is None or sw > 0) else None
+        self.pixels_per_token, self.channels_per_token = pixels_per_token, channels_per_token
+        self.rope_theta = 10000.0
+        self.encoder_depth, self.decoder_depth = encoder_depth, decoder_depth
+        self.encoder_width, self.decoder_width = encoder_width, decoder_width
+        self.encoder_heads, self.decoder_heads = encoder_heads, decoder_heads
+        self.mlp_factor = mlp_factor
+        self.checkpoint = checkpoint
+        self.spatial_stride = spatial_stride
+        self.temporal_stride = temporal_stride
+        self.is_encoder, self.is_decoder = encoder, decoder
+        self.sw = sw
+        self.attn_backend = attn_backend
+        self._quantization_applied = False
+
+        def stack(width, depth, heads, rates):
+            return nn.ModuleList([
+                Block(width, int(width * mlp_factor), heads, use_layer_scale, layer_scale_init, rates[i], sw, attn_backend)
+                for i in range(depth)])
+
+        if encoder:
+            self.patch_embed = nn.Linear(pixels_per_token, encoder_width)
+            self.to_code = nn.Linear(encoder_width, channels_per_token)
+            self.output_fn = _OutputNorm()
+            self.encoder_blocks = stack(encoder_width, encoder_depth, encoder_heads, [0.0] * encoder_depth)
+        if decoder:
+            self.decoder_embed = nn.Linear(channels_per_token, decoder_width)
+            self.to_pixels = nn.Linear(decoder_width, pixels_per_token)
+            rates = [drop_path_rate * i / max(decoder_depth - 1, 1) for i in range(decoder_depth)]
+            self.decoder_blocks = stack(decoder_width, decoder_depth, decoder_heads, rates)
+
+        # native state (not part of the state_dict)
+        self._handle: Optional[int] = None
+        self._packed: Dict[int, List[torch.Tensor]] = {}
+        self._packed_sig = None
+        self._ws: Dict[Any, torch.Tensor] = {}
+        self.last_launch_count = 0
+
+    # ------------------------------------------------------------------ native plumbing
+    def _sides(self):
+        out = []
+        if self.is_encoder:
+            out.append((0, self.patch_embed, self.to_code, self.encoder_blocks, self.encoder_width, self.encoder_heads))
+        if self.is_decoder:
+            out.append((1, self.decoder_embed, self.to_pixels, self.decoder_blocks, self.decoder_width, self.decoder_heads))
+        return out
+
+    def _signature(self):
+        ps = list(self.parameters())
+        return (ps[0].device, tuple(p.data_ptr() for p in ps), tuple(p._version for p in ps))
+
+    def __del__(self):
+        try:
+            if self._handle:
+                _lib.load().vtk_ae_destroy(self._handle)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    @torch.no_grad()
+    def _ensure_packed(self, device: torch.device) -> int:
+        """(Re)build the packed bf16 weights the kernels read and hand their pointers to the C handle.
+
+        w_in  [qp + 2*Hf, D] = [Wq; Wk; Wv; zeros up to qp; 16-row interleave of fc1's value/gate halves]
+        w_out [D, D + Hf]    = [out_proj | fc2]   (one GEMM over the concatenated K)
+        Rebuilt whenever a parameter's storage or version changes (load_state_dict, .to(), optimizer step).
+        """
+        sig = self._signature()
+        if self._handle is not None and sig == self._packed_sig:
+            return self._handle
+        lib = _lib.load()
+        if sig[0].type != "cuda":
+            raise RuntimeError("vitok_b200.AE: parameters must be on a CUDA device (model.to('cuda')); there is no CPU path")
+        if self._handle is None:
+            cfg = _lib.AEConfig()
+            cfg.pixels_per_token, cfg.channels_per_token = self.pixels_per_token, self.channels_per_token
+            if self.is_encoder:
+                cfg.enc_width, cfg.enc_depth, cfg.enc_heads = self.encoder_width, self.encoder_depth, self.encoder_heads
+                cfg.enc_hidden = _ffn_hidden(self.encoder_width, self.mlp_factor)
+            if self.is_decoder:
+                cfg.dec_width, cfg.dec_depth, cfg.dec_heads = self.decoder_width, self.decoder_depth, self.decoder_heads
+                cfg.dec_hidden = _ffn_hidden(self.decoder_width, self.mlp_factor)
+            cfg.norm_eps = 1e-6
+            h = ctypes.c_void_p()
+            _lib.check(lib.vtk_ae_create(ctypes.byref(cfg), ctypes.byref(h)))
+            self._handle = h.value
+        bf = torch.bfloat16
+
+        def dev(t):
+            return t.detach().to(device=device, dtype=bf).contiguous()
+
+        for side, lin_a, lin_b, blocks, width, heads in self._sides():
+            keep: List[torch.Tensor] = []
+            Hf = _ffn_hidden(width, self.mlp_factor)
+            qp = ((3 * width + 255) // 256) * 256
+            arr = (_lib.BlockWeights * max(len(blocks), 1))()
+            for i, blk in enumerate(blocks):
+                w_in = pack_w_in(dev(blk.attn.qkv_proj.weight), dev(blk.ffn.fc1.weight))
+                w_out = pack_w_out(dev(blk.attn.out_proj.weight), dev(blk.ffn.fc2.weight))
+                gamma = dev(blk.layer_scale.gamma) if isinstance(blk.layer_scale, _Scale) else torch.ones(width, dtype=bf, device=device)
+                tens = [w_in, w_out, dev(blk.norm1.weight), dev(blk.attn.norm_q.weight), dev(blk.attn.norm_k.weight), gamma]
+                keep.extend(tens)
+                (arr[i].w_in, arr[i].w_out, arr[i].norm1, arr[i].norm_q, arr[i].norm_k, arr[i].gamma) = [t.data_ptr() for t in tens]
+            proj = [dev(lin_a.weight), dev(lin_a.bias), dev(lin_b.weight), dev(lin_b.bias)]
+            keep.extend(proj)
+            axis = (width // heads) // 2
+            inv = (1.0 / (self.rope_theta ** (torch.arange(0, axis, 2).float() / axis))).contiguous()
+            inv_c = (ctypes.c_float * inv.numel())(*inv.tolist())
+            _lib.check(lib.vtk_ae_set_weights(self._handle, side, *[t.data_ptr() for t in proj], arr, len(blocks), inv_c,
+                                              inv.numel()))
+            self._packed[side] = keep
+        self._packed_sig = sig
+        return self._handle
+
+    def _workspace(self, side: int, B: int, N: int, device) -> torch.Tensor:
+        key = (side, B, N, device)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = _lib.load().vtk_ae_workspace_bytes(self._handle, side, B, N)
+            ws = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=device)
+            self._ws = {k: v for k, v in self._ws.items() if k[0] != side}  # one live workspace per side
+            self._ws[key] = ws
+        return ws
+
+    def _run(self, side: int, x: torch.Tensor, d: Dict[str, torch.Tensor], out_cols: int) -> torch.Tensor:
+        if self.sw is not None:
+            raise NotImplementedError("vitok_b200.AE: sliding-window attention (sw) is not implemented yet")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("vitok_b200.AE: backward is not implemented yet; call model.eval() / torch.no_grad()")
+        if not x.is_cuda:
+            raise RuntimeError("vitok_b200.AE: inputs must be CUDA tensors (there is no CPU path)")
+        if x.dim() != 3:
+            raise ValueError(f"expected a [B, N, C] tensor, got shape {tuple(x.shape)}")
+        B, N, cin = x.shape
+        want = (self.pixels_per_token if side == 0 else self.channels_per_token)
+        if cin != want:
+            raise RuntimeError(f"shape mismatch: last dim {cin} != {want}")
+        h = self._ensure_packed(x.device)
+        lib = _lib.load()
+        if x.dtype == torch.float32:
+            xin = _lib.cast_to_bf16(x)
+        elif x.dtype == torch.bfloat16:
+            xin = x.contiguous()
+        else:
+            raise RuntimeError(f"vitok_b200.AE: unsupported input dtype {x.dtype} (float32 or bfloat16)")
+        row, col = d["row_idx"], d["col_idx"]
+        row = row.to(device=x.device, dtype=torch.int64).contiguous()
+        col = col.to(device=x.device, dtype=torch.int64).contiguous()
+        if row.shape != (B, N) or col.shape != (B, N):
+            raise ValueError("x_positions and y_positions must have matching shapes [B, N]")
+        mask = d.get("patch_mask") if self.attn_backend == "sdpa" else None
+        m8 = None
+        if mask is not None:
+            m8 = mask.to(device=x.device).bool().contiguous().view(torch.uint8)
+        ws = self._workspace(side, B, N, x.device)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        out = torch.empty(B, N, out_cols, dtype=torch.bfloat16, device=x.device)
+        fn = lib.vtk_ae_encode if side == 0 else lib.vtk_ae_decode
+        _lib.check(fn(h, xin.data_ptr(), row.data_ptr(), col.data_ptr(), m8.data_ptr() if m8 is not None else None,
+                      B, N, out.data_ptr(), ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()), _lib.stream_ptr()))
+        self.last_launch_count = lib.vtk_ae_last_launch_count(h)
+        pdtype = next(self.parameters()).dtype
+        if pdtype == torch.float32 and not torch.is_autocast_enabled():
+            out = out.float()
+        return out
+
+    # ------------------------------------------------------------------ public surface
+    def encode(self, patch_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """patches [B,N,P] -> z [B,N,C]  (reference AE.encode, ae.py:189-216)."""
+        if not self.is_encoder:
+            raise AttributeError("this AE was built with encoder=False")
+        z = self._run(0, patch_dict["patches"], patch_dict, self.channels_per_token)
+        return {
+            "patch_mask": patch_dict.get("patch_mask"), "row_idx": patch_dict["row_idx"], "col_idx": patch_dict["col_idx"],
+            "orig_height": patch_dict.get("orig_height"), "orig_width": patch_dict.get("orig_width"), "z": z,
+        }
+
+    def decode(self, encode_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """z [B,N,C] -> patches [B,N,P]  (reference AE.decode, ae.py:218-243)."""
+        if not self.is_decoder:
+            raise AttributeError("this AE was built with decoder=False")
+        patches = self._run(1, encode_dict["z"], encode_dict, self.pixels_per_token)
+        return {
+            "patch_mask": encode_dict.get("patch_mask"), "row_idx": encode_dict.get("row_idx"),
+            "col_idx": encode_dict.get("col_idx"), "orig_height": encode_dict.get("orig_height"),
+            "orig_width": encode_dict.get("orig_width"), "patches": patches,
+        }
+
+    def forward(self, x: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        if self.is_encoder:
+            x = self.encode(x)
+        if self.is_decoder:
+            x = self.decode(x)
+        return x
+
+    def quantize(self) -> "AE":
+        """FP8 inference (reference ae.py:253-270 via torchao) -- not built yet; bf16 is the shipped precision."""
+        raise NotImplementedError("vitok_b200.AE.quantize: the FP8 tcgen05 path is not implemented yet (bf16 only)")
+
+
+def Model(**kw):
+    return AE(**kw)
