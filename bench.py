@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode images/sec of the B200-native ViTok-v2 AE hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c3]
+
+Contract (see DESIGN.md "Measurement"):
+  * one "step" = AE.encode + AE.decode over one batch of synthetic images of the named resolution;
+  * workload at N=1 (default c2) = BASELINE.json configs[1]: 350M-f16x64, bf16, 64 x 256x256 images per GPU
+    (weak scaling: every rank owns its own 64-image batch; no data-path collective);
+  * `value`   : whole-job images/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks;
+  * `e2e`     : same metric through the public API with HOST (pinned) buffers: H2D of patches + indices and D2H
+                of the reconstructed patches inside the timed region;
+  * `roofline`: the dominant kernel (QKV+SwiGLU tcgen05 GEMM): algorithmic FLOPs per launch / its mean launch
+                duration from CUDA events recorded around every launch inside a timed pass;
+  * `cpu_baseline` / `--impl reference`: the CPU oracle (oracle/, a restatement of the reference's PyTorch CPU
+                path; the only place bench.py touches oracle/) timed on the host cores on a bounded sample.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "vitok-release_b200"))
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (variant, per-GPU batch, resolution, max_tokens, attn_backend)
+    "c2": ("Ld4-Ld24/1x16x64", 64, 256, 256, "flash"),
+    "c4": ("Td4-T/1x16x64", 8, 512, 1024, "flash"),
+    "350M-512": ("Ld4-Ld24/1x16x64", 16, 512, 1024, "flash"),
+}
+METRIC = "encode+decode images/sec"
+UNIT = "images/s"
+CLS_NAMES = ["linear", "rmsnorm", "qkv_swiglu_gemm", "attention", "proj_residual_gemm", "misc"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_sustained": d["bf16_tflops_sustained"], "bf16_burst": d["bf16_tflops"], "hbm": d["hbm_gbs"], "src": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
+
+
+def flops_per_image(cfg, N):
+    """per layer 2N D (4D + 3Hf) + 4 N^2 D, plus the four projections."""
+    def hf(D):
+        return ((int(D * cfg["mlp_factor"]) + 8) // 16) * 16
+    tot = 0.0
+    for D, L in ((cfg["encoder_width"], cfg["encoder_depth"]), (cfg["decoder_width"], cfg["decoder_depth"])):
+        tot += L * (2.0 * N * D * (4 * D + 3 * hf(D)) + 4.0 * N * N * D)
+    P, C, De, Dd = cfg["pixels_per_token"], cfg["channels_per_token"], cfg["encoder_width"], cfg["decoder_width"]
+    tot += 2.0 * N * (P * De + De * C + C * Dd + Dd * P)
+    return tot
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, val in zip(names, r[5:9]):
+                    if val.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                continue
+        if sm:
+            load = sorted(sm)[len(sm) // 2:]   # samples under load = upper half
+            out = {"sm_mhz": statistics.median(load), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend, rank=rank, world_size=world,
+                                **({"device_id": torch.device("cuda", local)} if backend == "nccl" else {}))
+    return rank, world, local
+
+
+def max_over_ranks(value: float, world: int, device) -> float:
+    if world == 1:
+        return value
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world: int):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference's PyTorch CPU path) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(variant: str, n_images: int, res: int, steps: int, warmup: int):
+    from oracle import ae_oracle, pp_oracle
+    from oracle.weights import make_state_dict, synth_images
+    import numpy as np
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ae_oracle.decode_variant(variant)
+    sd = make_state_dict(cfg, seed=0)
+    T = (res // cfg["spatial_stride"]) ** 2
+    b = pp_oracle.collate([pp_oracle.patchify(i, cfg["spatial_stride"], T) for i in synth_images([(res, res)] * n_images, seed=1234)])
+    batch = {k: torch.from_numpy(np.asarray(v)) for k, v in b.items()}
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            enc = ae_oracle.encode(sd, batch, cfg["encoder_heads"])
+            ae_oracle.decode(sd, enc, cfg["decoder_heads"])
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return n_images * len(times) / total, cores, total / len(times)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    variant, batch, res, T, _ = WORKLOADS[args.workload]
+    n_img = 4 if res <= 256 else 1
+    rate, cores, sec = cpu_oracle_rate(variant, n_img, res, max(1, args.steps), max(0, min(args.warmup, 1)))
+    sample = f"{n_img} x {res}x{res} images per step, fp32, torch CPU ops on {cores} threads (oracle port of vitok/models/ae.py)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {variant} encode+decode @{res}px, batch {batch}/GPU", "variant": variant,
+                   "resolution": res, "tokens_per_image": T, "batch_per_gpu": batch},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local):
+    import vitok_b200 as vb
+    from vitok_b200 import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    variant, B, res, T, backend = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    cfg = vb.decode_variant(variant)
+    torch.manual_seed(0)
+    model = vb.AE(**cfg, attn_backend=backend).eval().to(device=dev, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(1234 + rank)
+    imgs = torch.rand(B, 3, res, res, generator=g) * 2 - 1
+    pd = vb.patchify_batch(imgs.to(dev), cfg["spatial_stride"], T, out_dtype=torch.bfloat16, device=dev)
+    N = T
+    lib = _lib.load()
+
+    def step(d):
+        with torch.no_grad():
+            return model.decode(model.encode(d))
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        out = step(pd)
+    torch.cuda.synchronize()
+    launches_per_step = None
+    barrier(world)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    n_launch = 0
+    for _ in range(args.steps):
+        with torch.no_grad():
+            e = model.encode(pd)
+            n_launch += model.last_launch_count
+            out = model.decode(e)
+            n_launch += model.last_launch_count
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    ms = max_over_ranks(ms, world, dev)
+    value = world * B * args.steps / (ms / 1e3)
+    launches_per_step = n_launch // max(args.steps, 1)
+
+    # ---- e2e: host buffers in, host buffers out, through the public API ---------------------------
+    host_in = {k: (v.cpu().pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in pd.items()
+               if k in ("patches", "row_idx", "col_idx", "patch_mask", "orig_height", "orig_width")}
+    host_out = torch.empty(B, N, cfg["pixels_per_token"], dtype=torch.bfloat16).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    d2h = host_out.numel() * host_out.element_size()
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+        o = step(d)
+        host_out.copy_(o["patches"], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier(world)
+    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    t_ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_ms = max_over_ranks(t_ev0.elapsed_time(t_ev1), world, dev)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # ---- per-kernel-class CUDA-event timing inside a timed pass (roofline of the dominant kernel) ---
+    roof, breakdown = None, None
+    if hasattr(lib, "vtk_ae_set_timing"):
+        import ctypes
+        h = model._handle
+        lib.vtk_ae_set_timing(h, 1)
+        ms_cls = (ctypes.c_float * 6)()
+        cnt_cls = (ctypes.c_int * 6)()
+        tot = [0.0] * 6
+        cnt = [0] * 6
+        prof_steps = min(args.steps, 10)
+        for _ in range(prof_steps):
+            with torch.no_grad():
+                e = model.encode(pd)
+                lib.vtk_ae_collect_timing(h, ms_cls, cnt_cls)
+                for i in range(6):
+                    tot[i] += ms_cls[i]; cnt[i] += cnt_cls[i]
+                model.decode(e)
+                lib.vtk_ae_collect_timing(h, ms_cls, cnt_cls)
+                for i in range(6):
+                    tot[i] += ms_cls[i]; cnt[i] += cnt_cls[i]
+        lib.vtk_ae_set_timing(h, 0)
+        breakdown = {CLS_NAMES[i]: {"ms_per_step": tot[i] / prof_steps, "launches_per_step": cnt[i] // prof_steps} for i in range(6)}
+        # dominant kernel: decoder QKV+SwiGLU GEMM; FLOPs per launch averaged over enc+dec launches
+        M = B * N
+        fl = 0.0
+        for D, L in ((cfg["encoder_width"], cfg["encoder_depth"]), (cfg["decoder_width"], cfg["decoder_depth"])):
+            hf = ((int(D * cfg["mlp_factor"]) + 8) // 16) * 16
+            fl += L * 2.0 * M * D * (3 * D + 2 * hf)
+        n_l = cfg["encoder_depth"] + cfg["decoder_depth"]
+        avg_ms = tot[2] / max(cnt[2], 1)
+        pk = peaks()
+        ach = (fl / n_l) / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        roof = {"kernel": "gemm_kernel<256,EPI_QKV_SWIGLU,8>", "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                "avg_launch_ms": avg_ms, "flops_per_launch": fl / n_l}
+
+    if rank != 0:
+        return
+    gf = flops_per_image(cfg, N) / 1e9
+    pk = peaks()
+    cpu = None
+    if world == 1 or rank == 0:
+        try:
+            n_img = 4 if res <= 256 else 1
+            rate, cores, sec = cpu_oracle_rate(variant, n_img, res, 2, 1)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n_img} x {res}x{res} images, fp32, 2 timed iterations after 1 warm-up ({sec:.2f} s each)"}
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {variant} encode+decode @{res}px, batch {B}/GPU", "variant": variant,
+                   "resolution": res, "tokens_per_image": N, "batch_per_gpu": B, "global_batch": B * world,
+                   "attn_backend": backend, "weights": "random init (seed 0)",
+                   "l2": "no flush: per-step working set (weights + activations) exceeds the 126 MB L2",
+                   "gflop_per_image": gf},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": n_launch,
+        "launches_per_step": launches_per_step,
+        "model_tflops": value * gf / 1e3 / world,
+        "model_frac_of_peak": value * gf / 1e3 / world / pk["bf16_sustained"],
+        "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if args.steps > 5:          # bounded: the whole run must end within a few minutes
+            args.steps = 5
+        run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    rank, world, local = dist_setup(args.gpus)
+    try:
+        run_ours(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

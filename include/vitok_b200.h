@@ -156,6 +156,12 @@ int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64
                   int B, int N, void* patches_out, void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels launched by the last vtk_ae_encode/decode on this handle (for gpu_launches accounting) */
 int vtk_ae_last_launch_count(vtk_ae_t h);
+/* Optional per-launch CUDA-event timing (bench.py's live roofline).  With timing enabled every kernel launched by
+ * vtk_ae_encode/decode is bracketed by an event pair on `stream`; vtk_ae_collect_timing synchronises on the last
+ * event and returns the summed milliseconds and launch counts per kernel class:
+ * 0 linear, 1 rmsnorm, 2 qkv+swiglu GEMM, 3 attention, 4 out_proj+fc2 residual GEMM, 5 misc (6 entries each). */
+int vtk_ae_set_timing(vtk_ae_t h, int enable);
+int vtk_ae_collect_timing(vtk_ae_t h, float* ms_by_class_host, int* launches_by_class_host);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

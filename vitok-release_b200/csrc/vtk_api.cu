@@ -115,10 +115,34 @@ static Workspace carve(const Side& s, void* base, long long M, int B) {
 
 }  // namespace vtk
 
+// kernel classes for the optional per-launch CUDA-event timing (bench.py roofline)
+enum { CLS_LINEAR = 0, CLS_RMSNORM = 1, CLS_QKV_SWIGLU = 2, CLS_ATTENTION = 3, CLS_PROJ_RESID = 4, CLS_MISC = 5, CLS_COUNT = 6 };
+
 struct vtk_ae_s {
   vtk_ae_config cfg;
   vtk::Side side[2];
   int last_launches = 0;
+  // timing: one (start, stop) event pair per launch of the last encode/decode call
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;      // 2 per launch
+  std::vector<int> ev_cls;
+  int ev_used = 0;
+};
+
+// RAII helper: records an event pair around one launch when timing is on
+struct LaunchTimer {
+  vtk_ae_s* h; cudaStream_t st; int idx = -1;
+  LaunchTimer(vtk_ae_s* h_, cudaStream_t st_, int cls) : h(h_), st(st_) {
+    if (!h->timing) return;
+    if ((size_t)(2 * h->ev_used + 2) > h->ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e); }
+      h->ev_cls.push_back(cls);
+    }
+    idx = h->ev_used++;
+    h->ev_cls[idx] = cls;
+    cudaEventRecord(h->ev[2 * idx], st);
+  }
+  ~LaunchTimer() { if (idx >= 0) cudaEventRecord(h->ev[2 * idx + 1], st); }
 };
 
 using namespace vtk;
@@ -304,6 +328,7 @@ int vtk_ae_destroy(vtk_ae_t h) {
   if (!h) return VTK_OK;
   for (int s = 0; s < 2; ++s)
     if (h->side[s].inv_freq) cudaFree(h->side[s].inv_freq);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return VTK_OK;
 }
@@ -341,29 +366,35 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
   const float eps = h->cfg.norm_eps;
   int r;
   if (s.depth > 0) {
-    if ((r = launch_rope_table(row_idx, col_idx, s.inv_freq, w.rope, M, d, st))) return r;
+    { LaunchTimer t(h, st, CLS_MISC); r = launch_rope_table(row_idx, col_idx, s.inv_freq, w.rope, M, d, st); }
+    if (r) return r;
     ++launches;
     if (patch_mask) {
-      if ((r = launch_kv_len(patch_mask, w.kv_len, w.is_prefix, B, N, st))) return r;
+      { LaunchTimer t(h, st, CLS_MISC); r = launch_kv_len(patch_mask, w.kv_len, w.is_prefix, B, N, st); }
+      if (r) return r;
       ++launches;
     }
   }
   for (int i = 0; i < s.depth; ++i) {
     const vtk_block_weights& b = s.blocks[i];
-    if ((r = launch_rmsnorm(w.x, D, (const bf16*)b.norm1, w.h, D, M, D, eps, st))) return r;
+    { LaunchTimer t(h, st, CLS_RMSNORM); r = launch_rmsnorm(w.x, D, (const bf16*)b.norm1, w.h, D, M, D, eps, st); }
+    if (r) return r;
     GemmArgs g1 = base_args(w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
     g1.epi.qkv = w.qkv; g1.epi.ld_qkv = 3 * D; g1.epi.act = w.a2 + D; g1.epi.ld_act = D + Hf;
     g1.epi.normq = (const bf16*)b.norm_q; g1.epi.normk = (const bf16*)b.norm_k; g1.epi.rope = w.rope;
     g1.epi.D = D; g1.epi.d = d; g1.epi.Hf = Hf; g1.epi.qp = qp; g1.epi.eps = eps;
-    if ((r = launch_gemm(EPI_QKV_SWIGLU, g1, st))) return r;
+    { LaunchTimer t(h, st, CLS_QKV_SWIGLU); r = launch_gemm(EPI_QKV_SWIGLU, g1, st); }
+    if (r) return r;
     AttnArgs a;
     a.q = w.qkv; a.k = w.qkv + D; a.v = w.qkv + 2 * D; a.ld_qkv = 3 * D; a.out = w.a2; a.ld_out = D + Hf;
     a.kv_len = patch_mask ? w.kv_len : nullptr; a.key_mask = patch_mask; a.prefix_flag = patch_mask ? w.is_prefix : nullptr;
     a.B = B; a.N = N; a.heads = s.heads; a.d = d; a.zero_invalid_rows = patch_mask ? 1 : 0;
-    if ((r = launch_attention(a, st))) return r;
+    { LaunchTimer t(h, st, CLS_ATTENTION); r = launch_attention(a, st); }
+    if (r) return r;
     GemmArgs g2 = base_args(w.a2, D + Hf, b.w_out, D + Hf, D, M, D, D + Hf);
     g2.epi.out = w.x; g2.epi.ldo = D; g2.epi.gamma = (const bf16*)b.gamma;
-    if ((r = launch_gemm(EPI_RESID, g2, st))) return r;
+    { LaunchTimer t(h, st, CLS_PROJ_RESID); r = launch_gemm(EPI_RESID, g2, st); }
+    if (r) return r;
     launches += 4;
   }
   return 0;
@@ -395,12 +426,15 @@ int vtk_ae_encode(vtk_ae_t h, const void* patches, const int64_t* row_idx, const
   int launches = 0;
   GemmArgs g = base_args(patches, P, s.w_a, P, D, M, D, P);           // patch_embed, ae.py:191
   g.epi.out = w.x; g.epi.ldo = D; g.epi.bias = s.b_a;
-  if ((r = launch_gemm(EPI_BIAS, g, st))) return r;
+  h->ev_used = 0;
+  { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, g, st); }
+  if (r) return r;
   ++launches;
   if ((r = run_blocks(h, s, w, row_idx, col_idx, patch_mask, B, N, st, launches))) return r;
   GemmArgs gz = base_args(w.x, D, s.w_b, D, C, M, C, D);               // to_code + output_fn, ae.py:207
   gz.epi.out = (bf16*)z_out; gz.epi.ldo = C; gz.epi.bias = s.b_b; gz.epi.eps = h->cfg.norm_eps;
-  if ((r = launch_gemm(EPI_BIAS_LN, gz, st))) return r;
+  { LaunchTimer t(h, st, CLS_MISC); r = launch_gemm(EPI_BIAS_LN, gz, st); }
+  if (r) return r;
   ++launches;
   h->last_launches = launches;
   return VTK_OK;
@@ -417,17 +451,43 @@ int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64
   int launches = 0;
   GemmArgs g = base_args(z, C, s.w_a, C, D, M, D, C);                  // decoder_embed, ae.py:220
   g.epi.out = w.x; g.epi.ldo = D; g.epi.bias = s.b_a;
-  if ((r = launch_gemm(EPI_BIAS, g, st))) return r;
+  h->ev_used = 0;
+  { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, g, st); }
+  if (r) return r;
   ++launches;
   if ((r = run_blocks(h, s, w, row_idx, col_idx, patch_mask, B, N, st, launches))) return r;
   GemmArgs gp = base_args(w.x, D, s.w_b, D, P, M, P, D);               // to_pixels, ae.py:242
   gp.epi.out = (bf16*)patches_out; gp.epi.ldo = P; gp.epi.bias = s.b_b;
-  if ((r = launch_gemm(EPI_BIAS, gp, st))) return r;
+  { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, gp, st); }
+  if (r) return r;
   ++launches;
   h->last_launches = launches;
   return VTK_OK;
 }
 
 int vtk_ae_last_launch_count(vtk_ae_t h) { return h ? h->last_launches : 0; }
+
+int vtk_ae_set_timing(vtk_ae_t h, int enable) {
+  VTK_REQUIRE(h, "vtk_ae_set_timing: null handle");
+  h->timing = enable != 0;
+  h->ev_used = 0;
+  return VTK_OK;
+}
+
+int vtk_ae_collect_timing(vtk_ae_t h, float* ms_by_class, int* launches_by_class) {
+  VTK_REQUIRE(h && ms_by_class && launches_by_class, "vtk_ae_collect_timing: null pointer");
+  for (int c = 0; c < CLS_COUNT; ++c) { ms_by_class[c] = 0.f; launches_by_class[c] = 0; }
+  if (h->ev_used == 0) return VTK_OK;
+  int r = check_cuda(cudaEventSynchronize(h->ev[2 * (h->ev_used - 1) + 1]), "cudaEventSynchronize(timing)");
+  if (r) return r;
+  for (int i = 0; i < h->ev_used; ++i) {
+    float ms = 0.f;
+    if ((r = check_cuda(cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]), "cudaEventElapsedTime"))) return r;
+    ms_by_class[h->ev_cls[i]] += ms;
+    launches_by_class[h->ev_cls[i]] += 1;
+  }
+  h->ev_used = 0;
+  return VTK_OK;
+}
 
 }  // extern "C"

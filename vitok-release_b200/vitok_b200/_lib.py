@@ -63,6 +63,8 @@ SIGNATURES = {
     "vtk_ae_encode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "vtk_ae_decode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "vtk_ae_last_launch_count": (c_int, [c_vp]),
+    "vtk_ae_set_timing": (c_int, [c_vp, c_int]),
+    "vtk_ae_collect_timing": (c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_int)]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
