@@ -115,7 +115,7 @@ def test_proj_residual(L, M, D, Hf):
     L.proj_residual(a, w, gamma, x)
     acc = F.linear(a.cpu().float(), w.cpu().float())
     ref = (x0.cpu() + (acc.to(torch.bfloat16) * gamma.cpu()))
-    report(f"proj_residual M={M} D={D}", x, ref.float(), max_abs=6e-2, rel_fro=4e-3)
+    report(f"proj_residual M={M} D={D}", x, ref.float(), max_abs=1.3e-1, rel_fro=4e-3)   # <= 2 bf16 ulp at |x| < 16
 
 
 def test_bad_args_raise(L):
