@@ -4,16 +4,20 @@
 // reference: out = softmax(q k^T / sqrt(d)) v per (image, head), q/k already QK-normed + RoPE'd by the
 // QKV GEMM epilogue.  The reference's sdpa backend masks keys with patch_mask (ae.py:173-187) by
 // materialising a [B,1,N,N] bool mask; here the mask is a per-image key length (padded keys are never
-// loaded -- whole kv tiles past kv_len[b] are skipped) plus an optional per-key byte mask for
-// non-prefix masks.  The flash backend's semantics (no mask) = kv_len null.
+// loaded -- whole kv tiles past kv_len[b] are skipped, padded query tiles exit at once) plus an optional
+// per-key byte mask for non-prefix masks.  The flash backend's semantics (no mask) = kv_len null.
 //
-// One CTA per (128-query tile, head, image), 6 warps:
-//   warp 0 : TMA producer (Q once, K/V tiles of 128 keys, 2-stage ring each)
-//   warp 1 : MMA issuer   S = Q K^T  (128 x 128 x d)  and  O += P V  (128 x d x 128), fp32 in TMEM
-//   warps 2-5 : softmax, one query row per thread (tcgen05.ld 32x32b): online max/sum in fp32, P -> bf16
-//               -> 128B-swizzled smem (A operand of the PV MMA), lazy rescale of O in TMEM.
-// S is double-buffered in TMEM so S_{j+1} is computed while softmax_j runs.
-// V is consumed as an MN-major B operand straight from its natural [key, d] layout (no transpose).
+// One CTA per (256-query block, head, image) = two 128-query tiles A and B that share every K/V tile:
+//   warps 0-3 : softmax warpgroup A   (one query row per thread, TMEM lane = row)
+//   warps 4-7 : softmax warpgroup B
+//   warp  8   : TMA producer (Q_a, Q_b once; K_j / V_j tiles of 128 keys through one smem ring)
+//   warp  9   : MMA issuer: S_x = Q_x K_j^T (128x128xd) and O_x += P_x V_j (128xdx128), fp32 in TMEM
+// Per tile a softmax thread pulls its 128 scores out of TMEM in one batch (so the MMA warp can start
+// S(j+1) immediately), takes the row max, exponentiates with ex2.approx (log2 domain, scale folded into an
+// FFMA), writes P as bf16 into 128B-swizzled shared memory (the A operand of the PV MMA) and rescales O in
+// TMEM only when its running max moved by more than 2^8 (lazy rescale; the stale max cancels in O / l).
+// While warpgroup A exponentiates, the tensor core works for B and vice versa.
+// V is consumed as an MN-major B operand straight from its [key, d] layout (no transpose pass).
 #include <math.h>
 #include <stdio.h>
 
@@ -22,23 +26,24 @@
 
 namespace vtk {
 
-static constexpr int ATT_BQ = 128;   // queries per CTA
+static constexpr int ATT_BQ = 128;   // queries per softmax warpgroup
 static constexpr int ATT_BKV = 128;  // keys per tile
 static constexpr int BLK = 16384;    // one [128 x 64] bf16 swizzled block
+static constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 template <int DH> struct AttnShape {
   static constexpr int NB = DH / 64;               // 64-column blocks per head
-  static constexpr int NP = (DH == 64) ? 2 : 1;    // P buffers
-  static constexpr int Q_BYTES = NB * BLK;
-  static constexpr int KV_BYTES = NB * BLK;        // one K (or V) tile
+  static constexpr int TILE_BYTES = NB * BLK;      // one Q / K / V tile
+  static constexpr int RK = 2;                     // K ring slots
+  static constexpr int RV = (DH == 64) ? 2 : 1;    // V ring slots (227 KB smem budget at d = 128)
   static constexpr int P_BYTES = 2 * BLK;          // 128 x 128 bf16
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + Q_BYTES;
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
-  static constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + NP * P_BYTES;
+  static constexpr int OFF_Q = 0;                  // Q_a, Q_b
+  static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + RK * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + RV * TILE_BYTES;      // P_a, P_b
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr uint32_t TMEM_COLS = 512;       // S0 [0,128) S1 [128,256) O [256, 256+DH)
+  static constexpr uint32_t TMEM_COLS = 512;       // S_a [0,128) S_b [128,256) O_a [256,256+DH) O_b [256+DH, 256+2DH)
 };
 
 struct AttnParams {
@@ -46,15 +51,20 @@ struct AttnParams {
   const int* kv_len; const uint8_t* key_mask; const int* prefix_flag;
   int N, heads, zero_invalid;
   float scale_log2;   // (1/sqrt(d)) * log2(e)
-  int q_col0, k_col0, v_col0;  // column offsets of head 0 inside the respective tensor maps
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int DH>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using S = AttnShape<DH>;
-  const int q0 = blockIdx.x * ATT_BQ;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const int warp = threadIdx.x >> 5;
@@ -63,19 +73,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   int kvlen = p.kv_len ? p.kv_len[img] : N;
   kvlen = kvlen < N ? kvlen : N;
   const long long row0 = (long long)img * N;
-
   const int T = (kvlen + ATT_BKV - 1) / ATT_BKV;
-  if (T == 0 || (p.zero_invalid && q0 >= kvlen)) {
-    // nothing to attend to (padded query tile / empty image): define the output as 0
-    if (warp >= 2) {
-      const int r = ((warp & 3) << 5) + lane;
-      if (q0 + r < N) {
-        bf16* op = p.out + (row0 + q0 + r) * p.ld_out + head * DH;
+  const int qlimit = p.zero_invalid ? kvlen : N;           // query rows >= qlimit are padding
+  const int nact = (T == 0 || q0 >= qlimit) ? 0 : ((q0 + ATT_BQ < qlimit) ? 2 : 1);
+
+  // query tiles with nothing to attend to: define the output as 0 (uniform per warpgroup)
+  if (warp < 8) {
+    const int wg = warp >> 2;
+    if (wg >= nact) {
+      const int qi = q0 + wg * ATT_BQ + (warp & 3) * 32 + lane;
+      if (qi < N) {
+        bf16* op = p.out + (row0 + qi) * p.ld_out + head * DH;
         for (int c = 0; c < DH; c += 8) st_global_v4(op + c, 0u, 0u, 0u, 0u);
       }
     }
-    return;
   }
+  if (nact == 0) return;   // whole CTA
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,18 +98,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint8_t* sP = smem + S::OFF_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* s_empty = bars + 11;  // [2]
-  uint64_t* p_full = bars + 13;   // [2]
-  uint64_t* p_empty = bars + 15;  // [2]
-  uint64_t* o_done = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* k_full = bars + 1;               // [2]
+  uint64_t* k_empty = bars + 3;              // [2]
+  uint64_t* v_full = bars + 5;               // [2]
+  uint64_t* v_empty = bars + 7;              // [2]
+  uint64_t* s_full = bars + 9;               // [2]
+  uint64_t* s_empty = s_full + 2;            // [2]
+  uint64_t* p_full = s_full + 4;             // [2]
+  uint64_t* pv_done = s_full + 6;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
-  if (warp == 1 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -109,12 +121,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 128);
       mbar_init(&p_full[i], 128);
-      mbar_init(&p_empty[i], 1);
+      mbar_init(&pv_done[i], 1);
     }
-    mbar_init(o_done, 1);
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 8) {
     tmem_alloc(tmem_slot, S::TMEM_COLS);
     tmem_relinquish();
   }
@@ -122,190 +133,213 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;          // + 128 * buffer
-  const uint32_t tmem_O = tmem_base + 256;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       // ===== TMA producer =====
-      mbar_expect_tx(q_full, S::Q_BYTES);
-      for (int nb = 0; nb < S::NB; ++nb)
-        tma_load_2d(sQ + nb * BLK, &tmQ, q_full, p.q_col0 + head * DH + nb * 64, (int)(row0 + q0));
+      mbar_expect_tx(q_full, (uint32_t)(nact * S::TILE_BYTES));
+      for (int t = 0; t < nact; ++t)
+        for (int nb = 0; nb < S::NB; ++nb)
+          tma_load_2d(sQ + t * S::TILE_BYTES + nb * BLK, &tmQ, q_full, head * DH + nb * 64, (int)(row0 + q0 + t * ATT_BQ));
+      // issue order K_0, K_1, V_0, K_2, V_1, ...: K_{j+1} is needed (for S(j+1)) before V_j (for PV(j))
+      auto load_k = [&](int j) {
+        const int slot = j % S::RK;
+        mbar_wait(&k_empty[slot], ((uint32_t)(j / S::RK) & 1u) ^ 1u);
+        mbar_expect_tx(&k_full[slot], S::TILE_BYTES);
+        for (int nb = 0; nb < S::NB; ++nb)
+          tma_load_2d(sK + slot * S::TILE_BYTES + nb * BLK, &tmK, &k_full[slot], head * DH + nb * 64,
+                      (int)(row0 + (long long)j * ATT_BKV));
+      };
+      load_k(0);
       for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t use_ph = (uint32_t)(j >> 1) & 1u;
-        const int krow = (int)(row0 + (long long)j * ATT_BKV);
-        mbar_wait(&k_empty[st], use_ph ^ 1);
-        mbar_expect_tx(&k_full[st], S::KV_BYTES);
+        if (j + 1 < T) load_k(j + 1);
+        const int slot = j % S::RV;
+        mbar_wait(&v_empty[slot], ((uint32_t)(j / S::RV) & 1u) ^ 1u);
+        mbar_expect_tx(&v_full[slot], S::TILE_BYTES);
         for (int nb = 0; nb < S::NB; ++nb)
-          tma_load_2d(sK + st * S::KV_BYTES + nb * BLK, &tmK, &k_full[st], p.k_col0 + head * DH + nb * 64, krow);
-        mbar_wait(&v_empty[st], use_ph ^ 1);
-        mbar_expect_tx(&v_full[st], S::KV_BYTES);
-        for (int nb = 0; nb < S::NB; ++nb)
-          tma_load_2d(sV + st * S::KV_BYTES + nb * BLK, &tmV, &v_full[st], p.v_col0 + head * DH + nb * 64, krow);
+          tma_load_2d(sV + slot * S::TILE_BYTES + nb * BLK, &tmV, &v_full[slot], head * DH + nb * 64,
+                      (int)(row0 + (long long)j * ATT_BKV));
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, DH, 0, 1);   // B (= V) is MN-major
-      auto issue_pv = [&](int i) {
-        const int pb = i % S::NP;
-        const int vs = i & 1;
-        mbar_wait(&p_full[pb], (uint32_t)(i / S::NP) & 1u);
-        mbar_wait(&v_full[vs], (uint32_t)(i >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP + pb * S::P_BYTES);
-        const uint32_t va = smem_u32(sV + vs * S::KV_BYTES);
+      auto k_wait = [&](int j) {
+        mbar_wait(&k_full[j % S::RK], (uint32_t)(j / S::RK) & 1u);
+        return smem_u32(sK + (j % S::RK) * S::TILE_BYTES);
+      };
+      auto v_wait = [&](int j) {
+        mbar_wait(&v_full[j % S::RV], (uint32_t)(j / S::RV) & 1u);
+        return smem_u32(sV + (j % S::RV) * S::TILE_BYTES);
+      };
+      auto issue_s = [&](int q, uint32_t ka) {
+        const uint32_t qa = smem_u32(sQ + q * S::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * BLK + (kk & 3) * 32;
+          umma_bf16_ss(tmem_base + q * 128, make_desc_kmajor_sw128(qa + off), make_desc_kmajor_sw128(ka + off), idesc_s,
+                       kk != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[q]);
+      };
+      auto issue_pv = [&](int q, int j, uint32_t va) {
+        const uint32_t pa = smem_u32(sP + q * S::P_BYTES);
 #pragma unroll
         for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
           const uint64_t adesc = make_desc_kmajor_sw128(pa + (kk >> 2) * BLK + (kk & 3) * 32);
           // V tile: NB blocks of [128 keys x 64 d]; MN-major: LBO = block stride, SBO = 8-key group stride
           const uint64_t bdesc = make_smem_desc(va + kk * 2048, BLK, 1024, 2);
-          umma_bf16_ss(tmem_O, adesc, bdesc, idesc_o, (i | kk) != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_base + 256 + q * DH, adesc, bdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
         }
-        umma_commit(&v_empty[vs]);
-        umma_commit(&p_empty[pb]);
-        umma_commit(o_done);
+        umma_commit(&pv_done[q]);
       };
       mbar_wait(q_full, 0);
-      for (int j = 0; j < T; ++j) {
-        const int sb = j & 1;
-        const uint32_t use_ph = (uint32_t)(j >> 1) & 1u;
-        mbar_wait(&k_full[sb], use_ph);
-        mbar_wait(&s_empty[sb], use_ph ^ 1);
+      {
+        const uint32_t ka = k_wait(0);
         tc_fence_after();
-        const uint32_t qa = smem_u32(sQ);
-        const uint32_t ka = smem_u32(sK + sb * S::KV_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * BLK + (kk & 3) * 32;
-          umma_bf16_ss(tmem_S + sb * 128, make_desc_kmajor_sw128(qa + off), make_desc_kmajor_sw128(ka + off), idesc_s,
-                       kk != 0 ? 1u : 0u);
-        }
-        umma_commit(&s_full[sb]);
-        umma_commit(&k_empty[sb]);
-        if (j > 0) issue_pv(j - 1);
+        for (int q = 0; q < nact; ++q) issue_s(q, ka);
+        umma_commit(&k_empty[0]);
       }
-      issue_pv(T - 1);
+      for (int j = 0; j < T; ++j) {
+        const uint32_t jp = (uint32_t)j & 1u;
+        if (j + 1 < T) {   // S(j+1) as soon as the softmax threads have pulled S(j) into registers
+          const uint32_t ka = k_wait(j + 1);
+          for (int q = 0; q < nact; ++q) {
+            mbar_wait(&s_empty[q], jp);
+            tc_fence_after();
+            issue_s(q, ka);
+          }
+          umma_commit(&k_empty[(j + 1) % S::RK]);
+        }
+        const uint32_t va = v_wait(j);
+        for (int q = 0; q < nact; ++q) {
+          mbar_wait(&p_full[q], jp);
+          tc_fence_after();
+          issue_pv(q, j, va);
+        }
+        umma_commit(&v_empty[j % S::RV]);
+      }
     }
-  } else {
-    // ===== softmax (warps 2..5): thread <-> query row =====
+  } else if ((warp >> 2) < nact) {
+    // ===== softmax warpgroups: thread <-> query row =====
+    const int q = warp >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + q * 128;
+    const uint32_t tO = tmem_base + lane_base + 256 + q * DH;
     const bool general_mask = p.key_mask != nullptr && !(p.prefix_flag != nullptr && p.prefix_flag[img] != 0);
     const uint8_t* kmask = general_mask ? p.key_mask + row0 : nullptr;
+    uint8_t* prow = sP + q * S::P_BYTES + r * 128;
+    const float sc = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < T; ++j) {
-      const int sb = j & 1;
       const int kv0 = j * ATT_BKV;
       const bool need_mask = (kv0 + ATT_BKV > kvlen) || (kmask != nullptr);
-      mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1u);
+      mbar_wait(&s_full[q], (uint32_t)j & 1u);
       __syncwarp();
       tc_fence_after();
-      const uint32_t ts = tmem_S + lane_base + sb * 128;
-      // pass 1: row max
-      float mx = -INFINITY;
-      for (int c = 0; c < ATT_BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(ts + c, v);
-        tmem_wait_ld();
-        if (need_mask) {
+      uint32_t v[4][32];
+      tmem_ld32(tS + 0, v[0]);
+      tmem_ld32(tS + 32, v[1]);
+      tmem_ld32(tS + 64, v[2]);
+      tmem_ld32(tS + 96, v[3]);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&s_empty[q]);   // S is in registers: the tensor core may overwrite it with S(j+1)
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int kc = kv0 + c + i;
+            const int kc = kv0 + c * 32 + i;
             const bool ok = kc < kvlen && (kmask == nullptr || kmask[kc] != 0);
-            mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
+            if (!ok) v[c][i] = 0xff800000u;   // -inf
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);   // m_run = -inf -> 0
-      // P buffer free?
-      const int pb = j % S::NP;
-      mbar_wait(&p_empty[pb], ((uint32_t)(j / S::NP) & 1u) ^ 1u);
-      __syncwarp();
-      uint8_t* prow = sP + pb * S::P_BYTES + r * 128;
-      float rowsum = 0.f;
-      for (int c = 0; c < ATT_BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(ts + c, v);
-        tmem_wait_ld();
-        uint32_t o[16];
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[1][i]));
+        mx2 = fmaxf(mx2, __uint_as_float(v[2][i]));
+        mx3 = fmaxf(mx3, __uint_as_float(v[3][i]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+      // lazy rescale: keep the stale max unless it moved by more than 2^8
+      float m_use = m_run, alpha = 1.f;
+      if (m_tile > m_run + RESCALE_THRESHOLD || m_run == -INFINITY) {
+        m_use = fmaxf(m_run, m_tile);
+        alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_use);
+      }
+      const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float e0 = exp2f(__uint_as_float(v[2 * i]) * p.scale_log2 - m_use);
-          float e1 = exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - m_use);
-          if (need_mask) {
-            const int kc = kv0 + c + 2 * i;
-            if (!(kc < kvlen && (kmask == nullptr || kmask[kc] != 0))) e0 = 0.f;
-            if (!(kc + 1 < kvlen && (kmask == nullptr || kmask[kc + 1] != 0))) e1 = 0.f;
-          }
-          rowsum += e0 + e1;
-          o[i] = pack_bf16x2(e0, e1);
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), sc, -m_sub));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), sc, -m_sub));
+          sum0 += e0;
+          sum1 += e1;
+          pk[c * 16 + i] = pack_bf16x2(e0, e1);
         }
-        // 32 columns = 4 chunks of 16 B; swizzle-128B: chunk' = chunk ^ (row & 7)
-        uint8_t* pblk = prow + (c >> 6) * BLK;
-        const int ch0 = (c & 63) >> 3;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int ch = (ch0 + g) ^ (r & 7);
-          *reinterpret_cast<uint4*>(pblk + (ch << 4)) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&s_empty[sb]);   // S buffer consumed
-      l_run = l_run * alpha + rowsum;
-      m_run = m_new;
-      // rescale O (needs PV_{j-1} complete)
+      l_run = l_run * alpha + (sum0 + sum1);
+      m_run = m_use;
+      // P buffer and O are free once PV(j-1) has completed
       if (j > 0) {
-        mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
+        mbar_wait(&pv_done[q], (uint32_t)(j - 1) & 1u);
         __syncwarp();
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
-          for (int c = 0; c < DH; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_O + lane_base + c, v);
-            tmem_wait_ld();
+      }
+      // 128 columns = 2 blocks x 8 chunks of 16 B; swizzle-128B: chunk' = chunk ^ (row & 7)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(tmem_O + lane_base + c, v);
-          }
-          tmem_wait_st();
+      for (int g = 0; g < 16; ++g) {
+        const int blk = g >> 3, ch = (g & 7) ^ (r & 7);
+        *reinterpret_cast<uint4*>(prow + blk * BLK + (ch << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      }
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+        for (int c = 0; c < DH; c += 32) {
+          uint32_t o[32];
+          tmem_ld32(tO + c, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tO + c, o);
         }
+        tmem_wait_st();
       }
       fence_proxy_async_smem();   // P (generic-proxy smem writes) -> visible to the MMA (async proxy)
       tc_fence_before();
-      mbar_arrive(&p_full[pb]);
+      mbar_arrive(&p_full[q]);
     }
     // epilogue: O / l
-    mbar_wait(o_done, (uint32_t)(T - 1) & 1u);
+    mbar_wait(&pv_done[q], (uint32_t)(T - 1) & 1u);
     __syncwarp();
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    const int qi = q0 + r;
+    const int qi = q0 + q * ATT_BQ + r;
     bool zero_row = false;
     if (p.zero_invalid) zero_row = (qi >= kvlen) || (kmask != nullptr && qi < N && kmask[qi] == 0);
-    const float sc = zero_row ? 0.f : inv;
+    const float osc = zero_row ? 0.f : inv;
     bf16* op = p.out + (row0 + qi) * p.ld_out + head * DH;
+#pragma unroll
     for (int c = 0; c < DH; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_O + lane_base + c, v);
+      uint32_t o[32];
+      tmem_ld32(tO + c, o);
       tmem_wait_ld();
       if (qi < N) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint32_t o[4];
+          uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            o[i] = pack_bf16x2(__uint_as_float(v[8 * g + 2 * i]) * sc, __uint_as_float(v[8 * g + 2 * i + 1]) * sc);
-          st_global_v4(op + c + 8 * g, o[0], o[1], o[2], o[3]);
+            w[i] = pack_bf16x2(__uint_as_float(o[8 * g + 2 * i]) * osc, __uint_as_float(o[8 * g + 2 * i + 1]) * osc);
+          st_global_v4(op + c + 8 * g, w[0], w[1], w[2], w[3]);
         }
       }
     }
@@ -313,7 +347,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, S::TMEM_COLS);
   }
@@ -333,7 +367,6 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   p.kv_len = a.kv_len; p.key_mask = a.key_mask; p.prefix_flag = a.prefix_flag;
   p.N = a.N; p.heads = a.heads; p.zero_invalid = a.zero_invalid_rows;
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
-  p.q_col0 = p.k_col0 = p.v_col0 = 0;
   auto kern = attn_kernel<DH>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -342,8 +375,8 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
       return -1;
     attr_set = true;
   }
-  dim3 grid((a.N + ATT_BQ - 1) / ATT_BQ, a.heads, a.B);
-  kern<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  dim3 grid((a.N + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a.heads, a.B);
+  kern<<<grid, 320, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   return check_cuda(cudaGetLastError(), "attention launch");
 }
 

@@ -62,8 +62,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > VTK_WAIT_LIMIT_CYCLES) {
+#ifdef VTK_DEBUG_WAIT
       printf("vtk: mbarrier wait timeout (block %d,%d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
