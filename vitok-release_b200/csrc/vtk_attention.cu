@@ -108,7 +108,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* pv_done = s_full + 6;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
-  if (warp == 9 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -125,9 +125,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     }
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, S::TMEM_COLS);
     tmem_relinquish();
+  }
+  if (warp == 8 && lane == 0) {
+    // Q tiles and K_0 go out before the CTA-wide sync: their latency overlaps the TMEM allocation
+    mbar_expect_tx(q_full, (uint32_t)(nact * S::TILE_BYTES));
+    for (int t = 0; t < nact; ++t)
+      for (int nb = 0; nb < S::NB; ++nb)
+        tma_load_2d(sQ + t * S::TILE_BYTES + nb * BLK, &tmQ, q_full, head * DH + nb * 64, (int)(row0 + q0 + t * ATT_BQ));
+    mbar_expect_tx(&k_full[0], S::TILE_BYTES);
+    for (int nb = 0; nb < S::NB; ++nb)
+      tma_load_2d(sK + nb * BLK, &tmK, &k_full[0], head * DH + nb * 64, (int)row0);
   }
   tc_fence_before();
   __syncthreads();
@@ -136,11 +146,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   if (warp == 8) {
     if (lane == 0) {
-      // ===== TMA producer =====
-      mbar_expect_tx(q_full, (uint32_t)(nact * S::TILE_BYTES));
-      for (int t = 0; t < nact; ++t)
-        for (int nb = 0; nb < S::NB; ++nb)
-          tma_load_2d(sQ + t * S::TILE_BYTES + nb * BLK, &tmQ, q_full, head * DH + nb * 64, (int)(row0 + q0 + t * ATT_BQ));
+      // ===== TMA producer ===== (Q and K_0 were issued before the sync)
       // issue order K_0, K_1, V_0, K_2, V_1, ...: K_{j+1} is needed (for S(j+1)) before V_j (for PV(j))
       auto load_k = [&](int j) {
         const int slot = j % S::RK;
@@ -150,7 +156,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           tma_load_2d(sK + slot * S::TILE_BYTES + nb * BLK, &tmK, &k_full[slot], head * DH + nb * 64,
                       (int)(row0 + (long long)j * ATT_BKV));
       };
-      load_k(0);
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) load_k(j + 1);
         const int slot = j % S::RV;
@@ -285,7 +290,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           const float e1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), sc, -m_sub));
           sum0 += e0;
           sum1 += e1;
-          pk[c * 16 + i] = pack_bf16x2(e0, e1);
+          // bf16 round-to-nearest (ties up) on the integer pipe: keeps the XU pipe for ex2 only
+          pk[c * 16 + i] = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);
         }
       l_run = l_run * alpha + (sum0 + sum1);
       m_run = m_use;
@@ -327,27 +333,28 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (p.zero_invalid) zero_row = (qi >= kvlen) || (kmask != nullptr && qi < N && kmask[qi] == 0);
     const float osc = zero_row ? 0.f : inv;
     bf16* op = p.out + (row0 + qi) * p.ld_out + head * DH;
+    uint32_t o[DH / 32][32];
 #pragma unroll
-    for (int c = 0; c < DH; c += 32) {
-      uint32_t o[32];
-      tmem_ld32(tO + c, o);
-      tmem_wait_ld();
-      if (qi < N) {
+    for (int c = 0; c < DH / 32; ++c) tmem_ld32(tO + c * 32, o[c]);
+    tmem_wait_ld();
+    if (qi < N) {
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            w[i] = pack_bf16x2(__uint_as_float(o[8 * g + 2 * i]) * osc, __uint_as_float(o[8 * g + 2 * i + 1]) * osc);
-          st_global_v4(op + c + 8 * g, w[0], w[1], w[2], w[3]);
+            w[i] = pack_bf16x2(__uint_as_float(o[c][8 * g + 2 * i]) * osc, __uint_as_float(o[c][8 * g + 2 * i + 1]) * osc);
+          st_global_v4(op + c * 32 + 8 * g, w[0], w[1], w[2], w[3]);
         }
-      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 9) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, S::TMEM_COLS);
   }

@@ -7,7 +7,8 @@
 //   warp 1   : MMA issuer    -- one lane issues tcgen05.mma (128 x {256|128} x 16), commits to mbarriers
 //   warp 2   : TMEM allocator (2 accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
 //   warp 3   : idle
-//   warps 4..: epilogue      -- tcgen05.ld (32x32b: one accumulator row per thread), fused math, 16-byte stores
+//   warps 4..: epilogue      -- 8 or 16 warps; tcgen05.ld (32x32b: one accumulator row per thread), fused math,
+//                               16-byte stores
 //
 // Tile scheduler: static persistent, m fastest (concurrent CTAs share the same weight rows in L2).  When the
 // last wave would be less than half full, its tiles are split into half-width tiles (UMMA N = BN/2) so the
@@ -40,52 +41,79 @@ template <int BN> struct GemmShape {
 };
 
 struct TileSched {
-  int num_m, full_tiles, total_tiles, bn;
-  // full_tiles big tiles, then (total_tiles - full_tiles) half-width tiles
+  int num_m, num_n, gm, full_tiles, total_tiles, bn;
+  // Big tiles are visited in bands of `gm` row-tiles: inside a band m is fastest and n sweeps all column
+  // tiles, so the band's A panel (gm x 128 x K) stays L2-resident while the weights stream through once
+  // per band.  full_tiles big tiles, then (total_tiles - full_tiles) half-width tiles.
+  __device__ __forceinline__ void big(int t, int& mi, int& ni) const {
+    const int band_tiles = gm * num_n;
+    const int band = t / band_tiles;
+    const int r = t - band * band_tiles;
+    const int rows = min(gm, num_m - band * gm);   // the last band may be short
+    ni = r / rows;
+    mi = band * gm + (r - ni * rows);
+  }
   __device__ __forceinline__ void decode(int t, int& m0, int& n0, int& width) const {
+    int mi, ni;
     if (t < full_tiles) {
-      m0 = (t % num_m) * BM;
-      n0 = (t / num_m) * bn;
+      big(t, mi, ni);
+      m0 = mi * BM;
+      n0 = ni * bn;
       width = bn;
     } else {
-      int u = t - full_tiles;
-      int bt = full_tiles + (u >> 1);
-      m0 = (bt % num_m) * BM;
-      n0 = (bt / num_m) * bn + (u & 1) * (bn >> 1);
+      const int u = t - full_tiles;
+      big(full_tiles + (u >> 1), mi, ni);
+      m0 = mi * BM;
+      n0 = ni * bn + (u & 1) * (bn >> 1);
       width = bn >> 1;
     }
   }
 };
 
 // ------------------------------------------------------------------------------------------------
-// epilogue bodies: one "unit" = U consecutive accumulator columns of this thread's row
+// epilogue bodies.  One accumulator row per thread; work is done in 16-column chunks so that 16 epilogue
+// warps (96 registers/thread) fit next to the 4 control warps.  Global operands (bias, gamma, RoPE table,
+// norm weights, residual) are requested BEFORE the TMEM load so both latencies overlap.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_bf16x8(const bf16* p, float (&f)[8]) {
   uint4 v = ld_global_nc_v4(p);
   f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
   f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
 }
+__device__ __forceinline__ float u4_lo(const uint4& v, int i) {   // element 2i of 8 packed bf16
+  const uint32_t w = i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+  return bf16_lo(w);
+}
+__device__ __forceinline__ float u4_hi(const uint4& v, int i) {   // element 2i+1
+  const uint32_t w = i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+  return bf16_hi(w);
+}
 
 // out = bf16(acc + bias)
 __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
                                               int ucols) {
-  for (int cc = 0; cc < ucols; cc += 32) {
-    if (n + cc >= N) break;  // warp-uniform
-    uint32_t r[32];
-    tmem_ld32(taddr + cc, r);
+  for (int cc = 0; cc < ucols; cc += 16) {
+    const int col = n + cc;
+    if (col >= N) break;  // warp-uniform
+    uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
+    const bool second = col + 8 < N;
+    if (p.bias) {
+      b0 = ld_global_nc_v4(p.bias + col);
+      if (second) b1 = ld_global_nc_v4(p.bias + col + 8);
+    }
+    uint32_t r[16];
+    tmem_ld16(taddr + cc, r);
     tmem_wait_ld();
+    if (row_ok) {
+      uint32_t o[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int col = n + cc + 8 * g;
-      if (col < N && row_ok) {
-        float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (p.bias) load_bf16x8(p.bias + col, b);
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          o[i] = pack_bf16x2(__uint_as_float(r[8 * g + 2 * i]) + b[2 * i], __uint_as_float(r[8 * g + 2 * i + 1]) + b[2 * i + 1]);
-        st_global_v4(p.out + (long long)row * p.ldo + col, o[0], o[1], o[2], o[3]);
+      for (int i = 0; i < 4; ++i) {
+        o[i] = pack_bf16x2(__uint_as_float(r[2 * i]) + u4_lo(b0, i), __uint_as_float(r[2 * i + 1]) + u4_hi(b0, i));
+        o[4 + i] = pack_bf16x2(__uint_as_float(r[8 + 2 * i]) + u4_lo(b1, i), __uint_as_float(r[8 + 2 * i + 1]) + u4_hi(b1, i));
       }
+      bf16* op = p.out + (long long)row * p.ldo + col;
+      st_global_v4(op, o[0], o[1], o[2], o[3]);
+      if (second) st_global_v4(op + 8, o[4], o[5], o[6], o[7]);
     }
   }
 }
@@ -93,34 +121,34 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
 // x = bf16(x + bf16(bf16(acc) * gamma)), in place
 __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
                                                int ucols) {
-  for (int cc = 0; cc < ucols; cc += 32) {
-    if (n + cc >= N) break;
-    uint4 xv[4];
-    bf16* xp = p.out + (long long)row * p.ldo + n + cc;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      xv[g] = make_uint4(0, 0, 0, 0);
-      if (row_ok && n + cc + 8 * g < N) xv[g] = ld_global_v4(xp + 8 * g);
+  for (int cc = 0; cc < ucols; cc += 16) {
+    const int col = n + cc;
+    if (col >= N) break;
+    const bool second = col + 8 < N;
+    bf16* xp = p.out + (long long)row * p.ldo + col;
+    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = make_uint4(0, 0, 0, 0);
+    if (row_ok) {
+      x0 = ld_global_v4(xp);
+      if (second) x1 = ld_global_v4(xp + 8);
     }
-    uint32_t r[32];
-    tmem_ld32(taddr + cc, r);
+    const uint4 g0 = ld_global_nc_v4(p.gamma + col);
+    const uint4 g1 = second ? ld_global_nc_v4(p.gamma + col + 8) : make_uint4(0, 0, 0, 0);
+    uint32_t r[16];
+    tmem_ld16(taddr + cc, r);
     tmem_wait_ld();
+    if (row_ok) {
+      uint32_t o[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int col = n + cc + 8 * g;
-      if (col < N && row_ok) {
-        float gm[8];
-        load_bf16x8(p.gamma + col, gm);
-        const uint32_t xin[4] = {xv[g].x, xv[g].y, xv[g].z, xv[g].w};
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float a0 = bf16r(bf16r(__uint_as_float(r[8 * g + 2 * i])) * gm[2 * i]);
-          float a1 = bf16r(bf16r(__uint_as_float(r[8 * g + 2 * i + 1])) * gm[2 * i + 1]);
-          o[i] = pack_bf16x2(bf16_lo(xin[i]) + a0, bf16_hi(xin[i]) + a1);
-        }
-        st_global_v4(xp + 8 * g, o[0], o[1], o[2], o[3]);
+      for (int i = 0; i < 4; ++i) {
+        float a0 = bf16r(bf16r(__uint_as_float(r[2 * i])) * u4_lo(g0, i));
+        float a1 = bf16r(bf16r(__uint_as_float(r[2 * i + 1])) * u4_hi(g0, i));
+        o[i] = pack_bf16x2(u4_lo(x0, i) + a0, u4_hi(x0, i) + a1);
+        float c0 = bf16r(bf16r(__uint_as_float(r[8 + 2 * i])) * u4_lo(g1, i));
+        float c1 = bf16r(bf16r(__uint_as_float(r[8 + 2 * i + 1])) * u4_hi(g1, i));
+        o[4 + i] = pack_bf16x2(u4_lo(x1, i) + c0, u4_hi(x1, i) + c1);
       }
+      st_global_v4(xp, o[0], o[1], o[2], o[3]);
+      if (second) st_global_v4(xp + 8, o[4], o[5], o[6], o[7]);
     }
   }
 }
@@ -130,24 +158,24 @@ __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t tadd
 __device__ __forceinline__ void epi_bias_ln_row(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int N) {
   float sum = 0.f;
   for (int c = 0; c < N; c += 16) {
-    uint32_t r[16];
-    tmem_ld16(taddr + c, r);
-    tmem_wait_ld();
     float b[16];
     load_bf16x8(p.bias + c, *reinterpret_cast<float(*)[8]>(&b[0]));
     load_bf16x8(p.bias + c + 8, *reinterpret_cast<float(*)[8]>(&b[8]));
+    uint32_t r[16];
+    tmem_ld16(taddr + c, r);
+    tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) sum += bf16r(__uint_as_float(r[i]) + b[i]);
   }
   const float mean = sum / (float)N;
   float var = 0.f;
   for (int c = 0; c < N; c += 16) {
-    uint32_t r[16];
-    tmem_ld16(taddr + c, r);
-    tmem_wait_ld();
     float b[16];
     load_bf16x8(p.bias + c, *reinterpret_cast<float(*)[8]>(&b[0]));
     load_bf16x8(p.bias + c + 8, *reinterpret_cast<float(*)[8]>(&b[8]));
+    uint32_t r[16];
+    tmem_ld16(taddr + c, r);
+    tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       float dv = bf16r(__uint_as_float(r[i]) + b[i]) - mean;
@@ -156,12 +184,12 @@ __device__ __forceinline__ void epi_bias_ln_row(const EpiParams& p, uint32_t tad
   }
   const float rstd = rsqrtf(var / (float)N + p.eps);
   for (int c = 0; c < N; c += 16) {
-    uint32_t r[16];
-    tmem_ld16(taddr + c, r);
-    tmem_wait_ld();
     float b[16];
     load_bf16x8(p.bias + c, *reinterpret_cast<float(*)[8]>(&b[0]));
     load_bf16x8(p.bias + c + 8, *reinterpret_cast<float(*)[8]>(&b[8]));
+    uint32_t r[16];
+    tmem_ld16(taddr + c, r);
+    tmem_wait_ld();
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -183,47 +211,43 @@ __device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, 
                                             int ncol, const bf16* w) {
   const int d = p.d;
   float ss = 0.f;
-  for (int cc = 0; cc < d; cc += 32) {
-    uint32_t r[32];
-    tmem_ld32(taddr + cc, r);
+  for (int cc = 0; cc < d; cc += 32) {   // two 16-column loads in flight per wait
+    uint32_t r0[16], r1[16];
+    tmem_ld16(taddr + cc, r0);
+    tmem_ld16(taddr + cc + 16, r1);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float t = bf16r(__uint_as_float(r[i]));
-      ss += t * t;
+    for (int i = 0; i < 16; ++i) {
+      const float t0 = bf16r(__uint_as_float(r0[i])), t1 = bf16r(__uint_as_float(r1[i]));
+      ss = fmaf(t0, t0, ss);
+      ss = fmaf(t1, t1, ss);
     }
   }
   const float rstd = rsqrtf(ss / (float)d + p.eps);
   const bf16* rope = p.rope + (long long)rrow * d;
-  for (int cc = 0; cc < d; cc += 32) {
-    uint32_t r[32];
-    tmem_ld32(taddr + cc, r);
+  bf16* op = p.qkv + (long long)row * p.ld_qkv + ncol;
+  for (int cc = 0; cc < d; cc += 16) {
+    const uint4 cs = ld_global_nc_v4(rope + (cc >> 1));              // 8 cos (pairs cc/2 .. cc/2+7)
+    const uint4 sn = ld_global_nc_v4(rope + (d >> 1) + (cc >> 1));   // 8 sin
+    const uint4 w0 = ld_global_nc_v4(w + cc);
+    const uint4 w1 = ld_global_nc_v4(w + cc + 8);
+    uint32_t r[16];
+    tmem_ld16(taddr + cc, r);
     tmem_wait_ld();
-    float cs[16], sn[16];
-    load_bf16x8(rope + (cc >> 1), *reinterpret_cast<float(*)[8]>(&cs[0]));
-    load_bf16x8(rope + (cc >> 1) + 8, *reinterpret_cast<float(*)[8]>(&cs[8]));
-    load_bf16x8(rope + (d >> 1) + (cc >> 1), *reinterpret_cast<float(*)[8]>(&sn[0]));
-    load_bf16x8(rope + (d >> 1) + (cc >> 1) + 8, *reinterpret_cast<float(*)[8]>(&sn[8]));
-    uint32_t o[16];
+    uint32_t o[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float wv[8];
-      load_bf16x8(w + cc + 8 * g, wv);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int e = 8 * g + 2 * i;   // even column of the pair within this 32-chunk
-        const int pi = e >> 1;         // pair index within chunk
-        float y0 = bf16r(bf16r(__uint_as_float(r[e])) * rstd * wv[2 * i]);
-        float y1 = bf16r(bf16r(__uint_as_float(r[e + 1])) * rstd * wv[2 * i + 1]);
-        float o0 = bf16r(y0 * cs[pi]) - bf16r(y1 * sn[pi]);
-        float o1 = bf16r(y0 * sn[pi]) + bf16r(y1 * cs[pi]);
-        o[pi] = pack_bf16x2(o0, o1);
-      }
+    for (int i = 0; i < 8; ++i) {   // pair i of this chunk = columns 2i, 2i+1
+      const float we = (i < 4) ? u4_lo(w0, i) : u4_lo(w1, i - 4);
+      const float wo = (i < 4) ? u4_hi(w0, i) : u4_hi(w1, i - 4);
+      const float c = (i & 1) ? u4_hi(cs, i >> 1) : u4_lo(cs, i >> 1);
+      const float sv = (i & 1) ? u4_hi(sn, i >> 1) : u4_lo(sn, i >> 1);
+      const float y0 = bf16r(bf16r(__uint_as_float(r[2 * i])) * rstd * we);
+      const float y1 = bf16r(bf16r(__uint_as_float(r[2 * i + 1])) * rstd * wo);
+      o[i] = pack_bf16x2(bf16r(y0 * c) - bf16r(y1 * sv), bf16r(y0 * sv) + bf16r(y1 * c));
     }
     if (row_ok) {
-      bf16* op = p.qkv + (long long)row * p.ld_qkv + ncol + cc;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) st_global_v4(op + 8 * g, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+      st_global_v4(op + cc, o[0], o[1], o[2], o[3]);
+      st_global_v4(op + cc + 8, o[4], o[5], o[6], o[7]);
     }
   }
 }
@@ -237,20 +261,17 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
       if (ncol >= threeD) break;  // zero-padded columns between 3D and qp
       const int seg = ncol / p.D;
       if (seg == 2) {  // V: plain bf16 copy
-        for (int cc = 0; cc < p.d; cc += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + hc + cc, r);
+        bf16* op = p.qkv + (long long)row * p.ld_qkv + ncol;
+        for (int cc = 0; cc < p.d; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + hc + cc, r);
           tmem_wait_ld();
           if (row_ok) {
-            bf16* op = p.qkv + (long long)row * p.ld_qkv + ncol + cc;
+            uint32_t o[8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t o[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = pack_bf16x2(__uint_as_float(r[8 * g + 2 * i]), __uint_as_float(r[8 * g + 2 * i + 1]));
-              st_global_v4(op + 8 * g, o[0], o[1], o[2], o[3]);
-            }
+            for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            st_global_v4(op + cc, o[0], o[1], o[2], o[3]);
+            st_global_v4(op + cc + 8, o[4], o[5], o[6], o[7]);
           }
         }
       } else {
@@ -263,16 +284,17 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
     for (int cc = 0; cc < ucols; cc += 32) {
       const int j = (n + cc - p.qp) >> 5;
       if (16 * j >= p.Hf) break;
-      uint32_t r[32];
-      tmem_ld32(taddr + cc, r);
+      uint32_t v[16], g[16];
+      tmem_ld16(taddr + cc, v);
+      tmem_ld16(taddr + cc + 16, g);
       tmem_wait_ld();
       uint32_t o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float v0 = bf16r(__uint_as_float(r[2 * i])), v1 = bf16r(__uint_as_float(r[2 * i + 1]));
-        float g0 = bf16r(__uint_as_float(r[16 + 2 * i])), g1 = bf16r(__uint_as_float(r[16 + 2 * i + 1]));
-        float s0 = bf16r(__fdividef(g0, 1.f + __expf(-g0)));
-        float s1 = bf16r(__fdividef(g1, 1.f + __expf(-g1)));
+        const float v0 = bf16r(__uint_as_float(v[2 * i])), v1 = bf16r(__uint_as_float(v[2 * i + 1]));
+        const float g0 = bf16r(__uint_as_float(g[2 * i])), g1 = bf16r(__uint_as_float(g[2 * i + 1]));
+        const float s0 = bf16r(__fdividef(g0, 1.f + __expf(-g0)));
+        const float s1 = bf16r(__fdividef(g1, 1.f + __expf(-g1)));
         o[i] = pack_bf16x2(s0 * v0, s1 * v1);
       }
       if (row_ok) {
@@ -384,7 +406,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===== epilogue =====
     const int ew = warp - 4;
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
-    const int half = ew >> 2;               // 0 or 1 when NEPI == 8
+    const int half = ew >> 2;               // column group: 0 .. NEPI/4-1
     constexpr int NHALF = NEPI / 4;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     int acc = 0;
@@ -436,8 +458,17 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
   TileSched sc;
   sc.bn = BN;
   sc.num_m = (a.M + BM - 1) / BM;
-  const int num_n = (a.N + BN - 1) / BN;
-  const int big = sc.num_m * num_n;
+  sc.num_n = (a.N + BN - 1) / BN;
+  // band height: keep the A panel of a band (gm x 128 x K bf16) around 32 MB so it stays in the 126 MB L2
+  // together with the weight tiles that are in flight
+  {
+    const long long panel = (long long)BM * a.K * 2;
+    long long gm = (32ll << 20) / (panel > 0 ? panel : 1);
+    if (gm < 1) gm = 1;
+    if (gm > sc.num_m) gm = sc.num_m;
+    sc.gm = (int)gm;
+  }
+  const int big = sc.num_m * sc.num_n;
   const int sms = num_sms();
   const int grid = big < sms ? big : sms;
   int rem = big % grid;
@@ -473,7 +504,7 @@ int launch_gemm(EpiKind kind, const GemmArgs& a, cudaStream_t stream) {
     case EPI_BIAS:
       if (a.N <= 64) return launch_gemm_t<64, EPI_BIAS, 8>(a, false, stream);
       if (a.N <= 128) return launch_gemm_t<128, EPI_BIAS, 8>(a, false, stream);
-      return launch_gemm_t<256, EPI_BIAS, 8>(a, true, stream);
+      return launch_gemm_t<256, EPI_BIAS, 16>(a, true, stream);
     case EPI_BIAS_LN:
       if (a.N % 16 || a.N > 256 || !a.epi.bias) { set_error("gemm: LN epilogue needs N%%16==0, N<=256 and a bias (N=%d)", a.N); return -2; }
       if (a.N <= 64) return launch_gemm_t<64, EPI_BIAS_LN, 4>(a, false, stream);
@@ -485,9 +516,9 @@ int launch_gemm(EpiKind kind, const GemmArgs& a, cudaStream_t stream) {
                   a.epi.d, a.epi.Hf, a.epi.qp);
         return -3;
       }
-      return launch_gemm_t<256, EPI_QKV_SWIGLU, 8>(a, true, stream);
+      return launch_gemm_t<256, EPI_QKV_SWIGLU, 16>(a, true, stream);
     case EPI_RESID:
-      return launch_gemm_t<256, EPI_RESID, 8>(a, true, stream);
+      return launch_gemm_t<256, EPI_RESID, 16>(a, true, stream);
   }
   set_error("gemm: unknown epilogue %d", (int)kind);
   return -2;
