@@ -132,7 +132,7 @@ typedef struct {
 
 typedef struct {
   const void* w_in;   /* packed [qp + 2*Hf, D]: see vtk_qkv_swiglu_bf16 */
-  const void* w_out;  /* packed [D, D + Hf] = [out_proj | fc2] */
+  const void* w_out;  /* packed [D, Kp] = [out_proj | fc2 | 0-pad], Kp = D + Hf rounded up to a multiple of 64 */
   const void* norm1;  /* [D] */
   const void* norm_q; /* [d] */
   const void* norm_k; /* [d] */

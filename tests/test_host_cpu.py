@@ -70,7 +70,8 @@ def test_weight_packing_layout():
     o, f2 = torch.randn(D, D, generator=g), torch.randn(D, Hf, generator=g)
     wo = pack_w_out(o, f2)
     a, act = torch.randn(5, D, generator=g), torch.randn(5, Hf, generator=g)
-    assert torch.allclose(torch.cat([a, act], 1) @ wo.T, a @ o.T + act @ f2.T, atol=1e-4)
+    assert wo.shape == (D, 512) and not wo[:, D + Hf:].any()          # pitch padded to a multiple of 64
+    assert torch.allclose(torch.cat([a, act], 1) @ wo[:, :D + Hf].T, a @ o.T + act @ f2.T, atol=1e-4)
 
 
 def test_dsl_parsing_like_reference():

@@ -54,23 +54,32 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
-                           uint64_t row_stride_elems, uint32_t box_rows) {
+int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows, uint64_t row_stride_elems,
+                     uint32_t box_inner, uint32_t box_rows, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return VTK_ERR_CUDA;
   cuuint64_t gdim[2] = {inner_elems, rows};
   cuuint64_t gstride[1] = {row_stride_elems * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (CUresult %d) base=%p inner=%llu rows=%llu stride=%llu box_rows=%u", (int)r,
-              base, (unsigned long long)inner_elems, (unsigned long long)rows, (unsigned long long)row_stride_elems, box_rows);
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) base=%p inner=%llu rows=%llu stride=%llu box=%ux%u swizzle=%d",
+              (int)r, base, (unsigned long long)inner_elems, (unsigned long long)rows, (unsigned long long)row_stride_elems,
+              box_inner, box_rows, swizzle_bytes);
     return VTK_ERR_CUDA;
   }
   return 0;
+}
+
+int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
+                           uint64_t row_stride_elems, uint32_t box_rows) {
+  return encode_tmap_bf16(out, base, inner_elems, rows, row_stride_elems, 64, box_rows, 128);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -83,6 +92,9 @@ struct Side {
   float* inv_freq = nullptr;  // device, d/4 floats
   int head_dim() const { return heads ? width / heads : 0; }
   int qp() const { return ((3 * width + 255) / 256) * 256; }
+  // row pitch of [attn | act] and of the packed [out_proj | fc2]: D + Hf rounded up to 64 elements so every
+  // row starts on a 128-byte line (a misaligned pitch makes each 128-byte TMA box row straddle two lines)
+  int kp() const { return ((width + hidden + 63) / 64) * 64; }
 };
 
 struct Workspace {
@@ -105,7 +117,7 @@ static Workspace carve(const Side& s, void* base, long long M, int B) {
   w.x = static_cast<bf16*>(take((size_t)M * D * 2));
   w.h = static_cast<bf16*>(take((size_t)M * D * 2));
   w.qkv = static_cast<bf16*>(take((size_t)M * 3 * D * 2));
-  w.a2 = static_cast<bf16*>(take((size_t)M * (D + Hf) * 2));
+  w.a2 = static_cast<bf16*>(take((size_t)M * s.kp() * 2));
   w.rope = static_cast<bf16*>(take((size_t)M * d * 2));
   w.kv_len = static_cast<int*>(take((size_t)B * 4));
   w.is_prefix = static_cast<int*>(take((size_t)B * 4));
@@ -362,7 +374,7 @@ size_t vtk_ae_workspace_bytes(vtk_ae_t h, int side, int B, int N) {
 
 static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int64_t* row_idx, const int64_t* col_idx,
                       const uint8_t* patch_mask, int B, int N, cudaStream_t st, int& launches) {
-  const int M = B * N, D = s.width, d = s.head_dim(), Hf = s.hidden, qp = s.qp();
+  const int M = B * N, D = s.width, d = s.head_dim(), Hf = s.hidden, qp = s.qp(), kp = s.kp();
   const float eps = h->cfg.norm_eps;
   int r;
   if (s.depth > 0) {
@@ -380,18 +392,18 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
     { LaunchTimer t(h, st, CLS_RMSNORM); r = launch_rmsnorm(w.x, D, (const bf16*)b.norm1, w.h, D, M, D, eps, st); }
     if (r) return r;
     GemmArgs g1 = base_args(w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
-    g1.epi.qkv = w.qkv; g1.epi.ld_qkv = 3 * D; g1.epi.act = w.a2 + D; g1.epi.ld_act = D + Hf;
+    g1.epi.qkv = w.qkv; g1.epi.ld_qkv = 3 * D; g1.epi.act = w.a2 + D; g1.epi.ld_act = kp;
     g1.epi.normq = (const bf16*)b.norm_q; g1.epi.normk = (const bf16*)b.norm_k; g1.epi.rope = w.rope;
     g1.epi.D = D; g1.epi.d = d; g1.epi.Hf = Hf; g1.epi.qp = qp; g1.epi.eps = eps;
     { LaunchTimer t(h, st, CLS_QKV_SWIGLU); r = launch_gemm(EPI_QKV_SWIGLU, g1, st); }
     if (r) return r;
     AttnArgs a;
-    a.q = w.qkv; a.k = w.qkv + D; a.v = w.qkv + 2 * D; a.ld_qkv = 3 * D; a.out = w.a2; a.ld_out = D + Hf;
+    a.q = w.qkv; a.k = w.qkv + D; a.v = w.qkv + 2 * D; a.ld_qkv = 3 * D; a.out = w.a2; a.ld_out = kp;
     a.kv_len = patch_mask ? w.kv_len : nullptr; a.key_mask = patch_mask; a.prefix_flag = patch_mask ? w.is_prefix : nullptr;
     a.B = B; a.N = N; a.heads = s.heads; a.d = d; a.zero_invalid_rows = patch_mask ? 1 : 0;
     { LaunchTimer t(h, st, CLS_ATTENTION); r = launch_attention(a, st); }
     if (r) return r;
-    GemmArgs g2 = base_args(w.a2, D + Hf, b.w_out, D + Hf, D, M, D, D + Hf);
+    GemmArgs g2 = base_args(w.a2, kp, b.w_out, kp, D, M, D, D + Hf);
     g2.epi.out = w.x; g2.epi.ldo = D; g2.epi.gamma = (const bf16*)b.gamma;
     { LaunchTimer t(h, st, CLS_PROJ_RESID); r = launch_gemm(EPI_RESID, g2, st); }
     if (r) return r;

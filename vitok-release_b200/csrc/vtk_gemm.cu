@@ -21,6 +21,7 @@
 //                   fc1 -> chunk -> silu(g) * v           modules/mlp.py:21-22
 //   EPI_RESID       out_proj + fc2 -> LayerScale -> +x    vitok/models/ae.py:62-65, modules/layerscale.py:23
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "vtk_common.cuh"
 #include "vtk_kernels.h"
@@ -32,12 +33,44 @@ static constexpr int BK = 64;                        // 64 bf16 = one 128-byte s
 static constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB
 static constexpr int SMEM_BUDGET = 192 * 1024;
 
+static constexpr int OUT_GRANULE_BYTES = 2048;       // [32 rows x 32 cols] bf16 staging block per epilogue warp
+
 template <int BN> struct GemmShape {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // ring | per-warp output staging (TMA-store epilogues only) | barriers | alignment slack
+  static constexpr int smem_bytes(int out_warps) { return STAGES * STAGE_BYTES + out_warps * OUT_GRANULE_BYTES + 256 + 1024; }
+};
+
+// Per-warp staging block for the TMA-store epilogues: 32 rows (this warp's TMEM lanes) x 32 bf16 columns,
+// 64-byte rows, SWIZZLE_64B (16-byte chunk index ^= (row >> 1) & 3) so that the 32 lanes' 16-byte writes
+// are bank-conflict free and the block can be written to global memory as full 64-byte row segments by
+// one cp.async.bulk.tensor store (clipped at the tensor bounds) instead of 32 row-strided 16-byte stores.
+struct OutStage {
+  uint8_t* buf;
+  int lane, row0;
+  bool store, dirty;
+  __device__ __forceinline__ void begin() {
+    if (dirty) {
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+      dirty = false;
+    }
+  }
+  __device__ __forceinline__ void put(int chunk, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    *reinterpret_cast<uint4*>(buf + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4)) = make_uint4(a, b, c, d);
+  }
+  __device__ __forceinline__ void flush(const CUtensorMap* tm, int col) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && store) {
+      tma_store_2d(tm, buf, col, row0);
+      tma_store_commit();
+    }
+    dirty = true;
+  }
 };
 
 struct TileSched {
@@ -118,14 +151,14 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
   }
 }
 
-// x = bf16(x + bf16(bf16(acc) * gamma)), in place
+// x = bf16(x + bf16(bf16(acc) * gamma)), in place; 32-column granules leave through the staging block
 __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
-                                               int ucols) {
+                                               int ucols, OutStage& st, const CUtensorMap* tmX) {
   for (int cc = 0; cc < ucols; cc += 16) {
     const int col = n + cc;
     if (col >= N) break;
     const bool second = col + 8 < N;
-    bf16* xp = p.out + (long long)row * p.ldo + col;
+    const bf16* xp = p.out + (long long)row * p.ldo + col;
     uint4 x0 = make_uint4(0, 0, 0, 0), x1 = make_uint4(0, 0, 0, 0);
     if (row_ok) {
       x0 = ld_global_v4(xp);
@@ -136,20 +169,21 @@ __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t tadd
     uint32_t r[16];
     tmem_ld16(taddr + cc, r);
     tmem_wait_ld();
-    if (row_ok) {
-      uint32_t o[8];
+    uint32_t o[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float a0 = bf16r(bf16r(__uint_as_float(r[2 * i])) * u4_lo(g0, i));
-        float a1 = bf16r(bf16r(__uint_as_float(r[2 * i + 1])) * u4_hi(g0, i));
-        o[i] = pack_bf16x2(u4_lo(x0, i) + a0, u4_hi(x0, i) + a1);
-        float c0 = bf16r(bf16r(__uint_as_float(r[8 + 2 * i])) * u4_lo(g1, i));
-        float c1 = bf16r(bf16r(__uint_as_float(r[8 + 2 * i + 1])) * u4_hi(g1, i));
-        o[4 + i] = pack_bf16x2(u4_lo(x1, i) + c0, u4_hi(x1, i) + c1);
-      }
-      st_global_v4(xp, o[0], o[1], o[2], o[3]);
-      if (second) st_global_v4(xp + 8, o[4], o[5], o[6], o[7]);
+    for (int i = 0; i < 4; ++i) {
+      float a0 = bf16r(bf16r(__uint_as_float(r[2 * i])) * u4_lo(g0, i));
+      float a1 = bf16r(bf16r(__uint_as_float(r[2 * i + 1])) * u4_hi(g0, i));
+      o[i] = pack_bf16x2(u4_lo(x0, i) + a0, u4_hi(x0, i) + a1);
+      float c0 = bf16r(bf16r(__uint_as_float(r[8 + 2 * i])) * u4_lo(g1, i));
+      float c1 = bf16r(bf16r(__uint_as_float(r[8 + 2 * i + 1])) * u4_hi(g1, i));
+      o[4 + i] = pack_bf16x2(u4_lo(x1, i) + c0, u4_hi(x1, i) + c1);
     }
+    const int half = (cc >> 4) & 1;
+    if (half == 0) st.begin();
+    st.put(2 * half, o[0], o[1], o[2], o[3]);
+    st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
+    if (half == 1 || col + 16 >= N) st.flush(tmX, col - 16 * half);
   }
 }
 
@@ -207,8 +241,8 @@ __device__ __forceinline__ void epi_bias_ln_row(const EpiParams& p, uint32_t tad
 
 // One q or k head: per-head RMSNorm over d (fp32, eps inside rsqrt) then interleaved-pair 2D RoPE with
 // bf16 rounding at every eager-op boundary of the reference.
-__device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, int row, int rrow, bool row_ok,
-                                            int ncol, const bf16* w) {
+__device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, int rrow, int ncol, const bf16* w,
+                                            OutStage& st, const CUtensorMap* tmQKV) {
   const int d = p.d;
   float ss = 0.f;
   for (int cc = 0; cc < d; cc += 32) {   // two 16-column loads in flight per wait
@@ -225,7 +259,6 @@ __device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, 
   }
   const float rstd = rsqrtf(ss / (float)d + p.eps);
   const bf16* rope = p.rope + (long long)rrow * d;
-  bf16* op = p.qkv + (long long)row * p.ld_qkv + ncol;
   for (int cc = 0; cc < d; cc += 16) {
     const uint4 cs = ld_global_nc_v4(rope + (cc >> 1));              // 8 cos (pairs cc/2 .. cc/2+7)
     const uint4 sn = ld_global_nc_v4(rope + (d >> 1) + (cc >> 1));   // 8 sin
@@ -245,15 +278,16 @@ __device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, 
       const float y1 = bf16r(bf16r(__uint_as_float(r[2 * i + 1])) * rstd * wo);
       o[i] = pack_bf16x2(bf16r(y0 * c) - bf16r(y1 * sv), bf16r(y0 * sv) + bf16r(y1 * c));
     }
-    if (row_ok) {
-      st_global_v4(op + cc, o[0], o[1], o[2], o[3]);
-      st_global_v4(op + cc + 8, o[4], o[5], o[6], o[7]);
-    }
+    const int half = (cc >> 4) & 1;
+    if (half == 0) st.begin();
+    st.put(2 * half, o[0], o[1], o[2], o[3]);
+    st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
+    if (half == 1) st.flush(tmQKV, ncol + cc - 16);
   }
 }
 
-__device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t taddr, int row, int rrow, bool row_ok,
-                                                    int n, int ucols) {
+__device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t taddr, int rrow, int n, int ucols,
+                                                    OutStage& st, const CUtensorMap* tmQKV, const CUtensorMap* tmACT) {
   if (n < p.qp) {
     const int threeD = 3 * p.D;
     for (int hc = 0; hc < ucols; hc += p.d) {
@@ -261,29 +295,31 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
       if (ncol >= threeD) break;  // zero-padded columns between 3D and qp
       const int seg = ncol / p.D;
       if (seg == 2) {  // V: plain bf16 copy
-        bf16* op = p.qkv + (long long)row * p.ld_qkv + ncol;
         for (int cc = 0; cc < p.d; cc += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + hc + cc, r);
           tmem_wait_ld();
-          if (row_ok) {
-            uint32_t o[8];
+          uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-            st_global_v4(op + cc, o[0], o[1], o[2], o[3]);
-            st_global_v4(op + cc + 8, o[4], o[5], o[6], o[7]);
-          }
+          for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          const int half = (cc >> 4) & 1;
+          if (half == 0) st.begin();
+          st.put(2 * half, o[0], o[1], o[2], o[3]);
+          st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
+          if (half == 1) st.flush(tmQKV, ncol + cc - 16);
         }
       } else {
-        epi_qk_head(p, taddr + hc, row, rrow, row_ok, ncol, seg == 0 ? p.normq : p.normk);
+        epi_qk_head(p, taddr + hc, rrow, ncol, seg == 0 ? p.normq : p.normk, st, tmQKV);
       }
     }
   } else {
     // SwiGLU: 32 packed columns = [v(16) | g(16)] -> 16 outputs; mlp.py:21-22 with bf16 rounding of
-    // fc1's output, of silu(g) and of the product.
+    // fc1's output, of silu(g) and of the product.  64 packed columns fill one 32-column output granule;
+    // columns at or beyond Hf come from zero weight rows and are clipped by the TMA store.
     for (int cc = 0; cc < ucols; cc += 32) {
       const int j = (n + cc - p.qp) >> 5;
-      if (16 * j >= p.Hf) break;
+      const int half = (cc >> 5) & 1;
+      if (16 * (j - half) >= p.Hf) break;   // whole granule out of range (warp-uniform)
       uint32_t v[16], g[16];
       tmem_ld16(taddr + cc, v);
       tmem_ld16(taddr + cc + 16, g);
@@ -297,11 +333,10 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
         const float s1 = bf16r(__fdividef(g1, 1.f + __expf(-g1)));
         o[i] = pack_bf16x2(s0 * v0, s1 * v1);
       }
-      if (row_ok) {
-        bf16* op = p.act + (long long)row * p.ld_act + 16 * j;
-        st_global_v4(op, o[0], o[1], o[2], o[3]);
-        st_global_v4(op + 8, o[4], o[5], o[6], o[7]);
-      }
+      if (half == 0) st.begin();
+      st.put(2 * half, o[0], o[1], o[2], o[3]);
+      st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
+      if (half == 1) st.flush(tmACT, 16 * (j - 1));
     }
   }
 }
@@ -311,14 +346,17 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
 // ------------------------------------------------------------------------------------------------
 template <int BN, int EPI, int NEPI>
 __global__ void __launch_bounds__(128 + 32 * NEPI, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const int M, const int N,
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M, const int N,
             const int K, const TileSched sched, const EpiParams epi) {
   using S = GemmShape<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + S::STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
+  uint8_t* sOut = smem + S::STAGES * S::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (kStaged ? NEPI * OUT_GRANULE_BYTES : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + S::STAGES;
   uint64_t* tfull = bars + 2 * S::STAGES;
@@ -409,25 +447,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = ew >> 2;               // column group: 0 .. NEPI/4-1
     constexpr int NHALF = NEPI / 4;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    OutStage st;
+    st.buf = sOut + ew * OUT_GRANULE_BYTES;
+    st.lane = lane;
+    st.row0 = 0;
+    st.store = epi.debug != 1;
+    st.dirty = false;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int t = blockIdx.x; t < sched.total_tiles; t += gridDim.x) {
       int m0, n0, width;
       sched.decode(t, m0, n0, width);
       const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < M;
+      const bool row_ok = row < M && epi.debug != 1;
+      st.row0 = m0 + quarter * 32;
       const int rrow = row_ok ? row : (M - 1);
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + (uint32_t)(acc * BN);
-      if (EPI == EPI_BIAS_LN) {
+      if (epi.debug == 2) {
+        // experiment: no epilogue work at all
+      } else if (EPI == EPI_BIAS_LN) {
         epi_bias_ln_row(epi, taddr, row, row_ok, N);
       } else {
         const int U = (EPI == EPI_QKV_SWIGLU && epi.d > 64) ? epi.d : 64;
         for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
           if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
-          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
-          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, row, rrow, row_ok, n0 + c0, U);
+          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0);
+          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, st, &tmO0, &tmO1);
         }
       }
       tc_fence_before();
@@ -435,6 +482,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+    if (kStaged && lane == 0) tma_store_wait_read();   // smem must outlive the last bulk store's reads
   }
 
   tc_fence_before();
@@ -478,19 +526,40 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
     sc.full_tiles = big - rem;
     sc.total_tiles = sc.full_tiles + 2 * rem;
   }
+  // output tensor maps for the TMA-store epilogues (box = 32 cols x 32 rows, SWIZZLE_64B)
+  CUtensorMap tmO0 = tmA, tmO1 = tmA;
+  constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
+  if (EPI == EPI_QKV_SWIGLU) {
+    if (encode_tmap_bf16(&tmO0, a.epi.qkv, (uint64_t)3 * a.epi.D, (uint64_t)a.M, (uint64_t)a.epi.ld_qkv, 32, 32, 64)) return -1;
+    if (encode_tmap_bf16(&tmO1, a.epi.act, (uint64_t)a.epi.Hf, (uint64_t)a.M, (uint64_t)a.epi.ld_act, 32, 32, 64)) return -1;
+  } else if (EPI == EPI_RESID) {
+    if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
+  }
+  const int smem_bytes = S::smem_bytes(kStaged ? NEPI : 0);
   auto kern = gemm_kernel<BN, EPI, NEPI>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES),
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
                    "cudaFuncSetAttribute(gemm)"))
       return -1;
     attr_set = true;
   }
-  kern<<<grid, 128 + 32 * NEPI, S::SMEM_BYTES, stream>>>(tmA, tmB, a.M, a.N, a.K, sc, a.epi);
+  kern<<<grid, 128 + 32 * NEPI, smem_bytes, stream>>>(tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
-int launch_gemm(EpiKind kind, const GemmArgs& a, cudaStream_t stream) {
+static int epi_debug_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VTK_EPI_DEBUG");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
+
+int launch_gemm(EpiKind kind, const GemmArgs& a_in, cudaStream_t stream) {
+  GemmArgs a = a_in;
+  a.epi.debug = epi_debug_mode();
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) { set_error("gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K); return -2; }
   if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.N % 8)) {
     set_error("gemm: K, N and the row strides must be multiples of 8 (K=%d N=%d lda=%lld ldb=%lld)", a.K, a.N, a.lda, a.ldb);

@@ -19,6 +19,9 @@ int num_sms();
 // Encode a 2-D bf16 row-major tensor map with 128-byte swizzle: inner box = 64 elements.
 int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
                            uint64_t row_stride_elems, uint32_t box_rows);
+// General form: box = box_inner x box_rows elements, swizzle_bytes in {0, 32, 64, 128} (box_inner * 2 <= swizzle span).
+int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows, uint64_t row_stride_elems,
+                     uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
 
 // ---------------------------------------------------------------------------------------------
 // GEMM  out = epilogue(A[M,K] * B[N,K]^T), bf16 in, fp32 accumulate in TMEM (vtk_gemm.cu)
@@ -46,6 +49,7 @@ struct EpiParams {
   int D, d, Hf, qp;     // qp = 3D rounded up to the tile width (start of the SwiGLU columns)
   // EPI_RESID
   const bf16* gamma;    // [N]
+  int debug;            // perf experiments only (env VTK_EPI_DEBUG): 1 = no global stores, 2 = skip epilogue math+stores
 };
 
 struct GemmArgs {

@@ -100,8 +100,17 @@ def pack_w_in(qkv_w: torch.Tensor, fc1_w: torch.Tensor) -> torch.Tensor:
 
 
 def pack_w_out(out_w: torch.Tensor, fc2_w: torch.Tensor) -> torch.Tensor:
-    """[out_proj | fc2] along K: attn_out + mlp_out becomes one GEMM over the concatenated activations."""
-    return torch.cat([out_w, fc2_w], dim=1).contiguous()
+    """[out_proj | fc2 | 0-pad] along K: attn_out + mlp_out becomes one GEMM over the concatenated activations.
+
+    The row pitch is rounded up to 64 elements (128 bytes) so that every row of the TMA boxes starts on a
+    128-byte line; the pad columns are zero and lie beyond K, so they are never multiplied.
+    """
+    k = out_w.shape[1] + fc2_w.shape[1]
+    kp = (k + 63) // 64 * 64
+    w = torch.zeros(out_w.shape[0], kp, dtype=out_w.dtype, device=out_w.device)
+    w[:, :out_w.shape[1]] = out_w
+    w[:, out_w.shape[1]:k] = fc2_w
+    return w
 
 
 # --------------------------------------------------------------------------------------
@@ -231,7 +240,7 @@ class AE(nn.Module):
         """(Re)build the packed bf16 weights the kernels read and hand their pointers to the C handle.
 
         w_in  [qp + 2*Hf, D] = [Wq; Wk; Wv; zeros up to qp; 16-row interleave of fc1's value/gate halves]
-        w_out [D, D + Hf]    = [out_proj | fc2]   (one GEMM over the concatenated K)
+        w_out [D, Kp]        = [out_proj | fc2 | 0-pad to a multiple of 64]   (one GEMM over the concatenated K)
         Rebuilt whenever a parameter's storage or version changes (load_state_dict, .to(), optimizer step).
         """
         sig = self._signature()
