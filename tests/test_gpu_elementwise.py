@@ -33,13 +33,31 @@ def test_rope_table(L, d):
     row = torch.arange(0, 64).repeat_interleave(64).cuda()
     col = torch.arange(0, 64).repeat(64).cuda()
     inv = ae_oracle.rope_inv_freq(d).cuda()
-    t = L.rope_table(row, col, inv, d).cpu()
+    M = row.numel()
+    c2, s2 = L.rope_table_decode(L.rope_table(row, col, inv, d).cpu(), M, d)
     cos, sin = ae_oracle.rope_cos_sin(row.cpu(), col.cpu(), d)
-    ref = torch.cat([cos, sin], dim=-1).to(torch.bfloat16)
+    cos, sin = cos.to(torch.bfloat16), sin.to(torch.bfloat16)
+    # pair-expanded layout: C2 = (c0,c0,c1,c1,...), S2 = (-s0,+s0,-s1,+s1,...)
+    assert torch.equal(c2[:, 0::2], c2[:, 1::2]) and torch.equal(s2[:, 0::2], -s2[:, 1::2])
+    t = torch.cat([c2[:, 0::2], s2[:, 1::2]], dim=-1)
+    ref = torch.cat([cos, sin], dim=-1)
     mism = (t != ref).float().mean().item()
     print(f"[parity] rope table d={d}: mismatching bf16 entries {mism:.2e}, max_abs {(t.float() - ref.float()).abs().max():.3e}")
     assert (t.float() - ref.float()).abs().max().item() <= 2 ** -7   # never more than 1 bf16 ulp at |x|<=1
     assert mism < 5e-3
+
+
+@pytest.mark.parametrize("M", [1, 33, 100])
+def test_rope_table_ragged_rows(L, M):
+    """M not a multiple of the 32-row group."""
+    d = 64
+    row = (torch.arange(M) // 7).cuda()
+    col = (torch.arange(M) % 7).cuda()
+    inv = ae_oracle.rope_inv_freq(d).cuda()
+    c2, s2 = L.rope_table_decode(L.rope_table(row, col, inv, d).cpu(), M, d)
+    cos, sin = ae_oracle.rope_cos_sin(row.cpu(), col.cpu(), d)
+    assert (c2[:, 0::2].float() - cos).abs().max().item() <= 2 ** -7
+    assert (s2[:, 1::2].float() - sin).abs().max().item() <= 2 ** -7
 
 
 def test_casts_bit_exact(L):

@@ -30,6 +30,8 @@ x = rn(M, D)
 
 
 def timeit(fn, n=20):
+    if len(sys.argv) > 2 and sys.argv[2] == "once":
+        n = 4
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -47,3 +49,32 @@ t2 = timeit(lambda: _lib.proj_residual(a2, wo, gamma, x))
 f1 = 2.0 * M * D * (3 * D + 2 * Hf)
 f2 = 2.0 * M * (D + Hf) * D
 print(f"{which} debug={os.environ.get('VTK_EPI_DEBUG', '0')}: qkv_swiglu {t1*1e3:.1f} us {f1/t1/1e9:.0f} TF/s | proj_resid {t2*1e3:.1f} us {f2/t2/1e9:.0f} TF/s")
+
+if len(sys.argv) > 2 and sys.argv[2] == "sustain":
+    # 2 s of back-to-back launches per GEMM with nvidia-smi clock sampling: is the kernel power-capped?
+    import subprocess, tempfile, time, statistics
+    for name, fn, fl in (("qkv_swiglu", lambda: _lib.qkv_swiglu(h, wp, D, d, Hf, qp, nq, nk, table), f1),
+                         ("proj_resid", lambda: _lib.proj_residual(a2, wo, gamma, x), f2)):
+        f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        p = subprocess.Popen(["nvidia-smi", "--id=0", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap",
+                              "--format=csv,noheader,nounits", "-lms", "50"], stdout=f, stderr=subprocess.DEVNULL)
+        torch.cuda.synchronize()
+        n = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        while time.time() - t0 < 2.0:
+            for _ in range(50):
+                fn()
+            n += 50
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        p.terminate(); p.wait()
+        rows = [r.split(",") for r in open(f.name).read().strip().splitlines() if r.strip()]
+        clk = [float(r[0]) for r in rows[5:]] or [0.0]
+        pw = [float(r[1]) for r in rows[5:]] or [0.0]
+        cap = sum("Active" in r[2] and "Not" not in r[2] for r in rows)
+        print(f"{which} sustain {name}: {ms*1e3:.1f} us {fl/ms/1e9:.0f} TF/s | sm clk median {statistics.median(clk):.0f} min {min(clk):.0f} MHz, "
+              f"power median {statistics.median(pw):.0f} W, power-cap samples {cap}/{len(rows)}")

@@ -118,7 +118,7 @@ static Workspace carve(const Side& s, void* base, long long M, int B) {
   w.h = static_cast<bf16*>(take((size_t)M * D * 2));
   w.qkv = static_cast<bf16*>(take((size_t)M * 3 * D * 2));
   w.a2 = static_cast<bf16*>(take((size_t)M * s.kp() * 2));
-  w.rope = static_cast<bf16*>(take((size_t)M * d * 2));
+  w.rope = static_cast<bf16*>(take((size_t)((M + 31) / 32 * 32) * 2 * d * 2));   // pair-expanded table, 32-row groups
   w.kv_len = static_cast<int*>(take((size_t)B * 4));
   w.is_prefix = static_cast<int*>(take((size_t)B * 4));
   w.bytes = off;

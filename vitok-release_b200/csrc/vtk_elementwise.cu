@@ -59,28 +59,44 @@ int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long lo
   return check_cuda(cudaGetLastError(), "rmsnorm launch");
 }
 
-// table[m, 0:d/2] = bf16(cos(angle)), table[m, d/2:d] = bf16(sin(angle));
-// angle_j = row*f_j for j < d/4, col*f_{j-d/4} for j >= d/4 (fp32, like the reference).
+// Pair-expanded, chunk-major RoPE table consumed by the QKV GEMM epilogue (vtk_gemm.cu, rope_row_ptr):
+//   per token row 2d bf16 = C2[d] = (c_0, c_0, c_1, c_1, ...) | S2[d] = (-s_0, +s_0, -s_1, +s_1, ...),
+//   c_j = bf16(cos(angle_j)), s_j = bf16(sin(angle_j)), angle_j = row*f_j for j < d/4, col*f_{j-d/4} for j >= d/4
+//   (fp32 angles like the reference, rotary_embedding.py:46-75; the bf16 cast is the one at :118-119);
+//   bf16 element offset(row m, element e) = ((m >> 5) * (d / 4) + (e >> 3)) * 256 + (m & 31) * 8 + (e & 7).
+// Rows are grouped by 32 so that one warp of the epilogue (32 consecutive rows) reads each 16-byte chunk
+// as 512 contiguous bytes.  The table holds ceil(M / 32) * 32 rows.
 __global__ void rope_table_kernel(const int64_t* __restrict__ row_idx, const int64_t* __restrict__ col_idx,
                                   const float* __restrict__ inv_freq, bf16* __restrict__ table, int M, int d) {
   const int half = d >> 1, quarter = d >> 2;
-  const long long total = (long long)M * half;
+  const long long groups = ((long long)M + 31) >> 5;
+  const long long total = groups * half * 32;   // thread <-> (group, pair j, row-in-group): coalesced-ish writes
+  uint32_t* tw = reinterpret_cast<uint32_t*>(table);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long m = i / half;
-    const int j = (int)(i - m * half);
+    const int ml = (int)(i & 31);
+    const long long t = i >> 5;
+    const int j = (int)(t % half);
+    const long long grp = t / half;
+    const long long m = grp * 32 + ml;
+    if (m >= M) continue;
     const float pos = j < quarter ? (float)row_idx[m] : (float)col_idx[m];
     const float f = inv_freq[j < quarter ? j : j - quarter];
     const float ang = pos * f;
-    table[m * d + j] = __float2bfloat16_rn(cosf(ang));
-    table[m * d + half + j] = __float2bfloat16_rn(sinf(ang));
+    const uint32_t c = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(cosf(ang)));
+    const uint32_t sn = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(sinf(ang)));
+    // 32-bit word w of the row (w < d/2: C2 pair w; w >= d/2: S2 pair w - d/2) lives in chunk w/4, slot w%4
+    const long long base = grp * (long long)(d >> 2);
+    const int wc = j, ws = half + j;
+    tw[((base + (wc >> 2)) * 32 + ml) * 4 + (wc & 3)] = c | (c << 16);
+    tw[((base + (ws >> 2)) * 32 + ml) * 4 + (ws & 3)] = (sn ^ 0x8000u) | (sn << 16);
   }
 }
 
 int launch_rope_table(const int64_t* row_idx, const int64_t* col_idx, const float* inv_freq, bf16* table, int M, int d,
                       cudaStream_t stream) {
-  if (d % 4) { set_error("rope: 2D RoPE requires head dimension divisible by 4"); return -2; }
+  if (d % 8) { set_error("rope: head dimension must be a multiple of 8 (2D RoPE needs d %% 4 == 0; table chunks need 8)"); return -2; }
   if (M <= 0) return 0;
-  const long long total = (long long)M * (d / 2);
+  const long long total = (((long long)M + 31) >> 5) * (d / 2) * 32;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;

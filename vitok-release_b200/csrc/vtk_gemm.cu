@@ -33,15 +33,15 @@ static constexpr int BK = 64;                        // 64 bf16 = one 128-byte s
 static constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB
 static constexpr int SMEM_BUDGET = 192 * 1024;
 
-static constexpr int OUT_GRANULE_BYTES = 2048;       // [32 rows x 32 cols] bf16 staging block per epilogue warp
+static constexpr int OUT_GRANULE_BYTES = 2048;       // [32 rows x 32 cols] bf16 staging block (two per epilogue warp)
 
 template <int BN> struct GemmShape {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  // ring | per-warp output staging (TMA-store epilogues only) | barriers | alignment slack
-  static constexpr int smem_bytes(int out_warps) { return STAGES * STAGE_BYTES + out_warps * OUT_GRANULE_BYTES + 256 + 1024; }
+  // ring | per-warp output staging (TMA-store epilogues only) | barriers | fp32 q/k norm weights | alignment slack
+  static constexpr int smem_bytes(int out_warps) { return STAGES * STAGE_BYTES + out_warps * 2 * OUT_GRANULE_BYTES + 256 + 1024 + 1024; }
 };
 
 // Per-warp staging block for the TMA-store epilogues: 32 rows (this warp's TMEM lanes) x 32 bf16 columns,
@@ -49,32 +49,30 @@ template <int BN> struct GemmShape {
 // are bank-conflict free and the block can be written to global memory as full 64-byte row segments by
 // one cp.async.bulk.tensor store (clipped at the tensor bounds) instead of 32 row-strided 16-byte stores.
 struct OutStage {
-  uint8_t* buf;
-  int lane, row0;
-  bool store, dirty;
+  uint8_t* base;     // two granule buffers per warp: the TMA store of one drains while the next is filled
+  int lane, row0, cur;
+  bool store;
   __device__ __forceinline__ void begin() {
-    if (dirty) {
-      if (lane == 0) tma_store_wait_read();
-      __syncwarp();
-      dirty = false;
-    }
+    cur ^= 1;
+    if (lane == 0) tma_store_wait_read_le1();   // the store issued from this buffer two granules ago has read it
+    __syncwarp();
   }
   __device__ __forceinline__ void put(int chunk, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    *reinterpret_cast<uint4*>(buf + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4)) = make_uint4(a, b, c, d);
+    *reinterpret_cast<uint4*>(base + cur * OUT_GRANULE_BYTES + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(a, b, c, d);
   }
   __device__ __forceinline__ void flush(const CUtensorMap* tm, int col) {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && store) {
-      tma_store_2d(tm, buf, col, row0);
+      tma_store_2d(tm, base + cur * OUT_GRANULE_BYTES, col, row0);
       tma_store_commit();
     }
-    dirty = true;
   }
 };
 
 struct TileSched {
-  int num_m, num_n, gm, full_tiles, total_tiles, bn;
+  int num_m, num_n, gm, full_tiles, total_tiles, bn, bm;
   // Big tiles are visited in bands of `gm` row-tiles: inside a band m is fastest and n sweeps all column
   // tiles, so the band's A panel (gm x 128 x K) stays L2-resident while the weights stream through once
   // per band.  full_tiles big tiles, then (total_tiles - full_tiles) half-width tiles.
@@ -90,13 +88,13 @@ struct TileSched {
     int mi, ni;
     if (t < full_tiles) {
       big(t, mi, ni);
-      m0 = mi * BM;
+      m0 = mi * bm;
       n0 = ni * bn;
       width = bn;
     } else {
       const int u = t - full_tiles;
       big(full_tiles + (u >> 1), mi, ni);
-      m0 = mi * BM;
+      m0 = mi * bm;
       n0 = ni * bn + (u & 1) * (bn >> 1);
       width = bn >> 1;
     }
@@ -151,39 +149,41 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
   }
 }
 
-// x = bf16(x + bf16(bf16(acc) * gamma)), in place; 32-column granules leave through the staging block
+// x = bf16(x + bf16(bf16(acc) * gamma)), in place; 32-column granules leave through the staging block.
+// Packed bf16x2 arithmetic: bf2_mul(bf16(acc), gamma) and bf2_add(x, .) round exactly where the reference's
+// eager bf16 ops do (layerscale.py:23, ae.py:64-65), at 1.5 instructions per element.
 __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
                                                int ucols, OutStage& st, const CUtensorMap* tmX) {
-  for (int cc = 0; cc < ucols; cc += 16) {
+  for (int cc = 0; cc < ucols; cc += 32) {
     const int col = n + cc;
     if (col >= N) break;
-    const bool second = col + 8 < N;
+    const int nch = min(4, (N - col) >> 3);   // 16-byte chunks of this granule inside the tensor (N % 8 == 0)
     const bf16* xp = p.out + (long long)row * p.ldo + col;
-    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = make_uint4(0, 0, 0, 0);
-    if (row_ok) {
-      x0 = ld_global_v4(xp);
-      if (second) x1 = ld_global_v4(xp + 8);
-    }
-    const uint4 g0 = ld_global_nc_v4(p.gamma + col);
-    const uint4 g1 = second ? ld_global_nc_v4(p.gamma + col + 8) : make_uint4(0, 0, 0, 0);
-    uint32_t r[16];
-    tmem_ld16(taddr + cc, r);
-    tmem_wait_ld();
-    uint32_t o[8];
+    uint4 xv[4], gv[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a0 = bf16r(bf16r(__uint_as_float(r[2 * i])) * u4_lo(g0, i));
-      float a1 = bf16r(bf16r(__uint_as_float(r[2 * i + 1])) * u4_hi(g0, i));
-      o[i] = pack_bf16x2(u4_lo(x0, i) + a0, u4_hi(x0, i) + a1);
-      float c0 = bf16r(bf16r(__uint_as_float(r[8 + 2 * i])) * u4_lo(g1, i));
-      float c1 = bf16r(bf16r(__uint_as_float(r[8 + 2 * i + 1])) * u4_hi(g1, i));
-      o[4 + i] = pack_bf16x2(u4_lo(x1, i) + c0, u4_hi(x1, i) + c1);
+    for (int j = 0; j < 4; ++j) {
+      xv[j] = make_uint4(0, 0, 0, 0);
+      gv[j] = make_uint4(0, 0, 0, 0);
+      if (j < nch) {
+        if (row_ok) xv[j] = ld_global_v4(xp + 8 * j);
+        gv[j] = ld_global_nc_v4(p.gamma + col + 8 * j);
+      }
     }
-    const int half = (cc >> 4) & 1;
-    if (half == 0) st.begin();
-    st.put(2 * half, o[0], o[1], o[2], o[3]);
-    st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
-    if (half == 1 || col + 16 >= N) st.flush(tmX, col - 16 * half);
+    uint32_t r[32];
+    tmem_ld32(taddr + cc, r);
+    tmem_wait_ld();
+    st.begin();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t xs[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+      const uint32_t gs[4] = {gv[j].x, gv[j].y, gv[j].z, gv[j].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        o[i] = bf2_add(xs[i], bf2_mul(bf2_cvt_bits(r[8 * j + 2 * i], r[8 * j + 2 * i + 1]), gs[i]));
+      st.put(j, o[0], o[1], o[2], o[3]);
+    }
+    st.flush(tmX, col);
   }
 }
 
@@ -239,104 +239,191 @@ __device__ __forceinline__ void epi_bias_ln_row(const EpiParams& p, uint32_t tad
   }
 }
 
-// One q or k head: per-head RMSNorm over d (fp32, eps inside rsqrt) then interleaved-pair 2D RoPE with
-// bf16 rounding at every eager-op boundary of the reference.
-__device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, int rrow, int ncol, const bf16* w,
-                                            OutStage& st, const CUtensorMap* tmQKV) {
+// RoPE table layout ("pair-expanded, chunk-major", written by rope_table_kernel): per token row 2d bf16 =
+//   C2[d] = (c_0, c_0, c_1, c_1, ...)  |  S2[d] = (-s_0, +s_0, -s_1, +s_1, ...)
+// stored in 16-byte chunks so that the 32 rows of one epilogue warp are contiguous per chunk:
+//   byte offset(row m, chunk c) = ((m >> 5) * (2d / 8) + c) * 512 + (m & 31) * 16
+// -> a warp-wide 16-byte load touches 4 cache lines instead of 32, and the pair (c,c) / (-s,s) words feed
+// HMUL2.BF16 directly:  out = Y * C2 + swap(Y) * S2   (rotary_embedding.py:121-124, bf16 rounding per op).
+__device__ __forceinline__ const uint4* rope_row_ptr(const EpiParams& p, int rrow) {
+  const long long grp = rrow >> 5;
+  return reinterpret_cast<const uint4*>(p.rope) + (grp * (p.d >> 2)) * 32 + (rrow & 31);
+}
+
+// One q or k head: per-head RMSNorm over d (fp32, eps inside rsqrt; attention.py:103, norm.py:22-25) then
+// interleaved-pair 2D RoPE.  w_s = this head kind's norm weight as fp32 in shared memory.
+__device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, const uint4* rope_row, int ncol,
+                                            const float* w_s, OutStage& st, const CUtensorMap* tmQKV) {
   const int d = p.d;
-  float ss = 0.f;
-  for (int cc = 0; cc < d; cc += 32) {   // two 16-column loads in flight per wait
-    uint32_t r0[16], r1[16];
-    tmem_ld16(taddr + cc, r0);
-    tmem_ld16(taddr + cc + 16, r1);
+  uint64_t ss2 = 0ull;
+  for (int cc = 0; cc < d; cc += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + cc, r);
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float t0 = bf16r(__uint_as_float(r0[i])), t1 = bf16r(__uint_as_float(r1[i]));
-      ss = fmaf(t0, t0, ss);
-      ss = fmaf(t1, t1, ss);
+      const uint64_t t = bf2_to_f2(bf2_cvt_bits(r[2 * i], r[2 * i + 1]));   // q as the bf16 GEMM output
+      ss2 = f2_fma(t, t, ss2);
     }
   }
-  const float rstd = rsqrtf(ss / (float)d + p.eps);
-  const bf16* rope = p.rope + (long long)rrow * d;
-  for (int cc = 0; cc < d; cc += 16) {
-    const uint4 cs = ld_global_nc_v4(rope + (cc >> 1));              // 8 cos (pairs cc/2 .. cc/2+7)
-    const uint4 sn = ld_global_nc_v4(rope + (d >> 1) + (cc >> 1));   // 8 sin
-    const uint4 w0 = ld_global_nc_v4(w + cc);
-    const uint4 w1 = ld_global_nc_v4(w + cc + 8);
-    uint32_t r[16];
-    tmem_ld16(taddr + cc, r);
-    tmem_wait_ld();
-    uint32_t o[8];
+  float s0, s1;
+  f2_unpack(ss2, s0, s1);
+  const float rstd = rsqrtf((s0 + s1) / (float)d + p.eps);
+  const uint64_t rstd2 = f2_pack(rstd, rstd);
+  const int s2_chunk0 = d >> 3;   // first chunk of the S2 half
+  for (int cc = 0; cc < d; cc += 32) {
+    uint4 c2[4], s2[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {   // pair i of this chunk = columns 2i, 2i+1
-      const float we = (i < 4) ? u4_lo(w0, i) : u4_lo(w1, i - 4);
-      const float wo = (i < 4) ? u4_hi(w0, i) : u4_hi(w1, i - 4);
-      const float c = (i & 1) ? u4_hi(cs, i >> 1) : u4_lo(cs, i >> 1);
-      const float sv = (i & 1) ? u4_hi(sn, i >> 1) : u4_lo(sn, i >> 1);
-      const float y0 = bf16r(bf16r(__uint_as_float(r[2 * i])) * rstd * we);
-      const float y1 = bf16r(bf16r(__uint_as_float(r[2 * i + 1])) * rstd * wo);
-      o[i] = pack_bf16x2(bf16r(y0 * c) - bf16r(y1 * sv), bf16r(y0 * sv) + bf16r(y1 * c));
+    for (int j = 0; j < 4; ++j) {
+      c2[j] = ld_global_nc_v4(rope_row + ((cc >> 3) + j) * 32);
+      s2[j] = ld_global_nc_v4(rope_row + (s2_chunk0 + (cc >> 3) + j) * 32);
     }
-    const int half = (cc >> 4) & 1;
-    if (half == 0) st.begin();
-    st.put(2 * half, o[0], o[1], o[2], o[3]);
-    st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
-    if (half == 1) st.flush(tmQKV, ncol + cc - 16);
+    uint32_t r[32];
+    tmem_ld32(taddr + cc, r);
+    tmem_wait_ld();
+    st.begin();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 wa = *reinterpret_cast<const float4*>(w_s + cc + 8 * j);
+      const float4 wb = *reinterpret_cast<const float4*>(w_s + cc + 8 * j + 4);
+      const uint64_t w2[4] = {f2_pack(wa.x, wa.y), f2_pack(wa.z, wa.w), f2_pack(wb.x, wb.y), f2_pack(wb.z, wb.w)};
+      const uint32_t cw[4] = {c2[j].x, c2[j].y, c2[j].z, c2[j].w};
+      const uint32_t sw[4] = {s2[j].x, s2[j].y, s2[j].z, s2[j].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint64_t t = bf2_to_f2(bf2_cvt_bits(r[8 * j + 2 * i], r[8 * j + 2 * i + 1]));
+        float y0, y1;
+        f2_unpack(f2_mul(f2_mul(t, rstd2), w2[i]), y0, y1);
+        const uint32_t Y = bf2_cvt(y0, y1);
+        o[i] = bf2_add(bf2_mul(Y, cw[i]), bf2_mul(bf2_swap(Y), sw[i]));
+      }
+      st.put(j, o[0], o[1], o[2], o[3]);
+    }
+    st.flush(tmQKV, ncol + cc);
+  }
+}
+
+// d = 64 specialisation: the head's 64 accumulator columns are read from TMEM once, kept as 32 packed bf16x2
+// registers (that IS the reference's bf16 q/k), and both the sum of squares and the normalise+rotate pass run
+// from those registers -- one TMEM round trip instead of two on the epilogue's critical path.
+__device__ __forceinline__ void epi_qk_head64(const EpiParams& p, uint32_t taddr, const uint4* rope_row, int ncol,
+                                              const float* w_s, OutStage& st, const CUtensorMap* tmQKV) {
+  uint32_t P[32];
+  uint64_t ss2 = 0ull;
+  {
+    uint32_t r0[32], r1[32];
+    tmem_ld32(taddr, r0);
+    tmem_ld32(taddr + 32, r1);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      P[i] = bf2_cvt_bits(r0[2 * i], r0[2 * i + 1]);
+      P[16 + i] = bf2_cvt_bits(r1[2 * i], r1[2 * i + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const uint64_t t = bf2_to_f2(P[i]);
+    ss2 = f2_fma(t, t, ss2);
+  }
+  float s0, s1;
+  f2_unpack(ss2, s0, s1);
+  const float rstd = rsqrtf((s0 + s1) * (1.f / 64.f) + p.eps);
+  const uint64_t rstd2 = f2_pack(rstd, rstd);
+#pragma unroll
+  for (int cc = 0; cc < 64; cc += 32) {
+    uint4 c2[4], s2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      c2[j] = ld_global_nc_v4(rope_row + ((cc >> 3) + j) * 32);
+      s2[j] = ld_global_nc_v4(rope_row + (8 + (cc >> 3) + j) * 32);
+    }
+    st.begin();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 wa = *reinterpret_cast<const float4*>(w_s + cc + 8 * j);
+      const float4 wb = *reinterpret_cast<const float4*>(w_s + cc + 8 * j + 4);
+      const uint64_t w2[4] = {f2_pack(wa.x, wa.y), f2_pack(wa.z, wa.w), f2_pack(wb.x, wb.y), f2_pack(wb.z, wb.w)};
+      const uint32_t cw[4] = {c2[j].x, c2[j].y, c2[j].z, c2[j].w};
+      const uint32_t sw[4] = {s2[j].x, s2[j].y, s2[j].z, s2[j].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float y0, y1;
+        f2_unpack(f2_mul(f2_mul(bf2_to_f2(P[(cc >> 1) + 4 * j + i]), rstd2), w2[i]), y0, y1);
+        const uint32_t Y = bf2_cvt(y0, y1);
+        o[i] = bf2_add(bf2_mul(Y, cw[i]), bf2_mul(bf2_swap(Y), sw[i]));
+      }
+      st.put(j, o[0], o[1], o[2], o[3]);
+    }
+    st.flush(tmQKV, ncol + cc);
   }
 }
 
 __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t taddr, int rrow, int n, int ucols,
-                                                    OutStage& st, const CUtensorMap* tmQKV, const CUtensorMap* tmACT) {
+                                                    const float* normw_s, OutStage& st, const CUtensorMap* tmQKV,
+                                                    const CUtensorMap* tmACT) {
   if (n < p.qp) {
     const int threeD = 3 * p.D;
+    const uint4* rope_row = rope_row_ptr(p, rrow);
     for (int hc = 0; hc < ucols; hc += p.d) {
       const int ncol = n + hc;
       if (ncol >= threeD) break;  // zero-padded columns between 3D and qp
       const int seg = ncol / p.D;
       if (seg == 2) {  // V: plain bf16 copy
-        for (int cc = 0; cc < p.d; cc += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + hc + cc, r);
+        for (int cc = 0; cc < p.d; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + hc + cc, r);
           tmem_wait_ld();
-          uint32_t o[8];
+          st.begin();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-          const int half = (cc >> 4) & 1;
-          if (half == 0) st.begin();
-          st.put(2 * half, o[0], o[1], o[2], o[3]);
-          st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
-          if (half == 1) st.flush(tmQKV, ncol + cc - 16);
+          for (int j = 0; j < 4; ++j)
+            st.put(j, bf2_cvt_bits(r[8 * j], r[8 * j + 1]), bf2_cvt_bits(r[8 * j + 2], r[8 * j + 3]),
+                   bf2_cvt_bits(r[8 * j + 4], r[8 * j + 5]), bf2_cvt_bits(r[8 * j + 6], r[8 * j + 7]));
+          st.flush(tmQKV, ncol + cc);
         }
       } else {
-        epi_qk_head(p, taddr + hc, rrow, ncol, seg == 0 ? p.normq : p.normk, st, tmQKV);
+        if (p.d == 64) epi_qk_head64(p, taddr + hc, rope_row, ncol, normw_s + seg * 128, st, tmQKV);
+        else epi_qk_head(p, taddr + hc, rope_row, ncol, normw_s + seg * 128, st, tmQKV);
       }
     }
   } else {
     // SwiGLU: 32 packed columns = [v(16) | g(16)] -> 16 outputs; mlp.py:21-22 with bf16 rounding of
-    // fc1's output, of silu(g) and of the product.  64 packed columns fill one 32-column output granule;
-    // columns at or beyond Hf come from zero weight rows and are clipped by the TMA store.
-    for (int cc = 0; cc < ucols; cc += 32) {
-      const int j = (n + cc - p.qp) >> 5;
-      const int half = (cc >> 5) & 1;
-      if (16 * (j - half) >= p.Hf) break;   // whole granule out of range (warp-uniform)
-      uint32_t v[16], g[16];
-      tmem_ld16(taddr + cc, v);
-      tmem_ld16(taddr + cc + 16, g);
+    // fc1's output, of silu(g) and of the product (bf2_mul).  64 packed columns fill one 32-column output
+    // granule; columns at or beyond Hf come from zero weight rows and are clipped by the TMA store.
+    const uint64_t nlog2e = f2_pack(-1.4426950408889634f, -1.4426950408889634f);
+    const uint64_t one2 = f2_pack(1.f, 1.f);
+    for (int cc = 0; cc < ucols; cc += 64) {
+      const int j0 = (n + cc - p.qp) >> 5;      // first of the two 32-column groups of this granule
+      if (16 * j0 >= p.Hf) break;               // whole granule out of range (warp-uniform)
+      uint32_t ra[32], rb[32];
+      tmem_ld32(taddr + cc, ra);
+      tmem_ld32(taddr + cc + 32, rb);
       tmem_wait_ld();
-      uint32_t o[8];
+      st.begin();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float v0 = bf16r(__uint_as_float(v[2 * i])), v1 = bf16r(__uint_as_float(v[2 * i + 1]));
-        const float g0 = bf16r(__uint_as_float(g[2 * i])), g1 = bf16r(__uint_as_float(g[2 * i + 1]));
-        const float s0 = bf16r(__fdividef(g0, 1.f + __expf(-g0)));
-        const float s1 = bf16r(__fdividef(g1, 1.f + __expf(-g1)));
-        o[i] = pack_bf16x2(s0 * v0, s1 * v1);
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t (&r)[32] = half ? rb : ra;
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t Vp = bf2_cvt_bits(r[2 * i], r[2 * i + 1]);
+          const uint64_t g2 = bf2_to_f2(bf2_cvt_bits(r[16 + 2 * i], r[16 + 2 * i + 1]));
+          float e0, e1, g0, g1;
+          f2_unpack(f2_mul(g2, nlog2e), e0, e1);
+          asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e0));
+          asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e1));
+          f2_unpack(f2_add(f2_pack(e0, e1), one2), e0, e1);   // 1 + exp(-g)  (>= 1, or +inf -> rcp = 0)
+          asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(e0));
+          asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(e1));
+          f2_unpack(f2_mul(g2, f2_pack(e0, e1)), g0, g1);     // silu(g) = g * sigmoid(g)
+          o[i] = bf2_mul(bf2_cvt(g0, g1), Vp);
+        }
+        st.put(2 * half, o[0], o[1], o[2], o[3]);
+        st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
       }
-      if (half == 0) st.begin();
-      st.put(2 * half, o[0], o[1], o[2], o[3]);
-      st.put(2 * half + 1, o[4], o[5], o[6], o[7]);
-      if (half == 1) st.flush(tmACT, 16 * (j - 1));
+      st.flush(tmACT, 16 * j0);
     }
   }
 }
@@ -356,12 +443,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* sB = smem + S::STAGES * A_STAGE_BYTES;
   constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
   uint8_t* sOut = smem + S::STAGES * S::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (kStaged ? NEPI * OUT_GRANULE_BYTES : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (kStaged ? NEPI * 2 * OUT_GRANULE_BYTES : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + S::STAGES;
   uint64_t* tfull = bars + 2 * S::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* normw_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][128] fp32: norm_q | norm_k
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -383,6 +471,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) {
     tmem_alloc(tmem_slot, S::TMEM_COLS);
     tmem_relinquish();
+  }
+  if (EPI == EPI_QKV_SWIGLU && warp >= 4) {
+    for (int i = threadIdx.x - 128; i < 2 * epi.d; i += 32 * NEPI) {
+      const int kind = i >= epi.d;
+      normw_s[kind * 128 + (i - kind * epi.d)] = __bfloat162float((kind ? epi.normk : epi.normq)[i - kind * epi.d]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -448,11 +542,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int NHALF = NEPI / 4;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     OutStage st;
-    st.buf = sOut + ew * OUT_GRANULE_BYTES;
+    st.base = sOut + ew * 2 * OUT_GRANULE_BYTES;
     st.lane = lane;
     st.row0 = 0;
+    st.cur = 0;
     st.store = epi.debug != 1;
-    st.dirty = false;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int t = blockIdx.x; t < sched.total_tiles; t += gridDim.x) {
@@ -474,7 +568,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
           if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
           if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0);
-          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, st, &tmO0, &tmO1);
+          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1);
         }
       }
       tc_fence_before();
@@ -505,6 +599,7 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
     return -1;
   TileSched sc;
   sc.bn = BN;
+  sc.bm = BM;
   sc.num_m = (a.M + BM - 1) / BM;
   sc.num_n = (a.N + BN - 1) / BN;
   // band height: keep the A panel of a band (gm x 128 x K bf16) around 32 MB so it stays in the 126 MB L2
@@ -548,6 +643,298 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cluster of 2, tcgen05 cta_group::2): one 256 x 256 output tile per pair.
+//
+// Each CTA owns 128 rows of the tile: it TMA-loads its own A rows and HALF of the B tile (the tensor core of
+// both SMs reads the two B halves from both shared memories), so per k-block a CTA stages 16 KB + 16 KB
+// instead of 16 KB + 32 KB: 2/3 of the L2->SM traffic, 2/3 of the shared-memory writes and reads, room for a
+// 6-stage ring.  The leader CTA (cluster rank 0) issues every MMA (M = 256); tcgen05.commit multicasts the
+// "slot free" and "accumulator ready" arrivals to both CTAs; all TMA loads of a stage complete on the
+// leader's full barrier; the epilogue warps of both CTAs release an accumulator on the leader's barrier.
+// The epilogue code is shared with the single-CTA kernel (each CTA finishes its own 128 x 256 half).
+// ------------------------------------------------------------------------------------------------
+static constexpr int G2_BN = 256;
+static constexpr int G2_B_STAGE_BYTES = (G2_BN / 2) * BK * 2;                 // 16 KB: this CTA's half of B
+static constexpr int G2_STAGE_BYTES = A_STAGE_BYTES + G2_B_STAGE_BYTES;       // 32 KB
+static constexpr int g2_smem_bytes(int stages, int out_warps) {
+  return stages * G2_STAGE_BYTES + out_warps * 2 * OUT_GRANULE_BYTES + 256 + 1024 + 1024;
+}
+
+template <bool P> __device__ __forceinline__ long long prof_clock() {
+  if constexpr (P) return clock64();
+  return 0;
+}
+
+template <int EPI, int NEPI, int G2_STAGES, bool PROF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M, const int N,
+             const int K, const TileSched sched, const EpiParams epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + G2_STAGES * A_STAGE_BYTES;
+  constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
+  uint8_t* sOut = smem + G2_STAGES * G2_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (kStaged ? NEPI * 2 * OUT_GRANULE_BYTES : 0));
+  uint64_t* full = bars;                    // [STAGES]  used in the leader only (count 1: its arrive.expect_tx)
+  uint64_t* empty = bars + G2_STAGES;       // [STAGES]  both CTAs (multicast commit)
+  uint64_t* tfull = bars + 2 * G2_STAGES;   // [2]       both CTAs (multicast commit)
+  uint64_t* tempty = tfull + 2;             // [2]       leader only: 2 * NEPI arrivals (epilogue warps of both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* normw_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 2 * NEPI);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, 512);
+    tmem_relinquish_2cta();
+  }
+  if (EPI == EPI_QKV_SWIGLU && warp >= 4) {
+    for (int i = threadIdx.x - 128; i < 2 * epi.d; i += 32 * NEPI) {
+      const int kind = i >= epi.d;
+      normw_s[kind * 128 + (i - kind * epi.d)] = __bfloat162float((kind ? epi.normk : epi.normq)[i - kind * epi.d]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs) =====
+      int s = 0;
+      uint32_t ph = 0;
+      long long w_empty = 0;
+      for (int t = cluster_id; t < sched.total_tiles; t += num_clusters) {
+        int m0, n0, width;
+        sched.decode(t, m0, n0, width);
+        const int hw = width >> 1;                                      // B rows staged by this CTA
+        const uint32_t tx = 2u * (A_STAGE_BYTES + (uint32_t)hw * BK * 2);   // both CTAs' bytes land on the leader's barrier
+        for (int kb = 0; kb < num_k; ++kb) {
+          const long long c0 = prof_clock<PROF>();
+          mbar_wait(&empty[s], ph ^ 1);
+          w_empty += prof_clock<PROF>() - c0;
+          const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full[s], tx);
+          tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BK, m0 + (int)rank * BM);
+          for (int nb = 0; nb < hw; nb += 64)
+            tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BK, n0 + (int)rank * hw + nb);
+          if (++s == G2_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+      if (PROF && epi.prof) atomicAdd(&epi.prof[5], (unsigned long long)w_empty);
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      long long w_full = 0, w_tempty = 0;
+      const long long t_begin = prof_clock<PROF>();
+      for (int t = cluster_id; t < sched.total_tiles; t += num_clusters) {
+        int m0, n0, width;
+        sched.decode(t, m0, n0, width);
+        const uint32_t idesc = make_idesc_bf16(2 * BM, width, 0, 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G2_BN);
+        long long c0 = prof_clock<PROF>();
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        w_tempty += prof_clock<PROF>() - c0;
+        tc_fence_after();
+        for (int kb = 0; kb < num_k; ++kb) {
+          c0 = prof_clock<PROF>();
+          mbar_wait(&full[s], ph);
+          w_full += prof_clock<PROF>() - c0;
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b0 = smem_u32(sB + s * G2_B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty[s]);   // slot reusable in both CTAs
+          if (++s == G2_STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2cta(&tfull[acc]);   // accumulator complete -> epilogues of both CTAs
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+      if (PROF && epi.prof) {
+        atomicAdd(&epi.prof[0], (unsigned long long)w_full);
+        atomicAdd(&epi.prof[1], (unsigned long long)w_tempty);
+        atomicAdd(&epi.prof[2], (unsigned long long)(prof_clock<PROF>() - t_begin));
+        atomicAdd(&epi.prof[7], 1ull);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, each on its own 128 rows) =====
+    const int ew = warp - 4;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int NHALF = NEPI / 4;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    OutStage st;
+    st.base = sOut + ew * 2 * OUT_GRANULE_BYTES;
+    st.lane = lane;
+    st.row0 = 0;
+    st.cur = 0;
+    st.store = epi.debug != 1;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    long long w_tfull = 0, w_work = 0;
+    const long long t_begin = prof_clock<PROF>();
+    for (int t = cluster_id; t < sched.total_tiles; t += num_clusters) {
+      int m0, n0, width;
+      sched.decode(t, m0, n0, width);
+      m0 += (int)rank * BM;
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < M && epi.debug != 1;
+      st.row0 = m0 + quarter * 32;
+      const int rrow = row < M ? row : (M - 1);
+      if (EPI == EPI_QKV_SWIGLU && n0 < 2 * epi.D) {
+        // q/k tile: pull this warp's 32 RoPE-table rows (one contiguous 32 * 4d-byte block, thanks to the
+        // chunk-major layout) into L1 while the accumulator is still being computed
+        const uint8_t* blk = reinterpret_cast<const uint8_t*>(epi.rope) + (long long)((m0 + quarter * 32) >> 5) * (128ll * epi.d);
+        if (m0 + quarter * 32 < M)
+          for (int off = lane * 128; off < 128 * epi.d; off += 32 * 128)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(blk + off));
+      }
+      if (EPI == EPI_RESID && row < M) {
+        // the residual rows of this warp's units: one 128-byte line per lane and unit
+        for (int c0 = half * 64; c0 < width; c0 += NHALF * 64)
+          if (n0 + c0 < N) asm volatile("prefetch.global.L1 [%0];" ::"l"(epi.out + (long long)row * epi.ldo + n0 + c0));
+      }
+      const long long c0 = prof_clock<PROF>();
+      mbar_wait(&tfull[acc], acc_ph);
+      const long long c1 = prof_clock<PROF>();
+      w_tfull += c1 - c0;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_base + (uint32_t)(acc * G2_BN);
+      if (epi.debug != 2) {
+        const int U = (EPI == EPI_QKV_SWIGLU && epi.d > 64) ? epi.d : 64;
+        for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
+          if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
+          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0);
+          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+      w_work += prof_clock<PROF>() - c1;
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+    if (kStaged && lane == 0) tma_store_wait_read();
+    if (PROF && epi.prof && lane == 0 && rank == 0) {   // per epilogue warp of the leader: slots 8.. = wait, 8+NEPI.. = work
+      atomicAdd(&epi.prof[8 + ew], (unsigned long long)w_tfull);
+      atomicAdd(&epi.prof[8 + NEPI + ew], (unsigned long long)w_work);
+      if (ew == 0) atomicAdd(&epi.prof[6], (unsigned long long)(prof_clock<PROF>() - t_begin));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer's shared memory / barriers stay alive until every MMA and arrive has landed
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+template <int EPI, int NEPI, int G2_STAGES>
+static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  if (encode_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BM)) return -1;
+  if (encode_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.b_rows, (uint64_t)a.ldb, 64)) return -1;
+  TileSched sc;
+  sc.bn = G2_BN;
+  sc.bm = 2 * BM;
+  sc.num_m = (a.M + 2 * BM - 1) / (2 * BM);
+  sc.num_n = (a.N + G2_BN - 1) / G2_BN;
+  {
+    const long long panel = 2ll * BM * a.K * 2;
+    long long gm = (32ll << 20) / (panel > 0 ? panel : 1);
+    if (gm < 1) gm = 1;
+    if (const char* e = getenv("VTK_GEMM_GM")) gm = atoi(e) > 0 ? atoi(e) : gm;
+    if (gm > sc.num_m) gm = sc.num_m;
+    sc.gm = (int)gm;
+  }
+  const int big = sc.num_m * sc.num_n;
+  const int pairs = num_sms() / 2;
+  const int clusters = big < pairs ? big : pairs;
+  const int rem = big % clusters;
+  sc.full_tiles = big;
+  sc.total_tiles = big;
+  if (rem > 0 && 2 * rem <= clusters) {   // short last wave: half-width tiles (UMMA N = 128)
+    sc.full_tiles = big - rem;
+    sc.total_tiles = sc.full_tiles + 2 * rem;
+  }
+  CUtensorMap tmO0 = tmA, tmO1 = tmA;
+  constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
+  if (EPI == EPI_QKV_SWIGLU) {
+    if (encode_tmap_bf16(&tmO0, a.epi.qkv, (uint64_t)3 * a.epi.D, (uint64_t)a.M, (uint64_t)a.epi.ld_qkv, 32, 32, 64)) return -1;
+    if (encode_tmap_bf16(&tmO1, a.epi.act, (uint64_t)a.epi.Hf, (uint64_t)a.M, (uint64_t)a.epi.ld_act, 32, 32, 64)) return -1;
+  } else if (EPI == EPI_RESID) {
+    if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
+  }
+  const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
+  auto kern = a.epi.prof ? gemm2_kernel<EPI, NEPI, G2_STAGES, true> : gemm2_kernel<EPI, NEPI, G2_STAGES, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[a.epi.prof ? 1 : 0]) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
+                   "cudaFuncSetAttribute(gemm2)"))
+      return -1;
+    attr_set[a.epi.prof ? 1 : 0] = true;
+  }
+  kern<<<2 * clusters, 128 + 32 * NEPI, smem_bytes, stream>>>(tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi);
+  return check_cuda(cudaGetLastError(), "gemm2 launch");
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// perf experiments: VTK_G2_STAGES (4 | 6), VTK_G2_NEPI (8 | 16)
+template <int EPI, int NEPI_DEFAULT>
+static int launch_gemm2_t(const GemmArgs& a, cudaStream_t stream) {
+  static const int stages = env_int("VTK_G2_STAGES", 6), nepi = env_int("VTK_G2_NEPI", NEPI_DEFAULT);
+  if (nepi == 8) return stages == 4 ? launch_gemm2_s<EPI, 8, 4>(a, stream) : launch_gemm2_s<EPI, 8, 6>(a, stream);
+  return stages == 4 ? launch_gemm2_s<EPI, 16, 4>(a, stream) : launch_gemm2_s<EPI, 16, 6>(a, stream);
+}
+
+static int gemm_pair_mode() {   // VTK_GEMM_PAIR=0 forces the single-CTA kernel (perf experiments)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VTK_GEMM_PAIR");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
+
+int launch_gemm_inner(EpiKind kind, const GemmArgs& a, cudaStream_t stream);
+
 static int epi_debug_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -557,9 +944,40 @@ static int epi_debug_mode() {
   return mode;
 }
 
+static unsigned long long* g_prof = nullptr;
+static int env_int(const char* name, int dflt);
+
+// VTK_GEMM_PROF=1: every pair-kernel launch is followed by a sync and a per-role cycle report on stderr.
+static void prof_report(const char* what, int NEPI) {
+  unsigned long long h[64];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, g_prof, sizeof(h), cudaMemcpyDeviceToHost);
+  const double n = h[7] ? (double)h[7] : 1.0;
+  fprintf(stderr, "[gemm prof] %s: per leader CTA: mma total %.0f cyc | mma wait full %.0f | mma wait tempty %.0f | producer wait empty %.0f | epi(w0) total %.0f\n",
+          what, h[2] / n, h[0] / n, h[1] / n, h[5] / (2 * n), h[6] / n);
+  fprintf(stderr, "[gemm prof]   epilogue warps wait-tfull / work (cycles per leader CTA):");
+  for (int i = 0; i < NEPI; ++i) fprintf(stderr, " %.0f/%.0f", h[8 + i] / n, h[8 + NEPI + i] / n);
+  fprintf(stderr, "\n");
+}
+
 int launch_gemm(EpiKind kind, const GemmArgs& a_in, cudaStream_t stream) {
   GemmArgs a = a_in;
   a.epi.debug = epi_debug_mode();
+  a.epi.prof = nullptr;
+  static int prof_mode = -1;
+  if (prof_mode < 0) { const char* e = getenv("VTK_GEMM_PROF"); prof_mode = e ? atoi(e) : 0; }
+  if (prof_mode) {
+    if (!g_prof) cudaMalloc(&g_prof, 64 * sizeof(unsigned long long));
+    cudaMemsetAsync(g_prof, 0, 64 * sizeof(unsigned long long), stream);
+    a.epi.prof = g_prof;
+    const int r = launch_gemm_inner(kind, a, stream);
+    if (r == 0) prof_report(kind == EPI_QKV_SWIGLU ? "qkv_swiglu" : kind == EPI_RESID ? "proj_resid" : "linear", env_int("VTK_G2_NEPI", 8));
+    return r;
+  }
+  return launch_gemm_inner(kind, a, stream);
+}
+
+int launch_gemm_inner(EpiKind kind, const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) { set_error("gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K); return -2; }
   if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.N % 8)) {
     set_error("gemm: K, N and the row strides must be multiples of 8 (K=%d N=%d lda=%lld ldb=%lld)", a.K, a.N, a.lda, a.ldb);
@@ -573,6 +991,7 @@ int launch_gemm(EpiKind kind, const GemmArgs& a_in, cudaStream_t stream) {
     case EPI_BIAS:
       if (a.N <= 64) return launch_gemm_t<64, EPI_BIAS, 8>(a, false, stream);
       if (a.N <= 128) return launch_gemm_t<128, EPI_BIAS, 8>(a, false, stream);
+      if (gemm_pair_mode() && a.M > BM) return launch_gemm2_t<EPI_BIAS, 8>(a, stream);
       return launch_gemm_t<256, EPI_BIAS, 16>(a, true, stream);
     case EPI_BIAS_LN:
       if (a.N % 16 || a.N > 256 || !a.epi.bias) { set_error("gemm: LN epilogue needs N%%16==0, N<=256 and a bias (N=%d)", a.N); return -2; }
@@ -585,9 +1004,11 @@ int launch_gemm(EpiKind kind, const GemmArgs& a_in, cudaStream_t stream) {
                   a.epi.d, a.epi.Hf, a.epi.qp);
         return -3;
       }
-      return launch_gemm_t<256, EPI_QKV_SWIGLU, 16>(a, true, stream);
+      if (gemm_pair_mode() && a.M > BM) return launch_gemm2_t<EPI_QKV_SWIGLU, 8>(a, stream);
+      return launch_gemm_t<256, EPI_QKV_SWIGLU, 8>(a, true, stream);
     case EPI_RESID:
-      return launch_gemm_t<256, EPI_RESID, 16>(a, true, stream);
+      if (gemm_pair_mode() && a.M > BM) return launch_gemm2_t<EPI_RESID, 8>(a, stream);
+      return launch_gemm_t<256, EPI_RESID, 8>(a, true, stream);
   }
   set_error("gemm: unknown epilogue %d", (int)kind);
   return -2;

@@ -45,10 +45,11 @@ struct EpiParams {
   long long ld_act;
   const bf16* normq;    // [d]
   const bf16* normk;    // [d]
-  const bf16* rope;     // [M, d]: cos[d/2] | sin[d/2], bf16-rounded
+  const bf16* rope;     // pair-expanded chunk-major table [ceil(M/32)*32, 2d] (see rope_table_kernel)
   int D, d, Hf, qp;     // qp = 3D rounded up to the tile width (start of the SwiGLU columns)
   // EPI_RESID
   const bf16* gamma;    // [N]
+  unsigned long long* prof;  // perf experiments only (env VTK_GEMM_PROF): per-role clock64 accumulators, or null
   int debug;            // perf experiments only (env VTK_EPI_DEBUG): 1 = no global stores, 2 = skip epilogue math+stores
 };
 

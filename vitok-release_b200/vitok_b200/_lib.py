@@ -160,10 +160,19 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor
 def rope_table(row_idx: torch.Tensor, col_idx: torch.Tensor, inv_freq: torch.Tensor, head_dim: int) -> torch.Tensor:
     _req(row_idx, torch.int64, "row_idx"); _req(col_idx, torch.int64, "col_idx"); _req(inv_freq, torch.float32, "inv_freq")
     M = row_idx.numel()
-    table = torch.empty(M, head_dim, dtype=torch.bfloat16, device=row_idx.device)
+    # pair-expanded, chunk-major layout (csrc/vtk_elementwise.cu: rope_table_kernel); decode with rope_table_decode
+    table = torch.zeros((M + 31) // 32 * 32, 2 * head_dim, dtype=torch.bfloat16, device=row_idx.device)
     check(load().vtk_rope_table(ptr(row_idx.contiguous()), ptr(col_idx.contiguous()), ptr(inv_freq), ptr(table), M,
                                 head_dim, stream_ptr()))
     return table
+
+
+def rope_table_decode(table: torch.Tensor, M: int, head_dim: int):
+    """Undo the kernel layout: returns (C2 [M, d], S2 [M, d]) with C2 = (c0,c0,c1,c1,..), S2 = (-s0,+s0,-s1,+s1,..)."""
+    d = head_dim
+    g = table.shape[0] // 32
+    t = table.reshape(g, 2 * d // 8, 32, 8).permute(0, 2, 1, 3).reshape(g * 32, 2 * d)[:M]
+    return t[:, :d], t[:, d:]
 
 
 def cast_to_bf16(x: torch.Tensor) -> torch.Tensor:
