@@ -74,7 +74,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "25"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
 
@@ -242,19 +242,49 @@ def run_ours(args, rank, world, local):
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
     d2h = host_out.numel() * host_out.element_size()
 
-    def e2e_step():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
-        o = step(d)
-        host_out.copy_(o["patches"], non_blocking=True)
+    # Double-buffered pipeline on three streams (copy-in / compute / copy-out): step i's H2D and step i-1's D2H
+    # overlap step i's kernels, the way a serving loop would drive the public API.  Every step still moves its
+    # own inputs host->device and its own result device->host inside the timed region.
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    s_main = torch.cuda.current_stream(dev)
+    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in host_in.items()} for _ in range(2)]
+    host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    for e in ev_free:
+        e.record(s_main)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_step(i):
+        b = i & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[b])                 # compute of step i-2 has consumed this input buffer
+            for k, v in host_in.items():
+                dev_in[b][k].copy_(v, non_blocking=True)
+            ev_in[b].record(s_in)
+        s_main.wait_event(ev_in[b])
+        o = step(dev_in[b])
+        ev_free[b].record(s_main)
+        ev_done[b].record(s_main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done[b])
+            o["patches"].record_stream(s_out)
+            host_outs[b].copy_(o["patches"], non_blocking=True)
+
+    def e2e_drain():
+        s_main.wait_stream(s_out)
+        s_main.wait_stream(s_in)
+
+    for i in range(4):
+        e2e_step(i)
+    e2e_drain()
     torch.cuda.synchronize()
     barrier(world)
     t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_ev0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    for i in range(args.steps):
+        e2e_step(i)
+    e2e_drain()
     t_ev1.record()
     torch.cuda.synchronize()
     barrier(world)

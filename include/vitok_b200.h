@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define VTK_ABI_VERSION 1
+#define VTK_ABI_VERSION 2
 
 typedef enum {
   VTK_OK = 0,
@@ -109,10 +109,12 @@ int vtk_proj_residual_bf16(const void* A, int64_t lda, const void* W, int64_t ld
 
 /* softmax(q k^T / sqrt(d)) v per (image, head); q,k,v,out rows = tokens, heads along columns.
  * kv_len/key_mask/is_prefix null = no masking (reference flash backend, modules/attention.py:109-117);
- * otherwise the sdpa backend's key masking (modules/attention.py:118-127). */
+ * otherwise the sdpa backend's key masking (modules/attention.py:118-127).
+ * window >= 0: sliding-window attention, query i sees keys j with |i - j| <= window on the token index, i.e.
+ * flash_attn_func(window_size=(window, window)) as called at modules/attention.py:113-116; window < 0 = full. */
 int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
                        const int* kv_len, const uint8_t* key_mask, const int* is_prefix, int B, int N, int heads, int d,
-                       int zero_invalid_rows, void* stream);
+                       int zero_invalid_rows, int window, void* stream);
 
 /* test-only: D[128,N] fp32 = A[128,K] * op(B) through one tcgen05 tile with explicit descriptor fields */
 int vtk_umma_probe(const void* A, const void* B, float* D, int N, int K, int b_mn_major, uint32_t lbo_bytes,
@@ -128,6 +130,7 @@ typedef struct {
   int32_t enc_width, enc_depth, enc_heads, enc_hidden; /* hidden = SwiGLU Hf; depth 0 = side absent */
   int32_t dec_width, dec_depth, dec_heads, dec_hidden;
   float norm_eps;                                       /* 1e-6 */
+  int32_t sliding_window;                               /* AE(sw=...), vitok/models/ae.py:90,99; <= 0 = full attention */
 } vtk_ae_config;
 
 typedef struct {

@@ -125,7 +125,7 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     return torch.stack([out_r, out_i], dim=-1).flatten(3)
 
 
-def attention_core(q, k, v, key_mask: Optional[torch.Tensor]) -> torch.Tensor:
+def attention_core(q, k, v, key_mask: Optional[torch.Tensor], window: Optional[int] = None) -> torch.Tensor:
     """softmax(q k^T / sqrt(d)) v, q/k/v [B, N, h, d] -> [B, N, h*d].
 
     key_mask None  = the flash backend (attention.py:109-117: all N keys).
@@ -139,6 +139,12 @@ def attention_core(q, k, v, key_mask: Optional[torch.Tensor]) -> torch.Tensor:
     s = torch.matmul(qf, kf.transpose(-1, -2)) / math.sqrt(d)
     if key_mask is not None:
         s = s.masked_fill(~key_mask[:, None, None, :], float("-inf"))
+    if window is not None and window >= 0:
+        # flash_attn_func(window_size=(w, w)) as called at attention.py:113-116: query i sees keys |i - j| <= w.
+        # flash-attn is a third-party CUDA-only dependency, so this branch restates its documented semantics
+        # (parity unpinned on CPU; tests/test_gpu_attention.py checks it against flash_attn itself on the GPU box).
+        idx = torch.arange(N)
+        s = s.masked_fill(((idx[:, None] - idx[None, :]).abs() > window)[None, None], float("-inf"))
     p = torch.softmax(s, dim=-1)
     p = torch.nan_to_num(p, nan=0.0)
     o = torch.matmul(p, vf)
@@ -148,7 +154,7 @@ def attention_core(q, k, v, key_mask: Optional[torch.Tensor]) -> torch.Tensor:
 
 
 def block_forward(sd: Dict[str, torch.Tensor], prefix: str, x, cos, sin, heads: int,
-                  key_mask: Optional[torch.Tensor]) -> torch.Tensor:
+                  key_mask: Optional[torch.Tensor], window: Optional[int] = None) -> torch.Tensor:
     """vitok/models/ae.py:55-65 (Block.forward), attention.py:92-129, mlp.py:20-23."""
     B, N, D = x.shape
     d = D // heads
@@ -158,7 +164,7 @@ def block_forward(sd: Dict[str, torch.Tensor], prefix: str, x, cos, sin, heads: 
     q = rms_norm(q, sd[prefix + "attn.norm_q.weight"])
     k = rms_norm(k, sd[prefix + "attn.norm_k.weight"])
     q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
-    a = attention_core(q, k, v, key_mask)
+    a = attention_core(q, k, v, key_mask, window)
     attn_out = F.linear(a, sd[prefix + "attn.out_proj.weight"])
     u = F.linear(h, sd[prefix + "ffn.fc1.weight"])
     val, gate = u.chunk(2, dim=-1)
@@ -178,15 +184,16 @@ def _depth(sd, side: str) -> int:
 
 
 def encode(sd: Dict[str, torch.Tensor], patch_dict: Dict[str, torch.Tensor], heads: int,
-           attn_backend: str = "sdpa", theta: float = 10000.0) -> Dict[str, torch.Tensor]:
-    """vitok/models/ae.py:189-216."""
+           attn_backend: str = "sdpa", theta: float = 10000.0, sw: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """vitok/models/ae.py:189-216.  sw = AE(sw=...) sliding window: flash backend only (attention.py:113-116)."""
+    window = sw if (attn_backend == "flash" and sw is not None and sw > 0) else None
     x = F.linear(patch_dict["patches"], sd["patch_embed.weight"], sd["patch_embed.bias"])
     D = x.shape[-1]
     cos, sin = rope_cos_sin(patch_dict["row_idx"], patch_dict["col_idx"], D // heads, theta)
     pm = patch_dict.get("patch_mask")
     key_mask = pm.bool() if (attn_backend == "sdpa" and pm is not None) else None
     for i in range(_depth(sd, "encoder")):
-        x = block_forward(sd, f"encoder_blocks.{i}.", x, cos, sin, heads, key_mask)
+        x = block_forward(sd, f"encoder_blocks.{i}.", x, cos, sin, heads, key_mask, window)
     z = layer_norm_noaffine(F.linear(x, sd["to_code.weight"], sd["to_code.bias"]))
     return {
         "patch_mask": patch_dict.get("patch_mask"), "row_idx": patch_dict["row_idx"],
@@ -196,15 +203,16 @@ def encode(sd: Dict[str, torch.Tensor], patch_dict: Dict[str, torch.Tensor], hea
 
 
 def decode(sd: Dict[str, torch.Tensor], enc: Dict[str, torch.Tensor], heads: int,
-           attn_backend: str = "sdpa", theta: float = 10000.0) -> Dict[str, torch.Tensor]:
+           attn_backend: str = "sdpa", theta: float = 10000.0, sw: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """vitok/models/ae.py:218-243."""
+    window = sw if (attn_backend == "flash" and sw is not None and sw > 0) else None
     x = F.linear(enc["z"], sd["decoder_embed.weight"], sd["decoder_embed.bias"])
     D = x.shape[-1]
     cos, sin = rope_cos_sin(enc["row_idx"], enc["col_idx"], D // heads, theta)
     pm = enc.get("patch_mask")
     key_mask = pm.bool() if (attn_backend == "sdpa" and pm is not None) else None
     for i in range(_depth(sd, "decoder")):
-        x = block_forward(sd, f"decoder_blocks.{i}.", x, cos, sin, heads, key_mask)
+        x = block_forward(sd, f"decoder_blocks.{i}.", x, cos, sin, heads, key_mask, window)
     return {
         "patch_mask": enc.get("patch_mask"), "row_idx": enc.get("row_idx"),
         "col_idx": enc.get("col_idx"), "orig_height": enc.get("orig_height"),

@@ -108,6 +108,37 @@ def test_c1_350M_vs_oracle(init, golden_dir):
     assert abs(z.mean(-1)).max() < 2e-2 and abs(z.var(-1, unbiased=False) - 1).max() < 5e-2   # LN bottleneck property
 
 
+@pytest.mark.parametrize("sw", [3, 40])
+def test_sliding_window_model(sw):
+    """AE(sw=...) (ae.py:90,99; attention.py:113-116): flash backend windows keys to |i - j| <= sw; sdpa ignores sw."""
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(SMALL)
+    sd = make_state_dict(cfg, seed=1, stress=True)
+    batch = _batch([(128, 128), (128, 128)], 16, 64, seed=7)
+    outs = {}
+    for backend in ("flash", "sdpa"):
+        m = vb.AE(**cfg, attn_backend=backend, sw=sw).eval()
+        m.load_state_dict(sd, strict=True)
+        m = m.to("cuda", torch.bfloat16)
+        with torch.no_grad():
+            enc = m.encode(_to_cuda(batch))
+            dec = m.decode(enc)
+        e_o = ae_oracle.encode(sd, batch, cfg["encoder_heads"], attn_backend=backend, sw=sw)
+        d_o = ae_oracle.decode(sd, e_o, cfg["decoder_heads"], attn_backend=backend, sw=sw)
+        report(f"sw={sw} {backend} z", enc["z"], e_o["z"], max_abs=8e-2, rel_fro=1.5e-2)
+        report(f"sw={sw} {backend} patches", dec["patches"], d_o["patches"], max_abs=8e-2, rel_fro=2e-2)
+        outs[backend] = dec["patches"]
+    # the window changes the result (flash) -- the sdpa backend equals the unwindowed model
+    m0 = vb.AE(**cfg, attn_backend="sdpa").eval()
+    m0.load_state_dict(sd, strict=True)
+    m0 = m0.to("cuda", torch.bfloat16)
+    with torch.no_grad():
+        ref = m0.decode(m0.encode(_to_cuda(batch)))["patches"]
+    assert torch.equal(ref, outs["sdpa"])
+    assert not torch.equal(ref, outs["flash"])
+    assert vb.AE(**cfg, sw=0).sw is None and vb.AE(**cfg, sw=-5).sw is None     # ae.py:99
+
+
 def test_state_dict_contract_and_halves():
     import vitok_b200 as vb
     cfg = vb.decode_variant(SMALL)

@@ -15,10 +15,10 @@ def L():
     return _lib
 
 
-def _ref(qkv, B, N, heads, d, mask):
+def _ref(qkv, B, N, heads, d, mask, window=None):
     t = qkv.cpu().reshape(B, N, 3, heads, d)
     q, k, v = t.unbind(2)
-    return ae_oracle.attention_core(q, k, v, mask.cpu() if mask is not None else None).reshape(B * N, heads * d)
+    return ae_oracle.attention_core(q, k, v, mask.cpu() if mask is not None else None, window).reshape(B * N, heads * d)
 
 
 @pytest.mark.parametrize("B,N,heads,d", [(2, 128, 2, 64), (2, 256, 4, 64), (1, 1024, 2, 64), (2, 256, 2, 128),
@@ -66,3 +66,28 @@ def test_masked_equals_unpadded(L):
     mask[0, :n] = True
     out = L.attention(padded, 1, N, heads, d, mask.cuda())
     assert torch.equal(out[:n], alone)
+
+
+@pytest.mark.parametrize("B,N,heads,d,w", [(2, 256, 2, 64, 16), (1, 1024, 2, 64, 100), (1, 1024, 2, 128, 128), (2, 512, 2, 128, 1),
+                                           (1, 640, 2, 64, 0), (1, 300, 2, 64, 37), (1, 1024, 1, 64, 5000), (1, 2048, 1, 128, 200)])
+def test_attention_sliding_window(L, B, N, heads, d, w):
+    """AE(sw=w) with the flash backend: |i - j| <= w (attention.py:113-116)."""
+    qkv = bf16_randn(B * N, 3 * heads * d, seed=45)
+    out = L.attention(qkv, B, N, heads, d, None, window=w)
+    report(f"attn window={w} N={N} d={d}", out, _ref(qkv, B, N, heads, d, None, w).float(), max_abs=3e-2, rel_fro=1e-2)
+
+
+@pytest.mark.parametrize("N,heads,d,w", [(512, 2, 64, 64), (1024, 2, 128, 100), (1024, 2, 64, -1)])
+def test_attention_vs_flash_attn_library(L, N, heads, d, w):
+    """The reference's flash backend IS flash_attn_func (third-party, pinned 2.8.3 in scripts/modal/modal_config.py);
+    when it is importable on the GPU box, compare against it directly, with and without window_size."""
+    fa = pytest.importorskip("flash_attn")
+    B = 2
+    qkv = bf16_randn(B * N, 3 * heads * d, seed=46)
+    out = L.attention(qkv, B, N, heads, d, None, window=w)
+    q, k, v = qkv.reshape(B, N, 3, heads, d).unbind(2)
+    try:
+        ref = fa.flash_attn_func(q.contiguous(), k.contiguous(), v.contiguous(), window_size=(w, w))
+    except RuntimeError as e:   # no kernel image for this device in the installed wheel
+        pytest.skip(f"flash_attn cannot run here: {e}")
+    report(f"attn vs flash_attn window={w} N={N} d={d}", out, ref.reshape(B * N, heads * d).float(), max_abs=2e-2, rel_fro=6e-3)

@@ -283,12 +283,13 @@ int vtk_proj_residual_bf16(const void* A, int64_t lda, const void* W, int64_t ld
 
 int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
                        const int* kv_len, const uint8_t* key_mask, const int* is_prefix, int B, int N, int heads, int d,
-                       int zero_invalid_rows, void* stream) {
+                       int zero_invalid_rows, int window, void* stream) {
   VTK_REQUIRE(q && k && v && out, "vtk_attention_bf16: null pointer");
   AttnArgs a;
   a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.ld_qkv = ld_qkv; a.out = (bf16*)out; a.ld_out = ld_out;
   a.kv_len = kv_len; a.key_mask = key_mask; a.prefix_flag = is_prefix; a.B = B; a.N = N; a.heads = heads; a.d = d;
   a.zero_invalid_rows = zero_invalid_rows;
+  a.window = window;
   return launch_attention(a, (cudaStream_t)stream);
 }
 
@@ -401,6 +402,8 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
     a.q = w.qkv; a.k = w.qkv + D; a.v = w.qkv + 2 * D; a.ld_qkv = 3 * D; a.out = w.a2; a.ld_out = kp;
     a.kv_len = patch_mask ? w.kv_len : nullptr; a.key_mask = patch_mask; a.prefix_flag = patch_mask ? w.is_prefix : nullptr;
     a.B = B; a.N = N; a.heads = s.heads; a.d = d; a.zero_invalid_rows = patch_mask ? 1 : 0;
+    // sliding window: flash backend only (attention.py:113-116); the sdpa backend (patch_mask given) ignores it
+    a.window = (!patch_mask && h->cfg.sliding_window > 0) ? h->cfg.sliding_window : -1;
     { LaunchTimer t(h, st, CLS_ATTENTION); r = launch_attention(a, st); }
     if (r) return r;
     GemmArgs g2 = base_args(w.a2, kp, b.w_out, kp, D, M, D, D + Hf);

@@ -20,6 +20,7 @@
 // V is consumed as an MN-major B operand straight from its [key, d] layout (no transpose pass).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "vtk_common.cuh"
 #include "vtk_kernels.h"
@@ -31,40 +32,55 @@ static constexpr int ATT_BKV = 128;  // keys per tile
 static constexpr int BLK = 16384;    // one [128 x 64] bf16 swizzled block
 static constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
-template <int DH> struct AttnShape {
+// NQ = query tiles per CTA.  NQ = 2 (one CTA per SM): two softmax warpgroups ping-pong on the tensor core and
+// share every K/V tile.  NQ = 1 (d = 64 only): 112 KB of shared memory and 256 TMEM columns, so TWO CTAs are
+// resident per SM and hide each other's load / MMA / store latencies -- the better shape for the short
+// sequences of the 256 px configs (N = 256: two K/V tiles per CTA, latency-bound otherwise).
+template <int DH, int NQ> struct AttnShape {
   static constexpr int NB = DH / 64;               // 64-column blocks per head
   static constexpr int TILE_BYTES = NB * BLK;      // one Q / K / V tile
   static constexpr int RK = 2;                     // K ring slots
   static constexpr int RV = (DH == 64) ? 2 : 1;    // V ring slots (227 KB smem budget at d = 128)
   static constexpr int P_BYTES = 2 * BLK;          // 128 x 128 bf16
-  static constexpr int OFF_Q = 0;                  // Q_a, Q_b
-  static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
+  static constexpr int OFF_Q = 0;                  // Q_a (, Q_b)
+  static constexpr int OFF_K = OFF_Q + NQ * TILE_BYTES;
   static constexpr int OFF_V = OFF_K + RK * TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + RV * TILE_BYTES;      // P_a, P_b
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr uint32_t TMEM_COLS = 512;       // S_a [0,128) S_b [128,256) O_a [256,256+DH) O_b [256+DH, 256+2DH)
+  static constexpr int OFF_P = OFF_V + RV * TILE_BYTES;      // P_a (, P_b)
+  static constexpr int OFF_BAR = OFF_P + NQ * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;           // the dynamic smem base is declared 1024-byte aligned
+  static constexpr uint32_t TMEM_COLS = NQ == 2 ? 512 : 256; // S_q at [q*128, +128), O_q at [NQ*128 + q*DH, +DH)
+  static constexpr int O_COL0 = NQ * 128;
+  static constexpr int THREADS = 128 * NQ + 64;
+  static constexpr int WARP_TMA = 4 * NQ, WARP_MMA = 4 * NQ + 1;
 };
 
 struct AttnParams {
   bf16* out; long long ld_out;
   const int* kv_len; const uint8_t* key_mask; const int* prefix_flag;
-  int N, heads, zero_invalid;
+  int N, heads, zero_invalid, tma_out;
+  int window;         // sliding window |i - j| <= window on the token index (flash backend, attention.py:113-116); < 0 = none
   float scale_log2;   // (1/sqrt(d)) * log2(e)
+  unsigned long long* prof;   // perf experiments (env VTK_ATTN_PROF): clock64 accumulators, or null
 };
 
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-template <int DH>
-__global__ void __launch_bounds__(320, 1)
+template <int DH, int NQ>
+__global__ void __launch_bounds__(128 * NQ + 64, NQ == 1 ? 2 : 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-            const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using S = AttnShape<DH>;
-  const int q0 = blockIdx.x * (2 * ATT_BQ);
+            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+  using S = AttnShape<DH, NQ>;
+  const long long t_cta0 = p.prof ? clock64() : 0;
+  const int q0 = blockIdx.x * (NQ * ATT_BQ);
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const int warp = threadIdx.x >> 5;
@@ -75,10 +91,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const long long row0 = (long long)img * N;
   const int T = (kvlen + ATT_BKV - 1) / ATT_BKV;
   const int qlimit = p.zero_invalid ? kvlen : N;           // query rows >= qlimit are padding
-  const int nact = (T == 0 || q0 >= qlimit) ? 0 : ((q0 + ATT_BQ < qlimit) ? 2 : 1);
+  const int nact = (T == 0 || q0 >= qlimit) ? 0 : ((NQ == 2 && q0 + ATT_BQ < qlimit) ? 2 : 1);
 
   // query tiles with nothing to attend to: define the output as 0 (uniform per warpgroup)
-  if (warp < 8) {
+  if (warp < 4 * NQ) {
     const int wg = warp >> 2;
     if (wg >= nact) {
       const int qi = q0 + wg * ATT_BQ + (warp & 3) * 32 + lane;
@@ -89,9 +105,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     }
   }
   if (nact == 0) return;   // whole CTA
+  // key tiles this CTA visits: all T, or only those intersecting the sliding window of its query rows
+  const int W = p.window;
+  int j_lo = 0, j_hi = T - 1;
+  if (W >= 0) {
+    const int q_last = min(q0 + nact * ATT_BQ, N) - 1;
+    j_lo = max(0, q0 - W) / ATT_BKV;
+    j_hi = min(T - 1, (int)min((long long)q_last + W, (long long)N - 1) / ATT_BKV);
+  }
+  const int Tn = j_hi - j_lo + 1;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem + S::OFF_Q;
   uint8_t* sK = smem + S::OFF_K;
   uint8_t* sV = smem + S::OFF_V;
@@ -108,28 +132,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* pv_done = s_full + 6;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&pv_done[i], 1);
+  if (warp == S::WARP_TMA) {
+    // 17 mbarriers, one lane each: [0] q_full | k_full[2] k_empty[2] v_full[2] v_empty[2] | s_full[2] s_empty[2] p_full[2] pv_done[2]
+    if (lane < 17) {
+      const bool wg_count = (lane >= 11 && lane <= 14);   // s_empty, p_full: all 128 softmax threads arrive
+      mbar_init(&bars[lane], wg_count ? 128u : 1u);
+    } else if (lane == 17) {
+      tma_prefetch_desc(&tmQ);
+    } else if (lane == 18) {
+      tma_prefetch_desc(&tmK);
+    } else if (lane == 19) {
+      tma_prefetch_desc(&tmV);
     }
     fence_barrier_init();
+    __syncwarp();
   }
-  if (warp == 9) {
+  if (warp == S::WARP_MMA) {
     tmem_alloc(tmem_slot, S::TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == S::WARP_TMA && lane == 0) {
     // Q tiles and K_0 go out before the CTA-wide sync: their latency overlaps the TMEM allocation
     mbar_expect_tx(q_full, (uint32_t)(nact * S::TILE_BYTES));
     for (int t = 0; t < nact; ++t)
@@ -137,36 +159,37 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tma_load_2d(sQ + t * S::TILE_BYTES + nb * BLK, &tmQ, q_full, head * DH + nb * 64, (int)(row0 + q0 + t * ATT_BQ));
     mbar_expect_tx(&k_full[0], S::TILE_BYTES);
     for (int nb = 0; nb < S::NB; ++nb)
-      tma_load_2d(sK + nb * BLK, &tmK, &k_full[0], head * DH + nb * 64, (int)row0);
+      tma_load_2d(sK + nb * BLK, &tmK, &k_full[0], head * DH + nb * 64, (int)(row0 + (long long)j_lo * ATT_BKV));
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long t_sync = p.prof ? clock64() : 0;
 
-  if (warp == 8) {
+  if (warp == S::WARP_TMA) {
     if (lane == 0) {
       // ===== TMA producer ===== (Q and K_0 were issued before the sync)
       // issue order K_0, K_1, V_0, K_2, V_1, ...: K_{j+1} is needed (for S(j+1)) before V_j (for PV(j))
-      auto load_k = [&](int j) {
-        const int slot = j % S::RK;
-        mbar_wait(&k_empty[slot], ((uint32_t)(j / S::RK) & 1u) ^ 1u);
+      auto load_k = [&](int jj) {   // jj = position in this CTA's tile sequence; key tile index = j_lo + jj
+        const int slot = jj % S::RK;
+        mbar_wait(&k_empty[slot], ((uint32_t)(jj / S::RK) & 1u) ^ 1u);
         mbar_expect_tx(&k_full[slot], S::TILE_BYTES);
         for (int nb = 0; nb < S::NB; ++nb)
           tma_load_2d(sK + slot * S::TILE_BYTES + nb * BLK, &tmK, &k_full[slot], head * DH + nb * 64,
-                      (int)(row0 + (long long)j * ATT_BKV));
+                      (int)(row0 + (long long)(j_lo + jj) * ATT_BKV));
       };
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) load_k(j + 1);
-        const int slot = j % S::RV;
-        mbar_wait(&v_empty[slot], ((uint32_t)(j / S::RV) & 1u) ^ 1u);
+      for (int jj = 0; jj < Tn; ++jj) {
+        if (jj + 1 < Tn) load_k(jj + 1);
+        const int slot = jj % S::RV;
+        mbar_wait(&v_empty[slot], ((uint32_t)(jj / S::RV) & 1u) ^ 1u);
         mbar_expect_tx(&v_full[slot], S::TILE_BYTES);
         for (int nb = 0; nb < S::NB; ++nb)
           tma_load_2d(sV + slot * S::TILE_BYTES + nb * BLK, &tmV, &v_full[slot], head * DH + nb * 64,
-                      (int)(row0 + (long long)j * ATT_BKV));
+                      (int)(row0 + (long long)(j_lo + jj) * ATT_BKV));
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == S::WARP_MMA) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);
@@ -196,7 +219,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           const uint64_t adesc = make_desc_kmajor_sw128(pa + (kk >> 2) * BLK + (kk & 3) * 32);
           // V tile: NB blocks of [128 keys x 64 d]; MN-major: LBO = block stride, SBO = 8-key group stride
           const uint64_t bdesc = make_smem_desc(va + kk * 2048, BLK, 1024, 2);
-          umma_bf16_ss(tmem_base + 256 + q * DH, adesc, bdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_base + S::O_COL0 + q * DH, adesc, bdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&pv_done[q]);
       };
@@ -207,9 +230,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         for (int q = 0; q < nact; ++q) issue_s(q, ka);
         umma_commit(&k_empty[0]);
       }
-      for (int j = 0; j < T; ++j) {
+      for (int j = 0; j < Tn; ++j) {   // j = position in the tile sequence
         const uint32_t jp = (uint32_t)j & 1u;
-        if (j + 1 < T) {   // S(j+1) as soon as the softmax threads have pulled S(j) into registers
+        if (j + 1 < Tn) {   // S(j+1) as soon as the softmax threads have pulled S(j) into registers
           const uint32_t ka = k_wait(j + 1);
           for (int q = 0; q < nact; ++q) {
             mbar_wait(&s_empty[q], jp);
@@ -234,16 +257,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const uint32_t tS = tmem_base + lane_base + q * 128;
-    const uint32_t tO = tmem_base + lane_base + 256 + q * DH;
+    const uint32_t tO = tmem_base + lane_base + S::O_COL0 + q * DH;
     const bool general_mask = p.key_mask != nullptr && !(p.prefix_flag != nullptr && p.prefix_flag[img] != 0);
     const uint8_t* kmask = general_mask ? p.key_mask + row0 : nullptr;
     uint8_t* prow = sP + q * S::P_BYTES + r * 128;
     const float sc = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const int kv0 = j * ATT_BKV;
-      const bool need_mask = (kv0 + ATT_BKV > kvlen) || (kmask != nullptr);
+    long long w_s = 0, w_pv = 0, t_first = 0;
+    const int qi = q0 + q * ATT_BQ + r;
+    for (int j = 0; j < Tn; ++j) {   // j = position in the tile sequence
+      const int kv0 = (j_lo + j) * ATT_BKV;
+      const int qt0 = q0 + q * ATT_BQ;
+      const bool win_mask = W >= 0 && (kv0 < qt0 + ATT_BQ - 1 - W || kv0 + ATT_BKV - 1 > qt0 + W);
+      const bool need_mask = (kv0 + ATT_BKV > kvlen) || (kmask != nullptr) || win_mask;
+      const long long ta = p.prof ? clock64() : 0;
       mbar_wait(&s_full[q], (uint32_t)j & 1u);
+      if (p.prof) { const long long tb = clock64(); if (j == 0) t_first = tb - t_sync; else w_s += tb - ta; }
       __syncwarp();
       tc_fence_after();
       uint32_t v[4][32];
@@ -260,17 +289,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int kc = kv0 + c * 32 + i;
-            const bool ok = kc < kvlen && (kmask == nullptr || kmask[kc] != 0);
+            const bool ok = kc < kvlen && (kmask == nullptr || kmask[kc] != 0) && (W < 0 || abs(kc - qi) <= W);
             if (!ok) v[c][i] = 0xff800000u;   // -inf
           }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(v[0][i]));
-        mx1 = fmaxf(mx1, __uint_as_float(v[1][i]));
-        mx2 = fmaxf(mx2, __uint_as_float(v[2][i]));
-        mx3 = fmaxf(mx3, __uint_as_float(v[3][i]));
+      for (int i = 0; i < 32; i += 2) {   // FMNMX3: two elements per instruction
+        mx0 = max3f(mx0, __uint_as_float(v[0][i]), __uint_as_float(v[0][i + 1]));
+        mx1 = max3f(mx1, __uint_as_float(v[1][i]), __uint_as_float(v[1][i + 1]));
+        mx2 = max3f(mx2, __uint_as_float(v[2][i]), __uint_as_float(v[2][i + 1]));
+        mx3 = max3f(mx3, __uint_as_float(v[3][i]), __uint_as_float(v[3][i + 1]));
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
       // lazy rescale: keep the stale max unless it moved by more than 2^8
@@ -280,33 +309,43 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_use);
       }
       const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
-      float sum0 = 0.f, sum1 = 0.f;
-      uint32_t pk[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), sc, -m_sub));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), sc, -m_sub));
-          sum0 += e0;
-          sum1 += e1;
-          // bf16 round-to-nearest (ties up) on the integer pipe: keeps the XU pipe for ex2 only
-          pk[c * 16 + i] = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);
-        }
-      l_run = l_run * alpha + (sum0 + sum1);
-      m_run = m_use;
-      // P buffer and O are free once PV(j-1) has completed
+      // packed pipeline per key pair: FFMA2 (scale, subtract max) -> 2 x MUFU.EX2 -> FADD2 (row sum) ->
+      // F2FP.BF16.PACK_AB (P as bf16x2, round to nearest even): 2.5 issue slots per element, XU does ex2 only
+      const uint64_t sc2 = f2_pack(sc, sc), nm2 = f2_pack(-m_sub, -m_sub);
+      uint64_t sum2a = 0ull, sum2b = 0ull;
+      // P buffer and O are free once PV(j-1) has completed (it was issued a whole softmax tile ago)
       if (j > 0) {
+        const long long tc = p.prof ? clock64() : 0;
         mbar_wait(&pv_done[q], (uint32_t)(j - 1) & 1u);
+        if (p.prof) w_pv += clock64() - tc;
         __syncwarp();
         tc_fence_after();
       }
-      // 128 columns = 2 blocks x 8 chunks of 16 B; swizzle-128B: chunk' = chunk ^ (row & 7)
+      // 128 columns = 2 blocks x 8 chunks of 16 B; swizzle-128B: chunk' = chunk ^ (row & 7); each 16-byte chunk
+      // (8 keys) is written as soon as it is exponentiated
 #pragma unroll
-      for (int g = 0; g < 16; ++g) {
-        const int blk = g >> 3, ch = (g & 7) ^ (r & 7);
-        *reinterpret_cast<uint4*>(prow + blk * BLK + (ch << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      }
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float e0, e1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][8 * g + 2 * i]), __uint_as_float(v[c][8 * g + 2 * i + 1])), sc2, nm2), e0, e1);
+            e0 = ex2_approx(e0);
+            e1 = ex2_approx(e1);
+            if (i & 1) sum2b = f2_add(sum2b, f2_pack(e0, e1));
+            else sum2a = f2_add(sum2a, f2_pack(e0, e1));
+            pk[i] = bf2_cvt(e0, e1);
+          }
+          const int gg = c * 4 + g;   // 16-byte chunk index 0..15 along the 128 keys
+          const int blk = gg >> 3, ch = (gg & 7) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + blk * BLK + (ch << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      float sum0, sum1;
+      f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
+      l_run = l_run * alpha + (sum0 + sum1);
+      m_run = m_use;
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
         for (int c = 0; c < DH; c += 32) {
@@ -324,11 +363,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       mbar_arrive(&p_full[q]);
     }
     // epilogue: O / l
-    mbar_wait(&pv_done[q], (uint32_t)(T - 1) & 1u);
+    const long long td = p.prof ? clock64() : 0;
+    mbar_wait(&pv_done[q], (uint32_t)(Tn - 1) & 1u);
+    const long long te = p.prof ? clock64() : 0;
     __syncwarp();
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    const int qi = q0 + q * ATT_BQ + r;
     bool zero_row = false;
     if (p.zero_invalid) zero_row = (qi >= kvlen) || (kmask != nullptr && qi < N && kmask[qi] == 0);
     const float osc = zero_row ? 0.f : inv;
@@ -337,7 +377,33 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 #pragma unroll
     for (int c = 0; c < DH / 32; ++c) tmem_ld32(tO + c * 32, o[c]);
     tmem_wait_ld();
-    if (qi < N) {
+    if (p.tma_out) {
+      // N % 128 == 0: the tile never straddles an image.  Stage this warp's 32 rows in the (now idle) Q buffer
+      // in the 128B-swizzled layout and let one TMA store per 64-column block write full 128-byte row segments.
+      uint8_t* srow = sQ + q * S::TILE_BYTES + r * 128;
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            w[i] = bf2_cvt(__uint_as_float(o[c][8 * g + 2 * i]) * osc, __uint_as_float(o[c][8 * g + 2 * i + 1]) * osc);
+          const int col = c * 32 + 8 * g;   // column inside the head
+          const int ch = ((col & 63) >> 3) ^ (r & 7);
+          *reinterpret_cast<uint4*>(srow + (col >> 6) * BLK + (ch << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int nb = 0; nb < S::NB; ++nb)
+          tma_store_2d(&tmO, sQ + q * S::TILE_BYTES + nb * BLK + quarter * 32 * 128, head * DH + nb * 64,
+                       (int)(row0 + q0 + q * ATT_BQ + quarter * 32));
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+    } else if (qi < N) {
 #pragma unroll
       for (int c = 0; c < DH / 32; ++c)
 #pragma unroll
@@ -349,32 +415,55 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           st_global_v4(op + c * 32 + 8 * g, w[0], w[1], w[2], w[3]);
         }
     }
+    if (p.prof && warp == 0 && lane == 0) {
+      const long long tf = clock64();
+      atomicAdd(&p.prof[0], (unsigned long long)(t_sync - t_cta0));   // prologue up to the CTA-wide sync
+      atomicAdd(&p.prof[1], (unsigned long long)t_first);             // sync -> first S ready (Q/K load + S MMA)
+      atomicAdd(&p.prof[2], (unsigned long long)w_s);                 // later waits for S
+      atomicAdd(&p.prof[3], (unsigned long long)w_pv);                // waits for PV(j-1) inside the loop
+      atomicAdd(&p.prof[4], (unsigned long long)(te - td));           // wait for the last PV
+      atomicAdd(&p.prof[5], (unsigned long long)(tf - te));           // O epilogue
+      atomicAdd(&p.prof[6], (unsigned long long)(tf - t_cta0));       // whole CTA
+      atomicAdd(&p.prof[7], 1ull);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == S::WARP_MMA) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, S::TMEM_COLS);
   }
 }
 
-template <int DH>
+template <int DH, int NQ>
 static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
-  using S = AttnShape<DH>;
+  using S = AttnShape<DH, NQ>;
   const long long Mrows = (long long)a.B * a.N;
   const long long cols = (long long)a.heads * a.d;
   CUtensorMap tmQ, tmK, tmV;
   if (encode_tmap_bf16_sw128(&tmQ, a.q, cols, Mrows, a.ld_qkv, ATT_BQ)) return -1;
   if (encode_tmap_bf16_sw128(&tmK, a.k, cols, Mrows, a.ld_qkv, ATT_BKV)) return -1;
   if (encode_tmap_bf16_sw128(&tmV, a.v, cols, Mrows, a.ld_qkv, ATT_BKV)) return -1;
+  CUtensorMap tmO;
+  if (encode_tmap_bf16(&tmO, a.out, cols, Mrows, a.ld_out, 64, 32, 128)) return -1;
   AttnParams p;
   p.out = a.out; p.ld_out = a.ld_out;
   p.kv_len = a.kv_len; p.key_mask = a.key_mask; p.prefix_flag = a.prefix_flag;
   p.N = a.N; p.heads = a.heads; p.zero_invalid = a.zero_invalid_rows;
+  p.tma_out = (a.N % ATT_BQ == 0) ? 1 : 0;
+  p.window = a.window;
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
-  auto kern = attn_kernel<DH>;
+  static const int prof_mode = getenv("VTK_ATTN_PROF") ? atoi(getenv("VTK_ATTN_PROF")) : 0;
+  static unsigned long long* d_prof = nullptr;
+  p.prof = nullptr;
+  if (prof_mode) {
+    if (!d_prof) cudaMalloc(&d_prof, 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), stream);
+    p.prof = d_prof;
+  }
+  auto kern = attn_kernel<DH, NQ>;
   static bool attr_set = false;
   if (!attr_set) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES),
@@ -382,16 +471,28 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
       return -1;
     attr_set = true;
   }
-  dim3 grid((a.N + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a.heads, a.B);
-  kern<<<grid, 320, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  dim3 grid((a.N + NQ * ATT_BQ - 1) / (NQ * ATT_BQ), a.heads, a.B);
+  kern<<<grid, S::THREADS, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  if (prof_mode) {
+    unsigned long long h[8];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    const double n = h[7] ? (double)h[7] : 1.0;
+    fprintf(stderr, "[attn prof] d=%d NQ=%d N=%d: per CTA cycles: prologue %.0f | first S ready %.0f | wait S %.0f | wait PV in loop %.0f | "
+            "wait last PV %.0f | epilogue %.0f | total %.0f (softmax+rest %.0f)\n", DH, NQ, a.N, h[0] / n, h[1] / n, h[2] / n, h[3] / n,
+            h[4] / n, h[5] / n, h[6] / n, (h[6] - h[0] - h[1] - h[2] - h[3] - h[4] - h[5]) / n);
+  }
   return check_cuda(cudaGetLastError(), "attention launch");
 }
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.B <= 0 || a.N <= 0 || a.heads <= 0) { set_error("attention: empty problem"); return -2; }
   if ((a.ld_qkv % 8) || (a.ld_out % 8)) { set_error("attention: row strides must be multiples of 8"); return -2; }
-  if (a.d == 64) return launch_attention_t<64>(a, stream);
-  if (a.d == 128) return launch_attention_t<128>(a, stream);
+  if (a.d == 64) {
+    static const int nq = getenv("VTK_ATTN_NQ") ? atoi(getenv("VTK_ATTN_NQ")) : 1;   // perf experiments: 2 = one CTA per SM
+    return nq == 2 ? launch_attention_t<64, 2>(a, stream) : launch_attention_t<64, 1>(a, stream);
+  }
+  if (a.d == 128) return launch_attention_t<128, 2>(a, stream);
   set_error("attention: head_dim %d unsupported (64 or 128)", a.d);
   return -3;
 }

@@ -47,6 +47,63 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
   }
 }
 
+// Single-pass variant: the row (D <= NV * 256 elements) stays in registers between the sum of squares and the
+// scaling, so x is read from HBM/L2 exactly once.  One warp per row, 16-byte vectors, lane-strided (coalesced).
+template <int NV>
+__global__ void __launch_bounds__(256) rmsnorm_reg_kernel(const bf16* __restrict__ x, long long ldx,
+                                                          const bf16* __restrict__ w, bf16* __restrict__ y,
+                                                          long long ldy, int M, int D, float eps) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  const float inv_d = 1.f / (float)D;
+  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
+       row += (long long)gridDim.x * warps_per_block) {
+    const bf16* xr = x + row * ldx;
+    uint4 q[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      q[i] = v < nvec ? ld_global_v4(xr + 8 * v) : make_uint4(0, 0, 0, 0);
+    }
+    uint64_t ss2 = 0ull;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t u[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t t = bf2_to_f2(u[k]);
+        ss2 = f2_fma(t, t, ss2);
+      }
+    }
+    float s0, s1;
+    f2_unpack(ss2, s0, s1);
+    float ss = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * inv_d + eps);
+    const uint64_t rstd2 = f2_pack(rstd, rstd);
+    bf16* yr = y + row * ldy;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const uint4 g = ld_global_nc_v4(w + 8 * v);
+        const uint32_t u[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+        const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a, b;
+          f2_unpack(f2_mul(f2_mul(bf2_to_f2(u[k]), rstd2), bf2_to_f2(gw[k])), a, b);
+          o[k] = bf2_cvt(a, b);
+        }
+        st_global_v4(yr + 8 * v, o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, int M, int D, float eps,
                    cudaStream_t stream) {
   if (D % 8 || ldx % 8 || ldy % 8) { set_error("rmsnorm: D and strides must be multiples of 8"); return -2; }
@@ -55,7 +112,10 @@ int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long lo
   long long blocks = ((long long)M + wpb - 1) / wpb;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  rmsnorm_kernel<<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
+  if (D <= 1024) rmsnorm_reg_kernel<4><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
+  else if (D <= 3072) rmsnorm_reg_kernel<12><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
+  else if (D <= 4096) rmsnorm_reg_kernel<16><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
+  else rmsnorm_kernel<<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
   return check_cuda(cudaGetLastError(), "rmsnorm launch");
 }
 

@@ -80,6 +80,7 @@ struct AttnArgs {
   const int* prefix_flag;       // [B] or null: 1 = key_mask[b] is a pure prefix (kv_len alone describes it)
   int B, N, heads, d;
   int zero_invalid_rows;        // 1: rows >= kv_len[b] (or with key_mask 0) are written as 0
+  int window;                   // sliding window: keys j with |i - j| <= window (flash_attn window_size=(w,w)); < 0 = none
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 

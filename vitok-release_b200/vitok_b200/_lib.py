@@ -27,7 +27,7 @@ class AEConfig(ctypes.Structure):
                 ("enc_hidden", ctypes.c_int32),
                 ("dec_width", ctypes.c_int32), ("dec_depth", ctypes.c_int32), ("dec_heads", ctypes.c_int32),
                 ("dec_hidden", ctypes.c_int32),
-                ("norm_eps", ctypes.c_float)]
+                ("norm_eps", ctypes.c_float), ("sliding_window", ctypes.c_int32)]
 
 
 class BlockWeights(ctypes.Structure):
@@ -53,7 +53,7 @@ SIGNATURES = {
                                     c_f32, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "vtk_proj_residual_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_attention_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
-                                   c_int, c_vp]),
+                                   c_int, c_int, c_vp]),
     "vtk_umma_probe": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u32, c_u32, c_u32, c_vp]),
     "vtk_ae_create": (c_int, [ctypes.POINTER(AEConfig), ctypes.POINTER(c_vp)]),
     "vtk_ae_destroy": (c_int, [c_vp]),
@@ -210,8 +210,10 @@ def proj_residual(a, w, gamma, x):
     return x
 
 
-def attention(qkv: torch.Tensor, B: int, N: int, heads: int, d: int, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """qkv [B*N, 3*heads*d] (q | k | v).  mask [B,N] bool -> sdpa semantics; None -> flash semantics."""
+def attention(qkv: torch.Tensor, B: int, N: int, heads: int, d: int, mask: Optional[torch.Tensor] = None,
+              window: int = -1) -> torch.Tensor:
+    """qkv [B*N, 3*heads*d] (q | k | v).  mask [B,N] bool -> sdpa semantics; None -> flash semantics.
+    window >= 0: sliding window |i - j| <= window (flash_attn window_size=(window, window))."""
     D = heads * d
     out = torch.empty(B * N, D, dtype=torch.bfloat16, device=qkv.device)
     kl = pf = m8 = None
@@ -220,7 +222,7 @@ def attention(qkv: torch.Tensor, B: int, N: int, heads: int, d: int, mask: Optio
         kl, pf = kv_len(mask)
     base = qkv.data_ptr()
     check(load().vtk_attention_bf16(base, base + 2 * D, base + 4 * D, qkv.stride(0), ptr(out), out.stride(0), ptr(kl),
-                                    ptr(m8), ptr(pf), B, N, heads, d, 1 if mask is not None else 0, stream_ptr()))
+                                    ptr(m8), ptr(pf), B, N, heads, d, 1 if mask is not None else 0, int(window), stream_ptr()))
     return out
 
 

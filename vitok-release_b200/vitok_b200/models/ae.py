@@ -14,7 +14,9 @@ Semantics kept from the reference (file:line in the reference tree):
     ``attn_backend="sdpa"``: keys masked by patch_mask (ae.py:173-187, attention.py:118-127).  Both
     run on the same tcgen05 attention kernel; padded keys are skipped, not masked after the fact;
   * unknown kwargs ignored (ae.py:92); ``sw <= 0`` -> None (ae.py:99).
-Not implemented yet (raise): sliding-window attention ``sw``, FP8 ``quantize()``, autograd/backward.
+``sw``: sliding-window attention |i-j| <= sw on the token index with the flash backend (attention.py:113-116);
+    ignored by the sdpa backend, as in the reference.
+Not implemented yet (raise): FP8 ``quantize()``, autograd/backward.
 """
 from __future__ import annotations
 
@@ -259,6 +261,7 @@ class AE(nn.Module):
                 cfg.dec_width, cfg.dec_depth, cfg.dec_heads = self.decoder_width, self.decoder_depth, self.decoder_heads
                 cfg.dec_hidden = _ffn_hidden(self.decoder_width, self.mlp_factor)
             cfg.norm_eps = 1e-6
+            cfg.sliding_window = int(self.sw) if self.sw else 0
             h = ctypes.c_void_p()
             _lib.check(lib.vtk_ae_create(ctypes.byref(cfg), ctypes.byref(h)))
             self._handle = h.value
@@ -301,8 +304,6 @@ class AE(nn.Module):
         return ws
 
     def _run(self, side: int, x: torch.Tensor, d: Dict[str, torch.Tensor], out_cols: int) -> torch.Tensor:
-        if self.sw is not None:
-            raise NotImplementedError("vitok_b200.AE: sliding-window attention (sw) is not implemented yet")
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("vitok_b200.AE: backward is not implemented yet; call model.eval() / torch.no_grad()")
         if not x.is_cuda:
