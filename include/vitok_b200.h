@@ -114,7 +114,54 @@ int vtk_proj_residual_bf16(const void* A, int64_t lda, const void* W, int64_t ld
  * flash_attn_func(window_size=(window, window)) as called at modules/attention.py:113-116; window < 0 = full. */
 int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
                        const int* kv_len, const uint8_t* key_mask, const int* is_prefix, int B, int N, int heads, int d,
-                       int zero_invalid_rows, int window, void* stream);
+                       int zero_invalid_rows, int window, float* lse, void* stream);
+/* lse (optional, may be null): [B*N, heads] fp32, log2-domain logsumexp of the scaled scores (+inf for zeroed rows);
+ * the training backward (vtk_attention_bwd_bf16) consumes it. */
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step (BASELINE config 5; scripts/train_vae.py:304-320,371-372 = forward, Charbonnier loss, backward,
+ * AdamW).  The GEMMs of forward and backward are vtk_linear_bf16 calls (dgrad against transposed weight copies,
+ * wgrad on vtk_transpose_bf16'd activations); everything else is below.  All tensors bf16 unless noted;
+ * gradient accumulators of norm weights / gamma / biases are fp32 and ADDED to (zero them first).
+ * ---------------------------------------------------------------------------------------------- */
+/* zraw [M, >=3D] raw q|k|v -> qkv [M,3D]: QK-RMSNorm over d + 2D RoPE, v copied (modules/attention.py:95-107) */
+int vtk_qk_norm_rope_fwd(const void* zraw, int64_t ldz, const void* norm_q, const void* norm_k, const void* rope_table,
+                         void* qkv, int64_t ld_qkv, int M, int heads, int d, float eps, void* stream);
+/* zraw[:, qp:] (16-col groups value|gate, the packed fc1 order) -> act [M,Hf] = silu(g) * v (modules/mlp.py:21-22) */
+int vtk_swiglu_fwd(const void* zraw, int64_t ldz, int qp, void* act, int64_t ld_act, int M, int Hf, void* stream);
+/* out = x + gamma * y (vitok/models/ae.py:64-65); contiguous [M,D] */
+int vtk_resid_fwd(const void* x, const void* y, const void* gamma, void* out, int M, int D, void* stream);
+/* out = LayerNorm_noaffine(x) over C <= 256 (modules/norm.py:28-39) */
+int vtk_layernorm_fwd(const void* x, void* out, int M, int C, float eps, void* stream);
+/* dy = dx * gamma; dgamma[D] += colsum(dx * y) */
+int vtk_resid_bwd(const void* dx, const void* y, const void* gamma, void* dy, float* dgamma, int M, int D, void* stream);
+/* out[C] += colsum(in [M,C]) (bias gradients) */
+int vtk_colsum(const void* in, int64_t ld, float* out, int M, int C, void* stream);
+/* d_act [M,Hf] + zraw -> dz[:, qp:] in the packed (value|gate) order */
+int vtk_swiglu_bwd(const void* dact, int64_t ldd, const void* zraw, int64_t ldz, int qp, void* dz, int64_t lddz, int M, int Hf,
+                   void* stream);
+/* in place on dz[:, 0:2D] (dq|dk w.r.t. roped q/k) -> gradient w.r.t. raw q/k; dw [2][d] fp32 += norm_q / norm_k grads */
+int vtk_qk_norm_rope_bwd(void* dz, int64_t lddz, const void* zraw, int64_t ldz, const void* norm_q, const void* norm_k,
+                         const void* rope_table, float* dw, int M, int heads, int d, float eps, void* stream);
+/* dx_out = dx_res + RMSNorm'(x; w)^T dh; dw[D] += colsum(dh * xhat) */
+int vtk_rmsnorm_bwd(const void* x, const void* dh, const void* w, const void* dx_res, void* dx_out, float* dw, int M, int D,
+                    float eps, void* stream);
+int vtk_layernorm_bwd(const void* zlin, const void* dz, void* dx, int M, int C, float eps, void* stream);
+/* out [C,R] = in [R,C]^T */
+int vtk_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, void* stream);
+/* Charbonnier loss (scripts/train_vae.py:314-320): loss_sum[B] fp32 += per-image masked mean (caller zeroes it and takes the
+ * batch mean); dpred (optional) = d(batch-mean loss)/d pred; n_valid[B] int32 = clamp_min(patch_mask.sum(1), 1) */
+int vtk_charbonnier(const void* pred, const void* target, const uint8_t* patch_mask, const int* n_valid, float* loss_sum,
+                    void* dpred, int B, int N, int P, float eps, void* stream);
+/* fused AdamW on bf16 param/grad/exp_avg/exp_avg_sq, fp32 math (torch.optim.AdamW semantics; scripts/train_vae.py:200-208) */
+int vtk_adamw_bf16(void* p, const void* g, void* m, void* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, void* stream);
+/* delta [M, heads] fp32 = rowsum over d of dO * O */
+int vtk_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, int M, int heads, int d, void* stream);
+/* attention backward: dq, dk, dv (row stride ld_d) from q,k,v,dO, lse (from vtk_attention_bf16) and delta */
+int vtk_attention_bwd_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, const void* dout, int64_t ld_do,
+                           const float* lse, const float* delta, void* dq, void* dk, void* dv, int64_t ld_d, const int* kv_len,
+                           int B, int N, int heads, int d, int zero_invalid_rows, int window, void* stream);
 
 /* test-only: D[128,N] fp32 = A[128,K] * op(B) through one tcgen05 tile with explicit descriptor fields */
 int vtk_umma_probe(const void* A, const void* B, float* D, int N, int K, int b_mn_major, uint32_t lbo_bytes,

@@ -224,3 +224,27 @@ def decode(sd: Dict[str, torch.Tensor], enc: Dict[str, torch.Tensor], heads: int
 def psnr(a: torch.Tensor, b: torch.Tensor, data_range: float = 2.0) -> float:
     mse = (a.double() - b.double()).pow(2).mean().item()
     return float("inf") if mse == 0 else 10.0 * math.log10(data_range * data_range / mse)
+
+
+def charbonnier_loss(pred: torch.Tensor, target: torch.Tensor, patch_mask: Optional[torch.Tensor], eps: float = 1e-3) -> torch.Tensor:
+    """scripts/train_vae.py:314-320 verbatim in meaning: per-token mean over the pixel dim of sqrt(diff^2 + eps^2)
+    (diff in fp32), masked, per-image mean over valid tokens (clamp_min 1), batch mean."""
+    diff = (pred - target).float()
+    per_token = (diff.pow(2) + eps ** 2).sqrt().mean(dim=2)
+    if patch_mask is None:
+        return per_token.mean(dim=1).mean()
+    per_token = per_token * patch_mask.float()
+    actual = patch_mask.sum(dim=1).clamp_min(1).float()
+    return (per_token.sum(dim=1) / actual).mean()
+
+
+def train_step_grads(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], enc_heads: int, dec_heads: int,
+                     attn_backend: str = "sdpa", eps: float = 1e-3, sw: Optional[int] = None):
+    """The training step of scripts/train_vae.py:304-320,371 (forward, Charbonnier loss, backward) on the CPU oracle
+    with torch autograd.  Returns (loss, {name: grad})."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    enc = encode(params, batch, enc_heads, attn_backend=attn_backend, sw=sw)
+    dec = decode(params, enc, dec_heads, attn_backend=attn_backend, sw=sw)
+    loss = charbonnier_loss(dec["patches"], batch["patches"], batch.get("patch_mask"), eps)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in params.items()}

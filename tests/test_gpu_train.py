@@ -1,0 +1,286 @@
+"""GPU parity of the training step (BASELINE config 5 path; scripts/train_vae.py:304-320,371-372): every backward
+kernel against torch autograd of the CPU oracle's restatement of the same op, then the whole step (loss + every
+parameter gradient) against the oracle, then a few optimizer steps."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import bf16_randn, report
+from oracle import ae_oracle, pp_oracle
+from oracle.make_golden import SMALL
+from oracle.weights import make_state_dict, synth_images
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def L():
+    from vitok_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def _rel(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return (torch.linalg.norm(got - ref) / torch.linalg.norm(ref).clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("R,C", [(64, 64), (256, 1024), (1000, 136), (8, 8), (264, 3776)])
+def test_transpose_bit_exact(L, R, C):
+    x = bf16_randn(R, C, seed=50)
+    out = torch.empty(C, R, dtype=BF, device="cuda")
+    L.check(L.load().vtk_transpose_bf16(x.data_ptr(), C, out.data_ptr(), R, R, C, L.stream_ptr()))
+    assert torch.equal(out, x.t().contiguous())
+
+
+def test_colsum_and_resid_bwd(L):
+    M, D = 777, 384
+    dx, y = bf16_randn(M, D, seed=51), bf16_randn(M, D, seed=52)
+    gamma = bf16_randn(D, seed=53, scale=0.5)
+    out = torch.zeros(D, dtype=torch.float32, device="cuda")
+    L.check(L.load().vtk_colsum(dx.data_ptr(), D, out.data_ptr(), M, D, L.stream_ptr()))
+    report("colsum", out, dx.float().sum(0), rel_fro=1e-5)
+    dy = torch.empty_like(dx)
+    dg = torch.zeros(D, dtype=torch.float32, device="cuda")
+    L.check(L.load().vtk_resid_bwd(dx.data_ptr(), y.data_ptr(), gamma.data_ptr(), dy.data_ptr(), dg.data_ptr(), M, D, L.stream_ptr()))
+    report("resid_bwd dgamma", dg, (dx.float() * y.float()).sum(0), rel_fro=1e-5)
+    assert torch.equal(dy, (dx.float() * gamma.float()).to(BF))
+    # forward counterpart: same rounding as the fused GEMM epilogue
+    x = bf16_randn(M, D, seed=54)
+    o = torch.empty_like(x)
+    L.check(L.load().vtk_resid_fwd(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), o.data_ptr(), M, D, L.stream_ptr()))
+    assert torch.equal(o, x + (y * gamma))
+
+
+@pytest.mark.parametrize("M,heads,d", [(200, 2, 64), (96, 3, 128)])
+def test_qk_norm_rope_fwd_bwd(L, M, heads, d):
+    D = heads * d
+    z = bf16_randn(M, 3 * D, seed=55)
+    g = torch.Generator().manual_seed(56)
+    wq = (torch.rand(d, generator=g) + 0.5).to(BF).cuda()
+    wk = (torch.rand(d, generator=g) + 0.5).to(BF).cuda()
+    row, col = (torch.arange(M) // 9).cuda(), (torch.arange(M) % 9).cuda()
+    table = L.rope_table(row, col, ae_oracle.rope_inv_freq(d).cuda(), d)
+    qkv = torch.empty(M, 3 * D, dtype=BF, device="cuda")
+    L.check(L.load().vtk_qk_norm_rope_fwd(z.data_ptr(), 3 * D, wq.data_ptr(), wk.data_ptr(), table.data_ptr(), qkv.data_ptr(), 3 * D,
+                                          M, heads, d, 1e-6, L.stream_ptr()))
+    # oracle in fp32 with autograd
+    zc = z.float().cpu().reshape(1, M, 3, heads, d).requires_grad_(True)
+    wqc, wkc = wq.float().cpu().requires_grad_(True), wk.float().cpu().requires_grad_(True)
+    cos, sin = ae_oracle.rope_cos_sin(row.cpu()[None], col.cpu()[None], d)
+    q = ae_oracle.apply_rope(ae_oracle.rms_norm(zc[:, :, 0], wqc), cos, sin)
+    k = ae_oracle.apply_rope(ae_oracle.rms_norm(zc[:, :, 1], wkc), cos, sin)
+    got = qkv.cpu().reshape(1, M, 3, heads, d)
+    report("qk fwd q", got[:, :, 0], q, max_abs=6e-2, rel_fro=6e-3)
+    report("qk fwd k", got[:, :, 1], k, max_abs=6e-2, rel_fro=6e-3)
+    assert torch.equal(got[:, :, 2], z.cpu().reshape(1, M, 3, heads, d)[:, :, 2])
+    dq, dk = bf16_randn(1, M, heads, d, seed=57).cpu().float(), bf16_randn(1, M, heads, d, seed=58).cpu().float()
+    (q * dq).sum().backward(retain_graph=True)
+    (k * dk).sum().backward()
+    dz = torch.zeros(M, 3 * D, dtype=BF, device="cuda")
+    dz.view(M, 3, heads, d)[:, 0] = dq[0].to(BF).cuda()
+    dz.view(M, 3, heads, d)[:, 1] = dk[0].to(BF).cuda()
+    dw = torch.zeros(2, d, dtype=torch.float32, device="cuda")
+    L.check(L.load().vtk_qk_norm_rope_bwd(dz.data_ptr(), 3 * D, z.data_ptr(), 3 * D, wq.data_ptr(), wk.data_ptr(), table.data_ptr(),
+                                          dw.data_ptr(), M, heads, d, 1e-6, L.stream_ptr()))
+    gz = zc.grad[0]
+    report("qk bwd dq_raw", dz.view(M, 3, heads, d)[:, 0], gz[:, 0], rel_fro=1.5e-2)
+    report("qk bwd dk_raw", dz.view(M, 3, heads, d)[:, 1], gz[:, 1], rel_fro=1.5e-2)
+    report("qk bwd dwq", dw[0], wqc.grad, rel_fro=1.5e-2)
+    report("qk bwd dwk", dw[1], wkc.grad, rel_fro=1.5e-2)
+
+
+def test_swiglu_fwd_bwd(L):
+    from vitok_b200.models.ae import pack_w_in
+    M, Hf, qp = 300, 336, 256
+    u = bf16_randn(M, 2 * Hf, seed=59)                      # reference order [value | gate]
+    # packed order: 16-column groups (value16 | gate16) after qp pad columns
+    zraw = torch.zeros(M, qp + 2 * Hf, dtype=BF, device="cuda")
+    zraw[:, qp:] = u.view(M, 2, Hf // 16, 16).permute(0, 2, 1, 3).reshape(M, 2 * Hf)
+    act = torch.empty(M, Hf, dtype=BF, device="cuda")
+    L.check(L.load().vtk_swiglu_fwd(zraw.data_ptr(), qp + 2 * Hf, qp, act.data_ptr(), Hf, M, Hf, L.stream_ptr()))
+    uc = u.float().cpu().requires_grad_(True)
+    val, gate = uc.chunk(2, dim=-1)
+    ref = F.silu(gate) * val
+    report("swiglu fwd", act, ref, max_abs=6e-2, rel_fro=5e-3)
+    dact = bf16_randn(M, Hf, seed=60)
+    (ref * dact.float().cpu()).sum().backward()
+    dz = torch.zeros_like(zraw)
+    L.check(L.load().vtk_swiglu_bwd(dact.data_ptr(), Hf, zraw.data_ptr(), qp + 2 * Hf, qp, dz.data_ptr(), qp + 2 * Hf, M, Hf, L.stream_ptr()))
+    du = dz[:, qp:].view(M, Hf // 16, 2, 16).permute(0, 2, 1, 3).reshape(M, 2 * Hf)
+    report("swiglu bwd", du, uc.grad, rel_fro=6e-3)
+
+
+@pytest.mark.parametrize("M,D", [(100, 256), (64, 1024), (40, 3072)])
+def test_rmsnorm_bwd(L, M, D):
+    x, dh, dres = bf16_randn(M, D, seed=61, scale=2.0), bf16_randn(M, D, seed=62), bf16_randn(M, D, seed=63)
+    w = (torch.rand(D, generator=torch.Generator().manual_seed(64)) + 0.5).to(BF).cuda()
+    xc, wc = x.float().cpu().requires_grad_(True), w.float().cpu().requires_grad_(True)
+    (ae_oracle.rms_norm(xc, wc) * dh.float().cpu()).sum().backward()
+    dx = torch.empty_like(x)
+    dw = torch.zeros(D, dtype=torch.float32, device="cuda")
+    L.check(L.load().vtk_rmsnorm_bwd(x.data_ptr(), dh.data_ptr(), w.data_ptr(), dres.data_ptr(), dx.data_ptr(), dw.data_ptr(), M, D, 1e-6,
+                                     L.stream_ptr()))
+    report(f"rmsnorm bwd dx D={D}", dx, xc.grad + dres.float().cpu(), rel_fro=5e-3)
+    report(f"rmsnorm bwd dw D={D}", dw, wc.grad, rel_fro=1e-4)
+
+
+@pytest.mark.parametrize("C", [16, 64, 256])
+def test_layernorm_fwd_bwd(L, C):
+    M = 130
+    zl, dz = bf16_randn(M, C, seed=65, scale=2.0), bf16_randn(M, C, seed=66)
+    out = torch.empty_like(zl)
+    L.check(L.load().vtk_layernorm_fwd(zl.data_ptr(), out.data_ptr(), M, C, 1e-6, L.stream_ptr()))
+    zc = zl.float().cpu().requires_grad_(True)
+    ref = ae_oracle.layer_norm_noaffine(zc)
+    report(f"ln fwd C={C}", out, ref, max_abs=3e-2, rel_fro=4e-3)
+    (ref * dz.float().cpu()).sum().backward()
+    dx = torch.empty_like(zl)
+    L.check(L.load().vtk_layernorm_bwd(zl.data_ptr(), dz.data_ptr(), dx.data_ptr(), M, C, 1e-6, L.stream_ptr()))
+    report(f"ln bwd C={C}", dx, zc.grad, rel_fro=6e-3)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_charbonnier(L, masked):
+    import vitok_b200 as vb
+    B, N, P = 3, 64, 768
+    pred = bf16_randn(B, N, P, seed=67).requires_grad_(True)
+    target = bf16_randn(B, N, P, seed=68)
+    mask = None
+    if masked:
+        mask = torch.zeros(B, N, dtype=torch.bool)
+        mask[0, :64], mask[1, :10] = True, True            # image 2 has no valid token (clamp_min(1) path)
+    loss = vb.charbonnier_loss(pred, target, mask.cuda() if masked else None, eps=1e-3)
+    loss.backward()
+    pc = pred.detach().cpu().float().requires_grad_(True)
+    ref = ae_oracle.charbonnier_loss(pc, target.cpu().float(), mask, 1e-3)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
+    report(f"charbonnier dpred masked={masked}", pred.grad, pc.grad, rel_fro=4e-3)
+
+
+def test_adamw_matches_torch(L):
+    import vitok_b200 as vb
+    torch.manual_seed(0)
+    p0 = torch.randn(5000)
+    ours = torch.nn.Parameter(p0.to(BF).cuda())
+    ref = torch.nn.Parameter(p0.to(BF).float())             # torch AdamW on fp32 copies of the same bf16 values
+    o1 = vb.FusedAdamW([ours], lr=1e-2, betas=(0.9, 0.99), weight_decay=0.05)
+    o2 = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.99), weight_decay=0.05)
+    for s in range(5):
+        g = torch.randn(5000, generator=torch.Generator().manual_seed(s)).to(BF)
+        ours.grad, ref.grad = g.cuda(), g.float()
+        o1.step(); o2.step()
+    report("adamw 5 steps", ours.data, ref.data, rel_fro=6e-3)   # bf16 storage of p / m / v between steps
+
+
+def _attn_inputs(B, N, heads, d, seed):
+    qkv = bf16_randn(B * N, 3 * heads * d, seed=seed)
+    do = bf16_randn(B * N, heads * d, seed=seed + 1)
+    return qkv, do
+
+
+@pytest.mark.parametrize("B,N,heads,d,lens,w", [
+    (2, 256, 2, 64, None, -1), (1, 512, 2, 128, None, -1), (2, 384, 2, 64, [384, 130], -1), (1, 200, 1, 64, None, -1),
+    (1, 512, 2, 64, None, 70), (2, 256, 1, 128, [100, 256], -1), (1, 1024, 1, 128, None, 200)])
+def test_attention_backward(L, B, N, heads, d, lens, w):
+    qkv, do = _attn_inputs(B, N, heads, d, 70)
+    D = heads * d
+    mask = None
+    if lens is not None:
+        mask = torch.zeros(B, N, dtype=torch.bool)
+        for b, n in enumerate(lens):
+            mask[b, :n] = True
+    lse = torch.empty(B * N, heads, dtype=torch.float32, device="cuda")
+    out = L.attention(qkv, B, N, heads, d, mask.cuda() if mask is not None else None, window=w, lse=lse)
+    # oracle autograd (fp32 on the bf16 values)
+    t = qkv.float().cpu().reshape(B, N, 3, heads, d).requires_grad_(True)
+    ref = ae_oracle.attention_core(t[:, :, 0], t[:, :, 1], t[:, :, 2], mask, w if w >= 0 else None)
+    report("attn fwd (train)", out, ref.reshape(B * N, D), max_abs=3e-2, rel_fro=1e-2)
+    dof = do.float().cpu().reshape(B, N, D)
+    if mask is not None:
+        dof = dof * mask[:, :, None]                        # the loss never feeds gradient into padded rows
+    (ref * dof).sum().backward()
+    delta = torch.empty(B * N, heads, dtype=torch.float32, device="cuda")
+    dod = dof.reshape(B * N, D).to(BF).cuda()
+    L.check(L.load().vtk_attn_delta(out.data_ptr(), D, dod.data_ptr(), D, delta.data_ptr(), B * N, heads, d, L.stream_ptr()))
+    dqkv = torch.full((B * N, 3 * D), float("nan"), dtype=BF, device="cuda")
+    kl = L.kv_len(mask.cuda())[0] if mask is not None else None
+    b0, g0 = qkv.data_ptr(), dqkv.data_ptr()
+    L.check(L.load().vtk_attention_bwd_bf16(b0, b0 + 2 * D, b0 + 4 * D, 3 * D, dod.data_ptr(), D, lse.data_ptr(), delta.data_ptr(),
+                                            g0, g0 + 2 * D, g0 + 4 * D, 3 * D, L.ptr(kl), B, N, heads, d, 1 if mask is not None else 0,
+                                            w, L.stream_ptr()))
+    got = dqkv.cpu().float().reshape(B, N, 3, heads, d)
+    assert torch.isfinite(got).all()
+    for i, nm in enumerate("qkv"):
+        report(f"attn bwd d{nm} N={N} d={d} w={w}", got[:, :, i], t.grad[:, :, i], rel_fro=2e-2)
+
+
+def _batch(sizes, patch, T, seed):
+    b = pp_oracle.collate([pp_oracle.patchify(i, patch, T) for i in synth_images(sizes, seed=seed)])
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in b.items()}
+
+
+@pytest.mark.parametrize("backend", ["sdpa", "flash"])
+def test_training_step_gradients_vs_oracle(backend):
+    """Loss and every parameter gradient of one training step vs the CPU oracle's autograd (fp32)."""
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(SMALL)
+    sd = make_state_dict(cfg, seed=1, stress=True)           # gamma ~ U(0.5, 1.5): the blocks matter
+    sizes = [(128, 128), (96, 64), (128, 112), (64, 128)] if backend == "sdpa" else [(128, 128)] * 4
+    batch = _batch(sizes, 16, 64, seed=11)
+    model = vb.AE(**cfg, attn_backend=backend).train()
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda", BF)
+    cb = {k: (v.cuda().to(BF) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+    out = model(cb)
+    loss = vb.charbonnier_loss(out["patches"], cb["patches"], cb["patch_mask"], eps=1e-3)
+    loss.backward()
+    sd_b = {k: v.to(BF).float() for k, v in sd.items()}      # the oracle sees the same bf16-rounded weights and inputs
+    bb = dict(batch)
+    bb["patches"] = batch["patches"].to(BF).float()
+    ref_loss, ref_g = ae_oracle.train_step_grads(sd_b, bb, cfg["encoder_heads"], cfg["decoder_heads"], attn_backend=backend)
+    print(f"[parity] train step {backend}: loss ours {loss.item():.6f} oracle {ref_loss.item():.6f}")
+    assert abs(loss.item() - ref_loss.item()) <= 5e-3 * abs(ref_loss.item())
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape and torch.isfinite(p.grad).all(), name
+        r = _rel(p.grad, ref_g[name])
+        if r > worst[1]:
+            worst = (name, r)
+        cos = F.cosine_similarity(p.grad.float().cpu().flatten(), ref_g[name].flatten(), dim=0).item()
+        assert cos >= 0.995, (name, cos, r)
+    print(f"[parity] train step {backend}: worst rel-Frobenius gradient error {worst[1]:.3e} at {worst[0]}")
+    assert worst[1] <= 8e-2
+
+
+def test_training_loop_reduces_loss():
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(SMALL)
+    torch.manual_seed(0)
+    model = vb.AE(**cfg, attn_backend="flash").train().to("cuda", BF)
+    decay = [p for n, p in model.named_parameters() if p.ndim > 1 and "norm" not in n and "bias" not in n]
+    no_decay = [p for n, p in model.named_parameters() if not (p.ndim > 1 and "norm" not in n and "bias" not in n)]
+    opt = vb.FusedAdamW([{"params": decay, "weight_decay": 0.01}, {"params": no_decay, "weight_decay": 0.0}], lr=3e-3, betas=(0.9, 0.99))
+    batch = _batch([(128, 128)] * 4, 16, 64, seed=3)
+    cb = {k: (v.cuda().to(BF) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+    losses = []
+    for _ in range(12):
+        opt.zero_grad(set_to_none=True)
+        out = model(cb)
+        loss = vb.charbonnier_loss(out["patches"], cb["patches"], cb["patch_mask"])
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print("[parity] losses", [round(x, 4) for x in losses])
+    assert losses[-1] < 0.9 * losses[0] and all(math.isfinite(x) for x in losses)
+    # inference path sees the updated weights (packed copies were invalidated by the optimizer)
+    model.eval()
+    with torch.no_grad():
+        o = model(cb)["patches"]
+    l2 = vb.charbonnier_loss(o, cb["patches"], cb["patch_mask"]).item()
+    assert l2 < losses[0]

@@ -283,13 +283,14 @@ int vtk_proj_residual_bf16(const void* A, int64_t lda, const void* W, int64_t ld
 
 int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
                        const int* kv_len, const uint8_t* key_mask, const int* is_prefix, int B, int N, int heads, int d,
-                       int zero_invalid_rows, int window, void* stream) {
+                       int zero_invalid_rows, int window, float* lse, void* stream) {
   VTK_REQUIRE(q && k && v && out, "vtk_attention_bf16: null pointer");
   AttnArgs a;
   a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.ld_qkv = ld_qkv; a.out = (bf16*)out; a.ld_out = ld_out;
   a.kv_len = kv_len; a.key_mask = key_mask; a.prefix_flag = is_prefix; a.B = B; a.N = N; a.heads = heads; a.d = d;
   a.zero_invalid_rows = zero_invalid_rows;
   a.window = window;
+  a.lse = lse;
   return launch_attention(a, (cudaStream_t)stream);
 }
 
@@ -298,6 +299,88 @@ int vtk_umma_probe(const void* A, const void* B, float* D, int N, int K, int b_m
   VTK_REQUIRE(A && B && D, "vtk_umma_probe: null pointer");
   return launch_umma_probe((const bf16*)A, (const bf16*)B, D, N, K, b_mn_major, lbo_bytes, sbo_bytes, kstep_bytes,
                            (cudaStream_t)stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// training step (BASELINE config 5): kernel-level entry points driven by vitok_b200/train.py
+// -------------------------------------------------------------------------------------------------
+int vtk_qk_norm_rope_fwd(const void* zraw, int64_t ldz, const void* norm_q, const void* norm_k, const void* rope_table,
+                         void* qkv, int64_t ld_qkv, int M, int heads, int d, float eps, void* stream) {
+  VTK_REQUIRE(zraw && norm_q && norm_k && rope_table && qkv, "vtk_qk_norm_rope_fwd: null pointer");
+  return launch_qk_norm_rope_fwd((const bf16*)zraw, ldz, (const bf16*)norm_q, (const bf16*)norm_k, (const bf16*)rope_table,
+                                 (bf16*)qkv, ld_qkv, M, heads, d, eps, (cudaStream_t)stream);
+}
+int vtk_swiglu_fwd(const void* zraw, int64_t ldz, int qp, void* act, int64_t ld_act, int M, int Hf, void* stream) {
+  VTK_REQUIRE(zraw && act, "vtk_swiglu_fwd: null pointer");
+  return launch_swiglu_fwd((const bf16*)zraw, ldz, qp, (bf16*)act, ld_act, M, Hf, (cudaStream_t)stream);
+}
+int vtk_resid_fwd(const void* x, const void* y, const void* gamma, void* out, int M, int D, void* stream) {
+  VTK_REQUIRE(x && y && gamma && out, "vtk_resid_fwd: null pointer");
+  return launch_resid_fwd((const bf16*)x, (const bf16*)y, (const bf16*)gamma, (bf16*)out, M, D, (cudaStream_t)stream);
+}
+int vtk_layernorm_fwd(const void* x, void* out, int M, int C, float eps, void* stream) {
+  VTK_REQUIRE(x && out, "vtk_layernorm_fwd: null pointer");
+  return launch_ln_fwd((const bf16*)x, (bf16*)out, M, C, eps, (cudaStream_t)stream);
+}
+int vtk_resid_bwd(const void* dx, const void* y, const void* gamma, void* dy, float* dgamma, int M, int D, void* stream) {
+  VTK_REQUIRE(dx && y && gamma && dy && dgamma, "vtk_resid_bwd: null pointer");
+  return launch_resid_bwd((const bf16*)dx, (const bf16*)y, (const bf16*)gamma, (bf16*)dy, dgamma, M, D, (cudaStream_t)stream);
+}
+int vtk_colsum(const void* in, int64_t ld, float* out, int M, int C, void* stream) {
+  VTK_REQUIRE(in && out, "vtk_colsum: null pointer");
+  return launch_colsum((const bf16*)in, ld, out, M, C, (cudaStream_t)stream);
+}
+int vtk_swiglu_bwd(const void* dact, int64_t ldd, const void* zraw, int64_t ldz, int qp, void* dz, int64_t lddz, int M, int Hf,
+                   void* stream) {
+  VTK_REQUIRE(dact && zraw && dz, "vtk_swiglu_bwd: null pointer");
+  return launch_swiglu_bwd((const bf16*)dact, ldd, (const bf16*)zraw, ldz, qp, (bf16*)dz, lddz, M, Hf, (cudaStream_t)stream);
+}
+int vtk_qk_norm_rope_bwd(void* dz, int64_t lddz, const void* zraw, int64_t ldz, const void* norm_q, const void* norm_k,
+                         const void* rope_table, float* dw, int M, int heads, int d, float eps, void* stream) {
+  VTK_REQUIRE(dz && zraw && norm_q && norm_k && rope_table && dw, "vtk_qk_norm_rope_bwd: null pointer");
+  return launch_qk_norm_rope_bwd((bf16*)dz, lddz, (const bf16*)zraw, ldz, (const bf16*)norm_q, (const bf16*)norm_k,
+                                 (const bf16*)rope_table, dw, M, heads, d, eps, (cudaStream_t)stream);
+}
+int vtk_rmsnorm_bwd(const void* x, const void* dh, const void* w, const void* dx_res, void* dx_out, float* dw, int M, int D,
+                    float eps, void* stream) {
+  VTK_REQUIRE(x && dh && w && dx_res && dx_out && dw, "vtk_rmsnorm_bwd: null pointer");
+  return launch_rmsnorm_bwd((const bf16*)x, (const bf16*)dh, (const bf16*)w, (const bf16*)dx_res, (bf16*)dx_out, dw, M, D, eps,
+                            (cudaStream_t)stream);
+}
+int vtk_layernorm_bwd(const void* zlin, const void* dz, void* dx, int M, int C, float eps, void* stream) {
+  VTK_REQUIRE(zlin && dz && dx, "vtk_layernorm_bwd: null pointer");
+  return launch_ln_bwd((const bf16*)zlin, (const bf16*)dz, (bf16*)dx, M, C, eps, (cudaStream_t)stream);
+}
+int vtk_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, void* stream) {
+  VTK_REQUIRE(in && out, "vtk_transpose_bf16: null pointer");
+  return launch_transpose((const bf16*)in, ldi, (bf16*)out, ldo, R, C, (cudaStream_t)stream);
+}
+int vtk_charbonnier(const void* pred, const void* target, const uint8_t* patch_mask, const int* n_valid, float* loss_sum,
+                    void* dpred, int B, int N, int P, float eps, void* stream) {
+  VTK_REQUIRE(pred && target && loss_sum, "vtk_charbonnier: null pointer");
+  VTK_REQUIRE(!patch_mask || n_valid, "vtk_charbonnier: n_valid is required with a patch_mask");
+  return launch_charbonnier((const bf16*)pred, (const bf16*)target, patch_mask, n_valid, loss_sum, (bf16*)dpred, B, N, P, eps,
+                            (cudaStream_t)stream);
+}
+int vtk_adamw_bf16(void* p, const void* g, void* m, void* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, void* stream) {
+  VTK_REQUIRE(p && g && m && v, "vtk_adamw_bf16: null pointer");
+  return launch_adamw((bf16*)p, (const bf16*)g, (bf16*)m, (bf16*)v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                      (cudaStream_t)stream);
+}
+int vtk_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, int M, int heads, int d, void* stream) {
+  VTK_REQUIRE(o && dout && delta, "vtk_attn_delta: null pointer");
+  return launch_attn_delta((const bf16*)o, ldo, (const bf16*)dout, lddo, delta, M, heads, d, (cudaStream_t)stream);
+}
+int vtk_attention_bwd_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, const void* dout, int64_t ld_do,
+                           const float* lse, const float* delta, void* dq, void* dk, void* dv, int64_t ld_d, const int* kv_len,
+                           int B, int N, int heads, int d, int zero_invalid_rows, int window, void* stream) {
+  VTK_REQUIRE(q && k && v && dout && lse && delta && dq && dk && dv, "vtk_attention_bwd_bf16: null pointer");
+  AttnBwdArgs a;
+  a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.ld_qkv = ld_qkv; a.dout = (const bf16*)dout; a.ld_do = ld_do;
+  a.lse = lse; a.delta = delta; a.dq = (bf16*)dq; a.dk = (bf16*)dk; a.dv = (bf16*)dv; a.ld_d = ld_d; a.kv_len = kv_len;
+  a.B = B; a.N = N; a.heads = heads; a.d = d; a.zero_invalid_rows = zero_invalid_rows; a.window = window;
+  return launch_attention_bwd(a, (cudaStream_t)stream);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -404,6 +487,7 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
     a.B = B; a.N = N; a.heads = s.heads; a.d = d; a.zero_invalid_rows = patch_mask ? 1 : 0;
     // sliding window: flash backend only (attention.py:113-116); the sdpa backend (patch_mask given) ignores it
     a.window = (!patch_mask && h->cfg.sliding_window > 0) ? h->cfg.sliding_window : -1;
+    a.lse = nullptr;
     { LaunchTimer t(h, st, CLS_ATTENTION); r = launch_attention(a, st); }
     if (r) return r;
     GemmArgs g2 = base_args(w.a2, kp, b.w_out, kp, D, M, D, D + Hf);

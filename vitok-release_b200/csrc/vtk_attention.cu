@@ -61,6 +61,7 @@ struct AttnParams {
   int window;         // sliding window |i - j| <= window on the token index (flash backend, attention.py:113-116); < 0 = none
   float scale_log2;   // (1/sqrt(d)) * log2(e)
   unsigned long long* prof;   // perf experiments (env VTK_ATTN_PROF): clock64 accumulators, or null
+  float* lse;                 // [B*N, heads] log2-domain logsumexp of the scaled scores (training), or null; +inf for zero rows
 };
 
 __device__ __forceinline__ float max3f(float a, float b, float c) {
@@ -101,6 +102,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       if (qi < N) {
         bf16* op = p.out + (row0 + qi) * p.ld_out + head * DH;
         for (int c = 0; c < DH; c += 8) st_global_v4(op + c, 0u, 0u, 0u, 0u);
+        if (p.lse) p.lse[(row0 + qi) * p.heads + head] = INFINITY;
       }
     }
   }
@@ -372,6 +374,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     bool zero_row = false;
     if (p.zero_invalid) zero_row = (qi >= kvlen) || (kmask != nullptr && qi < N && kmask[qi] == 0);
     const float osc = zero_row ? 0.f : inv;
+    if (p.lse && qi < N) p.lse[(row0 + qi) * p.heads + head] = (zero_row || !(l_run > 0.f)) ? INFINITY : m_run + log2f(l_run);
     bf16* op = p.out + (row0 + qi) * p.ld_out + head * DH;
     uint32_t o[DH / 32][32];
 #pragma unroll
@@ -454,6 +457,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   p.N = a.N; p.heads = a.heads; p.zero_invalid = a.zero_invalid_rows;
   p.tma_out = (a.N % ATT_BQ == 0) ? 1 : 0;
   p.window = a.window;
+  p.lse = a.lse;
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
   static const int prof_mode = getenv("VTK_ATTN_PROF") ? atoi(getenv("VTK_ATTN_PROF")) : 0;
   static unsigned long long* d_prof = nullptr;

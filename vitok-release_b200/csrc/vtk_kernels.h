@@ -81,8 +81,21 @@ struct AttnArgs {
   int B, N, heads, d;
   int zero_invalid_rows;        // 1: rows >= kv_len[b] (or with key_mask 0) are written as 0
   int window;                   // sliding window: keys j with |i - j| <= window (flash_attn window_size=(w,w)); < 0 = none
+  float* lse;                   // optional [B*N, heads] fp32: log2-domain logsumexp of the scaled scores (for the backward pass)
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+// attention backward (vtk_attention_bwd.cu): dq, dk, dv [B*N, ld_d] from q, k, v, dO, lse (log2 domain) and
+// delta = rowsum(dO * O).  Same masking arguments as the forward.
+struct AttnBwdArgs {
+  const bf16* q; const bf16* k; const bf16* v; long long ld_qkv;
+  const bf16* dout; long long ld_do;
+  const float* lse; const float* delta;   // [B*N, heads]
+  bf16* dq; bf16* dk; bf16* dv; long long ld_d;
+  const int* kv_len;
+  int B, N, heads, d, zero_invalid_rows, window;
+};
+int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // elementwise / HBM-bound kernels (vtk_elementwise.cu)
@@ -126,5 +139,30 @@ struct UnpatchifyArgs {
 int launch_unpatchify(const UnpatchifyArgs& a, cudaStream_t stream);
 int launch_grid_extent(const uint8_t* mask, const int64_t* row, const int64_t* col, int B, int N, int* out2,
                        cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// training step (vtk_train.cu, vtk_attention_bwd.cu)
+// ---------------------------------------------------------------------------------------------
+int launch_qk_norm_rope_fwd(const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk, const bf16* rope, bf16* qkv,
+                            long long ldq, int M, int heads, int d, float eps, cudaStream_t st);
+int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long long lda, int M, int Hf, cudaStream_t st);
+int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st);
+int launch_ln_fwd(const bf16* x, bf16* out, int M, int C, float eps, cudaStream_t st);
+int launch_resid_bwd(const bf16* dx, const bf16* y, const bf16* gamma, bf16* dy, float* dgamma, int M, int D, cudaStream_t st);
+int launch_colsum(const bf16* in, long long ld, float* out, int M, int C, cudaStream_t st);
+int launch_swiglu_bwd(const bf16* dact, long long ldd, const bf16* zraw, long long ldz, int qp, bf16* dz, long long lddz, int M,
+                      int Hf, cudaStream_t st);
+int launch_qk_norm_rope_bwd(bf16* dz, long long lddz, const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk,
+                            const bf16* rope, float* dw, int M, int heads, int d, float eps, cudaStream_t st);
+int launch_rmsnorm_bwd(const bf16* x, const bf16* dh, const bf16* w, const bf16* dx_res, bf16* dx_out, float* dw, int M, int D,
+                       float eps, cudaStream_t st);
+int launch_ln_bwd(const bf16* zlin, const bf16* dz, bf16* dx, int M, int C, float eps, cudaStream_t st);
+int launch_transpose(const bf16* in, long long ldi, bf16* out, long long ldo, int R, int C, cudaStream_t st);
+int launch_charbonnier(const bf16* pred, const bf16* target, const uint8_t* mask, const int* n_valid, float* loss_sum, bf16* dpred,
+                       int B, int N, int P, float eps, cudaStream_t st);
+int launch_adamw(bf16* p, const bf16* g, bf16* m, bf16* v, long long n, float lr, float b1, float b2, float eps, float wd, int step,
+                 float grad_scale, cudaStream_t st);
+int launch_attn_delta(const bf16* o, long long ldo, const bf16* dob, long long lddo, float* delta, int M, int heads, int d,
+                      cudaStream_t st);
 
 }  // namespace vtk

@@ -1,0 +1,683 @@
+// vtk_train.cu -- HBM-bound kernels of the training step (BASELINE config 5): the un-fused forward pieces that
+// keep what the backward pass needs, and the backward of every non-GEMM op of the AE block.
+//
+// Reference being restated (autograd of these eager ops; scripts/train_vae.py:304-320,371-372 drives them):
+//   Block.forward            vitok/models/ae.py:55-65        x + gamma * (attn(h) + mlp(h)), h = RMSNorm(x)
+//   RMSNorm                  modules/norm.py:17-25           fp32 math, eps inside rsqrt
+//   QK-norm + 2D RoPE        modules/attention.py:103-107, modules/rotary_embedding.py:102-129
+//   SwiGLU                   modules/mlp.py:20-23
+//   LayerNorm (no affine)    modules/norm.py:28-39           the latent bottleneck's output_fn
+//   Charbonnier loss         scripts/train_vae.py:314-320    sqrt(diff^2 + eps^2), masked per-image mean
+//   AdamW (fused, bf16)      scripts/train_vae.py:185-208    torch.optim.AdamW semantics, decoupled weight decay
+//
+// GEMMs of the backward pass (dgrad / wgrad) run on the tcgen05 GEMM of vtk_gemm.cu: dgrad against transposed
+// weight copies, wgrad on activations transposed by transpose_kernel below (both operands K-major).
+#include <algorithm>
+
+#include "vtk_common.cuh"
+#include "vtk_kernels.h"
+
+namespace vtk {
+
+static __device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x); f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
+  f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z); f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
+}
+static __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(bf2_cvt(f[0], f[1]), bf2_cvt(f[2], f[3]), bf2_cvt(f[4], f[5]), bf2_cvt(f[6], f[7]));
+}
+static int grid_for(long long work_items, int per_block, int waves = 16) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward pieces (same rounding points and the same packed bf16 arithmetic as the fused GEMM epilogues, so the
+// training forward is bit-identical to the inference forward)
+// ------------------------------------------------------------------------------------------------
+
+// zraw [M, >= 3D] (raw bf16 q | k | v of the QKV GEMM) -> qkv [M, 3D]: per-head RMSNorm(q), RMSNorm(k) over d,
+// 2D RoPE from the pair-expanded chunk-major table, v copied.  One warp per (row, head slot), lane <-> pairs.
+template <int DH>
+__global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(const bf16* __restrict__ zraw, long long ldz,
+                                                               const bf16* __restrict__ wq, const bf16* __restrict__ wk,
+                                                               const bf16* __restrict__ rope, bf16* __restrict__ qkv,
+                                                               long long ldq, int M, int heads, float eps) {
+  constexpr int PPL = DH / 64;   // pairs per lane
+  const int lane = threadIdx.x & 31;
+  const long long slots = (long long)M * 3 * heads;
+  const int D = heads * DH;
+  for (long long s = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); s < slots; s += (long long)gridDim.x * 8) {
+    const int m = (int)(s / (3 * heads));
+    const int hs = (int)(s - (long long)m * 3 * heads);
+    const int seg = hs / heads, head = hs - seg * heads;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(zraw + (long long)m * ldz + seg * D + head * DH);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(qkv + (long long)m * ldq + seg * D + head * DH);
+    uint32_t t[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) t[i] = src[lane + 32 * i];
+    if (seg == 2) {
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) dst[lane + 32 * i] = t[i];
+      continue;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) ss += bf16_lo(t[i]) * bf16_lo(t[i]) + bf16_hi(t[i]) * bf16_hi(t[i]);
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)DH + eps);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(seg == 0 ? wq : wk);
+    // table: row group (m >> 5), chunk c (8 bf16 = 4 words), row-in-group (m & 31)
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(rope) + ((long long)(m >> 5) * (DH >> 2)) * 128 + (m & 31) * 4;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const int pr = lane + 32 * i;   // pair index 0 .. DH/2-1
+      const uint32_t wv = w[pr];
+      const float y0 = bf16_lo(t[i]) * rstd * bf16_lo(wv), y1 = bf16_hi(t[i]) * rstd * bf16_hi(wv);
+      const uint32_t Y = bf2_cvt(y0, y1);
+      const uint32_t c2 = tw[(pr >> 2) * 128 + (pr & 3)];
+      const uint32_t s2 = tw[(((DH >> 1) + pr) >> 2) * 128 + (pr & 3)];
+      dst[pr] = bf2_add(bf2_mul(Y, c2), bf2_mul(bf2_swap(Y), s2));
+    }
+  }
+}
+
+// zraw[:, qp:] = 16-column groups (value16 | gate16) -> act [M, Hf] = bf16(bf16(silu(g)) * v)
+__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ zraw, long long ldz, int qp,
+                                                         bf16* __restrict__ act, long long lda, int M, int Hf) {
+  const int vec_per_row = Hf >> 3;
+  const long long total = (long long)M * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / vec_per_row);
+    const int o = (int)(i - (long long)m * vec_per_row) << 3;   // first of 8 output columns
+    const bf16* zp = zraw + (long long)m * ldz + qp + ((o >> 4) << 5) + (o & 8);
+    float v[8], g[8], r[8];
+    unpack8(ld_global_nc_v4(zp), v);
+    unpack8(ld_global_nc_v4(zp + 16), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float s = bf16r(g[k] * (1.f / (1.f + __expf(-g[k]))));
+      r[k] = s * v[k];
+    }
+    *reinterpret_cast<uint4*>(act + (long long)m * lda + o) = pack8(r);
+  }
+}
+
+// x_out = bf16(x + bf16(y * gamma))   (in place on x allowed)
+__global__ void __launch_bounds__(256) resid_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                        const bf16* __restrict__ gamma, bf16* __restrict__ out, int M, int D) {
+  const int vpr = D >> 3;
+  const long long total = (long long)M * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vpr) << 3;
+    const uint4 xv = ld_global_v4(x + i * 8), yv = ld_global_nc_v4(y + i * 8), gv = ld_global_nc_v4(gamma + c);
+    uint4 o;
+    o.x = bf2_add(xv.x, bf2_mul(yv.x, gv.x)); o.y = bf2_add(xv.y, bf2_mul(yv.y, gv.y));
+    o.z = bf2_add(xv.z, bf2_mul(yv.z, gv.z)); o.w = bf2_add(xv.w, bf2_mul(yv.w, gv.w));
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
+  }
+}
+
+// out = LN_noaffine(x) over C <= 256 columns (biased variance, fp32), one warp per row.  x already holds
+// bf16(linear + bias).
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  for (long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * 8) {
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = c < C ? __bfloat162float(x[m * C + c]) : 0.f;
+      s += v[k];
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) q += (v[k] - mean) * (v[k] - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) out[m * C + c] = __float2bfloat16_rn((v[k] - mean) * rstd);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pieces
+// ------------------------------------------------------------------------------------------------
+
+// dy = bf16(dx * gamma);  dgamma[c] += sum_rows dx * y   (fp32 atomics, one per column and block)
+// block = 32 column groups (8 columns each) x 8 row lanes; grid = (ceil(D/256), row chunks)
+__global__ void __launch_bounds__(256) resid_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ y,
+                                                        const bf16* __restrict__ gamma, bf16* __restrict__ dy,
+                                                        float* __restrict__ dgamma, int M, int D) {
+  __shared__ float red[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cg * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < D) {
+    float g[8];
+    unpack8(ld_global_nc_v4(gamma + c), g);
+    for (long long m = (long long)blockIdx.y * 8 + rl; m < M; m += (long long)gridDim.y * 8) {
+      float a[8], b[8], o[8];
+      unpack8(ld_global_nc_v4(dx + m * D + c), a);
+      unpack8(ld_global_nc_v4(y + m * D + c), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[k] += a[k] * b[k];
+        o[k] = a[k] * g[k];
+      }
+      *reinterpret_cast<uint4*>(dy + m * D + c) = pack8(o);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][cg * 8 + k] = acc[k];
+  __syncthreads();
+  const int col = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s += red[r][col];
+  if (blockIdx.x * 256 + col < D) atomicAdd(&dgamma[blockIdx.x * 256 + col], s);
+}
+
+// plain column sums: out[c] += sum_rows in[r, c]   (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ in, long long ld, float* __restrict__ out, int M, int C) {
+  __shared__ float red[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cg * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < C) {
+    for (long long m = (long long)blockIdx.y * 8 + rl; m < M; m += (long long)gridDim.y * 8) {
+      float a[8];
+      unpack8(ld_global_nc_v4(in + m * ld + c), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += a[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][cg * 8 + k] = acc[k];
+  __syncthreads();
+  const int col = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s += red[r][col];
+  if (blockIdx.x * 256 + col < C) atomicAdd(&out[blockIdx.x * 256 + col], s);
+}
+
+// SwiGLU backward: d_act [M, Hf] (row stride ldd), zraw (value16 | gate16 groups at column qp) ->
+// dz[:, qp:] in the same packed order:  d_val = d_act * silu(g),  d_gate = d_act * val * sig(g) * (1 + g * (1 - sig(g)))
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dact, long long ldd,
+                                                         const bf16* __restrict__ zraw, long long ldz, int qp,
+                                                         bf16* __restrict__ dz, long long lddz, int M, int Hf) {
+  const int vec_per_row = Hf >> 3;
+  const long long total = (long long)M * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / vec_per_row);
+    const int o = (int)(i - (long long)m * vec_per_row) << 3;
+    const long long zoff = qp + ((o >> 4) << 5) + (o & 8);
+    float v[8], g[8], d[8], dv[8], dg[8];
+    unpack8(ld_global_nc_v4(zraw + (long long)m * ldz + zoff), v);
+    unpack8(ld_global_nc_v4(zraw + (long long)m * ldz + zoff + 16), g);
+    unpack8(ld_global_nc_v4(dact + (long long)m * ldd + o), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sg = 1.f / (1.f + __expf(-g[k]));
+      dv[k] = d[k] * (g[k] * sg);
+      dg[k] = d[k] * v[k] * sg * (1.f + g[k] * (1.f - sg));
+    }
+    *reinterpret_cast<uint4*>(dz + (long long)m * lddz + zoff) = pack8(dv);
+    *reinterpret_cast<uint4*>(dz + (long long)m * lddz + zoff + 16) = pack8(dg);
+  }
+}
+
+// QK-norm + RoPE backward, in place on dz[:, 0:2D] (which holds dq | dk w.r.t. the roped, normed q/k):
+//   un-rotate:  g = R^T dq           (pair i: g0 = c*d0 + s*d1, g1 = -s*d0 + c*d1)
+//   RMSNorm:    xh = x * rstd, gw = g * w,  dx = rstd * (gw - xh * mean(gw * xh)),  dw += g * xh
+// One warp per (row, q-or-k head); the lane <-> pair mapping is fixed, so dw accumulates in registers and is
+// reduced once per block (shared memory) and once per grid (fp32 atomics).  dw = [2][DH] (q then k).
+template <int DH>
+__global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(bf16* __restrict__ dz, long long lddz,
+                                                               const bf16* __restrict__ zraw, long long ldz,
+                                                               const bf16* __restrict__ wq, const bf16* __restrict__ wk,
+                                                               const bf16* __restrict__ rope, float* __restrict__ dw,
+                                                               int M, int heads, float eps) {
+  constexpr int PPL = DH / 64;
+  __shared__ float red[8][2][DH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = heads * DH;
+  float acc[2][PPL][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) acc[a][i][0] = acc[a][i][1] = 0.f;
+  const long long slots = (long long)M * 2 * heads;
+  for (long long s = (long long)blockIdx.x * 8 + warp; s < slots; s += (long long)gridDim.x * 8) {
+    const int m = (int)(s / (2 * heads));
+    const int hs = (int)(s - (long long)m * 2 * heads);
+    const int seg = hs / heads, head = hs - seg * heads;
+    const uint32_t* xs = reinterpret_cast<const uint32_t*>(zraw + (long long)m * ldz + seg * D + head * DH);
+    uint32_t* dp = reinterpret_cast<uint32_t*>(dz + (long long)m * lddz + seg * D + head * DH);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(seg == 0 ? wq : wk);
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(rope) + ((long long)(m >> 5) * (DH >> 2)) * 128 + (m & 31) * 4;
+    float x0[PPL], x1[PPL], g0[PPL], g1[PPL];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const int pr = lane + 32 * i;
+      const uint32_t xv = xs[pr], dv = dp[pr];
+      x0[i] = bf16_lo(xv); x1[i] = bf16_hi(xv);
+      ss += x0[i] * x0[i] + x1[i] * x1[i];
+      const uint32_t c2 = tw[(pr >> 2) * 128 + (pr & 3)];
+      const uint32_t s2 = tw[(((DH >> 1) + pr) >> 2) * 128 + (pr & 3)];
+      const float c = bf16_lo(c2), sn = bf16_hi(s2);   // C2 = (c, c), S2 = (-s, +s)
+      const float d0 = bf16_lo(dv), d1 = bf16_hi(dv);
+      g0[i] = c * d0 + sn * d1;
+      g1[i] = -sn * d0 + c * d1;
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)DH + eps);
+    float dot = 0.f;
+    float gw0[PPL], gw1[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const int pr = lane + 32 * i;
+      const uint32_t wv = w[pr];
+      x0[i] *= rstd; x1[i] *= rstd;                       // xh
+      const float isq = seg == 0 ? 1.f : 0.f;             // (no dynamic indexing of the register accumulators)
+      acc[0][i][0] += isq * g0[i] * x0[i];
+      acc[0][i][1] += isq * g1[i] * x1[i];
+      acc[1][i][0] += (1.f - isq) * g0[i] * x0[i];
+      acc[1][i][1] += (1.f - isq) * g1[i] * x1[i];
+      gw0[i] = g0[i] * bf16_lo(wv); gw1[i] = g1[i] * bf16_hi(wv);
+      dot += gw0[i] * x0[i] + gw1[i] * x1[i];
+    }
+    dot = warp_sum(dot) / (float)DH;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i)
+      dp[lane + 32 * i] = bf2_cvt(rstd * (gw0[i] - x0[i] * dot), rstd * (gw1[i] - x1[i] * dot));
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      red[warp][a][2 * (lane + 32 * i)] = acc[a][i][0];
+      red[warp][a][2 * (lane + 32 * i) + 1] = acc[a][i][1];
+    }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * DH; e += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) s += red[wp][e / DH][e % DH];
+    atomicAdd(&dw[e], s);
+  }
+}
+
+// RMSNorm backward (norm1), one warp per row:  xh = x * rstd, gw = dh * w,
+//   dx_out = dx_res + rstd * (gw - xh * mean(gw * xh))   (dx_res = gradient arriving through the residual path)
+//   dw[c] += dh * xh.   Columns are lane-strided in 16-byte vectors, so each thread owns fixed columns.
+template <int NV>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dh,
+                                                          const bf16* __restrict__ w, const bf16* __restrict__ dx_res,
+                                                          bf16* __restrict__ dx_out, float* __restrict__ dw, int M, int D,
+                                                          float eps) {
+  extern __shared__ float red[];   // [8][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 3;
+  float acc[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+  for (long long m = (long long)blockIdx.x * 8 + warp; m < M; m += (long long)gridDim.x * 8) {
+    // three passes over the row (the re-reads hit L1/L2); only the dw accumulators live across rows
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float xv[8];
+        unpack8(ld_global_nc_v4(x + m * D + 8 * v), xv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ss += xv[k] * xv[k];
+      }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float xv[8], d[8], wv[8];
+        unpack8(ld_global_nc_v4(x + m * D + 8 * v), xv);
+        unpack8(ld_global_nc_v4(dh + m * D + 8 * v), d);
+        unpack8(ld_global_nc_v4(w + 8 * v), wv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = xv[k] * rstd;
+          acc[i][k] += d[k] * xh;
+          dot += d[k] * wv[k] * xh;
+        }
+      }
+    }
+    dot = warp_sum(dot) / (float)D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float xv[8], d[8], wv[8], r[8], o[8];
+        unpack8(ld_global_nc_v4(x + m * D + 8 * v), xv);
+        unpack8(ld_global_nc_v4(dh + m * D + 8 * v), d);
+        unpack8(ld_global_nc_v4(w + 8 * v), wv);
+        unpack8(ld_global_v4(dx_res + m * D + 8 * v), r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = r[k] + rstd * (d[k] * wv[k] - xv[k] * rstd * dot);
+        *reinterpret_cast<uint4*>(dx_out + m * D + 8 * v) = pack8(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[warp * D + 8 * v + k] = acc[i][k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) s += red[wp * D + c];
+    atomicAdd(&dw[c], s);
+  }
+}
+
+// LayerNorm (no affine) backward over C <= 256 columns, one warp per row.  zlin = bf16(linear + bias) is the
+// saved input: dx = rstd * (dz - mean(dz) - zh * mean(dz * zh)),  zh = (zlin - mean) * rstd
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ zlin, const bf16* __restrict__ dz,
+                                                     bf16* __restrict__ dx, int M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  for (long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * 8) {
+    float v[8], g[8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = c < C ? __bfloat162float(zlin[m * C + c]) : 0.f;
+      g[k] = c < C ? __bfloat162float(dz[m * C + c]) : 0.f;
+      s += v[k];
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) q += (v[k] - mean) * (v[k] - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float sg = 0.f, sgz = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = c < C ? (v[k] - mean) * rstd : 0.f;
+      sg += g[k];
+      sgz += g[k] * v[k];
+    }
+    sg = warp_sum(sg) / (float)C;
+    sgz = warp_sum(sgz) / (float)C;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) dx[m * C + c] = __float2bfloat16_rn(rstd * (g[k] - sg - v[k] * sgz));
+    }
+  }
+}
+
+// out [C, R] = in [R, C]^T  (bf16; R, C multiples of 8; row strides in elements).  64 x 64 tiles through
+// shared memory, 16-byte global accesses on both sides.
+__global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__ in, long long ldi, bf16* __restrict__ out,
+                                                        long long ldo, int R, int C) {
+  __shared__ uint16_t tile[64][64 + 2];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int t = threadIdx.x;
+  // load: 64 rows x 8 vectors of 8 columns; thread -> (row = t / 8 + 32 * pass, vec = t % 8)
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int r = (t >> 3) + 32 * pass, v = t & 7;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (r0 + r < R && c0 + 8 * v < C) q = ld_global_nc_v4(in + (long long)(r0 + r) * ldi + c0 + 8 * v);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      tile[r][8 * v + 2 * k] = (uint16_t)(u[k] & 0xFFFFu);
+      tile[r][8 * v + 2 * k + 1] = (uint16_t)(u[k] >> 16);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c = (t >> 3) + 32 * pass, v = t & 7;   // output row = input column c, output columns 8v..8v+7 = input rows
+    if (c0 + c < C && r0 + 8 * v < R) {
+      uint32_t u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        u[k] = (uint32_t)tile[8 * v + 2 * k][c] | ((uint32_t)tile[8 * v + 2 * k + 1][c] << 16);
+      *reinterpret_cast<uint4*>(out + (long long)(c0 + c) * ldo + r0 + 8 * v) = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+  }
+}
+
+// Charbonnier loss (scripts/train_vae.py:314-320): per token mean over P of sqrt(diff^2 + eps^2) with
+// diff = float(pred) - float(target); per image mean over its valid tokens; batch mean.
+//   loss_sum[b] += per-token means of image b (fp32 atomics);  n_valid[b] is computed by the caller
+//   dpred = diff / sqrt(diff^2 + eps^2) / (P * n_valid[b] * B) on valid tokens, 0 elsewhere.
+// One warp per token.
+__global__ void __launch_bounds__(256) charbonnier_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ target,
+                                                          const uint8_t* __restrict__ mask, const int* __restrict__ n_valid,
+                                                          float* __restrict__ loss_sum, bf16* __restrict__ dpred, int B, int N,
+                                                          int P, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = P >> 3;
+  const long long tokens = (long long)B * N;
+  for (long long tk = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tk < tokens; tk += (long long)gridDim.x * 8) {
+    const int b = (int)(tk / N);
+    const bool valid = mask == nullptr || mask[tk] != 0;
+    const int nv = mask == nullptr ? N : n_valid[b];
+    const float gscale = valid && nv > 0 ? 1.f / ((float)P * (float)nv * (float)B) : 0.f;
+    float s = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      float a[8], t[8], g[8];
+      unpack8(ld_global_nc_v4(pred + tk * P + 8 * v), a);
+      unpack8(ld_global_nc_v4(target + tk * P + 8 * v), t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = a[k] - t[k];
+        const float r = sqrtf(d * d + eps * eps);
+        s += r;
+        g[k] = d / r * gscale;
+      }
+      if (dpred) *reinterpret_cast<uint4*>(dpred + tk * P + 8 * v) = pack8(g);
+    }
+    s = warp_sum(s);
+    if (lane == 0 && valid && nv > 0) atomicAdd(&loss_sum[b], s / (float)P / (float)nv);
+  }
+}
+
+// fused AdamW on bf16 params / grads / moments with fp32 math (torch.optim.AdamW(fused=True) semantics):
+//   p *= 1 - lr * wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __restrict__ m,
+                                                    bf16* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                    float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pf = __bfloat162float(p[i]);
+    const float gf = __bfloat162float(g[i]) * grad_scale;
+    float mf = __bfloat162float(m[i]), vf = __bfloat162float(v[i]);
+    pf *= 1.f - lr * wd;
+    mf = b1 * mf + (1.f - b1) * gf;
+    vf = b2 * vf + (1.f - b2) * gf * gf;
+    const float denom = sqrtf(vf) / bc2_sqrt + eps;
+    pf -= (lr / bc1) * (mf / denom);
+    p[i] = __float2bfloat16_rn(pf);
+    m[i] = __float2bfloat16_rn(mf);
+    v[i] = __float2bfloat16_rn(vf);
+  }
+}
+
+// per attention row and head: delta = sum_d dO * O   (the softmax-backward row term), fp32 [M, heads]
+template <int DH>
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ dob,
+                                                         long long lddo, float* __restrict__ delta, int M, int heads) {
+  constexpr int PPL = DH / 64;
+  const int lane = threadIdx.x & 31;
+  const long long slots = (long long)M * heads;
+  for (long long s = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); s < slots; s += (long long)gridDim.x * 8) {
+    const long long m = s / heads;
+    const int head = (int)(s - m * heads);
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(o + m * ldo + head * DH);
+    const uint32_t* b = reinterpret_cast<const uint32_t*>(dob + m * lddo + head * DH);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const uint32_t x = a[lane + 32 * i], y = b[lane + 32 * i];
+      acc += bf16_lo(x) * bf16_lo(y) + bf16_hi(x) * bf16_hi(y);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) delta[s] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+#define VTK_TRAIN_CHECK(cond, ...) \
+  do {                             \
+    if (!(cond)) {                 \
+      set_error(__VA_ARGS__);      \
+      return -2;                   \
+    }                              \
+  } while (0)
+
+int launch_qk_norm_rope_fwd(const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk, const bf16* rope, bf16* qkv,
+                            long long ldq, int M, int heads, int d, float eps, cudaStream_t st) {
+  VTK_TRAIN_CHECK(d == 64 || d == 128, "qk_norm_rope: head_dim %d unsupported (64 or 128)", d);
+  if (M <= 0) return 0;
+  const int grid = grid_for((long long)M * 3 * heads, 8);
+  if (d == 64) qk_norm_rope_fwd_kernel<64><<<grid, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
+  else qk_norm_rope_fwd_kernel<128><<<grid, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
+  return check_cuda(cudaGetLastError(), "qk_norm_rope_fwd launch");
+}
+int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long long lda, int M, int Hf, cudaStream_t st) {
+  VTK_TRAIN_CHECK(Hf % 16 == 0 && lda % 8 == 0 && ldz % 8 == 0, "swiglu: Hf %% 16 and strides %% 8 required");
+  if (M <= 0) return 0;
+  swiglu_fwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(zraw, ldz, qp, act, lda, M, Hf);
+  return check_cuda(cudaGetLastError(), "swiglu_fwd launch");
+}
+int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st) {
+  VTK_TRAIN_CHECK(D % 8 == 0, "resid: D %% 8 required");
+  if (M <= 0) return 0;
+  resid_fwd_kernel<<<grid_for((long long)M * (D / 8), 256), 256, 0, st>>>(x, y, gamma, out, M, D);
+  return check_cuda(cudaGetLastError(), "resid_fwd launch");
+}
+int launch_ln_fwd(const bf16* x, bf16* out, int M, int C, float eps, cudaStream_t st) {
+  VTK_TRAIN_CHECK(C <= 256, "layernorm: C <= 256 required (C=%d)", C);
+  if (M <= 0) return 0;
+  ln_fwd_kernel<<<grid_for(M, 8), 256, 0, st>>>(x, out, M, C, eps);
+  return check_cuda(cudaGetLastError(), "ln_fwd launch");
+}
+int launch_resid_bwd(const bf16* dx, const bf16* y, const bf16* gamma, bf16* dy, float* dgamma, int M, int D, cudaStream_t st) {
+  VTK_TRAIN_CHECK(D % 8 == 0, "resid_bwd: D %% 8 required");
+  if (M <= 0) return 0;
+  dim3 grid((D + 255) / 256, (unsigned)std::min<long long>(((long long)M + 7) / 8, 4LL * num_sms()));
+  resid_bwd_kernel<<<grid, 256, 0, st>>>(dx, y, gamma, dy, dgamma, M, D);
+  return check_cuda(cudaGetLastError(), "resid_bwd launch");
+}
+int launch_colsum(const bf16* in, long long ld, float* out, int M, int C, cudaStream_t st) {
+  VTK_TRAIN_CHECK(C % 8 == 0 && ld % 8 == 0, "colsum: C, ld %% 8 required");
+  if (M <= 0) return 0;
+  dim3 grid((C + 255) / 256, (unsigned)std::min<long long>(((long long)M + 7) / 8, 4LL * num_sms()));
+  colsum_kernel<<<grid, 256, 0, st>>>(in, ld, out, M, C);
+  return check_cuda(cudaGetLastError(), "colsum launch");
+}
+int launch_swiglu_bwd(const bf16* dact, long long ldd, const bf16* zraw, long long ldz, int qp, bf16* dz, long long lddz, int M,
+                      int Hf, cudaStream_t st) {
+  VTK_TRAIN_CHECK(Hf % 16 == 0 && ldd % 8 == 0 && ldz % 8 == 0 && lddz % 8 == 0, "swiglu_bwd: Hf %% 16 and strides %% 8 required");
+  if (M <= 0) return 0;
+  swiglu_bwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(dact, ldd, zraw, ldz, qp, dz, lddz, M, Hf);
+  return check_cuda(cudaGetLastError(), "swiglu_bwd launch");
+}
+int launch_qk_norm_rope_bwd(bf16* dz, long long lddz, const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk,
+                            const bf16* rope, float* dw, int M, int heads, int d, float eps, cudaStream_t st) {
+  VTK_TRAIN_CHECK(d == 64 || d == 128, "qk_norm_rope_bwd: head_dim %d unsupported (64 or 128)", d);
+  if (M <= 0) return 0;
+  const int grid = grid_for((long long)M * 2 * heads, 8, 8);
+  if (d == 64) qk_norm_rope_bwd_kernel<64><<<grid, 256, 0, st>>>(dz, lddz, zraw, ldz, wq, wk, rope, dw, M, heads, eps);
+  else qk_norm_rope_bwd_kernel<128><<<grid, 256, 0, st>>>(dz, lddz, zraw, ldz, wq, wk, rope, dw, M, heads, eps);
+  return check_cuda(cudaGetLastError(), "qk_norm_rope_bwd launch");
+}
+int launch_rmsnorm_bwd(const bf16* x, const bf16* dh, const bf16* w, const bf16* dx_res, bf16* dx_out, float* dw, int M, int D,
+                       float eps, cudaStream_t st) {
+  VTK_TRAIN_CHECK(D % 8 == 0 && D <= 4096, "rmsnorm_bwd: D %% 8 == 0 and D <= 4096 required (D=%d)", D);
+  if (M <= 0) return 0;
+  const int grid = grid_for(M, 8, 4);
+  const size_t smem = (size_t)8 * D * sizeof(float);
+  auto run = [&](auto kern) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 256, smem, st>>>(x, dh, w, dx_res, dx_out, dw, M, D, eps);
+  };
+  if (D <= 1024) run(rmsnorm_bwd_kernel<4>);
+  else if (D <= 2048) run(rmsnorm_bwd_kernel<8>);
+  else run(rmsnorm_bwd_kernel<16>);
+  return check_cuda(cudaGetLastError(), "rmsnorm_bwd launch");
+}
+int launch_ln_bwd(const bf16* zlin, const bf16* dz, bf16* dx, int M, int C, float eps, cudaStream_t st) {
+  VTK_TRAIN_CHECK(C <= 256, "layernorm_bwd: C <= 256 required (C=%d)", C);
+  if (M <= 0) return 0;
+  ln_bwd_kernel<<<grid_for(M, 8), 256, 0, st>>>(zlin, dz, dx, M, C, eps);
+  return check_cuda(cudaGetLastError(), "ln_bwd launch");
+}
+int launch_transpose(const bf16* in, long long ldi, bf16* out, long long ldo, int R, int C, cudaStream_t st) {
+  VTK_TRAIN_CHECK(R % 8 == 0 && C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0, "transpose: sizes and strides must be multiples of 8");
+  if (R <= 0 || C <= 0) return 0;
+  dim3 grid((C + 63) / 64, (R + 63) / 64);
+  transpose_kernel<<<grid, 256, 0, st>>>(in, ldi, out, ldo, R, C);
+  return check_cuda(cudaGetLastError(), "transpose launch");
+}
+int launch_charbonnier(const bf16* pred, const bf16* target, const uint8_t* mask, const int* n_valid, float* loss_sum, bf16* dpred,
+                       int B, int N, int P, float eps, cudaStream_t st) {
+  VTK_TRAIN_CHECK(P % 8 == 0, "charbonnier: P %% 8 required");
+  if (B <= 0 || N <= 0) return 0;
+  charbonnier_kernel<<<grid_for((long long)B * N, 8), 256, 0, st>>>(pred, target, mask, n_valid, loss_sum, dpred, B, N, P, eps);
+  return check_cuda(cudaGetLastError(), "charbonnier launch");
+}
+int launch_adamw(bf16* p, const bf16* g, bf16* m, bf16* v, long long n, float lr, float b1, float b2, float eps, float wd, int step,
+                 float grad_scale, cudaStream_t st) {
+  if (n <= 0) return 0;
+  VTK_TRAIN_CHECK(step >= 1, "adamw: step must be >= 1");
+  const float bc1 = 1.f - powf(b1, (float)step), bc2s = sqrtf(1.f - powf(b2, (float)step));
+  adamw_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
+  return check_cuda(cudaGetLastError(), "adamw launch");
+}
+int launch_attn_delta(const bf16* o, long long ldo, const bf16* dob, long long lddo, float* delta, int M, int heads, int d,
+                      cudaStream_t st) {
+  VTK_TRAIN_CHECK(d == 64 || d == 128, "attn_delta: head_dim %d unsupported", d);
+  if (M <= 0) return 0;
+  const int grid = grid_for((long long)M * heads, 8);
+  if (d == 64) attn_delta_kernel<64><<<grid, 256, 0, st>>>(o, ldo, dob, lddo, delta, M, heads);
+  else attn_delta_kernel<128><<<grid, 256, 0, st>>>(o, ldo, dob, lddo, delta, M, heads);
+  return check_cuda(cudaGetLastError(), "attn_delta launch");
+}
+
+}  // namespace vtk

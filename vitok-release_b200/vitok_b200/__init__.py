@@ -8,7 +8,8 @@ libvitok_b200.so (hand-written sm_100a kernels); there is no CPU fallback.
 from .models.ae import AE, Model, decode_variant
 from .pp import OPS, build_transform, parse_op, patchify_batch, postprocess, preprocess, unpack, unpatchify
 from .data import patch_collate_fn
+from .train import FusedAdamW, charbonnier_loss
 
 __version__ = "0.1.0"
 __all__ = ["AE", "Model", "decode_variant", "build_transform", "parse_op", "OPS", "patch_collate_fn", "preprocess",
-           "postprocess", "unpatchify", "unpack", "patchify_batch"]
+           "postprocess", "unpatchify", "unpack", "patchify_batch", "charbonnier_loss", "FusedAdamW"]

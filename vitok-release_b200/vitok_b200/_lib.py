@@ -53,7 +53,23 @@ SIGNATURES = {
                                     c_f32, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "vtk_proj_residual_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_attention_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
-                                   c_int, c_int, c_vp]),
+                                   c_int, c_int, c_vp, c_vp]),
+    "vtk_qk_norm_rope_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
+    "vtk_swiglu_fwd": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
+    "vtk_resid_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "vtk_layernorm_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
+    "vtk_resid_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "vtk_colsum": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_vp]),
+    "vtk_swiglu_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
+    "vtk_qk_norm_rope_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp]),
+    "vtk_rmsnorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
+    "vtk_layernorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
+    "vtk_transpose_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp]),
+    "vtk_charbonnier": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp]),
+    "vtk_adamw_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_int, c_f32, c_vp]),
+    "vtk_attn_delta": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp]),
+    "vtk_attention_bwd_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
+                                       c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "vtk_umma_probe": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u32, c_u32, c_u32, c_vp]),
     "vtk_ae_create": (c_int, [ctypes.POINTER(AEConfig), ctypes.POINTER(c_vp)]),
     "vtk_ae_destroy": (c_int, [c_vp]),
@@ -211,7 +227,7 @@ def proj_residual(a, w, gamma, x):
 
 
 def attention(qkv: torch.Tensor, B: int, N: int, heads: int, d: int, mask: Optional[torch.Tensor] = None,
-              window: int = -1) -> torch.Tensor:
+              window: int = -1, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv [B*N, 3*heads*d] (q | k | v).  mask [B,N] bool -> sdpa semantics; None -> flash semantics.
     window >= 0: sliding window |i - j| <= window (flash_attn window_size=(window, window))."""
     D = heads * d
@@ -222,7 +238,7 @@ def attention(qkv: torch.Tensor, B: int, N: int, heads: int, d: int, mask: Optio
         kl, pf = kv_len(mask)
     base = qkv.data_ptr()
     check(load().vtk_attention_bf16(base, base + 2 * D, base + 4 * D, qkv.stride(0), ptr(out), out.stride(0), ptr(kl),
-                                    ptr(m8), ptr(pf), B, N, heads, d, 1 if mask is not None else 0, int(window), stream_ptr()))
+                                    ptr(m8), ptr(pf), B, N, heads, d, 1 if mask is not None else 0, int(window), ptr(lse), stream_ptr()))
     return out
 
 

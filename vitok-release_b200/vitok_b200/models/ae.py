@@ -16,7 +16,8 @@ Semantics kept from the reference (file:line in the reference tree):
   * unknown kwargs ignored (ae.py:92); ``sw <= 0`` -> None (ae.py:99).
 ``sw``: sliding-window attention |i-j| <= sw on the token index with the flash backend (attention.py:113-116);
     ignored by the sdpa backend, as in the reference.
-Not implemented yet (raise): FP8 ``quantize()``, autograd/backward.
+Training: ``model(batch)`` in train mode builds one autograd node (vitok_b200/train.py); encode/decode alone are
+    inference-only.  Not implemented (raises): FP8 ``quantize()``.
 """
 from __future__ import annotations
 
@@ -304,8 +305,9 @@ class AE(nn.Module):
         return ws
 
     def _run(self, side: int, x: torch.Tensor, d: Dict[str, torch.Tensor], out_cols: int) -> torch.Tensor:
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("vitok_b200.AE: backward is not implemented yet; call model.eval() / torch.no_grad()")
+        if self._wants_grad():
+            raise NotImplementedError("vitok_b200.AE: gradients flow through model(batch) (AE.forward) only; call encode/decode "
+                                      "under model.eval() or torch.no_grad()")
         if not x.is_cuda:
             raise RuntimeError("vitok_b200.AE: inputs must be CUDA tensors (there is no CPU path)")
         if x.dim() != 3:
@@ -365,7 +367,15 @@ class AE(nn.Module):
             "orig_width": encode_dict.get("orig_width"), "patches": patches,
         }
 
+    def _wants_grad(self) -> bool:
+        return self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def forward(self, x: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """encode then decode (ae.py:245-251).  In training mode with gradients enabled this is the training step's
+        forward: one autograd node whose backward runs the sm_100a backward kernels (vitok_b200/train.py)."""
+        if self._wants_grad():
+            from ..train import train_forward
+            return train_forward(self, x)
         if self.is_encoder:
             x = self.encode(x)
         if self.is_decoder:
