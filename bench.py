@@ -38,7 +38,11 @@ WORKLOADS = {
     "c2": ("Ld4-Ld24/1x16x64", 64, 256, 256, "flash"),
     "c4": ("Td4-T/1x16x64", 8, 512, 1024, "flash"),
     "350M-512": ("Ld4-Ld24/1x16x64", 16, 512, 1024, "flash"),
+    # training-step configs (BASELINE configs[4]): forward + Charbonnier + backward + AdamW, DDP all-reduce when N > 1
+    "c5": ("Td4-T/1x32x256", 8, 1024, 1024, "flash"),
+    "c5-350M": ("Ld4-Ld24/1x16x64", 16, 256, 256, "flash"),
 }
+TRAIN_WORKLOADS = ("c5", "c5-350M")
 METRIC = "encode+decode images/sec"
 UNIT = "images/s"
 CLS_NAMES = ["linear", "rmsnorm", "qkv_swiglu_gemm", "attention", "proj_residual_gemm", "misc"]
@@ -324,8 +328,13 @@ def run_ours(args, rank, world, local):
         avg_ms = tot[2] / max(cnt[2], 1)
         pk = peaks()
         ach = (fl / n_l) / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-        roof = {"kernel": "gemm_kernel<256,EPI_QKV_SWIGLU,8>", "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+        traffic = None   # dram bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/)
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload, {}).get("qkv_swiglu_gemm_dram_bytes_per_launch")
+        roof = {"kernel": "gemm2_kernel<EPI_QKV_SWIGLU> (cta_group::2, 256x256 pair tile)", "bound": "tensor", "achieved": ach,
+                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": traffic,
+                "peak_source": pk["src"] + " sustained bf16",
                 "avg_launch_ms": avg_ms, "flops_per_launch": fl / n_l}
 
     if rank != 0:
@@ -361,6 +370,75 @@ def run_ours(args, rank, world, local):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, rank, world, local):
+    """Training step (scripts/train_vae.py:304-320,371-372): model(batch) -> Charbonnier -> backward -> AdamW, wrapped in
+    DDP (train_vae.py:172) when world > 1 so the gradient all-reduce runs over NCCL."""
+    import vitok_b200 as vb
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    variant, B, res, T, backend = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    cfg = vb.decode_variant(variant)
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = vb.AE(**cfg, attn_backend=backend)
+    model = model.to(torch.bfloat16).train()
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(model, device_ids=[local], static_graph=True, gradient_as_bucket_view=True)
+    decay = [p for n, p in model.named_parameters() if not (p.ndim <= 1 or "bias" in n or "norm" in n or "embedding" in n)]
+    no_decay = [p for n, p in model.named_parameters() if (p.ndim <= 1 or "bias" in n or "norm" in n or "embedding" in n)]
+    opt = vb.FusedAdamW([{"params": decay, "weight_decay": 0.01}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-4, betas=(0.9, 0.99))
+    g = torch.Generator().manual_seed(1234 + rank)
+    imgs = torch.rand(B, 3, res, res, generator=g) * 2 - 1
+    pd = vb.patchify_batch(imgs.to(dev), cfg["spatial_stride"], T, out_dtype=torch.bfloat16, device=dev)
+    losses = []
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = net(pd)
+        loss = vb.charbonnier_loss(out["patches"], pd["patches"], pd["patch_mask"], eps=1e-3)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 1)):
+        losses.append(float(step()))
+    torch.cuda.synchronize()
+    barrier(world)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0.record()
+    for _ in range(args.steps):
+        last = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    losses.append(float(last))
+    clocks = sampler.stop() if sampler else None
+    ms = max_over_ranks(ev0.elapsed_time(ev1), world, dev)
+    if rank != 0:
+        return
+    N = T
+    gf = 3.0 * flops_per_image(cfg, N) / 1e9
+    value = world * B * args.steps / (ms / 1e3)
+    pk = peaks()
+    line = {
+        "metric": "training step images/sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {variant} training step @{res}px, batch {B}/GPU, Charbonnier + AdamW"
+                               + (", DDP all-reduce over NCCL" if world > 1 else ""),
+                   "variant": variant, "resolution": res, "tokens_per_image": N, "batch_per_gpu": B, "global_batch": B * world,
+                   "attn_backend": backend, "gflop_per_image_fwd_bwd": gf},
+        "model_tflops": value * gf / 1e3 / world, "model_frac_of_peak": value * gf / 1e3 / world / pk["bf16_sustained"],
+        "loss_first_last": [losses[0], losses[-1]], "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,7 +456,10 @@ def main():
         return
     rank, world, local = dist_setup(args.gpus)
     try:
-        run_ours(args, rank, world, local)
+        if args.workload in TRAIN_WORKLOADS:
+            run_train(args, rank, world, local)
+        else:
+            run_ours(args, rank, world, local)
     finally:
         if world > 1:
             import torch.distributed as dist
