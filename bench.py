@@ -8,8 +8,8 @@ Contract (see DESIGN.md "Measurement"):
   * workload at N=1 (default c2) = BASELINE.json configs[1]: 350M-f16x64, bf16, 64 x 256x256 images per GPU
     (weak scaling: every rank owns its own 64-image batch; no data-path collective);
   * `value`   : whole-job images/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks;
-  * `e2e`     : same metric through the public API with HOST (pinned) buffers: H2D of patches + indices and D2H
-                of the reconstructed patches inside the timed region;
+  * `e2e`     : same metric through the public API with HOST (pinned) buffers: uint8 images in (H2D), preprocess,
+                encode, decode, postprocess, uint8 reconstructions out (D2H), all inside the timed region;
   * `roofline`: the dominant kernel (QKV+SwiGLU tcgen05 GEMM): algorithmic FLOPs per launch / its mean launch
                 duration from CUDA events recorded around every launch inside a timed pass;
   * `cpu_baseline` / `--impl reference`: the CPU oracle (oracle/, a restatement of the reference's PyTorch CPU
@@ -240,18 +240,21 @@ def run_ours(args, rank, world, local):
     launches_per_step = n_launch // max(args.steps, 1)
 
     # ---- e2e: host buffers in, host buffers out, through the public API ---------------------------
-    host_in = {k: (v.cpu().pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in pd.items()
-               if k in ("patches", "row_idx", "col_idx", "patch_mask", "orig_height", "orig_width")}
-    host_out = torch.empty(B, N, cfg["pixels_per_token"], dtype=torch.bfloat16).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    d2h = host_out.numel() * host_out.element_size()
+    # The serving loop a user of the reference writes (README.md:62-65): decoded uint8 images on the host ->
+    # preprocess (to_tensor|normalize|patchify) -> encode -> decode -> postprocess (unpatchify, 0_255) -> uint8
+    # images on the host.  Per step: H2D of the uint8 HWC batch, D2H of the uint8 CHW reconstructions.
+    host_u8 = ((imgs.permute(0, 2, 3, 1) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+    host_out = torch.empty(B, 3, res, res, dtype=torch.uint8).pin_memory()
+    h2d = host_u8.numel()
+    d2h = host_out.numel()
+    patch = cfg["spatial_stride"]
 
     # Double-buffered pipeline on three streams (copy-in / compute / copy-out): step i's H2D and step i-1's D2H
     # overlap step i's kernels, the way a serving loop would drive the public API.  Every step still moves its
     # own inputs host->device and its own result device->host inside the timed region.
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     s_main = torch.cuda.current_stream(dev)
-    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in host_in.items()} for _ in range(2)]
+    dev_in = [torch.empty_like(host_u8, device=dev) for _ in range(2)]
     host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
@@ -262,18 +265,19 @@ def run_ours(args, rank, world, local):
     def e2e_step(i):
         b = i & 1
         with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_free[b])                 # compute of step i-2 has consumed this input buffer
-            for k, v in host_in.items():
-                dev_in[b][k].copy_(v, non_blocking=True)
+            s_in.wait_event(ev_free[b])                 # patchify of step i-2 has consumed this input buffer
+            dev_in[b].copy_(host_u8, non_blocking=True)
             ev_in[b].record(s_in)
         s_main.wait_event(ev_in[b])
-        o = step(dev_in[b])
+        d = vb.patchify_batch(dev_in[b], patch, T, out_dtype=torch.bfloat16, device=dev)
         ev_free[b].record(s_main)
+        o = step(d)
+        img = vb.unpatchify(o, patch, max_grid_size=res // patch, output_format="0_255")
         ev_done[b].record(s_main)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done[b])
-            o["patches"].record_stream(s_out)
-            host_outs[b].copy_(o["patches"], non_blocking=True)
+            img.record_stream(s_out)
+            host_outs[b].copy_(img, non_blocking=True)
 
     def e2e_drain():
         s_main.wait_stream(s_out)

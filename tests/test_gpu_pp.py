@@ -71,6 +71,22 @@ def test_uint8_fused_frontend_bit_exact():
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
 
 
+def test_uint8_batched_tensor_frontend_and_u8_roundtrip():
+    """A [B,H,W,3] uint8 batch (host or device) takes the one-copy path; with the fused 0_255 back-end the
+    uint8 -> patches -> uint8 round trip is the identity (io.py:115-119: round(clamp((x+1)/2)*255))."""
+    import vitok_b200 as vb
+    rng = np.random.default_rng(3)
+    u8 = rng.integers(0, 256, size=(5, 96, 128, 3), dtype=np.uint8)
+    want = pp_oracle.collate([pp_oracle.patchify(pp_oracle.normalize_u8(a), 16, 64) for a in u8])
+    for src in (torch.from_numpy(u8), torch.from_numpy(u8).cuda(), torch.from_numpy(u8).pin_memory()):
+        got = vb.patchify_batch(src, 16, 64)
+        for k in want:
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    back = vb.unpatchify(got, 16, max_grid_size=8, output_format="0_255")      # canvas 128 x 128, image in the top-left
+    assert back.dtype == torch.uint8
+    assert np.array_equal(back[:, :, :96, :128].permute(0, 2, 3, 1).cpu().numpy(), u8)
+
+
 def test_full_size_roundtrip_and_bf16():
     """BASELINE config sizes: 64 x 256^2 (c2) and 8 x 512^2 (c4): patchify -> unpatchify is the identity."""
     import vitok_b200 as vb

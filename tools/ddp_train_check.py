@@ -29,16 +29,19 @@ def main():
     cfg = vb.decode_variant(variant)
     torch.manual_seed(0)
     model = vb.AE(**cfg, attn_backend="flash").train().to(dev, torch.bfloat16)
+    # an un-wrapped twin for the hand-made reference: running the bare module's backward while DDP's hooks are
+    # installed would be counted by the static-graph bookkeeping of the first iteration
+    twin = vb.AE(**cfg, attn_backend="flash").train().to(dev, torch.bfloat16)
+    twin.load_state_dict(model.state_dict())
     ddp = DDP(model, device_ids=[local], static_graph=True)
     g = torch.Generator().manual_seed(100 + rank)
     imgs = torch.rand(4, 3, 256, 256, generator=g) * 2 - 1
     pd = vb.patchify_batch(imgs.to(dev), 16, 256, out_dtype=torch.bfloat16, device=dev)
 
     # local gradients without DDP, then their mean over ranks by hand
-    model.zero_grad(set_to_none=True)
-    loss = vb.charbonnier_loss(model(pd)["patches"], pd["patches"], pd["patch_mask"])
+    loss = vb.charbonnier_loss(twin(pd)["patches"], pd["patches"], pd["patch_mask"])
     loss.backward()
-    local_g = {n: p.grad.float().clone() for n, p in model.named_parameters()}
+    local_g = {n: p.grad.float().clone() for n, p in twin.named_parameters()}
     for t in local_g.values():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         t /= world
@@ -63,6 +66,13 @@ def main():
         opt.zero_grad(set_to_none=True)
         loss = vb.charbonnier_loss(ddp(pd)["patches"], pd["patches"], pd["patch_mask"])
         loss.backward()
+        if os.environ.get("DDP_CHECK_DEBUG"):
+            for n, p in list(model.named_parameters())[:3]:
+                for what, t in (("grad", p.grad), ("param", p.detach())):
+                    lst = [torch.zeros_like(t) for _ in range(world)]
+                    dist.all_gather(lst, t.contiguous())
+                    if rank == 0:
+                        print(f"step {len(losses)} {n} {what}: max |r0 - r1| = {(lst[0].float() - lst[1].float()).abs().max().item():.3e}", flush=True)
         opt.step()
         losses.append(float(loss))
     for n, p in model.named_parameters():

@@ -40,6 +40,13 @@ def patchify_batch(images: Union[torch.Tensor, Sequence[torch.Tensor], Sequence[
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("vitok_b200.patchify_batch: device must be a CUDA device (there is no CPU path)")
+    if (isinstance(images, torch.Tensor) and images.dim() == 4 and images.dtype == torch.uint8 and images.shape[-1] == 3
+            and images.is_contiguous() and (images.shape[1] * images.shape[2] * 3) % 4 == 0):
+        # a batched [B,H,W,3] uint8 tensor (decoded images): one H2D copy (if on the host) and one launch, with
+        # to_tensor|normalize(minus_one_to_one) fused into the kernel (ops.py:140-161)
+        B, H, W, _ = images.shape
+        packed = images.to(dev, non_blocking=True).reshape(-1)
+        return _patchify_packed(packed, [i * H * W * 3 for i in range(B)], [(H, W)] * B, 1, patch, max_tokens, out_dtype, dev)
     if isinstance(images, torch.Tensor) and images.dim() == 4:
         imgs: List = list(images.unbind(0)) if not images.is_contiguous() else None
         if imgs is None:
@@ -83,6 +90,9 @@ def patchify_batch(images: Union[torch.Tensor, Sequence[torch.Tensor], Sequence[
     return _patchify_packed(packed, offsets, sizes, 1 if u8 else 0, patch, max_tokens, out_dtype, dev)
 
 
+_TABLE_CACHE: Dict = {}
+
+
 def _patchify_packed(packed, offsets, sizes, in_dtype, patch, max_tokens, out_dtype, dev):
     B = len(sizes)
     for (h, w) in sizes:
@@ -92,7 +102,13 @@ def _patchify_packed(packed, offsets, sizes, in_dtype, patch, max_tokens, out_dt
                                "(use resize_to_token_budget first)")
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("patchify: out_dtype must be float32 or bfloat16")
-    table = torch.tensor([[o, h, w] for o, (h, w) in zip(offsets, sizes)], dtype=torch.int64).to(dev, non_blocking=True)
+    key = (dev, tuple(offsets), tuple(sizes))
+    table = _TABLE_CACHE.get(key)
+    if table is None:       # {offset, H, W} per image; cached so that a steady-state loop issues no pageable H2D copy
+        if len(_TABLE_CACHE) > 64:
+            _TABLE_CACHE.clear()
+        table = torch.tensor([[o, h, w] for o, (h, w) in zip(offsets, sizes)], dtype=torch.int64).to(dev)
+        _TABLE_CACHE[key] = table
     P = 3 * patch * patch
     T = max_tokens
     patches = torch.empty(B, T, P, dtype=out_dtype, device=dev)
