@@ -22,6 +22,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "vtk_common.cuh"
 #include "vtk_kernels.h"
 
@@ -73,6 +75,47 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Exponentiate one 128-key score tile held in registers (v = raw scores), accumulate the row sum and write P as
+// bf16 into the row's 128B-swizzled shared-memory slots.  Software-pipelined by hand: all FFMA2 (scale, subtract
+// max) first, then MUFU.EX2 of pair i+DIST is issued before the FADD2 / F2FP / STS that consume pair i, so a
+// warp never stalls on its own MUFU latency (ptxas otherwise places each consumer right behind its producer and
+// the XU pipe idles ~55 % of the exponentiation phase with only two softmax warps per scheduler).
+__device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[4][32], uint64_t sc2, uint64_t nm2, uint8_t* prow, int r,
+                                                 uint64_t& sum2a, uint64_t& sum2b) {
+#pragma unroll
+  for (int pr = 0; pr < 64; ++pr) {
+    float e0, e1;
+    f2_unpack(f2_fma(f2_pack(__uint_as_float(v[pr >> 4][2 * (pr & 15)]), __uint_as_float(v[pr >> 4][2 * (pr & 15) + 1])), sc2, nm2), e0, e1);
+    v[pr >> 4][2 * (pr & 15)] = __float_as_uint(e0);
+    v[pr >> 4][2 * (pr & 15) + 1] = __float_as_uint(e1);
+  }
+  constexpr int DIST = 3;
+  uint32_t pk[4];
+#pragma unroll
+  for (int pr = 0; pr < 64 + DIST; ++pr) {
+    if (pr < 64) {
+      uint32_t& a = v[pr >> 4][2 * (pr & 15)];
+      uint32_t& b = v[pr >> 4][2 * (pr & 15) + 1];
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a));
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(b));
+    }
+    if (pr >= DIST) {
+      const int q = pr - DIST;
+      const float e0 = __uint_as_float(v[q >> 4][2 * (q & 15)]), e1 = __uint_as_float(v[q >> 4][2 * (q & 15) + 1]);
+      if (q & 1) sum2b = f2_add(sum2b, f2_pack(e0, e1));
+      else sum2a = f2_add(sum2a, f2_pack(e0, e1));
+      pk[q & 3] = bf2_cvt(e0, e1);
+      if ((q & 3) == 3) {
+        const int gg = q >> 2;   // 16-byte chunk index 0..15 along the 128 keys; swizzle-128B: chunk' = chunk ^ (row & 7)
+        const int blk = gg >> 3, ch = (gg & 7) ^ (r & 7);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(prow + blk * BLK + (ch << 4))), "r"(pk[0]), "r"(pk[1]),
+                     "r"(pk[2]), "r"(pk[3])
+                     : "memory");
+      }
+    }
+  }
 }
 
 template <int DH, int NQ>
@@ -325,25 +368,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
       // 128 columns = 2 blocks x 8 chunks of 16 B; swizzle-128B: chunk' = chunk ^ (row & 7); each 16-byte chunk
       // (8 keys) is written as soon as it is exponentiated
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float e0, e1;
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][8 * g + 2 * i]), __uint_as_float(v[c][8 * g + 2 * i + 1])), sc2, nm2), e0, e1);
-            e0 = ex2_approx(e0);
-            e1 = ex2_approx(e1);
-            if (i & 1) sum2b = f2_add(sum2b, f2_pack(e0, e1));
-            else sum2a = f2_add(sum2a, f2_pack(e0, e1));
-            pk[i] = bf2_cvt(e0, e1);
-          }
-          const int gg = c * 4 + g;   // 16-byte chunk index 0..15 along the 128 keys
-          const int blk = gg >> 3, ch = (gg & 7) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + blk * BLK + (ch << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
+      softmax_exp_tile(v, sc2, nm2, prow, r, sum2a, sum2b);
       float sum0, sum1;
       f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
       l_run = l_run * alpha + (sum0 + sum1);
@@ -440,6 +465,411 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant for d = 64 (one 128-query tile per work item, two CTAs resident per SM).
+//
+// The one-shot kernel above pays barrier init + TMEM allocation + the first Q/K load (~3.9 k of ~10.5 k cycles per CTA
+// at N = 256, measured with VTK_ATTN_PROF) for every (image, head, query tile).  Here a CTA walks a strided list of work
+// items and the three roles run ahead of each other ACROSS items: the TMA thread refills the Q buffer as soon as the
+// last S MMA of the current item has been committed and the K/V rings as their slots drain, the MMA thread issues
+// S(next item, tile 0) while the softmax warps are still on the previous item's last tile / epilogue, so in steady
+// state the softmax warps never wait for a load.  O is staged in the (idle) P buffer and leaves through a TMA store
+// whose completion is only awaited right before P is written again.
+// Barrier phases are tracked with running counters (tiles / K loads / V loads / items seen by this CTA).
+// ------------------------------------------------------------------------------------------------
+struct AttnItem {
+  int img, head, q0, kvlen, qlimit, j_lo, Tn;
+  bool active;
+};
+
+__device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int w, int qtiles) {
+  AttnItem it;
+  const int per_img = qtiles * p.heads;
+  it.img = w / per_img;
+  const int r = w - it.img * per_img;
+  it.head = r / qtiles;
+  it.q0 = (r - it.head * qtiles) * ATT_BQ;
+  int kvlen = p.kv_len ? p.kv_len[it.img] : p.N;
+  it.kvlen = kvlen < p.N ? kvlen : p.N;
+  it.qlimit = p.zero_invalid ? it.kvlen : p.N;
+  const int T = (it.kvlen + ATT_BKV - 1) / ATT_BKV;
+  it.active = T > 0 && it.q0 < it.qlimit;
+  it.j_lo = 0;
+  int j_hi = T - 1;
+  if (p.window >= 0) {
+    const int q_last = min(it.q0 + ATT_BQ, p.N) - 1;
+    it.j_lo = max(0, it.q0 - p.window) / ATT_BKV;
+    j_hi = min(T - 1, (int)min((long long)q_last + p.window, (long long)p.N - 1) / ATT_BKV);
+  }
+  it.Tn = j_hi - it.j_lo + 1;
+  return it;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(192, 2)
+attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
+                    const int total_items, const int qtiles) {
+  using S = AttnShape<DH, 1>;
+  static_assert(DH == 64, "persistent attention: d = 64 only");
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N = p.N;
+  const int W = p.window;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem + S::OFF_Q;
+  uint8_t* sK = smem + S::OFF_K;
+  uint8_t* sV = smem + S::OFF_V;
+  uint8_t* sP = smem + S::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;               // [2]
+  uint64_t* k_empty = bars + 3;              // [2]
+  uint64_t* v_full = bars + 5;               // [2]
+  uint64_t* v_empty = bars + 7;              // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 10;             // count 128
+  uint64_t* p_full = bars + 11;              // count 128
+  uint64_t* pv_done = bars + 12;
+  uint64_t* q_empty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  if (warp == 4) {
+    if (lane < 14) mbar_init(&bars[lane], (lane == 10 || lane == 11) ? 128u : 1u);
+    else if (lane == 17) tma_prefetch_desc(&tmQ);
+    else if (lane == 18) tma_prefetch_desc(&tmK);
+    else if (lane == 19) tma_prefetch_desc(&tmV);
+    else if (lane == 20) tma_prefetch_desc(&tmO);
+    fence_barrier_init();
+    __syncwarp();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t n_item = 0, n_k = 0, n_v = 0;   // active items / K tiles / V tiles issued so far by this CTA
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const AttnItem it = attn_item(p, w, qtiles);
+        if (!it.active) continue;
+        const long long row0 = (long long)it.img * N;
+        if (n_item > 0) mbar_wait(q_empty, (n_item - 1) & 1u);     // last S MMA of the previous item has read Q
+        mbar_expect_tx(q_full, S::TILE_BYTES);
+        tma_load_2d(sQ, &tmQ, q_full, it.head * DH, (int)(row0 + it.q0));
+        ++n_item;
+        auto load_k = [&](int jj) {
+          const uint32_t slot = n_k % S::RK;
+          mbar_wait(&k_empty[slot], ((n_k / S::RK) & 1u) ^ 1u);
+          mbar_expect_tx(&k_full[slot], S::TILE_BYTES);
+          tma_load_2d(sK + slot * S::TILE_BYTES, &tmK, &k_full[slot], it.head * DH, (int)(row0 + (long long)(it.j_lo + jj) * ATT_BKV));
+          ++n_k;
+        };
+        load_k(0);
+        for (int jj = 0; jj < it.Tn; ++jj) {
+          if (jj + 1 < it.Tn) load_k(jj + 1);
+          const uint32_t slot = n_v % S::RV;
+          mbar_wait(&v_empty[slot], ((n_v / S::RV) & 1u) ^ 1u);
+          mbar_expect_tx(&v_full[slot], S::TILE_BYTES);
+          tma_load_2d(sV + slot * S::TILE_BYTES, &tmV, &v_full[slot], it.head * DH, (int)(row0 + (long long)(it.j_lo + jj) * ATT_BKV));
+          ++n_v;
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, DH, 0, 1);   // B (= V) is MN-major
+      uint32_t n_item = 0, n_k = 0, n_v = 0, n_t = 0;   // n_t = key tiles whose S has been issued so far
+      uint32_t n_pv = 0;                                 // key tiles whose PV has been issued so far
+      const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
+      auto issue_s = [&]() {   // S(tile n_t) = Q K^T; waits for the K tile and for the S buffer
+        const uint32_t slot = n_k % S::RK;
+        mbar_wait(&k_full[slot], (n_k / S::RK) & 1u);
+        if (n_t > 0) mbar_wait(s_empty, (n_t - 1) & 1u);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sK + slot * S::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16_ss(tmem_base, make_desc_kmajor_sw128(qa + kk * 32), make_desc_kmajor_sw128(ka + kk * 32), idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&k_empty[slot]);
+        umma_commit(s_full);
+        ++n_k;
+        ++n_t;
+      };
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const AttnItem it = attn_item(p, w, qtiles);
+        if (!it.active) continue;
+        mbar_wait(q_full, n_item & 1u);
+        ++n_item;
+        issue_s();
+        for (int jj = 0; jj < it.Tn; ++jj) {
+          if (jj + 1 < it.Tn) issue_s();          // S(jj+1) as soon as the softmax threads have pulled S(jj)
+          else umma_commit(q_empty);              // every S MMA of this item has been issued: Q may be refilled when they finish
+          const uint32_t slot = n_v % S::RV;
+          mbar_wait(&v_full[slot], (n_v / S::RV) & 1u);
+          mbar_wait(p_full, n_pv & 1u);
+          tc_fence_after();
+          const uint32_t va = smem_u32(sV + slot * S::TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
+            const uint64_t adesc = make_desc_kmajor_sw128(pa + (kk >> 2) * BLK + (kk & 3) * 32);
+            const uint64_t bdesc = make_smem_desc(va + kk * 2048, BLK, 1024, 2);
+            umma_bf16_ss(tmem_base + S::O_COL0, adesc, bdesc, idesc_o, (jj | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&v_empty[slot]);
+          umma_commit(pv_done);
+          ++n_v;
+          ++n_pv;
+        }
+      }
+    }
+  } else {
+    // ===== softmax warpgroup: thread <-> query row =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base;
+    const uint32_t tO = tmem_base + lane_base + S::O_COL0;
+    uint8_t* prow = sP + r * 128;
+    const float sc = p.scale_log2;
+    uint32_t n_t = 0;          // key tiles processed so far by this CTA (phase of s_full / p_full / pv_done)
+    bool store_pending = false;
+    const bool prof = p.prof != nullptr && warp == 0 && lane == 0;
+    long long c_wait_s = 0, c_load = 0, c_max = 0, c_wait_pv = 0, c_exp = 0, c_tail = 0, c_epi_wait = 0, c_epi = 0;
+    const long long c_begin = prof ? clock64() : 0;
+#define PCLK() (prof ? clock64() : 0)
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const AttnItem it = attn_item(p, w, qtiles);
+      const long long row0 = (long long)it.img * N;
+      const int qi = it.q0 + r;
+      if (!it.active) {   // nothing to attend to: the output rows are 0
+        if (qi < N) {
+          bf16* op = p.out + (row0 + qi) * p.ld_out + it.head * DH;
+          for (int c = 0; c < DH; c += 8) st_global_v4(op + c, 0u, 0u, 0u, 0u);
+          if (p.lse) p.lse[(row0 + qi) * p.heads + it.head] = INFINITY;
+        }
+        continue;
+      }
+      const int kvlen = it.kvlen;
+      const bool general_mask = p.key_mask != nullptr && !(p.prefix_flag != nullptr && p.prefix_flag[it.img] != 0);
+      const uint8_t* kmask = general_mask ? p.key_mask + row0 : nullptr;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < it.Tn; ++j, ++n_t) {
+        const int kv0 = (it.j_lo + j) * ATT_BKV;
+        const bool win_mask = W >= 0 && (kv0 < it.q0 + ATT_BQ - 1 - W || kv0 + ATT_BKV - 1 > it.q0 + W);
+        const bool need_mask = (kv0 + ATT_BKV > kvlen) || (kmask != nullptr) || win_mask;
+        const long long k0 = PCLK();
+        mbar_wait(s_full, n_t & 1u);
+        __syncwarp();
+        tc_fence_after();
+        const long long k1 = PCLK();
+        uint32_t v[4][32];
+        tmem_ld32(tS + 0, v[0]);
+        tmem_ld32(tS + 32, v[1]);
+        tmem_ld32(tS + 64, v[2]);
+        tmem_ld32(tS + 96, v[3]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(s_empty);   // S is in registers: the tensor core may overwrite it with the next tile's S
+        const long long k2 = PCLK();
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int kc = kv0 + c * 32 + i;
+              const bool ok = kc < kvlen && (kmask == nullptr || kmask[kc] != 0) && (W < 0 || abs(kc - qi) <= W);
+              if (!ok) v[c][i] = 0xff800000u;   // -inf
+            }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = max3f(mx0, __uint_as_float(v[0][i]), __uint_as_float(v[0][i + 1]));
+          mx1 = max3f(mx1, __uint_as_float(v[1][i]), __uint_as_float(v[1][i + 1]));
+          mx2 = max3f(mx2, __uint_as_float(v[2][i]), __uint_as_float(v[2][i + 1]));
+          mx3 = max3f(mx3, __uint_as_float(v[3][i]), __uint_as_float(v[3][i + 1]));
+        }
+        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+        float m_use = m_run, alpha = 1.f;
+        if (m_tile > m_run + RESCALE_THRESHOLD || m_run == -INFINITY) {
+          m_use = fmaxf(m_run, m_tile);
+          alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_use);
+        }
+        const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
+        const uint64_t sc2 = f2_pack(sc, sc), nm2 = f2_pack(-m_sub, -m_sub);
+        uint64_t sum2a = 0ull, sum2b = 0ull;
+        // the P buffer is free once the previous tile's PV (this item's or the previous item's last) has completed,
+        // and once the O tile staged in it by the previous item's epilogue has been read by its TMA store
+        const long long k3 = PCLK();
+        if (n_t > 0) {
+          mbar_wait(pv_done, (n_t - 1) & 1u);
+          __syncwarp();
+          tc_fence_after();
+        }
+        if (store_pending) {
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          store_pending = false;
+        }
+        const long long k4 = PCLK();
+      softmax_exp_tile(v, sc2, nm2, prow, r, sum2a, sum2b);
+        const long long k5 = PCLK();
+        float sum0, sum1;
+        f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
+        l_run = l_run * alpha + (sum0 + sum1);
+        m_run = m_use;
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int c = 0; c < DH; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + c, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + c, o);
+          }
+          tmem_wait_st();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        if (prof) {
+          const long long k6 = clock64();
+          c_wait_s += k1 - k0; c_load += k2 - k1; c_max += k3 - k2; c_wait_pv += k4 - k3; c_exp += k5 - k4; c_tail += k6 - k5;
+        }
+      }
+      // epilogue of the item: O / l
+      const long long e0 = PCLK();
+      mbar_wait(pv_done, (n_t - 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      const long long e1 = PCLK();
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      bool zero_row = false;
+      if (p.zero_invalid) zero_row = (qi >= kvlen) || (kmask != nullptr && qi < N && kmask[qi] == 0);
+      const float osc = zero_row ? 0.f : inv;
+      if (p.lse && qi < N) p.lse[(row0 + qi) * p.heads + it.head] = (zero_row || !(l_run > 0.f)) ? INFINITY : m_run + log2f(l_run);
+      uint32_t o[DH / 32][32];
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) tmem_ld32(tO + c * 32, o[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      if (p.tma_out) {
+        uint8_t* srow = sP + r * 128;   // O staged in block 0 of the P buffer (free: its last PV has completed)
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              wv[i] = bf2_cvt(__uint_as_float(o[c][8 * g + 2 * i]) * osc, __uint_as_float(o[c][8 * g + 2 * i + 1]) * osc);
+            const int col = c * 32 + 8 * g;
+            const int ch = (col >> 3) ^ (r & 7);
+            *reinterpret_cast<uint4*>(srow + (ch << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO, sP + quarter * 32 * 128, it.head * DH, (int)(row0 + it.q0 + quarter * 32));
+          tma_store_commit();
+        }
+        store_pending = true;
+      } else if (qi < N) {
+        bf16* op = p.out + (row0 + qi) * p.ld_out + it.head * DH;
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              wv[i] = bf2_cvt(__uint_as_float(o[c][8 * g + 2 * i]) * osc, __uint_as_float(o[c][8 * g + 2 * i + 1]) * osc);
+            st_global_v4(op + c * 32 + 8 * g, wv[0], wv[1], wv[2], wv[3]);
+          }
+      }
+      if (prof) { c_epi_wait += e1 - e0; c_epi += clock64() - e1; }
+    }
+    if (store_pending && lane == 0) tma_store_wait_read();
+    if (prof) {
+      const long long tot = clock64() - c_begin;
+      atomicAdd(&p.prof[0], (unsigned long long)c_wait_s); atomicAdd(&p.prof[1], (unsigned long long)c_load);
+      atomicAdd(&p.prof[2], (unsigned long long)c_max); atomicAdd(&p.prof[3], (unsigned long long)c_wait_pv);
+      atomicAdd(&p.prof[4], (unsigned long long)c_exp); atomicAdd(&p.prof[5], (unsigned long long)c_tail);
+      atomicAdd(&p.prof[6], (unsigned long long)c_epi_wait); atomicAdd(&p.prof[7], (unsigned long long)c_epi);
+      atomicAdd(&p.prof[8], (unsigned long long)tot); atomicAdd(&p.prof[9], (unsigned long long)n_t);
+    }
+#undef PCLK
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
+  using S = AttnShape<64, 1>;
+  const long long Mrows = (long long)a.B * a.N;
+  const long long cols = (long long)a.heads * a.d;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  if (encode_tmap_bf16_sw128(&tmQ, a.q, cols, Mrows, a.ld_qkv, ATT_BQ)) return -1;
+  if (encode_tmap_bf16_sw128(&tmK, a.k, cols, Mrows, a.ld_qkv, ATT_BKV)) return -1;
+  if (encode_tmap_bf16_sw128(&tmV, a.v, cols, Mrows, a.ld_qkv, ATT_BKV)) return -1;
+  if (encode_tmap_bf16(&tmO, a.out, cols, Mrows, a.ld_out, 64, 32, 128)) return -1;
+  AttnParams p;
+  p.out = a.out; p.ld_out = a.ld_out;
+  p.kv_len = a.kv_len; p.key_mask = a.key_mask; p.prefix_flag = a.prefix_flag;
+  p.N = a.N; p.heads = a.heads; p.zero_invalid = a.zero_invalid_rows;
+  p.tma_out = (a.N % ATT_BQ == 0) ? 1 : 0;
+  p.window = a.window;
+  p.lse = a.lse;
+  p.prof = nullptr;
+  static const int prof_mode = getenv("VTK_ATTN_PROF") ? atoi(getenv("VTK_ATTN_PROF")) : 0;
+  static unsigned long long* d_prof = nullptr;
+  if (prof_mode) {
+    if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream);
+    p.prof = d_prof;
+  }
+  p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
+  auto kern = attn_persist_kernel<64>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES), "cudaFuncSetAttribute(attn_persist)"))
+      return -1;
+    attr_set = true;
+  }
+  const int qtiles = (a.N + ATT_BQ - 1) / ATT_BQ;
+  const long long total = (long long)a.B * a.heads * qtiles;
+  if (total >= (1ll << 31)) { set_error("attention: too many work items"); return -2; }
+  const int grid = (int)std::min<long long>(total, 2ll * num_sms());
+  kern<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
+  if (prof_mode) {
+    unsigned long long h[16];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    const double nt = h[9] ? (double)h[9] : 1.0;
+    fprintf(stderr, "[attn prof] persistent N=%d grid=%d: cycles per key tile (softmax warp 0): wait S %.0f | tmem load %.0f | mask+max %.0f | "
+            "wait PV/store %.0f | exp+P %.0f | tail %.0f || per tile amortised: epilogue wait %.0f, epilogue %.0f, total %.0f\n",
+            a.N, grid, h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[6] / nt, h[7] / nt, h[8] / nt);
+  }
+  return check_cuda(cudaGetLastError(), "attention (persistent) launch");
+}
+
 template <int DH, int NQ>
 static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   using S = AttnShape<DH, NQ>;
@@ -493,7 +923,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.B <= 0 || a.N <= 0 || a.heads <= 0) { set_error("attention: empty problem"); return -2; }
   if ((a.ld_qkv % 8) || (a.ld_out % 8)) { set_error("attention: row strides must be multiples of 8"); return -2; }
   if (a.d == 64) {
-    static const int nq = getenv("VTK_ATTN_NQ") ? atoi(getenv("VTK_ATTN_NQ")) : 1;   // perf experiments: 2 = one CTA per SM
+    // perf experiments: VTK_ATTN_NQ = 0 (default) persistent kernel, 1 = one-shot CTAs (2 per SM), 2 = one-shot, one CTA per SM
+    static const int nq = getenv("VTK_ATTN_NQ") ? atoi(getenv("VTK_ATTN_NQ")) : 0;
+    if (nq == 0) return launch_attention_persist(a, stream);
     return nq == 2 ? launch_attention_t<64, 2>(a, stream) : launch_attention_t<64, 1>(a, stream);
   }
   if (a.d == 128) return launch_attention_t<128, 2>(a, stream);
