@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- encode+decode images/sec of the B200-native ViTok-v2 AE hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|350M-512|c5|c5-350M]
 
 Contract (see DESIGN.md "Measurement"):
   * one "step" = AE.encode + AE.decode over one batch of synthetic images of the named resolution;
@@ -38,6 +38,9 @@ WORKLOADS = {
     "c2": ("Ld4-Ld24/1x16x64", 64, 256, 256, "flash"),
     "c4": ("Td4-T/1x16x64", 8, 512, 1024, "flash"),
     "350M-512": ("Ld4-Ld24/1x16x64", 16, 512, 1024, "flash"),
+    # BASELINE configs[2]: NaFlex mixed-aspect batch (sizes drawn in [128,512]^2, non-multiples of 16 included), masked
+    # varlen attention (sdpa backend = the only reference backend that honours patch_mask); resolution 0 = ragged
+    "c3": ("Ld4-Ld24/1x16x16", 64, 0, 1024, "sdpa"),
     # training-step configs (BASELINE configs[4]): forward + Charbonnier + backward + AdamW, DDP all-reduce when N > 1
     "c5": ("Td4-T/1x32x256", 8, 1024, 1024, "flash"),
     "c5-350M": ("Ld4-Ld24/1x16x64", 16, 256, 256, "flash"),
@@ -54,6 +57,13 @@ def peaks():
         d = json.load(open(p))
         return {"bf16_sustained": d["bf16_tflops_sustained"], "bf16_burst": d["bf16_tflops"], "hbm": d["hbm_gbs"], "src": "measured"}
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
+
+
+def c3_sizes(n, seed):
+    """Seeded (H, W) list for the c3 workload: uniform in [128, 512], every image fits max_tokens = 1024 at p = 16."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    return [(int(rng.randint(128, 513)), int(rng.randint(128, 513))) for _ in range(n)]
 
 
 def flops_per_image(cfg, N):
@@ -144,7 +154,7 @@ def barrier(world: int):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (restatement of the reference's PyTorch CPU path) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(variant: str, n_images: int, res: int, steps: int, warmup: int):
+def cpu_oracle_rate(variant: str, n_images: int, res: int, steps: int, warmup: int, backend: str = "sdpa"):
     from oracle import ae_oracle, pp_oracle
     from oracle.weights import make_state_dict, synth_images
     import numpy as np
@@ -152,33 +162,42 @@ def cpu_oracle_rate(variant: str, n_images: int, res: int, steps: int, warmup: i
     torch.set_num_threads(cores)
     cfg = ae_oracle.decode_variant(variant)
     sd = make_state_dict(cfg, seed=0)
-    T = (res // cfg["spatial_stride"]) ** 2
-    b = pp_oracle.collate([pp_oracle.patchify(i, cfg["spatial_stride"], T) for i in synth_images([(res, res)] * n_images, seed=1234)])
+    if res > 0:
+        sizes, T = [(res, res)] * n_images, (res // cfg["spatial_stride"]) ** 2
+    else:
+        sizes, T = c3_sizes(n_images, 1234), 1024
+    b = pp_oracle.collate([pp_oracle.patchify(i, cfg["spatial_stride"], T) for i in synth_images(sizes, seed=1234)])
     batch = {k: torch.from_numpy(np.asarray(v)) for k, v in b.items()}
     times = []
     with torch.no_grad():
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            enc = ae_oracle.encode(sd, batch, cfg["encoder_heads"])
-            ae_oracle.decode(sd, enc, cfg["decoder_heads"])
+            enc = ae_oracle.encode(sd, batch, cfg["encoder_heads"], attn_backend=backend)
+            ae_oracle.decode(sd, enc, cfg["decoder_heads"], attn_backend=backend)
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
     return n_images * len(times) / total, cores, total / len(times)
 
 
+def _res_name(res):
+    return f"{res}px" if res > 0 else "128-512px mixed aspect (NaFlex, max_tokens 1024)"
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    variant, batch, res, T, _ = WORKLOADS[args.workload]
+    variant, batch, res, T, backend = WORKLOADS[args.workload]
     n_img = 4 if res <= 256 else 1
-    rate, cores, sec = cpu_oracle_rate(variant, n_img, res, max(1, args.steps), max(0, min(args.warmup, 1)))
-    sample = f"{n_img} x {res}x{res} images per step, fp32, torch CPU ops on {cores} threads (oracle port of vitok/models/ae.py)"
+    rate, cores, sec = cpu_oracle_rate(variant, n_img, res, max(1, args.steps), max(0, min(args.warmup, 1)),
+                                       "sdpa" if res == 0 else "sdpa")
+    sample = (f"{n_img} x {_res_name(res)} images per step, fp32, torch CPU ops on {cores} threads "
+              "(oracle port of vitok/models/ae.py)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {variant} encode+decode @{res}px, batch {batch}/GPU", "variant": variant,
+        "config": {"workload": f"{args.workload}: {variant} encode+decode @{_res_name(res)}, batch {batch}/GPU", "variant": variant,
                    "resolution": res, "tokens_per_image": T, "batch_per_gpu": batch},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -204,8 +223,17 @@ def run_ours(args, rank, world, local):
     torch.manual_seed(0)
     model = vb.AE(**cfg, attn_backend=backend).eval().to(device=dev, dtype=torch.bfloat16)
     g = torch.Generator().manual_seed(1234 + rank)
-    imgs = torch.rand(B, 3, res, res, generator=g) * 2 - 1
-    pd = vb.patchify_batch(imgs.to(dev), cfg["spatial_stride"], T, out_dtype=torch.bfloat16, device=dev)
+    patch = cfg["spatial_stride"]
+    ragged = res == 0
+    if ragged:
+        sizes = c3_sizes(B, 1234 + rank)
+        img_list = [torch.rand(3, h, w, generator=g) * 2 - 1 for h, w in sizes]
+        pd = vb.patchify_batch([i.to(dev) for i in img_list], patch, T, out_dtype=torch.bfloat16, device=dev)
+        n_valid = [-(-h // patch) * -(-w // patch) for h, w in sizes]
+    else:
+        imgs = torch.rand(B, 3, res, res, generator=g) * 2 - 1
+        pd = vb.patchify_batch(imgs.to(dev), patch, T, out_dtype=torch.bfloat16, device=dev)
+        n_valid = [T] * B
     N = T
     lib = _lib.load()
 
@@ -243,11 +271,15 @@ def run_ours(args, rank, world, local):
     # The serving loop a user of the reference writes (README.md:62-65): decoded uint8 images on the host ->
     # preprocess (to_tensor|normalize|patchify) -> encode -> decode -> postprocess (unpatchify, 0_255) -> uint8
     # images on the host.  Per step: H2D of the uint8 HWC batch, D2H of the uint8 CHW reconstructions.
-    host_u8 = ((imgs.permute(0, 2, 3, 1) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
-    host_out = torch.empty(B, 3, res, res, dtype=torch.uint8).pin_memory()
+    canvas = res if not ragged else 512
+    if ragged:   # one packed pinned buffer for the whole NaFlex batch (pack_images), one H2D copy per step
+        u8_list = [((i.permute(1, 2, 0) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous() for i in img_list]
+        host_u8, offs, szs = vb.pack_images(u8_list, pin=True)
+    else:
+        host_u8 = ((imgs.permute(0, 2, 3, 1) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+    host_out = torch.empty(B, 3, canvas, canvas, dtype=torch.uint8).pin_memory()
     h2d = host_u8.numel()
     d2h = host_out.numel()
-    patch = cfg["spatial_stride"]
 
     # Double-buffered pipeline on three streams (copy-in / compute / copy-out): step i's H2D and step i-1's D2H
     # overlap step i's kernels, the way a serving loop would drive the public API.  Every step still moves its
@@ -269,10 +301,13 @@ def run_ours(args, rank, world, local):
             dev_in[b].copy_(host_u8, non_blocking=True)
             ev_in[b].record(s_in)
         s_main.wait_event(ev_in[b])
-        d = vb.patchify_batch(dev_in[b], patch, T, out_dtype=torch.bfloat16, device=dev)
+        if ragged:
+            d = vb.patchify_packed(dev_in[b], offs, szs, patch, T, out_dtype=torch.bfloat16)
+        else:
+            d = vb.patchify_batch(dev_in[b], patch, T, out_dtype=torch.bfloat16, device=dev)
         ev_free[b].record(s_main)
         o = step(d)
-        img = vb.unpatchify(o, patch, max_grid_size=res // patch, output_format="0_255")
+        img = vb.unpatchify(o, patch, max_grid_size=canvas // patch, output_format="0_255")
         ev_done[b].record(s_main)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done[b])
@@ -323,7 +358,7 @@ def run_ours(args, rank, world, local):
         lib.vtk_ae_set_timing(h, 0)
         breakdown = {CLS_NAMES[i]: {"ms_per_step": tot[i] / prof_steps, "launches_per_step": cnt[i] // prof_steps} for i in range(6)}
         # dominant kernel: decoder QKV+SwiGLU GEMM; FLOPs per launch averaged over enc+dec launches
-        M = B * N
+        M = sum(n_valid)    # algorithmic rows: valid tokens only (padded tokens are not work)
         fl = 0.0
         for D, L in ((cfg["encoder_width"], cfg["encoder_depth"]), (cfg["decoder_width"], cfg["decoder_depth"])):
             hf = ((int(D * cfg["mlp_factor"]) + 8) // 16) * 16
@@ -343,7 +378,7 @@ def run_ours(args, rank, world, local):
 
     if rank != 0:
         return
-    gf = flops_per_image(cfg, N) / 1e9
+    gf = sum(flops_per_image(cfg, n) for n in n_valid) / B / 1e9     # per image, valid tokens only
     pk = peaks()
     cpu = None
     if world == 1 or rank == 0:
@@ -351,15 +386,16 @@ def run_ours(args, rank, world, local):
             n_img = 4 if res <= 256 else 1
             rate, cores, sec = cpu_oracle_rate(variant, n_img, res, 2, 1)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n_img} x {res}x{res} images, fp32, 2 timed iterations after 1 warm-up ({sec:.2f} s each)"}
+                   "sample": f"{n_img} x {_res_name(res)} images, fp32, 2 timed iterations after 1 warm-up ({sec:.2f} s each)"}
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {variant} encode+decode @{res}px, batch {B}/GPU", "variant": variant,
-                   "resolution": res, "tokens_per_image": N, "batch_per_gpu": B, "global_batch": B * world,
+        "config": {"workload": f"{args.workload}: {variant} encode+decode @{_res_name(res)}, batch {B}/GPU", "variant": variant,
+                   "resolution": res, "tokens_per_image": N, "valid_tokens_per_gpu": sum(n_valid),
+                   "token_packing": bool(ragged), "batch_per_gpu": B, "global_batch": B * world,
                    "attn_backend": backend, "weights": "random init (seed 0)",
                    "l2": "no flush: per-step working set (weights + activations) exceeds the 126 MB L2",
                    "gflop_per_image": gf},

@@ -86,6 +86,24 @@ int vtk_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream);
 /* kv_len[b] = 1 + last valid index, is_prefix[b] = mask is contiguous from 0.   vitok/models/ae.py:173-187 */
 int vtk_kv_len(const uint8_t* patch_mask, int* kv_len, int* is_prefix, int B, int N, void* stream);
 
+/* NaFlex token packing plan for a masked [B, N] batch (replaces the reference's [B,1,N,N] mask, vitok/models/ae.py:173-187,
+ * and its work on padded tokens).  Valid tokens are packed image after image, each image padded to a multiple of 128 rows:
+ *   n_valid [B]                  valid tokens per image
+ *   rel     [B*N]                rank of token t among the valid tokens of its image, -1 if masked
+ *   cu      [B+1]                packed row offset of each image; cu[B] = packed row count (stays on the device)
+ *   tile_img[B*ceil(N/128)]      image owning each 128-row packed tile (entries >= cu[B]/128 are not written)
+ *   tile_order[B*ceil(N/128)]    a permutation of the packed tiles [0, cu[B]/128), tiles of images with more key tiles
+ *                                first (ties in any order): the work list the attention kernel deals to its CTAs
+ *   src     [B*ceil128(N)]       packed row -> source row b*N+t, -1 for pad rows (entries >= cu[B] are not written)
+ * vtk_pack_rows gathers rows of `width` bf16 (packed[r] = in[src[r]], 0 for pad rows) for r < cu[B]; vtk_unpack_rows
+ * scatters them back (out[b,t] = packed[cu[b] + rel[b,t]], 0 for masked tokens). */
+int vtk_pack_plan(const uint8_t* patch_mask, int B, int N, int* n_valid, int* rel, int* cu, int* tile_img, int* tile_order,
+                  int* src, void* stream);
+int vtk_pack_rows(const void* in, int64_t ld_in, const int* src, const int* cu, int B, int N, void* packed, int64_t ld_packed,
+                  int width, void* stream);
+int vtk_unpack_rows(const void* packed, int64_t ld_packed, const int* rel, const int* cu, int B, int N, void* out,
+                    int64_t ld_out, int width, void* stream);
+
 /* out = bf16(A W^T + bias); bias may be null.                      nn.Linear: vitok/models/ae.py:191,220,242 */
 int vtk_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
                     int M, int N, int K, void* stream);
@@ -204,6 +222,13 @@ int vtk_ae_encode(vtk_ae_t h, const void* patches, const int64_t* row_idx, const
 /* AE.decode (vitok/models/ae.py:218-243): z [B,N,C] bf16 -> patches [B,N,P] bf16. */
 int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64_t* col_idx, const uint8_t* patch_mask,
                   int B, int N, void* patches_out, void* workspace, size_t workspace_bytes, void* stream);
+/* NaFlex token packing (default on).  When a patch_mask is given and head_dim == 64, vtk_ae_encode/decode gather the
+ * valid tokens of every image into a packed row range (each image padded to a multiple of 128 rows), run every kernel
+ * of the layer stack over the packed rows only -- the packed row count stays in device memory, nothing syncs -- and
+ * scatter the result back; masked tokens of the output are 0.  This replaces the reference's [B,1,N,N] mask
+ * (vitok/models/ae.py:173-187) and its work on padded tokens.  enable = 0 keeps the padded [B, N] layout with
+ * in-kernel key masking (results on valid tokens are identical for prefix masks). */
+int vtk_ae_set_packing(vtk_ae_t h, int enable);
 /* number of kernels launched by the last vtk_ae_encode/decode on this handle (for gpu_launches accounting) */
 int vtk_ae_last_launch_count(vtk_ae_t h);
 /* Optional per-launch CUDA-event timing (bench.py's live roofline).  With timing enabled every kernel launched by

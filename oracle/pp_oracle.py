@@ -153,3 +153,31 @@ def normalize_u8(img_u8_hwc: np.ndarray) -> np.ndarray:
     """
     x = img_u8_hwc.astype(np.float32).transpose(2, 0, 1) / np.float32(255.0)
     return (x - np.float32(0.5)) / np.float32(0.5)
+
+
+def pack_plan(mask: np.ndarray, tile: int = 128) -> Dict[str, np.ndarray]:
+    """Token-packing plan of a [B, N] bool mask: the index layout our packed NaFlex path uses in place of the
+    reference's [B,1,N,N] attention mask (vitok/models/ae.py:173-187 keeps key j of image b iff patch_mask[b, j]).
+
+    This is OUR layout, not a reference data structure: the oracle restates its definition in numpy so that the
+    CUDA index packing can be checked bit-exactly (include/vitok_b200.h: vtk_pack_plan).  Valid tokens keep their
+    order inside an image; every image is padded to a multiple of `tile` packed rows.
+    """
+    mask = np.asarray(mask).astype(bool)
+    B, N = mask.shape
+    n_valid = mask.sum(1).astype(np.int32)
+    rel = np.where(mask, np.cumsum(mask, axis=1) - 1, -1).astype(np.int32).reshape(-1)
+    padded = (n_valid + tile - 1) // tile * tile
+    cu = np.zeros(B + 1, np.int32)
+    cu[1:] = np.cumsum(padded)
+    total = int(cu[B])
+    src = np.full(total, -1, np.int32)
+    tile_img = np.zeros(total // tile, np.int32)
+    for b in range(B):
+        idx = np.nonzero(mask[b])[0]
+        src[cu[b]:cu[b] + len(idx)] = b * N + idx
+        tile_img[cu[b] // tile:cu[b + 1] // tile] = b
+    # attention work list: tiles of images with more key tiles first (any order among equal counts)
+    kt = padded // tile
+    tile_order = np.argsort(-kt[tile_img], kind="stable").astype(np.int32)
+    return {"n_valid": n_valid, "rel": rel, "cu": cu, "tile_img": tile_img, "tile_order": tile_order, "src": src}

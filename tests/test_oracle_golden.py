@@ -110,3 +110,29 @@ def test_ae_c1_matches_reference(init, golden_dir):
     assert np.abs(p.astype(np.float64).sum(-1) - g[f"{init}_patches_rowsum"]).max() <= 2e-3
     # z is per-token zero-mean / unit-variance (LN bottleneck)
     assert np.abs(z.mean(-1)).max() < 1e-5 and np.abs(z.var(-1) - 1).max() < 1e-3
+
+
+def test_pack_plan_oracle_properties():
+    """The token-packing plan (oracle/pp_oracle.py: pack_plan) keeps exactly the keys the reference's mask keeps
+    (ae.py:173-187: key j of image b iff patch_mask[b, j]) in their original order, image after image."""
+    import numpy as np
+    from oracle import pp_oracle
+    rng = np.random.RandomState(0)
+    mask = rng.rand(9, 300) > 0.3
+    mask[4] = False
+    mask[5, :129] = True
+    pl = pp_oracle.pack_plan(mask)
+    B, N = mask.shape
+    assert pl["cu"][0] == 0 and (pl["cu"] % 128 == 0).all() and pl["cu"][-1] == len(pl["src"])
+    for b in range(B):
+        rows = pl["src"][pl["cu"][b]:pl["cu"][b + 1]]
+        kept = rows[rows >= 0]
+        assert np.array_equal(kept, b * N + np.nonzero(mask[b])[0])          # same keys, same order
+        assert (rows[len(kept):] == -1).all() and len(rows) - len(kept) < 128
+        assert (pl["tile_img"][pl["cu"][b] // 128:pl["cu"][b + 1] // 128] == b).all()
+    valid = pl["rel"] >= 0
+    assert np.array_equal(valid.reshape(B, N), mask)
+    flat_rows = (pl["cu"][:-1, None] + pl["rel"].reshape(B, N))[mask]
+    assert np.array_equal(pl["src"][flat_rows], np.nonzero(mask.reshape(-1))[0])   # rel/cu invert src
+    kt = ((pl["n_valid"] + 127) // 128)[pl["tile_img"]][pl["tile_order"]]
+    assert (np.diff(kt) <= 0).all() and np.array_equal(np.sort(pl["tile_order"]), np.arange(len(pl["tile_img"])))

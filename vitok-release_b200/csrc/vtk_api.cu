@@ -2,6 +2,7 @@
 // tensor-map encoding, and the AE encode/decode layer loops.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -100,12 +101,15 @@ struct Side {
 struct Workspace {
   bf16 *x, *h, *qkv, *a2, *rope;
   int *kv_len, *is_prefix;
+  PackPlan plan;        // NaFlex token packing (masked batches): plan arrays + packed input / output staging rows
+  bf16 *pin, *pout;
   size_t bytes;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static Workspace carve(const Side& s, void* base, long long M, int B) {
+// M = row capacity of the activation buffers = B * ceil128(N) (the packed layout pads every image to 128 rows)
+static Workspace carve(const Side& s, void* base, int B, int N, int io_cols) {
   Workspace w;
   size_t off = 0;
   auto take = [&](size_t nbytes) {
@@ -113,7 +117,8 @@ static Workspace carve(const Side& s, void* base, long long M, int B) {
     off += align_up(nbytes, 1024);
     return p;
   };
-  const long long D = s.width, Hf = s.hidden, d = s.head_dim();
+  const long long M = PackPlan::row_capacity(B, N);
+  const long long D = s.width, d = s.head_dim();
   w.x = static_cast<bf16*>(take((size_t)M * D * 2));
   w.h = static_cast<bf16*>(take((size_t)M * D * 2));
   w.qkv = static_cast<bf16*>(take((size_t)M * 3 * D * 2));
@@ -121,9 +126,20 @@ static Workspace carve(const Side& s, void* base, long long M, int B) {
   w.rope = static_cast<bf16*>(take((size_t)((M + 31) / 32 * 32) * 2 * d * 2));   // pair-expanded table, 32-row groups
   w.kv_len = static_cast<int*>(take((size_t)B * 4));
   w.is_prefix = static_cast<int*>(take((size_t)B * 4));
+  w.plan.B = B; w.plan.N = N;
+  w.plan.n_valid = w.kv_len;
+  w.plan.rel = static_cast<int*>(take((size_t)B * N * 4));
+  w.plan.cu = static_cast<int*>(take((size_t)(B + 1) * 4));
+  w.plan.tile_img = static_cast<int*>(take((size_t)(M / 128) * 4));
+  w.plan.tile_order = static_cast<int*>(take((size_t)(M / 128) * 4));
+  w.plan.src = static_cast<int*>(take((size_t)M * 4));
+  w.pin = static_cast<bf16*>(take((size_t)M * io_cols * 2));
+  w.pout = static_cast<bf16*>(take((size_t)M * io_cols * 2));
   w.bytes = off;
   return w;
 }
+
+static int io_cols(const vtk_ae_config& c) { return c.pixels_per_token > c.channels_per_token ? c.pixels_per_token : c.channels_per_token; }
 
 }  // namespace vtk
 
@@ -134,6 +150,7 @@ struct vtk_ae_s {
   vtk_ae_config cfg;
   vtk::Side side[2];
   int last_launches = 0;
+  bool packing = true;   // NaFlex token packing for masked batches (vtk_ae_set_packing)
   // timing: one (start, stop) event pair per launch of the last encode/decode call
   bool timing = false;
   std::vector<cudaEvent_t> ev;      // 2 per launch
@@ -231,6 +248,34 @@ int vtk_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream) {
 int vtk_kv_len(const uint8_t* patch_mask, int* kv_len, int* is_prefix, int B, int N, void* stream) {
   VTK_REQUIRE(patch_mask && kv_len, "vtk_kv_len: null pointer");
   return launch_kv_len(patch_mask, kv_len, is_prefix, B, N, (cudaStream_t)stream);
+}
+
+int vtk_pack_plan(const uint8_t* patch_mask, int B, int N, int* n_valid, int* rel, int* cu, int* tile_img, int* tile_order,
+                  int* src, void* stream) {
+  VTK_REQUIRE(patch_mask && n_valid && rel && cu && tile_img && tile_order && src, "vtk_pack_plan: null pointer");
+  VTK_REQUIRE(B > 0 && N > 0 && PackPlan::row_capacity(B, N) < (1ll << 31), "vtk_pack_plan: bad batch shape B=%d N=%d", B, N);
+  PackPlan pl;
+  pl.B = B; pl.N = N; pl.n_valid = n_valid; pl.rel = rel; pl.cu = cu; pl.tile_img = tile_img; pl.tile_order = tile_order;
+  pl.src = src;
+  return launch_pack_plan(patch_mask, B, N, pl, (cudaStream_t)stream);
+}
+int vtk_pack_rows(const void* in, int64_t ld_in, const int* src, const int* cu, int B, int N, void* packed, int64_t ld_packed,
+                  int width, void* stream) {
+  VTK_REQUIRE(in && src && cu && packed, "vtk_pack_rows: null pointer");
+  VTK_REQUIRE(B > 0 && N > 0 && width > 0, "vtk_pack_rows: empty problem");
+  PackPlan pl;
+  pl.B = B; pl.N = N; pl.n_valid = nullptr; pl.rel = nullptr; pl.cu = const_cast<int*>(cu); pl.tile_img = nullptr;
+  pl.tile_order = nullptr; pl.src = const_cast<int*>(src);
+  return launch_pack_rows((const bf16*)in, ld_in, pl, PackPlan::row_capacity(B, N), (bf16*)packed, ld_packed, width, (cudaStream_t)stream);
+}
+int vtk_unpack_rows(const void* packed, int64_t ld_packed, const int* rel, const int* cu, int B, int N, void* out,
+                    int64_t ld_out, int width, void* stream) {
+  VTK_REQUIRE(packed && rel && cu && out, "vtk_unpack_rows: null pointer");
+  VTK_REQUIRE(B > 0 && N > 0 && width > 0, "vtk_unpack_rows: empty problem");
+  PackPlan pl;
+  pl.B = B; pl.N = N; pl.n_valid = nullptr; pl.rel = const_cast<int*>(rel); pl.cu = const_cast<int*>(cu); pl.tile_img = nullptr;
+  pl.tile_order = nullptr; pl.src = nullptr;
+  return launch_unpack_rows((const bf16*)packed, ld_packed, pl, (bf16*)out, ld_out, width, (cudaStream_t)stream);
 }
 
 static GemmArgs base_args(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t w_rows, int M, int N, int K) {
@@ -453,19 +498,28 @@ int vtk_ae_set_weights(vtk_ae_t h, int side, const void* w_a, const void* b_a, c
 
 size_t vtk_ae_workspace_bytes(vtk_ae_t h, int side, int B, int N) {
   if (!h || side < 0 || side > 1 || B <= 0 || N <= 0) return 0;
-  return carve(h->side[side], nullptr, (long long)B * N, B).bytes;
+  return carve(h->side[side], nullptr, B, N, io_cols(h->cfg)).bytes;
 }
 
+// Token packing is used whenever a mask is given and the attention kernel has the packed variant (head_dim 64).
+// vtk_ae_set_packing(h, 0) / VTK_NO_PACK=1 keep the padded [B, N] layout with in-kernel key masking (A/B experiments, parity tests).
+static bool use_packing(const vtk_ae_s* h, const Side& s, const uint8_t* patch_mask) {
+  static const int off = getenv("VTK_NO_PACK") ? atoi(getenv("VTK_NO_PACK")) : 0;
+  return patch_mask != nullptr && s.depth > 0 && s.head_dim() == 64 && h->packing && !off;
+}
+
+// rows = row capacity of the activation buffers; with `pl` the kernels read the live row count from pl->m_dev()
 static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int64_t* row_idx, const int64_t* col_idx,
-                      const uint8_t* patch_mask, int B, int N, cudaStream_t st, int& launches) {
-  const int M = B * N, D = s.width, d = s.head_dim(), Hf = s.hidden, qp = s.qp(), kp = s.kp();
+                      const uint8_t* patch_mask, int B, int N, int rows, const PackPlan* pl, cudaStream_t st, int& launches) {
+  const int M = rows, D = s.width, d = s.head_dim(), Hf = s.hidden, qp = s.qp(), kp = s.kp();
   const float eps = h->cfg.norm_eps;
+  const int* m_dev = pl ? pl->m_dev() : nullptr;
   int r;
   if (s.depth > 0) {
-    { LaunchTimer t(h, st, CLS_MISC); r = launch_rope_table(row_idx, col_idx, s.inv_freq, w.rope, M, d, st); }
+    { LaunchTimer t(h, st, CLS_MISC); r = launch_rope_table(row_idx, col_idx, s.inv_freq, w.rope, M, d, st, pl ? pl->src : nullptr, m_dev); }
     if (r) return r;
     ++launches;
-    if (patch_mask) {
+    if (patch_mask && !pl) {
       { LaunchTimer t(h, st, CLS_MISC); r = launch_kv_len(patch_mask, w.kv_len, w.is_prefix, B, N, st); }
       if (r) return r;
       ++launches;
@@ -473,30 +527,84 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
   }
   for (int i = 0; i < s.depth; ++i) {
     const vtk_block_weights& b = s.blocks[i];
-    { LaunchTimer t(h, st, CLS_RMSNORM); r = launch_rmsnorm(w.x, D, (const bf16*)b.norm1, w.h, D, M, D, eps, st); }
+    { LaunchTimer t(h, st, CLS_RMSNORM); r = launch_rmsnorm(w.x, D, (const bf16*)b.norm1, w.h, D, M, D, eps, st, m_dev); }
     if (r) return r;
     GemmArgs g1 = base_args(w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
     g1.epi.qkv = w.qkv; g1.epi.ld_qkv = 3 * D; g1.epi.act = w.a2 + D; g1.epi.ld_act = kp;
     g1.epi.normq = (const bf16*)b.norm_q; g1.epi.normk = (const bf16*)b.norm_k; g1.epi.rope = w.rope;
     g1.epi.D = D; g1.epi.d = d; g1.epi.Hf = Hf; g1.epi.qp = qp; g1.epi.eps = eps;
+    g1.epi.m_dev = m_dev;
     { LaunchTimer t(h, st, CLS_QKV_SWIGLU); r = launch_gemm(EPI_QKV_SWIGLU, g1, st); }
     if (r) return r;
     AttnArgs a;
     a.q = w.qkv; a.k = w.qkv + D; a.v = w.qkv + 2 * D; a.ld_qkv = 3 * D; a.out = w.a2; a.ld_out = kp;
-    a.kv_len = patch_mask ? w.kv_len : nullptr; a.key_mask = patch_mask; a.prefix_flag = patch_mask ? w.is_prefix : nullptr;
-    a.B = B; a.N = N; a.heads = s.heads; a.d = d; a.zero_invalid_rows = patch_mask ? 1 : 0;
-    // sliding window: flash backend only (attention.py:113-116); the sdpa backend (patch_mask given) ignores it
-    a.window = (!patch_mask && h->cfg.sliding_window > 0) ? h->cfg.sliding_window : -1;
+    a.B = B; a.N = N; a.heads = s.heads; a.d = d;
+    if (pl) {
+      // packed: image b = packed rows [cu[b], cu[b+1]) with its n_valid[b] tokens in front -- no key mask left
+      a.kv_len = pl->n_valid; a.key_mask = nullptr; a.prefix_flag = nullptr; a.zero_invalid_rows = 0;
+      a.cu = pl->cu; a.tile_img = pl->tile_img; a.tile_order = pl->tile_order; a.m_dev = m_dev; a.row_cap = M;
+      a.window = -1;
+    } else {
+      a.kv_len = patch_mask ? w.kv_len : nullptr; a.key_mask = patch_mask; a.prefix_flag = patch_mask ? w.is_prefix : nullptr;
+      a.zero_invalid_rows = patch_mask ? 1 : 0;
+      // sliding window: flash backend only (attention.py:113-116); the sdpa backend (patch_mask given) ignores it
+      a.window = (!patch_mask && h->cfg.sliding_window > 0) ? h->cfg.sliding_window : -1;
+    }
     a.lse = nullptr;
     { LaunchTimer t(h, st, CLS_ATTENTION); r = launch_attention(a, st); }
     if (r) return r;
     GemmArgs g2 = base_args(w.a2, kp, b.w_out, kp, D, M, D, D + Hf);
     g2.epi.out = w.x; g2.epi.ldo = D; g2.epi.gamma = (const bf16*)b.gamma;
+    g2.epi.m_dev = m_dev;
     { LaunchTimer t(h, st, CLS_PROJ_RESID); r = launch_gemm(EPI_RESID, g2, st); }
     if (r) return r;
     launches += 4;
   }
   return 0;
+}
+
+// [embed -> blocks -> head] over either the padded [B*N] rows or the packed rows of a masked batch
+static int run_side(vtk_ae_s* h, int side, const void* in, const int64_t* row_idx, const int64_t* col_idx,
+                    const uint8_t* patch_mask, int B, int N, void* out, void* workspace, cudaStream_t st) {
+  const Side& s = h->side[side];
+  const int P = h->cfg.pixels_per_token, C = h->cfg.channels_per_token, D = s.width;
+  const int cin = side == 0 ? P : C, cout = side == 0 ? C : P;
+  Workspace w = carve(s, workspace, B, N, io_cols(h->cfg));
+  const bool packed = use_packing(h, s, patch_mask);
+  const PackPlan* pl = packed ? &w.plan : nullptr;
+  const int rows = packed ? (int)PackPlan::row_capacity(B, N) : B * N;
+  const int* m_dev = packed ? pl->m_dev() : nullptr;
+  int launches = 0, r;
+  h->ev_used = 0;
+  const bf16* a_in = (const bf16*)in;
+  if (packed) {
+    { LaunchTimer t(h, st, CLS_MISC); r = launch_pack_plan(patch_mask, B, N, *pl, st); }
+    if (r) return r;
+    { LaunchTimer t(h, st, CLS_MISC); r = launch_pack_rows((const bf16*)in, cin, *pl, rows, w.pin, cin, cin, st); }
+    if (r) return r;
+    launches += 4;
+    a_in = w.pin;
+  }
+  GemmArgs g = base_args(a_in, cin, s.w_a, cin, D, rows, D, cin);       // patch_embed ae.py:191 / decoder_embed ae.py:220
+  g.epi.out = w.x; g.epi.ldo = D; g.epi.bias = s.b_a; g.epi.m_dev = m_dev;
+  { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, g, st); }
+  if (r) return r;
+  ++launches;
+  if ((r = run_blocks(h, s, w, row_idx, col_idx, patch_mask, B, N, rows, pl, st, launches))) return r;
+  bf16* o = packed ? w.pout : (bf16*)out;
+  GemmArgs gz = base_args(w.x, D, s.w_b, D, cout, rows, cout, D);
+  gz.epi.out = o; gz.epi.ldo = cout; gz.epi.bias = s.b_b; gz.epi.eps = h->cfg.norm_eps; gz.epi.m_dev = m_dev;
+  if (side == 0) { LaunchTimer t(h, st, CLS_MISC); r = launch_gemm(EPI_BIAS_LN, gz, st); }     // to_code + output_fn, ae.py:207
+  else { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, gz, st); }                 // to_pixels, ae.py:242
+  if (r) return r;
+  ++launches;
+  if (packed) {   // scatter back to [B, N, cout]; masked tokens read as 0
+    { LaunchTimer t(h, st, CLS_MISC); r = launch_unpack_rows(w.pout, cout, *pl, (bf16*)out, cout, cout, st); }
+    if (r) return r;
+    ++launches;
+  }
+  h->last_launches = launches;
+  return VTK_OK;
 }
 
 static int check_io(vtk_ae_t h, int side, const void* in, const int64_t* row_idx, const int64_t* col_idx, int B, int N,
@@ -506,7 +614,7 @@ static int check_io(vtk_ae_t h, int side, const void* in, const int64_t* row_idx
   VTK_REQUIRE(s.width > 0 && s.w_a, "%s: this model has no %s weights set", fn, side ? "decoder" : "encoder");
   VTK_REQUIRE(in && row_idx && col_idx && out && workspace, "%s: null pointer", fn);
   VTK_REQUIRE(B > 0 && N > 0, "%s: empty batch (B=%d N=%d)", fn, B, N);
-  VTK_REQUIRE((long long)B * N < (1ll << 31), "%s: B*N too large", fn);
+  VTK_REQUIRE(PackPlan::row_capacity(B, N) < (1ll << 31), "%s: B*N too large", fn);
   VTK_REQUIRE(workspace_bytes >= vtk_ae_workspace_bytes(h, side, B, N), "%s: workspace too small (%zu < %zu)", fn,
               workspace_bytes, vtk_ae_workspace_bytes(h, side, B, N));
   VTK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "%s: workspace must be 1024-byte aligned", fn);
@@ -518,49 +626,19 @@ int vtk_ae_encode(vtk_ae_t h, const void* patches, const int64_t* row_idx, const
                   void* stream) {
   int r = check_io(h, 0, patches, row_idx, col_idx, B, N, z_out, workspace, workspace_bytes, "vtk_ae_encode");
   if (r) return r;
-  const Side& s = h->side[0];
-  cudaStream_t st = (cudaStream_t)stream;
-  const int M = B * N, P = h->cfg.pixels_per_token, C = h->cfg.channels_per_token, D = s.width;
-  Workspace w = carve(s, workspace, M, B);
-  int launches = 0;
-  GemmArgs g = base_args(patches, P, s.w_a, P, D, M, D, P);           // patch_embed, ae.py:191
-  g.epi.out = w.x; g.epi.ldo = D; g.epi.bias = s.b_a;
-  h->ev_used = 0;
-  { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, g, st); }
-  if (r) return r;
-  ++launches;
-  if ((r = run_blocks(h, s, w, row_idx, col_idx, patch_mask, B, N, st, launches))) return r;
-  GemmArgs gz = base_args(w.x, D, s.w_b, D, C, M, C, D);               // to_code + output_fn, ae.py:207
-  gz.epi.out = (bf16*)z_out; gz.epi.ldo = C; gz.epi.bias = s.b_b; gz.epi.eps = h->cfg.norm_eps;
-  { LaunchTimer t(h, st, CLS_MISC); r = launch_gemm(EPI_BIAS_LN, gz, st); }
-  if (r) return r;
-  ++launches;
-  h->last_launches = launches;
-  return VTK_OK;
+  return run_side(h, 0, patches, row_idx, col_idx, patch_mask, B, N, z_out, workspace, (cudaStream_t)stream);
 }
 
 int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64_t* col_idx, const uint8_t* patch_mask,
                   int B, int N, void* patches_out, void* workspace, size_t workspace_bytes, void* stream) {
   int r = check_io(h, 1, z, row_idx, col_idx, B, N, patches_out, workspace, workspace_bytes, "vtk_ae_decode");
   if (r) return r;
-  const Side& s = h->side[1];
-  cudaStream_t st = (cudaStream_t)stream;
-  const int M = B * N, P = h->cfg.pixels_per_token, C = h->cfg.channels_per_token, D = s.width;
-  Workspace w = carve(s, workspace, M, B);
-  int launches = 0;
-  GemmArgs g = base_args(z, C, s.w_a, C, D, M, D, C);                  // decoder_embed, ae.py:220
-  g.epi.out = w.x; g.epi.ldo = D; g.epi.bias = s.b_a;
-  h->ev_used = 0;
-  { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, g, st); }
-  if (r) return r;
-  ++launches;
-  if ((r = run_blocks(h, s, w, row_idx, col_idx, patch_mask, B, N, st, launches))) return r;
-  GemmArgs gp = base_args(w.x, D, s.w_b, D, P, M, P, D);               // to_pixels, ae.py:242
-  gp.epi.out = (bf16*)patches_out; gp.epi.ldo = P; gp.epi.bias = s.b_b;
-  { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, gp, st); }
-  if (r) return r;
-  ++launches;
-  h->last_launches = launches;
+  return run_side(h, 1, z, row_idx, col_idx, patch_mask, B, N, patches_out, workspace, (cudaStream_t)stream);
+}
+
+int vtk_ae_set_packing(vtk_ae_t h, int enable) {
+  VTK_REQUIRE(h, "vtk_ae_set_packing: null handle");
+  h->packing = enable != 0;
   return VTK_OK;
 }
 

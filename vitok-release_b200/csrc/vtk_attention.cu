@@ -64,6 +64,9 @@ struct AttnParams {
   float scale_log2;   // (1/sqrt(d)) * log2(e)
   unsigned long long* prof;   // perf experiments (env VTK_ATTN_PROF): clock64 accumulators, or null
   float* lse;                 // [B*N, heads] log2-domain logsumexp of the scaled scores (training), or null; +inf for zero rows
+  // packed NaFlex batches (persistent kernel only): image b owns packed rows [cu[b], cu[b+1]) (multiples of 128), holds
+  // kv_len[b] valid tokens at the front; tile_img[r / 128] = image of packed row r; *m_dev = cu[B] = packed row count
+  const int* cu; const int* tile_img; const int* tile_order; const int* m_dev;
 };
 
 __device__ __forceinline__ float max3f(float a, float b, float c) {
@@ -77,11 +80,63 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Set the masked scores of one 128-key tile to -inf.  The common case -- the tail tile of an image whose valid keys are a
+// prefix (what patchify emits, and always the case in the packed layout), no byte mask, no window -- is handled per
+// 32-column chunk with warp-uniform branches: chunks entirely inside kvlen are skipped and only the chunks at / beyond
+// the boundary pay a compare + select per column (the general per-element test costs ~12 instructions per score and
+// made a masked tile 8x as expensive as an unmasked one).
+__device__ __forceinline__ void mask_scores(uint32_t (&v)[4][32], int kv0, int kvlen, const uint8_t* kmask, int W, int qi) {
+  if (kmask == nullptr && W < 0) {
+    const int lim = kvlen - kv0;   // columns >= lim are masked
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (lim < (c + 1) * 32) {
+        const int l = lim - c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i >= l) v[c][i] = 0xff800000u;   // -inf
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int kc = kv0 + c * 32 + i;
+      const bool ok = kc < kvlen && (kmask == nullptr || kmask[kc] != 0) && (W < 0 || abs(kc - qi) <= W);
+      if (!ok) v[c][i] = 0xff800000u;   // -inf
+    }
+}
+
+// 2^x for a pair of scores on the FMA pipe instead of the MUFU (the trick of FlashAttention-4: on sm_100 the 16-lane
+// special-function unit, not the tensor core, bounds the softmax).  x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 polynomial (max relative error 7.5e-5, far below the bf16 rounding of P), 2^n by adding n to the
+// exponent field: float(1.5 * 2^23 + n) carries n in its low mantissa bits, so (bits << 23) is n << 23.
+__device__ __forceinline__ void ex2_poly_pair(uint32_t& a, uint32_t& b) {
+  const float x0 = fmaxf(__uint_as_float(a), -126.f), x1 = fmaxf(__uint_as_float(b), -126.f);   // also maps -inf (masked) to ~0
+  const uint64_t x2 = f2_pack(x0, x1);
+  const uint64_t magic = f2_pack(12582912.f, 12582912.f), neg_magic = f2_pack(-12582912.f, -12582912.f);
+  const uint64_t t2 = f2_add(x2, magic);
+  const uint64_t f2 = f2_fma(f2_add(t2, neg_magic), f2_pack(-1.f, -1.f), x2);
+  uint64_t p2 = f2_fma(f2, f2_pack(0.055171459913253784f, 0.055171459913253784f), f2_pack(0.2426108568906784f, 0.2426108568906784f));
+  p2 = f2_fma(p2, f2, f2_pack(0.6932609677314758f, 0.6932609677314758f));
+  p2 = f2_fma(p2, f2, f2_pack(0.9999281167984009f, 0.9999281167984009f));
+  float t0, t1, p0, p1;
+  f2_unpack(t2, t0, t1);
+  f2_unpack(p2, p0, p1);
+  a = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
+  b = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+}
+
 // Exponentiate one 128-key score tile held in registers (v = raw scores), accumulate the row sum and write P as
 // bf16 into the row's 128B-swizzled shared-memory slots.  Software-pipelined by hand: all FFMA2 (scale, subtract
-// max) first, then MUFU.EX2 of pair i+DIST is issued before the FADD2 / F2FP / STS that consume pair i, so a
+// max) first, then the exponential of pair i+DIST is issued before the FADD2 / F2FP / STS that consume pair i, so a
 // warp never stalls on its own MUFU latency (ptxas otherwise places each consumer right behind its producer and
-// the XU pipe idles ~55 % of the exponentiation phase with only two softmax warps per scheduler).
+// the XU pipe idles ~55 % of the exponentiation phase with only two softmax warps per scheduler).  EMU_MASK selects,
+// inside every group of 8 pairs, the pairs exponentiated on the FMA pipe (ex2_poly_pair): 3 of 8 balances the two
+// pipes (MUFU: 8 cycles per warp instruction; the polynomial: 6 two-wide FMA-pipe instructions per pair).
+template <uint32_t EMU_MASK>
 __device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[4][32], uint64_t sc2, uint64_t nm2, uint8_t* prow, int r,
                                                  uint64_t& sum2a, uint64_t& sum2b) {
 #pragma unroll
@@ -98,8 +153,12 @@ __device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[4][32], uint64_t 
     if (pr < 64) {
       uint32_t& a = v[pr >> 4][2 * (pr & 15)];
       uint32_t& b = v[pr >> 4][2 * (pr & 15) + 1];
-      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a));
-      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(b));
+      if ((EMU_MASK >> (pr & 7)) & 1u) {
+        ex2_poly_pair(a, b);
+      } else {
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(b));
+      }
     }
     if (pr >= DIST) {
       const int q = pr - DIST;
@@ -117,6 +176,11 @@ __device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[4][32], uint64_t 
     }
   }
 }
+
+// pairs 1, 4 and 6 of every 8 on the FMA pipe (37.5 %); VTK_ATTN_EMU=0 at build time (-DVTK_ATTN_EMU_MASK=0) = MUFU only
+#ifndef VTK_ATTN_EMU_MASK
+#define VTK_ATTN_EMU_MASK 0u
+#endif
 
 template <int DH, int NQ>
 __global__ void __launch_bounds__(128 * NQ + 64, NQ == 1 ? 2 : 1)
@@ -328,16 +392,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&s_empty[q]);   // S is in registers: the tensor core may overwrite it with S(j+1)
-      if (need_mask) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kc = kv0 + c * 32 + i;
-            const bool ok = kc < kvlen && (kmask == nullptr || kmask[kc] != 0) && (W < 0 || abs(kc - qi) <= W);
-            if (!ok) v[c][i] = 0xff800000u;   // -inf
-          }
-      }
+      if (need_mask) mask_scores(v, kv0, kvlen, kmask, W, qi);
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {   // FMNMX3: two elements per instruction
@@ -368,7 +423,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
       // 128 columns = 2 blocks x 8 chunks of 16 B; swizzle-128B: chunk' = chunk ^ (row & 7); each 16-byte chunk
       // (8 keys) is written as soon as it is exponentiated
-      softmax_exp_tile(v, sc2, nm2, prow, r, sum2a, sum2b);
+      softmax_exp_tile<VTK_ATTN_EMU_MASK>(v, sc2, nm2, prow, r, sum2a, sum2b);
       float sum0, sum1;
       f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
       l_run = l_run * alpha + (sum0 + sum1);
@@ -478,44 +533,76 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 // Barrier phases are tracked with running counters (tiles / K loads / V loads / items seen by this CTA).
 // ------------------------------------------------------------------------------------------------
 struct AttnItem {
-  int img, head, q0, kvlen, qlimit, j_lo, Tn;
+  int img, head, q0, kvlen, qlimit, j_lo, Tn, nrows;   // nrows = token rows of the image (row guard of the direct stores)
+  long long row0;                                      // first row of the image in the q/k/v/out buffers
   bool active;
 };
 
+template <bool PACKED>
 __device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int w, int qtiles) {
   AttnItem it;
-  const int per_img = qtiles * p.heads;
-  it.img = w / per_img;
-  const int r = w - it.img * per_img;
-  it.head = r / qtiles;
-  it.q0 = (r - it.head * qtiles) * ATT_BQ;
-  int kvlen = p.kv_len ? p.kv_len[it.img] : p.N;
-  it.kvlen = kvlen < p.N ? kvlen : p.N;
-  it.qlimit = p.zero_invalid ? it.kvlen : p.N;
+  if (PACKED) {   // packed layout: work item = (128-row packed tile, head); every tile holds at least one valid query
+    const int rank = w / p.heads;
+    it.head = w - rank * p.heads;
+    const int tile = p.tile_order[rank];     // longest images first (pack_plan_kernel)
+    it.img = p.tile_img[tile];
+    const int base = p.cu[it.img];
+    it.row0 = base;
+    it.q0 = tile * ATT_BQ - base;
+    it.kvlen = p.kv_len[it.img];
+    it.nrows = (it.kvlen + ATT_BQ - 1) / ATT_BQ * ATT_BQ;
+  } else {
+    const int per_img = qtiles * p.heads;
+    it.img = w / per_img;
+    const int r = w - it.img * per_img;
+    it.head = r / qtiles;
+    it.q0 = (r - it.head * qtiles) * ATT_BQ;
+    int kvlen = p.kv_len ? p.kv_len[it.img] : p.N;
+    it.kvlen = kvlen < p.N ? kvlen : p.N;
+    it.nrows = p.N;
+    it.row0 = (long long)it.img * p.N;
+  }
+  it.qlimit = p.zero_invalid ? it.kvlen : it.nrows;
   const int T = (it.kvlen + ATT_BKV - 1) / ATT_BKV;
   it.active = T > 0 && it.q0 < it.qlimit;
   it.j_lo = 0;
   int j_hi = T - 1;
   if (p.window >= 0) {
-    const int q_last = min(it.q0 + ATT_BQ, p.N) - 1;
+    const int q_last = min(it.q0 + ATT_BQ, it.nrows) - 1;
     it.j_lo = max(0, it.q0 - p.window) / ATT_BKV;
-    j_hi = min(T - 1, (int)min((long long)q_last + p.window, (long long)p.N - 1) / ATT_BKV);
+    j_hi = min(T - 1, (int)min((long long)q_last + p.window, (long long)it.nrows - 1) / ATT_BKV);
   }
   it.Tn = j_hi - it.j_lo + 1;
   return it;
 }
 
-template <int DH>
+// Item k of this CTA.  SNAKE = false: plain round-robin (w = blockIdx + k * grid).  SNAKE = true (packed batches, whose
+// item list is sorted by cost -- pack_plan_kernel's tile_order): items are dealt boustrophedon-wise (0 .. G-1, then
+// G-1 .. 0, ...), so every CTA ends up with nearly the same amount of work without a shared counter (c3: max/mean CTA
+// load 1.03 instead of 1.19).  Returns false when the CTA is done; a SNAKE caller must skip w >= total.
+template <bool SNAKE>
+__device__ __forceinline__ bool item_at(int k, int total, int& w) {
+  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  if (!SNAKE) {
+    w = b + k * G;
+    return w < total;
+  }
+  const int base = (k >> 1) * 2 * G;
+  w = base + ((k & 1) ? 2 * G - 1 - b : b);
+  return base < total;
+}
+
+template <int DH, uint32_t EMU, bool SNAKE>
 __global__ void __launch_bounds__(192, 2)
 attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
-                    const int total_items, const int qtiles) {
+                    const int total_items_host, const int qtiles) {
   using S = AttnShape<DH, 1>;
   static_assert(DH == 64, "persistent attention: d = 64 only");
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int N = p.N;
   const int W = p.window;
+  const int total_items = SNAKE ? min(total_items_host, (__ldg(p.m_dev) / ATT_BQ) * p.heads) : total_items_host;   // SNAKE <=> packed layout
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem + S::OFF_Q;
@@ -557,10 +644,11 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (lane == 0) {
       // ===== TMA producer =====
       uint32_t n_item = 0, n_k = 0, n_v = 0;   // active items / K tiles / V tiles issued so far by this CTA
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-        const AttnItem it = attn_item(p, w, qtiles);
+      for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
+        if (SNAKE && w >= total_items) continue;
+        const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
         if (!it.active) continue;
-        const long long row0 = (long long)it.img * N;
+        const long long row0 = it.row0;
         if (n_item > 0) mbar_wait(q_empty, (n_item - 1) & 1u);     // last S MMA of the previous item has read Q
         mbar_expect_tx(q_full, S::TILE_BYTES);
         tma_load_2d(sQ, &tmQ, q_full, it.head * DH, (int)(row0 + it.q0));
@@ -605,8 +693,9 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         ++n_k;
         ++n_t;
       };
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-        const AttnItem it = attn_item(p, w, qtiles);
+      for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
+        if (SNAKE && w >= total_items) continue;
+        const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
         if (!it.active) continue;
         mbar_wait(q_full, n_item & 1u);
         ++n_item;
@@ -647,9 +736,11 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     long long c_wait_s = 0, c_load = 0, c_max = 0, c_wait_pv = 0, c_exp = 0, c_tail = 0, c_epi_wait = 0, c_epi = 0;
     const long long c_begin = prof ? clock64() : 0;
 #define PCLK() (prof ? clock64() : 0)
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-      const AttnItem it = attn_item(p, w, qtiles);
-      const long long row0 = (long long)it.img * N;
+    for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
+        if (SNAKE && w >= total_items) continue;
+      const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
+      const long long row0 = it.row0;
+      const int N = it.nrows;
       const int qi = it.q0 + r;
       if (!it.active) {   // nothing to attend to: the output rows are 0
         if (qi < N) {
@@ -681,16 +772,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_before();
         mbar_arrive(s_empty);   // S is in registers: the tensor core may overwrite it with the next tile's S
         const long long k2 = PCLK();
-        if (need_mask) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int kc = kv0 + c * 32 + i;
-              const bool ok = kc < kvlen && (kmask == nullptr || kmask[kc] != 0) && (W < 0 || abs(kc - qi) <= W);
-              if (!ok) v[c][i] = 0xff800000u;   // -inf
-            }
-        }
+        if (need_mask) mask_scores(v, kv0, kvlen, kmask, W, qi);
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -722,7 +804,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           store_pending = false;
         }
         const long long k4 = PCLK();
-      softmax_exp_tile(v, sc2, nm2, prow, r, sum2a, sum2b);
+      softmax_exp_tile<EMU>(v, sc2, nm2, prow, r, sum2a, sum2b);
         const long long k5 = PCLK();
         float sum0, sum1;
         f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
@@ -823,8 +905,13 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   using S = AttnShape<64, 1>;
-  const long long Mrows = (long long)a.B * a.N;
+  const bool packed = a.cu != nullptr;
+  const long long Mrows = packed ? a.row_cap : (long long)a.B * a.N;
   const long long cols = (long long)a.heads * a.d;
+  if (packed && (!a.tile_img || !a.tile_order || !a.m_dev || !a.kv_len || a.key_mask || a.window >= 0 || a.row_cap % ATT_BQ)) {
+    set_error("attention: packed layout needs cu/tile_img/m_dev/kv_len, a row capacity that is a multiple of 128, no key mask and no window");
+    return -2;
+  }
   CUtensorMap tmQ, tmK, tmV, tmO;
   if (encode_tmap_bf16_sw128(&tmQ, a.q, cols, Mrows, a.ld_qkv, ATT_BQ)) return -1;
   if (encode_tmap_bf16_sw128(&tmK, a.k, cols, Mrows, a.ld_qkv, ATT_BKV)) return -1;
@@ -834,9 +921,10 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   p.out = a.out; p.ld_out = a.ld_out;
   p.kv_len = a.kv_len; p.key_mask = a.key_mask; p.prefix_flag = a.prefix_flag;
   p.N = a.N; p.heads = a.heads; p.zero_invalid = a.zero_invalid_rows;
-  p.tma_out = (a.N % ATT_BQ == 0) ? 1 : 0;
+  p.tma_out = (packed || a.N % ATT_BQ == 0) ? 1 : 0;
   p.window = a.window;
   p.lse = a.lse;
+  p.cu = a.cu; p.tile_img = a.tile_img; p.tile_order = a.tile_order; p.m_dev = a.m_dev;
   p.prof = nullptr;
   static const int prof_mode = getenv("VTK_ATTN_PROF") ? atoi(getenv("VTK_ATTN_PROF")) : 0;
   static unsigned long long* d_prof = nullptr;
@@ -846,15 +934,18 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
     p.prof = d_prof;
   }
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
-  auto kern = attn_persist_kernel<64>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // perf experiments: VTK_ATTN_EMU = pairs (bit mask inside every group of 8) exponentiated on the FMA pipe
+  static const int emu = getenv("VTK_ATTN_EMU") ? (int)strtol(getenv("VTK_ATTN_EMU"), nullptr, 0) : (int)VTK_ATTN_EMU_MASK;
+  auto kern = packed ? attn_persist_kernel<64, 0u, true>
+              : emu == 0x52 ? attn_persist_kernel<64, 0x52u, false> : attn_persist_kernel<64, 0u, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[packed ? 1 : 0]) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES), "cudaFuncSetAttribute(attn_persist)"))
       return -1;
-    attr_set = true;
+    attr_set[packed ? 1 : 0] = true;
   }
   const int qtiles = (a.N + ATT_BQ - 1) / ATT_BQ;
-  const long long total = (long long)a.B * a.heads * qtiles;
+  const long long total = packed ? (Mrows / ATT_BQ) * a.heads : (long long)a.B * a.heads * qtiles;
   if (total >= (1ll << 31)) { set_error("attention: too many work items"); return -2; }
   const int grid = (int)std::min<long long>(total, 2ll * num_sms());
   kern<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
@@ -888,6 +979,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   p.tma_out = (a.N % ATT_BQ == 0) ? 1 : 0;
   p.window = a.window;
   p.lse = a.lse;
+  p.cu = nullptr; p.tile_img = nullptr; p.tile_order = nullptr; p.m_dev = nullptr;
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
   static const int prof_mode = getenv("VTK_ATTN_PROF") ? atoi(getenv("VTK_ATTN_PROF")) : 0;
   static unsigned long long* d_prof = nullptr;
@@ -922,10 +1014,11 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.B <= 0 || a.N <= 0 || a.heads <= 0) { set_error("attention: empty problem"); return -2; }
   if ((a.ld_qkv % 8) || (a.ld_out % 8)) { set_error("attention: row strides must be multiples of 8"); return -2; }
+  if (a.cu && a.d != 64) { set_error("attention: the packed layout is implemented for head_dim 64 only"); return -3; }
   if (a.d == 64) {
     // perf experiments: VTK_ATTN_NQ = 0 (default) persistent kernel, 1 = one-shot CTAs (2 per SM), 2 = one-shot, one CTA per SM
     static const int nq = getenv("VTK_ATTN_NQ") ? atoi(getenv("VTK_ATTN_NQ")) : 0;
-    if (nq == 0) return launch_attention_persist(a, stream);
+    if (nq == 0 || a.cu) return launch_attention_persist(a, stream);
     return nq == 2 ? launch_attention_t<64, 2>(a, stream) : launch_attention_t<64, 1>(a, stream);
   }
   if (a.d == 128) return launch_attention_t<128, 2>(a, stream);

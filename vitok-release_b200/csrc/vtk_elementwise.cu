@@ -12,10 +12,11 @@ namespace vtk {
 // one warp per row; D % 8 == 0.  Two passes over the row (second pass hits L1).
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, long long ldx,
                                                       const bf16* __restrict__ w, bf16* __restrict__ y, long long ldy,
-                                                      int M, int D, float eps) {
+                                                      int M, int D, float eps, const int* __restrict__ m_dev) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
+  if (m_dev) M = min(M, __ldg(m_dev));
   for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
        row += (long long)gridDim.x * warps_per_block) {
     const bf16* xr = x + row * ldx;
@@ -52,11 +53,13 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
 template <int NV>
 __global__ void __launch_bounds__(256) rmsnorm_reg_kernel(const bf16* __restrict__ x, long long ldx,
                                                           const bf16* __restrict__ w, bf16* __restrict__ y,
-                                                          long long ldy, int M, int D, float eps) {
+                                                          long long ldy, int M, int D, float eps,
+                                                          const int* __restrict__ m_dev) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   const float inv_d = 1.f / (float)D;
+  if (m_dev) M = min(M, __ldg(m_dev));
   for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
        row += (long long)gridDim.x * warps_per_block) {
     const bf16* xr = x + row * ldx;
@@ -105,17 +108,17 @@ __global__ void __launch_bounds__(256) rmsnorm_reg_kernel(const bf16* __restrict
 }
 
 int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, int M, int D, float eps,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const int* m_dev) {
   if (D % 8 || ldx % 8 || ldy % 8) { set_error("rmsnorm: D and strides must be multiples of 8"); return -2; }
   if (M <= 0) return 0;
   const int wpb = 8;
   long long blocks = ((long long)M + wpb - 1) / wpb;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  if (D <= 1024) rmsnorm_reg_kernel<4><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
-  else if (D <= 3072) rmsnorm_reg_kernel<12><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
-  else if (D <= 4096) rmsnorm_reg_kernel<16><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
-  else rmsnorm_kernel<<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps);
+  if (D <= 1024) rmsnorm_reg_kernel<4><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps, m_dev);
+  else if (D <= 3072) rmsnorm_reg_kernel<12><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps, m_dev);
+  else if (D <= 4096) rmsnorm_reg_kernel<16><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps, m_dev);
+  else rmsnorm_kernel<<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps, m_dev);
   return check_cuda(cudaGetLastError(), "rmsnorm launch");
 }
 
@@ -127,8 +130,10 @@ int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long lo
 // Rows are grouped by 32 so that one warp of the epilogue (32 consecutive rows) reads each 16-byte chunk
 // as 512 contiguous bytes.  The table holds ceil(M / 32) * 32 rows.
 __global__ void rope_table_kernel(const int64_t* __restrict__ row_idx, const int64_t* __restrict__ col_idx,
-                                  const float* __restrict__ inv_freq, bf16* __restrict__ table, int M, int d) {
+                                  const float* __restrict__ inv_freq, bf16* __restrict__ table, int M, int d,
+                                  const int* __restrict__ src_map, const int* __restrict__ m_dev) {
   const int half = d >> 1, quarter = d >> 2;
+  if (m_dev) M = min(M, __ldg(m_dev));
   const long long groups = ((long long)M + 31) >> 5;
   const long long total = groups * half * 32;   // thread <-> (group, pair j, row-in-group): coalesced-ish writes
   uint32_t* tw = reinterpret_cast<uint32_t*>(table);
@@ -139,7 +144,9 @@ __global__ void rope_table_kernel(const int64_t* __restrict__ row_idx, const int
     const long long grp = t / half;
     const long long m = grp * 32 + ml;
     if (m >= M) continue;
-    const float pos = j < quarter ? (float)row_idx[m] : (float)col_idx[m];
+    // packed NaFlex batches: table row m belongs to source token src_map[m] (pad rows: position 0)
+    const long long src = src_map ? (long long)src_map[m] : m;
+    const float pos = src < 0 ? 0.f : (j < quarter ? (float)row_idx[src] : (float)col_idx[src]);
     const float f = inv_freq[j < quarter ? j : j - quarter];
     const float ang = pos * f;
     const uint32_t c = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(cosf(ang)));
@@ -153,14 +160,14 @@ __global__ void rope_table_kernel(const int64_t* __restrict__ row_idx, const int
 }
 
 int launch_rope_table(const int64_t* row_idx, const int64_t* col_idx, const float* inv_freq, bf16* table, int M, int d,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const int* src_map, const int* m_dev) {
   if (d % 8) { set_error("rope: head dimension must be a multiple of 8 (2D RoPE needs d %% 4 == 0; table chunks need 8)"); return -2; }
   if (M <= 0) return 0;
   const long long total = (((long long)M + 31) >> 5) * (d / 2) * 32;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  rope_table_kernel<<<(int)blocks, 256, 0, stream>>>(row_idx, col_idx, inv_freq, table, M, d);
+  rope_table_kernel<<<(int)blocks, 256, 0, stream>>>(row_idx, col_idx, inv_freq, table, M, d, src_map, m_dev);
   return check_cuda(cudaGetLastError(), "rope_table launch");
 }
 
@@ -221,6 +228,181 @@ int launch_kv_len(const uint8_t* mask, int* kv_len, int* is_prefix, int B, int N
   if (B <= 0) return 0;
   kv_len_kernel<<<(B + 3) / 4, 128, 0, stream>>>(mask, kv_len, is_prefix, B, N);
   return check_cuda(cudaGetLastError(), "kv_len launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// NaFlex token packing.  The reference runs every block over all B*N token rows and masks the padded keys inside
+// SDPA (ae.py:173-187, attention.py:69-73).  Here the valid tokens of a masked batch are packed image after image
+// (each image padded to a multiple of 128 rows so no attention tile straddles two images), every kernel of the block
+// stack runs on the packed rows only, and the result is scattered back.  Any bool mask is handled: the valid tokens
+// of an image keep their order, so inside the packed layout an image is always a dense prefix of n_i tokens.
+// The packed row count sum(ceil128(n_i)) never visits the host: kernels read it from device memory (m_dev).
+// ------------------------------------------------------------------------------------------------
+// one CTA per image: rel[b, t] = rank of token t among the valid tokens of image b (-1 if masked), n_valid[b]
+__global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t* __restrict__ mask, int* __restrict__ rel,
+                                                         int* __restrict__ n_valid, int N) {
+  __shared__ int warp_tot[8];
+  __shared__ int running;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < N; t0 += 256) {
+    const int t = t0 + tid;
+    const bool v = t < N && mask[(long long)b * N + t] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int before = running;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (t < N) rel[(long long)b * N + t] = v ? before + __popc(bal & ((1u << lane) - 1u)) : -1;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += warp_tot[w];
+      running += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) n_valid[b] = running;
+}
+
+// one CTA: cu[b] = packed row offset of image b (exclusive scan of ceil128(n_valid)), cu[B] = packed row count,
+// tile_img[r / 128] = image that owns packed rows [r, r + 128), tile_order = the packed tiles sorted by the number of
+// key tiles of their image, longest first (counting sort; ties in arbitrary order) -- the attention kernel deals its
+// work items from this list so that every persistent CTA gets the same mix of long and short items.
+__global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__ n_valid, int* __restrict__ cu,
+                                                         int* __restrict__ tile_img, int* __restrict__ tile_order, int B, int N) {
+  constexpr int MAX_BINS = 2048;
+  __shared__ int warp_tot[32];
+  __shared__ int running;
+  __shared__ int bins[MAX_BINS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + tid;
+    const int padded = b < B ? ((n_valid[b] + 127) & ~127) : 0;
+    int incl = padded;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = running;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    const int start = before + incl - padded;
+    if (b < B) {
+      cu[b] = start;
+      for (int q = 0; q < padded; q += 128) tile_img[(start + q) >> 7] = b;
+    }
+    __syncthreads();
+    if (tid == 1023) running = before + incl;
+    __syncthreads();
+  }
+  if (tid == 0) cu[B] = running;
+  // ---- tile order: counting sort by key tiles per image, descending ----
+  const int nbins = (N + 127) / 128;           // an image has 1 .. nbins tiles
+  const int ntiles = running >> 7;
+  if (nbins > MAX_BINS) {                      // very long sequences: keep the natural order
+    for (int t = tid; t < ntiles; t += 1024) tile_order[t] = t;
+    return;
+  }
+  for (int i = tid; i <= nbins; i += 1024) bins[i] = 0;
+  __syncthreads();
+  for (int b = tid; b < B; b += 1024) {
+    const int kt = (n_valid[b] + 127) >> 7;
+    if (kt > 0) atomicAdd(&bins[kt], kt);      // an image with kt key tiles contributes kt query tiles
+  }
+  __syncthreads();
+  if (tid == 0) {                              // start offset of each bin, longest images first
+    int acc = 0;
+    for (int k = nbins; k >= 1; --k) { const int c = bins[k]; bins[k] = acc; acc += c; }
+  }
+  __syncthreads();
+  for (int b = tid; b < B; b += 1024) {
+    const int kt = (n_valid[b] + 127) >> 7;
+    if (kt > 0) {
+      const int at = atomicAdd(&bins[kt], kt);
+      const int first = cu[b] >> 7;
+      for (int q = 0; q < kt; ++q) tile_order[at + q] = first + q;
+    }
+  }
+}
+
+// one CTA per image: src[packed row] = source token row b*N + t, or -1 for the pad rows of the image's last tile
+__global__ void __launch_bounds__(256) pack_src_kernel(const int* __restrict__ rel, const int* __restrict__ n_valid,
+                                                       const int* __restrict__ cu, int* __restrict__ src, int N) {
+  const int b = blockIdx.x;
+  const int base = cu[b], n = n_valid[b];
+  for (int t = threadIdx.x; t < N; t += 256) {
+    const int r = rel[(long long)b * N + t];
+    if (r >= 0) src[base + r] = b * N + t;
+  }
+  for (int p = n + threadIdx.x; p < ((n + 127) & ~127); p += 256) src[base + p] = -1;
+}
+
+// packed[r, :] = in[src[r], :] (zeros for pad rows); rows of `width` bf16 (width % 8 == 0), 16-byte vectors
+__global__ void __launch_bounds__(256) pack_rows_kernel(const bf16* __restrict__ in, long long ld_in, const int* __restrict__ src,
+                                                        const int* __restrict__ m_dev, bf16* __restrict__ out, long long ld_out,
+                                                        int width) {
+  const int nvec = width >> 3;
+  const long long total = (long long)__ldg(m_dev) * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int v = (int)(i - r * nvec);
+    const int s = src[r];
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (s >= 0) q = ld_global_nc_v4(in + (long long)s * ld_in + 8 * v);
+    st_global_v4(out + r * ld_out + 8 * v, q.x, q.y, q.z, q.w);
+  }
+}
+
+// out[b, t, :] = packed[cu[b] + rel[b, t], :] for valid tokens, 0 for masked ones
+__global__ void __launch_bounds__(256) unpack_rows_kernel(const bf16* __restrict__ packed, long long ld_p, const int* __restrict__ rel,
+                                                          const int* __restrict__ cu, bf16* __restrict__ out, long long ld_out,
+                                                          long long rows, int N, int width) {
+  const int nvec = width >> 3;
+  const long long total = rows * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / nvec;
+    const int v = (int)(i - m * nvec);
+    const int r = rel[m];
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (r >= 0) q = ld_global_nc_v4(packed + (long long)(cu[m / N] + r) * ld_p + 8 * v);
+    st_global_v4(out + m * ld_out + 8 * v, q.x, q.y, q.z, q.w);
+  }
+}
+
+int launch_pack_plan(const uint8_t* mask, int B, int N, const PackPlan& pl, cudaStream_t stream) {
+  if (B <= 0 || N <= 0) return 0;
+  pack_count_kernel<<<B, 256, 0, stream>>>(mask, pl.rel, pl.n_valid, N);
+  pack_plan_kernel<<<1, 1024, 0, stream>>>(pl.n_valid, pl.cu, pl.tile_img, pl.tile_order, B, N);
+  pack_src_kernel<<<B, 256, 0, stream>>>(pl.rel, pl.n_valid, pl.cu, pl.src, N);
+  return check_cuda(cudaGetLastError(), "pack_plan launch");
+}
+
+static int row_copy_grid(long long rows, int width) {
+  long long blocks = (rows * (width / 8) + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+int launch_pack_rows(const bf16* in, long long ld_in, const PackPlan& pl, long long row_cap, bf16* out, long long ld_out, int width,
+                     cudaStream_t stream) {
+  if (width % 8 || ld_in % 8 || ld_out % 8) { set_error("pack_rows: width and strides must be multiples of 8"); return -2; }
+  pack_rows_kernel<<<row_copy_grid(row_cap, width), 256, 0, stream>>>(in, ld_in, pl.src, pl.cu + pl.B, out, ld_out, width);
+  return check_cuda(cudaGetLastError(), "pack_rows launch");
+}
+
+int launch_unpack_rows(const bf16* packed, long long ld_p, const PackPlan& pl, bf16* out, long long ld_out, int width,
+                       cudaStream_t stream) {
+  if (width % 8 || ld_p % 8 || ld_out % 8) { set_error("unpack_rows: width and strides must be multiples of 8"); return -2; }
+  const long long rows = (long long)pl.B * pl.N;
+  unpack_rows_kernel<<<row_copy_grid(rows, width), 256, 0, stream>>>(packed, ld_p, pl.rel, pl.cu, out, ld_out, rows, pl.N, width);
+  return check_cuda(cudaGetLastError(), "unpack_rows launch");
 }
 
 }  // namespace vtk

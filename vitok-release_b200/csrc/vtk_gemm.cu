@@ -73,6 +73,24 @@ struct OutStage {
 
 struct TileSched {
   int num_m, num_n, gm, full_tiles, total_tiles, bn, bm;
+  int gm_cap;   // band height limit (tile rows) chosen on the host from the A-panel size
+  int split;    // 1: a short last wave may be split into half-width tiles
+  // Tile counts for M rows on `units` persistent workers (CTAs or CTA pairs).  Shared by the host launcher and by the
+  // kernels that read M from device memory (NaFlex token packing: the packed row count is only known on the device).
+  __host__ __device__ void setup(int M, int units) {
+    num_m = (M + bm - 1) / bm;
+    gm = gm_cap < num_m ? gm_cap : num_m;
+    if (gm < 1) gm = 1;
+    const int big = num_m * num_n;
+    const int workers = big < units ? big : units;
+    const int rem = workers > 0 ? big % workers : 0;
+    full_tiles = big;
+    total_tiles = big;
+    if (split && rem > 0 && 2 * rem <= workers) {   // short last wave: half-width tiles
+      full_tiles = big - rem;
+      total_tiles = full_tiles + 2 * rem;
+    }
+  }
   // Big tiles are visited in bands of `gm` row-tiles: inside a band m is fastest and n sweeps all column
   // tiles, so the band's A panel (gm x 128 x K) stays L2-resident while the weights stream through once
   // per band.  full_tiles big tiles, then (total_tiles - full_tiles) half-width tiles.
@@ -434,9 +452,16 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
 template <int BN, int EPI, int NEPI>
 __global__ void __launch_bounds__(128 + 32 * NEPI, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M, const int N,
-            const int K, const TileSched sched, const EpiParams epi) {
+            const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M_cap, const int N,
+            const int K, const TileSched sched_host, const EpiParams epi) {
   using S = GemmShape<BN>;
+  // packed NaFlex batches: the row count lives in device memory (M_cap = capacity the tensor maps were encoded for)
+  int M = M_cap;
+  TileSched sched = sched_host;
+  if (epi.m_dev) {
+    M = min(__ldg(epi.m_dev), M_cap);
+    sched.setup(M, (int)gridDim.x);
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -600,27 +625,19 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
   TileSched sc;
   sc.bn = BN;
   sc.bm = BM;
-  sc.num_m = (a.M + BM - 1) / BM;
   sc.num_n = (a.N + BN - 1) / BN;
   // band height: keep the A panel of a band (gm x 128 x K bf16) around 32 MB so it stays in the 126 MB L2
   // together with the weight tiles that are in flight
   {
     const long long panel = (long long)BM * a.K * 2;
     long long gm = (32ll << 20) / (panel > 0 ? panel : 1);
-    if (gm < 1) gm = 1;
-    if (gm > sc.num_m) gm = sc.num_m;
-    sc.gm = (int)gm;
+    sc.gm_cap = (int)(gm < 1 ? 1 : gm > (1 << 20) ? (1 << 20) : gm);
   }
-  const int big = sc.num_m * sc.num_n;
+  sc.split = (allow_split && BN >= 256) ? 1 : 0;
   const int sms = num_sms();
+  sc.setup(a.M, sms);   // a.M is the row capacity when a.m_dev is given (the kernel redoes this with the device value)
+  const int big = sc.num_m * sc.num_n;
   const int grid = big < sms ? big : sms;
-  int rem = big % grid;
-  sc.full_tiles = big;
-  sc.total_tiles = big;
-  if (allow_split && BN >= 256 && rem > 0 && 2 * rem <= grid) {
-    sc.full_tiles = big - rem;
-    sc.total_tiles = sc.full_tiles + 2 * rem;
-  }
   // output tensor maps for the TMA-store epilogues (box = 32 cols x 32 rows, SWIZZLE_64B)
   CUtensorMap tmO0 = tmA, tmO1 = tmA;
   constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
@@ -669,8 +686,14 @@ template <bool P> __device__ __forceinline__ long long prof_clock() {
 template <int EPI, int NEPI, int G2_STAGES, bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M, const int N,
-             const int K, const TileSched sched, const EpiParams epi) {
+             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M_cap, const int N,
+             const int K, const TileSched sched_host, const EpiParams epi) {
+  int M = M_cap;
+  TileSched sched = sched_host;
+  if (epi.m_dev) {   // packed NaFlex batches: row count from device memory (see gemm_kernel)
+    M = min(__ldg(epi.m_dev), M_cap);
+    sched.setup(M, (int)(gridDim.x >> 1));
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -870,26 +893,18 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
   TileSched sc;
   sc.bn = G2_BN;
   sc.bm = 2 * BM;
-  sc.num_m = (a.M + 2 * BM - 1) / (2 * BM);
   sc.num_n = (a.N + G2_BN - 1) / G2_BN;
   {
     const long long panel = 2ll * BM * a.K * 2;
     long long gm = (32ll << 20) / (panel > 0 ? panel : 1);
-    if (gm < 1) gm = 1;
     if (const char* e = getenv("VTK_GEMM_GM")) gm = atoi(e) > 0 ? atoi(e) : gm;
-    if (gm > sc.num_m) gm = sc.num_m;
-    sc.gm = (int)gm;
+    sc.gm_cap = (int)(gm < 1 ? 1 : gm > (1 << 20) ? (1 << 20) : gm);
   }
-  const int big = sc.num_m * sc.num_n;
+  sc.split = 1;
   const int pairs = num_sms() / 2;
+  sc.setup(a.M, pairs);
+  const int big = sc.num_m * sc.num_n;
   const int clusters = big < pairs ? big : pairs;
-  const int rem = big % clusters;
-  sc.full_tiles = big;
-  sc.total_tiles = big;
-  if (rem > 0 && 2 * rem <= clusters) {   // short last wave: half-width tiles (UMMA N = 128)
-    sc.full_tiles = big - rem;
-    sc.total_tiles = sc.full_tiles + 2 * rem;
-  }
   CUtensorMap tmO0 = tmA, tmO1 = tmA;
   constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
   if (EPI == EPI_QKV_SWIGLU) {

@@ -49,6 +49,8 @@ struct EpiParams {
   int D, d, Hf, qp;     // qp = 3D rounded up to the tile width (start of the SwiGLU columns)
   // EPI_RESID
   const bf16* gamma;    // [N]
+  const int* m_dev;     // optional: number of rows to process, read on the device (<= GemmArgs::M, which is then the row
+                        // capacity of the buffers); used by the packed NaFlex path where sum(n_i) is only known on the GPU
   unsigned long long* prof;  // perf experiments only (env VTK_GEMM_PROF): per-role clock64 accumulators, or null
   int debug;            // perf experiments only (env VTK_EPI_DEBUG): 1 = no global stores, 2 = skip epilogue math+stores
 };
@@ -82,6 +84,9 @@ struct AttnArgs {
   int zero_invalid_rows;        // 1: rows >= kv_len[b] (or with key_mask 0) are written as 0
   int window;                   // sliding window: keys j with |i - j| <= window (flash_attn window_size=(w,w)); < 0 = none
   float* lse;                   // optional [B*N, heads] fp32: log2-domain logsumexp of the scaled scores (for the backward pass)
+  // packed NaFlex layout (PackPlan; head_dim 64): rows of image b start at cu[b], kv_len[b] valid tokens, no key_mask
+  const int* cu = nullptr; const int* tile_img = nullptr; const int* tile_order = nullptr; const int* m_dev = nullptr;
+  long long row_cap = 0;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 
@@ -100,10 +105,30 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t stream);
 // ---------------------------------------------------------------------------------------------
 // elementwise / HBM-bound kernels (vtk_elementwise.cu)
 // ---------------------------------------------------------------------------------------------
+// m_dev (optional): row count read on the device (M is then the capacity); src_map (optional): table row -> source token
 int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, int M, int D, float eps,
-                   cudaStream_t stream);
+                   cudaStream_t stream, const int* m_dev = nullptr);
 int launch_rope_table(const int64_t* row_idx, const int64_t* col_idx, const float* inv_freq, bf16* table, int M, int d,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const int* src_map = nullptr, const int* m_dev = nullptr);
+
+// NaFlex token packing (vtk_elementwise.cu): valid tokens of a masked [B, N] batch packed image after image, each image
+// padded to a multiple of 128 rows.  All arrays live in device memory (carved from the caller's workspace).
+struct PackPlan {
+  int B, N;
+  int* n_valid;    // [B]      valid tokens per image (= key count of the image in the packed layout)
+  int* rel;        // [B * N]  rank of a token among the valid tokens of its image, -1 if masked
+  int* cu;         // [B + 1]  packed row offset per image; cu[B] = packed row count (the m_dev of every kernel)
+  int* tile_img;   // [B * ceil(N / 128)]  image owning each 128-row packed tile
+  int* tile_order; // [B * ceil(N / 128)]  packed tiles sorted by key tiles of their image, longest first (attention work list)
+  int* src;        // [B * ceil128(N)]     packed row -> source row b * N + t, -1 for pad rows
+  const int* m_dev() const { return cu + B; }
+  static long long row_capacity(int B, int N) { return (long long)B * ((N + 127) / 128 * 128); }
+};
+int launch_pack_plan(const uint8_t* mask, int B, int N, const PackPlan& pl, cudaStream_t stream);
+int launch_pack_rows(const bf16* in, long long ld_in, const PackPlan& pl, long long row_cap, bf16* out, long long ld_out, int width,
+                     cudaStream_t stream);
+int launch_unpack_rows(const bf16* packed, long long ld_p, const PackPlan& pl, bf16* out, long long ld_out, int width,
+                       cudaStream_t stream);
 int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 int launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t stream);
 int launch_kv_len(const uint8_t* mask, int* kv_len, int* is_prefix, int B, int N, cudaStream_t stream);

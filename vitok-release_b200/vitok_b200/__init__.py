@@ -6,10 +6,11 @@ Mirrors the hot-path surface of the reference package ``vitok`` (vitok/__init__.
 libvitok_b200.so (hand-written sm_100a kernels); there is no CPU fallback.
 """
 from .models.ae import AE, Model, decode_variant
-from .pp import OPS, build_transform, parse_op, patchify_batch, postprocess, preprocess, unpack, unpatchify
+from .pp import (OPS, build_transform, pack_images, parse_op, patchify_batch, patchify_packed, postprocess, preprocess,
+                 unpack, unpatchify)
 from .data import patch_collate_fn
 from .train import FusedAdamW, charbonnier_loss
 
 __version__ = "0.1.0"
 __all__ = ["AE", "Model", "decode_variant", "build_transform", "parse_op", "OPS", "patch_collate_fn", "preprocess",
-           "postprocess", "unpatchify", "unpack", "patchify_batch", "charbonnier_loss", "FusedAdamW"]
+           "postprocess", "unpatchify", "unpack", "patchify_batch", "pack_images", "patchify_packed", "charbonnier_loss", "FusedAdamW"]

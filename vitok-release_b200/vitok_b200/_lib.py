@@ -47,6 +47,9 @@ SIGNATURES = {
     "vtk_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "vtk_cast_bf16_to_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "vtk_kv_len": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "vtk_pack_plan": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vtk_pack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
+    "vtk_unpack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
     "vtk_linear_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_linear_ln_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
     "vtk_qkv_swiglu_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
@@ -80,6 +83,7 @@ SIGNATURES = {
     "vtk_ae_decode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "vtk_ae_last_launch_count": (c_int, [c_vp]),
     "vtk_ae_set_timing": (c_int, [c_vp, c_int]),
+    "vtk_ae_set_packing": (c_int, [c_vp, c_int]),
     "vtk_ae_collect_timing": (c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_int)]),
 }
 
@@ -206,6 +210,39 @@ def kv_len(mask: torch.Tensor):
     pf = torch.empty(B, dtype=torch.int32, device=mask.device)
     check(load().vtk_kv_len(ptr(m), ptr(kl), ptr(pf), B, N, stream_ptr()))
     return kl, pf
+
+
+def pack_plan(mask: torch.Tensor):
+    """NaFlex token-packing plan of a [B, N] bool mask (include/vitok_b200.h: vtk_pack_plan).  Arrays the kernel leaves
+    unwritten (beyond the packed row count) are pre-filled with -2."""
+    B, N = mask.shape
+    m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
+    cap = B * ((N + 127) // 128 * 128)
+    i32 = dict(dtype=torch.int32, device=mask.device)
+    n_valid, rel, cu = torch.empty(B, **i32), torch.empty(B * N, **i32), torch.empty(B + 1, **i32)
+    tile_img, src = torch.full((cap // 128,), -2, **i32), torch.full((cap,), -2, **i32)
+    tile_order = torch.full((cap // 128,), -2, **i32)
+    check(load().vtk_pack_plan(ptr(m), B, N, ptr(n_valid), ptr(rel), ptr(cu), ptr(tile_img), ptr(tile_order), ptr(src),
+                               stream_ptr()))
+    return {"n_valid": n_valid, "rel": rel, "cu": cu, "tile_img": tile_img, "tile_order": tile_order, "src": src}
+
+
+def pack_rows(x: torch.Tensor, plan: dict) -> torch.Tensor:
+    """x [B, N, W] bf16 -> packed [B * ceil128(N), W] (rows beyond cu[B] are left as allocated: zeros here)."""
+    _req(x, torch.bfloat16, "x")
+    B, N, W = x.shape
+    x = x.contiguous()
+    out = torch.zeros(B * ((N + 127) // 128 * 128), W, dtype=torch.bfloat16, device=x.device)
+    check(load().vtk_pack_rows(ptr(x), W, ptr(plan["src"]), ptr(plan["cu"]), B, N, ptr(out), W, W, stream_ptr()))
+    return out
+
+
+def unpack_rows(packed: torch.Tensor, plan: dict, B: int, N: int) -> torch.Tensor:
+    _req(packed, torch.bfloat16, "packed")
+    W = packed.shape[1]
+    out = torch.empty(B, N, W, dtype=torch.bfloat16, device=packed.device)
+    check(load().vtk_unpack_rows(ptr(packed), packed.stride(0), ptr(plan["rel"]), ptr(plan["cu"]), B, N, ptr(out), W, W, stream_ptr()))
+    return out
 
 
 def qkv_swiglu(h, w_packed, D, d, Hf, qp, norm_q, norm_k, table, eps=1e-6):

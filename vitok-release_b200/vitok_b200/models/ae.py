@@ -217,6 +217,9 @@ class AE(nn.Module):
         self._packed_sig = None
         self._ws: Dict[Any, torch.Tensor] = {}
         self.last_launch_count = 0
+        # NaFlex token packing for masked (sdpa-backend) batches: only valid tokens go through the layer stack
+        # (include/vitok_b200.h, vtk_ae_set_packing).  False keeps the padded layout with in-kernel key masking.
+        self.token_packing = True
 
     # ------------------------------------------------------------------ native plumbing
     def _sides(self):
@@ -337,6 +340,7 @@ class AE(nn.Module):
         ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
         out = torch.empty(B, N, out_cols, dtype=torch.bfloat16, device=x.device)
         fn = lib.vtk_ae_encode if side == 0 else lib.vtk_ae_decode
+        _lib.check(lib.vtk_ae_set_packing(h, 1 if self.token_packing else 0))
         _lib.check(fn(h, xin.data_ptr(), row.data_ptr(), col.data_ptr(), m8.data_ptr() if m8 is not None else None,
                       B, N, out.data_ptr(), ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()), _lib.stream_ptr()))
         self.last_launch_count = lib.vtk_ae_last_launch_count(h)

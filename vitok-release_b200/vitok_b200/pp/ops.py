@@ -90,6 +90,42 @@ def patchify_batch(images: Union[torch.Tensor, Sequence[torch.Tensor], Sequence[
     return _patchify_packed(packed, offsets, sizes, 1 if u8 else 0, patch, max_tokens, out_dtype, dev)
 
 
+def pack_images(images: Sequence[Union[torch.Tensor, np.ndarray]], pin: bool = True):
+    """Flatten a ragged list of images (all uint8 [H,W,3] or all float32 [3,H,W]) into ONE host buffer so that a
+    serving loop moves a NaFlex batch to the GPU with a single H2D copy.  Returns (flat, offsets, sizes); feed the
+    device copy of ``flat`` to ``patchify_packed``.  Every image starts on a 16-byte boundary."""
+    imgs = [torch.from_numpy(i) if isinstance(i, np.ndarray) else i for i in images]
+    u8 = imgs[0].dtype == torch.uint8
+    sizes, offsets, off = [], [], 0
+    for t in imgs:
+        if u8 and (t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3):
+            raise ValueError("pack_images: uint8 images must be [H,W,3]")
+        if not u8 and (t.dtype != torch.float32 or t.dim() != 3 or t.shape[0] != 3):
+            raise ValueError("pack_images: float images must be [3,H,W] float32")
+        h, w = (int(t.shape[0]), int(t.shape[1])) if u8 else (int(t.shape[1]), int(t.shape[2]))
+        sizes.append((h, w))
+        offsets.append(off)
+        step = 16 if u8 else 4
+        off += (3 * h * w + step - 1) // step * step
+    flat = torch.zeros(off, dtype=imgs[0].dtype)
+    if pin:
+        flat = flat.pin_memory()
+    for t, o in zip(imgs, offsets):
+        flat[o:o + t.numel()] = t.reshape(-1).cpu()
+    return flat, offsets, sizes
+
+
+def patchify_packed(flat: torch.Tensor, offsets: Sequence[int], sizes: Sequence[Tuple[int, int]], patch: int = 16,
+                    max_tokens: int = 256, out_dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+    """patchify + collate of a batch laid out by ``pack_images`` (``flat`` already on the GPU): one kernel launch."""
+    if not flat.is_cuda:
+        raise RuntimeError("vitok_b200.patchify_packed: the packed image buffer must be on a CUDA device")
+    if flat.dtype not in (torch.uint8, torch.float32):
+        raise ValueError("patchify_packed: the packed buffer must be uint8 (HWC images) or float32 (CHW images)")
+    return _patchify_packed(flat, list(offsets), list(sizes), 1 if flat.dtype == torch.uint8 else 0, patch, max_tokens,
+                            out_dtype, flat.device)
+
+
 _TABLE_CACHE: Dict = {}
 
 
@@ -289,4 +325,4 @@ OPS = {
     "to_tensor": to_tensor, "normalize": normalize, "patchify": patchify,
 }
 
-__all__ = ["OPS", "patchify", "patchify_batch", "unpatchify", "unpack", "resize_to_token_budget", "_fit_to_token_budget"]
+__all__ = ["OPS", "patchify", "patchify_batch", "pack_images", "patchify_packed", "unpatchify", "unpack", "resize_to_token_budget", "_fit_to_token_budget"]
