@@ -13,61 +13,100 @@
 
 namespace vtk {
 
-__device__ __forceinline__ float load_pixel(const void* base, long long off, int in_dtype, int H, int W, int ch, int y,
-                                            int x) {
-  if (y >= H || x >= W) return 0.f;  // zero padding to the patch boundary (ops.py:235-238)
-  if (in_dtype == 0) return reinterpret_cast<const float*>(base)[off + ((long long)ch * H + y) * W + x];
-  const uint8_t u = reinterpret_cast<const uint8_t*>(base)[off + ((long long)y * W + x) * 3 + ch];
-  // ToTensor: u/255 (fp32 division); Normalize(0.5, 0.5): (t - 0.5) / 0.5
-  const float t = __fdiv_rn((float)u, 255.0f);
-  return __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);
+// ToTensor (u / 255, fp32 division) then Normalize(0.5, 0.5) ((t - 0.5) / 0.5 == (t - 0.5) * 2 exactly), ops.py:140-161
+__device__ __forceinline__ float norm_u8(uint32_t u) {
+  return __fmul_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), 0.5f), 2.0f);
 }
 
 template <typename OutT>
+__device__ __forceinline__ void store4(OutT* dst, float4 v) {
+  if (sizeof(OutT) == 4) *reinterpret_cast<float4*>(dst) = v;
+  else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+// One warp per token: the token's 3p^2 output elements are written as contiguous 16-byte (fp32) / 8-byte (bf16) chunks,
+// lane after lane (fully coalesced), and gathered from the image as 16-pixel row segments.  All per-token index work
+// (image table, grid, row / col) is done once per token; PT = compile-time patch size (16 / 32; 0 = any multiple of 4)
+// turns the per-chunk divisions into shifts -- the first version of this kernel spent its time in 64-bit div / mod
+// (issue-bound at 1.9 TB/s).  uint8 HWC input: a lane reads the 12 contiguous bytes of 4 pixels (3 x 32-bit loads) and
+// writes one chunk per channel; the 256-entry normalisation table lives in shared memory (bit-exact by construction).
+template <typename OutT, int PT>
 __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyArgs a) {
-  const int p = a.patch, T = a.max_tokens;
-  const int pp = p * p, P = 3 * pp, P4 = P >> 2, p4 = p >> 2;
-  const long long total = (long long)a.B * T * P4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int e4 = (int)(i % P4);
-    const long long bt = i / P4;
-    const int t = (int)(bt % T);
-    const int b = (int)(bt / T);
+  __shared__ float lut[256];
+  if (a.in_dtype == 1) {
+    lut[threadIdx.x] = norm_u8(threadIdx.x);
+    __syncthreads();
+  }
+  const int p = PT ? PT : a.patch, T = a.max_tokens;
+  const int pp = p * p, P = 3 * pp, p4 = p >> 2, chunks = pp >> 2;   // chunks = 4-pixel groups per channel
+  const int lane = threadIdx.x & 31;
+  const unsigned ntok = (unsigned)a.B * (unsigned)T;
+  const unsigned nwarp = gridDim.x * (blockDim.x >> 5);
+  for (unsigned bt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bt < ntok; bt += nwarp) {
+    const int b = (int)(bt / (unsigned)T), t = (int)(bt - (unsigned)b * (unsigned)T);
     const long long off = a.img_table[3 * b + 0];
     const int H = (int)a.img_table[3 * b + 1], W = (int)a.img_table[3 * b + 2];
     const int gr = (H + p - 1) / p, gc = (W + p - 1) / p;
     const int n = gr * gc;
     const bool valid = t < n && n <= T;
-    const int r = valid ? t / gc : 0, c = valid ? t % gc : 0;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-      const int ch = e4 / (p * p4);
-      const int rem = e4 - ch * (p * p4);
-      const int dy = rem / p4, dx = (rem - dy * p4) << 2;
-      const int y = r * p + dy, x = c * p + dx;
-      bool fast = false;
-      if (a.in_dtype == 0 && y < H && x + 3 < W) {
-        const long long idx = off + ((long long)ch * H + y) * W + x;
-        const float* src = reinterpret_cast<const float*>(a.images) + idx;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-          v = *reinterpret_cast<const float4*>(src);
-          fast = true;
+    const int r = valid ? t / gc : 0, c = valid ? t - (t / gc) * gc : 0;
+    OutT* dst = reinterpret_cast<OutT*>(a.patches) + (long long)bt * P;
+    if (!valid) {
+      for (int e4 = lane; e4 < 3 * chunks; e4 += 32) store4(dst + (e4 << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+    } else if (a.in_dtype == 0) {
+      const float* img = reinterpret_cast<const float*>(a.images) + off;
+      const bool al = ((reinterpret_cast<uintptr_t>(img) | ((uintptr_t)W << 2)) & 15) == 0;   // rows start 16-byte aligned
+#pragma unroll 2
+      for (int e4 = lane; e4 < 3 * chunks; e4 += 32) {
+        const int ch = e4 / chunks, rem = e4 - ch * chunks;
+        const int dy = rem / p4, dx = (rem - dy * p4) << 2;
+        const int y = r * p + dy, x = c * p + dx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);      // zero padding to the patch boundary (ops.py:235-238)
+        if (y < H) {
+          const float* src = img + ((long long)ch * H + y) * W + x;
+          if (al && x + 3 < W) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            if (x < W) v.x = __ldg(src);
+            if (x + 1 < W) v.y = __ldg(src + 1);
+            if (x + 2 < W) v.z = __ldg(src + 2);
+            if (x + 3 < W) v.w = __ldg(src + 3);
+          }
         }
+        store4(dst + (e4 << 2), v);
       }
-      if (!fast) {
-        v.x = load_pixel(a.images, off, a.in_dtype, H, W, ch, y, x);
-        v.y = load_pixel(a.images, off, a.in_dtype, H, W, ch, y, x + 1);
-        v.z = load_pixel(a.images, off, a.in_dtype, H, W, ch, y, x + 2);
-        v.w = load_pixel(a.images, off, a.in_dtype, H, W, ch, y, x + 3);
-      }
-    }
-    OutT* dst = reinterpret_cast<OutT*>(a.patches) + bt * P + ((long long)e4 << 2);
-    if (sizeof(OutT) == 4) {
-      *reinterpret_cast<float4*>(dst) = v;
     } else {
-      *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.images) + off;
+      const bool al = (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+      for (int q = lane; q < chunks; q += 32) {
+        const int dy = q / p4, dx = (q - dy * p4) << 2;
+        const int y = r * p + dy, x = c * p + dx;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+        if (y < H && x < W) {
+          const uint8_t* src = img + ((long long)y * W + x) * 3;    // 12 contiguous bytes: r g b r g b r g b r g b
+          uint32_t w0 = 0, w1 = 0, w2 = 0;
+          if (al && x + 3 < W && (((long long)y * W + x) & 3) == 0) {
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+            w0 = __ldg(s32); w1 = __ldg(s32 + 1); w2 = __ldg(s32 + 2);
+          } else {
+            const int nb = min(4, W - x) * 3;
+            for (int k = 0; k < nb; ++k) {
+              const uint32_t u = src[k];
+              if (k < 4) w0 |= u << (8 * k); else if (k < 8) w1 |= u << (8 * (k - 4)); else w2 |= u << (8 * (k - 8));
+            }
+          }
+          const int np = min(4, W - x);   // pixels inside the image; the rest stay 0.0 (padding is applied AFTER normalize)
+          v0.x = lut[w0 & 255]; v1.x = lut[(w0 >> 8) & 255]; v2.x = lut[(w0 >> 16) & 255];
+          if (np > 1) { v0.y = lut[w0 >> 24]; v1.y = lut[w1 & 255]; v2.y = lut[(w1 >> 8) & 255]; }
+          if (np > 2) { v0.z = lut[(w1 >> 16) & 255]; v1.z = lut[w1 >> 24]; v2.z = lut[w2 & 255]; }
+          if (np > 3) { v0.w = lut[(w2 >> 8) & 255]; v1.w = lut[(w2 >> 16) & 255]; v2.w = lut[w2 >> 24]; }
+        }
+        store4(dst + (q << 2), v0);
+        store4(dst + pp + (q << 2), v1);
+        store4(dst + 2 * pp + (q << 2), v2);
+      }
     }
-    if (e4 == 0) {  // index packing, one thread per token
+    if (lane == 0) {  // index packing, one lane per token
       a.patch_mask[bt] = valid ? 1 : 0;
       a.row_idx[bt] = r;
       a.col_idx[bt] = c;
@@ -83,15 +122,23 @@ __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyArgs a) {
   }
 }
 
+template <typename OutT>
+static void patchify_dispatch(const PatchifyArgs& a, int blocks, cudaStream_t stream) {
+  if (a.patch == 16) patchify_kernel<OutT, 16><<<blocks, 256, 0, stream>>>(a);
+  else if (a.patch == 32) patchify_kernel<OutT, 32><<<blocks, 256, 0, stream>>>(a);
+  else patchify_kernel<OutT, 0><<<blocks, 256, 0, stream>>>(a);
+}
+
 int launch_patchify(const PatchifyArgs& a, cudaStream_t stream) {
   if (a.patch % 4 || a.patch <= 0) { set_error("patchify: patch size must be a positive multiple of 4 (got %d)", a.patch); return -2; }
   if (a.B <= 0 || a.max_tokens <= 0) return 0;
-  const long long total = (long long)a.B * a.max_tokens * (3 * a.patch * a.patch / 4);
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)num_sms() * 16;   // multiple of the SM count, grid-stride beyond
+  const long long ntok = (long long)a.B * a.max_tokens;
+  if (ntok >= (1ll << 31)) { set_error("patchify: B * max_tokens too large"); return -2; }
+  long long blocks = (ntok + 7) / 8;                   // one warp per token, 8 warps per CTA
+  const long long cap = (long long)num_sms() * 8;     // a multiple of the SM count (8 resident CTAs per SM), warp-stride beyond
   if (blocks > cap) blocks = cap;
-  if (a.out_dtype == 0) patchify_kernel<float><<<(int)blocks, 256, 0, stream>>>(a);
-  else patchify_kernel<bf16><<<(int)blocks, 256, 0, stream>>>(a);
+  if (a.out_dtype == 0) patchify_dispatch<float>(a, (int)blocks, stream);
+  else patchify_dispatch<bf16>(a, (int)blocks, stream);
   return check_cuda(cudaGetLastError(), "patchify launch");
 }
 
@@ -130,49 +177,62 @@ __device__ __forceinline__ float convert_px(float x, int fmt, bool bf16_math) {
   return x;
 }
 
-template <typename T>
+// One warp per canvas cell (b, r, c): the token that owns the cell is looked up once, its 3p^2 elements are read as
+// contiguous 8 / 16-byte chunks (coalesced) and written as p-pixel row segments of the three channel planes.  PT = compile-
+// time patch size (16 / 32; 0 = any multiple of 4) so the per-chunk index math is shifts, not divisions.
+template <typename T, int PT>
 __global__ void __launch_bounds__(256) unpatchify_kernel(const UnpatchifyArgs a) {
-  const int p = a.patch, pp = p * p, P = 3 * pp;
-  const int Hc = a.gy * p, Wc = a.gx * p, W4 = Wc >> 2;
-  const long long total = (long long)a.B * 3 * Hc * W4;
+  const int p = PT ? PT : a.patch, pp = p * p, P = 3 * pp, p4 = p >> 2, chunks = pp >> 2;
+  const int Hc = a.gy * p, Wc = a.gx * p;
+  const int cells_per_img = a.gy * a.gx;
+  const unsigned ncell = (unsigned)a.B * (unsigned)cells_per_img;
   const bool bfm = sizeof(T) == 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W4) << 2;
-    long long q = i / W4;
-    const int y = (int)(q % Hc); q /= Hc;
-    const int ch = (int)(q % 3);
-    const int b = (int)(q / 3);
-    const int r = y / p, dy = y - r * p, c = x / p, dx = x - c * p;
-    const int cell = r * a.gx + c;
+  const int lane = threadIdx.x & 31;
+  const unsigned nwarp = gridDim.x * (blockDim.x >> 5);
+  for (unsigned bc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bc < ncell; bc += nwarp) {
+    const int b = (int)(bc / (unsigned)cells_per_img), cell = (int)(bc - (unsigned)b * (unsigned)cells_per_img);
+    const int r = cell / a.gx, c = cell - r * a.gx;
     // token 0 is re-scattered into cell 0 after the main scatter (ops.py:332-333)
-    int tok = (cell == 0) ? (a.patch_mask[(long long)b * a.N] ? 0 : -1) : a.cell_map[(long long)b * a.gy * a.gx + cell];
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (tok >= 0) {
-      const T* src = reinterpret_cast<const T*>(a.patches) + ((long long)b * a.N + tok) * P + ch * pp + dy * p + dx;
-      if (sizeof(T) == 4) {
-        const float4 f = *reinterpret_cast<const float4*>(src);
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-      } else {
-        const uint2 u = *reinterpret_cast<const uint2*>(src);
-        v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    const int tok = (cell == 0) ? (a.patch_mask[(long long)b * a.N] ? 0 : -1) : a.cell_map[bc];
+    const T* src = reinterpret_cast<const T*>(a.patches) + ((long long)b * a.N + (tok >= 0 ? tok : 0)) * P;
+#pragma unroll 2
+    for (int e4 = lane; e4 < 3 * chunks; e4 += 32) {
+      const int ch = e4 / chunks, rem = e4 - ch * chunks;
+      const int dy = rem / p4, dx = (rem - dy * p4) << 2;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (tok >= 0) {
+        if (sizeof(T) == 4) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(src + (e4 << 2)));
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(src + (e4 << 2)));
+          v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+        }
       }
-    }
-    const long long o = (((long long)b * 3 + ch) * Hc + y) * Wc + x;
-    if (a.out_format == 1) {
-      uchar4 u;
-      u.x = (unsigned char)convert_px(v[0], 1, bfm); u.y = (unsigned char)convert_px(v[1], 1, bfm);
-      u.z = (unsigned char)convert_px(v[2], 1, bfm); u.w = (unsigned char)convert_px(v[3], 1, bfm);
-      *reinterpret_cast<uchar4*>(reinterpret_cast<uint8_t*>(a.out) + o) = u;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = convert_px(v[k], a.out_format, bfm);
-      if (sizeof(T) == 4) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o) = make_float4(v[0], v[1], v[2], v[3]);
+      const long long o = (((long long)b * 3 + ch) * Hc + r * p + dy) * Wc + c * p + dx;
+      if (a.out_format == 1) {
+        uchar4 u;
+        u.x = (unsigned char)convert_px(v[0], 1, bfm); u.y = (unsigned char)convert_px(v[1], 1, bfm);
+        u.z = (unsigned char)convert_px(v[2], 1, bfm); u.w = (unsigned char)convert_px(v[3], 1, bfm);
+        *reinterpret_cast<uchar4*>(reinterpret_cast<uint8_t*>(a.out) + o) = u;
       } else {
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.out) + o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = convert_px(v[k], a.out_format, bfm);
+        if (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.out) + o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+        }
       }
     }
   }
+}
+
+template <typename T>
+static void unpatchify_dispatch(const UnpatchifyArgs& a, int blocks, cudaStream_t stream) {
+  if (a.patch == 16) unpatchify_kernel<T, 16><<<blocks, 256, 0, stream>>>(a);
+  else if (a.patch == 32) unpatchify_kernel<T, 32><<<blocks, 256, 0, stream>>>(a);
+  else unpatchify_kernel<T, 0><<<blocks, 256, 0, stream>>>(a);
 }
 
 int launch_unpatchify(const UnpatchifyArgs& a, cudaStream_t stream) {
@@ -187,11 +247,12 @@ int launch_unpatchify(const UnpatchifyArgs& a, cudaStream_t stream) {
     if (blocks > cap) blocks = cap;
     cellmap_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   }
-  const long long total = (long long)a.B * 3 * a.gy * a.patch * (a.gx * a.patch / 4);
-  long long blocks = (total + 255) / 256;
-  if (blocks > cap) blocks = cap;
-  if (a.dtype == 0) unpatchify_kernel<float><<<(int)blocks, 256, 0, stream>>>(a);
-  else unpatchify_kernel<bf16><<<(int)blocks, 256, 0, stream>>>(a);
+  if (cells >= (1ll << 31)) { set_error("unpatchify: canvas too large"); return -2; }
+  long long blocks = (cells + 7) / 8;                    // one warp per cell, 8 warps per CTA
+  const long long cap2 = (long long)num_sms() * 8;
+  if (blocks > cap2) blocks = cap2;
+  if (a.dtype == 0) unpatchify_dispatch<float>(a, (int)blocks, stream);
+  else unpatchify_dispatch<bf16>(a, (int)blocks, stream);
   return check_cuda(cudaGetLastError(), "unpatchify launch");
 }
 
