@@ -294,11 +294,24 @@ def run_ours(args, rank, world, local):
     for e in ev_free:
         e.record(s_main)
 
-    def e2e_step(i):
+    keep = [None, None]
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    for e in ev_copied:
+        e.record(s_main)
+    diag = {"h2d": [], "d2h": [], "cpu": []}
+
+    def e2e_step(i, timed=False):
         b = i & 1
+        c0 = time.perf_counter()
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_free[b])                 # patchify of step i-2 has consumed this input buffer
+            if timed:
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record(s_in)
             dev_in[b].copy_(host_u8, non_blocking=True)
+            if timed:
+                h1.record(s_in)
+                diag["h2d"].append((h0, h1))
             ev_in[b].record(s_in)
         s_main.wait_event(ev_in[b])
         if ragged:
@@ -309,10 +322,21 @@ def run_ours(args, rank, world, local):
         o = step(d)
         img = vb.unpatchify(o, patch, max_grid_size=canvas // patch, output_format="0_255")
         ev_done[b].record(s_main)
+        # the D2H copy of step i-2 (it read keep[b]) has finished before that tensor's memory can be reused on s_main
+        s_main.wait_event(ev_copied[b])
+        keep[b] = img
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done[b])
-            img.record_stream(s_out)
+            if timed:
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                d0.record(s_out)
             host_outs[b].copy_(img, non_blocking=True)
+            if timed:
+                d1.record(s_out)
+                diag["d2h"].append((d0, d1))
+            ev_copied[b].record(s_out)
+        if timed:
+            diag["cpu"].append((time.perf_counter() - c0) * 1e3)
 
     def e2e_drain():
         s_main.wait_stream(s_out)
@@ -326,13 +350,16 @@ def run_ours(args, rank, world, local):
     t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_ev0.record()
     for i in range(args.steps):
-        e2e_step(i)
+        e2e_step(i, timed=True)
     e2e_drain()
     t_ev1.record()
     torch.cuda.synchronize()
     barrier(world)
     e2e_ms = max_over_ranks(t_ev0.elapsed_time(t_ev1), world, dev)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    e2e_diag = {"h2d_copy_ms": statistics.mean(a.elapsed_time(b) for a, b in diag["h2d"]),
+                "d2h_copy_ms": statistics.mean(a.elapsed_time(b) for a, b in diag["d2h"]),
+                "cpu_enqueue_ms_per_step": statistics.mean(diag["cpu"])}
 
     # ---- per-kernel-class CUDA-event timing inside a timed pass (roofline of the dominant kernel) ---
     roof, breakdown = None, None
@@ -400,7 +427,7 @@ def run_ours(args, rank, world, local):
                    "l2": "no flush: per-step working set (weights + activations) exceeds the 126 MB L2",
                    "gflop_per_image": gf},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps, **e2e_diag},
         "gpu_launches": n_launch,
         "launches_per_step": launches_per_step,
         "model_tflops": value * gf / 1e3 / world,

@@ -222,6 +222,12 @@ int vtk_ae_encode(vtk_ae_t h, const void* patches, const int64_t* row_idx, const
 /* AE.decode (vitok/models/ae.py:218-243): z [B,N,C] bf16 -> patches [B,N,P] bf16. */
 int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64_t* col_idx, const uint8_t* patch_mask,
                   int B, int N, void* patches_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Fused Block.norm1 (vitok/models/ae.py:55, modules/norm.py:17-25).  Call after vtk_ae_set_weights with folded = 1 when
+ * every block's w_in of that side was packed with norm1.weight multiplied into its columns (W'[j,k] = W[j,k] * w[k]).
+ * Then no RMSNorm kernel runs: the GEMM that produces x (patch/decoder embed, out_proj+fc2 residual) also writes the
+ * per-row sums of squares, and the QKV+fc1 GEMM reads x directly and scales every accumulator row by
+ * rsqrt(mean(x^2) + eps): h W^T = rstd * (x (W*w)^T).  Needs width % 256 == 0.  folded = 0 (default): separate RMSNorm. */
+int vtk_ae_set_norm_folded(vtk_ae_t h, int side, int folded);
 /* NaFlex token packing (default on).  When a patch_mask is given and head_dim == 64, vtk_ae_encode/decode gather the
  * valid tokens of every image into a packed row range (each image padded to a multiple of 128 rows), run every kernel
  * of the layer stack over the packed rows only -- the packed row count stays in device memory, nothing syncs -- and

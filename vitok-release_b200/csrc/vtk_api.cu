@@ -91,6 +91,7 @@ struct Side {
   const bf16 *w_a = nullptr, *b_a = nullptr, *w_b = nullptr, *b_b = nullptr;
   std::vector<vtk_block_weights> blocks;
   float* inv_freq = nullptr;  // device, d/4 floats
+  bool norm_folded = false;   // w_in has norm1.weight folded into its columns: norm1 runs inside the GEMM epilogues
   int head_dim() const { return heads ? width / heads : 0; }
   int qp() const { return ((3 * width + 255) / 256) * 256; }
   // row pitch of [attn | act] and of the packed [out_proj | fc2]: D + Hf rounded up to 64 elements so every
@@ -100,6 +101,7 @@ struct Side {
 
 struct Workspace {
   bf16 *x, *h, *qkv, *a2, *rope;
+  float* ss;            // [rows, D / 64] per-unit sums of squares of x (fused norm1)
   int *kv_len, *is_prefix;
   PackPlan plan;        // NaFlex token packing (masked batches): plan arrays + packed input / output staging rows
   bf16 *pin, *pout;
@@ -124,6 +126,7 @@ static Workspace carve(const Side& s, void* base, int B, int N, int io_cols) {
   w.qkv = static_cast<bf16*>(take((size_t)M * 3 * D * 2));
   w.a2 = static_cast<bf16*>(take((size_t)M * s.kp() * 2));
   w.rope = static_cast<bf16*>(take((size_t)((M + 31) / 32 * 32) * 2 * d * 2));   // pair-expanded table, 32-row groups
+  w.ss = static_cast<float*>(take((size_t)M * ((D + 63) / 64) * 4));
   w.kv_len = static_cast<int*>(take((size_t)B * 4));
   w.is_prefix = static_cast<int*>(take((size_t)B * 4));
   w.plan.B = B; w.plan.N = N;
@@ -484,6 +487,7 @@ int vtk_ae_set_weights(vtk_ae_t h, int side, const void* w_a, const void* b_a, c
   VTK_REQUIRE(nblocks == 0 || blocks, "vtk_ae_set_weights: null blocks");
   VTK_REQUIRE(n_inv_freq == s.head_dim() / 4 && inv_freq_host, "vtk_ae_set_weights: inv_freq must have head_dim/4 entries");
   s.w_a = (const bf16*)w_a; s.b_a = (const bf16*)b_a; s.w_b = (const bf16*)w_b; s.b_b = (const bf16*)b_b;
+  s.norm_folded = false;
   s.blocks.assign(blocks, blocks + nblocks);
   for (int i = 0; i < nblocks; ++i) {
     const vtk_block_weights& b = s.blocks[i];
@@ -527,9 +531,14 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
   }
   for (int i = 0; i < s.depth; ++i) {
     const vtk_block_weights& b = s.blocks[i];
-    { LaunchTimer t(h, st, CLS_RMSNORM); r = launch_rmsnorm(w.x, D, (const bf16*)b.norm1, w.h, D, M, D, eps, st, m_dev); }
-    if (r) return r;
-    GemmArgs g1 = base_args(w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
+    const bool fused = s.norm_folded;   // norm1 inside the epilogues: x is the A operand, rows scaled by rsqrt(mean(x^2)+eps)
+    if (!fused) {
+      { LaunchTimer t(h, st, CLS_RMSNORM); r = launch_rmsnorm(w.x, D, (const bf16*)b.norm1, w.h, D, M, D, eps, st, m_dev); }
+      if (r) return r;
+      ++launches;
+    }
+    GemmArgs g1 = base_args(fused ? w.x : w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
+    if (fused) { g1.epi.ss_in = w.ss; g1.epi.ss_units = D / 64; g1.epi.ss_inv_d = 1.f / (float)D; }
     g1.epi.qkv = w.qkv; g1.epi.ld_qkv = 3 * D; g1.epi.act = w.a2 + D; g1.epi.ld_act = kp;
     g1.epi.normq = (const bf16*)b.norm_q; g1.epi.normk = (const bf16*)b.norm_k; g1.epi.rope = w.rope;
     g1.epi.D = D; g1.epi.d = d; g1.epi.Hf = Hf; g1.epi.qp = qp; g1.epi.eps = eps;
@@ -556,9 +565,10 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
     GemmArgs g2 = base_args(w.a2, kp, b.w_out, kp, D, M, D, D + Hf);
     g2.epi.out = w.x; g2.epi.ldo = D; g2.epi.gamma = (const bf16*)b.gamma;
     g2.epi.m_dev = m_dev;
+    if (fused && i + 1 < s.depth) { g2.epi.ss_out = w.ss; g2.epi.ss_ld = D / 64; }
     { LaunchTimer t(h, st, CLS_PROJ_RESID); r = launch_gemm(EPI_RESID, g2, st); }
     if (r) return r;
-    launches += 4;
+    launches += 3;
   }
   return 0;
 }
@@ -587,6 +597,7 @@ static int run_side(vtk_ae_s* h, int side, const void* in, const int64_t* row_id
   }
   GemmArgs g = base_args(a_in, cin, s.w_a, cin, D, rows, D, cin);       // patch_embed ae.py:191 / decoder_embed ae.py:220
   g.epi.out = w.x; g.epi.ldo = D; g.epi.bias = s.b_a; g.epi.m_dev = m_dev;
+  if (s.norm_folded && s.depth > 0) { g.epi.ss_out = w.ss; g.epi.ss_ld = D / 64; }
   { LaunchTimer t(h, st, CLS_LINEAR); r = launch_gemm(EPI_BIAS, g, st); }
   if (r) return r;
   ++launches;
@@ -634,6 +645,14 @@ int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64
   int r = check_io(h, 1, z, row_idx, col_idx, B, N, patches_out, workspace, workspace_bytes, "vtk_ae_decode");
   if (r) return r;
   return run_side(h, 1, z, row_idx, col_idx, patch_mask, B, N, patches_out, workspace, (cudaStream_t)stream);
+}
+
+int vtk_ae_set_norm_folded(vtk_ae_t h, int side, int folded) {
+  VTK_REQUIRE(h && (side == 0 || side == 1), "vtk_ae_set_norm_folded: bad handle/side");
+  Side& s = h->side[side];
+  VTK_REQUIRE(!folded || (s.width > 0 && s.width % 256 == 0), "vtk_ae_set_norm_folded: the fused norm needs width %% 256 == 0 (width=%d)", s.width);
+  s.norm_folded = folded != 0;
+  return VTK_OK;
 }
 
 int vtk_ae_set_packing(vtk_ae_t h, int enable) {

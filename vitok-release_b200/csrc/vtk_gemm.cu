@@ -141,6 +141,7 @@ __device__ __forceinline__ float u4_hi(const uint4& v, int i) {   // element 2i+
 // out = bf16(acc + bias)
 __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
                                               int ucols) {
+  uint64_t ss2 = 0ull;   // sum of squares of this unit's bf16 outputs (fused norm1, see EpiParams::ss_out)
   for (int cc = 0; cc < ucols; cc += 16) {
     const int col = n + cc;
     if (col >= N) break;  // warp-uniform
@@ -163,7 +164,20 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
       bf16* op = p.out + (long long)row * p.ldo + col;
       st_global_v4(op, o[0], o[1], o[2], o[3]);
       if (second) st_global_v4(op + 8, o[4], o[5], o[6], o[7]);
+      if (p.ss_out) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i >= 4 && !second) break;
+          const uint64_t t = bf2_to_f2(o[i]);
+          ss2 = f2_fma(t, t, ss2);
+        }
+      }
     }
+  }
+  if (p.ss_out && row_ok && n < N) {
+    float s0, s1;
+    f2_unpack(ss2, s0, s1);
+    p.ss_out[(long long)row * p.ss_ld + (n >> 6)] = s0 + s1;
   }
 }
 
@@ -172,6 +186,7 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
 // eager bf16 ops do (layerscale.py:23, ae.py:64-65), at 1.5 instructions per element.
 __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
                                                int ucols, OutStage& st, const CUtensorMap* tmX) {
+  uint64_t ss2 = 0ull;   // sum of squares of the new x over this 64-column unit (fused norm1 of the next block)
   for (int cc = 0; cc < ucols; cc += 32) {
     const int col = n + cc;
     if (col >= N) break;
@@ -200,8 +215,20 @@ __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t tadd
       for (int i = 0; i < 4; ++i)
         o[i] = bf2_add(xs[i], bf2_mul(bf2_cvt_bits(r[8 * j + 2 * i], r[8 * j + 2 * i + 1]), gs[i]));
       st.put(j, o[0], o[1], o[2], o[3]);
+      if (p.ss_out && j < nch) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint64_t t = bf2_to_f2(o[i]);
+          ss2 = f2_fma(t, t, ss2);
+        }
+      }
     }
     st.flush(tmX, col);
+  }
+  if (p.ss_out && row_ok && n < N) {
+    float s0, s1;
+    f2_unpack(ss2, s0, s1);
+    p.ss_out[(long long)row * p.ss_ld + (n >> 6)] = s0 + s1;
   }
 }
 
@@ -268,10 +295,17 @@ __device__ __forceinline__ const uint4* rope_row_ptr(const EpiParams& p, int rro
   return reinterpret_cast<const uint4*>(p.rope) + (grp * (p.d >> 2)) * 32 + (rrow & 31);
 }
 
+// GEMM output element pair as bf16: bf16(acc * rs) with rs = the row's fused-norm1 scale (1.0 when norm1 is not fused)
+__device__ __forceinline__ uint32_t cvt_acc2(uint32_t lo_bits, uint32_t hi_bits, uint64_t rs2) {
+  float a, b;
+  f2_unpack(f2_mul(f2_pack(__uint_as_float(lo_bits), __uint_as_float(hi_bits)), rs2), a, b);
+  return bf2_cvt(a, b);
+}
+
 // One q or k head: per-head RMSNorm over d (fp32, eps inside rsqrt; attention.py:103, norm.py:22-25) then
 // interleaved-pair 2D RoPE.  w_s = this head kind's norm weight as fp32 in shared memory.
 __device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, const uint4* rope_row, int ncol,
-                                            const float* w_s, OutStage& st, const CUtensorMap* tmQKV) {
+                                            const float* w_s, OutStage& st, const CUtensorMap* tmQKV, uint64_t rs2) {
   const int d = p.d;
   uint64_t ss2 = 0ull;
   for (int cc = 0; cc < d; cc += 32) {
@@ -280,7 +314,7 @@ __device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, 
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const uint64_t t = bf2_to_f2(bf2_cvt_bits(r[2 * i], r[2 * i + 1]));   // q as the bf16 GEMM output
+      const uint64_t t = bf2_to_f2(cvt_acc2(r[2 * i], r[2 * i + 1], rs2));   // q as the bf16 GEMM output
       ss2 = f2_fma(t, t, ss2);
     }
   }
@@ -310,7 +344,7 @@ __device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, 
       uint32_t o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint64_t t = bf2_to_f2(bf2_cvt_bits(r[8 * j + 2 * i], r[8 * j + 2 * i + 1]));
+        const uint64_t t = bf2_to_f2(cvt_acc2(r[8 * j + 2 * i], r[8 * j + 2 * i + 1], rs2));
         float y0, y1;
         f2_unpack(f2_mul(f2_mul(t, rstd2), w2[i]), y0, y1);
         const uint32_t Y = bf2_cvt(y0, y1);
@@ -326,7 +360,7 @@ __device__ __forceinline__ void epi_qk_head(const EpiParams& p, uint32_t taddr, 
 // registers (that IS the reference's bf16 q/k), and both the sum of squares and the normalise+rotate pass run
 // from those registers -- one TMEM round trip instead of two on the epilogue's critical path.
 __device__ __forceinline__ void epi_qk_head64(const EpiParams& p, uint32_t taddr, const uint4* rope_row, int ncol,
-                                              const float* w_s, OutStage& st, const CUtensorMap* tmQKV) {
+                                              const float* w_s, OutStage& st, const CUtensorMap* tmQKV, uint64_t rs2) {
   uint32_t P[32];
   uint64_t ss2 = 0ull;
   {
@@ -336,8 +370,8 @@ __device__ __forceinline__ void epi_qk_head64(const EpiParams& p, uint32_t taddr
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      P[i] = bf2_cvt_bits(r0[2 * i], r0[2 * i + 1]);
-      P[16 + i] = bf2_cvt_bits(r1[2 * i], r1[2 * i + 1]);
+      P[i] = cvt_acc2(r0[2 * i], r0[2 * i + 1], rs2);
+      P[16 + i] = cvt_acc2(r1[2 * i], r1[2 * i + 1], rs2);
     }
   }
 #pragma unroll
@@ -381,7 +415,7 @@ __device__ __forceinline__ void epi_qk_head64(const EpiParams& p, uint32_t taddr
 
 __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t taddr, int rrow, int n, int ucols,
                                                     const float* normw_s, OutStage& st, const CUtensorMap* tmQKV,
-                                                    const CUtensorMap* tmACT) {
+                                                    const CUtensorMap* tmACT, uint64_t rs2) {
   if (n < p.qp) {
     const int threeD = 3 * p.D;
     const uint4* rope_row = rope_row_ptr(p, rrow);
@@ -397,13 +431,13 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
           st.begin();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            st.put(j, bf2_cvt_bits(r[8 * j], r[8 * j + 1]), bf2_cvt_bits(r[8 * j + 2], r[8 * j + 3]),
-                   bf2_cvt_bits(r[8 * j + 4], r[8 * j + 5]), bf2_cvt_bits(r[8 * j + 6], r[8 * j + 7]));
+            st.put(j, cvt_acc2(r[8 * j], r[8 * j + 1], rs2), cvt_acc2(r[8 * j + 2], r[8 * j + 3], rs2),
+                   cvt_acc2(r[8 * j + 4], r[8 * j + 5], rs2), cvt_acc2(r[8 * j + 6], r[8 * j + 7], rs2));
           st.flush(tmQKV, ncol + cc);
         }
       } else {
-        if (p.d == 64) epi_qk_head64(p, taddr + hc, rope_row, ncol, normw_s + seg * 128, st, tmQKV);
-        else epi_qk_head(p, taddr + hc, rope_row, ncol, normw_s + seg * 128, st, tmQKV);
+        if (p.d == 64) epi_qk_head64(p, taddr + hc, rope_row, ncol, normw_s + seg * 128, st, tmQKV, rs2);
+        else epi_qk_head(p, taddr + hc, rope_row, ncol, normw_s + seg * 128, st, tmQKV, rs2);
       }
     }
   } else {
@@ -426,8 +460,8 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
         uint32_t o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t Vp = bf2_cvt_bits(r[2 * i], r[2 * i + 1]);
-          const uint64_t g2 = bf2_to_f2(bf2_cvt_bits(r[16 + 2 * i], r[16 + 2 * i + 1]));
+          const uint32_t Vp = cvt_acc2(r[2 * i], r[2 * i + 1], rs2);
+          const uint64_t g2 = bf2_to_f2(cvt_acc2(r[16 + 2 * i], r[16 + 2 * i + 1], rs2));
           float e0, e1, g0, g1;
           f2_unpack(f2_mul(g2, nlog2e), e0, e1);
           asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e0));
@@ -444,6 +478,21 @@ __device__ __forceinline__ void epi_qkv_swiglu_unit(const EpiParams& p, uint32_t
       st.flush(tmACT, 16 * j0);
     }
   }
+}
+
+// fused norm1: the row's scale rsqrt(mean(x^2) + eps) from the producer's per-unit sums of squares (fixed order)
+__device__ __forceinline__ uint64_t row_scale2(const EpiParams& p, int rrow) {
+  float rs = 1.f;
+  if (p.ss_in) {
+    const float4* sp = reinterpret_cast<const float4*>(p.ss_in + (long long)rrow * p.ss_units);
+    float ss = 0.f;
+    for (int u = 0; u < (p.ss_units >> 2); ++u) {
+      const float4 v = __ldg(sp + u);
+      ss += (v.x + v.y) + (v.z + v.w);
+    }
+    rs = rsqrtf(ss * p.ss_inv_d + p.eps);
+  }
+  return f2_pack(rs, rs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -581,6 +630,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool row_ok = row < M && epi.debug != 1;
       st.row0 = m0 + quarter * 32;
       const int rrow = row_ok ? row : (M - 1);
+      uint64_t rs2 = 0ull;
+      if (EPI == EPI_QKV_SWIGLU) rs2 = row_scale2(epi, rrow);
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + (uint32_t)(acc * BN);
@@ -593,7 +644,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
           if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
           if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0);
-          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1);
+          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1, rs2);
         }
       }
       tc_fence_before();
@@ -836,6 +887,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool row_ok = row < M && epi.debug != 1;
       st.row0 = m0 + quarter * 32;
       const int rrow = row < M ? row : (M - 1);
+      uint64_t rs2 = 0ull;
+      if (EPI == EPI_QKV_SWIGLU) rs2 = row_scale2(epi, rrow);
       if (EPI == EPI_QKV_SWIGLU && n0 < 2 * epi.D) {
         // q/k tile: pull this warp's 32 RoPE-table rows (one contiguous 32 * 4d-byte block, thanks to the
         // chunk-major layout) into L1 while the accumulator is still being computed
@@ -860,7 +913,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
           if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
           if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0);
-          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1);
+          if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1, rs2);
         }
       }
       tc_fence_before();

@@ -49,6 +49,12 @@ struct EpiParams {
   int D, d, Hf, qp;     // qp = 3D rounded up to the tile width (start of the SwiGLU columns)
   // EPI_RESID
   const bf16* gamma;    // [N]
+  // Fused Block.norm1 (norm.py:17-25): instead of a separate RMSNorm pass the producer of x (EPI_BIAS / EPI_RESID) also
+  // writes, per row, the sum of squares of its bf16 outputs for every 64-column unit (ss_out[row * ss_ld + col / 64];
+  // fixed summation order, no atomics), and the consumer (EPI_QKV_SWIGLU, whose weight has norm1.weight folded into its
+  // columns) multiplies each accumulator row by rsqrt(sum(ss_in[row, 0..ss_units)) * ss_inv_d + eps) before anything else.
+  float* ss_out; int ss_ld;
+  const float* ss_in; int ss_units; float ss_inv_d;
   const int* m_dev;     // optional: number of rows to process, read on the device (<= GemmArgs::M, which is then the row
                         // capacity of the buffers); used by the packed NaFlex path where sum(n_i) is only known on the GPU
   unsigned long long* prof;  // perf experiments only (env VTK_GEMM_PROF): per-role clock64 accumulators, or null

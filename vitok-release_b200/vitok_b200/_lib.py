@@ -84,6 +84,7 @@ SIGNATURES = {
     "vtk_ae_last_launch_count": (c_int, [c_vp]),
     "vtk_ae_set_timing": (c_int, [c_vp, c_int]),
     "vtk_ae_set_packing": (c_int, [c_vp, c_int]),
+    "vtk_ae_set_norm_folded": (c_int, [c_vp, c_int, c_int]),
     "vtk_ae_collect_timing": (c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_int)]),
 }
 

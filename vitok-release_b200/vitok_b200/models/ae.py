@@ -21,6 +21,8 @@ Training: ``model(batch)`` in train mode builds one autograd node (vitok_b200/tr
 """
 from __future__ import annotations
 
+import os
+
 import ctypes
 import re
 from typing import Any, Dict, List, Optional
@@ -216,10 +218,14 @@ class AE(nn.Module):
         self._packed: Dict[int, List[torch.Tensor]] = {}
         self._packed_sig = None
         self._ws: Dict[Any, torch.Tensor] = {}
+        self._plist: Optional[List[torch.Tensor]] = None
         self.last_launch_count = 0
         # NaFlex token packing for masked (sdpa-backend) batches: only valid tokens go through the layer stack
         # (include/vitok_b200.h, vtk_ae_set_packing).  False keeps the padded layout with in-kernel key masking.
         self.token_packing = True
+        # Block.norm1 fused into the GEMM epilogues (widths that are multiples of 256): no RMSNorm kernel, no h buffer
+        # round trip.  False keeps the separate RMSNorm kernel (rounds h to bf16 exactly where the reference does).
+        self.fuse_norm = os.environ.get("VTK_NO_FUSE_NORM", "0") != "1"
 
     # ------------------------------------------------------------------ native plumbing
     def _sides(self):
@@ -231,8 +237,25 @@ class AE(nn.Module):
         return out
 
     def _signature(self):
-        ps = list(self.parameters())
+        # (device, storage pointers, versions) of every parameter: changes on .to(), load_state_dict, optimizer steps.
+        # The module-tree walk is cached (it costs more than the check itself); anything that can replace a Parameter
+        # object goes through _apply / load_state_dict / train(), which drop the cache.
+        ps = self._plist
+        if ps is None:
+            ps = self._plist = list(self.parameters())
         return (ps[0].device, tuple(p.data_ptr() for p in ps), tuple(p._version for p in ps))
+
+    def _apply(self, fn, *args, **kwargs):
+        self._plist = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._plist = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def train(self, mode: bool = True):
+        self._plist = None
+        return super().train(mode)
 
     def __del__(self):
         try:
@@ -242,16 +265,19 @@ class AE(nn.Module):
             pass
 
     @torch.no_grad()
-    def _ensure_packed(self, device: torch.device) -> int:
+    def _ensure_packed(self, device: torch.device, fold_norm: bool = True) -> int:
         """(Re)build the packed bf16 weights the kernels read and hand their pointers to the C handle.
 
         w_in  [qp + 2*Hf, D] = [Wq; Wk; Wv; zeros up to qp; 16-row interleave of fc1's value/gate halves]
         w_out [D, Kp]        = [out_proj | fc2 | 0-pad to a multiple of 64]   (one GEMM over the concatenated K)
         Rebuilt whenever a parameter's storage or version changes (load_state_dict, .to(), optimizer step).
         """
-        sig = self._signature()
+        sig = (self._signature(), bool(fold_norm and self.fuse_norm))
         if self._handle is not None and sig == self._packed_sig:
             return self._handle
+        fold = sig[1]
+        sig0 = sig
+        sig = sig[0]
         lib = _lib.load()
         if sig[0].type != "cuda":
             raise RuntimeError("vitok_b200.AE: parameters must be on a CUDA device (model.to('cuda')); there is no CPU path")
@@ -280,7 +306,13 @@ class AE(nn.Module):
             qp = ((3 * width + 255) // 256) * 256
             arr = (_lib.BlockWeights * max(len(blocks), 1))()
             for i, blk in enumerate(blocks):
-                w_in = pack_w_in(dev(blk.attn.qkv_proj.weight), dev(blk.ffn.fc1.weight))
+                if fold and width % 256 == 0:
+                    # norm1 folded into the GEMM: h W^T = rstd * (x (W * w)^T)  (include/vitok_b200.h: vtk_ae_set_norm_folded)
+                    n1 = blk.norm1.weight.detach().to(device=device, dtype=torch.float32)[None, :]
+                    w_in = pack_w_in((blk.attn.qkv_proj.weight.detach().to(device=device, dtype=torch.float32) * n1).to(bf),
+                                     (blk.ffn.fc1.weight.detach().to(device=device, dtype=torch.float32) * n1).to(bf))
+                else:
+                    w_in = pack_w_in(dev(blk.attn.qkv_proj.weight), dev(blk.ffn.fc1.weight))
                 w_out = pack_w_out(dev(blk.attn.out_proj.weight), dev(blk.ffn.fc2.weight))
                 gamma = dev(blk.layer_scale.gamma) if isinstance(blk.layer_scale, _Scale) else torch.ones(width, dtype=bf, device=device)
                 tens = [w_in, w_out, dev(blk.norm1.weight), dev(blk.attn.norm_q.weight), dev(blk.attn.norm_k.weight), gamma]
@@ -293,8 +325,9 @@ class AE(nn.Module):
             inv_c = (ctypes.c_float * inv.numel())(*inv.tolist())
             _lib.check(lib.vtk_ae_set_weights(self._handle, side, *[t.data_ptr() for t in proj], arr, len(blocks), inv_c,
                                               inv.numel()))
+            _lib.check(lib.vtk_ae_set_norm_folded(self._handle, side, 1 if (fold and width % 256 == 0 and len(blocks) > 0) else 0))
             self._packed[side] = keep
-        self._packed_sig = sig
+        self._packed_sig = sig0
         return self._handle
 
     def _workspace(self, side: int, B: int, N: int, device) -> torch.Tensor:

@@ -186,7 +186,7 @@ class AETrainFunction(torch.autograd.Function):
         dev = patches.device
         if (B * N) % 8:
             raise ValueError("vitok_b200 training: B * N must be a multiple of 8 (token count is the K dimension of the wgrad GEMMs)")
-        model._ensure_packed(dev)
+        model._ensure_packed(dev, fold_norm=False)
         enc_w, dec_w = _SideWeights(model, 0), _SideWeights(model, 1)
         row = row.to(device=dev, dtype=torch.int64).contiguous()
         col = col.to(device=dev, dtype=torch.int64).contiguous()
