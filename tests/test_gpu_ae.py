@@ -189,3 +189,21 @@ def test_preprocess_encode_decode_postprocess_pipeline():
         out = model.decode(model.encode(d))
     recon = vb.postprocess(out, output_format="0_255", do_unpack=True, patch=16)
     assert [tuple(r.shape) for r in recon] == [(3, 256, 256), (3, 200, 120)] and recon[0].dtype == torch.uint8
+
+
+def test_torch_compile_fullgraph_encode_decode():
+    """README.md:57-58 of the reference: ``model.encode = torch.compile(model.encode, fullgraph=True)`` must keep working.
+    encode / decode reach the C ABI through one opaque torch op (vitok_b200::ae_run), so Dynamo captures a full graph."""
+    cfg0 = ae_oracle.decode_variant(SMALL)
+    sd = make_state_dict(cfg0, seed=1, stress=True)
+    model, cfg = _model(SMALL, sd, "sdpa")
+    batch = _to_cuda(_batch([(128, 128), (96, 64), (50, 120)], 16, 64, seed=5))
+    with torch.no_grad():
+        e0 = model.encode(batch)
+        d0 = model.decode(e0)
+        enc_c = torch.compile(model.encode, fullgraph=True)
+        dec_c = torch.compile(model.decode, fullgraph=True)
+        e1 = enc_c(batch)
+        d1 = dec_c(e1)
+    assert torch.equal(e0["z"], e1["z"]) and torch.equal(d0["patches"], d1["patches"])
+    assert set(e1) == set(e0) and set(d1) == set(d0)

@@ -128,3 +128,40 @@ def test_no_cpu_fallback():
             if f.endswith(".py"):
                 src += open(os.path.join(dp, f)).read()
     assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_pretrained_registry_and_local_safetensors_roundtrip(tmp_path):
+    """vitok/pretrained.py: same registry / return shape; weights ingest from local safetensors files."""
+    import json
+    import os
+    import torch
+    import vitok_b200 as vb
+    from vitok_b200 import pretrained as pt
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "variants.json")))
+    assert pt.list_pretrained() == ["350M-f16x16", "350M-f16x32", "350M-f16x64", "5B-f16x16", "5B-f16x32", "5B-f16x64",
+                                    "5B-f32x64", "5B-f32x128", "5B-f32x256"]
+    for name in pt.list_pretrained():
+        repo, files, variant = pt.get_pretrained_info(name)
+        assert repo == f"philippehansen/ViTok-v2-{name}" and files == ["encoder.safetensors", "decoder.safetensors"]
+        vb.decode_variant(variant)
+        if variant in golden:
+            assert vb.decode_variant(variant) == golden[variant]
+    with pytest.raises(KeyError):
+        pt.load_pretrained("1T-f1x1")
+    # a registry name with a small stand-in architecture on disk (no network here)
+    cfg = vb.decode_variant("w128_d2_h2-w256_d3_h2/1x16x16")
+    torch.manual_seed(3)
+    model = vb.AE(**cfg)
+    paths = pt.save_pretrained(model, str(tmp_path), "350M-f16x16")
+    assert [os.path.basename(p) for p in paths] == ["encoder.safetensors", "decoder.safetensors"]
+    data = pt.load_pretrained("350M-f16x16", local_dir=str(tmp_path))
+    assert data["variant"] == "Ld4-Ld24/1x16x16" and set(data) == {"variant", "encoder", "decoder"}
+    fresh = vb.AE(**cfg)
+    fresh.load_state_dict({**data["encoder"], **data["decoder"]})          # README.md:50-53
+    for (k, a), (_, b) in zip(model.state_dict().items(), fresh.state_dict().items()):
+        assert torch.equal(a, b), k
+    enc_only = vb.AE(**cfg, decoder=False)                                 # README.md:68-82
+    enc_only.load_state_dict(pt.load_pretrained("350M-f16x16", component="encoder", local_dir=str(tmp_path))["encoder"], strict=False)
+    dec_only = vb.AE(**cfg, encoder=False)
+    dec_only.load_state_dict(pt.load_pretrained("350M-f16x16", component="decoder", local_dir=str(tmp_path))["decoder"], strict=True)
+    assert not any(k.startswith("decoder") for k in enc_only.state_dict()) and not any(k.startswith("encoder") for k in dec_only.state_dict())

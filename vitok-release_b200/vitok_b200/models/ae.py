@@ -24,7 +24,9 @@ from __future__ import annotations
 import os
 
 import ctypes
+import itertools
 import re
+import weakref
 from typing import Any, Dict, List, Optional
 
 import torch
@@ -169,6 +171,27 @@ class _OutputNorm(_NoTorchPath):
     """LayerNorm without affine parameters (no state_dict entries), fused into the to_code GEMM epilogue."""
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# vitok_b200::ae_run -- the one opaque torch op behind AE.encode / AE.decode.  It exists so that TorchDynamo can trace
+# encode / decode (torch.compile(model.encode, fullgraph=True), reference README.md:57-58): the graph holds a single
+# call to this op, whose eager body does the C-ABI call.  Models are looked up by id (weak references).
+# ----------------------------------------------------------------------------------------------------------------
+_MODELS: "weakref.WeakValueDictionary[int, AE]" = weakref.WeakValueDictionary()
+_MODEL_IDS = itertools.count(1)
+
+
+@torch.library.custom_op("vitok_b200::ae_run", mutates_args=())
+def _ae_run(model_id: int, side: int, x: torch.Tensor, row: torch.Tensor, col: torch.Tensor,
+            mask: Optional[torch.Tensor]) -> torch.Tensor:
+    return _MODELS[model_id]._run_native(side, x, row, col, mask)
+
+
+@_ae_run.register_fake
+def _ae_run_fake(model_id, side, x, row, col, mask):
+    m = _MODELS[model_id]
+    return x.new_empty((x.shape[0], x.shape[1], m.channels_per_token if side == 0 else m.pixels_per_token), dtype=m._out_dtype())
+
+
 class AE(nn.Module):
     """ViTok-v2 autoencoder; see module docstring."""
 
@@ -220,6 +243,8 @@ class AE(nn.Module):
         self._ws: Dict[Any, torch.Tensor] = {}
         self._plist: Optional[List[torch.Tensor]] = None
         self.last_launch_count = 0
+        self._model_id = next(_MODEL_IDS)       # key of this instance for the vitok_b200::ae_run op
+        _MODELS[self._model_id] = self
         # NaFlex token packing for masked (sdpa-backend) batches: only valid tokens go through the layer stack
         # (include/vitok_b200.h, vtk_ae_set_packing).  False keeps the padded layout with in-kernel key masking.
         self.token_packing = True
@@ -341,6 +366,9 @@ class AE(nn.Module):
         return ws
 
     def _run(self, side: int, x: torch.Tensor, d: Dict[str, torch.Tensor], out_cols: int) -> torch.Tensor:
+        """Argument checks (traceable by TorchDynamo) + ONE opaque op, ``vitok_b200::ae_run``, that makes the C call.
+        The op is what lets ``torch.compile(model.encode, fullgraph=True)`` (reference README.md:57-58) capture encode /
+        decode as a single graph node instead of failing on the ctypes call."""
         if self._wants_grad():
             raise NotImplementedError("vitok_b200.AE: gradients flow through model(batch) (AE.forward) only; call encode/decode "
                                       "under model.eval() or torch.no_grad()")
@@ -352,20 +380,28 @@ class AE(nn.Module):
         want = (self.pixels_per_token if side == 0 else self.channels_per_token)
         if cin != want:
             raise RuntimeError(f"shape mismatch: last dim {cin} != {want}")
-        h = self._ensure_packed(x.device)
-        lib = _lib.load()
-        if x.dtype == torch.float32:
-            xin = _lib.cast_to_bf16(x)
-        elif x.dtype == torch.bfloat16:
-            xin = x.contiguous()
-        else:
+        if x.dtype not in (torch.float32, torch.bfloat16):
             raise RuntimeError(f"vitok_b200.AE: unsupported input dtype {x.dtype} (float32 or bfloat16)")
         row, col = d["row_idx"], d["col_idx"]
-        row = row.to(device=x.device, dtype=torch.int64).contiguous()
-        col = col.to(device=x.device, dtype=torch.int64).contiguous()
         if row.shape != (B, N) or col.shape != (B, N):
             raise ValueError("x_positions and y_positions must have matching shapes [B, N]")
         mask = d.get("patch_mask") if self.attn_backend == "sdpa" else None
+        return torch.ops.vitok_b200.ae_run(self._model_id, side, x, row, col, mask)
+
+    def _out_dtype(self) -> torch.dtype:
+        pdtype = next(self.parameters()).dtype
+        return torch.float32 if (pdtype == torch.float32 and not torch.is_autocast_enabled()) else torch.bfloat16
+
+    def _run_native(self, side: int, x: torch.Tensor, row: torch.Tensor, col: torch.Tensor,
+                    mask: Optional[torch.Tensor]) -> torch.Tensor:
+        """The body of ``vitok_b200::ae_run``: weight packing check, workspace, and the vtk_ae_encode / vtk_ae_decode call."""
+        B, N, _ = x.shape
+        out_cols = self.channels_per_token if side == 0 else self.pixels_per_token
+        h = self._ensure_packed(x.device)
+        lib = _lib.load()
+        xin = _lib.cast_to_bf16(x) if x.dtype == torch.float32 else x.contiguous()
+        row = row.to(device=x.device, dtype=torch.int64).contiguous()
+        col = col.to(device=x.device, dtype=torch.int64).contiguous()
         m8 = None
         if mask is not None:
             m8 = mask.to(device=x.device).bool().contiguous().view(torch.uint8)
@@ -377,8 +413,7 @@ class AE(nn.Module):
         _lib.check(fn(h, xin.data_ptr(), row.data_ptr(), col.data_ptr(), m8.data_ptr() if m8 is not None else None,
                       B, N, out.data_ptr(), ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()), _lib.stream_ptr()))
         self.last_launch_count = lib.vtk_ae_last_launch_count(h)
-        pdtype = next(self.parameters()).dtype
-        if pdtype == torch.float32 and not torch.is_autocast_enabled():
+        if self._out_dtype() == torch.float32:
             out = out.float()
         return out
 
