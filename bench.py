@@ -452,9 +452,15 @@ def run_train(args, rank, world, local):
         model = vb.AE(**cfg, attn_backend=backend)
     model = model.to(torch.bfloat16).train()
     net = model
+    sync_mode = "none"
     if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        net = DDP(model, device_ids=[local], static_graph=True, gradient_as_bucket_view=True)
+        if os.environ.get("VTK_TRAIN_DDP", "0") == "1":     # torch DDP (what scripts/train_vae.py:172 uses): all-reduce after backward
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            net = DDP(model, device_ids=[local], static_graph=True, gradient_as_bucket_view=True)
+            sync_mode = "torch DDP"
+        else:                                                # all-reduce issued per block from inside the backward loop
+            vb.enable_grad_sync(model)
+            sync_mode = "overlapped NCCL all-reduce (vb.enable_grad_sync)"
     decay = [p for n, p in model.named_parameters() if not (p.ndim <= 1 or "bias" in n or "norm" in n or "embedding" in n)]
     no_decay = [p for n, p in model.named_parameters() if (p.ndim <= 1 or "bias" in n or "norm" in n or "embedding" in n)]
     opt = vb.FusedAdamW([{"params": decay, "weight_decay": 0.01}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-4, betas=(0.9, 0.99))
@@ -497,7 +503,7 @@ def run_train(args, rank, world, local):
         "warmup": max(args.warmup, 1), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {variant} training step @{res}px, batch {B}/GPU, Charbonnier + AdamW"
-                               + (", DDP all-reduce over NCCL" if world > 1 else ""),
+                               + (f", gradient sync: {sync_mode}" if world > 1 else ""),
                    "variant": variant, "resolution": res, "tokens_per_image": N, "batch_per_gpu": B, "global_batch": B * world,
                    "attn_backend": backend, "gflop_per_image_fwd_bwd": gf},
         "model_tflops": value * gf / 1e3 / world, "model_frac_of_peak": value * gf / 1e3 / world / pk["bf16_sustained"],

@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define VTK_ABI_VERSION 2
+#define VTK_ABI_VERSION 3
 
 typedef enum {
   VTK_OK = 0,
@@ -146,7 +146,8 @@ int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_q
 int vtk_qk_norm_rope_fwd(const void* zraw, int64_t ldz, const void* norm_q, const void* norm_k, const void* rope_table,
                          void* qkv, int64_t ld_qkv, int M, int heads, int d, float eps, void* stream);
 /* zraw[:, qp:] (16-col groups value|gate, the packed fc1 order) -> act [M,Hf] = silu(g) * v (modules/mlp.py:21-22) */
-int vtk_swiglu_fwd(const void* zraw, int64_t ldz, int qp, void* act, int64_t ld_act, int M, int Hf, void* stream);
+/* layout: 0 = 16-column (value16 | gate16) groups (the packed w_in of the inference path), 1 = [value Hf | gate Hf] (fc1 rows as stored) */
+int vtk_swiglu_fwd(const void* zraw, int64_t ldz, int qp, void* act, int64_t ld_act, int M, int Hf, int layout, void* stream);
 /* out = x + gamma * y (vitok/models/ae.py:64-65); contiguous [M,D] */
 int vtk_resid_fwd(const void* x, const void* y, const void* gamma, void* out, int M, int D, void* stream);
 /* out = LayerNorm_noaffine(x) over C <= 256 (modules/norm.py:28-39) */
@@ -156,7 +157,7 @@ int vtk_resid_bwd(const void* dx, const void* y, const void* gamma, void* dy, fl
 /* out[C] += colsum(in [M,C]) (bias gradients) */
 int vtk_colsum(const void* in, int64_t ld, float* out, int M, int C, void* stream);
 /* d_act [M,Hf] + zraw -> dz[:, qp:] in the packed (value|gate) order */
-int vtk_swiglu_bwd(const void* dact, int64_t ldd, const void* zraw, int64_t ldz, int qp, void* dz, int64_t lddz, int M, int Hf,
+int vtk_swiglu_bwd(const void* dact, int64_t ldd, const void* zraw, int64_t ldz, int qp, void* dz, int64_t lddz, int M, int Hf, int layout,
                    void* stream);
 /* in place on dz[:, 0:2D] (dq|dk w.r.t. roped q/k) -> gradient w.r.t. raw q/k; dw [2][d] fp32 += norm_q / norm_k grads */
 int vtk_qk_norm_rope_bwd(void* dz, int64_t lddz, const void* zraw, int64_t ldz, const void* norm_q, const void* norm_k,

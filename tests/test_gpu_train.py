@@ -102,7 +102,7 @@ def test_swiglu_fwd_bwd(L):
     zraw = torch.zeros(M, qp + 2 * Hf, dtype=BF, device="cuda")
     zraw[:, qp:] = u.view(M, 2, Hf // 16, 16).permute(0, 2, 1, 3).reshape(M, 2 * Hf)
     act = torch.empty(M, Hf, dtype=BF, device="cuda")
-    L.check(L.load().vtk_swiglu_fwd(zraw.data_ptr(), qp + 2 * Hf, qp, act.data_ptr(), Hf, M, Hf, L.stream_ptr()))
+    L.check(L.load().vtk_swiglu_fwd(zraw.data_ptr(), qp + 2 * Hf, qp, act.data_ptr(), Hf, M, Hf, 0, L.stream_ptr()))
     uc = u.float().cpu().requires_grad_(True)
     val, gate = uc.chunk(2, dim=-1)
     ref = F.silu(gate) * val
@@ -110,9 +110,18 @@ def test_swiglu_fwd_bwd(L):
     dact = bf16_randn(M, Hf, seed=60)
     (ref * dact.float().cpu()).sum().backward()
     dz = torch.zeros_like(zraw)
-    L.check(L.load().vtk_swiglu_bwd(dact.data_ptr(), Hf, zraw.data_ptr(), qp + 2 * Hf, qp, dz.data_ptr(), qp + 2 * Hf, M, Hf, L.stream_ptr()))
+    L.check(L.load().vtk_swiglu_bwd(dact.data_ptr(), Hf, zraw.data_ptr(), qp + 2 * Hf, qp, dz.data_ptr(), qp + 2 * Hf, M, Hf, 0, L.stream_ptr()))
     du = dz[:, qp:].view(M, Hf // 16, 2, 16).permute(0, 2, 1, 3).reshape(M, 2 * Hf)
     report("swiglu bwd", du, uc.grad, rel_fro=6e-3)
+    # layout 1: fc1's own column order [value Hf | gate Hf] (training path, no weight repack) -- same numbers
+    zplain = torch.zeros(M, qp + 2 * Hf, dtype=BF, device="cuda")
+    zplain[:, qp:] = u
+    act1 = torch.empty(M, Hf, dtype=BF, device="cuda")
+    L.check(L.load().vtk_swiglu_fwd(zplain.data_ptr(), qp + 2 * Hf, qp, act1.data_ptr(), Hf, M, Hf, 1, L.stream_ptr()))
+    assert torch.equal(act1, act)
+    dz1 = torch.zeros_like(zplain)
+    L.check(L.load().vtk_swiglu_bwd(dact.data_ptr(), Hf, zplain.data_ptr(), qp + 2 * Hf, qp, dz1.data_ptr(), qp + 2 * Hf, M, Hf, 1, L.stream_ptr()))
+    assert torch.equal(dz1[:, qp:], du)
 
 
 @pytest.mark.parametrize("M,D", [(100, 256), (64, 1024), (40, 3072)])

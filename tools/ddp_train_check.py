@@ -83,6 +83,29 @@ def main():
     assert losses[-1] < losses[0]
     if rank == 0:
         print(f"ddp_train_check OK: world={world} worst grad rel err vs hand-made mean {worst:.3e}; loss {losses[0]:.4f} -> {losses[-1]:.4f}")
+
+    # ---- the same step with vb.enable_grad_sync (all-reduce issued from inside the backward loop, no DDP wrapper) ----
+    torch.manual_seed(1 + rank)                      # different initial parameters per rank: the broadcast must fix that
+    m2 = vb.AE(**cfg, attn_backend="flash").train().to(dev, torch.bfloat16)
+    vb.enable_grad_sync(m2)
+    for (n, p), (_, q) in zip(m2.named_parameters(), twin.named_parameters()):
+        lst = [torch.zeros_like(p.data) for _ in range(world)]
+        dist.all_gather(lst, p.data.contiguous())
+        assert all(torch.equal(x, lst[0]) for x in lst), f"{n}: broadcast_parameters left ranks different"
+    m2.load_state_dict(twin.state_dict())            # same weights as the hand-made reference above
+    loss = vb.charbonnier_loss(m2(pd)["patches"], pd["patches"], pd["patch_mask"])
+    loss.backward()
+    worst2 = 0.0
+    for n, p in m2.named_parameters():
+        ref = local_g[n]
+        worst2 = max(worst2, float((p.grad.float() - ref).norm() / ref.norm().clamp_min(1e-30)))
+        chk = p.grad.float().sum().double().reshape(1)
+        lst = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        assert all(float(x) == float(lst[0]) for x in lst), f"{n}: overlapped-sync gradients differ across ranks"
+    assert worst2 < 2e-2, worst2
+    if rank == 0:
+        print(f"grad_sync (overlapped all-reduce) OK: worst grad rel err vs hand-made mean {worst2:.3e}")
     dist.destroy_process_group()
 
 

@@ -358,9 +358,10 @@ int vtk_qk_norm_rope_fwd(const void* zraw, int64_t ldz, const void* norm_q, cons
   return launch_qk_norm_rope_fwd((const bf16*)zraw, ldz, (const bf16*)norm_q, (const bf16*)norm_k, (const bf16*)rope_table,
                                  (bf16*)qkv, ld_qkv, M, heads, d, eps, (cudaStream_t)stream);
 }
-int vtk_swiglu_fwd(const void* zraw, int64_t ldz, int qp, void* act, int64_t ld_act, int M, int Hf, void* stream) {
+int vtk_swiglu_fwd(const void* zraw, int64_t ldz, int qp, void* act, int64_t ld_act, int M, int Hf, int layout, void* stream) {
   VTK_REQUIRE(zraw && act, "vtk_swiglu_fwd: null pointer");
-  return launch_swiglu_fwd((const bf16*)zraw, ldz, qp, (bf16*)act, ld_act, M, Hf, (cudaStream_t)stream);
+  VTK_REQUIRE(layout == 0 || layout == 1, "vtk_swiglu_fwd: layout must be 0 (16-column value|gate groups) or 1 ([value | gate])");
+  return launch_swiglu_fwd((const bf16*)zraw, ldz, qp, (bf16*)act, ld_act, M, Hf, layout, (cudaStream_t)stream);
 }
 int vtk_resid_fwd(const void* x, const void* y, const void* gamma, void* out, int M, int D, void* stream) {
   VTK_REQUIRE(x && y && gamma && out, "vtk_resid_fwd: null pointer");
@@ -378,10 +379,11 @@ int vtk_colsum(const void* in, int64_t ld, float* out, int M, int C, void* strea
   VTK_REQUIRE(in && out, "vtk_colsum: null pointer");
   return launch_colsum((const bf16*)in, ld, out, M, C, (cudaStream_t)stream);
 }
-int vtk_swiglu_bwd(const void* dact, int64_t ldd, const void* zraw, int64_t ldz, int qp, void* dz, int64_t lddz, int M, int Hf,
+int vtk_swiglu_bwd(const void* dact, int64_t ldd, const void* zraw, int64_t ldz, int qp, void* dz, int64_t lddz, int M, int Hf, int layout,
                    void* stream) {
   VTK_REQUIRE(dact && zraw && dz, "vtk_swiglu_bwd: null pointer");
-  return launch_swiglu_bwd((const bf16*)dact, ldd, (const bf16*)zraw, ldz, qp, (bf16*)dz, lddz, M, Hf, (cudaStream_t)stream);
+  VTK_REQUIRE(layout == 0 || layout == 1, "vtk_swiglu_bwd: layout must be 0 or 1");
+  return launch_swiglu_bwd((const bf16*)dact, ldd, (const bf16*)zraw, ldz, qp, (bf16*)dz, lddz, M, Hf, layout, (cudaStream_t)stream);
 }
 int vtk_qk_norm_rope_bwd(void* dz, int64_t lddz, const void* zraw, int64_t ldz, const void* norm_q, const void* norm_k,
                          const void* rope_table, float* dw, int M, int heads, int d, float eps, void* stream) {

@@ -176,13 +176,13 @@ int launch_grid_extent(const uint8_t* mask, const int64_t* row, const int64_t* c
 // ---------------------------------------------------------------------------------------------
 int launch_qk_norm_rope_fwd(const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk, const bf16* rope, bf16* qkv,
                             long long ldq, int M, int heads, int d, float eps, cudaStream_t st);
-int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long long lda, int M, int Hf, cudaStream_t st);
+int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long long lda, int M, int Hf, int layout, cudaStream_t st);
 int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st);
 int launch_ln_fwd(const bf16* x, bf16* out, int M, int C, float eps, cudaStream_t st);
 int launch_resid_bwd(const bf16* dx, const bf16* y, const bf16* gamma, bf16* dy, float* dgamma, int M, int D, cudaStream_t st);
 int launch_colsum(const bf16* in, long long ld, float* out, int M, int C, cudaStream_t st);
 int launch_swiglu_bwd(const bf16* dact, long long ldd, const bf16* zraw, long long ldz, int qp, bf16* dz, long long lddz, int M,
-                      int Hf, cudaStream_t st);
+                      int Hf, int layout, cudaStream_t st);
 int launch_qk_norm_rope_bwd(bf16* dz, long long lddz, const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk,
                             const bf16* rope, float* dw, int M, int heads, int d, float eps, cudaStream_t st);
 int launch_rmsnorm_bwd(const bf16* x, const bf16* dh, const bf16* w, const bf16* dx_res, bf16* dx_out, float* dw, int M, int D,

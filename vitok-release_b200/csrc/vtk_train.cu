@@ -90,18 +90,24 @@ __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(const bf16* __res
   }
 }
 
-// zraw[:, qp:] = 16-column groups (value16 | gate16) -> act [M, Hf] = bf16(bf16(silu(g)) * v)
+// zraw[:, qp:] -> act [M, Hf] = bf16(bf16(silu(g)) * v).  layout 0: 16-column groups (value16 | gate16) -- the packed
+// w_in of the inference path; layout 1: [value Hf | gate Hf], fc1's own row order (training: no weight repack).
+__device__ __forceinline__ void swiglu_cols(int o, int qp, int Hf, int layout, long long& voff, long long& goff) {
+  if (layout == 0) { voff = qp + ((o >> 4) << 5) + (o & 8); goff = voff + 16; }
+  else { voff = qp + o; goff = voff + Hf; }
+}
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ zraw, long long ldz, int qp,
-                                                         bf16* __restrict__ act, long long lda, int M, int Hf) {
+                                                         bf16* __restrict__ act, long long lda, int M, int Hf, int layout) {
   const int vec_per_row = Hf >> 3;
   const long long total = (long long)M * vec_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / vec_per_row);
     const int o = (int)(i - (long long)m * vec_per_row) << 3;   // first of 8 output columns
-    const bf16* zp = zraw + (long long)m * ldz + qp + ((o >> 4) << 5) + (o & 8);
+    long long voff, goff;
+    swiglu_cols(o, qp, Hf, layout, voff, goff);
     float v[8], g[8], r[8];
-    unpack8(ld_global_nc_v4(zp), v);
-    unpack8(ld_global_nc_v4(zp + 16), g);
+    unpack8(ld_global_nc_v4(zraw + (long long)m * ldz + voff), v);
+    unpack8(ld_global_nc_v4(zraw + (long long)m * ldz + goff), g);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float s = bf16r(g[k] * (1.f / (1.f + __expf(-g[k]))));
@@ -221,16 +227,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ in
 // dz[:, qp:] in the same packed order:  d_val = d_act * silu(g),  d_gate = d_act * val * sig(g) * (1 + g * (1 - sig(g)))
 __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dact, long long ldd,
                                                          const bf16* __restrict__ zraw, long long ldz, int qp,
-                                                         bf16* __restrict__ dz, long long lddz, int M, int Hf) {
+                                                         bf16* __restrict__ dz, long long lddz, int M, int Hf, int layout) {
   const int vec_per_row = Hf >> 3;
   const long long total = (long long)M * vec_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / vec_per_row);
     const int o = (int)(i - (long long)m * vec_per_row) << 3;
-    const long long zoff = qp + ((o >> 4) << 5) + (o & 8);
+    long long zoff, goff;
+    swiglu_cols(o, qp, Hf, layout, zoff, goff);
     float v[8], g[8], d[8], dv[8], dg[8];
     unpack8(ld_global_nc_v4(zraw + (long long)m * ldz + zoff), v);
-    unpack8(ld_global_nc_v4(zraw + (long long)m * ldz + zoff + 16), g);
+    unpack8(ld_global_nc_v4(zraw + (long long)m * ldz + goff), g);
     unpack8(ld_global_nc_v4(dact + (long long)m * ldd + o), d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict_
       dg[k] = d[k] * v[k] * sg * (1.f + g[k] * (1.f - sg));
     }
     *reinterpret_cast<uint4*>(dz + (long long)m * lddz + zoff) = pack8(dv);
-    *reinterpret_cast<uint4*>(dz + (long long)m * lddz + zoff + 16) = pack8(dg);
+    *reinterpret_cast<uint4*>(dz + (long long)m * lddz + goff) = pack8(dg);
   }
 }
 
@@ -518,18 +525,44 @@ __global__ void __launch_bounds__(256) charbonnier_kernel(const bf16* __restrict
 
 // fused AdamW on bf16 params / grads / moments with fp32 math (torch.optim.AdamW(fused=True) semantics):
 //   p *= 1 - lr * wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+__device__ __forceinline__ void adamw_one(float& pf, float gf, float& mf, float& vf, float lr, float b1, float b2, float eps,
+                                          float wd, float bc1, float bc2_sqrt) {
+  pf *= 1.f - lr * wd;
+  mf = b1 * mf + (1.f - b1) * gf;
+  vf = b2 * vf + (1.f - b2) * gf * gf;
+  const float denom = sqrtf(vf) / bc2_sqrt + eps;
+  pf -= (lr / bc1) * (mf / denom);
+}
+
+// 8 elements (16 bytes of each of p, g, m, v) per thread and iteration: 4 coalesced 16-byte loads, 3 stores -- the optimizer
+// step is pure HBM streaming (14 bytes per parameter).  VEC = false: scalar fallback for unaligned / short tensors.
+template <bool VEC>
 __global__ void __launch_bounds__(256) adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __restrict__ m,
                                                     bf16* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                     float wd, float bc1, float bc2_sqrt, float grad_scale) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long done = 0;
+  if (VEC) {
+    const long long nvec = n >> 3;
+    for (long long i = tid; i < nvec; i += stride) {
+      const uint4 pq = ld_global_v4(p + 8 * i), gq = ld_global_nc_v4(g + 8 * i), mq = ld_global_v4(m + 8 * i), vq = ld_global_v4(v + 8 * i);
+      float pf[8], gf[8], mf[8], vf[8];
+      unpack8(pq, pf); unpack8(gq, gf); unpack8(mq, mf); unpack8(vq, vf);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) adamw_one(pf[k], gf[k] * grad_scale, mf[k], vf[k], lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      const uint4 po = pack8(pf), mo = pack8(mf), vo = pack8(vf);
+      st_global_v4(p + 8 * i, po.x, po.y, po.z, po.w);
+      st_global_v4(m + 8 * i, mo.x, mo.y, mo.z, mo.w);
+      st_global_v4(v + 8 * i, vo.x, vo.y, vo.z, vo.w);
+    }
+    done = nvec << 3;
+  }
+  for (long long i = done + tid; i < n; i += stride) {
     float pf = __bfloat162float(p[i]);
     const float gf = __bfloat162float(g[i]) * grad_scale;
     float mf = __bfloat162float(m[i]), vf = __bfloat162float(v[i]);
-    pf *= 1.f - lr * wd;
-    mf = b1 * mf + (1.f - b1) * gf;
-    vf = b2 * vf + (1.f - b2) * gf * gf;
-    const float denom = sqrtf(vf) / bc2_sqrt + eps;
-    pf -= (lr / bc1) * (mf / denom);
+    adamw_one(pf, gf, mf, vf, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
     p[i] = __float2bfloat16_rn(pf);
     m[i] = __float2bfloat16_rn(mf);
     v[i] = __float2bfloat16_rn(vf);
@@ -579,10 +612,10 @@ int launch_qk_norm_rope_fwd(const bf16* zraw, long long ldz, const bf16* wq, con
   else qk_norm_rope_fwd_kernel<128><<<grid, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
   return check_cuda(cudaGetLastError(), "qk_norm_rope_fwd launch");
 }
-int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long long lda, int M, int Hf, cudaStream_t st) {
+int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long long lda, int M, int Hf, int layout, cudaStream_t st) {
   VTK_TRAIN_CHECK(Hf % 16 == 0 && lda % 8 == 0 && ldz % 8 == 0, "swiglu: Hf %% 16 and strides %% 8 required");
   if (M <= 0) return 0;
-  swiglu_fwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(zraw, ldz, qp, act, lda, M, Hf);
+  swiglu_fwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(zraw, ldz, qp, act, lda, M, Hf, layout);
   return check_cuda(cudaGetLastError(), "swiglu_fwd launch");
 }
 int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st) {
@@ -612,10 +645,10 @@ int launch_colsum(const bf16* in, long long ld, float* out, int M, int C, cudaSt
   return check_cuda(cudaGetLastError(), "colsum launch");
 }
 int launch_swiglu_bwd(const bf16* dact, long long ldd, const bf16* zraw, long long ldz, int qp, bf16* dz, long long lddz, int M,
-                      int Hf, cudaStream_t st) {
+                      int Hf, int layout, cudaStream_t st) {
   VTK_TRAIN_CHECK(Hf % 16 == 0 && ldd % 8 == 0 && ldz % 8 == 0 && lddz % 8 == 0, "swiglu_bwd: Hf %% 16 and strides %% 8 required");
   if (M <= 0) return 0;
-  swiglu_bwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(dact, ldd, zraw, ldz, qp, dz, lddz, M, Hf);
+  swiglu_bwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(dact, ldd, zraw, ldz, qp, dz, lddz, M, Hf, layout);
   return check_cuda(cudaGetLastError(), "swiglu_bwd launch");
 }
 int launch_qk_norm_rope_bwd(bf16* dz, long long lddz, const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk,
@@ -667,7 +700,10 @@ int launch_adamw(bf16* p, const bf16* g, bf16* m, bf16* v, long long n, float lr
   if (n <= 0) return 0;
   VTK_TRAIN_CHECK(step >= 1, "adamw: step must be >= 1");
   const float bc1 = 1.f - powf(b1, (float)step), bc2s = sqrtf(1.f - powf(b2, (float)step));
-  adamw_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0 && n >= 8;
+  if (vec) adamw_kernel<true><<<grid_for((n + 7) / 8, 256, 8), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
+  else adamw_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
   return check_cuda(cudaGetLastError(), "adamw launch");
 }
 int launch_attn_delta(const bf16* o, long long ldo, const bf16* dob, long long lddo, float* delta, int M, int heads, int d,

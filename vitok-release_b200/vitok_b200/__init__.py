@@ -10,9 +10,9 @@ from .pp import (OPS, build_transform, pack_images, parse_op, patchify_batch, pa
                  unpack, unpatchify)
 from .data import patch_collate_fn
 from .pretrained import list_pretrained, load_pretrained, save_pretrained
-from .train import FusedAdamW, charbonnier_loss
+from .train import FusedAdamW, charbonnier_loss, enable_grad_sync
 
 __version__ = "0.1.0"
 __all__ = ["AE", "Model", "decode_variant", "build_transform", "parse_op", "OPS", "patch_collate_fn", "preprocess",
-           "postprocess", "unpatchify", "unpack", "patchify_batch", "pack_images", "patchify_packed", "charbonnier_loss", "FusedAdamW", "load_pretrained", "list_pretrained",
+           "postprocess", "unpatchify", "unpack", "patchify_batch", "pack_images", "patchify_packed", "charbonnier_loss", "FusedAdamW", "enable_grad_sync", "load_pretrained", "list_pretrained",
            "save_pretrained"]

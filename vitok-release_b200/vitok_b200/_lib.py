@@ -58,12 +58,12 @@ SIGNATURES = {
     "vtk_attention_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_vp, c_vp]),
     "vtk_qk_norm_rope_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
-    "vtk_swiglu_fwd": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
+    "vtk_swiglu_fwd": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_resid_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "vtk_layernorm_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
     "vtk_resid_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "vtk_colsum": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, c_vp]),
-    "vtk_swiglu_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
+    "vtk_swiglu_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_qk_norm_rope_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp]),
     "vtk_rmsnorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
     "vtk_layernorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),

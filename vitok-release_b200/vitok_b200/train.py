@@ -60,18 +60,117 @@ def _colsum(x: torch.Tensor, ld: int, M: int, C: int) -> torch.Tensor:
     return out
 
 
+class _GradSync:
+    """Data-parallel gradient averaging overlapped with the backward loop.
+
+    torch DDP (scripts/train_vae.py:172) also works with this model, but because ``model(batch)`` is ONE autograd node
+    all gradients reach DDP's reducer together, after the last backward kernel, and the 10 GB all-reduce of the 5B
+    model runs un-overlapped.  With ``enable_grad_sync(model)`` the backward loop itself issues an NCCL all-reduce
+    (AVG) for each block's weight gradients as soon as its wgrad GEMMs are queued -- NCCL runs them on its own stream
+    while the next block's kernels execute -- and the remaining small tensors go out as one flat bucket at the end.
+    The gradients autograd hands to the optimizer are already averaged.
+    """
+
+    def __init__(self, group=None, min_numel: int = 1 << 16):
+        import torch.distributed as dist
+        self.dist, self.group, self.min_numel = dist, group, min_numel
+        self.world = dist.get_world_size(group)
+        self.pending, self.small = [], []
+
+    def reduce(self, t: torch.Tensor) -> None:
+        if self.world == 1:
+            return
+        if t.numel() >= self.min_numel and t.is_contiguous():
+            self.pending.append(self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:
+            self.small.append(t)
+
+    def finish(self, named: Dict[str, torch.Tensor]) -> None:
+        """Average everything not yet reduced (small or strided tensors) as one flat fp32 bucket, then make the
+        current stream wait for every outstanding all-reduce."""
+        if self.world == 1:
+            return
+        seen = {id(t) for t in self.small}
+        rest = list(self.small) + [t for t in named.values() if t is not None and not getattr(t, "_vtk_reduced", False)
+                                   and id(t) not in seen]
+        if rest:
+            flat = torch.cat([t.reshape(-1).float() for t in rest])
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.group)
+            off = 0
+            for t in rest:
+                t.copy_(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
+        for w in self.pending:
+            w.wait()
+        self.pending, self.small = [], []
+
+
+def enable_grad_sync(model, process_group=None, broadcast_parameters: bool = True):
+    """Turn on overlapped data-parallel gradient averaging for ``model`` (see _GradSync).  Call once after
+    ``torch.distributed.init_process_group``; do NOT also wrap the model in DistributedDataParallel.  With
+    ``broadcast_parameters`` the parameters of rank 0 are copied to every rank first (what DDP's constructor does)."""
+    import torch.distributed as dist
+    if broadcast_parameters and dist.get_world_size(process_group) > 1:
+        with torch.no_grad():
+            for p in model.parameters():
+                dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                               group=process_group)
+                torch.autograd.graph.increment_version(p)
+    model._grad_sync_group = (process_group,)
+    return model
+
+
+def _transpose_into(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[:, :] (a [cols, rows] view, any row pitch) = x^T for a [rows, cols] matrix x (row pitch x.stride(0))."""
+    rows, cols = x.shape
+    _check(_lib.load().vtk_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, _lib.stream_ptr()))
+
+
 class _SideWeights:
-    """Packed bf16 weights of one side (encoder / decoder) plus the transposed copies the dgrad GEMMs read."""
+    """bf16 weights of one side (encoder / decoder) as the training kernels read them, built straight from the
+    parameters every step (the optimizer has just changed them):
+      * qkv_proj.weight [3D, D] and fc1.weight [2Hf, D] are used in place -- two forward GEMMs write the column ranges
+        [0, 3D) and [qp, qp + 2Hf) of zraw, so there is no packed / interleaved w_in copy and the wgrad GEMMs write
+        contiguous gradients in the parameters' own row order;
+      * w_out [D, kp] = [out_proj | fc2 | 0-pad] (one forward GEMM over the concatenated K);
+      * transposed copies for the dgrad GEMMs (tiled shared-memory transpose): w_in_t [D, ZP], w_out_t [kp, D].
+    """
 
     def __init__(self, model, side: int):
-        keep = model._packed[side]
-        depth = (len(keep) - 4) // 6
-        self.blocks = [keep[6 * i:6 * i + 6] for i in range(depth)]       # w_in, w_out, norm1, norm_q, norm_k, gamma
-        self.wa, self.ba, self.wb, self.bb = keep[6 * depth:6 * depth + 4]
-        self.w_in_t = [b[0].t().contiguous() for b in self.blocks]         # [D, ZP]
-        self.w_out_t = [b[1].t().contiguous() for b in self.blocks]        # [kp, D]
-        self.wa_t = self.wa.t().contiguous()
-        self.wb_t = self.wb.t().contiguous()
+        from .models.ae import _Scale, _ffn_hidden, pack_w_out
+        sd = {s[0]: s for s in model._sides()}[side]
+        _, lin_a, lin_b, blocks, width, heads = sd
+        dev = lin_a.weight.device
+        D, Hf = width, _ffn_hidden(width, model.mlp_factor)
+        qp = ((3 * D + 255) // 256) * 256
+        ZP, kp = qp + 2 * Hf, (D + Hf + 63) // 64 * 64
+
+        def b16(t):
+            return t.detach().to(BF).contiguous()
+
+        self.blocks = []
+        self.w_in_t, self.w_out_t = [], []
+        for blk in blocks:
+            wqkv, w1 = b16(blk.attn.qkv_proj.weight), b16(blk.ffn.fc1.weight)
+            wo, w2 = b16(blk.attn.out_proj.weight), b16(blk.ffn.fc2.weight)
+            w_out = pack_w_out(wo, w2)
+            w_in_t = torch.empty(D, ZP, dtype=BF, device=dev)
+            if qp > 3 * D:
+                w_in_t[:, 3 * D:qp].zero_()
+            _transpose_into(wqkv, w_in_t[:, :3 * D])
+            _transpose_into(w1, w_in_t[:, qp:])
+            w_out_t = torch.empty(kp, D, dtype=BF, device=dev)
+            if kp > D + Hf:
+                w_out_t[D + Hf:].zero_()
+            _transpose_into(wo, w_out_t[:D])
+            _transpose_into(w2, w_out_t[D:D + Hf])
+            gamma = b16(blk.layer_scale.gamma) if isinstance(blk.layer_scale, _Scale) else torch.ones(D, dtype=BF, device=dev)
+            self.blocks.append((wqkv, w1, w_out, b16(blk.norm1.weight), b16(blk.attn.norm_q.weight), b16(blk.attn.norm_k.weight), gamma))
+            self.w_in_t.append(w_in_t)
+            self.w_out_t.append(w_out_t)
+        self.wa, self.ba, self.wb, self.bb = b16(lin_a.weight), b16(lin_a.bias), b16(lin_b.weight), b16(lin_b.bias)
+        self.wa_t = _transpose(self.wa, self.wa.shape[0], self.wa.shape[1], self.wa.stride(0))
+        self.wb_t = _transpose(self.wb, self.wb.shape[0], self.wb.shape[1], self.wb.stride(0))
 
 
 def _side_forward(lib, model, sw: _SideWeights, side: int, xin: torch.Tensor, row, col, m8, B: int, N: int, saved: Dict):
@@ -101,10 +200,14 @@ def _side_forward(lib, model, sw: _SideWeights, side: int, xin: torch.Tensor, ro
     window = int(model.sw) if (model.sw and m8 is None) else -1
     layers = []
     for blk in sw.blocks:
-        w_in, w_out, n1, nq, nk, gamma = blk
+        wqkv, w1, w_out, n1, nq, nk, gamma = blk
         h = torch.empty(M, D, dtype=BF, device=dev)
         _check(lib.vtk_rmsnorm_bf16(x.data_ptr(), D, n1.data_ptr(), h.data_ptr(), D, M, D, 1e-6, st))
-        zraw = _linear(h, D, w_in, None, M, ZP, D)
+        zraw = torch.empty(M, ZP, dtype=BF, device=dev)       # [q | k | v | pad | fc1 value | fc1 gate]
+        if qp > 3 * D:
+            zraw[:, 3 * D:qp].zero_()
+        _linear(h, D, wqkv, None, M, 3 * D, D, out=zraw[:, :3 * D])
+        _linear(h, D, w1, None, M, 2 * Hf, D, out=zraw[:, qp:])
         qkv = torch.empty(M, 3 * D, dtype=BF, device=dev)
         _check(lib.vtk_qk_norm_rope_fwd(zraw.data_ptr(), ZP, nq.data_ptr(), nk.data_ptr(), rope.data_ptr(), qkv.data_ptr(), 3 * D,
                                         M, heads, d, 1e-6, st))
@@ -116,7 +219,7 @@ def _side_forward(lib, model, sw: _SideWeights, side: int, xin: torch.Tensor, ro
         _check(lib.vtk_attention_bf16(base, base + 2 * D, base + 4 * D, 3 * D, a2.data_ptr(), kp, _lib.ptr(kv),
                                       _lib.ptr(m8), _lib.ptr(pf), B, N, heads, d, 1 if m8 is not None else 0, window,
                                       lse.data_ptr(), st))
-        _check(lib.vtk_swiglu_fwd(zraw.data_ptr(), ZP, qp, a2.data_ptr() + 2 * D, kp, M, Hf, st))
+        _check(lib.vtk_swiglu_fwd(zraw.data_ptr(), ZP, qp, a2.data_ptr() + 2 * D, kp, M, Hf, 1, st))
         y = _linear(a2, kp, w_out, None, M, D, D + Hf)
         x_new = torch.empty(M, D, dtype=BF, device=dev)
         _check(lib.vtk_resid_fwd(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), x_new.data_ptr(), M, D, st))
@@ -127,7 +230,8 @@ def _side_forward(lib, model, sw: _SideWeights, side: int, xin: torch.Tensor, ro
     return x
 
 
-def _side_backward(lib, model, sw: _SideWeights, side: int, dx: torch.Tensor, saved: Dict, B: int, N: int, need_dxin: bool):
+def _side_backward(lib, model, sw: _SideWeights, side: int, dx: torch.Tensor, saved: Dict, B: int, N: int, need_dxin: bool,
+                   sync: Optional[_GradSync] = None):
     """dx = gradient w.r.t. the output of the last block.  Returns (block grads, dW_a, db_a, d_input)."""
     M, D, heads, d, Hf, qp, ZP, kp = saved["dims"]
     st = _lib.stream_ptr()
@@ -135,17 +239,20 @@ def _side_backward(lib, model, sw: _SideWeights, side: int, dx: torch.Tensor, sa
     rope, kv, window = saved["rope"], saved["kv"], saved["window"]
     grads: List[Dict[str, torch.Tensor]] = []
     for li in range(len(sw.blocks) - 1, -1, -1):
-        w_in, w_out, n1, nq, nk, gamma = sw.blocks[li]
+        wqkv, w1, w_out, n1, nq, nk, gamma = sw.blocks[li]
         x, h, zraw, qkv, a2, lse, y = saved["layers"][li]
         dy = torch.empty(M, D, dtype=BF, device=dev)
         dgamma = torch.zeros(D, dtype=torch.float32, device=dev)
         _check(lib.vtk_resid_bwd(dx.data_ptr(), y.data_ptr(), gamma.data_ptr(), dy.data_ptr(), dgamma.data_ptr(), M, D, st))
         da2 = _linear(dy, D, sw.w_out_t[li], None, M, kp, D)                      # [M, kp]: d[attn | act | pad]
-        dw_out = _wgrad(dy, D, D, a2, kp, kp, M)                                  # [D, kp]
+        dyt = _transpose(dy, M, D, D)                                             # [D, M]
+        a2t = _transpose(a2, M, kp, kp)                                           # [kp, M]: rows = [attn | act | pad]
+        dw_o = _linear(dyt, M, a2t[:D], None, D, D, M)                            # out_proj.weight grad [D, D]
+        dw_f2 = _linear(dyt, M, a2t[D:D + Hf], None, D, Hf, M)                    # fc2.weight grad [D, Hf]
         dz = torch.empty(M, ZP, dtype=BF, device=dev)
         if qp > 3 * D:
             dz[:, 3 * D:qp].zero_()
-        _check(lib.vtk_swiglu_bwd(da2.data_ptr() + 2 * D, kp, zraw.data_ptr(), ZP, qp, dz.data_ptr(), ZP, M, Hf, st))
+        _check(lib.vtk_swiglu_bwd(da2.data_ptr() + 2 * D, kp, zraw.data_ptr(), ZP, qp, dz.data_ptr(), ZP, M, Hf, 1, st))
         delta = torch.empty(M, heads, dtype=torch.float32, device=dev)
         _check(lib.vtk_attn_delta(a2.data_ptr(), kp, da2.data_ptr(), kp, delta.data_ptr(), M, heads, d, st))
         qb, zb = qkv.data_ptr(), dz.data_ptr()
@@ -156,16 +263,22 @@ def _side_backward(lib, model, sw: _SideWeights, side: int, dx: torch.Tensor, sa
         _check(lib.vtk_qk_norm_rope_bwd(dz.data_ptr(), ZP, zraw.data_ptr(), ZP, nq.data_ptr(), nk.data_ptr(), rope.data_ptr(),
                                         dwqk.data_ptr(), M, heads, d, 1e-6, st))
         dh = _linear(dz, ZP, sw.w_in_t[li], None, M, D, ZP)
-        dw_in = _wgrad(dz, ZP, ZP, h, D, D, M)                                    # [ZP, D]
+        dzt = _transpose(dz, M, ZP, ZP)                                           # [ZP, M]
+        ht = _transpose(h, M, D, D)                                               # [D, M]
+        dw_qkv = _linear(dzt, M, ht, None, 3 * D, D, M)                           # qkv_proj.weight grad [3D, D]
+        dw_fc1 = _linear(dzt[qp:], M, ht, None, 2 * Hf, D, M)                     # fc1.weight grad [2Hf, D], fc1's own row order
         dx_in = torch.empty(M, D, dtype=BF, device=dev)
         dw1 = torch.zeros(D, dtype=torch.float32, device=dev)
         _check(lib.vtk_rmsnorm_bwd(x.data_ptr(), dh.data_ptr(), n1.data_ptr(), dx.data_ptr(), dx_in.data_ptr(), dw1.data_ptr(),
                                    M, D, 1e-6, st))
-        grads.append(dict(
-            qkv=dw_in[:3 * D],
-            fc1=dw_in[qp:].view(Hf // 16, 2, 16, D).permute(1, 0, 2, 3).reshape(2 * Hf, D),   # undo the 16-row interleave
-            out=dw_out[:, :D], fc2=dw_out[:, D:D + Hf],
-            norm1=dw1, norm_q=dwqk[0], norm_k=dwqk[1], gamma=dgamma))
+        bg = dict(
+            qkv=dw_qkv, fc1=dw_fc1, out=dw_o, fc2=dw_f2,
+            norm1=dw1, norm_q=dwqk[0], norm_k=dwqk[1], gamma=dgamma)
+        if sync is not None:          # this block's big gradients leave for the all-reduce while the next block computes
+            for k in ("qkv", "fc1", "out", "fc2"):
+                sync.reduce(bg[k])
+                bg[k]._vtk_reduced = True
+        grads.append(bg)
         dx = dx_in
     grads.reverse()
     xin = saved["xin"]
@@ -186,7 +299,6 @@ class AETrainFunction(torch.autograd.Function):
         dev = patches.device
         if (B * N) % 8:
             raise ValueError("vitok_b200 training: B * N must be a multiple of 8 (token count is the K dimension of the wgrad GEMMs)")
-        model._ensure_packed(dev, fold_norm=False)
         enc_w, dec_w = _SideWeights(model, 0), _SideWeights(model, 1)
         row = row.to(device=dev, dtype=torch.int64).contiguous()
         col = col.to(device=dev, dtype=torch.int64).contiguous()
@@ -219,7 +331,9 @@ class AETrainFunction(torch.autograd.Function):
         g["to_pixels.weight"] = _wgrad(dout, P, P, xd, Dd, Dd, M)
         g["to_pixels.bias"] = _colsum(dout, P, M, P)
         dx = _linear(dout, P, dec_w.wb_t, None, M, Dd, P)
-        blocks, dwa, dba, dz = _side_backward(lib, model, dec_w, 1, dx, ctx.s_dec, B, N, True)
+        grp = getattr(model, "_grad_sync_group", None)
+        sync = _GradSync(grp[0]) if grp is not None else None
+        blocks, dwa, dba, dz = _side_backward(lib, model, dec_w, 1, dx, ctx.s_dec, B, N, True, sync)
         g["decoder_embed.weight"], g["decoder_embed.bias"] = dwa, dba
         for i, bg in enumerate(blocks):
             _name_block(g, f"decoder_blocks.{i}.", bg)
@@ -231,10 +345,12 @@ class AETrainFunction(torch.autograd.Function):
         g["to_code.weight"] = _wgrad(dzlin, C, C, xe, De, De, M)
         g["to_code.bias"] = _colsum(dzlin, C, M, C)
         dx = _linear(dzlin, C, enc_w.wb_t, None, M, De, C)
-        blocks, dwa, dba, _ = _side_backward(lib, model, enc_w, 0, dx, ctx.s_enc, B, N, False)
+        blocks, dwa, dba, _ = _side_backward(lib, model, enc_w, 0, dx, ctx.s_enc, B, N, False, sync)
         g["patch_embed.weight"], g["patch_embed.bias"] = dwa, dba
         for i, bg in enumerate(blocks):
             _name_block(g, f"encoder_blocks.{i}.", bg)
+        if sync is not None:
+            sync.finish(g)
         grads = []
         for name, dt in zip(ctx.names, ctx.param_dtypes):
             t = g.get(name)
