@@ -15,6 +15,9 @@
 //   dQ += dS K                 : A = dS K-major, B = K_j MN-major
 // The step loop is not software-pipelined (one tile pair in flight); S/dP recomputation makes it 7 MMAs per
 // tile pair instead of the minimal 5.  Attention is ~5 % of the step's FLOPs at config 5.
+// Two compute warpgroups (warps 0-3 and 8-11) split every [128 x 128] S / dP tile by columns (64 keys each; a warp may
+// only read the TMEM lanes of its quarter, so both groups own the same rows), which halves the P / dS latency that
+// sits between the two MMA groups; tiles that need no masking skip the per-element key test.
 #include <math.h>
 #include <stdio.h>
 
@@ -54,8 +57,42 @@ struct BwdParams {
   float scale, scale_log2;
 };
 
+// P and dS of one 32-key chunk of a row: P = exp2(S * scale*log2e - lse), dS = P * (dP - delta) * scale, written as bf16
+// into the row's 128B-swizzled slots.  MASKED = false: every key of the chunk is live (no per-element test).
+template <int MODE, bool MASKED>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&sv)[32], const uint32_t (&dv)[32], float lse_r, float delta_r,
+                                          float scale_log2, float scale, int kc0, int kvlen, int W, int qi, uint8_t* prow,
+                                          uint8_t* dsrow, int c, int r) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t pp[4], dd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float pv[2], dsv[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * g + 2 * i + e;
+        float pe = ex2_approx_bwd(fmaf(__uint_as_float(sv[col]), scale_log2, -lse_r));
+        if (MASKED) {
+          const int kc = kc0 + col;
+          const bool ok = kc < kvlen && (W < 0 || abs(kc - qi) <= W);
+          pe = ok ? pe : 0.f;
+        }
+        pv[e] = pe;
+        dsv[e] = pe * (__uint_as_float(dv[col]) - delta_r) * scale;
+      }
+      pp[i] = bf2_cvt(pv[0], pv[1]);
+      dd[i] = bf2_cvt(dsv[0], dsv[1]);
+    }
+    const int gg = c * 4 + g;   // 16-byte chunk index along the 128 keys
+    const int blk = gg >> 3, ch = (gg & 7) ^ (r & 7);
+    if (MODE == 0) *reinterpret_cast<uint4*>(prow + blk * BWD_BLK + (ch << 4)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+    *reinterpret_cast<uint4*>(dsrow + blk * BWD_BLK + (ch << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+  }
+}
+
 template <int DH, int MODE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
   using S = BwdShape<DH>;
@@ -116,13 +153,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* str_full = bars + 1;   // streamed tiles of this step landed
   uint64_t* str_free = bars + 2;   // second MMA group of this step has read the streamed tiles (+ P / dS)
   uint64_t* sdp_full = bars + 3;   // S and dP of this step are in TMEM
-  uint64_t* sdp_free = bars + 4;   // count 128: threads have pulled S / dP into registers
-  uint64_t* pds_full = bars + 5;   // count 128: P and dS of this step are in smem
+  uint64_t* sdp_free = bars + 4;   // count 256: threads have pulled S / dP into registers
+  uint64_t* pds_full = bars + 5;   // count 256: P and dS of this step are in smem
   uint64_t* acc_done = bars + 6;   // all MMAs finished (epilogue)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   if (warp == 4) {
-    if (lane < 7) mbar_init(&bars[lane], (lane == 4 || lane == 5) ? 128u : 1u);
+    if (lane < 7) mbar_init(&bars[lane], (lane == 4 || lane == 5) ? 256u : 1u);
     else if (lane == 8) tma_prefetch_desc(&tmQ);
     else if (lane == 9) tma_prefetch_desc(&tmK);
     else if (lane == 10) tma_prefetch_desc(&tmV);
@@ -213,8 +250,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       umma_commit(acc_done);
     }
-  } else {
-    // ===== compute warps: thread <-> query row of the current query tile =====
+  } else if (warp < 4 || warp >= 8) {
+    // ===== compute warps: thread <-> query row of the current query tile; column half = warpgroup =====
+    const int half = warp >> 3;   // 0: keys [0, 64) of the tile, 1: keys [64, 128)
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -248,35 +286,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(str_free, (uint32_t)(t - 1) & 1u);
         __syncwarp();
       }
+      const bool need_mask = (k0 + BWD_T > kvlen) || W >= 0;   // warp-uniform
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * half + cc;
         uint32_t sv[32], dv[32];
         tmem_ld32(tmem_base + lane_base + c * 32, sv);
         tmem_ld32(tmem_base + lane_base + 128 + c * 32, dv);
         tmem_wait_ld();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t pp[4], dd[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float pv[2], dsv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = 8 * g + 2 * i + e;
-              const int kc = k0 + c * 32 + col;
-              const bool ok = kc < kvlen && (W < 0 || abs(kc - qi) <= W);
-              const float pe = ok ? ex2_approx_bwd(fmaf(__uint_as_float(sv[col]), p.scale_log2, -lse_r)) : 0.f;
-              pv[e] = pe;
-              dsv[e] = pe * (__uint_as_float(dv[col]) - delta_r) * p.scale;
-            }
-            pp[i] = bf2_cvt(pv[0], pv[1]);
-            dd[i] = bf2_cvt(dsv[0], dsv[1]);
-          }
-          const int gg = c * 4 + g;   // 16-byte chunk index along the 128 keys
-          const int blk = gg >> 3, ch = (gg & 7) ^ (r & 7);
-          if (MODE == 0) *reinterpret_cast<uint4*>(prow + blk * BWD_BLK + (ch << 4)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-          *reinterpret_cast<uint4*>(dsrow + blk * BWD_BLK + (ch << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
-        }
+        if (need_mask) bwd_chunk<MODE, true>(sv, dv, lse_r, delta_r, p.scale_log2, p.scale, k0 + c * 32, kvlen, W, qi, prow, dsrow, c, r);
+        else bwd_chunk<MODE, false>(sv, dv, lse_r, delta_r, p.scale_log2, p.scale, k0 + c * 32, kvlen, W, qi, prow, dsrow, c, r);
       }
       tc_fence_before();
       mbar_arrive(sdp_free);
@@ -294,7 +313,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bf16* op = base + (row0 + ri) * p.ld_d + head * DH;
       const bool live = MODE == 0 ? (ri < kvlen) : (ri < qlimit);
 #pragma unroll
-      for (int c = 0; c < DH; c += 32) {
+      for (int c = half * (DH / 2); c < (half + 1) * (DH / 2); c += 32) {
         uint32_t o[32];
         tmem_ld32(tmem_base + lane_base + 256 + a * DH + c, o);
         tmem_wait_ld();
@@ -345,9 +364,9 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.N + BWD_T - 1) / BWD_T, a.heads, a.B);
-  k0<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, p);
+  k0<<<grid, 384, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, p);
   if (check_cuda(cudaGetLastError(), "attention bwd (dK/dV) launch")) return -1;
-  k1<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, p);
+  k1<<<grid, 384, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, p);
   return check_cuda(cudaGetLastError(), "attention bwd (dQ) launch");
 }
 
