@@ -92,6 +92,12 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.p = None
 
+    def n_samples(self) -> int:
+        try:
+            return sum(1 for r in open(self.f.name) if r.strip())
+        except Exception:  # noqa: BLE001
+            return 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
@@ -262,6 +268,14 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
     barrier(world)
     ms = ev0.elapsed_time(ev1)
+    if sampler is not None:
+        # nvidia-smi needs a few hundred ms to start: if the timed region was shorter than that, keep the same load
+        # running (untimed) until the sampler has seen it, so that `clocks` always describes the GPU under this workload
+        t_end = time.perf_counter() + 3.0
+        while sampler.n_samples() < 8 and time.perf_counter() < t_end:
+            for _ in range(4):
+                step(pd)
+            torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     ms = max_over_ranks(ms, world, dev)
     value = world * B * args.steps / (ms / 1e3)
@@ -523,8 +537,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
-        if args.steps > 5:          # bounded: the whole run must end within a few minutes
-            args.steps = 5
+        if args.steps > 20:         # bounded: the whole run must end within a few minutes
+            args.steps = 20
         run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
         return
     rank, world, local = dist_setup(args.gpus)
