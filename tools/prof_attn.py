@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.join(ROOT, "vitok-release_b200"))
 import torch  # noqa: E402
 from vitok_b200 import _lib  # noqa: E402
 
-shapes = [(64, 256, 16, 64), (8, 1024, 24, 128)]
+shapes = [(64, 256, 16, 64), (16, 1024, 16, 64), (8, 1024, 24, 128)]
 for (B, N, h, d) in shapes:
     qkv = (torch.randn(B * N, 3 * h * d, generator=torch.Generator().manual_seed(0)) * 1.0).to(torch.bfloat16).cuda()
     for _ in range(3):

@@ -85,11 +85,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // 32-column chunk with warp-uniform branches: chunks entirely inside kvlen are skipped and only the chunks at / beyond
 // the boundary pay a compare + select per column (the general per-element test costs ~12 instructions per score and
 // made a masked tile 8x as expensive as an unmasked one).
-__device__ __forceinline__ void mask_scores(uint32_t (&v)[4][32], int kv0, int kvlen, const uint8_t* kmask, int W, int qi) {
+template <int NCH>
+__device__ __forceinline__ void mask_scores(uint32_t (&v)[NCH][32], int kv0, int kvlen, const uint8_t* kmask, int W, int qi) {
   if (kmask == nullptr && W < 0) {
     const int lim = kvlen - kv0;   // columns >= lim are masked
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       if (lim < (c + 1) * 32) {
         const int l = lim - c * 32;
 #pragma unroll
@@ -100,7 +101,7 @@ __device__ __forceinline__ void mask_scores(uint32_t (&v)[4][32], int kv0, int k
     return;
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < NCH; ++c)
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int kc = kv0 + c * 32 + i;
@@ -136,11 +137,12 @@ __device__ __forceinline__ void ex2_poly_pair(uint32_t& a, uint32_t& b) {
 // the XU pipe idles ~55 % of the exponentiation phase with only two softmax warps per scheduler).  EMU_MASK selects,
 // inside every group of 8 pairs, the pairs exponentiated on the FMA pipe (ex2_poly_pair): 3 of 8 balances the two
 // pipes (MUFU: 8 cycles per warp instruction; the polynomial: 6 two-wide FMA-pipe instructions per pair).
-template <uint32_t EMU_MASK>
-__device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[4][32], uint64_t sc2, uint64_t nm2, uint8_t* prow, int r,
+template <uint32_t EMU_MASK, int NCH = 4>
+__device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[NCH][32], uint64_t sc2, uint64_t nm2, uint8_t* prow, int r,
                                                  uint64_t& sum2a, uint64_t& sum2b) {
+  constexpr int NP = NCH * 16;   // score pairs per row
 #pragma unroll
-  for (int pr = 0; pr < 64; ++pr) {
+  for (int pr = 0; pr < NP; ++pr) {
     float e0, e1;
     f2_unpack(f2_fma(f2_pack(__uint_as_float(v[pr >> 4][2 * (pr & 15)]), __uint_as_float(v[pr >> 4][2 * (pr & 15) + 1])), sc2, nm2), e0, e1);
     v[pr >> 4][2 * (pr & 15)] = __float_as_uint(e0);
@@ -149,8 +151,8 @@ __device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[4][32], uint64_t 
   constexpr int DIST = 3;
   uint32_t pk[4];
 #pragma unroll
-  for (int pr = 0; pr < 64 + DIST; ++pr) {
-    if (pr < 64) {
+  for (int pr = 0; pr < NP + DIST; ++pr) {
+    if (pr < NP) {
       uint32_t& a = v[pr >> 4][2 * (pr & 15)];
       uint32_t& b = v[pr >> 4][2 * (pr & 15) + 1];
       if ((EMU_MASK >> (pr & 7)) & 1u) {
@@ -903,6 +905,315 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split-key variant of the persistent kernel (d = 64): TWO softmax warpgroups per CTA, each an independent online softmax
+// over half of the keys of every 128-key tile (warpgroup h owns keys [64h, 64h + 64) of each tile) with its own running
+// max / sum and its own O accumulator in TMEM (S 128 + O_0 64 + O_1 64 columns = the 256 allocated).  The halves never
+// talk inside the key loop -- P_h V_h is a separate K = 64 MMA group with its own p_full / pv_done barriers -- and are
+// merged once per work item in the epilogue (the flash-decoding combine: O = (w_0 O_0 + w_1 O_1) / (w_0 l_0 + w_1 l_1),
+// w_h = 2^(m_h - max m)).  Same tensor-core work as one 128-key PV, but four softmax warps per scheduler instead of two
+// (2 CTAs per SM x 8 warps), which is what the MUFU / FMA / wait phases of a row need to overlap with somebody else's.
+// Softmax warps: 0-3 (h = 0) and 6-9 (h = 1) -- a warp may only touch the TMEM lanes of quarter (warp & 3), and
+// {6,7,8,9} & 3 = {2,3,0,1}; warp 4 = TMA, warp 5 = MMA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int DH, bool SNAKE>
+__global__ void __launch_bounds__(320, 2)
+attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
+                  const int total_items_host, const int qtiles) {
+  using S = AttnShape<DH, 1>;
+  static_assert(DH == 64, "split-key persistent attention: d = 64 only");
+  constexpr int HK = ATT_BKV / 2;   // keys per half tile
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int W = p.window;
+  const int total_items = SNAKE ? min(total_items_host, (__ldg(p.m_dev) / ATT_BQ) * p.heads) : total_items_host;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem + S::OFF_Q;
+  uint8_t* sK = smem + S::OFF_K;
+  uint8_t* sV = smem + S::OFF_V;
+  uint8_t* sP = smem + S::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;               // [2]
+  uint64_t* k_empty = bars + 3;              // [2]
+  uint64_t* v_full = bars + 5;               // [2]
+  uint64_t* v_empty = bars + 7;              // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 10;             // count 256
+  uint64_t* p_full = bars + 11;              // [2] count 128 each
+  uint64_t* pv_done = bars + 13;             // [2]
+  uint64_t* q_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  if (warp == 4) {
+    if (lane < 16) mbar_init(&bars[lane], lane == 10 ? 256u : (lane == 11 || lane == 12) ? 128u : 1u);
+    else if (lane == 17) tma_prefetch_desc(&tmQ);
+    else if (lane == 18) tma_prefetch_desc(&tmK);
+    else if (lane == 19) tma_prefetch_desc(&tmV);
+    else if (lane == 20) tma_prefetch_desc(&tmO);
+    fence_barrier_init();
+    __syncwarp();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===== TMA producer (identical to attn_persist_kernel) =====
+      uint32_t n_item = 0, n_k = 0, n_v = 0;
+      for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
+        if (SNAKE && w >= total_items) continue;
+        const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
+        if (!it.active) continue;
+        const long long row0 = it.row0;
+        if (n_item > 0) mbar_wait(q_empty, (n_item - 1) & 1u);
+        mbar_expect_tx(q_full, S::TILE_BYTES);
+        tma_load_2d(sQ, &tmQ, q_full, it.head * DH, (int)(row0 + it.q0));
+        ++n_item;
+        auto load_k = [&](int jj) {
+          const uint32_t slot = n_k % S::RK;
+          mbar_wait(&k_empty[slot], ((n_k / S::RK) & 1u) ^ 1u);
+          mbar_expect_tx(&k_full[slot], S::TILE_BYTES);
+          tma_load_2d(sK + slot * S::TILE_BYTES, &tmK, &k_full[slot], it.head * DH, (int)(row0 + (long long)(it.j_lo + jj) * ATT_BKV));
+          ++n_k;
+        };
+        load_k(0);
+        for (int jj = 0; jj < it.Tn; ++jj) {
+          if (jj + 1 < it.Tn) load_k(jj + 1);
+          const uint32_t slot = n_v % S::RV;
+          mbar_wait(&v_empty[slot], ((n_v / S::RV) & 1u) ^ 1u);
+          mbar_expect_tx(&v_full[slot], S::TILE_BYTES);
+          tma_load_2d(sV + slot * S::TILE_BYTES, &tmV, &v_full[slot], it.head * DH, (int)(row0 + (long long)(it.j_lo + jj) * ATT_BKV));
+          ++n_v;
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, DH, 0, 1);   // B (= V) is MN-major
+      uint32_t n_item = 0, n_k = 0, n_v = 0, n_t = 0, n_pv = 0;
+      const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
+      auto issue_s = [&]() {
+        const uint32_t slot = n_k % S::RK;
+        mbar_wait(&k_full[slot], (n_k / S::RK) & 1u);
+        if (n_t > 0) mbar_wait(s_empty, (n_t - 1) & 1u);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sK + slot * S::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16_ss(tmem_base, make_desc_kmajor_sw128(qa + kk * 32), make_desc_kmajor_sw128(ka + kk * 32), idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&k_empty[slot]);
+        umma_commit(s_full);
+        ++n_k;
+        ++n_t;
+      };
+      for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
+        if (SNAKE && w >= total_items) continue;
+        const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
+        if (!it.active) continue;
+        mbar_wait(q_full, n_item & 1u);
+        ++n_item;
+        issue_s();
+        for (int jj = 0; jj < it.Tn; ++jj) {
+          if (jj + 1 < it.Tn) issue_s();
+          else umma_commit(q_empty);
+          const uint32_t slot = n_v % S::RV;
+          mbar_wait(&v_full[slot], (n_v / S::RV) & 1u);
+          const uint32_t va = smem_u32(sV + slot * S::TILE_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {      // O_h += P_h V_h: keys [64h, 64h + 64) of the tile, K = 64
+            mbar_wait(&p_full[h], n_pv & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < HK / 16; ++k4) {
+              const int kk = h * (HK / 16) + k4;
+              const uint64_t adesc = make_desc_kmajor_sw128(pa + (kk >> 2) * BLK + (kk & 3) * 32);
+              const uint64_t bdesc = make_smem_desc(va + kk * 2048, BLK, 1024, 2);
+              umma_bf16_ss(tmem_base + S::O_COL0 + h * DH, adesc, bdesc, idesc_o, (jj | k4) != 0 ? 1u : 0u);
+            }
+            umma_commit(&pv_done[h]);
+          }
+          umma_commit(&v_empty[slot]);
+          ++n_v;
+          ++n_pv;
+        }
+      }
+    }
+  } else {
+    // ===== softmax warpgroups: thread <-> (query row, key half) =====
+    const int h = warp >= 6 ? 1 : 0;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + h * HK;
+    const uint32_t tOh = tmem_base + lane_base + S::O_COL0 + h * DH;
+    uint8_t* prow = sP + h * BLK + r * 128;                       // this half's [128 x 64] block of the P buffer
+    float2* exch = reinterpret_cast<float2*>(sP + BLK + 8192);    // [2][128] (m, l): lives in block 1, idle in the epilogue
+    const float sc = p.scale_log2;
+    uint32_t n_t = 0;
+    bool store_pending = false;
+    for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
+      if (SNAKE && w >= total_items) continue;
+      const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
+      const long long row0 = it.row0;
+      const int N = it.nrows;
+      const int qi = it.q0 + r;
+      if (!it.active) {   // nothing to attend to: the output rows are 0
+        if (qi < N) {
+          bf16* op = p.out + (row0 + qi) * p.ld_out + it.head * DH + h * (DH / 2);
+          for (int c = 0; c < DH / 2; c += 8) st_global_v4(op + c, 0u, 0u, 0u, 0u);
+          if (p.lse && h == 0) p.lse[(row0 + qi) * p.heads + it.head] = INFINITY;
+        }
+        continue;
+      }
+      const int kvlen = it.kvlen;
+      const bool general_mask = p.key_mask != nullptr && !(p.prefix_flag != nullptr && p.prefix_flag[it.img] != 0);
+      const uint8_t* kmask = general_mask ? p.key_mask + row0 : nullptr;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < it.Tn; ++j, ++n_t) {
+        const int kv0 = (it.j_lo + j) * ATT_BKV + h * HK;       // first key of this half tile
+        const bool win_mask = W >= 0 && (kv0 < it.q0 + ATT_BQ - 1 - W || kv0 + HK - 1 > it.q0 + W);
+        const bool need_mask = (kv0 + HK > kvlen) || (kmask != nullptr) || win_mask;
+        mbar_wait(s_full, n_t & 1u);
+        __syncwarp();
+        tc_fence_after();
+        uint32_t v[2][32];
+        tmem_ld32(tS + 0, v[0]);
+        tmem_ld32(tS + 32, v[1]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(s_empty);
+        if (need_mask) mask_scores<2>(v, kv0, kvlen, kmask, W, qi);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = max3f(mx0, __uint_as_float(v[0][i]), __uint_as_float(v[0][i + 1]));
+          mx1 = max3f(mx1, __uint_as_float(v[1][i]), __uint_as_float(v[1][i + 1]));
+        }
+        const float m_tile = fmaxf(mx0, mx1) * sc;
+        float m_use = m_run, alpha = 1.f;
+        if (m_tile > m_run + RESCALE_THRESHOLD || m_run == -INFINITY) {
+          m_use = fmaxf(m_run, m_tile);
+          alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_use);
+        }
+        const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
+        const uint64_t sc2 = f2_pack(sc, sc), nm2 = f2_pack(-m_sub, -m_sub);
+        uint64_t sum2a = 0ull, sum2b = 0ull;
+        // this half's P block is free once its previous PV has completed (and, for half 0, once the O tile staged in
+        // block 0 by the previous item's epilogue has been read by its TMA store)
+        if (n_t > 0) {
+          mbar_wait(&pv_done[h], (n_t - 1) & 1u);
+          __syncwarp();
+          tc_fence_after();
+        }
+        if (store_pending) {
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          store_pending = false;
+        }
+        softmax_exp_tile<0u, 2>(v, sc2, nm2, prow, r, sum2a, sum2b);
+        float sum0, sum1;
+        f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
+        l_run = l_run * alpha + (sum0 + sum1);
+        m_run = m_use;
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int c = 0; c < DH; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tOh + c, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tOh + c, o);
+          }
+          tmem_wait_st();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[h]);
+      }
+      // ---- epilogue of the item: merge the two halves ----
+      mbar_wait(&pv_done[0], (n_t - 1) & 1u);
+      mbar_wait(&pv_done[1], (n_t - 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      exch[h * 128 + r] = make_float2(m_run, l_run);
+      softmax_bar_sync();
+      const float2 oth = exch[(1 - h) * 128 + r];
+      const float M = fmaxf(m_run, oth.x);
+      const float w_self = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - M);
+      const float w_oth = (oth.x == -INFINITY) ? 0.f : ex2_approx(oth.x - M);
+      const float L = l_run * w_self + oth.y * w_oth;
+      const float inv = L > 0.f ? 1.f / L : 0.f;
+      bool zero_row = false;
+      if (p.zero_invalid) zero_row = (qi >= kvlen) || (kmask != nullptr && qi < N && kmask[qi] == 0);
+      const float osc = zero_row ? 0.f : inv;
+      if (p.lse && h == 0 && qi < N) p.lse[(row0 + qi) * p.heads + it.head] = (zero_row || !(L > 0.f)) ? INFINITY : M + log2f(L);
+      const float w0 = (h == 0 ? w_self : w_oth) * osc, w1 = (h == 0 ? w_oth : w_self) * osc;
+      // this thread finishes output columns [32h, 32h + 32) of its row: w0 * O_0 + w1 * O_1
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tmem_base + lane_base + S::O_COL0 + h * 32, o0);
+      tmem_ld32(tmem_base + lane_base + S::O_COL0 + DH + h * 32, o1);
+      tmem_wait_ld();
+      tc_fence_before();
+      uint32_t wv[4][4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = 8 * g + 2 * i;
+          wv[g][i] = bf2_cvt(__uint_as_float(o0[c0]) * w0 + __uint_as_float(o1[c0]) * w1,
+                             __uint_as_float(o0[c0 + 1]) * w0 + __uint_as_float(o1[c0 + 1]) * w1);
+        }
+      if (p.tma_out) {
+        uint8_t* srow = sP + r * 128;   // O staged in block 0 of the P buffer (free: both halves' last PV have completed)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ch = (h * 4 + g) ^ (r & 7);
+          *reinterpret_cast<uint4*>(srow + (ch << 4)) = make_uint4(wv[g][0], wv[g][1], wv[g][2], wv[g][3]);
+        }
+        fence_proxy_async_smem();
+        softmax_bar_sync();             // both halves' columns are staged (and every read of exch is done)
+        if (h == 0) {
+          if (lane == 0) {
+            tma_store_2d(&tmO, sP + quarter * 32 * 128, it.head * DH, (int)(row0 + it.q0 + quarter * 32));
+            tma_store_commit();
+          }
+          store_pending = true;
+        }
+      } else {
+        if (qi < N) {
+          bf16* op = p.out + (row0 + qi) * p.ld_out + it.head * DH + h * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) st_global_v4(op + 8 * g, wv[g][0], wv[g][1], wv[g][2], wv[g][3]);
+        }
+        softmax_bar_sync();             // every read of exch is done before half 1 writes P into block 1 again
+      }
+    }
+    if (store_pending && lane == 0) tma_store_wait_read();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
 static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   using S = AttnShape<64, 1>;
   const bool packed = a.cu != nullptr;
@@ -936,19 +1247,26 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
   // perf experiments: VTK_ATTN_EMU = pairs (bit mask inside every group of 8) exponentiated on the FMA pipe
   static const int emu = getenv("VTK_ATTN_EMU") ? (int)strtol(getenv("VTK_ATTN_EMU"), nullptr, 0) : (int)VTK_ATTN_EMU_MASK;
-  auto kern = packed ? attn_persist_kernel<64, 0u, true>
+  // VTK_ATTN_SPLIT=1 selects the split-key kernel (two softmax warpgroups per CTA).  Measured: 46.7 vs 45.9 us at the c2 shape,
+  // 116.9 vs 118.8 us at N = 1024 -- doubling the softmax warps does not help because all warps of a CTA wait for the same
+  // S tile and hit the MUFU in lock-step; it stays off until the halves get their own S buffers (independent pipelines).
+  static const int split = getenv("VTK_ATTN_SPLIT") ? atoi(getenv("VTK_ATTN_SPLIT")) : 0;
+  const bool use_split = split != 0 && !prof_mode && emu == 0;
+  auto kern = use_split ? (packed ? attn_split_kernel<64, true> : attn_split_kernel<64, false>)
+              : packed ? attn_persist_kernel<64, 0u, true>
               : emu == 0x52 ? attn_persist_kernel<64, 0x52u, false> : attn_persist_kernel<64, 0u, false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[packed ? 1 : 0]) {
+  static bool attr_set[4] = {false, false, false, false};
+  const int ai = (packed ? 1 : 0) + (use_split ? 2 : 0);
+  if (!attr_set[ai]) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES), "cudaFuncSetAttribute(attn_persist)"))
       return -1;
-    attr_set[packed ? 1 : 0] = true;
+    attr_set[ai] = true;
   }
   const int qtiles = (a.N + ATT_BQ - 1) / ATT_BQ;
   const long long total = packed ? (Mrows / ATT_BQ) * a.heads : (long long)a.B * a.heads * qtiles;
   if (total >= (1ll << 31)) { set_error("attention: too many work items"); return -2; }
   const int grid = (int)std::min<long long>(total, 2ll * num_sms());
-  kern<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
+  kern<<<grid, use_split ? 320 : 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
   if (prof_mode) {
     unsigned long long h[16];
     cudaDeviceSynchronize();
