@@ -906,13 +906,17 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
-// Split-key variant of the persistent kernel (d = 64): TWO softmax warpgroups per CTA, each an independent online softmax
-// over half of the keys of every 128-key tile (warpgroup h owns keys [64h, 64h + 64) of each tile) with its own running
-// max / sum and its own O accumulator in TMEM (S 128 + O_0 64 + O_1 64 columns = the 256 allocated).  The halves never
-// talk inside the key loop -- P_h V_h is a separate K = 64 MMA group with its own p_full / pv_done barriers -- and are
-// merged once per work item in the epilogue (the flash-decoding combine: O = (w_0 O_0 + w_1 O_1) / (w_0 l_0 + w_1 l_1),
-// w_h = 2^(m_h - max m)).  Same tensor-core work as one 128-key PV, but four softmax warps per scheduler instead of two
-// (2 CTAs per SM x 8 warps), which is what the MUFU / FMA / wait phases of a row need to overlap with somebody else's.
+// Split-key variant of the persistent kernel (d = 64): TWO independent softmax pipelines per CTA.  Warpgroup h owns keys
+// [64h, 64h + 64) of every 128-key tile: its own S_h = Q K_h^T (an N = 64 MMA into its own 64 TMEM columns), its own
+// running max / sum, its own P_h block in shared memory and its own O_h accumulator (TMEM: S_0 64 + S_1 64 + O_0 64 +
+// O_1 64 = the 256 columns allocated), with its own s_full / s_empty / p_full / pv_done barriers.  Inside an item the two
+// pipelines never wait for each other, so they drift out of phase and one half's MUFU phase overlaps the other's load /
+// max / wait phases -- with one S buffer all softmax warps of a CTA are released by the same event and hit the MUFU in
+// lock-step (a first version that only split the columns of a shared S tile was no faster than one warpgroup).  Same tensor
+// work as a 128-key tile.  The halves are merged once per item in the epilogue (flash-decoding combine:
+// O = (w_0 O_0 + w_1 O_1) / (w_0 l_0 + w_1 l_1), w_h = 2^(m_h - max m)).  The single MMA thread serves both pipelines from
+// a polling loop (mbarrier.try_wait): per half the order is S(0), then S(j+1) before PV(j); a K / V ring slot is released
+// when both halves have issued their MMA on it.
 // Softmax warps: 0-3 (h = 0) and 6-9 (h = 1) -- a warp may only touch the TMEM lanes of quarter (warp & 3), and
 // {6,7,8,9} & 3 = {2,3,0,1}; warp 4 = TMA, warp 5 = MMA.
 // ------------------------------------------------------------------------------------------------
@@ -925,7 +929,9 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   const int total_items_host, const int qtiles) {
   using S = AttnShape<DH, 1>;
   static_assert(DH == 64, "split-key persistent attention: d = 64 only");
-  constexpr int HK = ATT_BKV / 2;   // keys per half tile
+  constexpr int HK = ATT_BKV / 2;            // keys per half tile
+  constexpr uint32_t S_COL = 0;              // S_h at [64h, 64h + 64)
+  constexpr uint32_t O_COL = 128;            // O_h at [128 + 64h, 128 + 64h + 64)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int W = p.window;
@@ -942,19 +948,19 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* k_empty = bars + 3;              // [2]
   uint64_t* v_full = bars + 5;               // [2]
   uint64_t* v_empty = bars + 7;              // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_empty = bars + 10;             // count 256
-  uint64_t* p_full = bars + 11;              // [2] count 128 each
-  uint64_t* pv_done = bars + 13;             // [2]
-  uint64_t* q_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* s_full = bars + 9;               // [2] per half
+  uint64_t* s_empty = bars + 11;             // [2] count 128 each
+  uint64_t* p_full = bars + 13;              // [2] count 128 each
+  uint64_t* pv_done = bars + 15;             // [2]
+  uint64_t* q_empty = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   if (warp == 4) {
-    if (lane < 16) mbar_init(&bars[lane], lane == 10 ? 256u : (lane == 11 || lane == 12) ? 128u : 1u);
-    else if (lane == 17) tma_prefetch_desc(&tmQ);
-    else if (lane == 18) tma_prefetch_desc(&tmK);
-    else if (lane == 19) tma_prefetch_desc(&tmV);
-    else if (lane == 20) tma_prefetch_desc(&tmO);
+    if (lane < 18) mbar_init(&bars[lane], (lane >= 11 && lane <= 14) ? 128u : 1u);
+    else if (lane == 19) tma_prefetch_desc(&tmQ);
+    else if (lane == 20) tma_prefetch_desc(&tmK);
+    else if (lane == 21) tma_prefetch_desc(&tmV);
+    else if (lane == 22) tma_prefetch_desc(&tmO);
     fence_barrier_init();
     __syncwarp();
   }
@@ -1000,55 +1006,71 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);
-      const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, DH, 0, 1);   // B (= V) is MN-major
-      uint32_t n_item = 0, n_k = 0, n_v = 0, n_t = 0, n_pv = 0;
+      // ===== MMA issuer: one polling loop over the two half pipelines =====
+      const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, HK, 0, 0);   // S_h: 128 queries x 64 keys
+      const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, DH, 0, 1);   // O_h: B (= V_h) is MN-major
+      uint32_t n_item = 0, n_k = 0, n_v = 0;                         // K / V tiles consumed before the current item
+      uint32_t ns[2] = {0, 0}, npv[2] = {0, 0};                      // S / PV groups issued so far, per half (barrier phases)
       const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
-      auto issue_s = [&]() {
-        const uint32_t slot = n_k % S::RK;
-        mbar_wait(&k_full[slot], (n_k / S::RK) & 1u);
-        if (n_t > 0) mbar_wait(s_empty, (n_t - 1) & 1u);
-        tc_fence_after();
-        const uint32_t ka = smem_u32(sK + slot * S::TILE_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16_ss(tmem_base, make_desc_kmajor_sw128(qa + kk * 32), make_desc_kmajor_sw128(ka + kk * 32), idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&k_empty[slot]);
-        umma_commit(s_full);
-        ++n_k;
-        ++n_t;
-      };
       for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
         if (SNAKE && w >= total_items) continue;
         const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
         if (!it.active) continue;
         mbar_wait(q_full, n_item & 1u);
         ++n_item;
-        issue_s();
-        for (int jj = 0; jj < it.Tn; ++jj) {
-          if (jj + 1 < it.Tn) issue_s();
-          else umma_commit(q_empty);
-          const uint32_t slot = n_v % S::RV;
-          mbar_wait(&v_full[slot], (n_v / S::RV) & 1u);
-          const uint32_t va = smem_u32(sV + slot * S::TILE_BYTES);
+        const int Tn = it.Tn;
+        int js[2] = {0, 0}, jp[2] = {0, 0};   // next S tile / next PV tile of each half inside this item
+        bool q_released = false;
+        const long long t0 = clock64();
+        while (jp[0] < Tn || jp[1] < Tn) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {      // O_h += P_h V_h: keys [64h, 64h + 64) of the tile, K = 64
-            mbar_wait(&p_full[h], n_pv & 1u);
-            tc_fence_after();
+          for (int h = 0; h < 2; ++h) {
+            // S_h(js): allowed at most one tile ahead of this half's PV
+            if (js[h] < Tn && js[h] <= jp[h] + 1) {
+              const uint32_t kt = n_k + (uint32_t)js[h];
+              const uint32_t slot = kt % S::RK;
+              if (mbar_try_wait(&k_full[slot], (kt / S::RK) & 1u) && (ns[h] == 0 || mbar_try_wait(&s_empty[h], (ns[h] - 1) & 1u))) {
+                tc_fence_after();
+                const uint32_t ka = smem_u32(sK + slot * S::TILE_BYTES) + h * (HK * 128);   // key rows [64h, 64h + 64): 128 B per row
 #pragma unroll
-            for (int k4 = 0; k4 < HK / 16; ++k4) {
-              const int kk = h * (HK / 16) + k4;
-              const uint64_t adesc = make_desc_kmajor_sw128(pa + (kk >> 2) * BLK + (kk & 3) * 32);
-              const uint64_t bdesc = make_smem_desc(va + kk * 2048, BLK, 1024, 2);
-              umma_bf16_ss(tmem_base + S::O_COL0 + h * DH, adesc, bdesc, idesc_o, (jj | k4) != 0 ? 1u : 0u);
+                for (int kk = 0; kk < DH / 16; ++kk)
+                  umma_bf16_ss(tmem_base + S_COL + h * HK, make_desc_kmajor_sw128(qa + kk * 32), make_desc_kmajor_sw128(ka + kk * 32),
+                               idesc_s, kk != 0 ? 1u : 0u);
+                umma_commit(&s_full[h]);
+                if (js[1 - h] > js[h]) umma_commit(&k_empty[slot]);   // the other half has already used this K tile
+                ++js[h];
+                ++ns[h];
+                if (!q_released && js[0] == Tn && js[1] == Tn) {       // every S MMA of this item has been issued
+                  umma_commit(q_empty);
+                  q_released = true;
+                }
+              }
             }
-            umma_commit(&pv_done[h]);
+            // O_h += P_h V_h (K = 64)
+            if (jp[h] < js[h]) {
+              const uint32_t vt = n_v + (uint32_t)jp[h];
+              const uint32_t slot = vt % S::RV;
+              if (mbar_try_wait(&v_full[slot], (vt / S::RV) & 1u) && mbar_try_wait(&p_full[h], npv[h] & 1u)) {
+                tc_fence_after();
+                const uint32_t va = smem_u32(sV + slot * S::TILE_BYTES);
+#pragma unroll
+                for (int k4 = 0; k4 < HK / 16; ++k4) {
+                  const int kk = h * (HK / 16) + k4;
+                  const uint64_t adesc = make_desc_kmajor_sw128(pa + h * BLK + k4 * 32);
+                  const uint64_t bdesc = make_smem_desc(va + kk * 2048, BLK, 1024, 2);
+                  umma_bf16_ss(tmem_base + O_COL + h * DH, adesc, bdesc, idesc_o, (jp[h] | k4) != 0 ? 1u : 0u);
+                }
+                umma_commit(&pv_done[h]);
+                if (jp[1 - h] > jp[h]) umma_commit(&v_empty[slot]);   // the other half has already used this V tile
+                ++jp[h];
+                ++npv[h];
+              }
+            }
           }
-          umma_commit(&v_empty[slot]);
-          ++n_v;
-          ++n_pv;
+          if (clock64() - t0 > VTK_WAIT_LIMIT_CYCLES) __trap();
         }
+        n_k += (uint32_t)Tn;
+        n_v += (uint32_t)Tn;
       }
     }
   } else {
@@ -1057,8 +1079,8 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + h * HK;
-    const uint32_t tOh = tmem_base + lane_base + S::O_COL0 + h * DH;
+    const uint32_t tS = tmem_base + lane_base + S_COL + h * HK;
+    const uint32_t tOh = tmem_base + lane_base + O_COL + h * DH;
     uint8_t* prow = sP + h * BLK + r * 128;                       // this half's [128 x 64] block of the P buffer
     float2* exch = reinterpret_cast<float2*>(sP + BLK + 8192);    // [2][128] (m, l): lives in block 1, idle in the epilogue
     const float sc = p.scale_log2;
@@ -1086,7 +1108,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int kv0 = (it.j_lo + j) * ATT_BKV + h * HK;       // first key of this half tile
         const bool win_mask = W >= 0 && (kv0 < it.q0 + ATT_BQ - 1 - W || kv0 + HK - 1 > it.q0 + W);
         const bool need_mask = (kv0 + HK > kvlen) || (kmask != nullptr) || win_mask;
-        mbar_wait(s_full, n_t & 1u);
+        mbar_wait(&s_full[h], n_t & 1u);
         __syncwarp();
         tc_fence_after();
         uint32_t v[2][32];
@@ -1094,7 +1116,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_ld32(tS + 32, v[1]);
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(s_empty);
+        mbar_arrive(&s_empty[h]);
         if (need_mask) mask_scores<2>(v, kv0, kvlen, kmask, W, qi);
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -1164,8 +1186,8 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float w0 = (h == 0 ? w_self : w_oth) * osc, w1 = (h == 0 ? w_oth : w_self) * osc;
       // this thread finishes output columns [32h, 32h + 32) of its row: w0 * O_0 + w1 * O_1
       uint32_t o0[32], o1[32];
-      tmem_ld32(tmem_base + lane_base + S::O_COL0 + h * 32, o0);
-      tmem_ld32(tmem_base + lane_base + S::O_COL0 + DH + h * 32, o1);
+      tmem_ld32(tmem_base + lane_base + O_COL + h * 32, o0);
+      tmem_ld32(tmem_base + lane_base + O_COL + DH + h * 32, o1);
       tmem_wait_ld();
       tc_fence_before();
       uint32_t wv[4][4];
@@ -1247,9 +1269,10 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
   // perf experiments: VTK_ATTN_EMU = pairs (bit mask inside every group of 8) exponentiated on the FMA pipe
   static const int emu = getenv("VTK_ATTN_EMU") ? (int)strtol(getenv("VTK_ATTN_EMU"), nullptr, 0) : (int)VTK_ATTN_EMU_MASK;
-  // VTK_ATTN_SPLIT=1 selects the split-key kernel (two softmax warpgroups per CTA).  Measured: 46.7 vs 45.9 us at the c2 shape,
-  // 116.9 vs 118.8 us at N = 1024 -- doubling the softmax warps does not help because all warps of a CTA wait for the same
-  // S tile and hit the MUFU in lock-step; it stays off until the halves get their own S buffers (independent pipelines).
+  // VTK_ATTN_SPLIT=1 selects the split-key kernel (two independent softmax pipelines per CTA).  Measured on B200: 47.4 vs 45.7 us
+  // at the c2 shape, 120.5 vs 120.0 us at N = 1024 -- neither doubling the softmax warps nor de-phasing them changes the time,
+  // so the ~1660 cycles per 128 x 128 tile per SM are not MUFU contention between lock-stepped warps (S read-back from TMEM,
+  // 64 KB per tile, is the next suspect).  It stays an opt-in experiment.
   static const int split = getenv("VTK_ATTN_SPLIT") ? atoi(getenv("VTK_ATTN_SPLIT")) : 0;
   const bool use_split = split != 0 && !prof_mode && emu == 0;
   auto kern = use_split ? (packed ? attn_split_kernel<64, true> : attn_split_kernel<64, false>)
