@@ -77,12 +77,14 @@ def test_attention_sliding_window(L, B, N, heads, d, w):
     report(f"attn window={w} N={N} d={d}", out, _ref(qkv, B, N, heads, d, None, w).float(), max_abs=3e-2, rel_fro=1e-2)
 
 
-@pytest.mark.parametrize("N,heads,d,w", [(512, 2, 64, 64), (1024, 2, 128, 100), (1024, 2, 64, -1)])
+@pytest.mark.parametrize("N,heads,d,w", [(512, 2, 64, 64), (1024, 2, 128, 100), (1024, 2, 64, -1),
+                                         # high-resolution decode: 2048 px / 4096 px at p = 16 with a sliding window
+                                         (16384, 2, 64, 1024), (65536, 1, 128, 2048)])
 def test_attention_vs_flash_attn_library(L, N, heads, d, w):
     """The reference's flash backend IS flash_attn_func (third-party, pinned 2.8.3 in scripts/modal/modal_config.py);
     when it is importable on the GPU box, compare against it directly, with and without window_size."""
     fa = pytest.importorskip("flash_attn")
-    B = 2
+    B = 2 if N <= 4096 else 1
     qkv = bf16_randn(B * N, 3 * heads * d, seed=46)
     out = L.attention(qkv, B, N, heads, d, None, window=w)
     q, k, v = qkv.reshape(B, N, 3, heads, d).unbind(2)

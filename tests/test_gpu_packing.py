@@ -94,8 +94,12 @@ def _cuda(batch):
     return {k: (v.cuda().to(torch.bfloat16) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
 
 
-def test_packed_equals_padded_on_valid_tokens():
-    model, cfg, _ = _model(D64)
+D128 = "w128_d2_h2-w256_d3_h2/1x16x16"  # decoder head_dim 128: images padded to 256 packed rows (two query tiles per attention CTA)
+
+
+@pytest.mark.parametrize("variant", [D64, D128])
+def test_packed_equals_padded_on_valid_tokens(variant):
+    model, cfg, _ = _model(variant)
     batch = _ragged_batch([(256, 320), (96, 64), (50, 120), (16, 16), (320, 256), (130, 131)], 16, 320, seed=11)
     cb = _cuda(batch)
     valid = batch["patch_mask"]

@@ -119,7 +119,8 @@ static Workspace carve(const Side& s, void* base, int B, int N, int io_cols) {
     off += align_up(nbytes, 1024);
     return p;
   };
-  const long long M = PackPlan::row_capacity(B, N);
+  const int pad = s.head_dim() == 128 ? 256 : 128;
+  const long long M = PackPlan::row_capacity(B, N, pad);
   const long long D = s.width, d = s.head_dim();
   w.x = static_cast<bf16*>(take((size_t)M * D * 2));
   w.h = static_cast<bf16*>(take((size_t)M * D * 2));
@@ -129,7 +130,7 @@ static Workspace carve(const Side& s, void* base, int B, int N, int io_cols) {
   w.ss = static_cast<float*>(take((size_t)M * ((D + 63) / 64) * 4));
   w.kv_len = static_cast<int*>(take((size_t)B * 4));
   w.is_prefix = static_cast<int*>(take((size_t)B * 4));
-  w.plan.B = B; w.plan.N = N;
+  w.plan.B = B; w.plan.N = N; w.plan.pad = pad;
   w.plan.n_valid = w.kv_len;
   w.plan.rel = static_cast<int*>(take((size_t)B * N * 4));
   w.plan.cu = static_cast<int*>(take((size_t)(B + 1) * 4));
@@ -511,7 +512,7 @@ size_t vtk_ae_workspace_bytes(vtk_ae_t h, int side, int B, int N) {
 // vtk_ae_set_packing(h, 0) / VTK_NO_PACK=1 keep the padded [B, N] layout with in-kernel key masking (A/B experiments, parity tests).
 static bool use_packing(const vtk_ae_s* h, const Side& s, const uint8_t* patch_mask) {
   static const int off = getenv("VTK_NO_PACK") ? atoi(getenv("VTK_NO_PACK")) : 0;
-  return patch_mask != nullptr && s.depth > 0 && s.head_dim() == 64 && h->packing && !off;
+  return patch_mask != nullptr && s.depth > 0 && (s.head_dim() == 64 || s.head_dim() == 128) && h->packing && !off;
 }
 
 // rows = row capacity of the activation buffers; with `pl` the kernels read the live row count from pl->m_dev()
@@ -584,7 +585,7 @@ static int run_side(vtk_ae_s* h, int side, const void* in, const int64_t* row_id
   Workspace w = carve(s, workspace, B, N, io_cols(h->cfg));
   const bool packed = use_packing(h, s, patch_mask);
   const PackPlan* pl = packed ? &w.plan : nullptr;
-  const int rows = packed ? (int)PackPlan::row_capacity(B, N) : B * N;
+  const int rows = packed ? (int)PackPlan::row_capacity(B, N, w.plan.pad) : B * N;
   const int* m_dev = packed ? pl->m_dev() : nullptr;
   int launches = 0, r;
   h->ev_used = 0;
@@ -627,7 +628,7 @@ static int check_io(vtk_ae_t h, int side, const void* in, const int64_t* row_idx
   VTK_REQUIRE(s.width > 0 && s.w_a, "%s: this model has no %s weights set", fn, side ? "decoder" : "encoder");
   VTK_REQUIRE(in && row_idx && col_idx && out && workspace, "%s: null pointer", fn);
   VTK_REQUIRE(B > 0 && N > 0, "%s: empty batch (B=%d N=%d)", fn, B, N);
-  VTK_REQUIRE(PackPlan::row_capacity(B, N) < (1ll << 31), "%s: B*N too large", fn);
+  VTK_REQUIRE(PackPlan::row_capacity(B, N, 256) < (1ll << 31), "%s: B*N too large", fn);
   VTK_REQUIRE(workspace_bytes >= vtk_ae_workspace_bytes(h, side, B, N), "%s: workspace too small (%zu < %zu)", fn,
               workspace_bytes, vtk_ae_workspace_bytes(h, side, B, N));
   VTK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "%s: workspace must be 1024-byte aligned", fn);

@@ -155,7 +155,9 @@ __device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[NCH][32], uint64_
     if (pr < NP) {
       uint32_t& a = v[pr >> 4][2 * (pr & 15)];
       uint32_t& b = v[pr >> 4][2 * (pr & 15) + 1];
-      if ((EMU_MASK >> (pr & 7)) & 1u) {
+      if (EMU_MASK == 0xFFFFu) {
+        // timing experiment only (VTK_ATTN_EMU=0xFFFF): no exponential at all
+      } else if ((EMU_MASK >> (pr & 7)) & 1u) {
         ex2_poly_pair(a, b);
       } else {
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a));
@@ -190,15 +192,28 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
   using S = AttnShape<DH, NQ>;
   const long long t_cta0 = p.prof ? clock64() : 0;
-  const int q0 = blockIdx.x * (NQ * ATT_BQ);
   const int head = blockIdx.y;
-  const int img = blockIdx.z;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int N = p.N;
-  int kvlen = p.kv_len ? p.kv_len[img] : N;
-  kvlen = kvlen < N ? kvlen : N;
-  const long long row0 = (long long)img * N;
+  int q0, img, N, kvlen;
+  long long row0;
+  if (p.cu) {
+    // packed NaFlex layout (images padded to NQ * 128 rows): blockIdx.x = group of NQ packed tiles, all of one image
+    const int first_tile = blockIdx.x * NQ;
+    if (first_tile * ATT_BQ >= __ldg(p.m_dev)) return;   // beyond the packed rows of this batch (whole CTA)
+    img = p.tile_img[first_tile];
+    row0 = p.cu[img];
+    q0 = first_tile * ATT_BQ - (int)row0;
+    kvlen = p.kv_len[img];
+    N = (kvlen + NQ * ATT_BQ - 1) / (NQ * ATT_BQ) * (NQ * ATT_BQ);
+  } else {
+    q0 = blockIdx.x * (NQ * ATT_BQ);
+    img = blockIdx.z;
+    N = p.N;
+    kvlen = p.kv_len ? p.kv_len[img] : N;
+    kvlen = kvlen < N ? kvlen : N;
+    row0 = (long long)img * N;
+  }
   const int T = (kvlen + ATT_BKV - 1) / ATT_BKV;
   const int qlimit = p.zero_invalid ? kvlen : N;           // query rows >= qlimit are padding
   const int nact = (T == 0 || q0 >= qlimit) ? 0 : ((NQ == 2 && q0 + ATT_BQ < qlimit) ? 2 : 1);
@@ -766,11 +781,18 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         const long long k1 = PCLK();
         uint32_t v[4][32];
-        tmem_ld32(tS + 0, v[0]);
-        tmem_ld32(tS + 32, v[1]);
-        tmem_ld32(tS + 64, v[2]);
-        tmem_ld32(tS + 96, v[3]);
-        tmem_wait_ld();
+        if (EMU == 0xFFFEu) {   // timing experiment only (VTK_ATTN_EMU=0xFFFE): S is not read back from TMEM
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[c][i] = __float_as_uint((float)((lane + i + c) & 7));
+        } else {
+          tmem_ld32(tS + 0, v[0]);
+          tmem_ld32(tS + 32, v[1]);
+          tmem_ld32(tS + 64, v[2]);
+          tmem_ld32(tS + 96, v[3]);
+          tmem_wait_ld();
+        }
         tc_fence_before();
         mbar_arrive(s_empty);   // S is in registers: the tensor core may overwrite it with the next tile's S
         const long long k2 = PCLK();
@@ -1277,7 +1299,9 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   const bool use_split = split != 0 && !prof_mode && emu == 0;
   auto kern = use_split ? (packed ? attn_split_kernel<64, true> : attn_split_kernel<64, false>)
               : packed ? attn_persist_kernel<64, 0u, true>
-              : emu == 0x52 ? attn_persist_kernel<64, 0x52u, false> : attn_persist_kernel<64, 0u, false>;
+              : emu == 0x52 ? attn_persist_kernel<64, 0x52u, false>
+              : emu == 0xFFFF ? attn_persist_kernel<64, 0xFFFFu, false>
+              : emu == 0xFFFE ? attn_persist_kernel<64, 0xFFFEu, false> : attn_persist_kernel<64, 0u, false>;
   static bool attr_set[4] = {false, false, false, false};
   const int ai = (packed ? 1 : 0) + (use_split ? 2 : 0);
   if (!attr_set[ai]) {
@@ -1305,7 +1329,12 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
 template <int DH, int NQ>
 static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   using S = AttnShape<DH, NQ>;
-  const long long Mrows = (long long)a.B * a.N;
+  const bool packed = a.cu != nullptr;
+  if (packed && (!a.tile_img || !a.m_dev || !a.kv_len || a.key_mask || a.window >= 0 || a.row_cap % (NQ * ATT_BQ))) {
+    set_error("attention: packed layout needs cu/tile_img/m_dev/kv_len, a row capacity that is a multiple of %d, no key mask and no window", NQ * ATT_BQ);
+    return -2;
+  }
+  const long long Mrows = packed ? a.row_cap : (long long)a.B * a.N;
   const long long cols = (long long)a.heads * a.d;
   CUtensorMap tmQ, tmK, tmV;
   if (encode_tmap_bf16_sw128(&tmQ, a.q, cols, Mrows, a.ld_qkv, ATT_BQ)) return -1;
@@ -1317,10 +1346,10 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   p.out = a.out; p.ld_out = a.ld_out;
   p.kv_len = a.kv_len; p.key_mask = a.key_mask; p.prefix_flag = a.prefix_flag;
   p.N = a.N; p.heads = a.heads; p.zero_invalid = a.zero_invalid_rows;
-  p.tma_out = (a.N % ATT_BQ == 0) ? 1 : 0;
+  p.tma_out = (packed || a.N % ATT_BQ == 0) ? 1 : 0;
   p.window = a.window;
   p.lse = a.lse;
-  p.cu = nullptr; p.tile_img = nullptr; p.tile_order = nullptr; p.m_dev = nullptr;
+  p.cu = a.cu; p.tile_img = a.tile_img; p.tile_order = a.tile_order; p.m_dev = a.m_dev;
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
   static const int prof_mode = getenv("VTK_ATTN_PROF") ? atoi(getenv("VTK_ATTN_PROF")) : 0;
   static unsigned long long* d_prof = nullptr;
@@ -1339,6 +1368,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.N + NQ * ATT_BQ - 1) / (NQ * ATT_BQ), a.heads, a.B);
+  if (packed) grid = dim3((unsigned)(Mrows / (NQ * ATT_BQ)), a.heads, 1);
   kern<<<grid, S::THREADS, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   if (prof_mode) {
     unsigned long long h[8];
@@ -1355,7 +1385,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.B <= 0 || a.N <= 0 || a.heads <= 0) { set_error("attention: empty problem"); return -2; }
   if ((a.ld_qkv % 8) || (a.ld_out % 8)) { set_error("attention: row strides must be multiples of 8"); return -2; }
-  if (a.cu && a.d != 64) { set_error("attention: the packed layout is implemented for head_dim 64 only"); return -3; }
+  if (a.cu && a.d != 64 && a.d != 128) { set_error("attention: the packed layout is implemented for head_dim 64 and 128"); return -3; }
   if (a.d == 64) {
     // perf experiments: VTK_ATTN_NQ = 0 (default) persistent kernel, 1 = one-shot CTAs (2 per SM), 2 = one-shot, one CTA per SM
     static const int nq = getenv("VTK_ATTN_NQ") ? atoi(getenv("VTK_ATTN_NQ")) : 0;

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t* __restri
 // key tiles of their image, longest first (counting sort; ties in arbitrary order) -- the attention kernel deals its
 // work items from this list so that every persistent CTA gets the same mix of long and short items.
 __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__ n_valid, int* __restrict__ cu,
-                                                         int* __restrict__ tile_img, int* __restrict__ tile_order, int B, int N) {
+                                                         int* __restrict__ tile_img, int* __restrict__ tile_order, int B, int N,
+                                                         int pad) {
   constexpr int MAX_BINS = 2048;
   __shared__ int warp_tot[32];
   __shared__ int running;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__
   __syncthreads();
   for (int b0 = 0; b0 < B; b0 += 1024) {
     const int b = b0 + tid;
-    const int padded = b < B ? ((n_valid[b] + 127) & ~127) : 0;
+    const int padded = b < B ? ((n_valid[b] + pad - 1) / pad * pad) : 0;   // pad = 128, or 256 for the two-tile CTAs of d = 128
     int incl = padded;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__
   }
   if (tid == 0) cu[B] = running;
   // ---- tile order: counting sort by key tiles per image, descending ----
-  const int nbins = (N + 127) / 128;           // an image has 1 .. nbins tiles
+  const int nbins = (N + pad - 1) / pad * (pad / 128);   // an image has 1 .. nbins 128-row tiles
   const int ntiles = running >> 7;
   if (nbins > MAX_BINS) {                      // very long sequences: keep the natural order
     for (int t = tid; t < ntiles; t += 1024) tile_order[t] = t;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__
   for (int i = tid; i <= nbins; i += 1024) bins[i] = 0;
   __syncthreads();
   for (int b = tid; b < B; b += 1024) {
-    const int kt = (n_valid[b] + 127) >> 7;
+    const int kt = ((n_valid[b] + pad - 1) / pad * pad) >> 7;
     if (kt > 0) atomicAdd(&bins[kt], kt);      // an image with kt key tiles contributes kt query tiles
   }
   __syncthreads();
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__
   }
   __syncthreads();
   for (int b = tid; b < B; b += 1024) {
-    const int kt = (n_valid[b] + 127) >> 7;
+    const int kt = ((n_valid[b] + pad - 1) / pad * pad) >> 7;
     if (kt > 0) {
       const int at = atomicAdd(&bins[kt], kt);
       const int first = cu[b] >> 7;
@@ -333,14 +334,14 @@ __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__
 
 // one CTA per image: src[packed row] = source token row b*N + t, or -1 for the pad rows of the image's last tile
 __global__ void __launch_bounds__(256) pack_src_kernel(const int* __restrict__ rel, const int* __restrict__ n_valid,
-                                                       const int* __restrict__ cu, int* __restrict__ src, int N) {
+                                                       const int* __restrict__ cu, int* __restrict__ src, int N, int pad) {
   const int b = blockIdx.x;
   const int base = cu[b], n = n_valid[b];
   for (int t = threadIdx.x; t < N; t += 256) {
     const int r = rel[(long long)b * N + t];
     if (r >= 0) src[base + r] = b * N + t;
   }
-  for (int p = n + threadIdx.x; p < ((n + 127) & ~127); p += 256) src[base + p] = -1;
+  for (int p = n + threadIdx.x; p < (n + pad - 1) / pad * pad; p += 256) src[base + p] = -1;
 }
 
 // packed[r, :] = in[src[r], :] (zeros for pad rows); rows of `width` bf16 (width % 8 == 0), 16-byte vectors
@@ -378,8 +379,9 @@ __global__ void __launch_bounds__(256) unpack_rows_kernel(const bf16* __restrict
 int launch_pack_plan(const uint8_t* mask, int B, int N, const PackPlan& pl, cudaStream_t stream) {
   if (B <= 0 || N <= 0) return 0;
   pack_count_kernel<<<B, 256, 0, stream>>>(mask, pl.rel, pl.n_valid, N);
-  pack_plan_kernel<<<1, 1024, 0, stream>>>(pl.n_valid, pl.cu, pl.tile_img, pl.tile_order, B, N);
-  pack_src_kernel<<<B, 256, 0, stream>>>(pl.rel, pl.n_valid, pl.cu, pl.src, N);
+  if (pl.pad != 128 && pl.pad != 256) { set_error("pack_plan: row padding must be 128 or 256 (got %d)", pl.pad); return -2; }
+  pack_plan_kernel<<<1, 1024, 0, stream>>>(pl.n_valid, pl.cu, pl.tile_img, pl.tile_order, B, N, pl.pad);
+  pack_src_kernel<<<B, 256, 0, stream>>>(pl.rel, pl.n_valid, pl.cu, pl.src, N, pl.pad);
   return check_cuda(cudaGetLastError(), "pack_plan launch");
 }
 

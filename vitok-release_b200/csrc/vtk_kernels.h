@@ -121,6 +121,7 @@ int launch_rope_table(const int64_t* row_idx, const int64_t* col_idx, const floa
 // padded to a multiple of 128 rows.  All arrays live in device memory (carved from the caller's workspace).
 struct PackPlan {
   int B, N;
+  int pad = 128;   // rows every image is padded to in the packed layout: 128, or 256 when the attention CTA owns two query tiles (d = 128)
   int* n_valid;    // [B]      valid tokens per image (= key count of the image in the packed layout)
   int* rel;        // [B * N]  rank of a token among the valid tokens of its image, -1 if masked
   int* cu;         // [B + 1]  packed row offset per image; cu[B] = packed row count (the m_dev of every kernel)
@@ -128,7 +129,7 @@ struct PackPlan {
   int* tile_order; // [B * ceil(N / 128)]  packed tiles sorted by key tiles of their image, longest first (attention work list)
   int* src;        // [B * ceil128(N)]     packed row -> source row b * N + t, -1 for pad rows
   const int* m_dev() const { return cu + B; }
-  static long long row_capacity(int B, int N) { return (long long)B * ((N + 127) / 128 * 128); }
+  static long long row_capacity(int B, int N, int pad = 128) { return (long long)B * ((N + pad - 1) / pad * pad); }
 };
 int launch_pack_plan(const uint8_t* mask, int B, int N, const PackPlan& pl, cudaStream_t stream);
 int launch_pack_rows(const bf16* in, long long ld_in, const PackPlan& pl, long long row_cap, bf16* out, long long ld_out, int width,
