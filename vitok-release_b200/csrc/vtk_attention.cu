@@ -181,6 +181,38 @@ __device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[NCH][32], uint64_
   }
 }
 
+// Same, but P goes to TENSOR MEMORY (columns [tP, tP + 64) of the thread's lane: key pair q -> 32-bit column q, low half =
+// key 2q) as the A operand of a tcgen05.mma that reads A from TMEM: no 32 KB shared-memory write + read per tile.
+__device__ __forceinline__ void softmax_exp_tile_tmem(uint32_t (&v)[4][32], uint64_t sc2, uint64_t nm2, uint32_t tP,
+                                                      uint64_t& sum2a, uint64_t& sum2b) {
+#pragma unroll
+  for (int pr = 0; pr < 64; ++pr) {
+    float e0, e1;
+    f2_unpack(f2_fma(f2_pack(__uint_as_float(v[pr >> 4][2 * (pr & 15)]), __uint_as_float(v[pr >> 4][2 * (pr & 15) + 1])), sc2, nm2), e0, e1);
+    v[pr >> 4][2 * (pr & 15)] = __float_as_uint(e0);
+    v[pr >> 4][2 * (pr & 15) + 1] = __float_as_uint(e1);
+  }
+  constexpr int DIST = 3;
+  uint32_t pk[8];
+#pragma unroll
+  for (int pr = 0; pr < 64 + DIST; ++pr) {
+    if (pr < 64) {
+      uint32_t& a = v[pr >> 4][2 * (pr & 15)];
+      uint32_t& b = v[pr >> 4][2 * (pr & 15) + 1];
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a));
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(b));
+    }
+    if (pr >= DIST) {
+      const int q = pr - DIST;
+      const float e0 = __uint_as_float(v[q >> 4][2 * (q & 15)]), e1 = __uint_as_float(v[q >> 4][2 * (q & 15) + 1]);
+      if (q & 1) sum2b = f2_add(sum2b, f2_pack(e0, e1));
+      else sum2a = f2_add(sum2a, f2_pack(e0, e1));
+      pk[q & 7] = bf2_cvt(e0, e1);
+      if ((q & 7) == 7) tmem_st8(tP + (q & ~7), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+    }
+  }
+}
+
 // pairs 1, 4 and 6 of every 8 on the FMA pipe (37.5 %); VTK_ATTN_EMU=0 at build time (-DVTK_ATTN_EMU_MASK=0) = MUFU only
 #ifndef VTK_ATTN_EMU_MASK
 #define VTK_ATTN_EMU_MASK 0u
@@ -609,13 +641,14 @@ __device__ __forceinline__ bool item_at(int k, int total, int& w) {
   return base < total;
 }
 
-template <int DH, uint32_t EMU, bool SNAKE>
+template <int DH, uint32_t EMU, bool SNAKE, bool PTMEM = false>
 __global__ void __launch_bounds__(192, 2)
 attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
                     const int total_items_host, const int qtiles) {
   using S = AttnShape<DH, 1>;
   static_assert(DH == 64, "persistent attention: d = 64 only");
+  constexpr uint32_t P_COL = S::O_COL0 + DH;   // PTMEM: P (bf16, 128 keys = 64 columns) after S [0,128) and O [128,192)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int W = p.window;
@@ -727,9 +760,13 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t va = smem_u32(sV + slot * S::TILE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-            const uint64_t adesc = make_desc_kmajor_sw128(pa + (kk >> 2) * BLK + (kk & 3) * 32);
             const uint64_t bdesc = make_smem_desc(va + kk * 2048, BLK, 1024, 2);
-            umma_bf16_ss(tmem_base + S::O_COL0, adesc, bdesc, idesc_o, (jj | kk) != 0 ? 1u : 0u);
+            if (PTMEM) {   // A = P from tensor memory: 16 keys = 8 packed 32-bit columns per MMA
+              umma_bf16_ts(tmem_base + S::O_COL0, tmem_base + P_COL + kk * 8, bdesc, idesc_o, (jj | kk) != 0 ? 1u : 0u);
+            } else {
+              const uint64_t adesc = make_desc_kmajor_sw128(pa + (kk >> 2) * BLK + (kk & 3) * 32);
+              umma_bf16_ss(tmem_base + S::O_COL0, adesc, bdesc, idesc_o, (jj | kk) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&v_empty[slot]);
           umma_commit(pv_done);
@@ -822,13 +859,18 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           __syncwarp();
           tc_fence_after();
         }
-        if (store_pending) {
+        if (!PTMEM && store_pending) {   // (PTMEM: the staging buffer is not P's; it is awaited in the epilogue)
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
           store_pending = false;
         }
         const long long k4 = PCLK();
-      softmax_exp_tile<EMU>(v, sc2, nm2, prow, r, sum2a, sum2b);
+        if (PTMEM) {
+          softmax_exp_tile_tmem(v, sc2, nm2, tmem_base + lane_base + P_COL, sum2a, sum2b);
+          tmem_wait_st();
+        } else {
+          softmax_exp_tile<EMU>(v, sc2, nm2, prow, r, sum2a, sum2b);
+        }
         const long long k5 = PCLK();
         float sum0, sum1;
         f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
@@ -871,6 +913,11 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_wait_ld();
       tc_fence_before();
       if (p.tma_out) {
+        if (PTMEM && store_pending) {   // the previous item's TMA store has read the staging rows
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          store_pending = false;
+        }
         uint8_t* srow = sP + r * 128;   // O staged in block 0 of the P buffer (free: its last PV has completed)
 #pragma unroll
         for (int c = 0; c < DH / 32; ++c)
@@ -1296,14 +1343,18 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   // so the ~1660 cycles per 128 x 128 tile per SM are not MUFU contention between lock-stepped warps (S read-back from TMEM,
   // 64 KB per tile, is the next suspect).  It stays an opt-in experiment.
   static const int split = getenv("VTK_ATTN_SPLIT") ? atoi(getenv("VTK_ATTN_SPLIT")) : 0;
+  // P stays in tensor memory (A operand of the PV MMA read from TMEM, no 32 KB shared-memory round trip per tile): 3-4 % faster
+  // than the shared-memory P buffer (43.9 vs 45.6 us at the c2 shape); VTK_ATTN_PTMEM=0 selects the shared-memory variant
+  static const int ptmem = getenv("VTK_ATTN_PTMEM") ? atoi(getenv("VTK_ATTN_PTMEM")) : 1;
   const bool use_split = split != 0 && !prof_mode && emu == 0;
   auto kern = use_split ? (packed ? attn_split_kernel<64, true> : attn_split_kernel<64, false>)
-              : packed ? attn_persist_kernel<64, 0u, true>
+              : packed ? (ptmem ? attn_persist_kernel<64, 0u, true, true> : attn_persist_kernel<64, 0u, true>)
+              : ptmem ? attn_persist_kernel<64, 0u, false, true>
               : emu == 0x52 ? attn_persist_kernel<64, 0x52u, false>
               : emu == 0xFFFF ? attn_persist_kernel<64, 0xFFFFu, false>
               : emu == 0xFFFE ? attn_persist_kernel<64, 0xFFFEu, false> : attn_persist_kernel<64, 0u, false>;
-  static bool attr_set[4] = {false, false, false, false};
-  const int ai = (packed ? 1 : 0) + (use_split ? 2 : 0);
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  const int ai = (packed ? 1 : 0) + (use_split ? 2 : 0) + (ptmem ? 4 : 0);
   if (!attr_set[ai]) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES), "cudaFuncSetAttribute(attn_persist)"))
       return -1;
