@@ -207,3 +207,31 @@ def test_torch_compile_fullgraph_encode_decode():
         d1 = dec_c(e1)
     assert torch.equal(e0["z"], e1["z"]) and torch.equal(d0["patches"], d1["patches"])
     assert set(e1) == set(e0) and set(d1) == set(d0)
+
+
+@pytest.mark.parametrize("backend", ["sdpa", "flash"])
+def test_5b_width_shallow_vs_oracle(backend):
+    """The 5B models' widths (D = 3072, 24 heads of 128, Hf = 8208, BASELINE configs[3]) on a 1 + 2 block stack: the d = 128
+    attention kernel, the K / N tails of Hf, norm1 fused over 48 column units and (sdpa) token packing with 256-row padding,
+    end to end against the fp32 CPU oracle under stress init."""
+    variant = "w3072_d1_h24-w3072_d2_h24/1x16x64"
+    cfg0 = ae_oracle.decode_variant(variant)
+    sd = make_state_dict(cfg0, seed=3, stress=True)
+    model, cfg = _model(variant, sd, backend)
+    batch = _batch([(256, 192), (144, 100), (320, 320)], 16, 400, seed=9)
+    with torch.no_grad():
+        enc = model.encode(_to_cuda(batch))
+        dec = model.decode(enc)
+    valid = batch["patch_mask"] if backend == "sdpa" else torch.ones_like(batch["patch_mask"])
+    e_o = ae_oracle.encode(sd, batch, cfg["encoder_heads"], attn_backend=backend)
+    d_o = ae_oracle.decode(sd, e_o, cfg["decoder_heads"], attn_backend=backend)
+    sdb = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    bb = {k: (v.to(torch.bfloat16) if v.dtype == torch.float32 else v) for k, v in batch.items()}
+    e_b = ae_oracle.encode(sdb, bb, cfg["encoder_heads"], attn_backend=backend)
+    d_b = ae_oracle.decode(sdb, e_b, cfg["decoder_heads"], attn_backend=backend)
+    own_z = (e_b["z"].float() - e_o["z"])[valid].abs().max().item()
+    own_p = (d_b["patches"].float() - d_o["patches"])[valid].abs().max().item()
+    ma_z, _ = report(f"5B-width {backend} z", enc["z"].cpu().float()[valid], e_o["z"][valid])
+    ma_p, _ = report(f"5B-width {backend} patches", dec["patches"].cpu().float()[valid], d_o["patches"][valid])
+    print(f"[parity] reference-bf16 own error: z {own_z:.3e} patches {own_p:.3e}")
+    assert ma_z <= max(2 * own_z, 5e-2) and ma_p <= max(2 * own_p, 5e-2)
