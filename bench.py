@@ -228,6 +228,8 @@ def run_ours(args, rank, world, local):
     cfg = vb.decode_variant(variant)
     torch.manual_seed(0)
     model = vb.AE(**cfg, attn_backend=backend).eval().to(device=dev, dtype=torch.bfloat16)
+    if args.quantize:
+        model.quantize()
     g = torch.Generator().manual_seed(1234 + rank)
     patch = cfg["spatial_stride"]
     ragged = res == 0
@@ -432,7 +434,8 @@ def run_ours(args, rank, world, local):
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp8 e4m3 block GEMMs (AE.quantize), bf16 elsewhere" if args.quantize else "bf16",
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {variant} encode+decode @{_res_name(res)}, batch {B}/GPU", "variant": variant,
                    "resolution": res, "tokens_per_image": N, "valid_tokens_per_gpu": sum(n_valid),
@@ -534,6 +537,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--quantize", action="store_true",
+                    help="AE.quantize(): FP8 (e4m3) block GEMMs -- a separate, reduced-precision line; the headline stays bf16")
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))

@@ -104,6 +104,15 @@ int vtk_pack_rows(const void* in, int64_t ld_in, const int* src, const int* cu, 
 int vtk_unpack_rows(const void* packed, int64_t ld_packed, const int* rel, const int* cu, int B, int N, void* out,
                     int64_t ld_out, int width, void* stream);
 
+/* FP8 inference building blocks (reference AE.quantize, vitok/models/ae.py:253-270 = torchao
+ * Float8DynamicActivationFloat8WeightConfig on the Linears of every block).
+ * vtk_quant_rows_e4m3: dynamic per-row activation quantisation, q[row,:K] = e4m3(x[row,:K] / scale[row]), scale = amax / 448.
+ * vtk_proj_residual_fp8: x += gamma * (scale_a[row] * w_scale * (A8 W8^T)) with e4m3 operands on the tcgen05 kind::f8f6f4 path
+ * (lda / ldw / K in bytes = elements, multiples of 16). */
+int vtk_quant_rows_e4m3(const void* x, int64_t ldx, void* q, int64_t ldq, float* scale, int M, int K, void* stream);
+int vtk_proj_residual_fp8(const void* A8, int64_t lda, const float* a_scale, const void* W8, int64_t ldw, float w_scale,
+                          const void* gamma, void* x, int64_t ldx, int M, int N, int K, void* stream);
+
 /* out = bf16(A W^T + bias); bias may be null.                      nn.Linear: vitok/models/ae.py:191,220,242 */
 int vtk_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
                     int M, int N, int K, void* stream);
@@ -229,6 +238,19 @@ int vtk_ae_decode(vtk_ae_t h, const void* z, const int64_t* row_idx, const int64
  * per-row sums of squares, and the QKV+fc1 GEMM reads x directly and scales every accumulator row by
  * rsqrt(mean(x^2) + eps): h W^T = rstd * (x (W*w)^T).  Needs width % 256 == 0.  folded = 0 (default): separate RMSNorm. */
 int vtk_ae_set_norm_folded(vtk_ae_t h, int side, int folded);
+/* FP8 inference (AE.quantize, vitok/models/ae.py:253-270).  After vtk_ae_set_weights + vtk_ae_set_norm_folded(.., 1): hand over, per
+ * block, e4m3 copies of the packed weights (w_in8 [qp + 2*Hf, D], w_out8 [D, Kp], one byte per element, same packing and row
+ * pitches in ELEMENTS as the bf16 ones) and their per-tensor scales (w ~= w8 * scale).  From then on the two GEMMs of every
+ * block of that side run on the tcgen05 kind::f8f6f4 path: their A operands (x, [attn | act]) are quantised per row on the fly
+ * (vtk_quant_rows_e4m3) and the epilogues rescale the accumulators; attention, embeds and the latent bottleneck stay bf16.
+ * nblocks = 0 switches the side back to bf16.  The pointers must stay valid (caller-owned), like the bf16 weights. */
+typedef struct vtk_block_fp8 {
+  const void* w_in8;
+  const void* w_out8;
+  float w_in_scale;
+  float w_out_scale;
+} vtk_block_fp8;
+int vtk_ae_set_fp8_weights(vtk_ae_t h, int side, const vtk_block_fp8* blocks, int nblocks);
 /* NaFlex token packing (default on).  When a patch_mask is given and head_dim == 64, vtk_ae_encode/decode gather the
  * valid tokens of every image into a packed row range (each image padded to a multiple of 128 rows), run every kernel
  * of the layer stack over the packed rows only -- the packed row count stays in device memory, nothing syncs -- and

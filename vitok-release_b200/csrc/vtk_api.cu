@@ -78,6 +78,26 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner_elems, u
   return 0;
 }
 
+// 2-D row-major tensor of bytes (fp8 e4m3), 128-byte swizzle: inner box = 128 elements = 128 bytes
+int encode_tmap_u8_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows, uint64_t row_stride_bytes,
+                         uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return VTK_ERR_CUDA;
+  cuuint64_t gdim[2] = {inner_elems, rows};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(u8) failed (CUresult %d) base=%p inner=%llu rows=%llu stride=%llu box_rows=%u", (int)r, base,
+              (unsigned long long)inner_elems, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_rows);
+    return VTK_ERR_CUDA;
+  }
+  return 0;
+}
+
 int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
                            uint64_t row_stride_elems, uint32_t box_rows) {
   return encode_tmap_bf16(out, base, inner_elems, rows, row_stride_elems, 64, box_rows, 128);
@@ -90,6 +110,7 @@ struct Side {
   int width = 0, depth = 0, heads = 0, hidden = 0;
   const bf16 *w_a = nullptr, *b_a = nullptr, *w_b = nullptr, *b_b = nullptr;
   std::vector<vtk_block_weights> blocks;
+  std::vector<vtk_block_fp8> fp8;   // non-empty: the block GEMMs run with e4m3 operands (AE.quantize)
   float* inv_freq = nullptr;  // device, d/4 floats
   bool norm_folded = false;   // w_in has norm1.weight folded into its columns: norm1 runs inside the GEMM epilogues
   int head_dim() const { return heads ? width / heads : 0; }
@@ -101,6 +122,8 @@ struct Side {
 
 struct Workspace {
   bf16 *x, *h, *qkv, *a2, *rope;
+  uint8_t *x8, *a28;    // FP8 inference: e4m3 copies of x and of [attn | act], and their per-row scales
+  float *sx, *sa;
   float* ss;            // [rows, D / 64] per-unit sums of squares of x (fused norm1)
   int *kv_len, *is_prefix;
   PackPlan plan;        // NaFlex token packing (masked batches): plan arrays + packed input / output staging rows
@@ -128,6 +151,13 @@ static Workspace carve(const Side& s, void* base, int B, int N, int io_cols) {
   w.a2 = static_cast<bf16*>(take((size_t)M * s.kp() * 2));
   w.rope = static_cast<bf16*>(take((size_t)((M + 31) / 32 * 32) * 2 * d * 2));   // pair-expanded table, 32-row groups
   w.ss = static_cast<float*>(take((size_t)M * ((D + 63) / 64) * 4));
+  w.x8 = w.a28 = nullptr; w.sx = w.sa = nullptr;
+  if (!s.fp8.empty()) {
+    w.x8 = static_cast<uint8_t*>(take((size_t)M * D));
+    w.a28 = static_cast<uint8_t*>(take((size_t)M * s.kp()));
+    w.sx = static_cast<float*>(take((size_t)M * 4));
+    w.sa = static_cast<float*>(take((size_t)M * 4));
+  }
   w.kv_len = static_cast<int*>(take((size_t)B * 4));
   w.is_prefix = static_cast<int*>(take((size_t)B * 4));
   w.plan.B = B; w.plan.N = N; w.plan.pad = pad;
@@ -330,6 +360,21 @@ int vtk_proj_residual_bf16(const void* A, int64_t lda, const void* W, int64_t ld
   return launch_gemm(EPI_RESID, g, (cudaStream_t)stream);
 }
 
+int vtk_quant_rows_e4m3(const void* x, int64_t ldx, void* q, int64_t ldq, float* scale, int M, int K, void* stream) {
+  VTK_REQUIRE(x && q && scale, "vtk_quant_rows_e4m3: null pointer");
+  return launch_quant_rows_e4m3((const bf16*)x, ldx, (uint8_t*)q, ldq, scale, M, K, nullptr, (cudaStream_t)stream);
+}
+
+int vtk_proj_residual_fp8(const void* A8, int64_t lda, const float* a_scale, const void* W8, int64_t ldw, float w_scale,
+                          const void* gamma, void* x, int64_t ldx, int M, int N, int K, void* stream) {
+  VTK_REQUIRE(A8 && a_scale && W8 && gamma && x, "vtk_proj_residual_fp8: null pointer");
+  VTK_REQUIRE(ldx % 8 == 0, "vtk_proj_residual_fp8: ldx must be a multiple of 8");
+  GemmArgs g = base_args(A8, lda, W8, ldw, N, M, N, K);
+  g.fp8 = 1;
+  g.epi.out = (bf16*)x; g.epi.ldo = ldx; g.epi.gamma = (const bf16*)gamma; g.epi.a_scale = a_scale; g.epi.w_scale = w_scale;
+  return launch_gemm(EPI_RESID, g, (cudaStream_t)stream);
+}
+
 int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
                        const int* kv_len, const uint8_t* key_mask, const int* is_prefix, int B, int N, int heads, int d,
                        int zero_invalid_rows, int window, float* lse, void* stream) {
@@ -491,6 +536,7 @@ int vtk_ae_set_weights(vtk_ae_t h, int side, const void* w_a, const void* b_a, c
   VTK_REQUIRE(n_inv_freq == s.head_dim() / 4 && inv_freq_host, "vtk_ae_set_weights: inv_freq must have head_dim/4 entries");
   s.w_a = (const bf16*)w_a; s.b_a = (const bf16*)b_a; s.w_b = (const bf16*)w_b; s.b_b = (const bf16*)b_b;
   s.norm_folded = false;
+  s.fp8.clear();
   s.blocks.assign(blocks, blocks + nblocks);
   for (int i = 0; i < nblocks; ++i) {
     const vtk_block_weights& b = s.blocks[i];
@@ -540,7 +586,15 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
       if (r) return r;
       ++launches;
     }
-    GemmArgs g1 = base_args(fused ? w.x : w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
+    const bool f8 = !s.fp8.empty();     // AE.quantize: e4m3 operands for both block GEMMs (needs the fused norm)
+    if (f8) {
+      { LaunchTimer t(h, st, CLS_MISC); r = launch_quant_rows_e4m3(w.x, D, w.x8, D, w.sx, M, D, m_dev, st); }
+      if (r) return r;
+      ++launches;
+    }
+    GemmArgs g1 = f8 ? base_args(w.x8, D, s.fp8[i].w_in8, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D)
+                     : base_args(fused ? w.x : w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
+    if (f8) { g1.fp8 = 1; g1.epi.a_scale = w.sx; g1.epi.w_scale = s.fp8[i].w_in_scale; }
     if (fused) { g1.epi.ss_in = w.ss; g1.epi.ss_units = D / 64; g1.epi.ss_inv_d = 1.f / (float)D; }
     g1.epi.qkv = w.qkv; g1.epi.ld_qkv = 3 * D; g1.epi.act = w.a2 + D; g1.epi.ld_act = kp;
     g1.epi.normq = (const bf16*)b.norm_q; g1.epi.normk = (const bf16*)b.norm_k; g1.epi.rope = w.rope;
@@ -565,7 +619,13 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
     a.lse = nullptr;
     { LaunchTimer t(h, st, CLS_ATTENTION); r = launch_attention(a, st); }
     if (r) return r;
-    GemmArgs g2 = base_args(w.a2, kp, b.w_out, kp, D, M, D, D + Hf);
+    if (f8) {
+      { LaunchTimer t(h, st, CLS_MISC); r = launch_quant_rows_e4m3(w.a2, kp, w.a28, kp, w.sa, M, D + Hf, m_dev, st); }
+      if (r) return r;
+      ++launches;
+    }
+    GemmArgs g2 = f8 ? base_args(w.a28, kp, s.fp8[i].w_out8, kp, D, M, D, D + Hf) : base_args(w.a2, kp, b.w_out, kp, D, M, D, D + Hf);
+    if (f8) { g2.fp8 = 1; g2.epi.a_scale = w.sa; g2.epi.w_scale = s.fp8[i].w_out_scale; }
     g2.epi.out = w.x; g2.epi.ldo = D; g2.epi.gamma = (const bf16*)b.gamma;
     g2.epi.m_dev = m_dev;
     if (fused && i + 1 < s.depth) { g2.epi.ss_out = w.ss; g2.epi.ss_ld = D / 64; }
@@ -655,6 +715,20 @@ int vtk_ae_set_norm_folded(vtk_ae_t h, int side, int folded) {
   Side& s = h->side[side];
   VTK_REQUIRE(!folded || (s.width > 0 && s.width % 256 == 0), "vtk_ae_set_norm_folded: the fused norm needs width %% 256 == 0 (width=%d)", s.width);
   s.norm_folded = folded != 0;
+  return VTK_OK;
+}
+
+int vtk_ae_set_fp8_weights(vtk_ae_t h, int side, const vtk_block_fp8* blocks, int nblocks) {
+  VTK_REQUIRE(h && (side == 0 || side == 1), "vtk_ae_set_fp8_weights: bad handle/side");
+  Side& s = h->side[side];
+  if (nblocks == 0) { s.fp8.clear(); return VTK_OK; }
+  VTK_REQUIRE(blocks && nblocks == s.depth, "vtk_ae_set_fp8_weights: expected %d blocks, got %d", s.depth, nblocks);
+  VTK_REQUIRE(s.norm_folded, "vtk_ae_set_fp8_weights: the FP8 path needs the fused norm1 (vtk_ae_set_norm_folded, width %% 256 == 0)");
+  VTK_REQUIRE((s.width + s.hidden) % 16 == 0, "vtk_ae_set_fp8_weights: width + hidden must be a multiple of 16");
+  for (int i = 0; i < nblocks; ++i)
+    VTK_REQUIRE(blocks[i].w_in8 && blocks[i].w_out8 && blocks[i].w_in_scale > 0.f && blocks[i].w_out_scale > 0.f,
+                "vtk_ae_set_fp8_weights: null pointer / non-positive scale in block %d", i);
+  s.fp8.assign(blocks, blocks + nblocks);
   return VTK_OK;
 }
 

@@ -199,6 +199,17 @@ __device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t d_tmem, uint64_t ades
       : "memory");
 }
 
+// Same with FP8 (e4m3) operands: kind::f8f6f4, K = 32 elements (= 32 bytes of a K-major row) per instruction, fp32 accumulate.
+__device__ __forceinline__ void umma_f8_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor (tcgen05 "SmemDescriptor", 64-bit):
 //   [0,14)  start address >> 4      [16,30) leading-dim byte offset >> 4
 //   [32,46) stride-dim byte offset >> 4     [46,48) version = 1 (sm_100)
@@ -225,6 +236,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// kind::f8f6f4 with e4m3 A/B (format code 0) and fp32 D; both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------------------------

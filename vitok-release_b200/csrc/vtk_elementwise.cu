@@ -203,6 +203,61 @@ int launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t s
   return check_cuda(cudaGetLastError(), "cast launch");
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP8 inference (reference AE.quantize, ae.py:253-270: torchao Float8DynamicActivationFloat8Weight on every Linear of the
+// blocks): dynamic activation quantisation.  One warp per row: amax over the row, scale = amax / 448, q = e4m3(x / scale)
+// (round to nearest even, saturating); the GEMM epilogue multiplies its accumulator row by scale[row] * weight_scale.
+// Per-row scales (torchao's PerRow granularity) need no grid-wide reduction before the first byte can be written.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {   // bytes (a, b, c, d), a in the low byte
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+
+__global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const bf16* __restrict__ x, long long ldx, uint8_t* __restrict__ q,
+                                                              long long ldq, float* __restrict__ scale, int M, int K,
+                                                              const int* __restrict__ m_dev) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = K >> 3;   // 8 bf16 = 16 bytes in, 8 bytes out
+  if (m_dev) M = min(M, __ldg(m_dev));
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * 8) {
+    const bf16* xr = x + row * ldx;
+    float amax = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 u = ld_global_v4(xr + 8 * v);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fmaxf(fabsf(bf16_lo(w[i])), fabsf(bf16_hi(w[i]))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float sc = amax > 0.f ? amax / 448.f : 1.f;
+    const float inv = amax > 0.f ? 448.f / amax : 1.f;
+    if (lane == 0) scale[row] = sc;
+    uint8_t* qr = q + row * ldq;
+    for (int v = lane; v < nvec; v += 32) {   // second pass: the row comes from L1 / L2
+      const uint4 u = ld_global_v4(xr + 8 * v);
+      uint2 o;
+      o.x = e4m3x4(bf16_lo(u.x) * inv, bf16_hi(u.x) * inv, bf16_lo(u.y) * inv, bf16_hi(u.y) * inv);
+      o.y = e4m3x4(bf16_lo(u.z) * inv, bf16_hi(u.z) * inv, bf16_lo(u.w) * inv, bf16_hi(u.w) * inv);
+      *reinterpret_cast<uint2*>(qr + 8 * v) = o;
+    }
+  }
+}
+
+int launch_quant_rows_e4m3(const bf16* x, long long ldx, uint8_t* q, long long ldq, float* scale, int M, int K, const int* m_dev,
+                           cudaStream_t stream) {
+  if (K % 8 || ldx % 8 || ldq % 8) { set_error("quant_rows: K and the row strides must be multiples of 8"); return -2; }
+  if (M <= 0) return 0;
+  long long blocks = ((long long)M + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  quant_rows_e4m3_kernel<<<(int)blocks, 256, 0, stream>>>(x, ldx, q, ldq, scale, M, K, m_dev);
+  return check_cuda(cudaGetLastError(), "quant_rows launch");
+}
+
 // one warp per image: kv_len = 1 + index of the last valid token (0 if none); is_prefix = mask is all-ones
 // on [0, kv_len).
 __global__ void kv_len_kernel(const uint8_t* __restrict__ mask, int* __restrict__ kv_len, int* __restrict__ is_prefix,

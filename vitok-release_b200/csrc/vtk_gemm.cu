@@ -138,6 +138,13 @@ __device__ __forceinline__ float u4_hi(const uint4& v, int i) {   // element 2i+
   return bf16_hi(w);
 }
 
+// GEMM output element pair as bf16: bf16(acc * rs) with rs = the row's fused-norm1 scale (1.0 when norm1 is not fused)
+__device__ __forceinline__ uint32_t cvt_acc2(uint32_t lo_bits, uint32_t hi_bits, uint64_t rs2) {
+  float a, b;
+  f2_unpack(f2_mul(f2_pack(__uint_as_float(lo_bits), __uint_as_float(hi_bits)), rs2), a, b);
+  return bf2_cvt(a, b);
+}
+
 // out = bf16(acc + bias)
 __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
                                               int ucols) {
@@ -185,7 +192,7 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
 // Packed bf16x2 arithmetic: bf2_mul(bf16(acc), gamma) and bf2_add(x, .) round exactly where the reference's
 // eager bf16 ops do (layerscale.py:23, ae.py:64-65), at 1.5 instructions per element.
 __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
-                                               int ucols, OutStage& st, const CUtensorMap* tmX) {
+                                               int ucols, OutStage& st, const CUtensorMap* tmX, uint64_t rs2) {
   uint64_t ss2 = 0ull;   // sum of squares of the new x over this 64-column unit (fused norm1 of the next block)
   for (int cc = 0; cc < ucols; cc += 32) {
     const int col = n + cc;
@@ -213,7 +220,7 @@ __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t tadd
       uint32_t o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        o[i] = bf2_add(xs[i], bf2_mul(bf2_cvt_bits(r[8 * j + 2 * i], r[8 * j + 2 * i + 1]), gs[i]));
+        o[i] = bf2_add(xs[i], bf2_mul(cvt_acc2(r[8 * j + 2 * i], r[8 * j + 2 * i + 1], rs2), gs[i]));   // rs2 = 1 unless FP8
       st.put(j, o[0], o[1], o[2], o[3]);
       if (p.ss_out && j < nch) {
 #pragma unroll
@@ -293,13 +300,6 @@ __device__ __forceinline__ void epi_bias_ln_row(const EpiParams& p, uint32_t tad
 __device__ __forceinline__ const uint4* rope_row_ptr(const EpiParams& p, int rrow) {
   const long long grp = rrow >> 5;
   return reinterpret_cast<const uint4*>(p.rope) + (grp * (p.d >> 2)) * 32 + (rrow & 31);
-}
-
-// GEMM output element pair as bf16: bf16(acc * rs) with rs = the row's fused-norm1 scale (1.0 when norm1 is not fused)
-__device__ __forceinline__ uint32_t cvt_acc2(uint32_t lo_bits, uint32_t hi_bits, uint64_t rs2) {
-  float a, b;
-  f2_unpack(f2_mul(f2_pack(__uint_as_float(lo_bits), __uint_as_float(hi_bits)), rs2), a, b);
-  return bf2_cvt(a, b);
 }
 
 // One q or k head: per-head RMSNorm over d (fp32, eps inside rsqrt; attention.py:103, norm.py:22-25) then
@@ -492,6 +492,7 @@ __device__ __forceinline__ uint64_t row_scale2(const EpiParams& p, int rrow) {
     }
     rs = rsqrtf(ss * p.ss_inv_d + p.eps);
   }
+  if (p.a_scale) rs *= __ldg(p.a_scale + rrow) * p.w_scale;   // FP8 operands: dynamic per-row activation scale x weight scale
   return f2_pack(rs, rs);
 }
 
@@ -643,7 +644,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int U = (EPI == EPI_QKV_SWIGLU && epi.d > 64) ? epi.d : 64;
         for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
           if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
-          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0);
+          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0, f2_pack(1.f, 1.f));
           if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1, rs2);
         }
       }
@@ -734,7 +735,7 @@ template <bool P> __device__ __forceinline__ long long prof_clock() {
   return 0;
 }
 
-template <int EPI, int NEPI, int G2_STAGES, bool PROF>
+template <int EPI, int NEPI, int G2_STAGES, bool PROF, bool FP8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M_cap, const int N,
@@ -764,7 +765,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int num_k = (K + BK - 1) / BK;
+  constexpr int BKE = FP8 ? 2 * BK : BK;   // elements per k-block: one 128-byte swizzle row of bf16 (64) or e4m3 (128)
+  const int num_k = (K + BKE - 1) / BKE;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -811,9 +813,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           w_empty += prof_clock<PROF>() - c0;
           const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
           if (rank == 0) mbar_expect_tx(&full[s], tx);
-          tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BK, m0 + (int)rank * BM);
+          tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BKE, m0 + (int)rank * BM);
           for (int nb = 0; nb < hw; nb += 64)
-            tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BK, n0 + (int)rank * hw + nb);
+            tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb);
           if (++s == G2_STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -831,7 +833,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int t = cluster_id; t < sched.total_tiles; t += num_clusters) {
         int m0, n0, width;
         sched.decode(t, m0, n0, width);
-        const uint32_t idesc = make_idesc_bf16(2 * BM, width, 0, 0);
+        const uint32_t idesc = FP8 ? make_idesc_e4m3(2 * BM, width) : make_idesc_bf16(2 * BM, width, 0, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G2_BN);
         long long c0 = prof_clock<PROF>();
         mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -846,8 +848,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t b0 = smem_u32(sB + s * G2_B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
+            if (FP8) umma_f8_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
+                                   (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_2cta(&empty[s]);   // slot reusable in both CTAs
           if (++s == G2_STAGES) { s = 0; ph ^= 1; }
@@ -888,7 +892,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       st.row0 = m0 + quarter * 32;
       const int rrow = row < M ? row : (M - 1);
       uint64_t rs2 = 0ull;
-      if (EPI == EPI_QKV_SWIGLU) rs2 = row_scale2(epi, rrow);
+      if (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID) rs2 = row_scale2(epi, rrow);
       if (EPI == EPI_QKV_SWIGLU && n0 < 2 * epi.D) {
         // q/k tile: pull this warp's 32 RoPE-table rows (one contiguous 32 * 4d-byte block, thanks to the
         // chunk-major layout) into L1 while the accumulator is still being computed
@@ -912,7 +916,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int U = (EPI == EPI_QKV_SWIGLU && epi.d > 64) ? epi.d : 64;
         for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
           if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
-          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0);
+          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0, rs2);
           if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1, rs2);
         }
       }
@@ -941,8 +945,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 template <int EPI, int NEPI, int G2_STAGES>
 static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
-  if (encode_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BM)) return -1;
-  if (encode_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.b_rows, (uint64_t)a.ldb, 64)) return -1;
+  if (a.fp8) {
+    if (encode_tmap_u8_sw128(&tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BM)) return -1;
+    if (encode_tmap_u8_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.b_rows, (uint64_t)a.ldb, 64)) return -1;
+  } else {
+    if (encode_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BM)) return -1;
+    if (encode_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.b_rows, (uint64_t)a.ldb, 64)) return -1;
+  }
   TileSched sc;
   sc.bn = G2_BN;
   sc.bm = 2 * BM;
@@ -967,13 +976,14 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
     if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
   }
   const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
-  auto kern = a.epi.prof ? gemm2_kernel<EPI, NEPI, G2_STAGES, true> : gemm2_kernel<EPI, NEPI, G2_STAGES, false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[a.epi.prof ? 1 : 0]) {
+  auto kern = a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true>
+              : a.epi.prof ? gemm2_kernel<EPI, NEPI, G2_STAGES, true> : gemm2_kernel<EPI, NEPI, G2_STAGES, false>;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[a.fp8 ? 2 : a.epi.prof ? 1 : 0]) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
                    "cudaFuncSetAttribute(gemm2)"))
       return -1;
-    attr_set[a.epi.prof ? 1 : 0] = true;
+    attr_set[a.fp8 ? 2 : a.epi.prof ? 1 : 0] = true;
   }
   kern<<<2 * clusters, 128 + 32 * NEPI, smem_bytes, stream>>>(tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi);
   return check_cuda(cudaGetLastError(), "gemm2 launch");
@@ -1054,6 +1064,20 @@ int launch_gemm_inner(EpiKind kind, const GemmArgs& a, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) {
     set_error("gemm: operand pointers must be 16-byte aligned");
     return -2;
+  }
+  if (a.fp8) {   // e4m3 operands: CTA-pair kernel only (any M: rows beyond M are zero-filled by TMA and never stored)
+    if ((a.K % 16) || (a.lda % 16) || (a.ldb % 16)) { set_error("gemm(fp8): K and the row strides must be multiples of 16 bytes"); return -2; }
+    if (kind == EPI_QKV_SWIGLU) {
+      if (!(a.epi.d == 32 || a.epi.d == 64 || a.epi.d == 128) || a.epi.qp % 256 || a.epi.D % a.epi.d || a.epi.Hf % 16) {
+        set_error("gemm(fp8): unsupported attention geometry D=%d d=%d Hf=%d qp=%d", a.epi.D, a.epi.d, a.epi.Hf, a.epi.qp);
+        return -3;
+      }
+      return launch_gemm2_s<EPI_QKV_SWIGLU, 8, 6>(a, stream);
+    }
+    if (kind == EPI_RESID) return launch_gemm2_s<EPI_RESID, 8, 6>(a, stream);
+    if (kind == EPI_BIAS) return launch_gemm2_s<EPI_BIAS, 8, 6>(a, stream);
+    set_error("gemm(fp8): epilogue %d has no FP8 variant", (int)kind);
+    return -3;
   }
   switch (kind) {
     case EPI_BIAS:

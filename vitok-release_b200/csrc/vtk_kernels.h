@@ -19,6 +19,9 @@ int num_sms();
 // Encode a 2-D bf16 row-major tensor map with 128-byte swizzle: inner box = 64 elements.
 int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
                            uint64_t row_stride_elems, uint32_t box_rows);
+// fp8 (1-byte elements): inner box = 128 elements, 128-byte swizzle
+int encode_tmap_u8_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows, uint64_t row_stride_bytes,
+                         uint32_t box_rows);
 // General form: box = box_inner x box_rows elements, swizzle_bytes in {0, 32, 64, 128} (box_inner * 2 <= swizzle span).
 int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows, uint64_t row_stride_elems,
                      uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
@@ -55,6 +58,9 @@ struct EpiParams {
   // columns) multiplies each accumulator row by rsqrt(sum(ss_in[row, 0..ss_units)) * ss_inv_d + eps) before anything else.
   float* ss_out; int ss_ld;
   const float* ss_in; int ss_units; float ss_inv_d;
+  // FP8 operands (GemmArgs::fp8): every accumulator row is multiplied by a_scale[row] * w_scale (per-row activation scale
+  // of the dynamic quantisation x per-tensor weight scale) before anything else, on top of the fused-norm1 scale
+  const float* a_scale; float w_scale;
   const int* m_dev;     // optional: number of rows to process, read on the device (<= GemmArgs::M, which is then the row
                         // capacity of the buffers); used by the packed NaFlex path where sum(n_i) is only known on the GPU
   unsigned long long* prof;  // perf experiments only (env VTK_GEMM_PROF): per-role clock64 accumulators, or null
@@ -66,6 +72,7 @@ struct GemmArgs {
   const bf16* B; long long ldb;   // [N_rows, K], row stride ldb (N_rows may be < N: OOB rows read as 0)
   long long b_rows;
   int M, N, K;                    // N = number of output (packed) columns to cover
+  int fp8;                        // 1: A and B hold e4m3 bytes (lda / ldb / K in elements = bytes); CTA-pair kernel only
   EpiParams epi;
 };
 
@@ -138,6 +145,9 @@ int launch_unpack_rows(const bf16* packed, long long ld_p, const PackPlan& pl, b
                        cudaStream_t stream);
 int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 int launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t stream);
+// dynamic per-row FP8 (e4m3) quantisation: q[row, :K] = e4m3(x[row, :K] / scale[row]), scale[row] = amax(row) / 448
+int launch_quant_rows_e4m3(const bf16* x, long long ldx, uint8_t* q, long long ldq, float* scale, int M, int K, const int* m_dev,
+                           cudaStream_t stream);
 int launch_kv_len(const uint8_t* mask, int* kv_len, int* is_prefix, int B, int N, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------

@@ -34,6 +34,10 @@ class BlockWeights(ctypes.Structure):
     _fields_ = [("w_in", c_vp), ("w_out", c_vp), ("norm1", c_vp), ("norm_q", c_vp), ("norm_k", c_vp), ("gamma", c_vp)]
 
 
+class BlockFp8(ctypes.Structure):
+    _fields_ = [("w_in8", c_vp), ("w_out8", c_vp), ("w_in_scale", ctypes.c_float), ("w_out_scale", ctypes.c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol include/vitok_b200.h declares
 SIGNATURES = {
     "vtk_last_error": (ctypes.c_char_p, []),
@@ -50,6 +54,8 @@ SIGNATURES = {
     "vtk_pack_plan": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vtk_pack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
     "vtk_unpack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
+    "vtk_quant_rows_e4m3": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp]),
+    "vtk_proj_residual_fp8": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_linear_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_linear_ln_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
     "vtk_qkv_swiglu_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
@@ -84,6 +90,7 @@ SIGNATURES = {
     "vtk_ae_last_launch_count": (c_int, [c_vp]),
     "vtk_ae_set_timing": (c_int, [c_vp, c_int]),
     "vtk_ae_set_packing": (c_int, [c_vp, c_int]),
+    "vtk_ae_set_fp8_weights": (c_int, [c_vp, c_int, ctypes.POINTER(BlockFp8), c_int]),
     "vtk_ae_set_norm_folded": (c_int, [c_vp, c_int, c_int]),
     "vtk_ae_collect_timing": (c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_int)]),
 }
@@ -244,6 +251,25 @@ def unpack_rows(packed: torch.Tensor, plan: dict, B: int, N: int) -> torch.Tenso
     out = torch.empty(B, N, W, dtype=torch.bfloat16, device=packed.device)
     check(load().vtk_unpack_rows(ptr(packed), packed.stride(0), ptr(plan["rel"]), ptr(plan["cu"]), B, N, ptr(out), W, W, stream_ptr()))
     return out
+
+
+def quant_rows_e4m3(x: torch.Tensor):
+    """Dynamic per-row FP8 quantisation: returns (q [M, K] float8_e4m3fn, scale [M] fp32) with x ~= q * scale[:, None]."""
+    _req(x, torch.bfloat16, "x")
+    M, K = x.shape
+    q = torch.empty(M, K, dtype=torch.uint8, device=x.device)
+    scale = torch.empty(M, dtype=torch.float32, device=x.device)
+    check(load().vtk_quant_rows_e4m3(ptr(x), x.stride(0), ptr(q), q.stride(0), ptr(scale), M, K, stream_ptr()))
+    return q.view(torch.float8_e4m3fn), scale
+
+
+def proj_residual_fp8(a8, a_scale, w8, w_scale: float, gamma, x):
+    """x += gamma * (a_scale[:, None] * w_scale * (a8 @ w8^T)) with e4m3 operands (tcgen05 kind::f8f6f4)."""
+    M, K = a8.shape
+    N = w8.shape[0]
+    check(load().vtk_proj_residual_fp8(ptr(a8), a8.stride(0), ptr(a_scale), ptr(w8), w8.stride(0), float(w_scale), ptr(gamma),
+                                       ptr(x), x.stride(0), M, N, K, stream_ptr()))
+    return x
 
 
 def qkv_swiglu(h, w_packed, D, d, Hf, qp, norm_q, norm_k, table, eps=1e-6):

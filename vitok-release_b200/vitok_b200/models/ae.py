@@ -106,6 +106,14 @@ def pack_w_in(qkv_w: torch.Tensor, fc1_w: torch.Tensor) -> torch.Tensor:
     return w_in
 
 
+def _quantize_e4m3(w: torch.Tensor):
+    """Per-tensor e4m3 quantisation of a packed weight matrix: returns (uint8 view of the e4m3 bytes, scale) with w ~= w8 * scale."""
+    wf = w.float()
+    amax = float(wf.abs().max())
+    scale = amax / 448.0 if amax > 0 else 1.0
+    return (wf / scale).to(torch.float8_e4m3fn).view(torch.uint8).contiguous(), scale
+
+
 def pack_w_out(out_w: torch.Tensor, fc2_w: torch.Tensor) -> torch.Tensor:
     """[out_proj | fc2 | 0-pad] along K: attn_out + mlp_out becomes one GEMM over the concatenated activations.
 
@@ -297,10 +305,11 @@ class AE(nn.Module):
         w_out [D, Kp]        = [out_proj | fc2 | 0-pad to a multiple of 64]   (one GEMM over the concatenated K)
         Rebuilt whenever a parameter's storage or version changes (load_state_dict, .to(), optimizer step).
         """
-        sig = (self._signature(), bool(fold_norm and self.fuse_norm))
+        sig = (self._signature(), bool(fold_norm and self.fuse_norm), bool(self._quantization_applied and fold_norm))
         if self._handle is not None and sig == self._packed_sig:
             return self._handle
         fold = sig[1]
+        fp8 = sig[2]
         sig0 = sig
         sig = sig[0]
         lib = _lib.load()
@@ -330,6 +339,7 @@ class AE(nn.Module):
             Hf = _ffn_hidden(width, self.mlp_factor)
             qp = ((3 * width + 255) // 256) * 256
             arr = (_lib.BlockWeights * max(len(blocks), 1))()
+            arr8 = (_lib.BlockFp8 * max(len(blocks), 1))()
             for i, blk in enumerate(blocks):
                 if fold and width % 256 == 0:
                     # norm1 folded into the GEMM: h W^T = rstd * (x (W * w)^T)  (include/vitok_b200.h: vtk_ae_set_norm_folded)
@@ -343,6 +353,11 @@ class AE(nn.Module):
                 tens = [w_in, w_out, dev(blk.norm1.weight), dev(blk.attn.norm_q.weight), dev(blk.attn.norm_k.weight), gamma]
                 keep.extend(tens)
                 (arr[i].w_in, arr[i].w_out, arr[i].norm1, arr[i].norm_q, arr[i].norm_k, arr[i].gamma) = [t.data_ptr() for t in tens]
+                if fp8:      # e4m3 copies of the packed matrices, one scale each (w ~= w8 * scale)
+                    q_in, s_in = _quantize_e4m3(w_in)
+                    q_out, s_out = _quantize_e4m3(w_out)
+                    keep.extend([q_in, q_out])
+                    arr8[i].w_in8, arr8[i].w_out8, arr8[i].w_in_scale, arr8[i].w_out_scale = q_in.data_ptr(), q_out.data_ptr(), s_in, s_out
             proj = [dev(lin_a.weight), dev(lin_a.bias), dev(lin_b.weight), dev(lin_b.bias)]
             keep.extend(proj)
             axis = (width // heads) // 2
@@ -351,12 +366,13 @@ class AE(nn.Module):
             _lib.check(lib.vtk_ae_set_weights(self._handle, side, *[t.data_ptr() for t in proj], arr, len(blocks), inv_c,
                                               inv.numel()))
             _lib.check(lib.vtk_ae_set_norm_folded(self._handle, side, 1 if (fold and width % 256 == 0 and len(blocks) > 0) else 0))
+            _lib.check(lib.vtk_ae_set_fp8_weights(self._handle, side, arr8, len(blocks) if (fp8 and len(blocks) > 0) else 0))
             self._packed[side] = keep
         self._packed_sig = sig0
         return self._handle
 
     def _workspace(self, side: int, B: int, N: int, device) -> torch.Tensor:
-        key = (side, B, N, device)
+        key = (side, B, N, device, self._quantization_applied)
         ws = self._ws.get(key)
         if ws is None:
             nbytes = _lib.load().vtk_ae_workspace_bytes(self._handle, side, B, N)
@@ -455,8 +471,21 @@ class AE(nn.Module):
         return x
 
     def quantize(self) -> "AE":
-        """FP8 inference (reference ae.py:253-270 via torchao) -- not built yet; bf16 is the shipped precision."""
-        raise NotImplementedError("vitok_b200.AE.quantize: the FP8 tcgen05 path is not implemented yet (bf16 only)")
+        """FP8 inference (reference ae.py:253-270: torchao ``Float8DynamicActivationFloat8WeightConfig`` on every Linear of the
+        blocks).  The packed block weights are quantised to e4m3 with one scale per packed matrix, the activations entering the
+        two block GEMMs are quantised per row on the fly, and both GEMMs run on the tcgen05 ``kind::f8f6f4`` path; attention, the
+        embeds and the latent bottleneck stay bf16, as in the reference.  Idempotent; inference only."""
+        if self._quantization_applied:
+            return self
+        for _, _, _, blocks, width, _ in self._sides():
+            if len(blocks) and width % 256:
+                raise NotImplementedError(f"vitok_b200.AE.quantize: the FP8 path needs widths that are multiples of 256 (got {width})")
+        if not self.fuse_norm:
+            raise NotImplementedError("vitok_b200.AE.quantize: the FP8 path runs on the fused-norm GEMMs (fuse_norm must stay True)")
+        self._quantization_applied = True
+        self._packed_sig = None      # re-pack (and quantise) on the next call
+        self._ws = {}                # the workspace grows by the e4m3 activation copies
+        return self
 
 
 def Model(**kw):
