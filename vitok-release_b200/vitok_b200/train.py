@@ -75,13 +75,20 @@ class _GradSync:
         import torch.distributed as dist
         self.dist, self.group, self.min_numel = dist, group, min_numel
         self.world = dist.get_world_size(group)
+        self.avg = dist.get_backend(group) == "nccl"     # ReduceOp.AVG is NCCL-only; elsewhere (gloo in the CPU tests): SUM, then scale
         self.pending, self.small = [], []
+
+    def _all_reduce(self, t: torch.Tensor, async_op: bool):
+        if self.avg:
+            return self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        w = self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+        return (w, t) if async_op else t.div_(self.world)
 
     def reduce(self, t: torch.Tensor) -> None:
         if self.world == 1:
             return
         if t.numel() >= self.min_numel and t.is_contiguous():
-            self.pending.append(self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG, group=self.group, async_op=True))
+            self.pending.append(self._all_reduce(t, True))
         else:
             self.small.append(t)
 
@@ -95,13 +102,17 @@ class _GradSync:
                                    and id(t) not in seen]
         if rest:
             flat = torch.cat([t.reshape(-1).float() for t in rest])
-            self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG, group=self.group)
+            self._all_reduce(flat, False)
             off = 0
             for t in rest:
                 t.copy_(flat[off:off + t.numel()].view_as(t))
                 off += t.numel()
         for w in self.pending:
-            w.wait()
+            if isinstance(w, tuple):      # SUM fallback: scale once the sum has arrived
+                w[0].wait()
+                w[1].div_(self.world)
+            else:
+                w.wait()
         self.pending, self.small = [], []
 
 
