@@ -4,7 +4,15 @@ import csv
 import sys
 
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
-first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+first = 0
+if len(sys.argv) > 2:      # an ID, or a kernel-name substring: start at its first launch (skips model set-up)
+    if sys.argv[2].isdigit():
+        first = int(sys.argv[2])
+    else:
+        hdr0 = rows[0]
+        k0, i0 = hdr0.index("Kernel Name"), hdr0.index("ID")
+        hits = [int(r[i0]) for r in rows[1:] if sys.argv[2] in r[k0]]
+        first = min(hits) if hits else 0
 hdr = rows[0]
 ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
 agg = {}
