@@ -86,9 +86,11 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        if os.environ.get("VTK_BENCH_NO_SAMPLER") == "1":     # debugging aid: no nvidia-smi polling during the timed region
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "25"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
 
@@ -274,7 +276,7 @@ def run_ours(args, rank, world, local):
         # nvidia-smi needs a few hundred ms to start: if the timed region was shorter than that, keep the same load
         # running (untimed) until the sampler has seen it, so that `clocks` always describes the GPU under this workload
         t_end = time.perf_counter() + 3.0
-        while sampler.n_samples() < 8 and time.perf_counter() < t_end:
+        while sampler.n_samples() < 4 and time.perf_counter() < t_end:
             for _ in range(4):
                 step(pd)
             torch.cuda.synchronize()

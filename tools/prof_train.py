@@ -40,6 +40,13 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); step(); e1.record(); torch.cuda.synchronize()
 print(f"{wl}: step {e0.elapsed_time(e1):.2f} ms")
+e0.record()
+for _ in range(3):
+    step()
+e1.record(); torch.cuda.synchronize()
+print(f"{wl}: 3 back-to-back steps {e0.elapsed_time(e1) / 3:.2f} ms/step")
+if len(sys.argv) > 2 and sys.argv[2] == "noprof":
+    sys.exit(0)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
