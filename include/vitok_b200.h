@@ -104,6 +104,14 @@ int vtk_pack_rows(const void* in, int64_t ld_in, const int* src, const int* cu, 
 int vtk_unpack_rows(const void* packed, int64_t ld_packed, const int* rel, const int* cu, int B, int N, void* out,
                     int64_t ld_out, int width, void* stream);
 
+/* out [M, N] = At^T Bt for At [K, M] and Bt [K, N] row-major (row strides lda / ldb): the weight gradient dW = dY^T X of the
+ * training step without transposing either operand (the tensor core reads both tiles MN-major).  M, N multiples of 8. */
+int vtk_linear_tn_bf16(const void* At, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo, int M, int N, int K,
+                       void* stream);
+/* out [M, N] = A Bt for A [M, K] and Bt [K, N] row-major: the data gradient dX = dY W with the weight W [out, in] used as stored. */
+int vtk_linear_nn_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo, int M, int N, int K,
+                       void* stream);
+
 /* FP8 inference building blocks (reference AE.quantize, vitok/models/ae.py:253-270 = torchao
  * Float8DynamicActivationFloat8WeightConfig on the Linears of every block).
  * vtk_quant_rows_e4m3: dynamic per-row activation quantisation, q[row,:K] = e4m3(x[row,:K] / scale[row]), scale = amax / 448.

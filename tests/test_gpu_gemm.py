@@ -125,3 +125,26 @@ def test_bad_args_raise(L):
         L.linear(a, w)
     with pytest.raises(RuntimeError):
         L.linear(a.cpu(), w.cpu())
+
+
+@pytest.mark.parametrize("K,M,N", [(1000, 256, 512), (4096, 3072, 1024), (333, 776, 136), (64, 128, 64), (8192, 1024, 2736)])
+def test_linear_tn_transposed_operands(K, M, N):
+    """out = At^T Bt with both operands given transposed (the training step's weight gradient dW = dY^T X): the tensor core
+    reads the [k, column] tiles MN-major, no transpose pass.  Operands are column slices of wider buffers (row pitch > width)."""
+    from vitok_b200 import _lib
+    at_full = bf16_randn(K, M + 64, seed=81)
+    bt_full = bf16_randn(K, N + 24, seed=82)
+    at, bt = at_full[:, 32:32 + M], bt_full[:, 8:8 + N]
+    out = _lib.linear_tn(at, bt)
+    ref = at.float().t() @ bt.float()
+    report(f"linear_tn K={K} M={M} N={N}", out, ref, rel_fro=4e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (8192, 1024, 3760), (300, 136, 776), (4096, 11280, 3072)])
+def test_linear_nn_b_transposed(M, N, K):
+    """out = A Bt with B given as [K, N] row-major (the data gradient dX = dY W, W used as stored)."""
+    from vitok_b200 import _lib
+    a = bf16_randn(M, K + 8, seed=83)[:, :K]
+    bt = bf16_randn(K, N + 16, seed=84)[:, 8:8 + N]
+    out = _lib.linear_nn(a, bt)
+    report(f"linear_nn M={M} N={N} K={K}", out, a.float() @ bt.float(), rel_fro=4e-3)

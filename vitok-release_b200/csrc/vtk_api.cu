@@ -329,6 +329,26 @@ int vtk_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, cons
   return launch_gemm(EPI_BIAS, g, (cudaStream_t)stream);
 }
 
+int vtk_linear_tn_bf16(const void* At, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo, int M, int N, int K,
+                       void* stream) {
+  VTK_REQUIRE(At && Bt && out, "vtk_linear_tn_bf16: null pointer");
+  VTK_REQUIRE(ldo % 8 == 0, "vtk_linear_tn_bf16: ldo must be a multiple of 8");
+  GemmArgs g = base_args(At, lda, Bt, ldb, N, M, N, K);
+  g.trans = 3;
+  g.epi.out = (bf16*)out; g.epi.ldo = ldo;
+  return launch_gemm(EPI_BIAS, g, (cudaStream_t)stream);
+}
+
+int vtk_linear_nn_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo, int M, int N, int K,
+                       void* stream) {
+  VTK_REQUIRE(A && Bt && out, "vtk_linear_nn_bf16: null pointer");
+  VTK_REQUIRE(ldo % 8 == 0, "vtk_linear_nn_bf16: ldo must be a multiple of 8");
+  GemmArgs g = base_args(A, lda, Bt, ldb, N, M, N, K);
+  g.trans = 2;
+  g.epi.out = (bf16*)out; g.epi.ldo = ldo;
+  return launch_gemm(EPI_BIAS, g, (cudaStream_t)stream);
+}
+
 int vtk_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
                        int M, int N, int K, float eps, void* stream) {
   VTK_REQUIRE(A && W && out && bias, "vtk_linear_ln_bf16: null pointer");

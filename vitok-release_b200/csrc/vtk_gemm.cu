@@ -735,7 +735,11 @@ template <bool P> __device__ __forceinline__ long long prof_clock() {
   return 0;
 }
 
-template <int EPI, int NEPI, int G2_STAGES, bool PROF, bool FP8 = false>
+// TRANS = true: both operands are given TRANSPOSED in memory ("TN" product, the weight gradient dW = dY^T X of the training
+// step): A is [K, M] row-major and B is [K, N] row-major, so their tiles are staged as [64 k-rows x 64 columns] swizzled
+// blocks and read by the tensor core MN-major (idesc a_major = b_major = 1, LBO = block stride 8 KB) -- no transpose pass.
+// TRANS = 2: only B is given transposed ([K, N] row-major) -- the data gradient dX = dY W with W used as stored.
+template <int EPI, int NEPI, int G2_STAGES, bool PROF, bool FP8 = false, int TRANS = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M_cap, const int N,
@@ -813,9 +817,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           w_empty += prof_clock<PROF>() - c0;
           const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
           if (rank == 0) mbar_expect_tx(&full[s], tx);
-          tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BKE, m0 + (int)rank * BM);
-          for (int nb = 0; nb < hw; nb += 64)
-            tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb);
+          if (TRANS & 1) {   // boxes of [64 k-rows x 64 columns]: coordinates (column, k)
+            for (int mb = 0; mb < BM; mb += 64)
+              tma_load_2d_2cta(sA + s * A_STAGE_BYTES + mb * (BK * 2), &tmA, fb, m0 + (int)rank * BM + mb, kb * BK);
+          } else {
+            tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BKE, m0 + (int)rank * BM);
+          }
+          for (int nb = 0; nb < hw; nb += 64) {
+            if (TRANS & 2) tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, n0 + (int)rank * hw + nb, kb * BK);
+            else tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb);
+          }
           if (++s == G2_STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -833,7 +844,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int t = cluster_id; t < sched.total_tiles; t += num_clusters) {
         int m0, n0, width;
         sched.decode(t, m0, n0, width);
-        const uint32_t idesc = FP8 ? make_idesc_e4m3(2 * BM, width) : make_idesc_bf16(2 * BM, width, 0, 0);
+        const uint32_t idesc = FP8 ? make_idesc_e4m3(2 * BM, width) : make_idesc_bf16(2 * BM, width, (TRANS & 1) ? 1 : 0, (TRANS & 2) ? 1 : 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G2_BN);
         long long c0 = prof_clock<PROF>();
         mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -848,7 +859,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t b0 = smem_u32(sB + s * G2_B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            if (FP8) umma_f8_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
+            if (TRANS) umma_bf16_ss_2cta(d_tmem,   // MN-major: 16 k-rows = 2 KB inside a block, 8 KB between column blocks
+                                         (TRANS & 1) ? make_smem_desc(a0 + k * 2048, 8192, 1024, 2) : make_desc_kmajor_sw128(a0 + k * 32),
+                                         (TRANS & 2) ? make_smem_desc(b0 + k * 2048, 8192, 1024, 2) : make_desc_kmajor_sw128(b0 + k * 32),
+                                         idesc, (kb | k) != 0 ? 1u : 0u);
+            else if (FP8) umma_f8_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
                                      (kb | k) != 0 ? 1u : 0u);
             else umma_bf16_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
                                    (kb | k) != 0 ? 1u : 0u);
@@ -945,7 +960,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 template <int EPI, int NEPI, int G2_STAGES>
 static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
-  if (a.fp8) {
+  if (a.trans) {   // transposed operand(s) [K, columns] row-major: boxes of 64 columns x 64 k-rows
+    if (a.trans & 1) { if (encode_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 64)) return -1; }
+    else if (encode_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BM)) return -1;
+    if (encode_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.b_rows, (uint64_t)a.K, (uint64_t)a.ldb, 64)) return -1;
+  } else if (a.fp8) {
     if (encode_tmap_u8_sw128(&tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BM)) return -1;
     if (encode_tmap_u8_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.b_rows, (uint64_t)a.ldb, 64)) return -1;
   } else {
@@ -976,14 +995,16 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
     if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
   }
   const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
-  auto kern = a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true>
+  auto kern = a.trans == 3 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 3>
+              : a.trans == 2 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 2>
+              : a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true>
               : a.epi.prof ? gemm2_kernel<EPI, NEPI, G2_STAGES, true> : gemm2_kernel<EPI, NEPI, G2_STAGES, false>;
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[a.fp8 ? 2 : a.epi.prof ? 1 : 0]) {
+  static bool attr_set[5] = {false, false, false, false, false};
+  if (!attr_set[a.trans == 3 ? 4 : a.trans ? 3 : a.fp8 ? 2 : a.epi.prof ? 1 : 0]) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
                    "cudaFuncSetAttribute(gemm2)"))
       return -1;
-    attr_set[a.fp8 ? 2 : a.epi.prof ? 1 : 0] = true;
+    attr_set[a.trans == 3 ? 4 : a.trans ? 3 : a.fp8 ? 2 : a.epi.prof ? 1 : 0] = true;
   }
   kern<<<2 * clusters, 128 + 32 * NEPI, smem_bytes, stream>>>(tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi);
   return check_cuda(cudaGetLastError(), "gemm2 launch");
@@ -1057,13 +1078,24 @@ int launch_gemm(EpiKind kind, const GemmArgs& a_in, cudaStream_t stream) {
 
 int launch_gemm_inner(EpiKind kind, const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) { set_error("gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K); return -2; }
-  if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.N % 8)) {
+  if (!a.trans && ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.N % 8))) {
     set_error("gemm: K, N and the row strides must be multiples of 8 (K=%d N=%d lda=%lld ldb=%lld)", a.K, a.N, a.lda, a.ldb);
     return -2;
   }
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) {
     set_error("gemm: operand pointers must be 16-byte aligned");
     return -2;
+  }
+  if (a.trans) {   // transposed operands (weight gradients): CTA-pair kernel, plain epilogue
+    if (kind != EPI_BIAS || a.fp8 || (a.trans != 2 && a.trans != 3)) {
+      set_error("gemm(trans): only the plain bf16 epilogue has transposed-operand variants (trans = 2: B, 3: A and B)");
+      return -3;
+    }
+    if (((a.trans & 1) && (a.M % 8)) || (!(a.trans & 1) && (a.K % 8)) || (a.lda % 8) || (a.ldb % 8) || (a.N % 8)) {
+      set_error("gemm(trans): the contiguous dimensions and the row strides must be multiples of 8");
+      return -2;
+    }
+    return launch_gemm2_s<EPI_BIAS, 8, 6>(a, stream);
   }
   if (a.fp8) {   // e4m3 operands: CTA-pair kernel only (any M: rows beyond M are zero-filled by TMA and never stored)
     if ((a.K % 16) || (a.lda % 16) || (a.ldb % 16)) { set_error("gemm(fp8): K and the row strides must be multiples of 16 bytes"); return -2; }

@@ -72,6 +72,7 @@ struct GemmArgs {
   const bf16* B; long long ldb;   // [N_rows, K], row stride ldb (N_rows may be < N: OOB rows read as 0)
   long long b_rows;
   int M, N, K;                    // N = number of output (packed) columns to cover
+  int trans;                      // 3: A is [K, M] and B is [K, N] row-major (out = A^T B); 2: only B is [K, N] (out = A B); CTA-pair kernel, EPI_BIAS
   int fp8;                        // 1: A and B hold e4m3 bytes (lda / ldb / K in elements = bytes); CTA-pair kernel only
   EpiParams epi;
 };

@@ -57,6 +57,8 @@ SIGNATURES = {
     "vtk_quant_rows_e4m3": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp]),
     "vtk_proj_residual_fp8": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_linear_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    "vtk_linear_tn_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    "vtk_linear_nn_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_linear_ln_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
     "vtk_qkv_swiglu_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                     c_f32, c_vp, c_i64, c_vp, c_i64, c_vp]),
@@ -164,6 +166,26 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
     check(load().vtk_linear_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), M, N, K,
                                  stream_ptr()))
+    return out
+
+
+def linear_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
+    """out [M, N] = at^T @ bt for at [K, M], bt [K, N] (row-major, any row pitch): transposed-operand GEMM."""
+    _req(at, torch.bfloat16, "at"); _req(bt, torch.bfloat16, "bt")
+    K, M = at.shape
+    N = bt.shape[1]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=at.device)
+    check(load().vtk_linear_tn_bf16(ptr(at), at.stride(0), ptr(bt), bt.stride(0), ptr(out), out.stride(0), M, N, K, stream_ptr()))
+    return out
+
+
+def linear_nn(a: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
+    """out [M, N] = a @ bt for a [M, K], bt [K, N] (row-major, any row pitch): B is read MN-major, no transposed copy."""
+    _req(a, torch.bfloat16, "a"); _req(bt, torch.bfloat16, "bt")
+    M, K = a.shape
+    N = bt.shape[1]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    check(load().vtk_linear_nn_bf16(ptr(a), a.stride(0), ptr(bt), bt.stride(0), ptr(out), out.stride(0), M, N, K, stream_ptr()))
     return out
 
 

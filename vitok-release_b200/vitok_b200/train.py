@@ -48,10 +48,20 @@ def _transpose(x: torch.Tensor, rows: int, cols: int, ld: int) -> torch.Tensor:
 
 
 def _wgrad(dy: torch.Tensor, ld_dy: int, n1: int, x: torch.Tensor, ld_x: int, n2: int, M: int) -> torch.Tensor:
-    """dW [n1, n2] = dy[:, :n1]^T @ x[:, :n2]: both operands transposed to K-major (K = tokens), then one GEMM."""
-    dyt = _transpose(dy, M, n1, ld_dy)
-    xt = _transpose(x, M, n2, ld_x)
-    return _linear(dyt, dyt.stride(0), xt, None, n1, n2, dyt.shape[1])
+    """dW [n1, n2] = dy[:, :n1]^T @ x[:, :n2] on the transposed-operand GEMM (both tiles read MN-major; no transpose pass)."""
+    out = torch.empty(n1, n2, dtype=BF, device=dy.device)
+    _check(_lib.load().vtk_linear_tn_bf16(dy.data_ptr(), ld_dy, x.data_ptr(), ld_x, out.data_ptr(), n2, n1, n2, M, _lib.stream_ptr()))
+    return out
+
+
+def _dgrad(dy: torch.Tensor, ld_dy: int, w: torch.Tensor, M: int, n_in: int, n_out: int, out: Optional[torch.Tensor] = None,
+           accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dX [M, n_in] = dy[:, :n_out] @ w for a weight w [n_out, n_in] used as stored (B operand read MN-major)."""
+    if out is None:
+        out = torch.empty(M, n_in, dtype=BF, device=dy.device)
+    _check(_lib.load().vtk_linear_nn_bf16(dy.data_ptr(), ld_dy, w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, n_in, n_out,
+                                          _lib.stream_ptr()))
+    return out
 
 
 def _colsum(x: torch.Tensor, ld: int, M: int, C: int) -> torch.Tensor:
@@ -131,57 +141,32 @@ def enable_grad_sync(model, process_group=None, broadcast_parameters: bool = Tru
     return model
 
 
-def _transpose_into(x: torch.Tensor, out: torch.Tensor) -> None:
-    """out[:, :] (a [cols, rows] view, any row pitch) = x^T for a [rows, cols] matrix x (row pitch x.stride(0))."""
-    rows, cols = x.shape
-    _check(_lib.load().vtk_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, _lib.stream_ptr()))
-
-
 class _SideWeights:
-    """bf16 weights of one side (encoder / decoder) as the training kernels read them, built straight from the
-    parameters every step (the optimizer has just changed them):
-      * qkv_proj.weight [3D, D] and fc1.weight [2Hf, D] are used in place -- two forward GEMMs write the column ranges
-        [0, 3D) and [qp, qp + 2Hf) of zraw, so there is no packed / interleaved w_in copy and the wgrad GEMMs write
-        contiguous gradients in the parameters' own row order;
-      * w_out [D, kp] = [out_proj | fc2 | 0-pad] (one forward GEMM over the concatenated K);
-      * transposed copies for the dgrad GEMMs (tiled shared-memory transpose): w_in_t [D, ZP], w_out_t [kp, D].
+    """bf16 weights of one side (encoder / decoder) as the training kernels read them, taken straight from the parameters
+    every step (the optimizer has just changed them) -- nothing is repacked or transposed:
+      * qkv_proj.weight [3D, D] and fc1.weight [2Hf, D] feed two forward GEMMs that write the column ranges [0, 3D) and
+        [qp, qp + 2Hf) of zraw; their data gradients come from the same tensors read MN-major (vtk_linear_nn_bf16) and their
+        weight gradients from the transposed-operand GEMM (vtk_linear_tn_bf16), in the parameters' own row order;
+      * w_out [D, kp] = [out_proj | fc2 | 0-pad] is the one packed copy (one forward GEMM over the concatenated K).
     """
 
     def __init__(self, model, side: int):
-        from .models.ae import _Scale, _ffn_hidden, pack_w_out
+        from .models.ae import _Scale, pack_w_out
         sd = {s[0]: s for s in model._sides()}[side]
         _, lin_a, lin_b, blocks, width, heads = sd
         dev = lin_a.weight.device
-        D, Hf = width, _ffn_hidden(width, model.mlp_factor)
-        qp = ((3 * D + 255) // 256) * 256
-        ZP, kp = qp + 2 * Hf, (D + Hf + 63) // 64 * 64
+        D = width
 
         def b16(t):
             return t.detach().to(BF).contiguous()
 
         self.blocks = []
-        self.w_in_t, self.w_out_t = [], []
         for blk in blocks:
             wqkv, w1 = b16(blk.attn.qkv_proj.weight), b16(blk.ffn.fc1.weight)
-            wo, w2 = b16(blk.attn.out_proj.weight), b16(blk.ffn.fc2.weight)
-            w_out = pack_w_out(wo, w2)
-            w_in_t = torch.empty(D, ZP, dtype=BF, device=dev)
-            if qp > 3 * D:
-                w_in_t[:, 3 * D:qp].zero_()
-            _transpose_into(wqkv, w_in_t[:, :3 * D])
-            _transpose_into(w1, w_in_t[:, qp:])
-            w_out_t = torch.empty(kp, D, dtype=BF, device=dev)
-            if kp > D + Hf:
-                w_out_t[D + Hf:].zero_()
-            _transpose_into(wo, w_out_t[:D])
-            _transpose_into(w2, w_out_t[D:D + Hf])
+            w_out = pack_w_out(b16(blk.attn.out_proj.weight), b16(blk.ffn.fc2.weight))
             gamma = b16(blk.layer_scale.gamma) if isinstance(blk.layer_scale, _Scale) else torch.ones(D, dtype=BF, device=dev)
             self.blocks.append((wqkv, w1, w_out, b16(blk.norm1.weight), b16(blk.attn.norm_q.weight), b16(blk.attn.norm_k.weight), gamma))
-            self.w_in_t.append(w_in_t)
-            self.w_out_t.append(w_out_t)
         self.wa, self.ba, self.wb, self.bb = b16(lin_a.weight), b16(lin_a.bias), b16(lin_b.weight), b16(lin_b.bias)
-        self.wa_t = _transpose(self.wa, self.wa.shape[0], self.wa.shape[1], self.wa.stride(0))
-        self.wb_t = _transpose(self.wb, self.wb.shape[0], self.wb.shape[1], self.wb.stride(0))
 
 
 def _side_forward(lib, model, sw: _SideWeights, side: int, xin: torch.Tensor, row, col, m8, B: int, N: int, saved: Dict):
@@ -255,11 +240,9 @@ def _side_backward(lib, model, sw: _SideWeights, side: int, dx: torch.Tensor, sa
         dy = torch.empty(M, D, dtype=BF, device=dev)
         dgamma = torch.zeros(D, dtype=torch.float32, device=dev)
         _check(lib.vtk_resid_bwd(dx.data_ptr(), y.data_ptr(), gamma.data_ptr(), dy.data_ptr(), dgamma.data_ptr(), M, D, st))
-        da2 = _linear(dy, D, sw.w_out_t[li], None, M, kp, D)                      # [M, kp]: d[attn | act | pad]
-        dyt = _transpose(dy, M, D, D)                                             # [D, M]
-        a2t = _transpose(a2, M, kp, kp)                                           # [kp, M]: rows = [attn | act | pad]
-        dw_o = _linear(dyt, M, a2t[:D], None, D, D, M)                            # out_proj.weight grad [D, D]
-        dw_f2 = _linear(dyt, M, a2t[D:D + Hf], None, D, Hf, M)                    # fc2.weight grad [D, Hf]
+        da2 = _dgrad(dy, D, w_out, M, kp, D)                                      # [M, kp]: d[attn | act | pad] = dy @ [out_proj | fc2 | 0]
+        dw_o = _wgrad(dy, D, D, a2, kp, D, M)                                     # out_proj.weight grad [D, D] = dy^T attn
+        dw_f2 = _wgrad(dy, D, D, a2[:, D:], kp, Hf, M)                            # fc2.weight grad [D, Hf] = dy^T act
         dz = torch.empty(M, ZP, dtype=BF, device=dev)
         if qp > 3 * D:
             dz[:, 3 * D:qp].zero_()
@@ -273,11 +256,11 @@ def _side_backward(lib, model, sw: _SideWeights, side: int, dx: torch.Tensor, sa
         dwqk = torch.zeros(2, d, dtype=torch.float32, device=dev)
         _check(lib.vtk_qk_norm_rope_bwd(dz.data_ptr(), ZP, zraw.data_ptr(), ZP, nq.data_ptr(), nk.data_ptr(), rope.data_ptr(),
                                         dwqk.data_ptr(), M, heads, d, 1e-6, st))
-        dh = _linear(dz, ZP, sw.w_in_t[li], None, M, D, ZP)
-        dzt = _transpose(dz, M, ZP, ZP)                                           # [ZP, M]
-        ht = _transpose(h, M, D, D)                                               # [D, M]
-        dw_qkv = _linear(dzt, M, ht, None, 3 * D, D, M)                           # qkv_proj.weight grad [3D, D]
-        dw_fc1 = _linear(dzt[qp:], M, ht, None, 2 * Hf, D, M)                     # fc1.weight grad [2Hf, D], fc1's own row order
+        dh = _dgrad(dz, ZP, wqkv, M, D, 3 * D)                                    # dz[:, :3D] @ Wqkv ...
+        dh1 = _dgrad(dz[:, qp:], ZP, w1, M, D, 2 * Hf)                            # ... + dz[:, qp:] @ W1 (added inside rmsnorm_bwd's input below)
+        dh.add_(dh1)
+        dw_qkv = _wgrad(dz, ZP, 3 * D, h, D, D, M)                                # qkv_proj.weight grad [3D, D]
+        dw_fc1 = _wgrad(dz[:, qp:], ZP, 2 * Hf, h, D, D, M)                       # fc1.weight grad [2Hf, D], fc1's own row order
         dx_in = torch.empty(M, D, dtype=BF, device=dev)
         dw1 = torch.zeros(D, dtype=torch.float32, device=dev)
         _check(lib.vtk_rmsnorm_bwd(x.data_ptr(), dh.data_ptr(), n1.data_ptr(), dx.data_ptr(), dx_in.data_ptr(), dw1.data_ptr(),
@@ -296,7 +279,7 @@ def _side_backward(lib, model, sw: _SideWeights, side: int, dx: torch.Tensor, sa
     cin = xin.shape[-1]
     dwa = _wgrad(dx, D, D, xin.reshape(M, cin), cin, cin, M)                     # [D, cin]
     dba = _colsum(dx, D, M, D)
-    dxin = _linear(dx, D, sw.wa_t, None, M, cin, D) if need_dxin else None      # [M, cin]
+    dxin = _dgrad(dx, D, sw.wa, M, cin, D) if need_dxin else None               # [M, cin]
     return grads, dwa, dba, dxin
 
 
@@ -341,7 +324,7 @@ class AETrainFunction(torch.autograd.Function):
         Dd = xd.shape[1]
         g["to_pixels.weight"] = _wgrad(dout, P, P, xd, Dd, Dd, M)
         g["to_pixels.bias"] = _colsum(dout, P, M, P)
-        dx = _linear(dout, P, dec_w.wb_t, None, M, Dd, P)
+        dx = _dgrad(dout, P, dec_w.wb, M, Dd, P)
         grp = getattr(model, "_grad_sync_group", None)
         sync = _GradSync(grp[0]) if grp is not None else None
         blocks, dwa, dba, dz = _side_backward(lib, model, dec_w, 1, dx, ctx.s_dec, B, N, True, sync)
@@ -355,7 +338,7 @@ class AETrainFunction(torch.autograd.Function):
         De = xe.shape[1]
         g["to_code.weight"] = _wgrad(dzlin, C, C, xe, De, De, M)
         g["to_code.bias"] = _colsum(dzlin, C, M, C)
-        dx = _linear(dzlin, C, enc_w.wb_t, None, M, De, C)
+        dx = _dgrad(dzlin, C, enc_w.wb, M, De, C)
         blocks, dwa, dba, _ = _side_backward(lib, model, enc_w, 0, dx, ctx.s_enc, B, N, False, sync)
         g["patch_embed.weight"], g["patch_embed.bias"] = dwa, dba
         for i, bg in enumerate(blocks):
