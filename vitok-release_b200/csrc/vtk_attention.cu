@@ -110,39 +110,17 @@ __device__ __forceinline__ void mask_scores(uint32_t (&v)[NCH][32], int kv0, int
     }
 }
 
-// 2^x for a pair of scores on the FMA pipe instead of the MUFU (the trick of FlashAttention-4: on sm_100 the 16-lane
-// special-function unit, not the tensor core, bounds the softmax).  x = n + f with n = round(x), f in [-0.5, 0.5];
-// 2^f by a degree-3 polynomial (max relative error 7.5e-5, far below the bf16 rounding of P), 2^n by adding n to the
-// exponent field: float(1.5 * 2^23 + n) carries n in its low mantissa bits, so (bits << 23) is n << 23.
-__device__ __forceinline__ void ex2_poly_pair(uint32_t& a, uint32_t& b) {
-  const float x0 = fmaxf(__uint_as_float(a), -126.f), x1 = fmaxf(__uint_as_float(b), -126.f);   // also maps -inf (masked) to ~0
-  const uint64_t x2 = f2_pack(x0, x1);
-  const uint64_t magic = f2_pack(12582912.f, 12582912.f), neg_magic = f2_pack(-12582912.f, -12582912.f);
-  const uint64_t t2 = f2_add(x2, magic);
-  const uint64_t f2 = f2_fma(f2_add(t2, neg_magic), f2_pack(-1.f, -1.f), x2);
-  uint64_t p2 = f2_fma(f2, f2_pack(0.055171459913253784f, 0.055171459913253784f), f2_pack(0.2426108568906784f, 0.2426108568906784f));
-  p2 = f2_fma(p2, f2, f2_pack(0.6932609677314758f, 0.6932609677314758f));
-  p2 = f2_fma(p2, f2, f2_pack(0.9999281167984009f, 0.9999281167984009f));
-  float t0, t1, p0, p1;
-  f2_unpack(t2, t0, t1);
-  f2_unpack(p2, p0, p1);
-  a = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
-  b = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
-}
-
 // Exponentiate one 128-key score tile held in registers (v = raw scores), accumulate the row sum and write P as
 // bf16 into the row's 128B-swizzled shared-memory slots.  Software-pipelined by hand: all FFMA2 (scale, subtract
 // max) first, then the exponential of pair i+DIST is issued before the FADD2 / F2FP / STS that consume pair i, so a
 // warp never stalls on its own MUFU latency (ptxas otherwise places each consumer right behind its producer and
-// the XU pipe idles ~55 % of the exponentiation phase with only two softmax warps per scheduler).  EMU_MASK selects,
-// inside every group of 8 pairs, the pairs exponentiated on the FMA pipe (ex2_poly_pair): 3 of 8 balances the two
-// pipes (MUFU: 8 cycles per warp instruction; the polynomial: 6 two-wide FMA-pipe instructions per pair).
-template <uint32_t EMU_MASK, int NCH = 4>
-__device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[NCH][32], uint64_t sc2, uint64_t nm2, uint8_t* prow, int r,
+// the XU pipe idles ~55 % of the exponentiation phase with only two softmax warps per scheduler).
+// (Exponentiating part of the pairs with a degree-3 polynomial on the FMA pipe, FlashAttention-4's trick, was measured
+// 4-9 % SLOWER here -- the f32x2 FMA pipe is as loaded as the MUFU -- and was removed; profiles/README.md.)
+__device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[4][32], uint64_t sc2, uint64_t nm2, uint8_t* prow, int r,
                                                  uint64_t& sum2a, uint64_t& sum2b) {
-  constexpr int NP = NCH * 16;   // score pairs per row
 #pragma unroll
-  for (int pr = 0; pr < NP; ++pr) {
+  for (int pr = 0; pr < 64; ++pr) {
     float e0, e1;
     f2_unpack(f2_fma(f2_pack(__uint_as_float(v[pr >> 4][2 * (pr & 15)]), __uint_as_float(v[pr >> 4][2 * (pr & 15) + 1])), sc2, nm2), e0, e1);
     v[pr >> 4][2 * (pr & 15)] = __float_as_uint(e0);
@@ -151,18 +129,12 @@ __device__ __forceinline__ void softmax_exp_tile(uint32_t (&v)[NCH][32], uint64_
   constexpr int DIST = 3;
   uint32_t pk[4];
 #pragma unroll
-  for (int pr = 0; pr < NP + DIST; ++pr) {
-    if (pr < NP) {
+  for (int pr = 0; pr < 64 + DIST; ++pr) {
+    if (pr < 64) {
       uint32_t& a = v[pr >> 4][2 * (pr & 15)];
       uint32_t& b = v[pr >> 4][2 * (pr & 15) + 1];
-      if (EMU_MASK == 0xFFFFu) {
-        // timing experiment only (VTK_ATTN_EMU=0xFFFF): no exponential at all
-      } else if ((EMU_MASK >> (pr & 7)) & 1u) {
-        ex2_poly_pair(a, b);
-      } else {
-        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a));
-        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(b));
-      }
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a));
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(b));
     }
     if (pr >= DIST) {
       const int q = pr - DIST;
@@ -212,11 +184,6 @@ __device__ __forceinline__ void softmax_exp_tile_tmem(uint32_t (&v)[4][32], uint
     }
   }
 }
-
-// pairs 1, 4 and 6 of every 8 on the FMA pipe (37.5 %); VTK_ATTN_EMU=0 at build time (-DVTK_ATTN_EMU_MASK=0) = MUFU only
-#ifndef VTK_ATTN_EMU_MASK
-#define VTK_ATTN_EMU_MASK 0u
-#endif
 
 template <int DH, int NQ>
 __global__ void __launch_bounds__(128 * NQ + 64, NQ == 1 ? 2 : 1)
@@ -472,7 +439,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
       // 128 columns = 2 blocks x 8 chunks of 16 B; swizzle-128B: chunk' = chunk ^ (row & 7); each 16-byte chunk
       // (8 keys) is written as soon as it is exponentiated
-      softmax_exp_tile<VTK_ATTN_EMU_MASK>(v, sc2, nm2, prow, r, sum2a, sum2b);
+      softmax_exp_tile(v, sc2, nm2, prow, r, sum2a, sum2b);
       float sum0, sum1;
       f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
       l_run = l_run * alpha + (sum0 + sum1);
@@ -641,7 +608,7 @@ __device__ __forceinline__ bool item_at(int k, int total, int& w) {
   return base < total;
 }
 
-template <int DH, uint32_t EMU, bool SNAKE, bool PTMEM = false>
+template <int DH, bool SNAKE, bool PTMEM>
 __global__ void __launch_bounds__(192, 2)
 attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
@@ -818,18 +785,11 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         const long long k1 = PCLK();
         uint32_t v[4][32];
-        if (EMU == 0xFFFEu) {   // timing experiment only (VTK_ATTN_EMU=0xFFFE): S is not read back from TMEM
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[c][i] = __float_as_uint((float)((lane + i + c) & 7));
-        } else {
-          tmem_ld32(tS + 0, v[0]);
-          tmem_ld32(tS + 32, v[1]);
-          tmem_ld32(tS + 64, v[2]);
-          tmem_ld32(tS + 96, v[3]);
-          tmem_wait_ld();
-        }
+        tmem_ld32(tS + 0, v[0]);
+        tmem_ld32(tS + 32, v[1]);
+        tmem_ld32(tS + 64, v[2]);
+        tmem_ld32(tS + 96, v[3]);
+        tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(s_empty);   // S is in registers: the tensor core may overwrite it with the next tile's S
         const long long k2 = PCLK();
@@ -869,7 +829,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           softmax_exp_tile_tmem(v, sc2, nm2, tmem_base + lane_base + P_COL, sum2a, sum2b);
           tmem_wait_st();
         } else {
-          softmax_exp_tile<EMU>(v, sc2, nm2, prow, r, sum2a, sum2b);
+          softmax_exp_tile(v, sc2, nm2, prow, r, sum2a, sum2b);
         }
         const long long k5 = PCLK();
         float sum0, sum1;
@@ -974,337 +934,6 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Split-key variant of the persistent kernel (d = 64): TWO independent softmax pipelines per CTA.  Warpgroup h owns keys
-// [64h, 64h + 64) of every 128-key tile: its own S_h = Q K_h^T (an N = 64 MMA into its own 64 TMEM columns), its own
-// running max / sum, its own P_h block in shared memory and its own O_h accumulator (TMEM: S_0 64 + S_1 64 + O_0 64 +
-// O_1 64 = the 256 columns allocated), with its own s_full / s_empty / p_full / pv_done barriers.  Inside an item the two
-// pipelines never wait for each other, so they drift out of phase and one half's MUFU phase overlaps the other's load /
-// max / wait phases -- with one S buffer all softmax warps of a CTA are released by the same event and hit the MUFU in
-// lock-step (a first version that only split the columns of a shared S tile was no faster than one warpgroup).  Same tensor
-// work as a 128-key tile.  The halves are merged once per item in the epilogue (flash-decoding combine:
-// O = (w_0 O_0 + w_1 O_1) / (w_0 l_0 + w_1 l_1), w_h = 2^(m_h - max m)).  The single MMA thread serves both pipelines from
-// a polling loop (mbarrier.try_wait): per half the order is S(0), then S(j+1) before PV(j); a K / V ring slot is released
-// when both halves have issued their MMA on it.
-// Softmax warps: 0-3 (h = 0) and 6-9 (h = 1) -- a warp may only touch the TMEM lanes of quarter (warp & 3), and
-// {6,7,8,9} & 3 = {2,3,0,1}; warp 4 = TMA, warp 5 = MMA.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-template <int DH, bool SNAKE>
-__global__ void __launch_bounds__(320, 2)
-attn_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p,
-                  const int total_items_host, const int qtiles) {
-  using S = AttnShape<DH, 1>;
-  static_assert(DH == 64, "split-key persistent attention: d = 64 only");
-  constexpr int HK = ATT_BKV / 2;            // keys per half tile
-  constexpr uint32_t S_COL = 0;              // S_h at [64h, 64h + 64)
-  constexpr uint32_t O_COL = 128;            // O_h at [128 + 64h, 128 + 64h + 64)
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int W = p.window;
-  const int total_items = SNAKE ? min(total_items_host, (__ldg(p.m_dev) / ATT_BQ) * p.heads) : total_items_host;
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem + S::OFF_Q;
-  uint8_t* sK = smem + S::OFF_K;
-  uint8_t* sV = smem + S::OFF_V;
-  uint8_t* sP = smem + S::OFF_P;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;               // [2]
-  uint64_t* k_empty = bars + 3;              // [2]
-  uint64_t* v_full = bars + 5;               // [2]
-  uint64_t* v_empty = bars + 7;              // [2]
-  uint64_t* s_full = bars + 9;               // [2] per half
-  uint64_t* s_empty = bars + 11;             // [2] count 128 each
-  uint64_t* p_full = bars + 13;              // [2] count 128 each
-  uint64_t* pv_done = bars + 15;             // [2]
-  uint64_t* q_empty = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-
-  if (warp == 4) {
-    if (lane < 18) mbar_init(&bars[lane], (lane >= 11 && lane <= 14) ? 128u : 1u);
-    else if (lane == 19) tma_prefetch_desc(&tmQ);
-    else if (lane == 20) tma_prefetch_desc(&tmK);
-    else if (lane == 21) tma_prefetch_desc(&tmV);
-    else if (lane == 22) tma_prefetch_desc(&tmO);
-    fence_barrier_init();
-    __syncwarp();
-  }
-  if (warp == 5) {
-    tmem_alloc(tmem_slot, S::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      // ===== TMA producer (identical to attn_persist_kernel) =====
-      uint32_t n_item = 0, n_k = 0, n_v = 0;
-      for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
-        if (SNAKE && w >= total_items) continue;
-        const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
-        if (!it.active) continue;
-        const long long row0 = it.row0;
-        if (n_item > 0) mbar_wait(q_empty, (n_item - 1) & 1u);
-        mbar_expect_tx(q_full, S::TILE_BYTES);
-        tma_load_2d(sQ, &tmQ, q_full, it.head * DH, (int)(row0 + it.q0));
-        ++n_item;
-        auto load_k = [&](int jj) {
-          const uint32_t slot = n_k % S::RK;
-          mbar_wait(&k_empty[slot], ((n_k / S::RK) & 1u) ^ 1u);
-          mbar_expect_tx(&k_full[slot], S::TILE_BYTES);
-          tma_load_2d(sK + slot * S::TILE_BYTES, &tmK, &k_full[slot], it.head * DH, (int)(row0 + (long long)(it.j_lo + jj) * ATT_BKV));
-          ++n_k;
-        };
-        load_k(0);
-        for (int jj = 0; jj < it.Tn; ++jj) {
-          if (jj + 1 < it.Tn) load_k(jj + 1);
-          const uint32_t slot = n_v % S::RV;
-          mbar_wait(&v_empty[slot], ((n_v / S::RV) & 1u) ^ 1u);
-          mbar_expect_tx(&v_full[slot], S::TILE_BYTES);
-          tma_load_2d(sV + slot * S::TILE_BYTES, &tmV, &v_full[slot], it.head * DH, (int)(row0 + (long long)(it.j_lo + jj) * ATT_BKV));
-          ++n_v;
-        }
-      }
-    }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      // ===== MMA issuer: one polling loop over the two half pipelines =====
-      const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, HK, 0, 0);   // S_h: 128 queries x 64 keys
-      const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, DH, 0, 1);   // O_h: B (= V_h) is MN-major
-      uint32_t n_item = 0, n_k = 0, n_v = 0;                         // K / V tiles consumed before the current item
-      uint32_t ns[2] = {0, 0}, npv[2] = {0, 0};                      // S / PV groups issued so far, per half (barrier phases)
-      const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
-      for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
-        if (SNAKE && w >= total_items) continue;
-        const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
-        if (!it.active) continue;
-        mbar_wait(q_full, n_item & 1u);
-        ++n_item;
-        const int Tn = it.Tn;
-        int js[2] = {0, 0}, jp[2] = {0, 0};   // next S tile / next PV tile of each half inside this item
-        bool q_released = false;
-        const long long t0 = clock64();
-        while (jp[0] < Tn || jp[1] < Tn) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            // S_h(js): allowed at most one tile ahead of this half's PV
-            if (js[h] < Tn && js[h] <= jp[h] + 1) {
-              const uint32_t kt = n_k + (uint32_t)js[h];
-              const uint32_t slot = kt % S::RK;
-              if (mbar_try_wait(&k_full[slot], (kt / S::RK) & 1u) && (ns[h] == 0 || mbar_try_wait(&s_empty[h], (ns[h] - 1) & 1u))) {
-                tc_fence_after();
-                const uint32_t ka = smem_u32(sK + slot * S::TILE_BYTES) + h * (HK * 128);   // key rows [64h, 64h + 64): 128 B per row
-#pragma unroll
-                for (int kk = 0; kk < DH / 16; ++kk)
-                  umma_bf16_ss(tmem_base + S_COL + h * HK, make_desc_kmajor_sw128(qa + kk * 32), make_desc_kmajor_sw128(ka + kk * 32),
-                               idesc_s, kk != 0 ? 1u : 0u);
-                umma_commit(&s_full[h]);
-                if (js[1 - h] > js[h]) umma_commit(&k_empty[slot]);   // the other half has already used this K tile
-                ++js[h];
-                ++ns[h];
-                if (!q_released && js[0] == Tn && js[1] == Tn) {       // every S MMA of this item has been issued
-                  umma_commit(q_empty);
-                  q_released = true;
-                }
-              }
-            }
-            // O_h += P_h V_h (K = 64)
-            if (jp[h] < js[h]) {
-              const uint32_t vt = n_v + (uint32_t)jp[h];
-              const uint32_t slot = vt % S::RV;
-              if (mbar_try_wait(&v_full[slot], (vt / S::RV) & 1u) && mbar_try_wait(&p_full[h], npv[h] & 1u)) {
-                tc_fence_after();
-                const uint32_t va = smem_u32(sV + slot * S::TILE_BYTES);
-#pragma unroll
-                for (int k4 = 0; k4 < HK / 16; ++k4) {
-                  const int kk = h * (HK / 16) + k4;
-                  const uint64_t adesc = make_desc_kmajor_sw128(pa + h * BLK + k4 * 32);
-                  const uint64_t bdesc = make_smem_desc(va + kk * 2048, BLK, 1024, 2);
-                  umma_bf16_ss(tmem_base + O_COL + h * DH, adesc, bdesc, idesc_o, (jp[h] | k4) != 0 ? 1u : 0u);
-                }
-                umma_commit(&pv_done[h]);
-                if (jp[1 - h] > jp[h]) umma_commit(&v_empty[slot]);   // the other half has already used this V tile
-                ++jp[h];
-                ++npv[h];
-              }
-            }
-          }
-          if (clock64() - t0 > VTK_WAIT_LIMIT_CYCLES) __trap();
-        }
-        n_k += (uint32_t)Tn;
-        n_v += (uint32_t)Tn;
-      }
-    }
-  } else {
-    // ===== softmax warpgroups: thread <-> (query row, key half) =====
-    const int h = warp >= 6 ? 1 : 0;
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + S_COL + h * HK;
-    const uint32_t tOh = tmem_base + lane_base + O_COL + h * DH;
-    uint8_t* prow = sP + h * BLK + r * 128;                       // this half's [128 x 64] block of the P buffer
-    float2* exch = reinterpret_cast<float2*>(sP + BLK + 8192);    // [2][128] (m, l): lives in block 1, idle in the epilogue
-    const float sc = p.scale_log2;
-    uint32_t n_t = 0;
-    bool store_pending = false;
-    for (int k = 0, w; item_at<SNAKE>(k, total_items, w); ++k) {
-      if (SNAKE && w >= total_items) continue;
-      const AttnItem it = attn_item<SNAKE>(p, w, qtiles);
-      const long long row0 = it.row0;
-      const int N = it.nrows;
-      const int qi = it.q0 + r;
-      if (!it.active) {   // nothing to attend to: the output rows are 0
-        if (qi < N) {
-          bf16* op = p.out + (row0 + qi) * p.ld_out + it.head * DH + h * (DH / 2);
-          for (int c = 0; c < DH / 2; c += 8) st_global_v4(op + c, 0u, 0u, 0u, 0u);
-          if (p.lse && h == 0) p.lse[(row0 + qi) * p.heads + it.head] = INFINITY;
-        }
-        continue;
-      }
-      const int kvlen = it.kvlen;
-      const bool general_mask = p.key_mask != nullptr && !(p.prefix_flag != nullptr && p.prefix_flag[it.img] != 0);
-      const uint8_t* kmask = general_mask ? p.key_mask + row0 : nullptr;
-      float m_run = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < it.Tn; ++j, ++n_t) {
-        const int kv0 = (it.j_lo + j) * ATT_BKV + h * HK;       // first key of this half tile
-        const bool win_mask = W >= 0 && (kv0 < it.q0 + ATT_BQ - 1 - W || kv0 + HK - 1 > it.q0 + W);
-        const bool need_mask = (kv0 + HK > kvlen) || (kmask != nullptr) || win_mask;
-        mbar_wait(&s_full[h], n_t & 1u);
-        __syncwarp();
-        tc_fence_after();
-        uint32_t v[2][32];
-        tmem_ld32(tS + 0, v[0]);
-        tmem_ld32(tS + 32, v[1]);
-        tmem_wait_ld();
-        tc_fence_before();
-        mbar_arrive(&s_empty[h]);
-        if (need_mask) mask_scores<2>(v, kv0, kvlen, kmask, W, qi);
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          mx0 = max3f(mx0, __uint_as_float(v[0][i]), __uint_as_float(v[0][i + 1]));
-          mx1 = max3f(mx1, __uint_as_float(v[1][i]), __uint_as_float(v[1][i + 1]));
-        }
-        const float m_tile = fmaxf(mx0, mx1) * sc;
-        float m_use = m_run, alpha = 1.f;
-        if (m_tile > m_run + RESCALE_THRESHOLD || m_run == -INFINITY) {
-          m_use = fmaxf(m_run, m_tile);
-          alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_use);
-        }
-        const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
-        const uint64_t sc2 = f2_pack(sc, sc), nm2 = f2_pack(-m_sub, -m_sub);
-        uint64_t sum2a = 0ull, sum2b = 0ull;
-        // this half's P block is free once its previous PV has completed (and, for half 0, once the O tile staged in
-        // block 0 by the previous item's epilogue has been read by its TMA store)
-        if (n_t > 0) {
-          mbar_wait(&pv_done[h], (n_t - 1) & 1u);
-          __syncwarp();
-          tc_fence_after();
-        }
-        if (store_pending) {
-          if (lane == 0) tma_store_wait_read();
-          __syncwarp();
-          store_pending = false;
-        }
-        softmax_exp_tile<0u, 2>(v, sc2, nm2, prow, r, sum2a, sum2b);
-        float sum0, sum1;
-        f2_unpack(f2_add(sum2a, sum2b), sum0, sum1);
-        l_run = l_run * alpha + (sum0 + sum1);
-        m_run = m_use;
-        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll
-          for (int c = 0; c < DH; c += 32) {
-            uint32_t o[32];
-            tmem_ld32(tOh + c, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tOh + c, o);
-          }
-          tmem_wait_st();
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(&p_full[h]);
-      }
-      // ---- epilogue of the item: merge the two halves ----
-      mbar_wait(&pv_done[0], (n_t - 1) & 1u);
-      mbar_wait(&pv_done[1], (n_t - 1) & 1u);
-      __syncwarp();
-      tc_fence_after();
-      exch[h * 128 + r] = make_float2(m_run, l_run);
-      softmax_bar_sync();
-      const float2 oth = exch[(1 - h) * 128 + r];
-      const float M = fmaxf(m_run, oth.x);
-      const float w_self = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - M);
-      const float w_oth = (oth.x == -INFINITY) ? 0.f : ex2_approx(oth.x - M);
-      const float L = l_run * w_self + oth.y * w_oth;
-      const float inv = L > 0.f ? 1.f / L : 0.f;
-      bool zero_row = false;
-      if (p.zero_invalid) zero_row = (qi >= kvlen) || (kmask != nullptr && qi < N && kmask[qi] == 0);
-      const float osc = zero_row ? 0.f : inv;
-      if (p.lse && h == 0 && qi < N) p.lse[(row0 + qi) * p.heads + it.head] = (zero_row || !(L > 0.f)) ? INFINITY : M + log2f(L);
-      const float w0 = (h == 0 ? w_self : w_oth) * osc, w1 = (h == 0 ? w_oth : w_self) * osc;
-      // this thread finishes output columns [32h, 32h + 32) of its row: w0 * O_0 + w1 * O_1
-      uint32_t o0[32], o1[32];
-      tmem_ld32(tmem_base + lane_base + O_COL + h * 32, o0);
-      tmem_ld32(tmem_base + lane_base + O_COL + DH + h * 32, o1);
-      tmem_wait_ld();
-      tc_fence_before();
-      uint32_t wv[4][4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c0 = 8 * g + 2 * i;
-          wv[g][i] = bf2_cvt(__uint_as_float(o0[c0]) * w0 + __uint_as_float(o1[c0]) * w1,
-                             __uint_as_float(o0[c0 + 1]) * w0 + __uint_as_float(o1[c0 + 1]) * w1);
-        }
-      if (p.tma_out) {
-        uint8_t* srow = sP + r * 128;   // O staged in block 0 of the P buffer (free: both halves' last PV have completed)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int ch = (h * 4 + g) ^ (r & 7);
-          *reinterpret_cast<uint4*>(srow + (ch << 4)) = make_uint4(wv[g][0], wv[g][1], wv[g][2], wv[g][3]);
-        }
-        fence_proxy_async_smem();
-        softmax_bar_sync();             // both halves' columns are staged (and every read of exch is done)
-        if (h == 0) {
-          if (lane == 0) {
-            tma_store_2d(&tmO, sP + quarter * 32 * 128, it.head * DH, (int)(row0 + it.q0 + quarter * 32));
-            tma_store_commit();
-          }
-          store_pending = true;
-        }
-      } else {
-        if (qi < N) {
-          bf16* op = p.out + (row0 + qi) * p.ld_out + it.head * DH + h * 32;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) st_global_v4(op + 8 * g, wv[g][0], wv[g][1], wv[g][2], wv[g][3]);
-        }
-        softmax_bar_sync();             // every read of exch is done before half 1 writes P into block 1 again
-      }
-    }
-    if (store_pending && lane == 0) tma_store_wait_read();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, S::TMEM_COLS);
-  }
-}
-
 static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   using S = AttnShape<64, 1>;
   const bool packed = a.cu != nullptr;
@@ -1336,25 +965,13 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
     p.prof = d_prof;
   }
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
-  // perf experiments: VTK_ATTN_EMU = pairs (bit mask inside every group of 8) exponentiated on the FMA pipe
-  static const int emu = getenv("VTK_ATTN_EMU") ? (int)strtol(getenv("VTK_ATTN_EMU"), nullptr, 0) : (int)VTK_ATTN_EMU_MASK;
-  // VTK_ATTN_SPLIT=1 selects the split-key kernel (two independent softmax pipelines per CTA).  Measured on B200: 47.4 vs 45.7 us
-  // at the c2 shape, 120.5 vs 120.0 us at N = 1024 -- neither doubling the softmax warps nor de-phasing them changes the time,
-  // so the ~1660 cycles per 128 x 128 tile per SM are not MUFU contention between lock-stepped warps (S read-back from TMEM,
-  // 64 KB per tile, is the next suspect).  It stays an opt-in experiment.
-  static const int split = getenv("VTK_ATTN_SPLIT") ? atoi(getenv("VTK_ATTN_SPLIT")) : 0;
   // P stays in tensor memory (A operand of the PV MMA read from TMEM, no 32 KB shared-memory round trip per tile): 3-4 % faster
   // than the shared-memory P buffer (43.9 vs 45.6 us at the c2 shape); VTK_ATTN_PTMEM=0 selects the shared-memory variant
   static const int ptmem = getenv("VTK_ATTN_PTMEM") ? atoi(getenv("VTK_ATTN_PTMEM")) : 1;
-  const bool use_split = split != 0 && !prof_mode && emu == 0;
-  auto kern = use_split ? (packed ? attn_split_kernel<64, true> : attn_split_kernel<64, false>)
-              : packed ? (ptmem ? attn_persist_kernel<64, 0u, true, true> : attn_persist_kernel<64, 0u, true>)
-              : ptmem ? attn_persist_kernel<64, 0u, false, true>
-              : emu == 0x52 ? attn_persist_kernel<64, 0x52u, false>
-              : emu == 0xFFFF ? attn_persist_kernel<64, 0xFFFFu, false>
-              : emu == 0xFFFE ? attn_persist_kernel<64, 0xFFFEu, false> : attn_persist_kernel<64, 0u, false>;
-  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
-  const int ai = (packed ? 1 : 0) + (use_split ? 2 : 0) + (ptmem ? 4 : 0);
+  auto kern = packed ? (ptmem ? attn_persist_kernel<64, true, true> : attn_persist_kernel<64, true, false>)
+                     : (ptmem ? attn_persist_kernel<64, false, true> : attn_persist_kernel<64, false, false>);
+  static bool attr_set[4] = {false, false, false, false};
+  const int ai = (packed ? 1 : 0) + (ptmem ? 2 : 0);
   if (!attr_set[ai]) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES), "cudaFuncSetAttribute(attn_persist)"))
       return -1;
@@ -1364,7 +981,7 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   const long long total = packed ? (Mrows / ATT_BQ) * a.heads : (long long)a.B * a.heads * qtiles;
   if (total >= (1ll << 31)) { set_error("attention: too many work items"); return -2; }
   const int grid = (int)std::min<long long>(total, 2ll * num_sms());
-  kern<<<grid, use_split ? 320 : 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
+  kern<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
   if (prof_mode) {
     unsigned long long h[16];
     cudaDeviceSynchronize();
