@@ -235,3 +235,23 @@ def test_5b_width_shallow_vs_oracle(backend):
     ma_p, _ = report(f"5B-width {backend} patches", dec["patches"].cpu().float()[valid], d_o["patches"][valid])
     print(f"[parity] reference-bf16 own error: z {own_z:.3e} patches {own_p:.3e}")
     assert ma_z <= max(2 * own_z, 5e-2) and ma_p <= max(2 * own_p, 5e-2)
+
+
+@pytest.mark.parametrize("backend", ["sdpa", "flash"])
+def test_cuda_graph_replay_equals_eager(backend):
+    """GraphedAE: the whole encode -> decode call sequence of one (B, N) shape captured in a CUDA graph (the C ABI makes no
+    allocation and no host sync; with token packing the packed row count stays on the device) replays bit-identically, also
+    for a DIFFERENT ragged batch of the same shape than the one it was captured with."""
+    import vitok_b200 as vb
+    cfg0 = ae_oracle.decode_variant(SMALL)
+    sd = make_state_dict(cfg0, seed=1, stress=True)
+    model, cfg = _model(SMALL, sd, backend)
+    b1 = _to_cuda(_batch([(128, 128), (96, 64), (50, 120)], 16, 64, seed=5))
+    b2 = _to_cuda(_batch([(64, 100), (128, 128), (16, 16)], 16, 64, seed=6))
+    graphed = vb.GraphedAE(model, b1)
+    for b in (b2, b1):
+        with torch.no_grad():
+            eager = model.decode(model.encode(b))
+        out = graphed(b)
+        assert torch.equal(out["patches"], eager["patches"])
+        assert out["orig_height"] is b["orig_height"]
