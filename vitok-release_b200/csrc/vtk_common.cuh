@@ -180,12 +180,21 @@ __device__ __forceinline__ void tmem_relinquish_2cta() {
 __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// arrive (count 1) on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair once every
-// previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+// arrive (count 1) on the mbarrier at the same shared-memory offset in every CTA of `cta_mask` (cluster ranks) once every
+// previously issued tcgen05.mma of this thread has completed; default = both CTAs of a 2-CTA cluster
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
+}
+// TMA load multicast to the CTAs of `cta_mask` (same CTA-relative destination offset in each); the completion bytes are
+// signalled on the mbarrier at bar's offset in the LEADER (even rank) of each destination CTA's pair (cta_group::2)
+__device__ __forceinline__ void tma_load_2d_2cta_mc(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
 }
 // D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA) and B split N/2 per CTA.  Issued by ONE
 // thread of the leader CTA (cluster rank 0); descriptors are shared-memory offsets valid in both CTAs.

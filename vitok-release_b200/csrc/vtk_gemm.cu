@@ -739,8 +739,12 @@ template <bool P> __device__ __forceinline__ long long prof_clock() {
 // step): A is [K, M] row-major and B is [K, N] row-major, so their tiles are staged as [64 k-rows x 64 columns] swizzled
 // blocks and read by the tensor core MN-major (idesc a_major = b_major = 1, LBO = block stride 8 KB) -- no transpose pass.
 // TRANS = 2: only B is given transposed ([K, N] row-major) -- the data gradient dX = dY W with W used as stored.
-template <int EPI, int NEPI, int G2_STAGES, bool PROF, bool FP8 = false, int TRANS = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
+// CL = 4: a cluster of TWO CTA pairs working on vertically adjacent 256-row tiles of the same N-tile.  The B (weight) tile is
+// the same for both pairs, so every CTA loads only half of its B share and TMA-multicasts it to its counterpart in the other pair
+// (rank r <-> r ^ 2): 48 KB instead of 64 KB leave L2 per pair and k-block, which is what bounds the main loop.
+// A stage slot is then written by two producers, so its "empty" barrier collects the MMA commits of both pairs.
+template <int EPI, int NEPI, int G2_STAGES, bool PROF, bool FP8 = false, int TRANS = 0, int CL = 2>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M_cap, const int N,
              const int K, const TileSched sched_host, const EpiParams epi) {
@@ -748,7 +752,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   TileSched sched = sched_host;
   if (epi.m_dev) {   // packed NaFlex batches: row count from device memory (see gemm_kernel)
     M = min(__ldg(epi.m_dev), M_cap);
-    sched.setup(M, (int)(gridDim.x >> 1));
+    sched.setup(M, (int)(gridDim.x / CL));
   }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -766,9 +770,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
+  const uint32_t crank = cluster_ctarank();   // rank in the cluster
+  const uint32_t rank = crank & 1u;           // rank inside the CTA pair
+  const uint32_t pair = crank >> 1;           // 0, or 0 / 1 with CL = 4
+  const uint32_t lead = crank & ~1u;          // cluster rank of this pair's leader CTA
+  const int cluster_id = blockIdx.x / CL;
+  const int num_clusters = gridDim.x / CL;
   constexpr int BKE = FP8 ? 2 * BK : BK;   // elements per k-block: one 128-byte swizzle row of bf16 (64) or e4m3 (128)
   const int num_k = (K + BKE - 1) / BKE;
 
@@ -777,7 +784,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < G2_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL / 2);   // one MMA commit per pair that writes into this CTA's slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -815,17 +822,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const long long c0 = prof_clock<PROF>();
           mbar_wait(&empty[s], ph ^ 1);
           w_empty += prof_clock<PROF>() - c0;
-          const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
+          const uint32_t fb = mapa_u32(smem_u32(&full[s]), lead);
           if (rank == 0) mbar_expect_tx(&full[s], tx);
           if (TRANS & 1) {   // boxes of [64 k-rows x 64 columns]: coordinates (column, k)
             for (int mb = 0; mb < BM; mb += 64)
-              tma_load_2d_2cta(sA + s * A_STAGE_BYTES + mb * (BK * 2), &tmA, fb, m0 + (int)rank * BM + mb, kb * BK);
+              tma_load_2d_2cta(sA + s * A_STAGE_BYTES + mb * (BK * 2), &tmA, fb, m0 + (int)crank * BM + mb, kb * BK);
           } else {
-            tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BKE, m0 + (int)rank * BM);
+            tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BKE, m0 + (int)crank * BM);
           }
-          for (int nb = 0; nb < hw; nb += 64) {
-            if (TRANS & 2) tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, n0 + (int)rank * hw + nb, kb * BK);
-            else tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb);
+          if (CL == 4) {   // this CTA fetches half of its B share and multicasts it to its counterpart in the other pair
+            const int nb = (int)pair * (hw >> 1);
+            tma_load_2d_2cta_mc(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb,
+                                (uint16_t)((1u << rank) | (1u << (rank + 2))));
+          } else {
+            for (int nb = 0; nb < hw; nb += 64) {
+              if (TRANS & 2) tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, n0 + (int)rank * hw + nb, kb * BK);
+              else tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb);
+            }
           }
           if (++s == G2_STAGES) { s = 0; ph ^= 1; }
         }
@@ -868,10 +881,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             else umma_bf16_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
                                    (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_2cta(&empty[s]);   // slot reusable in both CTAs
+          umma_commit_2cta(&empty[s], CL == 4 ? (uint16_t)0xF : (uint16_t)3);   // slot reusable: told to every CTA that writes into it
           if (++s == G2_STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_2cta(&tfull[acc]);   // accumulator complete -> epilogues of both CTAs
+        umma_commit_2cta(&tfull[acc], (uint16_t)(3u << lead));   // accumulator complete -> epilogues of both CTAs of this pair
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
       if (PROF && epi.prof) {
@@ -901,7 +914,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int t = cluster_id; t < sched.total_tiles; t += num_clusters) {
       int m0, n0, width;
       sched.decode(t, m0, n0, width);
-      m0 += (int)rank * BM;
+      m0 += (int)crank * BM;
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < M && epi.debug != 1;
       st.row0 = m0 + quarter * 32;
@@ -937,7 +950,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), lead));
       w_work += prof_clock<PROF>() - c1;
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
@@ -955,6 +968,43 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, 512);
   }
+}
+
+// 4-CTA-cluster launch (gemm2_kernel<..., CL = 4>): super-tiles of 512 x 256, no half-width tiles; the number of co-resident
+// clusters is what the hardware can place (GPCs whose SM count is not a multiple of 4 leave SMs unused)
+template <int EPI, int NEPI, int G2_STAGES>
+static int launch_gemm2_cl4(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, TileSched sc, cudaStream_t stream) {
+  sc.bm = 4 * BM;
+  sc.split = 0;
+  constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
+  const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
+  auto kern = a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true, 0, 4> : gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 0, 4>;
+  static int max_clusters[2] = {0, 0};
+  const int vi = a.fp8 ? 1 : 0;
+  if (max_clusters[vi] == 0) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute(gemm2 cl4)")) return -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(128 + 32 * NEPI); cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 4; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (check_cuda(cudaOccupancyMaxActiveClusters(&n, kern, &cfg), "cudaOccupancyMaxActiveClusters(gemm2 cl4)")) return -1;
+    if (n <= 0) { set_error("gemm2 cl4: no 4-CTA cluster fits on this device"); return -1; }
+    max_clusters[vi] = n;
+  }
+  sc.setup(a.M, max_clusters[vi]);
+  const int big = sc.num_m * sc.num_n;
+  const int clusters = big < max_clusters[vi] ? big : max_clusters[vi];
+  CUtensorMap tmO0 = tmA, tmO1 = tmA;
+  if (EPI == EPI_QKV_SWIGLU) {
+    if (encode_tmap_bf16(&tmO0, a.epi.qkv, (uint64_t)3 * a.epi.D, (uint64_t)a.M, (uint64_t)a.epi.ld_qkv, 32, 32, 64)) return -1;
+    if (encode_tmap_bf16(&tmO1, a.epi.act, (uint64_t)a.epi.Hf, (uint64_t)a.M, (uint64_t)a.epi.ld_act, 32, 32, 64)) return -1;
+  } else if (EPI == EPI_RESID) {
+    if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
+  }
+  kern<<<4 * clusters, 128 + 32 * NEPI, smem_bytes, stream>>>(tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi);
+  return check_cuda(cudaGetLastError(), "gemm2 (4-CTA cluster) launch");
 }
 
 template <int EPI, int NEPI, int G2_STAGES>
@@ -982,6 +1032,13 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
     sc.gm_cap = (int)(gm < 1 ? 1 : gm > (1 << 20) ? (1 << 20) : gm);
   }
   sc.split = 1;
+  // 4-CTA clusters (two pairs sharing the B tile by TMA multicast): bf16 / fp8 K-major operands, enough M for two 256-row tiles
+  // Measured (B200, c2 / c4 in the bench pipeline): out_proj+fc2 residual GEMM 3.19 -> 3.11 ms / 21.5 -> 20.5 ms, but the QKV+fc1 GEMM
+  // 6.99 -> 7.18 / 43.9 -> 45.2 ms -- only 33 clusters (132 of 148 SMs) are co-resident, which the epilogue-heavy kernel feels more than
+  // it gains from the lighter L2 traffic.  Default: residual GEMM only.  VTK_GEMM_CL4 = 0 never, 1 every epilogue kind.
+  static const int cl4_mode = getenv("VTK_GEMM_CL4") ? atoi(getenv("VTK_GEMM_CL4")) : -1;
+  const bool cl4 = (cl4_mode == 1 || (cl4_mode == -1 && EPI == EPI_RESID)) && !a.trans && !a.epi.prof && a.M > 2 * BM;
+  if (cl4) return launch_gemm2_cl4<EPI, NEPI, G2_STAGES>(a, tmA, tmB, sc, stream);
   const int pairs = num_sms() / 2;
   sc.setup(a.M, pairs);
   const int big = sc.num_m * sc.num_n;
