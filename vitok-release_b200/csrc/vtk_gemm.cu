@@ -1035,9 +1035,10 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
   // 4-CTA clusters (two pairs sharing the B tile by TMA multicast): bf16 / fp8 K-major operands, enough M for two 256-row tiles
   // Measured (B200, c2 / c4 in the bench pipeline): out_proj+fc2 residual GEMM 3.19 -> 3.11 ms / 21.5 -> 20.5 ms, but the QKV+fc1 GEMM
   // 6.99 -> 7.18 / 43.9 -> 45.2 ms -- only 33 clusters (132 of 148 SMs) are co-resident, which the epilogue-heavy kernel feels more than
-  // it gains from the lighter L2 traffic.  Default: residual GEMM only.  VTK_GEMM_CL4 = 0 never, 1 every epilogue kind.
+  // it gains from the lighter L2 traffic.  Default: the light epilogues (residual, plain / bias; the 5B training step's forward GEMMs
+  // gain 1 %).  VTK_GEMM_CL4 = 0 never, 1 every epilogue kind.
   static const int cl4_mode = getenv("VTK_GEMM_CL4") ? atoi(getenv("VTK_GEMM_CL4")) : -1;
-  const bool cl4 = (cl4_mode == 1 || (cl4_mode == -1 && EPI == EPI_RESID)) && !a.trans && !a.epi.prof && a.M > 2 * BM;
+  const bool cl4 = (cl4_mode == 1 || (cl4_mode == -1 && (EPI == EPI_RESID || EPI == EPI_BIAS))) && !a.trans && !a.epi.prof && a.M > 2 * BM;
   if (cl4) return launch_gemm2_cl4<EPI, NEPI, G2_STAGES>(a, tmA, tmB, sc, stream);
   const int pairs = num_sms() / 2;
   sc.setup(a.M, pairs);
