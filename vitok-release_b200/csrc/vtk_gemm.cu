@@ -976,6 +976,7 @@ template <int EPI, int NEPI, int G2_STAGES>
 static int launch_gemm2_cl4(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, TileSched sc, cudaStream_t stream) {
   sc.bm = 4 * BM;
   sc.split = 0;
+  sc.gm_cap = sc.gm_cap > 1 ? sc.gm_cap / 2 : 1;   // the band height was sized for 256-row tiles: keep the A panel of a band at ~32 MB
   constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
   const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
   auto kern = a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true, 0, 4> : gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 0, 4>;
