@@ -197,8 +197,7 @@ def run_reference(args, rank, world):
         return
     variant, batch, res, T, backend = WORKLOADS[args.workload]
     n_img = 4 if res <= 256 else 1
-    rate, cores, sec = cpu_oracle_rate(variant, n_img, res, max(1, args.steps), max(0, min(args.warmup, 1)),
-                                       "sdpa" if res == 0 else "sdpa")
+    rate, cores, sec = cpu_oracle_rate(variant, n_img, res, max(1, args.steps), max(0, min(args.warmup, 1)))
     sample = (f"{n_img} x {_res_name(res)} images per step, fp32, torch CPU ops on {cores} threads "
               "(oracle port of vitok/models/ae.py)")
     line = {

@@ -40,13 +40,6 @@ def _linear(a: torch.Tensor, lda: int, w: torch.Tensor, bias: Optional[torch.Ten
     return out
 
 
-def _transpose(x: torch.Tensor, rows: int, cols: int, ld: int) -> torch.Tensor:
-    """[rows, cols] (row pitch ld) -> contiguous [cols, rows]."""
-    out = torch.empty(cols, rows, dtype=BF, device=x.device)
-    _check(_lib.load().vtk_transpose_bf16(x.data_ptr(), ld, out.data_ptr(), rows, rows, cols, _lib.stream_ptr()))
-    return out
-
-
 def _wgrad(dy: torch.Tensor, ld_dy: int, n1: int, x: torch.Tensor, ld_x: int, n2: int, M: int) -> torch.Tensor:
     """dW [n1, n2] = dy[:, :n1]^T @ x[:, :n2] on the transposed-operand GEMM (both tiles read MN-major; no transpose pass)."""
     out = torch.empty(n1, n2, dtype=BF, device=dy.device)
