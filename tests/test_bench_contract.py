@@ -1,0 +1,56 @@
+"""The bench.py output contract, checked on the committed evidence lines (profiles/) -- no GPU needed.  A line that loses a
+key the driver / judge reads (roofline, cpu_baseline, e2e, clocks, gpu_launches) would otherwise only be noticed on the GPU box."""
+import glob
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _line(path):
+    return json.loads([l for l in open(path) if l.startswith("{")][-1])
+
+
+def _latest(pattern):
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)), key=os.path.getmtime)
+    if not files:
+        pytest.skip(f"no committed bench line matches {pattern}")
+    return files[-1]
+
+
+@pytest.mark.parametrize("pattern", ["r01_bench_c2_v*.json", "r01_bench_c3_v*.json", "r01_bench_c4_v*.json"])
+def test_ours_line_has_the_contract_keys(pattern):
+    d = _line(_latest(pattern))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "encode+decode images/sec" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic" and d["warmup"] >= 3
+    assert "workload" in d["config"] and "model" not in d["config"]
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] != d["value"]                          # measured separately, not a copy of the device-resident number
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert d["gpu_launches"] > 0 and d["clocks"]["sm_max_mhz"]
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert not (bad & set(d["clocks"]["reasons"]))
+
+
+def test_reference_line_has_the_contract_keys():
+    d = _line(_latest("r01_bench_ref_v*.json"))
+    assert d["impl"] == "reference" and d["metric"] == "encode+decode images/sec" and d["unit"] == "images/s"
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port" and d["gpu_launches"] == 0
+
+
+def test_traffic_file_matches_the_capture_it_cites():
+    t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["c2"]
+    assert t["qkv_swiglu_gemm_dram_bytes_per_launch"] >= t["algorithmic_bytes_per_launch"] * 0.95
+    assert t["qkv_swiglu_gemm_dram_bytes_per_launch"] <= t["algorithmic_bytes_per_launch"] * 1.25     # no wasted re-reads
+    cited = t["source"].split(":")[0]
+    assert os.path.exists(os.path.join(ROOT, cited)), cited
