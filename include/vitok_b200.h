@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define VTK_ABI_VERSION 3
+#define VTK_ABI_VERSION 4
 
 typedef enum {
   VTK_OK = 0,
@@ -87,19 +87,21 @@ int vtk_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream);
 int vtk_kv_len(const uint8_t* patch_mask, int* kv_len, int* is_prefix, int B, int N, void* stream);
 
 /* NaFlex token packing plan for a masked [B, N] batch (replaces the reference's [B,1,N,N] mask, vitok/models/ae.py:173-187,
- * and its work on padded tokens).  Valid tokens are packed image after image, each image padded to a multiple of 128 rows:
+ * and its work on padded tokens).  Valid tokens are packed image after image, each image padded to `pad` rows (a multiple
+ * of 8; the AE uses 16), and attention works on groups of `qrows` (128 or 256) query rows of one image:
  *   n_valid [B]                  valid tokens per image
  *   rel     [B*N]                rank of token t among the valid tokens of its image, -1 if masked
  *   cu      [B+1]                packed row offset of each image; cu[B] = packed row count (stays on the device)
- *   tile_img[B*ceil(N/128)]      image owning each 128-row packed tile (entries >= cu[B]/128 are not written)
- *   tile_order[B*ceil(N/128)]    a permutation of the packed tiles [0, cu[B]/128), tiles of images with more key tiles
- *                                first (ties in any order): the work list the attention kernel deals to its CTAs
- *   src     [B*ceil128(N)]       packed row -> source row b*N+t, -1 for pad rows (entries >= cu[B] are not written)
- * vtk_pack_rows gathers rows of `width` bf16 (packed[r] = in[src[r]], 0 for pad rows) for r < cu[B]; vtk_unpack_rows
- * scatters them back (out[b,t] = packed[cu[b] + rel[b,t]], 0 for masked tokens). */
-int vtk_pack_plan(const uint8_t* patch_mask, int B, int N, int* n_valid, int* rel, int* cu, int* tile_img, int* tile_order,
-                  int* src, void* stream);
-int vtk_pack_rows(const void* in, int64_t ld_in, const int* src, const int* cu, int B, int N, void* packed, int64_t ld_packed,
+ *   cuq     [B+1]                first attention group of each image; cuq[B] = number of groups
+ *   grp_img [B*ceil(N/qrows)]    image of each group (entries >= cuq[B] are not written)
+ *   grp_order[B*ceil(N/qrows)]   a permutation of the groups [0, cuq[B]), groups of images with more 128-key tiles first
+ *                                (ties in any order): the work list the attention kernel deals to its CTAs
+ *   src     [B*ceil(N/pad)*pad]  packed row -> source row b*N+t, -1 for pad rows (entries >= cu[B] are not written)
+ * vtk_pack_rows gathers rows of `width` bf16 (packed[r] = in[src[r]], 0 for pad rows) for r < cu[B] (row_cap = capacity of
+ * `packed` / `src`, sizes the grid); vtk_unpack_rows scatters them back (out[b,t] = packed[cu[b] + rel[b,t]], 0 for masked tokens). */
+int vtk_pack_plan(const uint8_t* patch_mask, int B, int N, int pad, int qrows, int* n_valid, int* rel, int* cu, int* cuq,
+                  int* grp_img, int* grp_order, int* src, void* stream);
+int vtk_pack_rows(const void* in, int64_t ld_in, const int* src, const int* cu, int B, int64_t row_cap, void* packed, int64_t ld_packed,
                   int width, void* stream);
 int vtk_unpack_rows(const void* packed, int64_t ld_packed, const int* rel, const int* cu, int B, int N, void* out,
                     int64_t ld_out, int width, void* stream);
@@ -259,8 +261,8 @@ typedef struct vtk_block_fp8 {
   float w_out_scale;
 } vtk_block_fp8;
 int vtk_ae_set_fp8_weights(vtk_ae_t h, int side, const vtk_block_fp8* blocks, int nblocks);
-/* NaFlex token packing (default on).  When a patch_mask is given and head_dim == 64, vtk_ae_encode/decode gather the
- * valid tokens of every image into a packed row range (each image padded to a multiple of 128 rows), run every kernel
+/* NaFlex token packing (default on).  When a patch_mask is given, vtk_ae_encode/decode gather the
+ * valid tokens of every image into a packed row range (each image padded to 16 rows), run every kernel
  * of the layer stack over the packed rows only -- the packed row count stays in device memory, nothing syncs -- and
  * scatter the result back; masked tokens of the output are 0.  This replaces the reference's [B,1,N,N] mask
  * (vitok/models/ae.py:173-187) and its work on padded tokens.  enable = 0 keeps the padded [B, N] layout with

@@ -155,29 +155,32 @@ def normalize_u8(img_u8_hwc: np.ndarray) -> np.ndarray:
     return (x - np.float32(0.5)) / np.float32(0.5)
 
 
-def pack_plan(mask: np.ndarray, tile: int = 128) -> Dict[str, np.ndarray]:
+def pack_plan(mask: np.ndarray, pad: int = 16, qrows: int = 128) -> Dict[str, np.ndarray]:
     """Token-packing plan of a [B, N] bool mask: the index layout our packed NaFlex path uses in place of the
     reference's [B,1,N,N] attention mask (vitok/models/ae.py:173-187 keeps key j of image b iff patch_mask[b, j]).
 
     This is OUR layout, not a reference data structure: the oracle restates its definition in numpy so that the
     CUDA index packing can be checked bit-exactly (include/vitok_b200.h: vtk_pack_plan).  Valid tokens keep their
-    order inside an image; every image is padded to a multiple of `tile` packed rows.
+    order inside an image; every image is padded to a multiple of `pad` packed rows; attention works on groups of
+    `qrows` query rows of one image.
     """
     mask = np.asarray(mask).astype(bool)
     B, N = mask.shape
     n_valid = mask.sum(1).astype(np.int32)
     rel = np.where(mask, np.cumsum(mask, axis=1) - 1, -1).astype(np.int32).reshape(-1)
-    padded = (n_valid + tile - 1) // tile * tile
+    padded = (n_valid + pad - 1) // pad * pad
+    groups = (n_valid + qrows - 1) // qrows
     cu = np.zeros(B + 1, np.int32)
     cu[1:] = np.cumsum(padded)
-    total = int(cu[B])
-    src = np.full(total, -1, np.int32)
-    tile_img = np.zeros(total // tile, np.int32)
+    cuq = np.zeros(B + 1, np.int32)
+    cuq[1:] = np.cumsum(groups)
+    src = np.full(int(cu[B]), -1, np.int32)
+    grp_img = np.zeros(int(cuq[B]), np.int32)
     for b in range(B):
         idx = np.nonzero(mask[b])[0]
         src[cu[b]:cu[b] + len(idx)] = b * N + idx
-        tile_img[cu[b] // tile:cu[b + 1] // tile] = b
-    # attention work list: tiles of images with more key tiles first (any order among equal counts)
-    kt = padded // tile
-    tile_order = np.argsort(-kt[tile_img], kind="stable").astype(np.int32)
-    return {"n_valid": n_valid, "rel": rel, "cu": cu, "tile_img": tile_img, "tile_order": tile_order, "src": src}
+        grp_img[cuq[b]:cuq[b + 1]] = b
+    # attention work list: groups of images with more 128-key tiles first (any order among equal counts)
+    kt = (n_valid + 127) // 128
+    grp_order = np.argsort(-kt[grp_img], kind="stable").astype(np.int32)
+    return {"n_valid": n_valid, "rel": rel, "cu": cu, "cuq": cuq, "grp_img": grp_img, "grp_order": grp_order, "src": src}

@@ -38,23 +38,23 @@ def _masks():
 
 
 @pytest.mark.parametrize("ci", range(4))
-def test_pack_plan_bit_exact(ci):
+@pytest.mark.parametrize("pad,qrows", [(16, 128), (16, 256), (128, 128)])
+def test_pack_plan_bit_exact(ci, pad, qrows):
     from vitok_b200 import _lib
     mask = _masks()[ci]
-    ref = pp_oracle.pack_plan(mask.numpy())
-    got = {k: v.cpu().numpy() for k, v in _lib.pack_plan(mask.cuda()).items()}
-    total = int(ref["cu"][-1])
-    assert np.array_equal(got["n_valid"], ref["n_valid"])
-    assert np.array_equal(got["rel"], ref["rel"])
-    assert np.array_equal(got["cu"], ref["cu"])
+    ref = pp_oracle.pack_plan(mask.numpy(), pad, qrows)
+    got = {k: v.cpu().numpy() for k, v in _lib.pack_plan(mask.cuda(), pad, qrows).items()}
+    total, ngrp = int(ref["cu"][-1]), int(ref["cuq"][-1])
+    for k in ("n_valid", "rel", "cu", "cuq"):
+        assert np.array_equal(got[k], ref[k]), k
     assert np.array_equal(got["src"][:total], ref["src"])
-    assert np.array_equal(got["tile_img"][:total // 128], ref["tile_img"])
-    assert (got["src"][total:] == -2).all() and (got["tile_img"][total // 128:] == -2).all()   # nothing written past the end
-    # tile_order: a permutation of the tiles with non-increasing key-tile counts (ties may come in any order)
-    order = got["tile_order"][:total // 128]
-    assert np.array_equal(np.sort(order), np.arange(total // 128)) and (got["tile_order"][total // 128:] == -2).all()
-    kt = ((ref["n_valid"] + 127) // 128)[ref["tile_img"]]
-    assert np.array_equal(kt[order], kt[ref["tile_order"]]) and (np.diff(kt[order]) <= 0).all()
+    assert np.array_equal(got["grp_img"][:ngrp], ref["grp_img"])
+    assert (got["src"][total:] == -2).all() and (got["grp_img"][ngrp:] == -2).all()   # nothing written past the end
+    # grp_order: a permutation of the groups with non-increasing key-tile counts (ties may come in any order)
+    order = got["grp_order"][:ngrp]
+    assert np.array_equal(np.sort(order), np.arange(ngrp)) and (got["grp_order"][ngrp:] == -2).all()
+    kt = ((ref["n_valid"] + 127) // 128)[ref["grp_img"]]
+    assert np.array_equal(kt[order], kt[ref["grp_order"]]) and (np.diff(kt[order]) <= 0).all()
 
 
 @pytest.mark.parametrize("ci", range(3))
@@ -94,7 +94,7 @@ def _cuda(batch):
     return {k: (v.cuda().to(torch.bfloat16) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
 
 
-D128 = "w128_d2_h2-w256_d3_h2/1x16x16"  # decoder head_dim 128: images padded to 256 packed rows (two query tiles per attention CTA)
+D128 = "w128_d2_h2-w256_d3_h2/1x16x16"  # decoder head_dim 128: attention groups of 256 query rows (two query tiles per CTA)
 
 
 @pytest.mark.parametrize("variant", [D64, D128])

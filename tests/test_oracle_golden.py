@@ -121,18 +121,20 @@ def test_pack_plan_oracle_properties():
     mask = rng.rand(9, 300) > 0.3
     mask[4] = False
     mask[5, :129] = True
-    pl = pp_oracle.pack_plan(mask)
-    B, N = mask.shape
-    assert pl["cu"][0] == 0 and (pl["cu"] % 128 == 0).all() and pl["cu"][-1] == len(pl["src"])
-    for b in range(B):
-        rows = pl["src"][pl["cu"][b]:pl["cu"][b + 1]]
-        kept = rows[rows >= 0]
-        assert np.array_equal(kept, b * N + np.nonzero(mask[b])[0])          # same keys, same order
-        assert (rows[len(kept):] == -1).all() and len(rows) - len(kept) < 128
-        assert (pl["tile_img"][pl["cu"][b] // 128:pl["cu"][b + 1] // 128] == b).all()
-    valid = pl["rel"] >= 0
-    assert np.array_equal(valid.reshape(B, N), mask)
-    flat_rows = (pl["cu"][:-1, None] + pl["rel"].reshape(B, N))[mask]
-    assert np.array_equal(pl["src"][flat_rows], np.nonzero(mask.reshape(-1))[0])   # rel/cu invert src
-    kt = ((pl["n_valid"] + 127) // 128)[pl["tile_img"]][pl["tile_order"]]
-    assert (np.diff(kt) <= 0).all() and np.array_equal(np.sort(pl["tile_order"]), np.arange(len(pl["tile_img"])))
+    for pad, qrows in ((16, 128), (16, 256), (128, 128)):
+        pl = pp_oracle.pack_plan(mask, pad, qrows)
+        B, N = mask.shape
+        assert pl["cu"][0] == 0 and (pl["cu"] % pad == 0).all() and pl["cu"][-1] == len(pl["src"])
+        for b in range(B):
+            rows = pl["src"][pl["cu"][b]:pl["cu"][b + 1]]
+            kept = rows[rows >= 0]
+            assert np.array_equal(kept, b * N + np.nonzero(mask[b])[0])          # same keys, same order
+            assert (rows[len(kept):] == -1).all() and len(rows) - len(kept) < pad
+            g = pl["grp_img"][pl["cuq"][b]:pl["cuq"][b + 1]]
+            assert (g == b).all() and len(g) == -(-int(pl["n_valid"][b]) // qrows)   # groups cover the image's valid rows
+        valid = pl["rel"] >= 0
+        assert np.array_equal(valid.reshape(B, N), mask)
+        flat_rows = (pl["cu"][:-1, None] + pl["rel"].reshape(B, N))[mask]
+        assert np.array_equal(pl["src"][flat_rows], np.nonzero(mask.reshape(-1))[0])   # rel/cu invert src
+        kt = ((pl["n_valid"] + 127) // 128)[pl["grp_img"]][pl["grp_order"]]
+        assert (np.diff(kt) <= 0).all() and np.array_equal(np.sort(pl["grp_order"]), np.arange(len(pl["grp_img"])))

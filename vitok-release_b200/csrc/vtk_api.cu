@@ -142,8 +142,9 @@ static Workspace carve(const Side& s, void* base, int B, int N, int io_cols) {
     off += align_up(nbytes, 1024);
     return p;
   };
-  const int pad = s.head_dim() == 128 ? 256 : 128;
-  const long long M = PackPlan::row_capacity(B, N, pad);
+  const int qrows = s.head_dim() == 128 ? 256 : 128;      // query rows per attention work group
+  const long long M = PackPlan::row_capacity(B, N, 16);   // >= B * N, so it also holds the padded (un-packed) layout
+  const long long G = PackPlan::group_capacity(B, N, qrows);
   const long long D = s.width, d = s.head_dim();
   w.x = static_cast<bf16*>(take((size_t)M * D * 2));
   w.h = static_cast<bf16*>(take((size_t)M * D * 2));
@@ -160,12 +161,13 @@ static Workspace carve(const Side& s, void* base, int B, int N, int io_cols) {
   }
   w.kv_len = static_cast<int*>(take((size_t)B * 4));
   w.is_prefix = static_cast<int*>(take((size_t)B * 4));
-  w.plan.B = B; w.plan.N = N; w.plan.pad = pad;
+  w.plan.B = B; w.plan.N = N; w.plan.pad = 16; w.plan.qrows = qrows;
   w.plan.n_valid = w.kv_len;
   w.plan.rel = static_cast<int*>(take((size_t)B * N * 4));
   w.plan.cu = static_cast<int*>(take((size_t)(B + 1) * 4));
-  w.plan.tile_img = static_cast<int*>(take((size_t)(M / 128) * 4));
-  w.plan.tile_order = static_cast<int*>(take((size_t)(M / 128) * 4));
+  w.plan.cuq = static_cast<int*>(take((size_t)(B + 1) * 4));
+  w.plan.grp_img = static_cast<int*>(take((size_t)G * 4));
+  w.plan.grp_order = static_cast<int*>(take((size_t)G * 4));
   w.plan.src = static_cast<int*>(take((size_t)M * 4));
   w.pin = static_cast<bf16*>(take((size_t)M * io_cols * 2));
   w.pout = static_cast<bf16*>(take((size_t)M * io_cols * 2));
@@ -284,31 +286,31 @@ int vtk_kv_len(const uint8_t* patch_mask, int* kv_len, int* is_prefix, int B, in
   return launch_kv_len(patch_mask, kv_len, is_prefix, B, N, (cudaStream_t)stream);
 }
 
-int vtk_pack_plan(const uint8_t* patch_mask, int B, int N, int* n_valid, int* rel, int* cu, int* tile_img, int* tile_order,
-                  int* src, void* stream) {
-  VTK_REQUIRE(patch_mask && n_valid && rel && cu && tile_img && tile_order && src, "vtk_pack_plan: null pointer");
-  VTK_REQUIRE(B > 0 && N > 0 && PackPlan::row_capacity(B, N) < (1ll << 31), "vtk_pack_plan: bad batch shape B=%d N=%d", B, N);
+int vtk_pack_plan(const uint8_t* patch_mask, int B, int N, int pad, int qrows, int* n_valid, int* rel, int* cu, int* cuq,
+                  int* grp_img, int* grp_order, int* src, void* stream) {
+  VTK_REQUIRE(patch_mask && n_valid && rel && cu && cuq && grp_img && grp_order && src, "vtk_pack_plan: null pointer");
+  VTK_REQUIRE(B > 0 && N > 0 && pad > 0 && PackPlan::row_capacity(B, N, pad) < (1ll << 31), "vtk_pack_plan: bad batch shape B=%d N=%d", B, N);
   PackPlan pl;
-  pl.B = B; pl.N = N; pl.n_valid = n_valid; pl.rel = rel; pl.cu = cu; pl.tile_img = tile_img; pl.tile_order = tile_order;
-  pl.src = src;
+  pl.B = B; pl.N = N; pl.pad = pad; pl.qrows = qrows;
+  pl.n_valid = n_valid; pl.rel = rel; pl.cu = cu; pl.cuq = cuq; pl.grp_img = grp_img; pl.grp_order = grp_order; pl.src = src;
   return launch_pack_plan(patch_mask, B, N, pl, (cudaStream_t)stream);
 }
-int vtk_pack_rows(const void* in, int64_t ld_in, const int* src, const int* cu, int B, int N, void* packed, int64_t ld_packed,
+int vtk_pack_rows(const void* in, int64_t ld_in, const int* src, const int* cu, int B, int64_t row_cap, void* packed, int64_t ld_packed,
                   int width, void* stream) {
   VTK_REQUIRE(in && src && cu && packed, "vtk_pack_rows: null pointer");
-  VTK_REQUIRE(B > 0 && N > 0 && width > 0, "vtk_pack_rows: empty problem");
+  VTK_REQUIRE(B > 0 && row_cap > 0 && width > 0, "vtk_pack_rows: empty problem");
   PackPlan pl;
-  pl.B = B; pl.N = N; pl.n_valid = nullptr; pl.rel = nullptr; pl.cu = const_cast<int*>(cu); pl.tile_img = nullptr;
-  pl.tile_order = nullptr; pl.src = const_cast<int*>(src);
-  return launch_pack_rows((const bf16*)in, ld_in, pl, PackPlan::row_capacity(B, N), (bf16*)packed, ld_packed, width, (cudaStream_t)stream);
+  pl.B = B; pl.N = 0; pl.n_valid = nullptr; pl.rel = nullptr; pl.cu = const_cast<int*>(cu); pl.cuq = nullptr; pl.grp_img = nullptr;
+  pl.grp_order = nullptr; pl.src = const_cast<int*>(src);
+  return launch_pack_rows((const bf16*)in, ld_in, pl, row_cap, (bf16*)packed, ld_packed, width, (cudaStream_t)stream);
 }
 int vtk_unpack_rows(const void* packed, int64_t ld_packed, const int* rel, const int* cu, int B, int N, void* out,
                     int64_t ld_out, int width, void* stream) {
   VTK_REQUIRE(packed && rel && cu && out, "vtk_unpack_rows: null pointer");
   VTK_REQUIRE(B > 0 && N > 0 && width > 0, "vtk_unpack_rows: empty problem");
   PackPlan pl;
-  pl.B = B; pl.N = N; pl.n_valid = nullptr; pl.rel = const_cast<int*>(rel); pl.cu = const_cast<int*>(cu); pl.tile_img = nullptr;
-  pl.tile_order = nullptr; pl.src = nullptr;
+  pl.B = B; pl.N = N; pl.n_valid = nullptr; pl.rel = const_cast<int*>(rel); pl.cu = const_cast<int*>(cu); pl.cuq = nullptr;
+  pl.grp_img = nullptr; pl.grp_order = nullptr; pl.src = nullptr;
   return launch_unpack_rows((const bf16*)packed, ld_packed, pl, (bf16*)out, ld_out, width, (cudaStream_t)stream);
 }
 
@@ -628,7 +630,8 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
     if (pl) {
       // packed: image b = packed rows [cu[b], cu[b+1]) with its n_valid[b] tokens in front -- no key mask left
       a.kv_len = pl->n_valid; a.key_mask = nullptr; a.prefix_flag = nullptr; a.zero_invalid_rows = 0;
-      a.cu = pl->cu; a.tile_img = pl->tile_img; a.tile_order = pl->tile_order; a.m_dev = m_dev; a.row_cap = M;
+      a.cu = pl->cu; a.cuq = pl->cuq; a.grp_img = pl->grp_img; a.grp_order = pl->grp_order; a.row_cap = M;
+      a.grp_cap = (int)PackPlan::group_capacity(B, N, pl->qrows);
       a.window = -1;
     } else {
       a.kv_len = patch_mask ? w.kv_len : nullptr; a.key_mask = patch_mask; a.prefix_flag = patch_mask ? w.is_prefix : nullptr;
@@ -665,7 +668,7 @@ static int run_side(vtk_ae_s* h, int side, const void* in, const int64_t* row_id
   Workspace w = carve(s, workspace, B, N, io_cols(h->cfg));
   const bool packed = use_packing(h, s, patch_mask);
   const PackPlan* pl = packed ? &w.plan : nullptr;
-  const int rows = packed ? (int)PackPlan::row_capacity(B, N, w.plan.pad) : B * N;
+  const int rows = packed ? (int)PackPlan::row_capacity(B, N, w.plan.pad) : B * N;   // capacity; the live count is pl->m_dev()
   const int* m_dev = packed ? pl->m_dev() : nullptr;
   int launches = 0, r;
   h->ev_used = 0;
@@ -708,7 +711,7 @@ static int check_io(vtk_ae_t h, int side, const void* in, const int64_t* row_idx
   VTK_REQUIRE(s.width > 0 && s.w_a, "%s: this model has no %s weights set", fn, side ? "decoder" : "encoder");
   VTK_REQUIRE(in && row_idx && col_idx && out && workspace, "%s: null pointer", fn);
   VTK_REQUIRE(B > 0 && N > 0, "%s: empty batch (B=%d N=%d)", fn, B, N);
-  VTK_REQUIRE(PackPlan::row_capacity(B, N, 256) < (1ll << 31), "%s: B*N too large", fn);
+  VTK_REQUIRE(PackPlan::row_capacity(B, N, 16) < (1ll << 31), "%s: B*N too large", fn);
   VTK_REQUIRE(workspace_bytes >= vtk_ae_workspace_bytes(h, side, B, N), "%s: workspace too small (%zu < %zu)", fn,
               workspace_bytes, vtk_ae_workspace_bytes(h, side, B, N));
   VTK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "%s: workspace must be 1024-byte aligned", fn);

@@ -64,9 +64,10 @@ struct AttnParams {
   float scale_log2;   // (1/sqrt(d)) * log2(e)
   unsigned long long* prof;   // perf experiments (env VTK_ATTN_PROF): clock64 accumulators, or null
   float* lse;                 // [B*N, heads] log2-domain logsumexp of the scaled scores (training), or null; +inf for zero rows
-  // packed NaFlex batches (persistent kernel only): image b owns packed rows [cu[b], cu[b+1]) (multiples of 128), holds
-  // kv_len[b] valid tokens at the front; tile_img[r / 128] = image of packed row r; *m_dev = cu[B] = packed row count
-  const int* cu; const int* tile_img; const int* tile_order; const int* m_dev;
+  // packed NaFlex batches: image b owns packed rows [cu[b], cu[b+1]) and holds kv_len[b] valid tokens at the front; work group g
+  // (128 query rows for the persistent kernel, NQ * 128 for the one-shot kernel) is the (g - cuq[img])-th group of image
+  // img = grp_img[g]; cuq[B] (= *n_grp) groups exist; grp_order lists them longest image first
+  const int* cu; const int* cuq; const int* grp_img; const int* grp_order; const int* n_grp;
 };
 
 __device__ __forceinline__ float max3f(float a, float b, float c) {
@@ -197,14 +198,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   int q0, img, N, kvlen;
   long long row0;
   if (p.cu) {
-    // packed NaFlex layout (images padded to NQ * 128 rows): blockIdx.x = group of NQ packed tiles, all of one image
-    const int first_tile = blockIdx.x * NQ;
-    if (first_tile * ATT_BQ >= __ldg(p.m_dev)) return;   // beyond the packed rows of this batch (whole CTA)
-    img = p.tile_img[first_tile];
+    // packed NaFlex layout: blockIdx.x = work group (NQ * 128 query rows of one image)
+    const int grp = blockIdx.x;
+    if (grp >= __ldg(p.n_grp)) return;   // beyond the groups of this batch (whole CTA)
+    img = p.grp_img[grp];
     row0 = p.cu[img];
-    q0 = first_tile * ATT_BQ - (int)row0;
+    q0 = (grp - p.cuq[img]) * (NQ * ATT_BQ);
     kvlen = p.kv_len[img];
-    N = (kvlen + NQ * ATT_BQ - 1) / (NQ * ATT_BQ) * (NQ * ATT_BQ);
+    N = kvlen;                           // rows >= kvlen of the last tile belong to the next image: never stored
   } else {
     q0 = blockIdx.x * (NQ * ATT_BQ);
     img = blockIdx.z;
@@ -476,8 +477,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 #pragma unroll
     for (int c = 0; c < DH / 32; ++c) tmem_ld32(tO + c * 32, o[c]);
     tmem_wait_ld();
-    if (p.tma_out) {
-      // N % 128 == 0: the tile never straddles an image.  Stage this warp's 32 rows in the (now idle) Q buffer
+    if (p.tma_out && (p.cu == nullptr || q0 + (q + 1) * ATT_BQ <= N)) {
+      // the tile does not straddle an image (N % 128 == 0, or a full tile of a packed image).  Stage this warp's 32 rows in the (now idle) Q buffer
       // in the 128B-swizzled layout and let one TMA store per 64-column block write full 128-byte row segments.
       uint8_t* srow = sQ + q * S::TILE_BYTES + r * 128;
 #pragma unroll
@@ -557,16 +558,15 @@ struct AttnItem {
 template <bool PACKED>
 __device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int w, int qtiles) {
   AttnItem it;
-  if (PACKED) {   // packed layout: work item = (128-row packed tile, head); every tile holds at least one valid query
+  if (PACKED) {   // packed layout: work item = (group of 128 query rows of one image, head); every group holds a valid query
     const int rank = w / p.heads;
     it.head = w - rank * p.heads;
-    const int tile = p.tile_order[rank];     // longest images first (pack_plan_kernel)
-    it.img = p.tile_img[tile];
-    const int base = p.cu[it.img];
-    it.row0 = base;
-    it.q0 = tile * ATT_BQ - base;
+    const int grp = p.grp_order[rank];       // longest images first (pack_plan_kernel)
+    it.img = p.grp_img[grp];
+    it.row0 = p.cu[it.img];
+    it.q0 = (grp - p.cuq[it.img]) * ATT_BQ;
     it.kvlen = p.kv_len[it.img];
-    it.nrows = (it.kvlen + ATT_BQ - 1) / ATT_BQ * ATT_BQ;
+    it.nrows = it.kvlen;                     // rows >= kvlen of the last tile belong to the next image: never stored
   } else {
     const int per_img = qtiles * p.heads;
     it.img = w / per_img;
@@ -593,7 +593,7 @@ __device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int w, int qt
 }
 
 // Item k of this CTA.  SNAKE = false: plain round-robin (w = blockIdx + k * grid).  SNAKE = true (packed batches, whose
-// item list is sorted by cost -- pack_plan_kernel's tile_order): items are dealt boustrophedon-wise (0 .. G-1, then
+// item list is sorted by cost -- pack_plan_kernel's grp_order): items are dealt boustrophedon-wise (0 .. G-1, then
 // G-1 .. 0, ...), so every CTA ends up with nearly the same amount of work without a shared counter (c3: max/mean CTA
 // load 1.03 instead of 1.19).  Returns false when the CTA is done; a SNAKE caller must skip w >= total.
 template <bool SNAKE>
@@ -619,7 +619,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int W = p.window;
-  const int total_items = SNAKE ? min(total_items_host, (__ldg(p.m_dev) / ATT_BQ) * p.heads) : total_items_host;   // SNAKE <=> packed layout
+  const int total_items = SNAKE ? min(total_items_host, __ldg(p.n_grp) * p.heads) : total_items_host;   // SNAKE <=> packed layout
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem + S::OFF_Q;
@@ -872,7 +872,7 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int c = 0; c < DH / 32; ++c) tmem_ld32(tO + c * 32, o[c]);
       tmem_wait_ld();
       tc_fence_before();
-      if (p.tma_out) {
+      if (p.tma_out && (!SNAKE || it.q0 + ATT_BQ <= it.nrows)) {   // packed: only full tiles leave through TMA (a partial tile shares rows with the next image)
         if (PTMEM && store_pending) {   // the previous item's TMA store has read the staging rows
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
@@ -939,8 +939,8 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   const bool packed = a.cu != nullptr;
   const long long Mrows = packed ? a.row_cap : (long long)a.B * a.N;
   const long long cols = (long long)a.heads * a.d;
-  if (packed && (!a.tile_img || !a.tile_order || !a.m_dev || !a.kv_len || a.key_mask || a.window >= 0 || a.row_cap % ATT_BQ)) {
-    set_error("attention: packed layout needs cu/tile_img/m_dev/kv_len, a row capacity that is a multiple of 128, no key mask and no window");
+  if (packed && (!a.cuq || !a.grp_img || !a.grp_order || !a.kv_len || a.key_mask || a.window >= 0 || a.row_cap <= 0 || a.grp_cap <= 0)) {
+    set_error("attention: packed layout needs cu/cuq/grp_img/grp_order/kv_len, row and group capacities, no key mask and no window");
     return -2;
   }
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -955,7 +955,7 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   p.tma_out = (packed || a.N % ATT_BQ == 0) ? 1 : 0;
   p.window = a.window;
   p.lse = a.lse;
-  p.cu = a.cu; p.tile_img = a.tile_img; p.tile_order = a.tile_order; p.m_dev = a.m_dev;
+  p.cu = a.cu; p.cuq = a.cuq; p.grp_img = a.grp_img; p.grp_order = a.grp_order; p.n_grp = a.cuq ? a.cuq + a.B : nullptr;
   p.prof = nullptr;
   static const int prof_mode = getenv("VTK_ATTN_PROF") ? atoi(getenv("VTK_ATTN_PROF")) : 0;
   static unsigned long long* d_prof = nullptr;
@@ -978,7 +978,7 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
     attr_set[ai] = true;
   }
   const int qtiles = (a.N + ATT_BQ - 1) / ATT_BQ;
-  const long long total = packed ? (Mrows / ATT_BQ) * a.heads : (long long)a.B * a.heads * qtiles;
+  const long long total = packed ? (long long)a.grp_cap * a.heads : (long long)a.B * a.heads * qtiles;
   if (total >= (1ll << 31)) { set_error("attention: too many work items"); return -2; }
   const int grid = (int)std::min<long long>(total, 2ll * num_sms());
   kern<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
@@ -998,8 +998,8 @@ template <int DH, int NQ>
 static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   using S = AttnShape<DH, NQ>;
   const bool packed = a.cu != nullptr;
-  if (packed && (!a.tile_img || !a.m_dev || !a.kv_len || a.key_mask || a.window >= 0 || a.row_cap % (NQ * ATT_BQ))) {
-    set_error("attention: packed layout needs cu/tile_img/m_dev/kv_len, a row capacity that is a multiple of %d, no key mask and no window", NQ * ATT_BQ);
+  if (packed && (!a.cuq || !a.grp_img || !a.kv_len || a.key_mask || a.window >= 0 || a.row_cap <= 0 || a.grp_cap <= 0)) {
+    set_error("attention: packed layout needs cu/cuq/grp_img/kv_len, row and group capacities, no key mask and no window");
     return -2;
   }
   const long long Mrows = packed ? a.row_cap : (long long)a.B * a.N;
@@ -1017,7 +1017,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   p.tma_out = (packed || a.N % ATT_BQ == 0) ? 1 : 0;
   p.window = a.window;
   p.lse = a.lse;
-  p.cu = a.cu; p.tile_img = a.tile_img; p.tile_order = a.tile_order; p.m_dev = a.m_dev;
+  p.cu = a.cu; p.cuq = a.cuq; p.grp_img = a.grp_img; p.grp_order = a.grp_order; p.n_grp = a.cuq ? a.cuq + a.B : nullptr;
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
   static const int prof_mode = getenv("VTK_ATTN_PROF") ? atoi(getenv("VTK_ATTN_PROF")) : 0;
   static unsigned long long* d_prof = nullptr;
@@ -1036,7 +1036,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.N + NQ * ATT_BQ - 1) / (NQ * ATT_BQ), a.heads, a.B);
-  if (packed) grid = dim3((unsigned)(Mrows / (NQ * ATT_BQ)), a.heads, 1);
+  if (packed) grid = dim3((unsigned)a.grp_cap, a.heads, 1);
   kern<<<grid, S::THREADS, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   if (prof_mode) {
     unsigned long long h[8];

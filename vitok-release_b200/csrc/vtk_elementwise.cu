@@ -321,55 +321,59 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t* __restri
   if (tid == 0) n_valid[b] = running;
 }
 
-// one CTA: cu[b] = packed row offset of image b (exclusive scan of ceil128(n_valid)), cu[B] = packed row count,
-// tile_img[r / 128] = image that owns packed rows [r, r + 128), tile_order = the packed tiles sorted by the number of
-// key tiles of their image, longest first (counting sort; ties in arbitrary order) -- the attention kernel deals its
-// work items from this list so that every persistent CTA gets the same mix of long and short items.
-__global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__ n_valid, int* __restrict__ cu,
-                                                         int* __restrict__ tile_img, int* __restrict__ tile_order, int B, int N,
-                                                         int pad) {
+// one CTA: cu[b] = packed row offset of image b (exclusive scan of n_valid rounded up to `pad` rows), cu[B] = packed row
+// count; attention work groups (`qrows` = 128 or 256 query rows of ONE image each): cuq[b] = first group of image b,
+// cuq[B] = number of groups, grp_img[g] = image of group g, grp_order = the groups sorted by the number of key tiles of
+// their image, longest first (counting sort; ties in arbitrary order) -- the attention kernel deals its work items from
+// this list so that every persistent CTA gets the same mix of long and short items.
+__global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__ n_valid, int* __restrict__ cu, int* __restrict__ cuq,
+                                                         int* __restrict__ grp_img, int* __restrict__ grp_order, int B, int N, int pad,
+                                                         int qrows) {
   constexpr int MAX_BINS = 2048;
-  __shared__ int warp_tot[32];
-  __shared__ int running;
+  __shared__ int warp_tot[2][32];
+  __shared__ int running[2];
   __shared__ int bins[MAX_BINS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) running = 0;
+  if (tid < 2) running[tid] = 0;
   __syncthreads();
   for (int b0 = 0; b0 < B; b0 += 1024) {
     const int b = b0 + tid;
-    const int padded = b < B ? ((n_valid[b] + pad - 1) / pad * pad) : 0;   // pad = 128, or 256 for the two-tile CTAs of d = 128
-    int incl = padded;
+    const int n = b < B ? n_valid[b] : 0;
+    const int padded = (n + pad - 1) / pad * pad;
+    const int groups = (n + qrows - 1) / qrows;
+    int incl_r = padded, incl_g = groups;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+      const int vr = __shfl_up_sync(0xffffffffu, incl_r, o), vg = __shfl_up_sync(0xffffffffu, incl_g, o);
+      if (lane >= o) { incl_r += vr; incl_g += vg; }
     }
-    if (lane == 31) warp_tot[warp] = incl;
+    if (lane == 31) { warp_tot[0][warp] = incl_r; warp_tot[1][warp] = incl_g; }
     __syncthreads();
-    int before = running;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
-    const int start = before + incl - padded;
+    int before_r = running[0], before_g = running[1];
+    for (int w = 0; w < warp; ++w) { before_r += warp_tot[0][w]; before_g += warp_tot[1][w]; }
     if (b < B) {
-      cu[b] = start;
-      for (int q = 0; q < padded; q += 128) tile_img[(start + q) >> 7] = b;
+      cu[b] = before_r + incl_r - padded;
+      const int g0 = before_g + incl_g - groups;
+      cuq[b] = g0;
+      for (int q = 0; q < groups; ++q) grp_img[g0 + q] = b;
     }
     __syncthreads();
-    if (tid == 1023) running = before + incl;
+    if (tid == 1023) { running[0] = before_r + incl_r; running[1] = before_g + incl_g; }
     __syncthreads();
   }
-  if (tid == 0) cu[B] = running;
-  // ---- tile order: counting sort by key tiles per image, descending ----
-  const int nbins = (N + pad - 1) / pad * (pad / 128);   // an image has 1 .. nbins 128-row tiles
-  const int ntiles = running >> 7;
+  if (tid == 0) { cu[B] = running[0]; cuq[B] = running[1]; }
+  // ---- group order: counting sort by key tiles per image, descending ----
+  const int nbins = (N + 127) / 128;           // an image has 1 .. nbins key tiles
+  const int ngroups = running[1];
   if (nbins > MAX_BINS) {                      // very long sequences: keep the natural order
-    for (int t = tid; t < ntiles; t += 1024) tile_order[t] = t;
+    for (int t = tid; t < ngroups; t += 1024) grp_order[t] = t;
     return;
   }
   for (int i = tid; i <= nbins; i += 1024) bins[i] = 0;
   __syncthreads();
   for (int b = tid; b < B; b += 1024) {
-    const int kt = ((n_valid[b] + pad - 1) / pad * pad) >> 7;
-    if (kt > 0) atomicAdd(&bins[kt], kt);      // an image with kt key tiles contributes kt query tiles
+    const int n = n_valid[b];
+    if (n > 0) atomicAdd(&bins[(n + 127) >> 7], (n + qrows - 1) / qrows);
   }
   __syncthreads();
   if (tid == 0) {                              // start offset of each bin, longest images first
@@ -378,11 +382,12 @@ __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__
   }
   __syncthreads();
   for (int b = tid; b < B; b += 1024) {
-    const int kt = ((n_valid[b] + pad - 1) / pad * pad) >> 7;
-    if (kt > 0) {
-      const int at = atomicAdd(&bins[kt], kt);
-      const int first = cu[b] >> 7;
-      for (int q = 0; q < kt; ++q) tile_order[at + q] = first + q;
+    const int n = n_valid[b];
+    if (n > 0) {
+      const int groups = (n + qrows - 1) / qrows;
+      const int at = atomicAdd(&bins[(n + 127) >> 7], groups);
+      const int first = cuq[b];
+      for (int q = 0; q < groups; ++q) grp_order[at + q] = first + q;
     }
   }
 }
@@ -434,8 +439,11 @@ __global__ void __launch_bounds__(256) unpack_rows_kernel(const bf16* __restrict
 int launch_pack_plan(const uint8_t* mask, int B, int N, const PackPlan& pl, cudaStream_t stream) {
   if (B <= 0 || N <= 0) return 0;
   pack_count_kernel<<<B, 256, 0, stream>>>(mask, pl.rel, pl.n_valid, N);
-  if (pl.pad != 128 && pl.pad != 256) { set_error("pack_plan: row padding must be 128 or 256 (got %d)", pl.pad); return -2; }
-  pack_plan_kernel<<<1, 1024, 0, stream>>>(pl.n_valid, pl.cu, pl.tile_img, pl.tile_order, B, N, pl.pad);
+  if (pl.pad < 8 || pl.pad % 8 || (pl.qrows != 128 && pl.qrows != 256)) {
+    set_error("pack_plan: row padding must be a positive multiple of 8 and the attention group 128 or 256 rows (got %d, %d)", pl.pad, pl.qrows);
+    return -2;
+  }
+  pack_plan_kernel<<<1, 1024, 0, stream>>>(pl.n_valid, pl.cu, pl.cuq, pl.grp_img, pl.grp_order, B, N, pl.pad, pl.qrows);
   pack_src_kernel<<<B, 256, 0, stream>>>(pl.rel, pl.n_valid, pl.cu, pl.src, N, pl.pad);
   return check_cuda(cudaGetLastError(), "pack_plan launch");
 }

@@ -98,9 +98,11 @@ struct AttnArgs {
   int zero_invalid_rows;        // 1: rows >= kv_len[b] (or with key_mask 0) are written as 0
   int window;                   // sliding window: keys j with |i - j| <= window (flash_attn window_size=(w,w)); < 0 = none
   float* lse;                   // optional [B*N, heads] fp32: log2-domain logsumexp of the scaled scores (for the backward pass)
-  // packed NaFlex layout (PackPlan; head_dim 64): rows of image b start at cu[b], kv_len[b] valid tokens, no key_mask
-  const int* cu = nullptr; const int* tile_img = nullptr; const int* tile_order = nullptr; const int* m_dev = nullptr;
-  long long row_cap = 0;
+  // packed NaFlex layout (PackPlan): rows of image b start at cu[b] and hold kv_len[b] valid tokens, no key_mask; work group g
+  // (128 query rows at d = 64, 256 at d = 128) belongs to image grp_img[g] and is the (g - cuq[grp_img[g]])-th of that image
+  const int* cu = nullptr; const int* cuq = nullptr; const int* grp_img = nullptr; const int* grp_order = nullptr;
+  long long row_cap = 0;   // rows of the q / k / v / out buffers
+  int grp_cap = 0;         // capacity of the group arrays (grid size of the one-shot kernel)
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 
@@ -126,18 +128,25 @@ int launch_rope_table(const int64_t* row_idx, const int64_t* col_idx, const floa
                       cudaStream_t stream, const int* src_map = nullptr, const int* m_dev = nullptr);
 
 // NaFlex token packing (vtk_elementwise.cu): valid tokens of a masked [B, N] batch packed image after image, each image
-// padded to a multiple of 128 rows.  All arrays live in device memory (carved from the caller's workspace).
+// padded to `pad` rows (16: row tiles of the GEMMs may straddle images; only 16-byte alignment of the rows matters).
+// Attention works on groups of `qrows` query rows of one image (128, or 256 for the two-tile CTAs of d = 128); a group's
+// last tile may be partial -- its rows beyond n_valid belong to the next image and are neither attended to (keys are
+// masked by n_valid) nor stored.  All arrays live in device memory (carved from the caller's workspace).
 struct PackPlan {
   int B, N;
-  int pad = 128;   // rows every image is padded to in the packed layout: 128, or 256 when the attention CTA owns two query tiles (d = 128)
+  int pad = 16;     // rows every image is padded to in the packed layout
+  int qrows = 128;  // query rows per attention work group
   int* n_valid;    // [B]      valid tokens per image (= key count of the image in the packed layout)
   int* rel;        // [B * N]  rank of a token among the valid tokens of its image, -1 if masked
   int* cu;         // [B + 1]  packed row offset per image; cu[B] = packed row count (the m_dev of every kernel)
-  int* tile_img;   // [B * ceil(N / 128)]  image owning each 128-row packed tile
-  int* tile_order; // [B * ceil(N / 128)]  packed tiles sorted by key tiles of their image, longest first (attention work list)
-  int* src;        // [B * ceil128(N)]     packed row -> source row b * N + t, -1 for pad rows
+  int* cuq;        // [B + 1]  first attention group of each image; cuq[B] = number of groups
+  int* grp_img;    // [B * ceil(N / qrows)]  image of each group
+  int* grp_order;  // [B * ceil(N / qrows)]  groups sorted by key tiles of their image, longest first (attention work list)
+  int* src;        // [row capacity]         packed row -> source row b * N + t, -1 for pad rows
   const int* m_dev() const { return cu + B; }
-  static long long row_capacity(int B, int N, int pad = 128) { return (long long)B * ((N + pad - 1) / pad * pad); }
+  const int* n_groups() const { return cuq + B; }
+  static long long row_capacity(int B, int N, int pad = 16) { return (long long)B * ((N + pad - 1) / pad * pad); }
+  static long long group_capacity(int B, int N, int qrows) { return (long long)B * ((N + qrows - 1) / qrows); }
 };
 int launch_pack_plan(const uint8_t* mask, int B, int N, const PackPlan& pl, cudaStream_t stream);
 int launch_pack_rows(const bf16* in, long long ld_in, const PackPlan& pl, long long row_cap, bf16* out, long long ld_out, int width,

@@ -51,8 +51,8 @@ SIGNATURES = {
     "vtk_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "vtk_cast_bf16_to_f32": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "vtk_kv_len": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
-    "vtk_pack_plan": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "vtk_pack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
+    "vtk_pack_plan": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vtk_pack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_int, c_vp]),
     "vtk_unpack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
     "vtk_quant_rows_e4m3": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp]),
     "vtk_proj_residual_fp8": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
@@ -242,28 +242,29 @@ def kv_len(mask: torch.Tensor):
     return kl, pf
 
 
-def pack_plan(mask: torch.Tensor):
+def pack_plan(mask: torch.Tensor, pad: int = 16, qrows: int = 128):
     """NaFlex token-packing plan of a [B, N] bool mask (include/vitok_b200.h: vtk_pack_plan).  Arrays the kernel leaves
-    unwritten (beyond the packed row count) are pre-filled with -2."""
+    unwritten (beyond the packed row / group counts) are pre-filled with -2."""
     B, N = mask.shape
     m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
-    cap = B * ((N + 127) // 128 * 128)
+    cap = B * ((N + pad - 1) // pad * pad)
+    gcap = B * ((N + qrows - 1) // qrows)
     i32 = dict(dtype=torch.int32, device=mask.device)
-    n_valid, rel, cu = torch.empty(B, **i32), torch.empty(B * N, **i32), torch.empty(B + 1, **i32)
-    tile_img, src = torch.full((cap // 128,), -2, **i32), torch.full((cap,), -2, **i32)
-    tile_order = torch.full((cap // 128,), -2, **i32)
-    check(load().vtk_pack_plan(ptr(m), B, N, ptr(n_valid), ptr(rel), ptr(cu), ptr(tile_img), ptr(tile_order), ptr(src),
-                               stream_ptr()))
-    return {"n_valid": n_valid, "rel": rel, "cu": cu, "tile_img": tile_img, "tile_order": tile_order, "src": src}
+    n_valid, rel, cu, cuq = torch.empty(B, **i32), torch.empty(B * N, **i32), torch.empty(B + 1, **i32), torch.empty(B + 1, **i32)
+    grp_img, grp_order, src = torch.full((gcap,), -2, **i32), torch.full((gcap,), -2, **i32), torch.full((cap,), -2, **i32)
+    check(load().vtk_pack_plan(ptr(m), B, N, pad, qrows, ptr(n_valid), ptr(rel), ptr(cu), ptr(cuq), ptr(grp_img), ptr(grp_order),
+                               ptr(src), stream_ptr()))
+    return {"n_valid": n_valid, "rel": rel, "cu": cu, "cuq": cuq, "grp_img": grp_img, "grp_order": grp_order, "src": src}
 
 
 def pack_rows(x: torch.Tensor, plan: dict) -> torch.Tensor:
-    """x [B, N, W] bf16 -> packed [B * ceil128(N), W] (rows beyond cu[B] are left as allocated: zeros here)."""
+    """x [B, N, W] bf16 -> packed [row capacity of the plan, W] (rows beyond cu[B] are left as allocated: zeros here)."""
     _req(x, torch.bfloat16, "x")
     B, N, W = x.shape
     x = x.contiguous()
-    out = torch.zeros(B * ((N + 127) // 128 * 128), W, dtype=torch.bfloat16, device=x.device)
-    check(load().vtk_pack_rows(ptr(x), W, ptr(plan["src"]), ptr(plan["cu"]), B, N, ptr(out), W, W, stream_ptr()))
+    cap = plan["src"].numel()
+    out = torch.zeros(cap, W, dtype=torch.bfloat16, device=x.device)
+    check(load().vtk_pack_rows(ptr(x), W, ptr(plan["src"]), ptr(plan["cu"]), B, cap, ptr(out), W, W, stream_ptr()))
     return out
 
 
