@@ -173,3 +173,27 @@ def test_c3_ragged_batch_equals_single_images():
     print(f"[parity] c3 ragged-vs-single: z max-abs {worst_z:.3e}, patches max-abs {worst_p:.3e} (tokens: {sum(n)} of {64 * 1024})")
     assert worst_z == 0.0 and worst_p == 0.0
     assert (enc["z"][~batch["patch_mask"]] == 0).all()
+
+
+def test_fully_masked_batch_is_all_zero_and_does_not_hang():
+    """Edge case: no valid token at all (packed row count 0 -> every kernel gets an empty problem from device memory)."""
+    model, cfg, _ = _model(D64)
+    batch = _ragged_batch([(64, 64), (32, 48)], 16, 64, seed=3)
+    batch["patch_mask"] = torch.zeros_like(batch["patch_mask"])
+    with torch.no_grad():
+        enc = model.encode(_cuda(batch))
+        dec = model.decode(enc)
+    torch.cuda.synchronize()
+    assert (enc["z"] == 0).all() and (dec["patches"] == 0).all()
+    # and a batch where only ONE image has tokens
+    batch = _ragged_batch([(64, 64), (32, 48), (128, 16)], 16, 64, seed=4)
+    batch["patch_mask"][0] = False
+    batch["patch_mask"][2] = False
+    cb = _cuda(batch)
+    with torch.no_grad():
+        model.token_packing = True
+        d1 = model.decode(model.encode(cb))
+        model.token_packing = False
+        d0 = model.decode(model.encode(cb))
+    valid = batch["patch_mask"]
+    assert torch.equal(d1["patches"].cpu()[valid], d0["patches"].cpu()[valid]) and (d1["patches"].cpu()[~valid] == 0).all()
