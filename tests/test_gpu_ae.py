@@ -255,3 +255,36 @@ def test_cuda_graph_replay_equals_eager(backend):
         out = graphed(b)
         assert torch.equal(out["patches"], eager["patches"])
         assert out["orig_height"] is b["orig_height"]
+
+
+@pytest.mark.parametrize("backend", ["sdpa", "flash"])
+def test_reference_smoke_case_Bd2_Bd4(backend):
+    """The reference's own AE smoke test (tests/cpu/test_ae.py:43-76,162-233): variant Bd2-Bd4/1x16x32, B = 2, N = 64 random
+    patches on an 8 x 8 grid with a full mask -- there it only asserts shapes and finiteness; here also parity with the oracle
+    (width 768 = 3 column tiles, 12 heads of 64, Hf = 2048)."""
+    variant = "Bd2-Bd4/1x16x32"
+    cfg0 = ae_oracle.decode_variant(variant)
+    sd = make_state_dict(cfg0, seed=2, stress=True)
+    model, cfg = _model(variant, sd, backend)
+    g = torch.Generator().manual_seed(0)
+    B, N = 2, 64
+    yy, xx = torch.meshgrid(torch.arange(8), torch.arange(8), indexing="ij")
+    batch = {
+        "patches": torch.randn(B, N, cfg["pixels_per_token"], generator=g),
+        "patch_mask": torch.ones(B, N, dtype=torch.bool),
+        "row_idx": yy.reshape(1, N).repeat(B, 1), "col_idx": xx.reshape(1, N).repeat(B, 1),
+        "orig_height": torch.full((B,), 128), "orig_width": torch.full((B,), 128),
+    }
+    with torch.no_grad():
+        enc = model.encode(_to_cuda(batch))
+        dec = model.decode(enc)
+    assert enc["z"].shape == (B, N, cfg["channels_per_token"]) and dec["patches"].shape == batch["patches"].shape   # test_ae.py:224-229
+    assert torch.isfinite(enc["z"]).all() and torch.isfinite(dec["patches"]).all()
+    e_o = ae_oracle.encode(sd, batch, cfg["encoder_heads"], attn_backend=backend)
+    d_o = ae_oracle.decode(sd, e_o, cfg["decoder_heads"], attn_backend=backend)
+    sdb = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    bb = {k: (v.to(torch.bfloat16) if v.dtype == torch.float32 else v) for k, v in batch.items()}
+    d_b = ae_oracle.decode(sdb, ae_oracle.encode(sdb, bb, cfg["encoder_heads"], attn_backend=backend), cfg["decoder_heads"], attn_backend=backend)
+    own_p = (d_b["patches"].float() - d_o["patches"]).abs().max().item()
+    ma_p, _ = report(f"Bd2-Bd4 {backend} patches", dec["patches"].cpu().float(), d_o["patches"])
+    assert ma_p <= max(2 * own_p, 5e-2)
