@@ -15,6 +15,8 @@ variant, B, res, T, backend = WORKLOADS[wl]
 cfg = vb.decode_variant(variant)
 torch.manual_seed(0)
 model = vb.AE(**cfg, attn_backend=backend).eval().to("cuda", torch.bfloat16)
+if os.environ.get("VTK_PROF_QUANTIZE") == "1":      # FP8 block GEMMs (AE.quantize)
+    model.quantize()
 imgs = (torch.rand(B, 3, res, res, generator=torch.Generator().manual_seed(1234)) * 2 - 1).cuda()
 pd = vb.patchify_batch(imgs, cfg["spatial_stride"], T, out_dtype=torch.bfloat16)
 with torch.no_grad():
