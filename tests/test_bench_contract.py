@@ -54,3 +54,22 @@ def test_traffic_file_matches_the_capture_it_cites():
     assert t["qkv_swiglu_gemm_dram_bytes_per_launch"] <= t["algorithmic_bytes_per_launch"] * 1.25     # no wasted re-reads
     cited = t["source"].split(":")[0]
     assert os.path.exists(os.path.join(ROOT, cited)), cited
+
+
+def test_flop_model_matches_the_survey_numbers():
+    """bench.py's algorithmic FLOPs per image (verified there against FlopCounterMode): 350M @N=256
+    189.01 GFLOP, 350M @N=1024 846.2, 5B-f16x64 @N=256 2592.6, @N=1024 10 795.5, 5B-f32x256 @N=1024 10 826.9."""
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "vitok-release_b200"))
+    import bench
+    from oracle import ae_oracle
+    cases = [("Ld4-Ld24/1x16x64", 256, 189.01), ("Ld4-Ld24/1x16x64", 1024, 846.2), ("Td4-T/1x16x64", 256, 2592.6),
+             ("Td4-T/1x16x64", 1024, 10795.5), ("Td4-T/1x32x256", 1024, 10826.9)]
+    for variant, n, gflop in cases:
+        got = bench.flops_per_image(ae_oracle.decode_variant(variant), n) / 1e9
+        assert abs(got - gflop) / gflop < 1e-3, (variant, n, got, gflop)
+    # valid-token accounting of the NaFlex workload: the sizes are seeded and every image fits the token budget
+    sizes = bench.c3_sizes(64, 1234)
+    assert len(sizes) == 64 and all(128 <= h <= 512 and 128 <= w <= 512 and -(-h // 16) * -(-w // 16) <= 1024 for h, w in sizes)
+    assert sizes == bench.c3_sizes(64, 1234) and sizes != bench.c3_sizes(64, 1235)
