@@ -199,8 +199,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   long long row0;
   if (p.cu) {
     // packed NaFlex layout: blockIdx.x = work group (NQ * 128 query rows of one image)
-    const int grp = blockIdx.x;
-    if (grp >= __ldg(p.n_grp)) return;   // beyond the groups of this batch (whole CTA)
+    if ((int)blockIdx.x >= __ldg(p.n_grp)) return;   // beyond the groups of this batch (whole CTA)
+    const int grp = p.grp_order ? p.grp_order[blockIdx.x] : (int)blockIdx.x;   // CTAs are issued in index order: longest images first
     img = p.grp_img[grp];
     row0 = p.cu[img];
     q0 = (grp - p.cuq[img]) * (NQ * ATT_BQ);
