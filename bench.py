@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- encode+decode images/sec of the B200-native ViTok-v2 AE hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|350M-512|c5|c5-350M]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling auto|weak|strong]
+                    [--workload c2|c3|c4|350M-512|350M-2048sw|350M-4096sw|c5|c5-350M]
 
 Contract (see DESIGN.md "Measurement"):
   * one "step" = AE.encode + AE.decode over one batch of synthetic images of the named resolution;
-  * workload at N=1 (default c2) = BASELINE.json configs[1]: 350M-f16x64, bf16, 64 x 256x256 images per GPU
-    (weak scaling: every rank owns its own 64-image batch; no data-path collective);
+  * workload at N=1 (default c2) = BASELINE.json configs[1]: 350M-f16x64, bf16, 64 x 256x256 images;
+  * N > 1 (torchrun, one rank per GPU, no data-path collective): c2 is BASELINE's "batch 64 ... batch-sharded to 2/4/8", i.e.
+    STRONG scaling -- the 64-image batch is dealt 64/N images per rank and the step is replayed from a CUDA graph
+    (vitok_b200.GraphedAE / GraphedCodec) -- and the line also carries the WEAK-scaling figure (64 images on every rank) under
+    "weak"; --scaling weak|strong forces one of them as `value`.  The other workloads keep a fixed per-GPU batch (weak);
   * `value`   : whole-job images/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks;
   * `e2e`     : same metric through the public API with HOST (pinned) buffers: uint8 images in (H2D), preprocess,
                 encode, decode, postprocess, uint8 reconstructions out (D2H), all inside the timed region;
@@ -41,11 +45,16 @@ WORKLOADS = {
     # BASELINE configs[2]: NaFlex mixed-aspect batch (sizes drawn in [128,512]^2, non-multiples of 16 included), masked
     # varlen attention (sdpa backend = the only reference backend that honours patch_mask); resolution 0 = ragged
     "c3": ("Ld4-Ld24/1x16x16", 64, 0, 1024, "sdpa"),
+    # very-high-resolution decode of the reference's project page (docs/index.html:1140,1304): 2048 px = 16 384
+    # tokens, 4096 px = 65 536 tokens per image; --sw W adds the sliding window AE(sw=W) (ae.py:90,99; attention.py:113-116)
+    "350M-2048": ("Ld4-Ld24/1x16x64", 2, 2048, 16384, "flash"),
+    "350M-4096": ("Ld4-Ld24/1x16x64", 1, 4096, 65536, "flash"),
     # training-step configs (BASELINE configs[4]): forward + Charbonnier + backward + AdamW, DDP all-reduce when N > 1
     "c5": ("Td4-T/1x32x256", 8, 1024, 1024, "flash"),
     "c5-350M": ("Ld4-Ld24/1x16x64", 16, 256, 256, "flash"),
 }
 TRAIN_WORKLOADS = ("c5", "c5-350M")
+STRONG_GLOBAL_BATCH = {"c2": 64}     # workloads BASELINE.json words as "batch B ... batch-sharded to 2/4/8": strong scaling when N > 1
 METRIC = "encode+decode images/sec"
 UNIT = "images/s"
 CLS_NAMES = ["linear", "rmsnorm", "qkv_swiglu_gemm", "attention", "proj_residual_gemm", "misc"]
@@ -192,20 +201,56 @@ def _res_name(res):
     return f"{res}px" if res > 0 else "128-512px mixed aspect (NaFlex, max_tokens 1024)"
 
 
+def resolve_scaling(args, world):
+    """('strong' | 'weak', per-GPU batch).  Strong: a fixed global batch dealt to the ranks (BASELINE's "batch-sharded")."""
+    variant, B, res, T, backend = WORKLOADS[args.workload]
+    if args.batch:
+        return ("weak", args.batch) if args.scaling != "strong" else ("strong", max(1, args.batch // world))
+    gb = STRONG_GLOBAL_BATCH.get(args.workload)
+    mode = args.scaling
+    if mode == "auto":
+        mode = "strong" if (gb and world > 1) else "weak"
+    if mode == "strong":
+        gb = gb or B
+        if gb % world:
+            raise SystemExit(f"bench.py: global batch {gb} is not divisible by {world} GPUs")
+        return "strong", gb // world
+    return "weak", B
+
+
+def make_config(args, world, scaling, B):
+    """The `config` object of the JSON line -- identical for our arm and the reference arm (same workload, same batch)."""
+    variant, _, res, T, backend = WORKLOADS[args.workload]
+    return {"workload": f"{args.workload}: {variant} encode+decode @{_res_name(res)}, "
+                        + (f"global batch {B * world} sharded {B}/GPU" if scaling == "strong" else f"batch {B}/GPU"),
+            "variant": variant, "resolution": res, "tokens_per_image": T, "batch_per_gpu": B, "global_batch": B * world,
+            "attn_backend": backend, "sliding_window": args.sw or None, "weights": "random init (seed 0)"}
+
+
 def run_reference(args, rank, world):
+    """The reference's CPU path (the oracle port of vitok/models/ae.py, fp32, all host threads) on this arm's config.  A step
+    is the config's batch when one step fits in ~10 s of CPU work (c2: the whole 64-image batch dealt as in our arm), else a
+    bounded sample of it, stated in cpu_baseline.sample and config.reference_sample."""
     if rank != 0:
         return
-    variant, batch, res, T, backend = WORKLOADS[args.workload]
-    n_img = 4 if res <= 256 else 1
-    rate, cores, sec = cpu_oracle_rate(variant, n_img, res, max(1, args.steps), max(0, min(args.warmup, 1)))
-    sample = (f"{n_img} x {_res_name(res)} images per step, fp32, torch CPU ops on {cores} threads "
-              "(oracle port of vitok/models/ae.py)")
+    variant, _, res, T, backend = WORKLOADS[args.workload]
+    scaling, B = resolve_scaling(args, world)
+    est_gflop_img = {256: 189.0, 512: 846.0}.get(res, 1e9) if variant.startswith("L") else 1e9
+    full = B * est_gflop_img <= 64 * 189.0 * 1.01            # one step <= the c2 batch (~7 s on 16 cores)
+    n_img = B if full else (4 if (0 < res <= 256) else 1)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if not full:            # bounded: the whole run must end within a few minutes; the line prints what was actually run
+        steps, warmup = min(steps, 3 if est_gflop_img > 1e6 else 20), min(warmup, 1)
+    rate, cores, sec = cpu_oracle_rate(variant, n_img, res, steps, warmup)
+    sample = (f"{n_img} x {_res_name(res)} images per step ({'the whole per-rank batch' if full else 'a bounded sample of the batch'}), "
+              f"fp32, torch CPU ops on {cores} threads (oracle port of vitok/models/ae.py), {steps} timed steps after {warmup} warm-up")
+    cfg = make_config(args, world, scaling, B)
+    if not full:
+        cfg["reference_sample"] = f"{n_img} of {B} images per step"
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {variant} encode+decode @{_res_name(res)}, batch {batch}/GPU", "variant": variant,
-                   "resolution": res, "tokens_per_image": T, "batch_per_gpu": batch},
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -216,57 +261,58 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local):
-    import vitok_b200 as vb
-    from vitok_b200 import _lib
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    variant, B, res, T, backend = WORKLOADS[args.workload]
-    if args.batch:
-        B = args.batch
-    cfg = vb.decode_variant(variant)
-    torch.manual_seed(0)
-    model = vb.AE(**cfg, attn_backend=backend).eval().to(device=dev, dtype=torch.bfloat16)
-    if args.quantize:
-        model.quantize()
-    g = torch.Generator().manual_seed(1234 + rank)
-    patch = cfg["spatial_stride"]
-    ragged = res == 0
-    if ragged:
-        sizes = c3_sizes(B, 1234 + rank)
-        img_list = [torch.rand(3, h, w, generator=g) * 2 - 1 for h, w in sizes]
-        pd = vb.patchify_batch([i.to(dev) for i in img_list], patch, T, out_dtype=torch.bfloat16, device=dev)
-        n_valid = [-(-h // patch) * -(-w // patch) for h, w in sizes]
-    else:
-        imgs = torch.rand(B, 3, res, res, generator=g) * 2 - 1
-        pd = vb.patchify_batch(imgs.to(dev), patch, T, out_dtype=torch.bfloat16, device=dev)
-        n_valid = [T] * B
-    N = T
-    lib = _lib.load()
+class Inputs:
+    """Synthetic batch of one rank: float images, the patch dict resident in HBM and the pinned uint8 host copy."""
 
-    def step(d):
+    def __init__(self, vb, cfg, wl, B, rank, dev):
+        variant, _, res, T, backend = wl
+        g = torch.Generator().manual_seed(1234 + rank)
+        self.patch = patch = cfg["spatial_stride"]
+        self.ragged = res == 0
+        self.B, self.T, self.res = B, T, res
+        if self.ragged:
+            self.sizes = c3_sizes(B, 1234 + rank)
+            img_list = [torch.rand(3, h, w, generator=g) * 2 - 1 for h, w in self.sizes]
+            self.pd = vb.patchify_batch([i.to(dev) for i in img_list], patch, T, out_dtype=torch.bfloat16, device=dev)
+            self.n_valid = [-(-h // patch) * -(-w // patch) for h, w in self.sizes]
+            u8_list = [((i.permute(1, 2, 0) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous() for i in img_list]
+            self.host_u8, self.offs, self.szs = vb.pack_images(u8_list, pin=True)
+            self.canvas = 512
+        else:
+            imgs = torch.rand(B, 3, res, res, generator=g) * 2 - 1
+            self.pd = vb.patchify_batch(imgs.to(dev), patch, T, out_dtype=torch.bfloat16, device=dev)
+            self.n_valid = [T] * B
+            self.host_u8 = ((imgs.permute(0, 2, 3, 1) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+            self.canvas = res
+        self.host_out = [torch.empty(B, 3, self.canvas, self.canvas, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+
+def time_resident(vb, model, inp, steps, warmup, world, dev, use_graph, sampler_rank0):
+    """Device-resident timing: encode + decode over the HBM-resident patch dict, CUDA events on the launching stream,
+    barrier + synchronize on both sides, max over ranks.  Returns (ms total, launches per step, clocks)."""
+    def eager():
         with torch.no_grad():
-            return model.decode(model.encode(d))
+            e = model.encode(inp.pd)
+            n = model.last_launch_count
+            o = model.decode(e)
+            return o, n + model.last_launch_count
 
-    # ---- device-resident timing -----------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        out = step(pd)
+    _, per_step = eager()
+    if use_graph:
+        graphed = vb.GraphedAE(model, inp.pd)
+        run = lambda: graphed(inp.pd)       # noqa: E731  (static inputs: no copies, one graph launch)
+    else:
+        run = lambda: eager()[0]            # noqa: E731
+    for _ in range(max(warmup, 3)):
+        run()
     torch.cuda.synchronize()
-    launches_per_step = None
     barrier(world)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(dev.index) if sampler_rank0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    n_launch = 0
-    for _ in range(args.steps):
-        with torch.no_grad():
-            e = model.encode(pd)
-            n_launch += model.last_launch_count
-            out = model.decode(e)
-            n_launch += model.last_launch_count
+    for _ in range(steps):
+        run()
     ev1.record()
     torch.cuda.synchronize()
     barrier(world)
@@ -277,51 +323,43 @@ def run_ours(args, rank, world, local):
         t_end = time.perf_counter() + 3.0
         while sampler.n_samples() < 4 and time.perf_counter() < t_end:
             for _ in range(4):
-                step(pd)
+                run()
             torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    ms = max_over_ranks(ms, world, dev)
-    value = world * B * args.steps / (ms / 1e3)
-    launches_per_step = n_launch // max(args.steps, 1)
+    return max_over_ranks(ms, world, dev), per_step, clocks
 
-    # ---- e2e: host buffers in, host buffers out, through the public API ---------------------------
-    # The serving loop a user of the reference writes (README.md:62-65): decoded uint8 images on the host ->
-    # preprocess (to_tensor|normalize|patchify) -> encode -> decode -> postprocess (unpatchify, 0_255) -> uint8
-    # images on the host.  Per step: H2D of the uint8 HWC batch, D2H of the uint8 CHW reconstructions.
-    canvas = res if not ragged else 512
-    if ragged:   # one packed pinned buffer for the whole NaFlex batch (pack_images), one H2D copy per step
-        u8_list = [((i.permute(1, 2, 0) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous() for i in img_list]
-        host_u8, offs, szs = vb.pack_images(u8_list, pin=True)
-    else:
-        host_u8 = ((imgs.permute(0, 2, 3, 1) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
-    host_out = torch.empty(B, 3, canvas, canvas, dtype=torch.uint8).pin_memory()
-    h2d = host_u8.numel()
-    d2h = host_out.numel()
 
-    # Double-buffered pipeline on three streams (copy-in / compute / copy-out): step i's H2D and step i-1's D2H
-    # overlap step i's kernels, the way a serving loop would drive the public API.  Every step still moves its
-    # own inputs host->device and its own result device->host inside the timed region.
+def time_e2e(vb, model, inp, steps, world, dev, use_graph):
+    """The serving loop a user of the reference writes (README.md:62-65): decoded uint8 images on the host -> preprocess
+    (to_tensor|normalize|patchify) -> encode -> decode -> postprocess (unpatchify, 0_255) -> uint8 images on the host.
+    Per step: H2D of the uint8 HWC batch, D2H of the uint8 CHW reconstructions, both inside the timed region, double-buffered
+    on copy-in / compute / copy-out streams so that step i's copies overlap step i+-1's kernels.  With use_graph the device
+    work of a step is one replay of vitok_b200.GraphedCodec (two instances = the two buffers)."""
+    B, patch, T, canvas = inp.B, inp.patch, inp.T, inp.canvas
+    host_u8 = inp.host_u8
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     s_main = torch.cuda.current_stream(dev)
-    dev_in = [torch.empty_like(host_u8, device=dev) for _ in range(2)]
-    host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
-    for e in ev_free:
-        e.record(s_main)
-
-    keep = [None, None]
     ev_copied = [torch.cuda.Event() for _ in range(2)]
-    for e in ev_copied:
-        e.record(s_main)
     diag = {"h2d": [], "d2h": [], "cpu": []}
+    if use_graph:
+        first = host_u8.to(dev)
+        codecs = [vb.GraphedCodec(model, (first, inp.offs, inp.szs) if inp.ragged else first, patch, T,
+                                  max_grid_size=canvas // patch, output_format="0_255") for _ in range(2)]
+        dev_in = [c.static_in for c in codecs]
+    else:
+        dev_in = [torch.empty_like(host_u8, device=dev) for _ in range(2)]
+    for e in ev_free + ev_copied:
+        e.record(s_main)
+    keep = [None, None]
 
-    def e2e_step(i, timed=False):
+    def step(i, timed=False):
         b = i & 1
         c0 = time.perf_counter()
         with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_free[b])                 # patchify of step i-2 has consumed this input buffer
+            s_in.wait_event(ev_free[b])                 # the patchify of step i-2 has consumed this input buffer
             if timed:
                 h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 h0.record(s_in)
@@ -331,23 +369,29 @@ def run_ours(args, rank, world, local):
                 diag["h2d"].append((h0, h1))
             ev_in[b].record(s_in)
         s_main.wait_event(ev_in[b])
-        if ragged:
-            d = vb.patchify_packed(dev_in[b], offs, szs, patch, T, out_dtype=torch.bfloat16)
+        if use_graph:
+            s_main.wait_event(ev_copied[b])             # the D2H copy of step i-2 has read this codec's output buffer
+            img = codecs[b]()
+            ev_free[b].record(s_main)
         else:
-            d = vb.patchify_batch(dev_in[b], patch, T, out_dtype=torch.bfloat16, device=dev)
-        ev_free[b].record(s_main)
-        o = step(d)
-        img = vb.unpatchify(o, patch, max_grid_size=canvas // patch, output_format="0_255")
+            if inp.ragged:
+                d = vb.patchify_packed(dev_in[b], inp.offs, inp.szs, patch, T, out_dtype=torch.bfloat16)
+            else:
+                d = vb.patchify_batch(dev_in[b], patch, T, out_dtype=torch.bfloat16, device=dev)
+            ev_free[b].record(s_main)
+            with torch.no_grad():
+                o = model.decode(model.encode(d))
+            img = vb.unpatchify(o, patch, max_grid_size=canvas // patch, output_format="0_255")
+            # the D2H copy of step i-2 (it read keep[b]) has finished before that tensor's memory can be reused on s_main
+            s_main.wait_event(ev_copied[b])
+            keep[b] = img
         ev_done[b].record(s_main)
-        # the D2H copy of step i-2 (it read keep[b]) has finished before that tensor's memory can be reused on s_main
-        s_main.wait_event(ev_copied[b])
-        keep[b] = img
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done[b])
             if timed:
                 d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 d0.record(s_out)
-            host_outs[b].copy_(img, non_blocking=True)
+            inp.host_out[b].copy_(img, non_blocking=True)
             if timed:
                 d1.record(s_out)
                 diag["d2h"].append((d0, d1))
@@ -355,107 +399,146 @@ def run_ours(args, rank, world, local):
         if timed:
             diag["cpu"].append((time.perf_counter() - c0) * 1e3)
 
-    def e2e_drain():
+    def drain():
         s_main.wait_stream(s_out)
         s_main.wait_stream(s_in)
 
     for i in range(4):
-        e2e_step(i)
-    e2e_drain()
+        step(i)
+    drain()
     torch.cuda.synchronize()
     barrier(world)
-    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_ev0.record()
-    for i in range(args.steps):
-        e2e_step(i, timed=True)
-    e2e_drain()
-    t_ev1.record()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        step(i, timed=True)
+    drain()
+    t1.record()
     torch.cuda.synchronize()
     barrier(world)
-    e2e_ms = max_over_ranks(t_ev0.elapsed_time(t_ev1), world, dev)
-    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
-    e2e_diag = {"h2d_copy_ms": statistics.mean(a.elapsed_time(b) for a, b in diag["h2d"]),
-                "d2h_copy_ms": statistics.mean(a.elapsed_time(b) for a, b in diag["d2h"]),
-                "cpu_enqueue_ms_per_step": statistics.mean(diag["cpu"])}
+    ms = max_over_ranks(t0.elapsed_time(t1), world, dev)
+    return {"value": world * B * steps / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": host_u8.numel(),
+            "d2h_bytes_per_step": inp.host_out[0].numel(), "ms_per_step": ms / steps,
+            "h2d_copy_ms": statistics.mean(a.elapsed_time(b) for a, b in diag["h2d"]),
+            "d2h_copy_ms": statistics.mean(a.elapsed_time(b) for a, b in diag["d2h"]),
+            "cpu_enqueue_ms_per_step": statistics.mean(diag["cpu"]), "cuda_graph": bool(use_graph),
+            "launches_per_step": codecs[0].launches if use_graph else None}
 
-    # ---- per-kernel-class CUDA-event timing inside a timed pass (roofline of the dominant kernel) ---
-    roof, breakdown = None, None
-    if hasattr(lib, "vtk_ae_set_timing"):
-        import ctypes
-        h = model._handle
-        lib.vtk_ae_set_timing(h, 1)
-        ms_cls = (ctypes.c_float * 6)()
-        cnt_cls = (ctypes.c_int * 6)()
-        tot = [0.0] * 6
-        cnt = [0] * 6
-        prof_steps = min(args.steps, 10)
-        for _ in range(prof_steps):
-            with torch.no_grad():
-                e = model.encode(pd)
-                lib.vtk_ae_collect_timing(h, ms_cls, cnt_cls)
-                for i in range(6):
-                    tot[i] += ms_cls[i]; cnt[i] += cnt_cls[i]
-                model.decode(e)
-                lib.vtk_ae_collect_timing(h, ms_cls, cnt_cls)
-                for i in range(6):
-                    tot[i] += ms_cls[i]; cnt[i] += cnt_cls[i]
-        lib.vtk_ae_set_timing(h, 0)
-        breakdown = {CLS_NAMES[i]: {"ms_per_step": tot[i] / prof_steps, "launches_per_step": cnt[i] // prof_steps} for i in range(6)}
-        # dominant kernel: decoder QKV+SwiGLU GEMM; FLOPs per launch averaged over enc+dec launches
-        M = sum(n_valid)    # algorithmic rows: valid tokens only (padded tokens are not work)
-        fl = 0.0
-        for D, L in ((cfg["encoder_width"], cfg["encoder_depth"]), (cfg["decoder_width"], cfg["decoder_depth"])):
-            hf = ((int(D * cfg["mlp_factor"]) + 8) // 16) * 16
-            fl += L * 2.0 * M * D * (3 * D + 2 * hf)
-        n_l = cfg["encoder_depth"] + cfg["decoder_depth"]
-        avg_ms = tot[2] / max(cnt[2], 1)
-        pk = peaks()
-        ach = (fl / n_l) / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-        traffic = None   # dram bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/)
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload, {}).get("qkv_swiglu_gemm_dram_bytes_per_launch")
-        # --quantize: no FP8 peak was measured on this pool; the dense e4m3 rate of the tensor core is twice the bf16 one, so the
-        # denominator is 2 x the measured sustained bf16 figure (stated in peak_source); traffic is the bf16 capture's and is dropped
-        peak = pk["bf16_sustained"] * (2.0 if args.quantize else 1.0)
-        roof = {"kernel": "gemm2_kernel<EPI_QKV_SWIGLU> (cta_group::2, 256x256 pair tile" + (", e4m3 operands)" if args.quantize else ")"),
-                "bound": "tensor", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None if args.quantize else traffic,
-                "peak_source": pk["src"] + (" sustained bf16 x 2 (dense e4m3 : bf16 rate)" if args.quantize else " sustained bf16"),
-                "avg_launch_ms": avg_ms, "flops_per_launch": fl / n_l}
 
+def kernel_breakdown(lib, model, cfg, inp, steps, args):
+    """Per-kernel-class CUDA-event timing inside a timed (eager) pass + the roofline object of the dominant kernel."""
+    import ctypes
+    h = model._handle
+    lib.vtk_ae_set_timing(h, 1)
+    ms_cls, cnt_cls = (ctypes.c_float * 6)(), (ctypes.c_int * 6)()
+    tot, cnt = [0.0] * 6, [0] * 6
+    prof_steps = min(steps, 10)
+    for _ in range(prof_steps):
+        with torch.no_grad():
+            e = model.encode(inp.pd)
+            lib.vtk_ae_collect_timing(h, ms_cls, cnt_cls)
+            for i in range(6):
+                tot[i] += ms_cls[i]; cnt[i] += cnt_cls[i]
+            model.decode(e)
+            lib.vtk_ae_collect_timing(h, ms_cls, cnt_cls)
+            for i in range(6):
+                tot[i] += ms_cls[i]; cnt[i] += cnt_cls[i]
+    lib.vtk_ae_set_timing(h, 0)
+    breakdown = {CLS_NAMES[i]: {"ms_per_step": tot[i] / prof_steps, "launches_per_step": cnt[i] // prof_steps} for i in range(6)}
+    # dominant kernel: QKV+SwiGLU GEMM; FLOPs per launch averaged over the encoder + decoder launches
+    M = sum(inp.n_valid)    # algorithmic rows: valid tokens only (padded tokens are not work)
+    fl = 0.0
+    for D, L in ((cfg["encoder_width"], cfg["encoder_depth"]), (cfg["decoder_width"], cfg["decoder_depth"])):
+        hf = ((int(D * cfg["mlp_factor"]) + 8) // 16) * 16
+        fl += L * 2.0 * M * D * (3 * D + 2 * hf)
+    n_l = cfg["encoder_depth"] + cfg["decoder_depth"]
+    avg_ms = tot[2] / max(cnt[2], 1)
+    pk = peaks()
+    ach = (fl / n_l) / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+    # dram bytes per launch of this kernel from the newest committed `ncu --set full` capture of this build's kernel at this
+    # workload's full batch (profiles/rNN_traffic.json, written by tools/ncu_summary.py); null for any other shape
+    traffic, tsrc = None, None
+    for name in sorted((f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")), reverse=True):
+        ent = json.load(open(os.path.join(ROOT, "profiles", name))).get(args.workload, {})
+        if ent.get("qkv_swiglu_gemm_dram_bytes_per_launch") and ent.get("batch", WORKLOADS[args.workload][1]) == inp.B:
+            traffic, tsrc = ent["qkv_swiglu_gemm_dram_bytes_per_launch"], name
+            break
+    # --quantize: no FP8 peak was measured on this pool; the dense e4m3 rate of the tensor core is twice the bf16 one, so the
+    # denominator is 2 x the measured sustained bf16 figure (stated in peak_source); traffic is the bf16 capture's and is dropped
+    peak = pk["bf16_sustained"] * (2.0 if args.quantize else 1.0)
+    roof = {"kernel": "gemm2_kernel<EPI_QKV_SWIGLU> (cta_group::2, 256x256 pair tile" + (", e4m3 operands)" if args.quantize else ")"),
+            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": None if args.quantize else traffic, "traffic_source": tsrc,
+            "peak_source": pk["src"] + (" sustained bf16 x 2 (dense e4m3 : bf16 rate)" if args.quantize else " sustained bf16"),
+            "avg_launch_ms": avg_ms, "flops_per_launch": fl / n_l}
+    return roof, breakdown
+
+
+def run_ours(args, rank, world, local):
+    import vitok_b200 as vb
+    from vitok_b200 import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    wl = WORKLOADS[args.workload]
+    variant, B_weak, res, T, backend = wl
+    scaling, B = resolve_scaling(args, world)
+    cfg = vb.decode_variant(variant)
+    torch.manual_seed(0)
+    model = vb.AE(**cfg, attn_backend=backend, sw=(args.sw or None)).eval().to(device=dev, dtype=torch.bfloat16)
+    if args.quantize:
+        model.quantize()
+    lib = _lib.load()
+    # CUDA-graph replay of the step: at small per-GPU batches the ~100 launches of a step take the host longer than the GPU
+    # needs to run them (B = 8: 2 ms of GPU work, 5 ms of launches).  auto = whenever the per-GPU batch is below 32 images.
+    use_graph = args.graph == "on" or (args.graph == "auto" and B * T < 32 * 256)
+    inp = Inputs(vb, cfg, wl, B, rank, dev)
+    ms, launches_per_step, clocks = time_resident(vb, model, inp, args.steps, args.warmup, world, dev, use_graph, rank == 0)
+    value = world * B * args.steps / (ms / 1e3)
+    e2e = time_e2e(vb, model, inp, args.steps, world, dev, use_graph)
+    roof, breakdown = kernel_breakdown(lib, model, cfg, inp, args.steps, args)
+
+    # the other scaling mode of this workload, measured in the same run (c2, N > 1: `value` is the strong-scaling figure -- 64
+    # images dealt to the ranks -- and "weak" is 64 images on every rank; --scaling weak swaps them)
+    other = None
+    if world > 1 and args.workload in STRONG_GLOBAL_BATCH and not args.batch and args.both:
+        o_scaling = "weak" if scaling == "strong" else "strong"
+        oB = B_weak if o_scaling == "weak" else STRONG_GLOBAL_BATCH[args.workload] // world
+        o_graph = args.graph == "on" or (args.graph == "auto" and oB * T < 32 * 256)
+        o_inp = Inputs(vb, cfg, wl, oB, rank, dev)
+        o_ms, _, _ = time_resident(vb, model, o_inp, args.steps, args.warmup, world, dev, o_graph, False)
+        o_e2e = time_e2e(vb, model, o_inp, args.steps, world, dev, o_graph)
+        other = {"scaling": o_scaling, "value": world * oB * args.steps / (o_ms / 1e3), "unit": UNIT, "ms_per_step": o_ms / args.steps,
+                 "batch_per_gpu": oB, "global_batch": oB * world, "cuda_graph": bool(o_graph),
+                 "e2e": {k: o_e2e[k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}}
     if rank != 0:
         return
-    gf = sum(flops_per_image(cfg, n) for n in n_valid) / B / 1e9     # per image, valid tokens only
+    gf = sum(flops_per_image(cfg, n) for n in inp.n_valid) / B / 1e9     # per image, valid tokens only
     pk = peaks()
-    cpu = None
-    if world == 1 or rank == 0:
-        try:
-            n_img = 4 if res <= 256 else 1
-            rate, cores, sec = cpu_oracle_rate(variant, n_img, res, 2, 1)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n_img} x {_res_name(res)} images, fp32, 2 timed iterations after 1 warm-up ({sec:.2f} s each)"}
-        except Exception as ex:  # noqa: BLE001
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    try:
+        n_img = 4 if 0 < res <= 256 else 1
+        c_res = res if res <= 512 else 512                                   # bounded sample: the CPU leg stops at 512 px
+        rate, cores, sec = cpu_oracle_rate(variant, n_img, c_res, 2, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_img} x {_res_name(c_res)} images, fp32, 2 timed iterations after 1 warm-up ({sec:.2f} s each)"}
+    except Exception as ex:  # noqa: BLE001
+        cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    config = make_config(args, world, scaling, B)
+    config.update({"valid_tokens_per_gpu": sum(inp.n_valid), "token_packing": bool(inp.ragged), "cuda_graph": bool(use_graph),
+                   "l2": "no flush: per-step working set (weights + activations) exceeds the 126 MB L2", "gflop_per_image": gf})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "fp8 e4m3 block GEMMs (AE.quantize), bf16 elsewhere" if args.quantize else "bf16",
-        "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {variant} encode+decode @{_res_name(res)}, batch {B}/GPU", "variant": variant,
-                   "resolution": res, "tokens_per_image": N, "valid_tokens_per_gpu": sum(n_valid),
-                   "token_packing": bool(ragged), "batch_per_gpu": B, "global_batch": B * world,
-                   "attn_backend": backend, "weights": "random init (seed 0)",
-                   "l2": "no flush: per-step working set (weights + activations) exceeds the 126 MB L2",
-                   "gflop_per_image": gf},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps, **e2e_diag},
-        "gpu_launches": n_launch,
-        "launches_per_step": launches_per_step,
+        "data": "synthetic", "config": config, "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "model_tflops": value * gf / 1e3 / world,
         "model_frac_of_peak": value * gf / 1e3 / world / pk["bf16_sustained"],
         "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu, "clocks": clocks,
     }
+    if other is not None:
+        line[other["scaling"]] = other
     print(json.dumps(line), flush=True)
 
 
@@ -542,13 +625,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="auto: strong for c2 at N > 1 (BASELINE: batch 64 sharded to 2/4/8), weak otherwise")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the step from a CUDA graph (auto: small per-GPU batches)")
+    ap.add_argument("--no-both", dest="both", action="store_false", help="c2 at N > 1: skip the second (other scaling mode) measurement")
+    ap.add_argument("--sw", type=int, default=0, help="sliding-window radius in tokens, AE(sw=W) (flash backend)")
     ap.add_argument("--quantize", action="store_true",
                     help="AE.quantize(): FP8 (e4m3) block GEMMs -- a separate, reduced-precision line; the headline stays bf16")
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
-        if args.steps > 20:         # bounded: the whole run must end within a few minutes
-            args.steps = 20
         run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
         return
     rank, world, local = dist_setup(args.gpus)

@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define VTK_ABI_VERSION 4
+#define VTK_ABI_VERSION 5
 
 typedef enum {
   VTK_OK = 0,
@@ -36,7 +36,14 @@ typedef enum {
 
 const char* vtk_last_error(void);
 int vtk_abi_version(void);
-int vtk_sm_count(void); /* <0 when no CUDA device is usable */
+int vtk_sm_count(void); /* of the current device; <0 when no CUDA device is usable */
+/* Runtime switches of the kernels (process-wide; no reference counterpart -- they select between implementations of the same
+ * arithmetic).  "pdl": launch every kernel of the path with programmatic dependent launch (prologue overlaps the previous kernel's
+ * tail; default 1, env VTK_PDL).  "gemm_splitk": split-K over the two CTA pairs of a 4-CTA cluster for the out_proj+fc2 residual
+ * GEMM of small batches (<= 37 output tiles; default 1, env VTK_GEMM_SPLITK) -- the two K-halves are summed in fp32, so results
+ * differ from the un-split kernel in the last bit of the accumulator; set 0 where bit-identical results across batch sizes
+ * matter.  Returns VTK_ERR_BAD_ARG for an unknown name. */
+int vtk_set_flag(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * NaFlex pre/post-processing                                   vitok/pp/ops.py, vitok/pp/io.py

@@ -118,6 +118,34 @@ def test_proj_residual(L, M, D, Hf):
     report(f"proj_residual M={M} D={D}", x, ref.float(), max_abs=1.3e-1, rel_fro=4e-3)   # <= 2 bf16 ulp at |x| < 16
 
 
+@pytest.mark.parametrize("M,D,Hf", [(2048, 1024, 2736), (1000, 1024, 2736), (1024, 1024, 2736), (264, 1024, 2736), (768, 3072, 8208)])
+def test_proj_residual_split_k(L, M, D, Hf):
+    """Small batches run the residual GEMM split-K over the two CTA pairs of a 4-CTA cluster (K-halves summed in fp32 through
+    distributed shared memory).  Same answer as the un-split kernel up to the fp32 summation order: equal to the fp32
+    reference within the usual gate, and the two kernels differ from each other by at most one bf16 ulp on a few elements."""
+    a = bf16_randn(M, D + Hf, seed=40)
+    w = bf16_randn(D, D + Hf, seed=41, scale=1 / math.sqrt(D + Hf))
+    gamma = (torch.rand(D, generator=torch.Generator().manual_seed(42)) + 0.5).to(torch.bfloat16).cuda()
+    x0 = bf16_randn(M, D, seed=43)
+    outs = {}
+    try:
+        for flag in (1, 0):
+            L.set_flag("gemm_splitk", flag)
+            x = x0.clone()
+            L.proj_residual(a, w, gamma, x)
+            outs[flag] = x
+    finally:
+        L.set_flag("gemm_splitk", 1)
+    acc = F.linear(a.cpu().float(), w.cpu().float())
+    ref = (x0.cpu() + (acc.to(torch.bfloat16) * gamma.cpu()))
+    report(f"proj_residual split-K M={M} D={D}", outs[1], ref.float(), max_abs=1.3e-1, rel_fro=4e-3)
+    report(f"proj_residual un-split M={M} D={D}", outs[0], ref.float(), max_abs=1.3e-1, rel_fro=4e-3)
+    diff = (outs[1].float() - outs[0].float()).abs()
+    frac = float((diff > 0).float().mean())
+    assert frac < 0.05, frac                                  # only accumulators that sat on a bf16 rounding boundary move
+    assert float(diff.max()) <= 2 * float(outs[0].float().abs().max()) * 2 ** -8
+
+
 def test_bad_args_raise(L):
     a = bf16_randn(128, 100, seed=1)   # K not a multiple of 8
     w = bf16_randn(64, 100, seed=2)

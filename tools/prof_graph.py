@@ -8,10 +8,12 @@ sys.path.insert(0, os.path.join(ROOT, "vitok-release_b200"))
 import torch  # noqa: E402
 import vitok_b200 as vb  # noqa: E402
 
+print(f"VTK_PDL={os.environ.get('VTK_PDL', '1')} VTK_GEMM_CL4={os.environ.get('VTK_GEMM_CL4', 'auto')}")
+
 cfg = vb.decode_variant("Ld4-Ld24/1x16x64")
 torch.manual_seed(0)
 model = vb.AE(**cfg, attn_backend="flash").eval().to("cuda", torch.bfloat16)
-for B in (1, 8, 16, 64):
+for B in (1, 4, 8, 16, 32, 64):
     imgs = (torch.rand(B, 3, 256, 256) * 2 - 1).cuda()
     pd = vb.patchify_batch(imgs, 16, 256, out_dtype=torch.bfloat16)
     graphed = vb.GraphedAE(model, pd)

@@ -27,14 +27,24 @@ int check_cuda(cudaError_t e, const char* what) {
   return VTK_ERR_CUDA;
 }
 
-int num_sms() {
-  static int sms = 0;
-  if (sms > 0) return sms;
+int num_sms() {   // of the CURRENT device (cached per device: one process may drive several GPUs)
+  static int sms[64] = {0};
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev >= 0 && dev < 64 && sms[dev] > 0) return sms[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  sms = n;
-  return sms;
+  if (dev >= 0 && dev < 64) sms[dev] = n;
+  return n;
+}
+
+static int g_flag_pdl = -1, g_flag_splitk = -1;
+bool pdl_enabled() {
+  if (g_flag_pdl < 0) g_flag_pdl = getenv("VTK_PDL") ? atoi(getenv("VTK_PDL")) : 1;
+  return g_flag_pdl != 0;
+}
+int flag_gemm_splitk() {
+  if (g_flag_splitk < 0) g_flag_splitk = getenv("VTK_GEMM_SPLITK") ? atoi(getenv("VTK_GEMM_SPLITK")) : 1;
+  return g_flag_splitk;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -225,6 +235,14 @@ extern "C" {
 const char* vtk_last_error(void) { return g_err; }
 int vtk_abi_version(void) { return VTK_ABI_VERSION; }
 int vtk_sm_count(void) { return num_sms(); }
+
+int vtk_set_flag(const char* name, int value) {
+  VTK_REQUIRE(name, "vtk_set_flag: null name");
+  if (!strcmp(name, "pdl")) { g_flag_pdl = value ? 1 : 0; return VTK_OK; }
+  if (!strcmp(name, "gemm_splitk")) { g_flag_splitk = value ? 1 : 0; return VTK_OK; }
+  set_error("vtk_set_flag: unknown flag '%s' (pdl, gemm_splitk)", name);
+  return VTK_ERR_BAD_ARG;
+}
 
 int vtk_patchify(const void* images, const int64_t* img_table, int in_dtype, int B, int patch, int max_tokens,
                  int out_dtype, void* patches, uint8_t* patch_mask, int64_t* row_idx, int64_t* col_idx,

@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(128 * NQ + 64, NQ == 1 ? 2 : 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
   using S = AttnShape<DH, NQ>;
+  pdl_wait();      // PDL: the work description below is read from global memory (pack plan, kv_len), so wait first
+  pdl_trigger();
   const long long t_cta0 = p.prof ? clock64() : 0;
   const int head = blockIdx.y;
   const int warp = threadIdx.x >> 5;
@@ -619,7 +621,6 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int W = p.window;
-  const int total_items = SNAKE ? min(total_items_host, __ldg(p.n_grp) * p.heads) : total_items_host;   // SNAKE <=> packed layout
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem + S::OFF_Q;
@@ -656,6 +657,10 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: barrier init + TMEM allocation overlapped the previous kernel's tail; global memory only from here on
+  pdl_trigger();
+  pdl_wait();
+  const int total_items = SNAKE ? min(total_items_host, __ldg(p.n_grp) * p.heads) : total_items_host;   // SNAKE <=> packed layout
 
   if (warp == 4) {
     if (lane == 0) {
@@ -981,7 +986,8 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   const long long total = packed ? (long long)a.grp_cap * a.heads : (long long)a.B * a.heads * qtiles;
   if (total >= (1ll << 31)) { set_error("attention: too many work items"); return -2; }
   const int grid = (int)std::min<long long>(total, 2ll * num_sms());
-  kern<<<grid, 192, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
+  const cudaError_t lerr = launch_k(kern, dim3(grid), dim3(192), S::SMEM_BYTES, stream, tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
+  if (lerr != cudaSuccess) return check_cuda(lerr, "attention (persistent) launch");
   if (prof_mode) {
     unsigned long long h[16];
     cudaDeviceSynchronize();
@@ -1037,7 +1043,8 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
   }
   dim3 grid((a.N + NQ * ATT_BQ - 1) / (NQ * ATT_BQ), a.heads, a.B);
   if (packed) grid = dim3((unsigned)a.grp_cap, a.heads, 1);
-  kern<<<grid, S::THREADS, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  const cudaError_t lerr = launch_k(kern, grid, dim3(S::THREADS), S::SMEM_BYTES, stream, tmQ, tmK, tmV, tmO, p);
+  if (lerr != cudaSuccess) return check_cuda(lerr, "attention launch");
   if (prof_mode) {
     unsigned long long h[8];
     cudaDeviceSynchronize();

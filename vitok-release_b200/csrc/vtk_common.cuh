@@ -25,6 +25,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// barrier among `nthreads` threads of the CTA (a multiple of 32; ids 1..15 -- 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the encode / decode chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (vtk_kernels.h: launch_k): its CTAs may become resident and run
+// their prologue (barrier init, TMEM allocation, tensor-map prefetch -- nothing that touches global memory another
+// kernel writes) while the previous kernel of the stream is still draining; pdl_wait() then blocks until that kernel
+// has completed and its memory is visible.  pdl_trigger() lets the NEXT kernel of the stream start the same way.
+// Both are no-ops for a kernel launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier
@@ -161,6 +176,37 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // arrive on a (possibly remote) mbarrier
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire: pairs with mbar_arrive_cluster (release.cluster) from another CTA of the cluster, making that
+// CTA's earlier st.shared::cluster writes into this CTA's shared memory visible
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity))
+    if (clock64() - t0 > VTK_WAIT_LIMIT_CYCLES) __trap();
+}
+// bulk copy shared::cta -> shared::cluster (another CTA's shared memory, address from mapa_u32); completes `bytes` on the
+// mbarrier at bar_cluster_addr (in the destination CTA).  The source must have been made visible to the async proxy
+// (fence_proxy_async_smem) and stay untouched until the copy has completed.
+__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(smem_u32(src_smem)), "r"(bytes), "r"(bar_cluster_addr)
+               : "memory");
+}
+// 16-byte store into the shared memory of another CTA of the cluster (address from mapa_u32)
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 // TMA load whose completion is signalled on an mbarrier that may live in the peer CTA (shared::cluster address)
 __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,

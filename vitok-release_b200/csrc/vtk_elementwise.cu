@@ -13,6 +13,8 @@ namespace vtk {
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, long long ldx,
                                                       const bf16* __restrict__ w, bf16* __restrict__ y, long long ldy,
                                                       int M, int D, float eps, const int* __restrict__ m_dev) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(256) rmsnorm_reg_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ w, bf16* __restrict__ y,
                                                           long long ldy, int M, int D, float eps,
                                                           const int* __restrict__ m_dev) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
@@ -115,10 +119,10 @@ int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long lo
   long long blocks = ((long long)M + wpb - 1) / wpb;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  if (D <= 1024) rmsnorm_reg_kernel<4><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps, m_dev);
-  else if (D <= 3072) rmsnorm_reg_kernel<12><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps, m_dev);
-  else if (D <= 4096) rmsnorm_reg_kernel<16><<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps, m_dev);
-  else rmsnorm_kernel<<<(int)blocks, wpb * 32, 0, stream>>>(x, ldx, w, y, ldy, M, D, eps, m_dev);
+  if (D <= 1024) (void)launch_k(rmsnorm_reg_kernel<4>, dim3((int)blocks), dim3(wpb * 32), 0, stream, x, ldx, w, y, ldy, M, D, eps, m_dev);
+  else if (D <= 3072) (void)launch_k(rmsnorm_reg_kernel<12>, dim3((int)blocks), dim3(wpb * 32), 0, stream, x, ldx, w, y, ldy, M, D, eps, m_dev);
+  else if (D <= 4096) (void)launch_k(rmsnorm_reg_kernel<16>, dim3((int)blocks), dim3(wpb * 32), 0, stream, x, ldx, w, y, ldy, M, D, eps, m_dev);
+  else (void)launch_k(rmsnorm_kernel, dim3((int)blocks), dim3(wpb * 32), 0, stream, x, ldx, w, y, ldy, M, D, eps, m_dev);
   return check_cuda(cudaGetLastError(), "rmsnorm launch");
 }
 
@@ -132,6 +136,8 @@ int launch_rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long lo
 __global__ void rope_table_kernel(const int64_t* __restrict__ row_idx, const int64_t* __restrict__ col_idx,
                                   const float* __restrict__ inv_freq, bf16* __restrict__ table, int M, int d,
                                   const int* __restrict__ src_map, const int* __restrict__ m_dev) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int half = d >> 1, quarter = d >> 2;
   if (m_dev) M = min(M, __ldg(m_dev));
   const long long groups = ((long long)M + 31) >> 5;
@@ -167,11 +173,13 @@ int launch_rope_table(const int64_t* row_idx, const int64_t* col_idx, const floa
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  rope_table_kernel<<<(int)blocks, 256, 0, stream>>>(row_idx, col_idx, inv_freq, table, M, d, src_map, m_dev);
+  (void)launch_k(rope_table_kernel, dim3((int)blocks), dim3(256), 0, stream, row_idx, col_idx, inv_freq, table, M, d, src_map, m_dev);
   return check_cuda(cudaGetLastError(), "rope_table launch");
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const long long nvec = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
@@ -183,6 +191,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
     out[i] = __float2bfloat16_rn(in[i]);
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long n) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __bfloat162float(in[i]);
 }
@@ -194,12 +204,12 @@ static int cast_grid(long long n) {
 int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) { set_error("cast: pointers must be 16-byte aligned"); return -2; }
-  cast_f32_bf16_kernel<<<cast_grid(n), 256, 0, stream>>>(in, out, n);
+  (void)launch_k(cast_f32_bf16_kernel, dim3(cast_grid(n)), dim3(256), 0, stream, in, out, n);
   return check_cuda(cudaGetLastError(), "cast launch");
 }
 int launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
-  cast_bf16_f32_kernel<<<cast_grid(n), 256, 0, stream>>>(in, out, n);
+  (void)launch_k(cast_bf16_f32_kernel, dim3(cast_grid(n)), dim3(256), 0, stream, in, out, n);
   return check_cuda(cudaGetLastError(), "cast launch");
 }
 
@@ -219,6 +229,8 @@ __device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
 __global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const bf16* __restrict__ x, long long ldx, uint8_t* __restrict__ q,
                                                               long long ldq, float* __restrict__ scale, int M, int K,
                                                               const int* __restrict__ m_dev) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int nvec = K >> 3;   // 8 bf16 = 16 bytes in, 8 bytes out
   if (m_dev) M = min(M, __ldg(m_dev));
@@ -254,7 +266,7 @@ int launch_quant_rows_e4m3(const bf16* x, long long ldx, uint8_t* q, long long l
   long long blocks = ((long long)M + 7) / 8;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  quant_rows_e4m3_kernel<<<(int)blocks, 256, 0, stream>>>(x, ldx, q, ldq, scale, M, K, m_dev);
+  (void)launch_k(quant_rows_e4m3_kernel, dim3((int)blocks), dim3(256), 0, stream, x, ldx, q, ldq, scale, M, K, m_dev);
   return check_cuda(cudaGetLastError(), "quant_rows launch");
 }
 
@@ -262,6 +274,8 @@ int launch_quant_rows_e4m3(const bf16* x, long long ldx, uint8_t* q, long long l
 // on [0, kv_len).
 __global__ void kv_len_kernel(const uint8_t* __restrict__ mask, int* __restrict__ kv_len, int* __restrict__ is_prefix,
                               int B, int N) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
@@ -281,7 +295,7 @@ __global__ void kv_len_kernel(const uint8_t* __restrict__ mask, int* __restrict_
 }
 int launch_kv_len(const uint8_t* mask, int* kv_len, int* is_prefix, int B, int N, cudaStream_t stream) {
   if (B <= 0) return 0;
-  kv_len_kernel<<<(B + 3) / 4, 128, 0, stream>>>(mask, kv_len, is_prefix, B, N);
+  (void)launch_k(kv_len_kernel, dim3((B + 3) / 4), dim3(128), 0, stream, mask, kv_len, is_prefix, B, N);
   return check_cuda(cudaGetLastError(), "kv_len launch");
 }
 
@@ -296,6 +310,8 @@ int launch_kv_len(const uint8_t* mask, int* kv_len, int* is_prefix, int B, int N
 // one CTA per image: rel[b, t] = rank of token t among the valid tokens of image b (-1 if masked), n_valid[b]
 __global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t* __restrict__ mask, int* __restrict__ rel,
                                                          int* __restrict__ n_valid, int N) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   __shared__ int warp_tot[8];
   __shared__ int running;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -329,6 +345,8 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t* __restri
 __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__ n_valid, int* __restrict__ cu, int* __restrict__ cuq,
                                                          int* __restrict__ grp_img, int* __restrict__ grp_order, int B, int N, int pad,
                                                          int qrows) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   constexpr int MAX_BINS = 2048;
   __shared__ int warp_tot[2][32];
   __shared__ int running[2];
@@ -395,6 +413,8 @@ __global__ void __launch_bounds__(1024) pack_plan_kernel(const int* __restrict__
 // one CTA per image: src[packed row] = source token row b*N + t, or -1 for the pad rows of the image's last tile
 __global__ void __launch_bounds__(256) pack_src_kernel(const int* __restrict__ rel, const int* __restrict__ n_valid,
                                                        const int* __restrict__ cu, int* __restrict__ src, int N, int pad) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int b = blockIdx.x;
   const int base = cu[b], n = n_valid[b];
   for (int t = threadIdx.x; t < N; t += 256) {
@@ -408,6 +428,8 @@ __global__ void __launch_bounds__(256) pack_src_kernel(const int* __restrict__ r
 __global__ void __launch_bounds__(256) pack_rows_kernel(const bf16* __restrict__ in, long long ld_in, const int* __restrict__ src,
                                                         const int* __restrict__ m_dev, bf16* __restrict__ out, long long ld_out,
                                                         int width) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int nvec = width >> 3;
   const long long total = (long long)__ldg(m_dev) * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -424,6 +446,8 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const bf16* __restrict__
 __global__ void __launch_bounds__(256) unpack_rows_kernel(const bf16* __restrict__ packed, long long ld_p, const int* __restrict__ rel,
                                                           const int* __restrict__ cu, bf16* __restrict__ out, long long ld_out,
                                                           long long rows, int N, int width) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int nvec = width >> 3;
   const long long total = rows * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -438,13 +462,13 @@ __global__ void __launch_bounds__(256) unpack_rows_kernel(const bf16* __restrict
 
 int launch_pack_plan(const uint8_t* mask, int B, int N, const PackPlan& pl, cudaStream_t stream) {
   if (B <= 0 || N <= 0) return 0;
-  pack_count_kernel<<<B, 256, 0, stream>>>(mask, pl.rel, pl.n_valid, N);
+  (void)launch_k(pack_count_kernel, dim3(B), dim3(256), 0, stream, mask, pl.rel, pl.n_valid, N);
   if (pl.pad < 8 || pl.pad % 8 || (pl.qrows != 128 && pl.qrows != 256)) {
     set_error("pack_plan: row padding must be a positive multiple of 8 and the attention group 128 or 256 rows (got %d, %d)", pl.pad, pl.qrows);
     return -2;
   }
-  pack_plan_kernel<<<1, 1024, 0, stream>>>(pl.n_valid, pl.cu, pl.cuq, pl.grp_img, pl.grp_order, B, N, pl.pad, pl.qrows);
-  pack_src_kernel<<<B, 256, 0, stream>>>(pl.rel, pl.n_valid, pl.cu, pl.src, N, pl.pad);
+  (void)launch_k(pack_plan_kernel, dim3(1), dim3(1024), 0, stream, pl.n_valid, pl.cu, pl.cuq, pl.grp_img, pl.grp_order, B, N, pl.pad, pl.qrows);
+  (void)launch_k(pack_src_kernel, dim3(B), dim3(256), 0, stream, pl.rel, pl.n_valid, pl.cu, pl.src, N, pl.pad);
   return check_cuda(cudaGetLastError(), "pack_plan launch");
 }
 
@@ -458,7 +482,7 @@ static int row_copy_grid(long long rows, int width) {
 int launch_pack_rows(const bf16* in, long long ld_in, const PackPlan& pl, long long row_cap, bf16* out, long long ld_out, int width,
                      cudaStream_t stream) {
   if (width % 8 || ld_in % 8 || ld_out % 8) { set_error("pack_rows: width and strides must be multiples of 8"); return -2; }
-  pack_rows_kernel<<<row_copy_grid(row_cap, width), 256, 0, stream>>>(in, ld_in, pl.src, pl.cu + pl.B, out, ld_out, width);
+  (void)launch_k(pack_rows_kernel, dim3(row_copy_grid(row_cap, width)), dim3(256), 0, stream, in, ld_in, pl.src, pl.cu + pl.B, out, ld_out, width);
   return check_cuda(cudaGetLastError(), "pack_rows launch");
 }
 
@@ -466,7 +490,7 @@ int launch_unpack_rows(const bf16* packed, long long ld_p, const PackPlan& pl, b
                        cudaStream_t stream) {
   if (width % 8 || ld_p % 8 || ld_out % 8) { set_error("unpack_rows: width and strides must be multiples of 8"); return -2; }
   const long long rows = (long long)pl.B * pl.N;
-  unpack_rows_kernel<<<row_copy_grid(rows, width), 256, 0, stream>>>(packed, ld_p, pl.rel, pl.cu, out, ld_out, rows, pl.N, width);
+  (void)launch_k(unpack_rows_kernel, dim3(row_copy_grid(rows, width)), dim3(256), 0, stream, packed, ld_p, pl.rel, pl.cu, out, ld_out, rows, pl.N, width);
   return check_cuda(cudaGetLastError(), "unpack_rows launch");
 }
 

@@ -73,6 +73,7 @@ struct OutStage {
 
 struct TileSched {
   int num_m, num_n, gm, full_tiles, total_tiles, bn, bm;
+  int workers;  // persistent workers (CTAs or CTA pairs) the schedule was built for = the launch grid
   int gm_cap;   // band height limit (tile rows) chosen on the host from the A-panel size
   int split;    // 1: a short last wave may be split into half-width tiles
   // Tile counts for M rows on `units` persistent workers (CTAs or CTA pairs).  Shared by the host launcher and by the
@@ -82,13 +83,26 @@ struct TileSched {
     gm = gm_cap < num_m ? gm_cap : num_m;
     if (gm < 1) gm = 1;
     const int big = num_m * num_n;
-    const int workers = big < units ? big : units;
+    workers = big < units ? big : units;
     const int rem = workers > 0 ? big % workers : 0;
     full_tiles = big;
     total_tiles = big;
     if (split && rem > 0 && 2 * rem <= workers) {   // short last wave: half-width tiles
       full_tiles = big - rem;
       total_tiles = full_tiles + 2 * rem;
+    }
+    // Small problems (the per-GPU shards of a strong-scaled batch: M = 2048 rows x N = 1024 is 32 pair tiles for 74 pairs):
+    // when cutting EVERY tile in half shortens the schedule -- cost in full-tile times: waves of full tiles (+ 1/2 for a
+    // split last wave) against half-waves of half tiles -- all tiles are half-width, so twice as many workers are busy.
+    if (split == 1 && workers > 0) {
+      const int cur2 = 2 * ((full_tiles + workers - 1) / workers) + (total_tiles > full_tiles ? 1 : 0);   // in half-tile times
+      const int hw = 2 * big < units ? 2 * big : units;
+      const int half2 = (2 * big + hw - 1) / hw;
+      if (half2 < cur2) {
+        full_tiles = 0;
+        total_tiles = 2 * big;
+        workers = hw;
+      }
     }
   }
   // Big tiles are visited in bands of `gm` row-tiles: inside a band m is fastest and n sweeps all column
@@ -191,8 +205,12 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
 // x = bf16(x + bf16(bf16(acc) * gamma)), in place; 32-column granules leave through the staging block.
 // Packed bf16x2 arithmetic: bf2_mul(bf16(acc), gamma) and bf2_add(x, .) round exactly where the reference's
 // eager bf16 ops do (layerscale.py:23, ae.py:64-65), at 1.5 instructions per element.
+// partial (split-K, gemm2_kernel<..., SK>): the OTHER K-half's fp32 accumulator in shared memory, as [32 rows x 32 columns] blocks of
+// 4 KB (128-byte rows, 16-byte chunks XOR-swizzled by row & 7; block = warp quarter * 8 + column / 32); the pointer addresses this
+// thread's row in column block 0 of its quarter.  Added to the TMEM accumulator first; tcol = column of taddr inside the tile.
 __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t taddr, int row, bool row_ok, int n, int N,
-                                               int ucols, OutStage& st, const CUtensorMap* tmX, uint64_t rs2) {
+                                               int ucols, OutStage& st, const CUtensorMap* tmX, uint64_t rs2,
+                                               const uint8_t* partial = nullptr, int tcol = 0) {
   uint64_t ss2 = 0ull;   // sum of squares of the new x over this 64-column unit (fused norm1 of the next block)
   for (int cc = 0; cc < ucols; cc += 32) {
     const int col = n + cc;
@@ -212,6 +230,17 @@ __device__ __forceinline__ void epi_resid_unit(const EpiParams& p, uint32_t tadd
     uint32_t r[32];
     tmem_ld32(taddr + cc, r);
     tmem_wait_ld();
+    if (partial) {
+      const uint8_t* prow = partial + ((tcol + cc) >> 5) * 4096;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 pv = *reinterpret_cast<const float4*>(prow + ((j ^ (st.lane & 7)) << 4));
+        r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + pv.x);
+        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + pv.y);
+        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + pv.z);
+        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + pv.w);
+      }
+    }
     st.begin();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -505,13 +534,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M_cap, const int N,
             const int K, const TileSched sched_host, const EpiParams epi) {
   using S = GemmShape<BN>;
-  // packed NaFlex batches: the row count lives in device memory (M_cap = capacity the tensor maps were encoded for)
   int M = M_cap;
   TileSched sched = sched_host;
-  if (epi.m_dev) {
-    M = min(__ldg(epi.m_dev), M_cap);
-    sched.setup(M, (int)gridDim.x);
-  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -547,16 +571,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_alloc(tmem_slot, S::TMEM_COLS);
     tmem_relinquish();
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; nothing below may run before it has completed
+  pdl_trigger();
+  pdl_wait();
+  if (epi.m_dev) {   // packed NaFlex batches: the row count lives in device memory (M_cap = capacity the tensor maps were encoded for)
+    M = min(__ldg(epi.m_dev), M_cap);
+    sched.setup(M, (int)gridDim.x);
+  }
   if (EPI == EPI_QKV_SWIGLU && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 2 * epi.d; i += 32 * NEPI) {
       const int kind = i >= epi.d;
       normw_s[kind * 128 + (i - kind * epi.d)] = __bfloat162float((kind ? epi.normk : epi.normq)[i - kind * epi.d]);
     }
+    named_bar_sync(1, 32 * NEPI);   // epilogue warps only
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -688,8 +720,7 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
   sc.split = (allow_split && BN >= 256) ? 1 : 0;
   const int sms = num_sms();
   sc.setup(a.M, sms);   // a.M is the row capacity when a.m_dev is given (the kernel redoes this with the device value)
-  const int big = sc.num_m * sc.num_n;
-  const int grid = big < sms ? big : sms;
+  const int grid = sc.workers;
   // output tensor maps for the TMA-store epilogues (box = 32 cols x 32 rows, SWIZZLE_64B)
   CUtensorMap tmO0 = tmA, tmO1 = tmA;
   constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
@@ -708,8 +739,8 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
       return -1;
     attr_set = true;
   }
-  kern<<<grid, 128 + 32 * NEPI, smem_bytes, stream>>>(tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi);
-  return check_cuda(cudaGetLastError(), "gemm launch");
+  return check_cuda(launch_k(kern, dim3(grid), dim3(128 + 32 * NEPI), smem_bytes, stream, tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi),
+                    "gemm launch");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -743,17 +774,19 @@ template <bool P> __device__ __forceinline__ long long prof_clock() {
 // the same for both pairs, so every CTA loads only half of its B share and TMA-multicasts it to its counterpart in the other pair
 // (rank r <-> r ^ 2): 48 KB instead of 64 KB leave L2 per pair and k-block, which is what bounds the main loop.
 // A stage slot is then written by two producers, so its "empty" barrier collects the MMA commits of both pairs.
-template <int EPI, int NEPI, int G2_STAGES, bool PROF, bool FP8 = false, int TRANS = 0, int CL = 2>
+// SK = true (CL = 4, EPI_RESID): SPLIT-K over the two pairs of the cluster -- both pairs compute the SAME 256 x 256 tile, pair p over
+// k-blocks [p * ceil(num_k / 2), ...).  For the small per-GPU batches of a strong-scaled job (M = 2048 rows: 32 tiles for 74 pairs) the
+// main loop is bound by what ONE SM can pull from L2 (~40 B/clk), so the only way to go faster is to put more SMs on the same bytes:
+// 32 tiles x 2 K-halves keep 128 SMs busy (23.9 -> ~14 us per launch).  Pair 1 then ships its fp32 accumulator through distributed
+// shared memory into the (now idle) stage ring of pair 0, whose epilogue adds it to its own accumulator and finishes the tile.
+// ONE tile per cluster (the host launches exactly as many clusters as tiles): the ring is not reused after the reduction.
+template <int EPI, int NEPI, int G2_STAGES, bool PROF, bool FP8 = false, int TRANS = 0, int CL = 2, bool SK = false>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const int M_cap, const int N,
              const int K, const TileSched sched_host, const EpiParams epi) {
   int M = M_cap;
   TileSched sched = sched_host;
-  if (epi.m_dev) {   // packed NaFlex batches: row count from device memory (see gemm_kernel)
-    M = min(__ldg(epi.m_dev), M_cap);
-    sched.setup(M, (int)(gridDim.x / CL));
-  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -766,7 +799,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = bars + 2 * G2_STAGES;   // [2]       both CTAs (multicast commit)
   uint64_t* tempty = tfull + 2;             // [2]       leader only: 2 * NEPI arrivals (epilogue warps of both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* peer_done = tempty + 4;         // SK, pair 1: pair 0's MMAs have completed (its stage ring may be overwritten)
+  uint64_t* part_full = tempty + 5;         // SK, pair 0: pair 1's accumulator has arrived in this CTA's ring (128 KB of bulk copies)
   float* normw_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  static_assert(!SK || (CL == 4 && EPI == EPI_RESID && TRANS == 0), "split-K: 4-CTA cluster, residual epilogue, K-major operands");
+  static_assert(!SK || G2_STAGES * G2_STAGE_BYTES >= BM * G2_BN * 4, "split-K: the stage ring must hold a 128 x 256 fp32 accumulator");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -774,38 +811,58 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t rank = crank & 1u;           // rank inside the CTA pair
   const uint32_t pair = crank >> 1;           // 0, or 0 / 1 with CL = 4
   const uint32_t lead = crank & ~1u;          // cluster rank of this pair's leader CTA
+  const uint32_t rrank = SK ? rank : crank;   // which 128-row slice of the cluster's tile this CTA owns
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
   constexpr int BKE = FP8 ? 2 * BK : BK;   // elements per k-block: one 128-byte swizzle row of bf16 (64) or e4m3 (128)
   const int num_k = (K + BKE - 1) / BKE;
+  int kb0 = 0, kb1 = num_k;                // this pair's k-blocks
+  if (SK) {
+    const int kh = (num_k + 1) >> 1;
+    kb0 = (int)pair * kh;
+    kb1 = min(num_k, kb0 + kh);
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < G2_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL / 2);   // one MMA commit per pair that writes into this CTA's slot
+      mbar_init(&empty[s], SK ? 1 : CL / 2);   // one MMA commit per pair that writes into this CTA's slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 2 * NEPI);
     }
+    if (SK) {
+      mbar_init(peer_done, 1);
+      mbar_init(part_full, 1);
+    }
     fence_barrier_init();
+    if (SK && pair == 0) mbar_expect_tx(part_full, BM * G2_BN * 4);   // the partner's 128 x 256 fp32 accumulator, by bulk copies
   }
   if (warp == 2) {
     tmem_alloc_2cta(tmem_slot, 512);
     tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // PDL: the prologue above overlapped the previous kernel's tail; global memory is touched only from here on
+  pdl_trigger();
+  pdl_wait();
+  if (epi.m_dev) {   // packed NaFlex batches: row count from device memory (see gemm_kernel)
+    M = min(__ldg(epi.m_dev), M_cap);
+    sched.setup(M, (int)(gridDim.x / CL));
   }
   if (EPI == EPI_QKV_SWIGLU && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 2 * epi.d; i += 32 * NEPI) {
       const int kind = i >= epi.d;
       normw_s[kind * 128 + (i - kind * epi.d)] = __bfloat162float((kind ? epi.normk : epi.normq)[i - kind * epi.d]);
     }
+    named_bar_sync(1, 32 * NEPI);   // epilogue warps only
   }
-  tc_fence_before();
-  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -818,7 +875,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         sched.decode(t, m0, n0, width);
         const int hw = width >> 1;                                      // B rows staged by this CTA
         const uint32_t tx = 2u * (A_STAGE_BYTES + (uint32_t)hw * BK * 2);   // both CTAs' bytes land on the leader's barrier
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           const long long c0 = prof_clock<PROF>();
           mbar_wait(&empty[s], ph ^ 1);
           w_empty += prof_clock<PROF>() - c0;
@@ -826,11 +883,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (rank == 0) mbar_expect_tx(&full[s], tx);
           if (TRANS & 1) {   // boxes of [64 k-rows x 64 columns]: coordinates (column, k)
             for (int mb = 0; mb < BM; mb += 64)
-              tma_load_2d_2cta(sA + s * A_STAGE_BYTES + mb * (BK * 2), &tmA, fb, m0 + (int)crank * BM + mb, kb * BK);
+              tma_load_2d_2cta(sA + s * A_STAGE_BYTES + mb * (BK * 2), &tmA, fb, m0 + (int)rrank * BM + mb, kb * BK);
           } else {
-            tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BKE, m0 + (int)crank * BM);
+            tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BKE, m0 + (int)rrank * BM);
           }
-          if (CL == 4) {   // this CTA fetches half of its B share and multicasts it to its counterpart in the other pair
+          if (CL == 4 && !SK) {   // this CTA fetches half of its B share and multicasts it to its counterpart in the other pair
             const int nb = (int)pair * (hw >> 1);
             tma_load_2d_2cta_mc(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb,
                                 (uint16_t)((1u << rank) | (1u << (rank + 2))));
@@ -863,7 +920,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&tempty[acc], acc_ph ^ 1);
         w_tempty += prof_clock<PROF>() - c0;
         tc_fence_after();
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           c0 = prof_clock<PROF>();
           mbar_wait(&full[s], ph);
           w_full += prof_clock<PROF>() - c0;
@@ -875,16 +932,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (TRANS) umma_bf16_ss_2cta(d_tmem,   // MN-major: 16 k-rows = 2 KB inside a block, 8 KB between column blocks
                                          (TRANS & 1) ? make_smem_desc(a0 + k * 2048, 8192, 1024, 2) : make_desc_kmajor_sw128(a0 + k * 32),
                                          (TRANS & 2) ? make_smem_desc(b0 + k * 2048, 8192, 1024, 2) : make_desc_kmajor_sw128(b0 + k * 32),
-                                         idesc, (kb | k) != 0 ? 1u : 0u);
+                                         idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             else if (FP8) umma_f8_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
-                                     (kb | k) != 0 ? 1u : 0u);
+                                     ((kb - kb0) | k) != 0 ? 1u : 0u);
             else umma_bf16_ss_2cta(d_tmem, make_desc_kmajor_sw128(a0 + k * 32), make_desc_kmajor_sw128(b0 + k * 32), idesc,
-                                   (kb | k) != 0 ? 1u : 0u);
+                                   ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
-          umma_commit_2cta(&empty[s], CL == 4 ? (uint16_t)0xF : (uint16_t)3);   // slot reusable: told to every CTA that writes into it
+          umma_commit_2cta(&empty[s], (CL == 4 && !SK) ? (uint16_t)0xF : (uint16_t)(3u << lead));   // slot reusable: told to every CTA that writes into it
           if (++s == G2_STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit_2cta(&tfull[acc], (uint16_t)(3u << lead));   // accumulator complete -> epilogues of both CTAs of this pair
+        if (SK && pair == 0) umma_commit_2cta(peer_done, (uint16_t)0xC);   // ... and pair 1 may overwrite this pair's stage ring
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
       if (PROF && epi.prof) {
@@ -914,7 +972,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int t = cluster_id; t < sched.total_tiles; t += num_clusters) {
       int m0, n0, width;
       sched.decode(t, m0, n0, width);
-      m0 += (int)crank * BM;
+      m0 += (int)rrank * BM;
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < M && epi.debug != 1;
       st.row0 = m0 + quarter * 32;
@@ -940,11 +998,42 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       w_tfull += c1 - c0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + (uint32_t)(acc * G2_BN);
+      const uint8_t* partial = nullptr;
+      if (SK) {
+        if (pair == 1) {
+          // Ship this K-half's accumulator to the partner CTA (crank - 2: same rows, other K-half).  Every warp stages its
+          // [32 rows x 32 columns] fp32 blocks (4 KB, 128-byte rows, 16-byte chunks XOR-swizzled by row & 7) in THIS CTA's idle
+          // stage ring and sends each with one bulk shared->shared::cluster copy that completes on the partner's part_full.
+          bool peer_ready = false;
+          for (int c0 = half * 64; c0 < width; c0 += NHALF * 64)
+            for (int cc = 0; cc < 64; cc += 32) {
+              uint32_t r[32];
+              tmem_ld32(taddr + c0 + cc, r);
+              tmem_wait_ld();
+              const uint32_t blk = (uint32_t)(quarter * 8 + ((c0 + cc) >> 5)) * 4096u;
+              uint8_t* rowp = sA + blk + (uint32_t)lane * 128u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (!peer_ready) { mbar_wait(peer_done, 0); peer_ready = true; }   // the partner pair's MMAs have read the last of its ring
+                bulk_copy_to_cluster(mapa_u32(smem_u32(sA + blk), crank - 2u), sA + blk, 4096u, mapa_u32(smem_u32(part_full), crank - 2u));
+              }
+            }
+          tc_fence_before();
+          if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+          continue;
+        }
+        mbar_wait(part_full, 0);   // all 128 KB of the partner's accumulator have landed in this CTA's ring
+        partial = sA + (uint32_t)(quarter * 8) * 4096u + (uint32_t)lane * 128u;
+      }
       if (epi.debug != 2) {
         const int U = (EPI == EPI_QKV_SWIGLU && epi.d > 64) ? epi.d : 64;
         for (int c0 = half * U; c0 < width; c0 += NHALF * U) {
           if (EPI == EPI_BIAS) epi_bias_unit(epi, taddr + c0, row, row_ok, n0 + c0, N, U);
-          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0, rs2);
+          if (EPI == EPI_RESID) epi_resid_unit(epi, taddr + c0, row, row < M, n0 + c0, N, U, st, &tmO0, rs2, partial, c0);
           if (EPI == EPI_QKV_SWIGLU) epi_qkv_swiglu_unit(epi, taddr + c0, rrow, n0 + c0, U, normw_s, st, &tmO0, &tmO1, rs2);
         }
       }
@@ -972,6 +1061,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 // 4-CTA-cluster launch (gemm2_kernel<..., CL = 4>): super-tiles of 512 x 256, no half-width tiles; the number of co-resident
 // clusters is what the hardware can place (GPCs whose SM count is not a multiple of 4 leave SMs unused)
+// split-K launch (gemm2_kernel<..., CL = 4, SK = true>): one 256 x 256 tile per 4-CTA cluster, K halved between its two pairs
+template <int NEPI, int G2_STAGES>
+static int launch_gemm2_sk(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, TileSched sc, cudaStream_t stream, bool& taken) {
+  taken = false;
+  sc.bm = 2 * BM;
+  sc.split = 0;
+  const int smem_bytes = g2_smem_bytes(G2_STAGES, NEPI);
+  auto kern = gemm2_kernel<EPI_RESID, NEPI, G2_STAGES, false, false, 0, 4, true>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute(gemm2 split-K)")) return -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(128 + 32 * NEPI); cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 4; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (check_cuda(cudaOccupancyMaxActiveClusters(&n, kern, &cfg), "cudaOccupancyMaxActiveClusters(gemm2 split-K)")) return -1;
+    max_clusters = n > 0 ? n : -1;
+  }
+  sc.setup(a.M, 1 << 20);
+  const int tiles = sc.num_m * sc.num_n;
+  if (max_clusters < 0 || tiles > max_clusters) return 0;   // not every tile gets its own co-resident cluster: caller falls back
+  CUtensorMap tmO0 = tmA, tmO1 = tmA;
+  if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
+  taken = true;
+  return check_cuda(launch_k(kern, dim3(4 * tiles), dim3(128 + 32 * NEPI), smem_bytes, stream, tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi),
+                    "gemm2 (split-K) launch");
+}
+
 template <int EPI, int NEPI, int G2_STAGES>
 static int launch_gemm2_cl4(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, TileSched sc, cudaStream_t stream) {
   sc.bm = 4 * BM;
@@ -1004,9 +1123,11 @@ static int launch_gemm2_cl4(const GemmArgs& a, const CUtensorMap& tmA, const CUt
   } else if (EPI == EPI_RESID) {
     if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
   }
-  kern<<<4 * clusters, 128 + 32 * NEPI, smem_bytes, stream>>>(tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi);
-  return check_cuda(cudaGetLastError(), "gemm2 (4-CTA cluster) launch");
+  return check_cuda(launch_k(kern, dim3(4 * clusters), dim3(128 + 32 * NEPI), smem_bytes, stream, tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc,
+                             a.epi), "gemm2 (4-CTA cluster) launch");
 }
+
+static int env_int(const char* name, int dflt);
 
 template <int EPI, int NEPI, int G2_STAGES>
 static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
@@ -1032,19 +1153,31 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
     if (const char* e = getenv("VTK_GEMM_GM")) gm = atoi(e) > 0 ? atoi(e) : gm;
     sc.gm_cap = (int)(gm < 1 ? 1 : gm > (1 << 20) ? (1 << 20) : gm);
   }
-  sc.split = 1;
+  sc.split = env_int("VTK_GEMM_ALLHALF", 1) ? 1 : 3;   // perf experiments: 0 keeps full-width tiles (split bit 2 = no all-half mode)
   // 4-CTA clusters (two pairs sharing the B tile by TMA multicast): bf16 / fp8 K-major operands, enough M for two 256-row tiles
   // Measured (B200, c2 / c4 in the bench pipeline): out_proj+fc2 residual GEMM 3.19 -> 3.11 ms / 21.5 -> 20.5 ms, but the QKV+fc1 GEMM
   // 6.99 -> 7.18 / 43.9 -> 45.2 ms -- only 33 clusters (132 of 148 SMs) are co-resident, which the epilogue-heavy kernel feels more than
   // it gains from the lighter L2 traffic.  Default: the light epilogues (residual, plain / bias; the 5B training step's forward GEMMs
   // gain 1 %).  VTK_GEMM_CL4 = 0 never, 1 every epilogue kind.
+  // Split-K for the residual GEMM of small batches: at most pairs / 2 tiles (half of the SMs would idle) and a long K
+  if constexpr (EPI == EPI_RESID) {
+    const long long tiles2 = (long long)((a.M + 2 * BM - 1) / (2 * BM)) * sc.num_n;
+    if (flag_gemm_splitk() && !a.fp8 && !a.trans && !a.epi.prof && a.M > BM && 2 * tiles2 <= num_sms() / 2 && a.K >= 16 * BK) {
+      bool taken = false;
+      const int r = launch_gemm2_sk<NEPI, G2_STAGES>(a, tmA, tmB, sc, stream, taken);
+      if (r || taken) return r;
+    }
+  }
   static const int cl4_mode = getenv("VTK_GEMM_CL4") ? atoi(getenv("VTK_GEMM_CL4")) : -1;
-  const bool cl4 = (cl4_mode == 1 || (cl4_mode == -1 && (EPI == EPI_RESID || EPI == EPI_BIAS))) && !a.trans && !a.epi.prof && a.M > 2 * BM;
+  // ... and only when the 512-row super tiles fill the ~33 co-resident clusters at least once: below that (the small per-GPU
+  // batches of a strong-scaled job) the pair kernel with half-width tiles keeps more SMs busy
+  const long long tiles4 = (long long)((a.M + 4 * BM - 1) / (4 * BM)) * sc.num_n;
+  const bool cl4 = (cl4_mode == 1 || (cl4_mode == -1 && (EPI == EPI_RESID || EPI == EPI_BIAS) && tiles4 >= num_sms() / 4 - 4)) && !a.trans &&
+                   !a.epi.prof && a.M > 2 * BM;
   if (cl4) return launch_gemm2_cl4<EPI, NEPI, G2_STAGES>(a, tmA, tmB, sc, stream);
   const int pairs = num_sms() / 2;
   sc.setup(a.M, pairs);
-  const int big = sc.num_m * sc.num_n;
-  const int clusters = big < pairs ? big : pairs;
+  const int clusters = sc.workers;
   CUtensorMap tmO0 = tmA, tmO1 = tmA;
   constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
   if (EPI == EPI_QKV_SWIGLU) {
@@ -1065,8 +1198,8 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
       return -1;
     attr_set[a.trans == 3 ? 4 : a.trans ? 3 : a.fp8 ? 2 : a.epi.prof ? 1 : 0] = true;
   }
-  kern<<<2 * clusters, 128 + 32 * NEPI, smem_bytes, stream>>>(tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi);
-  return check_cuda(cudaGetLastError(), "gemm2 launch");
+  return check_cuda(launch_k(kern, dim3(2 * clusters), dim3(128 + 32 * NEPI), smem_bytes, stream, tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc,
+                             a.epi), "gemm2 launch");
 }
 
 static int env_int(const char* name, int dflt) {

@@ -16,6 +16,23 @@ void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
 
+// Kernel launch with programmatic dependent launch (PDL, vtk_common.cuh: pdl_wait / pdl_trigger): the kernel's prologue
+// overlaps the tail of the previous kernel of the stream.  Works inside CUDA-graph capture (programmatic edges).  Only for
+// kernels that call pdl_wait() before their first access to global memory.  VTK_PDL=0 launches them fully serialised.
+bool pdl_enabled();
+// runtime switches (include/vitok_b200.h: vtk_set_flag)
+int flag_gemm_splitk();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Encode a 2-D bf16 row-major tensor map with 128-byte swizzle: inner box = 64 elements.
 int encode_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t rows,
                            uint64_t row_stride_elems, uint32_t box_rows);

@@ -32,6 +32,8 @@ __device__ __forceinline__ void store4(OutT* dst, float4 v) {
 // writes one chunk per channel; the 256-entry normalisation table lives in shared memory (bit-exact by construction).
 template <typename OutT, int PT>
 __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyArgs a) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   __shared__ float lut[256];
   if (a.in_dtype == 1) {
     lut[threadIdx.x] = norm_u8(threadIdx.x);
@@ -124,9 +126,9 @@ __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyArgs a) {
 
 template <typename OutT>
 static void patchify_dispatch(const PatchifyArgs& a, int blocks, cudaStream_t stream) {
-  if (a.patch == 16) patchify_kernel<OutT, 16><<<blocks, 256, 0, stream>>>(a);
-  else if (a.patch == 32) patchify_kernel<OutT, 32><<<blocks, 256, 0, stream>>>(a);
-  else patchify_kernel<OutT, 0><<<blocks, 256, 0, stream>>>(a);
+  if (a.patch == 16) (void)launch_k(patchify_kernel<OutT, 16>, dim3(blocks), dim3(256), 0, stream, a);
+  else if (a.patch == 32) (void)launch_k(patchify_kernel<OutT, 32>, dim3(blocks), dim3(256), 0, stream, a);
+  else (void)launch_k(patchify_kernel<OutT, 0>, dim3(blocks), dim3(256), 0, stream, a);
 }
 
 int launch_patchify(const PatchifyArgs& a, cudaStream_t stream) {
@@ -146,6 +148,8 @@ int launch_patchify(const PatchifyArgs& a, cudaStream_t stream) {
 // unpatchify
 // ---------------------------------------------------------------------------------------------
 __global__ void cellmap_kernel(const UnpatchifyArgs a) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const long long total = (long long)a.B * a.N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     if (!a.patch_mask[i]) continue;
@@ -182,6 +186,8 @@ __device__ __forceinline__ float convert_px(float x, int fmt, bool bf16_math) {
 // time patch size (16 / 32; 0 = any multiple of 4) so the per-chunk index math is shifts, not divisions.
 template <typename T, int PT>
 __global__ void __launch_bounds__(256) unpatchify_kernel(const UnpatchifyArgs a) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   const int p = PT ? PT : a.patch, pp = p * p, P = 3 * pp, p4 = p >> 2, chunks = pp >> 2;
   const int Hc = a.gy * p, Wc = a.gx * p;
   const int cells_per_img = a.gy * a.gx;
@@ -230,9 +236,9 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const UnpatchifyArgs a)
 
 template <typename T>
 static void unpatchify_dispatch(const UnpatchifyArgs& a, int blocks, cudaStream_t stream) {
-  if (a.patch == 16) unpatchify_kernel<T, 16><<<blocks, 256, 0, stream>>>(a);
-  else if (a.patch == 32) unpatchify_kernel<T, 32><<<blocks, 256, 0, stream>>>(a);
-  else unpatchify_kernel<T, 0><<<blocks, 256, 0, stream>>>(a);
+  if (a.patch == 16) (void)launch_k(unpatchify_kernel<T, 16>, dim3(blocks), dim3(256), 0, stream, a);
+  else if (a.patch == 32) (void)launch_k(unpatchify_kernel<T, 32>, dim3(blocks), dim3(256), 0, stream, a);
+  else (void)launch_k(unpatchify_kernel<T, 0>, dim3(blocks), dim3(256), 0, stream, a);
 }
 
 int launch_unpatchify(const UnpatchifyArgs& a, cudaStream_t stream) {
@@ -245,7 +251,7 @@ int launch_unpatchify(const UnpatchifyArgs& a, cudaStream_t stream) {
   {
     long long blocks = ((long long)a.B * a.N + 255) / 256;
     if (blocks > cap) blocks = cap;
-    cellmap_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+    (void)launch_k(cellmap_kernel, dim3((int)blocks), dim3(256), 0, stream, a);
   }
   if (cells >= (1ll << 31)) { set_error("unpatchify: canvas too large"); return -2; }
   long long blocks = (cells + 7) / 8;                    // one warp per cell, 8 warps per CTA
@@ -259,6 +265,8 @@ int launch_unpatchify(const UnpatchifyArgs& a, cudaStream_t stream) {
 // out2[0] = max(row)+1, out2[1] = max(col)+1 over valid tokens (ops.py:319-321); out2 must be zeroed.
 __global__ void grid_extent_kernel(const uint8_t* __restrict__ mask, const int64_t* __restrict__ row,
                                    const int64_t* __restrict__ col, long long total, int* out2) {
+  pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
+  pdl_trigger();
   int my = 0, mx = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     if (mask[i]) {
@@ -284,7 +292,7 @@ int launch_grid_extent(const uint8_t* mask, const int64_t* row, const int64_t* c
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
-  grid_extent_kernel<<<(int)blocks, 256, 0, stream>>>(mask, row, col, total, out2);
+  (void)launch_k(grid_extent_kernel, dim3((int)blocks), dim3(256), 0, stream, mask, row, col, total, out2);
   return check_cuda(cudaGetLastError(), "grid_extent launch");
 }
 

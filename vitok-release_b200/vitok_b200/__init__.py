@@ -9,7 +9,7 @@ from .models.ae import AE, Model, decode_variant
 from .pp import (OPS, build_transform, pack_images, parse_op, patchify_batch, patchify_packed, postprocess, preprocess,
                  unpack, unpatchify)
 from .data import patch_collate_fn
-from .graphs import GraphedAE
+from .graphs import GraphedAE, GraphedCodec
 from .parallel import shard_by_tokens, shard_range
 from .pretrained import list_pretrained, load_pretrained, save_pretrained
 from .train import FusedAdamW, charbonnier_loss, enable_grad_sync
@@ -17,4 +17,4 @@ from .train import FusedAdamW, charbonnier_loss, enable_grad_sync
 __version__ = "0.1.0"
 __all__ = ["AE", "Model", "decode_variant", "build_transform", "parse_op", "OPS", "patch_collate_fn", "preprocess",
            "postprocess", "unpatchify", "unpack", "patchify_batch", "pack_images", "patchify_packed", "charbonnier_loss", "FusedAdamW", "enable_grad_sync", "load_pretrained", "list_pretrained",
-           "save_pretrained", "shard_range", "shard_by_tokens", "GraphedAE"]
+           "save_pretrained", "shard_range", "shard_by_tokens", "GraphedAE", "GraphedCodec"]

@@ -43,6 +43,7 @@ SIGNATURES = {
     "vtk_last_error": (ctypes.c_char_p, []),
     "vtk_abi_version": (c_int, []),
     "vtk_sm_count": (c_int, []),
+    "vtk_set_flag": (c_int, [ctypes.c_char_p, c_int]),
     "vtk_patchify": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vtk_grid_extent": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "vtk_unpatchify": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
@@ -118,6 +119,11 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+def set_flag(name: str, value: int) -> None:
+    """Process-wide kernel switch (include/vitok_b200.h: vtk_set_flag): "pdl", "gemm_splitk"."""
+    check(load().vtk_set_flag(name.encode(), int(value)))
+
+
 def last_error() -> str:
     return (load().vtk_last_error() or b"").decode("utf-8", "replace")
 
@@ -134,7 +140,41 @@ def check(rc: int) -> None:
 
 
 def stream_ptr() -> int:
+    """Current stream of the CURRENT device: call under ``device_of(tensor)`` so that it is the tensors' device."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def device_of(*tensors) -> "torch.cuda.device":
+    """Context manager that makes the CUDA device of ``tensors`` current for the C calls inside it (kernel launches,
+    tensor-map encoding, ``stream_ptr()`` and the per-device SM count all use the current device).  Raises on tensors
+    that live on different devices or on the host."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("vitok_b200: tensors must live on a CUDA device (there is no CPU path)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"vitok_b200: tensors on different devices ({dev} and {t.device})")
+    if dev is None:
+        raise RuntimeError("vitok_b200: no CUDA tensor given")
+    return torch.cuda.device(dev)
+
+
+def _on_device(fn):
+    """Run ``fn`` with the device of its first tensor argument current (see device_of)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        first = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        if first is None or not first.is_cuda:
+            return fn(*args, **kwargs)      # the wrapper's own checks raise the "no CPU path" error
+        with torch.cuda.device(first.device):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -159,6 +199,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 # thin kernel-level wrappers (used by the parity tests; the model path goes
 # through vtk_ae_encode / vtk_ae_decode)
 # ---------------------------------------------------------------------------
+@_on_device
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
     M, K = a.shape
@@ -169,6 +210,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+@_on_device
 def linear_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
     """out [M, N] = at^T @ bt for at [K, M], bt [K, N] (row-major, any row pitch): transposed-operand GEMM."""
     _req(at, torch.bfloat16, "at"); _req(bt, torch.bfloat16, "bt")
@@ -179,6 +221,7 @@ def linear_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def linear_nn(a: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
     """out [M, N] = a @ bt for a [M, K], bt [K, N] (row-major, any row pitch): B is read MN-major, no transposed copy."""
     _req(a, torch.bfloat16, "a"); _req(bt, torch.bfloat16, "bt")
@@ -189,6 +232,7 @@ def linear_nn(a: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def linear_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(bias, torch.bfloat16, "bias")
     M, K = a.shape
@@ -199,6 +243,7 @@ def linear_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, eps: float =
     return out
 
 
+@_on_device
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     _req(x, torch.bfloat16, "x"); _req(w, torch.bfloat16, "w")
     M, D = x.shape
@@ -207,6 +252,7 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor
     return y
 
 
+@_on_device
 def rope_table(row_idx: torch.Tensor, col_idx: torch.Tensor, inv_freq: torch.Tensor, head_dim: int) -> torch.Tensor:
     _req(row_idx, torch.int64, "row_idx"); _req(col_idx, torch.int64, "col_idx"); _req(inv_freq, torch.float32, "inv_freq")
     M = row_idx.numel()
@@ -225,6 +271,7 @@ def rope_table_decode(table: torch.Tensor, M: int, head_dim: int):
     return t[:, :d], t[:, d:]
 
 
+@_on_device
 def cast_to_bf16(x: torch.Tensor) -> torch.Tensor:
     _req(x, torch.float32, "x")
     x = x.contiguous()
@@ -233,6 +280,7 @@ def cast_to_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def kv_len(mask: torch.Tensor):
     B, N = mask.shape
     m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
@@ -242,6 +290,7 @@ def kv_len(mask: torch.Tensor):
     return kl, pf
 
 
+@_on_device
 def pack_plan(mask: torch.Tensor, pad: int = 16, qrows: int = 128):
     """NaFlex token-packing plan of a [B, N] bool mask (include/vitok_b200.h: vtk_pack_plan).  Arrays the kernel leaves
     unwritten (beyond the packed row / group counts) are pre-filled with -2."""
@@ -257,6 +306,7 @@ def pack_plan(mask: torch.Tensor, pad: int = 16, qrows: int = 128):
     return {"n_valid": n_valid, "rel": rel, "cu": cu, "cuq": cuq, "grp_img": grp_img, "grp_order": grp_order, "src": src}
 
 
+@_on_device
 def pack_rows(x: torch.Tensor, plan: dict) -> torch.Tensor:
     """x [B, N, W] bf16 -> packed [row capacity of the plan, W] (rows beyond cu[B] are left as allocated: zeros here)."""
     _req(x, torch.bfloat16, "x")
@@ -268,6 +318,7 @@ def pack_rows(x: torch.Tensor, plan: dict) -> torch.Tensor:
     return out
 
 
+@_on_device
 def unpack_rows(packed: torch.Tensor, plan: dict, B: int, N: int) -> torch.Tensor:
     _req(packed, torch.bfloat16, "packed")
     W = packed.shape[1]
@@ -276,6 +327,7 @@ def unpack_rows(packed: torch.Tensor, plan: dict, B: int, N: int) -> torch.Tenso
     return out
 
 
+@_on_device
 def quant_rows_e4m3(x: torch.Tensor):
     """Dynamic per-row FP8 quantisation: returns (q [M, K] float8_e4m3fn, scale [M] fp32) with x ~= q * scale[:, None]."""
     _req(x, torch.bfloat16, "x")
@@ -286,6 +338,7 @@ def quant_rows_e4m3(x: torch.Tensor):
     return q.view(torch.float8_e4m3fn), scale
 
 
+@_on_device
 def proj_residual_fp8(a8, a_scale, w8, w_scale: float, gamma, x):
     """x += gamma * (a_scale[:, None] * w_scale * (a8 @ w8^T)) with e4m3 operands (tcgen05 kind::f8f6f4)."""
     M, K = a8.shape
@@ -295,6 +348,7 @@ def proj_residual_fp8(a8, a_scale, w8, w_scale: float, gamma, x):
     return x
 
 
+@_on_device
 def qkv_swiglu(h, w_packed, D, d, Hf, qp, norm_q, norm_k, table, eps=1e-6):
     M = h.shape[0]
     qkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=h.device)
@@ -305,6 +359,7 @@ def qkv_swiglu(h, w_packed, D, d, Hf, qp, norm_q, norm_k, table, eps=1e-6):
     return qkv, act
 
 
+@_on_device
 def proj_residual(a, w, gamma, x):
     M, K = a.shape
     N = w.shape[0]
@@ -313,6 +368,7 @@ def proj_residual(a, w, gamma, x):
     return x
 
 
+@_on_device
 def attention(qkv: torch.Tensor, B: int, N: int, heads: int, d: int, mask: Optional[torch.Tensor] = None,
               window: int = -1, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv [B*N, 3*heads*d] (q | k | v).  mask [B,N] bool -> sdpa semantics; None -> flash semantics.
@@ -329,6 +385,7 @@ def attention(qkv: torch.Tensor, B: int, N: int, heads: int, d: int, mask: Optio
     return out
 
 
+@_on_device
 def umma_probe(a: torch.Tensor, b: torch.Tensor, n: int, k: int, b_mn_major: bool, lbo: int, sbo: int, kstep: int):
     d = torch.zeros(128, n, dtype=torch.float32, device=a.device)
     check(load().vtk_umma_probe(ptr(a), ptr(b), ptr(d), n, k, 1 if b_mn_major else 0, lbo, sbo, kstep, stream_ptr()))

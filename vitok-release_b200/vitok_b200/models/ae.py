@@ -17,7 +17,7 @@ Semantics kept from the reference (file:line in the reference tree):
 ``sw``: sliding-window attention |i-j| <= sw on the token index with the flash backend (attention.py:113-116);
     ignored by the sdpa backend, as in the reference.
 Training: ``model(batch)`` in train mode builds one autograd node (vitok_b200/train.py); encode/decode alone are
-    inference-only.  Not implemented (raises): FP8 ``quantize()``.
+    inference-only.  ``quantize()`` (FP8 block GEMMs) needs widths that are multiples of 256 and raises otherwise.
 """
 from __future__ import annotations
 
@@ -259,6 +259,8 @@ class AE(nn.Module):
         # Block.norm1 fused into the GEMM epilogues (widths that are multiples of 256): no RMSNorm kernel, no h buffer
         # round trip.  False keeps the separate RMSNorm kernel (rounds h to bf16 exactly where the reference does).
         self.fuse_norm = os.environ.get("VTK_NO_FUSE_NORM", "0") != "1"
+        # True: re-pack the weights on every call (for code that writes parameters through ``.data``; see invalidate_packed)
+        self.always_repack = False
 
     # ------------------------------------------------------------------ native plumbing
     def _sides(self):
@@ -297,6 +299,17 @@ class AE(nn.Module):
         except Exception:  # noqa: BLE001  (interpreter shutdown)
             pass
 
+    def invalidate_packed(self) -> "AE":
+        """Drop the packed / folded / FP8 weight copies so that the next encode / decode rebuilds them from the parameters.
+        The copies are re-built automatically when a parameter's storage or ``_version`` changes (``load_state_dict``,
+        ``.to()``, in-place ops, optimizer steps); writes that bypass the version counter -- ``p.data.copy_(ema)``,
+        ``torch._foreach_*`` on ``.data``, custom optimizers -- must call this (or set ``model.always_repack = True``)."""
+        self._packed_sig = None
+        self._plist = None
+        return self
+
+    refresh_weights = invalidate_packed
+
     @torch.no_grad()
     def _ensure_packed(self, device: torch.device, fold_norm: bool = True) -> int:
         """(Re)build the packed bf16 weights the kernels read and hand their pointers to the C handle.
@@ -306,7 +319,7 @@ class AE(nn.Module):
         Rebuilt whenever a parameter's storage or version changes (load_state_dict, .to(), optimizer step).
         """
         sig = (self._signature(), bool(fold_norm and self.fuse_norm), bool(self._quantization_applied and fold_norm))
-        if self._handle is not None and sig == self._packed_sig:
+        if self._handle is not None and sig == self._packed_sig and not self.always_repack:
             return self._handle
         fold = sig[1]
         fp8 = sig[2]
@@ -411,6 +424,14 @@ class AE(nn.Module):
     def _run_native(self, side: int, x: torch.Tensor, row: torch.Tensor, col: torch.Tensor,
                     mask: Optional[torch.Tensor]) -> torch.Tensor:
         """The body of ``vitok_b200::ae_run``: weight packing check, workspace, and the vtk_ae_encode / vtk_ae_decode call."""
+        pdev = next(self.parameters()).device
+        if pdev != x.device:
+            raise RuntimeError(f"vitok_b200.AE: the model is on {pdev} but the input is on {x.device}")
+        with torch.cuda.device(x.device):     # kernels, tensor maps and stream_ptr() follow the CURRENT device
+            return self._run_on_device(side, x, row, col, mask)
+
+    def _run_on_device(self, side: int, x: torch.Tensor, row: torch.Tensor, col: torch.Tensor,
+                       mask: Optional[torch.Tensor]) -> torch.Tensor:
         B, N, _ = x.shape
         out_cols = self.channels_per_token if side == 0 else self.pixels_per_token
         h = self._ensure_packed(x.device)

@@ -151,10 +151,11 @@ def _patchify_packed(packed, offsets, sizes, in_dtype, patch, max_tokens, out_dt
     mask = torch.empty(B, T, dtype=torch.bool, device=dev)
     idx = torch.empty(3, B, T, dtype=torch.int64, device=dev)
     meta = torch.empty(4, B, dtype=torch.int64, device=dev)
-    _lib.check(_lib.load().vtk_patchify(packed.data_ptr(), table.data_ptr(), in_dtype, B, patch, T,
-                                        0 if out_dtype == torch.float32 else 1, patches.data_ptr(), mask.data_ptr(),
-                                        idx[0].data_ptr(), idx[1].data_ptr(), idx[2].data_ptr(), meta.data_ptr(), None,
-                                        _lib.stream_ptr()))
+    with _lib.device_of(packed, patches):       # the launch and stream_ptr() follow the tensors' device, not the current one
+        _lib.check(_lib.load().vtk_patchify(packed.data_ptr(), table.data_ptr(), in_dtype, B, patch, T,
+                                            0 if out_dtype == torch.float32 else 1, patches.data_ptr(), mask.data_ptr(),
+                                            idx[0].data_ptr(), idx[1].data_ptr(), idx[2].data_ptr(), meta.data_ptr(), None,
+                                            _lib.stream_ptr()))
     return {"patches": patches, "patch_mask": mask, "row_idx": idx[0], "col_idx": idx[1], "time_idx": idx[2],
             "orig_height": meta[0], "orig_width": meta[1], "grid_rows": meta[2], "grid_cols": meta[3]}
 
@@ -194,21 +195,22 @@ def unpatchify(patch_dict: dict, patch: int = 16, max_grid_size: Optional[int] =
     row = row.to(device=dev, dtype=torch.int64).contiguous()
     col = col.to(device=dev, dtype=torch.int64).contiguous()
     lib = _lib.load()
-    if max_grid_size is None:
-        ext = torch.empty(2, dtype=torch.int32, device=dev)
-        _lib.check(lib.vtk_grid_extent(m8.data_ptr(), row.data_ptr(), col.data_ptr(), B, N, ext.data_ptr(), _lib.stream_ptr()))
-        gy, gx = (int(v) for v in ext.tolist())  # the reference syncs here too (ops.py:320-321)
-        if gy == 0 or gx == 0:
-            raise RuntimeError("unpatchify: no valid patches (max() of an empty tensor in the reference)")
-    else:
-        gy = gx = int(max_grid_size)
-    fmt = _FMT[output_format]
-    out_dtype = torch.uint8 if fmt == 1 else patches.dtype
-    out = torch.empty(B, 3, gy * patch, gx * patch, dtype=out_dtype, device=dev)
-    cell = torch.empty(B * gy * gx, dtype=torch.int32, device=dev)
-    _lib.check(lib.vtk_unpatchify(patches.data_ptr(), 0 if patches.dtype == torch.float32 else 1, m8.data_ptr(),
-                                  row.data_ptr(), col.data_ptr(), B, N, patch, gy, gx, cell.data_ptr(), out.data_ptr(), fmt,
-                                  None, _lib.stream_ptr()))
+    with _lib.device_of(patches, m8, row, col):
+        if max_grid_size is None:
+            ext = torch.empty(2, dtype=torch.int32, device=dev)
+            _lib.check(lib.vtk_grid_extent(m8.data_ptr(), row.data_ptr(), col.data_ptr(), B, N, ext.data_ptr(), _lib.stream_ptr()))
+            gy, gx = (int(v) for v in ext.tolist())  # the reference syncs here too (ops.py:320-321)
+            if gy == 0 or gx == 0:
+                raise RuntimeError("unpatchify: no valid patches (max() of an empty tensor in the reference)")
+        else:
+            gy = gx = int(max_grid_size)
+        fmt = _FMT[output_format]
+        out_dtype = torch.uint8 if fmt == 1 else patches.dtype
+        out = torch.empty(B, 3, gy * patch, gx * patch, dtype=out_dtype, device=dev)
+        cell = torch.empty(B * gy * gx, dtype=torch.int32, device=dev)
+        _lib.check(lib.vtk_unpatchify(patches.data_ptr(), 0 if patches.dtype == torch.float32 else 1, m8.data_ptr(),
+                                      row.data_ptr(), col.data_ptr(), B, N, patch, gy, gx, cell.data_ptr(), out.data_ptr(), fmt,
+                                      None, _lib.stream_ptr()))
     return out
 
 
