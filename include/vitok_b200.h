@@ -60,6 +60,15 @@ int vtk_set_flag(const char* name, int value);
 int vtk_patchify(const void* images, const int64_t* img_table, int in_dtype, int B, int patch, int max_tokens,
                  int out_dtype, void* patches, uint8_t* patch_mask, int64_t* row_idx, int64_t* col_idx,
                  int64_t* time_idx, int64_t* meta, int* status, void* stream);
+/* The same with a host-side hint: max_h / max_w = the largest image height / width of the batch (0 = unknown).  With the hint the
+ * uint8 front end runs a row-coalesced kernel over the batch's bounding box (thread = 4 pixels of an image row, 384 contiguous bytes
+ * per warp) with the normalisation done arithmetically; results are bit-identical to vtk_patchify. */
+int vtk_patchify_ex(const void* images, const int64_t* img_table, int in_dtype, int B, int patch, int max_tokens, int out_dtype,
+                    void* patches, uint8_t* patch_mask, int64_t* row_idx, int64_t* col_idx, int64_t* time_idx, int64_t* meta, int* status,
+                    int max_h, int max_w, void* stream);
+/* test hook: *mismatches (device int) = number of uint8 values for which the arithmetic to_tensor|normalize of the row kernel differs
+ * from the IEEE-division form (u / 255 - 0.5) / 0.5 of vitok/pp/ops.py:140-161; must be 0 */
+int vtk_patchify_selftest(int* mismatches, void* stream);
 
 /* max(row)+1, max(col)+1 over valid tokens -> out2[2] (device).        vitok/pp/ops.py:319-321 */
 int vtk_grid_extent(const uint8_t* patch_mask, const int64_t* row_idx, const int64_t* col_idx, int B, int N, int* out2,
@@ -127,6 +136,10 @@ int vtk_linear_nn_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, 
  * vtk_proj_residual_fp8: x += gamma * (scale_a[row] * w_scale * (A8 W8^T)) with e4m3 operands on the tcgen05 kind::f8f6f4 path
  * (lda / ldw / K in bytes = elements, multiples of 16). */
 int vtk_quant_rows_e4m3(const void* x, int64_t ldx, void* q, int64_t ldq, float* scale, int M, int K, void* stream);
+/* The same with ONE dynamic scale for the whole tensor (torchao's default PerTensor granularity of
+ * Float8DynamicActivationFloat8WeightConfig, the reference's ae.py:253-270): amax_ws = one device float of workspace; scale[row] is
+ * written for every row (all equal) so the GEMM epilogues are unchanged.  Costs one more read of x. */
+int vtk_quant_tensor_e4m3(const void* x, int64_t ldx, void* q, int64_t ldq, float* scale, float* amax_ws, int M, int K, void* stream);
 int vtk_proj_residual_fp8(const void* A8, int64_t lda, const float* a_scale, const void* W8, int64_t ldw, float w_scale,
                           const void* gamma, void* x, int64_t ldx, int M, int N, int K, void* stream);
 
@@ -159,8 +172,24 @@ int vtk_proj_residual_bf16(const void* A, int64_t lda, const void* W, int64_t ld
 int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out,
                        const int* kv_len, const uint8_t* key_mask, const int* is_prefix, int B, int N, int heads, int d,
                        int zero_invalid_rows, int window, float* lse, void* stream);
+/* The same on the packed NaFlex layout of vtk_pack_plan (the form the layer stack runs masked batches in): image b owns packed rows
+ * [cu[b], cu[b+1]) with its n_valid[b] tokens in front; q / k / v / out have row_cap rows.  qrows of the plan must be 128 (d = 64)
+ * or 256 (d = 128). */
+int vtk_attention_packed_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out, const int* n_valid,
+                              const int* cu, const int* cuq, const int* grp_img, const int* grp_order, int B, int N, int heads, int d,
+                              int64_t row_cap, int grp_cap, void* stream);
 /* lse (optional, may be null): [B*N, heads] fp32, log2-domain logsumexp of the scaled scores (+inf for zeroed rows);
  * the training backward (vtk_attention_bwd_bf16) consumes it. */
+
+/* out [M,N] (+)= A [M,K] @ Bt [K,N] with B read as stored (the data gradient dX = dY W; vtk_linear_nn_bf16); accumulate != 0 adds to
+ * what `out` already holds, in fp32 before the bf16 rounding (dh = dz_qkv Wqkv + dz_fc1 W1 without a separate add pass). */
+int vtk_linear_nn_acc_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo, int M, int N, int K,
+                           int accumulate, void* stream);
+/* out [M,N] = A[:, :K0] W0^T + A[:, K0:K0+K1] W1^T with W0 [N,K0], W1 [N,K1] as stored: out_proj(attn) + fc2(act)
+ * (modules/attention.py:129 + modules/mlp.py:22) over the concatenated activations WITHOUT a packed [out_proj | fc2] copy -- the
+ * training step's weights change every step.  One accumulator when K0 is a multiple of 64 (pair kernel), else two GEMMs. */
+int vtk_linear2_bf16(const void* A, int64_t lda, const void* W0, int64_t ldw0, const void* W1, int64_t ldw1, void* out, int64_t ldo,
+                     int M, int N, int K0, int K1, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training step (BASELINE config 5; scripts/train_vae.py:304-320,371-372 = forward, Charbonnier loss, backward,
@@ -176,6 +205,15 @@ int vtk_qk_norm_rope_fwd(const void* zraw, int64_t ldz, const void* norm_q, cons
 int vtk_swiglu_fwd(const void* zraw, int64_t ldz, int qp, void* act, int64_t ld_act, int M, int Hf, int layout, void* stream);
 /* out = x + gamma * y (vitok/models/ae.py:64-65); contiguous [M,D] */
 int vtk_resid_fwd(const void* x, const void* y, const void* gamma, void* out, int M, int D, void* stream);
+/* The same with stochastic depth (drop_path, vitok/models/ae.py:15-30,65; decoder blocks in train mode): keep [B] fp32 holds the
+ * per-image draw floor(keep_prob + U[0,1)) in {0, 1}, image b = rows [b * rows_per_image, (b+1) * rows_per_image):
+ * out = x + bf16(bf16(gamma * y) / keep_prob) * keep[b].  keep == NULL: identical to vtk_resid_fwd. */
+int vtk_resid_fwd_dp(const void* x, const void* y, const void* gamma, void* out, int M, int D, const float* keep, int rows_per_image,
+                     float keep_prob, void* stream);
+/* backward of vtk_resid_fwd_dp: the LayerScale output's gradient is bf16(dx * keep[b] / keep_prob); dy = that * gamma,
+ * dgamma[D] += colsum(that * y) */
+int vtk_resid_bwd_dp(const void* dx, const void* y, const void* gamma, void* dy, float* dgamma, int M, int D, const float* keep,
+                     int rows_per_image, float keep_prob, void* stream);
 /* out = LayerNorm_noaffine(x) over C <= 256 (modules/norm.py:28-39) */
 int vtk_layernorm_fwd(const void* x, void* out, int M, int C, float eps, void* stream);
 /* dy = dx * gamma; dgamma[D] += colsum(dx * y) */
@@ -201,6 +239,18 @@ int vtk_charbonnier(const void* pred, const void* target, const uint8_t* patch_m
 /* fused AdamW on bf16 param/grad/exp_avg/exp_avg_sq, fp32 math (torch.optim.AdamW semantics; scripts/train_vae.py:200-208) */
 int vtk_adamw_bf16(void* p, const void* g, void* m, void* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, float grad_scale, void* stream);
+/* Multi-tensor AdamW with the reference's optimizer precision (scripts/train_vae.py:200-208: fp32 parameters and fp32 Adam moments under
+ * autocast).  Per tensor: `master` = fp32 parameter values (for an fp32 model parameter: the parameter itself), `p16` = the bf16 model
+ * parameter re-emitted from the master in the same pass (NULL for fp32 parameters), `g` = gradient (bf16, or fp32 when g_is_f32),
+ * `m` / `v` = fp32 exp_avg / exp_avg_sq; torch.optim.AdamW semantics (decoupled weight decay, bias correction with `step` >= 1).
+ * The table is read on the host; all tensor pointers are device pointers. */
+typedef struct {
+  float* master; void* p16; const void* g; float* m; float* v; long long n; float weight_decay; int g_is_f32;
+} vtk_adamw_tensor;
+int vtk_adamw_multi(const vtk_adamw_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps, int step,
+                    float grad_scale, void* stream);
+/* x [n] bf16 *= *scale (fp32 scalar in device memory): the loss gradient arriving at vtk_charbonnier's dpred */
+int vtk_scale_by_dev(void* x, const float* scale, int64_t n, void* stream);
 /* delta [M, heads] fp32 = rowsum over d of dO * O */
 int vtk_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, int M, int heads, int d, void* stream);
 /* attention backward: dq, dk, dv (row stride ld_d) from q,k,v,dO, lse (from vtk_attention_bf16) and delta */
@@ -274,6 +324,9 @@ int vtk_ae_set_fp8_weights(vtk_ae_t h, int side, const vtk_block_fp8* blocks, in
  * scatter the result back; masked tokens of the output are 0.  This replaces the reference's [B,1,N,N] mask
  * (vitok/models/ae.py:173-187) and its work on padded tokens.  enable = 0 keeps the padded [B, N] layout with
  * in-kernel key masking (results on valid tokens are identical for prefix masks). */
+/* FP8 activation scale granularity of the quantised block GEMMs: 0 = per row (default: finer, no extra pass), 1 = per tensor
+ * (torchao-equivalent numerics). */
+int vtk_ae_set_fp8_granularity(vtk_ae_t h, int per_tensor);
 int vtk_ae_set_packing(vtk_ae_t h, int enable);
 /* number of kernels launched by the last vtk_ae_encode/decode on this handle (for gpu_launches accounting) */
 int vtk_ae_last_launch_count(vtk_ae_t h);

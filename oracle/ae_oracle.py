@@ -153,8 +153,18 @@ def attention_core(q, k, v, key_mask: Optional[torch.Tensor], window: Optional[i
     return o.permute(0, 2, 1, 3).reshape(B, N, h * d).to(q.dtype)
 
 
+def drop_path(x: torch.Tensor, keep: Optional[torch.Tensor], keep_prob: float) -> torch.Tensor:
+    """vitok/models/ae.py:15-30 with the random draw made explicit: keep [B] in {0, 1} is floor(keep_prob + U[0,1)) per
+    sample (the reference draws it with torch.rand); x / keep_prob * keep.  keep None = eval mode / rate 0: identity."""
+    if keep is None:
+        return x
+    shape = (x.shape[0],) + (1,) * (x.ndim - 1)
+    return x.div(keep_prob) * keep.to(x.dtype).reshape(shape)
+
+
 def block_forward(sd: Dict[str, torch.Tensor], prefix: str, x, cos, sin, heads: int,
-                  key_mask: Optional[torch.Tensor], window: Optional[int] = None) -> torch.Tensor:
+                  key_mask: Optional[torch.Tensor], window: Optional[int] = None,
+                  keep: Optional[torch.Tensor] = None, keep_prob: float = 1.0) -> torch.Tensor:
     """vitok/models/ae.py:55-65 (Block.forward), attention.py:92-129, mlp.py:20-23."""
     B, N, D = x.shape
     d = D // heads
@@ -173,7 +183,7 @@ def block_forward(sd: Dict[str, torch.Tensor], prefix: str, x, cos, sin, heads: 
     g = sd.get(prefix + "layer_scale.gamma")
     if g is not None:
         comb = comb * g
-    return x + comb
+    return x + drop_path(comb, keep, keep_prob)
 
 
 def _depth(sd, side: str) -> int:
@@ -203,16 +213,21 @@ def encode(sd: Dict[str, torch.Tensor], patch_dict: Dict[str, torch.Tensor], hea
 
 
 def decode(sd: Dict[str, torch.Tensor], enc: Dict[str, torch.Tensor], heads: int,
-           attn_backend: str = "sdpa", theta: float = 10000.0, sw: Optional[int] = None) -> Dict[str, torch.Tensor]:
-    """vitok/models/ae.py:218-243."""
+           attn_backend: str = "sdpa", theta: float = 10000.0, sw: Optional[int] = None,
+           drop_keep: Optional[Dict[int, torch.Tensor]] = None, drop_path_rate: float = 0.0) -> Dict[str, torch.Tensor]:
+    """vitok/models/ae.py:218-243.  Training-mode stochastic depth (ae.py:143-152: decoder block i has rate
+    drop_path_rate * i / (depth - 1)): drop_keep[i] = that block's per-sample 0/1 draw."""
     window = sw if (attn_backend == "flash" and sw is not None and sw > 0) else None
     x = F.linear(enc["z"], sd["decoder_embed.weight"], sd["decoder_embed.bias"])
     D = x.shape[-1]
     cos, sin = rope_cos_sin(enc["row_idx"], enc["col_idx"], D // heads, theta)
     pm = enc.get("patch_mask")
     key_mask = pm.bool() if (attn_backend == "sdpa" and pm is not None) else None
-    for i in range(_depth(sd, "decoder")):
-        x = block_forward(sd, f"decoder_blocks.{i}.", x, cos, sin, heads, key_mask, window)
+    depth = _depth(sd, "decoder")
+    for i in range(depth):
+        rate = drop_path_rate * i / max(depth - 1, 1)
+        keep = drop_keep.get(i) if (drop_keep is not None and rate > 0.0) else None
+        x = block_forward(sd, f"decoder_blocks.{i}.", x, cos, sin, heads, key_mask, window, keep, 1.0 - rate)
     return {
         "patch_mask": enc.get("patch_mask"), "row_idx": enc.get("row_idx"),
         "col_idx": enc.get("col_idx"), "orig_height": enc.get("orig_height"),
@@ -238,13 +253,36 @@ def charbonnier_loss(pred: torch.Tensor, target: torch.Tensor, patch_mask: Optio
     return (per_token.sum(dim=1) / actual).mean()
 
 
+def ssim(a: torch.Tensor, b: torch.Tensor, data_range: float = 1.0, win: int = 11, sigma: float = 1.5) -> float:
+    """Structural similarity of two image batches [B, C, H, W] as torchmetrics' StructuralSimilarityIndexMeasure computes it
+    (the reference's reduced-precision gate, tests/gpu/test_float8_inference.py:348-354, vitok/metrics.py): 11 x 11 gaussian
+    window (sigma 1.5), K1 = 0.01, K2 = 0.03, per-channel, reflect-padded by half a window and cropped again, mean over
+    everything.  Test infrastructure only."""
+    a, b = a.double(), b.double()
+    C = a.shape[1]
+    ax = torch.arange(win, dtype=torch.float64) - (win - 1) / 2
+    g1 = torch.exp(-(ax / sigma) ** 2 / 2)
+    g1 = g1 / g1.sum()
+    kernel = (g1[:, None] * g1[None, :]).expand(C, 1, win, win).contiguous()
+    pad = (win - 1) // 2
+    ap, bp = F.pad(a, (pad, pad, pad, pad), mode="reflect"), F.pad(b, (pad, pad, pad, pad), mode="reflect")
+    stack = torch.cat([ap, bp, ap * ap, bp * bp, ap * bp])
+    out = F.conv2d(stack, kernel, groups=C)
+    mu_a, mu_b, e_aa, e_bb, e_ab = out.split(a.shape[0])
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    va, vb, cab = e_aa - mu_a * mu_a, e_bb - mu_b * mu_b, e_ab - mu_a * mu_b
+    s = ((2 * mu_a * mu_b + c1) * (2 * cab + c2)) / ((mu_a * mu_a + mu_b * mu_b + c1) * (va + vb + c2))
+    return float(s[..., pad:-pad, pad:-pad].mean())
+
+
 def train_step_grads(sd: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], enc_heads: int, dec_heads: int,
-                     attn_backend: str = "sdpa", eps: float = 1e-3, sw: Optional[int] = None):
+                     attn_backend: str = "sdpa", eps: float = 1e-3, sw: Optional[int] = None,
+                     drop_keep: Optional[Dict[int, torch.Tensor]] = None, drop_path_rate: float = 0.0):
     """The training step of scripts/train_vae.py:304-320,371 (forward, Charbonnier loss, backward) on the CPU oracle
     with torch autograd.  Returns (loss, {name: grad})."""
     params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
     enc = encode(params, batch, enc_heads, attn_backend=attn_backend, sw=sw)
-    dec = decode(params, enc, dec_heads, attn_backend=attn_backend, sw=sw)
+    dec = decode(params, enc, dec_heads, attn_backend=attn_backend, sw=sw, drop_keep=drop_keep, drop_path_rate=drop_path_rate)
     loss = charbonnier_loss(dec["patches"], batch["patches"], batch.get("patch_mask"), eps)
     loss.backward()
     return loss.detach(), {k: v.grad for k, v in params.items()}

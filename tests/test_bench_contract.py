@@ -73,3 +73,30 @@ def test_flop_model_matches_the_survey_numbers():
     sizes = bench.c3_sizes(64, 1234)
     assert len(sizes) == 64 and all(128 <= h <= 512 and 128 <= w <= 512 and -(-h // 16) * -(-w // 16) <= 1024 for h, w in sizes)
     assert sizes == bench.c3_sizes(64, 1234) and sizes != bench.c3_sizes(64, 1235)
+
+
+def test_scaling_modes_and_shared_config():
+    """c2 is BASELINE's "batch 64 ... batch-sharded to 2/4/8": strong scaling when N > 1 (64 / N images per rank), weak at N = 1 and
+    for every other workload; --scaling forces one; both arms print the same `config` object."""
+    import sys
+    import types
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "vitok-release_b200"))
+    import bench
+
+    def args(**kw):
+        d = dict(workload="c2", batch=0, scaling="auto", sw=0)
+        d.update(kw)
+        return types.SimpleNamespace(**d)
+
+    assert bench.resolve_scaling(args(), 1) == ("weak", 64)
+    assert [bench.resolve_scaling(args(), n) for n in (2, 4, 8)] == [("strong", 32), ("strong", 16), ("strong", 8)]
+    assert bench.resolve_scaling(args(scaling="weak"), 8) == ("weak", 64)
+    assert bench.resolve_scaling(args(scaling="strong"), 1) == ("strong", 64)
+    assert bench.resolve_scaling(args(workload="c4"), 8) == ("weak", 8)
+    assert bench.resolve_scaling(args(workload="c3"), 8) == ("weak", 64)
+    assert bench.resolve_scaling(args(batch=8), 1) == ("weak", 8)
+    with pytest.raises(SystemExit):
+        bench.resolve_scaling(args(), 3)
+    c = bench.make_config(args(), 8, "strong", 8)
+    assert c["global_batch"] == 64 and c["batch_per_gpu"] == 8 and "sharded 8/GPU" in c["workload"] and "model" not in c

@@ -99,3 +99,49 @@ def test_quantized_model_vs_bf16_and_oracle(backend):
     # e4m3 has 3 mantissa bits: one GEMM on quantised operands is ~3.7 % off (test above); 5 blocks under stress init stay below 10 %
     assert rz < 1e-1 and rp < 1.2e-1 and psnr > 30.0
     assert torch.isfinite(d8["patches"]).all()
+
+
+def test_per_tensor_quantiser_matches_torch_cast(L):
+    """vtk_quant_tensor_e4m3 (torchao's default PerTensor granularity): one scale = amax(tensor) / 448 for every row, bytes equal to
+    torch's float8_e4m3fn cast of x * (448 / amax)."""
+    x = bf16_randn(777, 1032, seed=50, scale=3.0)
+    q, scale = L.quant_tensor_e4m3(x)
+    amax = x.float().abs().max()
+    assert torch.equal(scale, torch.full_like(scale, float(amax) / 448.0))
+    ref_q = (x.float() * (448.0 / amax)).to(torch.float8_e4m3fn)
+    assert torch.equal(q.view(torch.uint8), ref_q.view(torch.uint8))
+
+
+@pytest.mark.parametrize("granularity", ["row", "tensor"])
+def test_reference_acceptance_gate_ssim(granularity):
+    """The reference's own gate for its reduced-precision path (tests/gpu/test_float8_inference.py:286-354): reconstructions of the
+    quantised and of the bf16 model, reshaped to images, must have SSIM >= 0.99 (torchmetrics StructuralSimilarityIndexMeasure,
+    data_range = 2.0) and contain no NaN / Inf.  Model: 350M-f16x64 on 4 x 256 x 256 images (BASELINE configs[0]); weights: the
+    reference's default random init (pretrained weights need the Hub) -- and, for information, the stress init of the parity tests,
+    where every block's output is ~1e4 times larger than at init.  SSIM is oracle/ae_oracle.ssim (torchmetrics is not installed)."""
+    import numpy as np
+    import vitok_b200 as vb
+    from oracle import ae_oracle, pp_oracle
+    from oracle.weights import make_state_dict, synth_images
+    variant = "Ld4-Ld24/1x16x64"
+    cfg = vb.decode_variant(variant)
+    b = pp_oracle.collate([pp_oracle.patchify(i, 16, 256) for i in synth_images([(256, 256)] * 4, seed=1234)])
+    batch = {k: torch.from_numpy(np.asarray(v)) for k, v in b.items()}
+    cb = {k: (v.cuda().to(BF) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+    scores = {}
+    for init in ("default", "stress"):
+        sd = make_state_dict(ae_oracle.decode_variant(variant), seed=1 if init == "stress" else 0, stress=init == "stress")
+        model = vb.AE(**cfg, attn_backend="flash").eval()
+        model.load_state_dict(sd, strict=True)
+        model = model.to("cuda", BF)
+        model.fp8_activation_scale = granularity
+        with torch.no_grad():
+            img16 = vb.unpatchify(model.decode(model.encode(cb)), 16, max_grid_size=16).float().cpu()
+            model.quantize()
+            out8 = model.decode(model.encode(cb))
+            img8 = vb.unpatchify(out8, 16, max_grid_size=16).float().cpu()
+        assert torch.isfinite(img8).all()
+        scores[init] = ae_oracle.ssim(img8, img16, data_range=2.0)
+    print(f"[parity] FP8 ({granularity} activation scale) vs bf16 reconstruction SSIM: default init {scores['default']:.5f}, stress init {scores['stress']:.5f}")
+    assert scores["default"] >= 0.99
+    assert scores["stress"] >= 0.90

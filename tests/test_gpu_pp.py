@@ -87,6 +87,50 @@ def test_uint8_batched_tensor_frontend_and_u8_roundtrip():
     assert np.array_equal(back[:, :, :96, :128].permute(0, 2, 3, 1).cpu().numpy(), u8)
 
 
+def test_arithmetic_normalisation_equals_ieee_division_for_all_bytes():
+    """The row-coalesced uint8 front end normalises with three FMAs instead of u / 255 (no table, no division sequence): bit-identical
+    to (u / 255 - 0.5) / 0.5 for all 256 inputs (device-side exhaustive check), and the kernel's output equals numpy's on them."""
+    import vitok_b200 as vb
+    from vitok_b200 import _lib
+    bad = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().vtk_patchify_selftest(bad.data_ptr(), _lib.stream_ptr()))
+    assert int(bad.item()) == 0
+    ramp = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, axis=2)       # one 16 x 16 patch holding every byte value
+    got = vb.patchify_batch([ramp], 16, 1)["patches"].cpu().numpy().reshape(3, 256)
+    want = ((np.arange(256, dtype=np.float32) / np.float32(255.0)) - np.float32(0.5)) / np.float32(0.5)
+    assert np.array_equal(got[0], want) and np.array_equal(got[2], want)
+
+
+@pytest.mark.parametrize("out_format", ["as_is", "0_255", "zero_to_one"])
+def test_unpatchify_row_and_cell_kernels_agree(out_format):
+    """unpatchify has two kernels (row-coalesced writes for p = 16 / 32, cell-per-warp for any other patch size); on a ragged batch with
+    padded tokens and a canvas larger than every image they produce identical bytes (p = 16 / 32 vs the same data pushed through the
+    generic kernel by choosing p = 8 is not comparable, so the A/B is done through an env switch in a subprocess)."""
+    import os, subprocess, sys, tempfile
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import vitok_b200 as vb
+rng = np.random.default_rng(5)
+imgs = [torch.from_numpy(rng.standard_normal((3, h, w)).astype(np.float32)) for h, w in [(128, 128), (96, 64), (50, 120), (16, 16)]]
+for dt in (torch.float32, torch.bfloat16):
+    d = vb.patchify_batch(imgs, 16, 64, out_dtype=dt)
+    out = vb.unpatchify(d, 16, max_grid_size=9, output_format=%r)
+    np.save(sys.argv[1] + str(dt)[-4:] + ".npy", out.float().cpu().numpy())
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    with tempfile.TemporaryDirectory() as td:
+        for mode in ("1", "0"):
+            env = dict(os.environ, VTK_UNPATCHIFY_ROWS=mode)
+            r = subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "vitok-release_b200"), out_format), os.path.join(td, mode)],
+                               env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs[mode] = [np.load(os.path.join(td, mode + sfx + ".npy")) for sfx in ("at32", "at16")]
+    for a, b in zip(outs["1"], outs["0"]):
+        assert np.array_equal(a, b)
+
+
 def test_full_size_roundtrip_and_bf16():
     """BASELINE config sizes: 64 x 256^2 (c2) and 8 x 512^2 (c4): patchify -> unpatchify is the identity."""
     import vitok_b200 as vb

@@ -172,6 +172,32 @@ def test_charbonnier(L, masked):
     report(f"charbonnier dpred masked={masked}", pred.grad, pc.grad, rel_fro=4e-3)
 
 
+def test_resid_drop_path_kernels(L):
+    """vtk_resid_fwd_dp / vtk_resid_bwd_dp vs autograd of the oracle's drop_path (ae.py:15-30,65) with an explicit draw."""
+    B, N, D, keep_prob = 5, 24, 384, 0.7
+    M = B * N
+    x, y = bf16_randn(M, D, seed=151), bf16_randn(M, D, seed=152)
+    gamma = bf16_randn(D, seed=153, scale=0.5)
+    keep = torch.tensor([1.0, 0.0, 1.0, 1.0, 0.0])
+    o = torch.empty_like(x)
+    L.check(L.load().vtk_resid_fwd_dp(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), o.data_ptr(), M, D, keep.cuda().data_ptr(), N, keep_prob,
+                                      L.stream_ptr()))
+    comb = (y.cpu() * gamma.cpu()).reshape(B, N, D)                       # bf16, like the reference's LayerScale output
+    ref = x.cpu().reshape(B, N, D) + ae_oracle.drop_path(comb, keep, keep_prob)
+    assert torch.equal(o.cpu().reshape(B, N, D), ref)                     # same bf16 rounding points as the eager reference
+    # backward: fp32 autograd of the same expression
+    yc, gc = y.float().cpu().requires_grad_(True), gamma.float().cpu().requires_grad_(True)
+    dx = bf16_randn(M, D, seed=154)
+    (ae_oracle.drop_path((yc * gc).reshape(B, N, D), keep, keep_prob) * dx.float().cpu().reshape(B, N, D)).sum().backward()
+    dy = torch.empty_like(x)
+    dg = torch.zeros(D, dtype=torch.float32, device="cuda")
+    L.check(L.load().vtk_resid_bwd_dp(dx.data_ptr(), y.data_ptr(), gamma.data_ptr(), dy.data_ptr(), dg.data_ptr(), M, D,
+                                      keep.cuda().data_ptr(), N, keep_prob, L.stream_ptr()))
+    report("resid_bwd_dp dy", dy, yc.grad, rel_fro=6e-3)
+    report("resid_bwd_dp dgamma", dg, gc.grad, rel_fro=6e-3)
+    assert float(dy.view(B, N, D)[1].abs().max()) == 0.0 and float(dy.view(B, N, D)[4].abs().max()) == 0.0   # dropped images: no gradient
+
+
 def test_adamw_matches_torch(L):
     import vitok_b200 as vb
     torch.manual_seed(0)
@@ -184,7 +210,59 @@ def test_adamw_matches_torch(L):
         g = torch.randn(5000, generator=torch.Generator().manual_seed(s)).to(BF)
         ours.grad, ref.grad = g.cuda(), g.float()
         o1.step(); o2.step()
-    report("adamw 5 steps", ours.data, ref.data, rel_fro=6e-3)   # bf16 storage of p / m / v between steps
+    report("adamw 5 steps (bf16 param)", ours.data, ref.data.to(BF), max_abs=1.6e-2, rel_fro=2e-3)   # = bf16 rounding of the fp32 result
+    report("adamw 5 steps (fp32 master)", o1.state[ours]["master"], ref.data, rel_fro=1e-6)
+    report("adamw exp_avg_sq", o1.state[ours]["exp_avg_sq"], o2.state[ref]["exp_avg_sq"], rel_fro=1e-6)
+
+
+@pytest.mark.parametrize("pdtype", [BF, torch.float32])
+def test_adamw_small_lr_many_steps_vs_torch_fp32(L, pdtype):
+    """The reference recipe (train_vae.py:200-208: lr 1e-4 ... 3e-4, fp32 parameters and moments).  With bf16 parameters and no
+    master copy, an update below half a bf16 ulp is rounded away: weights of magnitude ~1 (all norm weights) would never move
+    at lr 1e-4.  FusedAdamW keeps an fp32 master and fp32 moments: after 300 steps of a constant-sign gradient the bf16
+    parameters have moved exactly as torch's fp32 AdamW moves them (also with beta2 = 0.999)."""
+    import vitok_b200 as vb
+    n = 4096 + 3                                                     # odd length: the scalar tail of the vector kernel
+    p0 = torch.ones(n) + 0.25 * torch.randn(n, generator=torch.Generator().manual_seed(1))
+    ours = torch.nn.Parameter(p0.to(pdtype).cuda())
+    ref = torch.nn.Parameter(p0.to(pdtype).float().clone())           # (for fp32 the casts are no-ops: do not alias p0)
+    o1 = vb.FusedAdamW([ours], lr=1e-4, betas=(0.9, 0.999), weight_decay=0.01)
+    o2 = torch.optim.AdamW([ref], lr=1e-4, betas=(0.9, 0.999), weight_decay=0.01)
+    gsign = torch.where(torch.arange(n) % 2 == 0, 1.0, -1.0)
+    for s in range(300):
+        g = (gsign * (1.0 + 0.1 * torch.randn(n, generator=torch.Generator().manual_seed(100 + s)))).to(BF)
+        ours.grad, ref.grad = g.to(pdtype).cuda(), g.float()
+        o1.step(); o2.step()
+    moved = (ref.data - p0.to(pdtype).float()).abs()
+    assert float(moved.min()) > 2e-2                                   # ~300 * 1e-4: several bf16 ulps at |w| ~ 1 (ulp 7.8e-3)
+    master = o1.state[ours].get("master", ours.data)
+    report(f"adamw 300 steps lr 1e-4 master ({pdtype})", master, ref.data, max_abs=2e-5, rel_fro=1e-5)
+    if pdtype == BF:
+        assert torch.equal(ours.data.cpu(), master.cpu().to(BF))       # the bf16 parameter is the rounded master
+        assert float((ours.data.float().cpu() - p0.to(BF).float()).abs().min()) > 1e-2      # every bf16 weight moved
+
+
+def test_linear2_and_dgrad_accumulate(L):
+    """vtk_linear2_bf16 (out_proj(attn) + fc2(act) over two weight matrices, one accumulator) and the accumulating data-gradient
+    GEMM: vs fp32 matmuls, for the pair-kernel shape (K0 % 64 == 0, large M) and for the two-GEMM fallback shapes."""
+    for M, N, K0, K1 in [(1024, 1024, 1024, 2736), (2048, 3072, 3072, 8208), (300, 256, 256, 688), (96, 128, 128, 336), (512, 384, 72, 200)]:
+        a = bf16_randn(M, K0 + K1 + 8, seed=160)[:, :K0 + K1]
+        w0 = bf16_randn(N, K0, seed=161, scale=1 / math.sqrt(K0 + K1))
+        w1 = bf16_randn(N, K1, seed=162, scale=1 / math.sqrt(K0 + K1))
+        out = torch.empty(M, N, dtype=BF, device="cuda")
+        L.check(L.load().vtk_linear2_bf16(a.data_ptr(), a.stride(0), w0.data_ptr(), K0, w1.data_ptr(), K1, out.data_ptr(), N, M, N, K0, K1,
+                                          L.stream_ptr()))
+        ref = a[:, :K0].float() @ w0.float().t() + a[:, K0:].float() @ w1.float().t()
+        report(f"linear2 M={M} N={N} K={K0}+{K1}", out, ref, rel_fro=5e-3)
+    M, N, K = 1000, 512, 264
+    a, bt = bf16_randn(M, K, seed=163), bf16_randn(K, N, seed=164, scale=1 / math.sqrt(K))
+    base = bf16_randn(M, N, seed=165)
+    out = base.clone()
+    L.check(L.load().vtk_linear_nn_acc_bf16(a.data_ptr(), K, bt.data_ptr(), N, out.data_ptr(), N, M, N, K, 1, L.stream_ptr()))
+    report("linear_nn accumulate", out, base.float() + a.float() @ bt.float(), rel_fro=4e-3)
+    out2 = base.clone()
+    L.check(L.load().vtk_linear_nn_acc_bf16(a.data_ptr(), K, bt.data_ptr(), N, out2.data_ptr(), N, M, N, K, 0, L.stream_ptr()))
+    report("linear_nn overwrite", out2, a.float() @ bt.float(), rel_fro=4e-3)
 
 
 def _attn_inputs(B, N, heads, d, seed):
@@ -293,3 +371,196 @@ def test_training_loop_reduces_loss():
         o = model(cb)["patches"]
     l2 = vb.charbonnier_loss(o, cb["patches"], cb["patch_mask"]).item()
     assert l2 < losses[0]
+
+
+def _train_once(model, cb):
+    import vitok_b200 as vb
+    for p in model.parameters():
+        p.grad = None
+    out = model(cb)
+    loss = vb.charbonnier_loss(out["patches"], cb["patches"], cb["patch_mask"], eps=1e-3)
+    loss.backward()
+    return loss.detach(), out["patches"].detach(), {n: p.grad.clone() for n, p in model.named_parameters()}
+
+
+def test_training_drop_path_vs_oracle(monkeypatch):
+    """AE(drop_path_rate > 0) in train mode (ae.py:15-30,65,143-152): decoder block i drops images with rate * i / (depth - 1).
+    The draws come from torch.rand exactly as in the reference; here torch.rand is patched so that the same draws can be
+    handed to the oracle, and loss + gradients are compared.  Then: seeded runs repeat, other seeds differ, eval ignores it."""
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(SMALL)
+    sd = make_state_dict(cfg, seed=1, stress=True)
+    batch = _batch([(128, 128)] * 6, 16, 64, seed=12)
+    rate = 0.5
+    model = vb.AE(**cfg, attn_backend="flash", drop_path_rate=rate).train()
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda", BF)
+    cb = {k: (v.cuda().to(BF) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+    depth = cfg["decoder_depth"]
+    draws = [torch.rand(6, generator=torch.Generator().manual_seed(200 + i)) for i in range(depth)]
+    calls = []
+    real_rand = torch.rand
+
+    def fake_rand(shape, dtype=None, device=None, **kw):
+        u = draws[1 + len(calls)]                      # block 0 has rate 0 and draws nothing
+        calls.append(tuple(shape))
+        return u.reshape(shape).to(dtype=dtype, device=device)
+
+    monkeypatch.setattr(torch, "rand", fake_rand)
+    loss, _, grads = _train_once(model, cb)
+    monkeypatch.setattr(torch, "rand", real_rand)
+    assert calls == [(6, 1, 1)] * (depth - 1)
+    keep = {i: (1.0 - rate * i / (depth - 1) + draws[i].to(BF)).floor().float() for i in range(1, depth)}
+    assert any(float(k.min()) == 0.0 for k in keep.values()) and any(float(k.max()) == 1.0 for k in keep.values())
+    sd_b = {k: v.to(BF).float() for k, v in sd.items()}
+    bb = dict(batch)
+    bb["patches"] = batch["patches"].to(BF).float()
+    ref_loss, ref_g = ae_oracle.train_step_grads(sd_b, bb, cfg["encoder_heads"], cfg["decoder_heads"], attn_backend="flash",
+                                                 drop_keep=keep, drop_path_rate=rate)
+    assert abs(loss.item() - ref_loss.item()) <= 5e-3 * abs(ref_loss.item())
+    worst = max((_rel(grads[n], ref_g[n]), n) for n in grads)
+    print(f"[parity] drop_path train step: loss {loss.item():.6f} / {ref_loss.item():.6f}, worst gradient rel-Fro {worst[0]:.3e} at {worst[1]}")
+    assert worst[0] <= 8e-2
+    # the real generator: same seed -> same step, another seed -> another set of dropped images; eval mode: no drop_path
+    torch.manual_seed(5)
+    l1, o1, _ = _train_once(model, cb)
+    torch.manual_seed(5)
+    l2, o2, _ = _train_once(model, cb)
+    torch.manual_seed(6)
+    l3, o3, _ = _train_once(model, cb)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+    model.eval()
+    with torch.no_grad():
+        e1 = model(cb)["patches"]
+        e2 = model(cb)["patches"]
+    assert torch.equal(e1, e2)
+
+
+@pytest.mark.parametrize("ck", [1, 2])
+def test_activation_checkpointing_is_bit_identical(ck):
+    """AE(checkpoint=k) (ae.py:159-160,202-205,231-233): blocks with i % k == 0 keep only their input and are re-run inside the
+    backward pass.  Output and every weight gradient are bit-identical to the un-checkpointed step (also with drop_path: the
+    block's draw is kept, not re-drawn), the vector gradients equal up to the order of their fp32 atomic sums, and the forward pass
+    holds less memory."""
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(SMALL)
+    sd = make_state_dict(cfg, seed=1, stress=True)
+    batch = _batch([(128, 128), (96, 64), (128, 112), (64, 128)], 16, 64, seed=11)
+    cb = {k: (v.cuda().to(BF) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+    res = {}
+    for c in (0, ck):
+        m = vb.AE(**cfg, attn_backend="sdpa", checkpoint=c, drop_path_rate=0.3).train()
+        m.load_state_dict(sd, strict=True)
+        m = m.to("cuda", BF)
+        torch.manual_seed(9)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        out = m(cb)
+        held = torch.cuda.memory_allocated() - base
+        loss = vb.charbonnier_loss(out["patches"], cb["patches"], cb["patch_mask"], eps=1e-3)
+        loss.backward()
+        res[c] = (loss.detach(), out["patches"].detach(), {n: p.grad.clone() for n, p in m.named_parameters()}, held)
+    assert torch.equal(res[0][1], res[ck][1])                                   # same forward (and the same stochastic-depth draws)
+    assert abs(float(res[0][0]) - float(res[ck][0])) <= 1e-6 * abs(float(res[0][0]))   # the loss sums per-token terms with fp32 atomics
+    for n in res[0][2]:
+        a, b = res[0][2][n], res[ck][2][n]
+        if a.ndim >= 2:
+            assert torch.equal(a, b), n                                          # GEMM-produced gradients: bit-identical
+        else:                                                                    # norm weights / gamma / biases: fp32 atomic column sums
+            assert _rel(a, b) <= 1e-4, (n, _rel(a, b))
+    print(f"[parity] activations held after forward: checkpoint=0 {res[0][3] / 2**20:.1f} MiB, checkpoint={ck} {res[ck][3] / 2**20:.1f} MiB")
+    assert res[ck][3] < (0.45 if ck == 1 else 0.8) * res[0][3]
+
+
+def test_training_with_non_prefix_mask_vs_oracle():
+    """The reference's autograd handles any patch_mask (ae.py:173-187).  Here a mask with holes is turned into a prefix mask by
+    permuting tokens (positions travel in row_idx / col_idx), the prefix path runs, and the output is permuted back."""
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(SMALL)
+    sd = make_state_dict(cfg, seed=1, stress=True)
+    batch = _batch([(128, 128), (96, 64), (128, 112), (64, 128)], 16, 64, seed=13)
+    g = torch.Generator().manual_seed(3)
+    mask = batch["patch_mask"].clone()
+    mask &= torch.rand(mask.shape, generator=g) > 0.3          # knock holes into every image
+    mask[:, 0] = True
+    batch["patch_mask"] = mask
+    model = vb.AE(**cfg, attn_backend="sdpa").train()
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda", BF)
+    cb = {k: (v.cuda().to(BF) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+    loss, out, grads = _train_once(model, cb)
+    sd_b = {k: v.to(BF).float() for k, v in sd.items()}
+    bb = dict(batch)
+    bb["patches"] = batch["patches"].to(BF).float()
+    ref_loss, ref_g = ae_oracle.train_step_grads(sd_b, bb, cfg["encoder_heads"], cfg["decoder_heads"], attn_backend="sdpa")
+    assert abs(loss.item() - ref_loss.item()) <= 5e-3 * abs(ref_loss.item())
+    worst = max((_rel(grads[n], ref_g[n]), n) for n in grads)
+    print(f"[parity] non-prefix mask train step: worst gradient rel-Fro {worst[0]:.3e} at {worst[1]}")
+    assert worst[0] <= 8e-2
+    # forward values on valid tokens equal the inference path's (which packs valid tokens)
+    model.eval()
+    with torch.no_grad():
+        inf = model(cb)["patches"]
+    report("train-mode vs eval-mode output on valid tokens", out[mask.cuda()], inf[mask.cuda()].float(), max_abs=6e-2, rel_fro=1e-2)
+
+
+def test_double_backward_raises_and_patches_get_a_gradient():
+    import vitok_b200 as vb
+    cfg = vb.decode_variant(SMALL)
+    sd = make_state_dict(cfg, seed=1, stress=True)
+    batch = _batch([(128, 128)] * 2, 16, 64, seed=14)
+    model = vb.AE(**cfg, attn_backend="flash").train()
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda", BF)
+    cb = {k: (v.cuda().to(BF) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+    cb["patches"] = cb["patches"].clone().requires_grad_(True)
+    out = model(cb)["patches"]
+    w = bf16_randn(*out.shape, seed=15)
+    (out * w).sum().backward(retain_graph=True)
+    assert cb["patches"].grad is not None and cb["patches"].grad.shape == cb["patches"].shape
+    # oracle: d sum(out * w) / d patches
+    sd_b = {k: v.to(BF).float() for k, v in sd.items()}
+    pc = batch["patches"].to(BF).float().requires_grad_(True)
+    bb = dict(batch)
+    bb["patches"] = pc
+    enc = ae_oracle.encode(sd_b, bb, cfg["encoder_heads"], attn_backend="flash")
+    dec = ae_oracle.decode(sd_b, enc, cfg["decoder_heads"], attn_backend="flash")
+    (dec["patches"] * w.float().cpu()).sum().backward()
+    report("d out / d patches", cb["patches"].grad, pc.grad, rel_fro=8e-2)
+    with pytest.raises(RuntimeError, match="already run"):
+        (out * w).sum().backward()
+
+
+def test_5b_shape_training_gradients_vs_oracle():
+    """BASELINE configs[4] at its real block shape: 5B-f32x256 widths (D = 3072, 24 heads of 128, Hf = 8208), patch 32
+    (P = 3072), C = 256, N = 1024 tokens -- one encoder + one decoder block, one 1024 x 1024 image.  Loss and every parameter
+    gradient vs fp32 CPU autograd of the oracle (the d = 128 attention backward at 8 x 8 tile pairs, the transposed-operand GEMMs
+    at K = 1024 tokens, the two-weight forward GEMM at K = 3072 + 8208)."""
+    import os
+    import vitok_b200 as vb
+    variant = "w3072_d1_h24-w3072_d1_h24/1x32x256"
+    cfg = vb.decode_variant(variant)
+    sd = make_state_dict(cfg, seed=4, stress=True)
+    batch = _batch([(1024, 1024)], 32, 1024, seed=21)
+    model = vb.AE(**cfg, attn_backend="flash").train()
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda", BF)
+    cb = {k: (v.cuda().to(BF) if v.dtype == torch.float32 else v.cuda()) for k, v in batch.items()}
+    loss, _, grads = _train_once(model, cb)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd_b = {k: v.to(BF).float() for k, v in sd.items()}
+    bb = dict(batch)
+    bb["patches"] = batch["patches"].to(BF).float()
+    ref_loss, ref_g = ae_oracle.train_step_grads(sd_b, bb, cfg["encoder_heads"], cfg["decoder_heads"], attn_backend="flash")
+    print(f"[parity] 5B-shape train step: loss ours {loss.item():.6f} oracle {ref_loss.item():.6f}")
+    assert abs(loss.item() - ref_loss.item()) <= 5e-3 * abs(ref_loss.item())
+    worst = ("", 0.0)
+    for name, g in grads.items():
+        assert torch.isfinite(g).all(), name
+        r = _rel(g, ref_g[name])
+        cos = F.cosine_similarity(g.float().cpu().flatten(), ref_g[name].flatten(), dim=0).item()
+        assert cos >= 0.995, (name, cos, r)
+        worst = max(worst, (name, r), key=lambda t: t[1])
+    print(f"[parity] 5B-shape train step: worst rel-Frobenius gradient error {worst[1]:.3e} at {worst[0]}")
+    assert worst[1] <= 8e-2

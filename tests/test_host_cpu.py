@@ -165,3 +165,15 @@ def test_pretrained_registry_and_local_safetensors_roundtrip(tmp_path):
     dec_only = vb.AE(**cfg, encoder=False)
     dec_only.load_state_dict(pt.load_pretrained("350M-f16x16", component="decoder", local_dir=str(tmp_path))["decoder"], strict=True)
     assert not any(k.startswith("decoder") for k in enc_only.state_dict()) and not any(k.startswith("encoder") for k in dec_only.state_dict())
+
+
+def test_preprocess_without_patchify_behaves_like_the_reference():
+    """vitok/pp/io.py:43-49 runs ANY pipeline through build_transform + patch_collate_fn and then moves dict values to the device;
+    a pipeline that does not end in patchify therefore yields a stacked tensor and fails on `.items()` -- same here (no extra
+    "must end with patchify" rule of our own)."""
+    from PIL import Image
+    import numpy as np
+    import vitok_b200 as vb
+    img = Image.fromarray(np.zeros((32, 32, 3), dtype=np.uint8))
+    with pytest.raises(AttributeError):
+        vb.preprocess([img, img], pp="to_tensor|normalize(minus_one_to_one)", device="cpu")

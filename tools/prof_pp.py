@@ -12,7 +12,8 @@ import vitok_b200 as vb  # noqa: E402
 from vitok_b200 import _lib  # noqa: E402
 
 dev = "cuda"
-B, R, p, T = 64, 256, 16, 256
+B, R, p, T = int(sys.argv[1]) if len(sys.argv) > 1 else 64, 256, 16, 256     # B = 64: the c2 batch; B = 512: long enough to hide launch + ramp
+print(f"--- batch {B} x {R}x{R}")
 g = torch.Generator().manual_seed(0)
 img_f = (torch.rand(B, 3, R, R, generator=g) * 2 - 1).to(dev)
 img_u = (torch.rand(B, R, R, 3, generator=g) * 255).to(torch.uint8).to(dev)

@@ -134,6 +134,7 @@ struct Workspace {
   bf16 *x, *h, *qkv, *a2, *rope;
   uint8_t *x8, *a28;    // FP8 inference: e4m3 copies of x and of [attn | act], and their per-row scales
   float *sx, *sa;
+  float* amax;          // FP8 per-tensor activation scale: two device floats (x, [attn | act])
   float* ss;            // [rows, D / 64] per-unit sums of squares of x (fused norm1)
   int *kv_len, *is_prefix;
   PackPlan plan;        // NaFlex token packing (masked batches): plan arrays + packed input / output staging rows
@@ -162,12 +163,13 @@ static Workspace carve(const Side& s, void* base, int B, int N, int io_cols) {
   w.a2 = static_cast<bf16*>(take((size_t)M * s.kp() * 2));
   w.rope = static_cast<bf16*>(take((size_t)((M + 31) / 32 * 32) * 2 * d * 2));   // pair-expanded table, 32-row groups
   w.ss = static_cast<float*>(take((size_t)M * ((D + 63) / 64) * 4));
-  w.x8 = w.a28 = nullptr; w.sx = w.sa = nullptr;
+  w.x8 = w.a28 = nullptr; w.sx = w.sa = nullptr; w.amax = nullptr;
   if (!s.fp8.empty()) {
     w.x8 = static_cast<uint8_t*>(take((size_t)M * D));
     w.a28 = static_cast<uint8_t*>(take((size_t)M * s.kp()));
     w.sx = static_cast<float*>(take((size_t)M * 4));
     w.sa = static_cast<float*>(take((size_t)M * 4));
+    w.amax = static_cast<float*>(take(1024));
   }
   w.kv_len = static_cast<int*>(take((size_t)B * 4));
   w.is_prefix = static_cast<int*>(take((size_t)B * 4));
@@ -197,6 +199,7 @@ struct vtk_ae_s {
   vtk::Side side[2];
   int last_launches = 0;
   bool packing = true;   // NaFlex token packing for masked batches (vtk_ae_set_packing)
+  bool fp8_per_tensor = false;   // FP8 activations quantised with one dynamic scale per tensor instead of per row (vtk_ae_set_fp8_granularity)
   // timing: one (start, stop) event pair per launch of the last encode/decode call
   bool timing = false;
   std::vector<cudaEvent_t> ev;      // 2 per launch
@@ -257,6 +260,25 @@ int vtk_patchify(const void* images, const int64_t* img_table, int in_dtype, int
   a.out_dtype = out_dtype; a.patches = patches; a.patch_mask = patch_mask; a.row_idx = row_idx; a.col_idx = col_idx;
   a.time_idx = time_idx; a.meta = meta; a.status = status;
   return launch_patchify(a, (cudaStream_t)stream);
+}
+
+int vtk_patchify_ex(const void* images, const int64_t* img_table, int in_dtype, int B, int patch, int max_tokens, int out_dtype,
+                    void* patches, uint8_t* patch_mask, int64_t* row_idx, int64_t* col_idx, int64_t* time_idx, int64_t* meta, int* status,
+                    int max_h, int max_w, void* stream) {
+  VTK_REQUIRE(images && img_table && patches && patch_mask && row_idx && col_idx && time_idx && meta, "vtk_patchify_ex: null pointer");
+  VTK_REQUIRE(in_dtype == 0 || in_dtype == 1, "vtk_patchify_ex: in_dtype must be 0 (f32 CHW) or 1 (u8 HWC)");
+  VTK_REQUIRE(out_dtype == 0 || out_dtype == 1, "vtk_patchify_ex: out_dtype must be 0 (f32) or 1 (bf16)");
+  VTK_REQUIRE(B >= 0 && max_tokens >= 0 && max_h >= 0 && max_w >= 0, "vtk_patchify_ex: negative size");
+  PatchifyArgs a;
+  a.images = images; a.img_table = img_table; a.in_dtype = in_dtype; a.B = B; a.patch = patch; a.max_tokens = max_tokens;
+  a.out_dtype = out_dtype; a.patches = patches; a.patch_mask = patch_mask; a.row_idx = row_idx; a.col_idx = col_idx;
+  a.time_idx = time_idx; a.meta = meta; a.status = status; a.max_h = max_h; a.max_w = max_w;
+  return launch_patchify(a, (cudaStream_t)stream);
+}
+
+int vtk_patchify_selftest(int* mismatches, void* stream) {
+  VTK_REQUIRE(mismatches, "vtk_patchify_selftest: null pointer");
+  return launch_patchify_selftest(mismatches, (cudaStream_t)stream);
 }
 
 int vtk_grid_extent(const uint8_t* patch_mask, const int64_t* row_idx, const int64_t* col_idx, int B, int N, int* out2,
@@ -369,6 +391,37 @@ int vtk_linear_nn_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, 
   return launch_gemm(EPI_BIAS, g, (cudaStream_t)stream);
 }
 
+int vtk_linear_nn_acc_bf16(const void* A, int64_t lda, const void* Bt, int64_t ldb, void* out, int64_t ldo, int M, int N, int K,
+                           int accumulate, void* stream) {
+  VTK_REQUIRE(A && Bt && out, "vtk_linear_nn_acc_bf16: null pointer");
+  VTK_REQUIRE(ldo % 8 == 0, "vtk_linear_nn_acc_bf16: ldo must be a multiple of 8");
+  GemmArgs g = base_args(A, lda, Bt, ldb, N, M, N, K);
+  g.trans = 2;
+  g.epi.out = (bf16*)out; g.epi.ldo = ldo; g.epi.accumulate = accumulate ? 1 : 0;
+  return launch_gemm(EPI_BIAS, g, (cudaStream_t)stream);
+}
+
+int vtk_linear2_bf16(const void* A, int64_t lda, const void* W0, int64_t ldw0, const void* W1, int64_t ldw1, void* out, int64_t ldo,
+                     int M, int N, int K0, int K1, void* stream) {
+  VTK_REQUIRE(A && W0 && W1 && out, "vtk_linear2_bf16: null pointer");
+  VTK_REQUIRE(ldo % 8 == 0 && K0 > 0 && K1 > 0, "vtk_linear2_bf16: ldo must be a multiple of 8 and both K parts non-empty");
+  const bool aligned = ((reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(A)) & 15) == 0;
+  if (M > 128 && N > 128 && K0 % 64 == 0 && ldw1 % 8 == 0 && aligned && !(getenv("VTK_GEMM_PAIR") && atoi(getenv("VTK_GEMM_PAIR")) == 0)) {
+    GemmArgs g = base_args(A, lda, W0, ldw0, N, M, N, K0 + K1);       // one accumulator over both K ranges
+    g.B2 = (const bf16*)W1; g.ldb2 = ldw1; g.epi.k_split = K0;
+    g.epi.out = (bf16*)out; g.epi.ldo = ldo;
+    return launch_gemm(EPI_BIAS, g, (cudaStream_t)stream);
+  }
+  // small / oddly shaped problems: two GEMMs, the second one adding to the first one's output
+  GemmArgs g0 = base_args(A, lda, W0, ldw0, N, M, N, K0);
+  g0.epi.out = (bf16*)out; g0.epi.ldo = ldo;
+  int r = launch_gemm(EPI_BIAS, g0, (cudaStream_t)stream);
+  if (r) return r;
+  GemmArgs g1 = base_args((const bf16*)A + K0, lda, W1, ldw1, N, M, N, K1);
+  g1.epi.out = (bf16*)out; g1.epi.ldo = ldo; g1.epi.accumulate = 1;
+  return launch_gemm(EPI_BIAS, g1, (cudaStream_t)stream);
+}
+
 int vtk_linear_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
                        int M, int N, int K, float eps, void* stream) {
   VTK_REQUIRE(A && W && out && bias, "vtk_linear_ln_bf16: null pointer");
@@ -404,6 +457,10 @@ int vtk_quant_rows_e4m3(const void* x, int64_t ldx, void* q, int64_t ldq, float*
   VTK_REQUIRE(x && q && scale, "vtk_quant_rows_e4m3: null pointer");
   return launch_quant_rows_e4m3((const bf16*)x, ldx, (uint8_t*)q, ldq, scale, M, K, nullptr, (cudaStream_t)stream);
 }
+int vtk_quant_tensor_e4m3(const void* x, int64_t ldx, void* q, int64_t ldq, float* scale, float* amax_ws, int M, int K, void* stream) {
+  VTK_REQUIRE(x && q && scale && amax_ws, "vtk_quant_tensor_e4m3: null pointer");
+  return launch_quant_rows_e4m3((const bf16*)x, ldx, (uint8_t*)q, ldq, scale, M, K, nullptr, (cudaStream_t)stream, amax_ws);
+}
 
 int vtk_proj_residual_fp8(const void* A8, int64_t lda, const float* a_scale, const void* W8, int64_t ldw, float w_scale,
                           const void* gamma, void* x, int64_t ldx, int M, int N, int K, void* stream) {
@@ -425,6 +482,18 @@ int vtk_attention_bf16(const void* q, const void* k, const void* v, int64_t ld_q
   a.zero_invalid_rows = zero_invalid_rows;
   a.window = window;
   a.lse = lse;
+  return launch_attention(a, (cudaStream_t)stream);
+}
+
+int vtk_attention_packed_bf16(const void* q, const void* k, const void* v, int64_t ld_qkv, void* out, int64_t ld_out, const int* n_valid,
+                              const int* cu, const int* cuq, const int* grp_img, const int* grp_order, int B, int N, int heads, int d,
+                              int64_t row_cap, int grp_cap, void* stream) {
+  VTK_REQUIRE(q && k && v && out && n_valid && cu && cuq && grp_img && grp_order, "vtk_attention_packed_bf16: null pointer");
+  AttnArgs a;
+  a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.ld_qkv = ld_qkv; a.out = (bf16*)out; a.ld_out = ld_out;
+  a.kv_len = n_valid; a.key_mask = nullptr; a.prefix_flag = nullptr; a.B = B; a.N = N; a.heads = heads; a.d = d;
+  a.zero_invalid_rows = 0; a.window = -1; a.lse = nullptr;
+  a.cu = cu; a.cuq = cuq; a.grp_img = grp_img; a.grp_order = grp_order; a.row_cap = row_cap; a.grp_cap = grp_cap;
   return launch_attention(a, (cudaStream_t)stream);
 }
 
@@ -452,6 +521,18 @@ int vtk_swiglu_fwd(const void* zraw, int64_t ldz, int qp, void* act, int64_t ld_
 int vtk_resid_fwd(const void* x, const void* y, const void* gamma, void* out, int M, int D, void* stream) {
   VTK_REQUIRE(x && y && gamma && out, "vtk_resid_fwd: null pointer");
   return launch_resid_fwd((const bf16*)x, (const bf16*)y, (const bf16*)gamma, (bf16*)out, M, D, (cudaStream_t)stream);
+}
+int vtk_resid_fwd_dp(const void* x, const void* y, const void* gamma, void* out, int M, int D, const float* keep, int rows_per_image,
+                     float keep_prob, void* stream) {
+  VTK_REQUIRE(x && y && gamma && out, "vtk_resid_fwd_dp: null pointer");
+  return launch_resid_fwd((const bf16*)x, (const bf16*)y, (const bf16*)gamma, (bf16*)out, M, D, (cudaStream_t)stream, keep, rows_per_image,
+                          keep_prob);
+}
+int vtk_resid_bwd_dp(const void* dx, const void* y, const void* gamma, void* dy, float* dgamma, int M, int D, const float* keep,
+                     int rows_per_image, float keep_prob, void* stream) {
+  VTK_REQUIRE(dx && y && gamma && dy && dgamma, "vtk_resid_bwd_dp: null pointer");
+  return launch_resid_bwd((const bf16*)dx, (const bf16*)y, (const bf16*)gamma, (bf16*)dy, dgamma, M, D, (cudaStream_t)stream, keep,
+                          rows_per_image, keep_prob);
 }
 int vtk_layernorm_fwd(const void* x, void* out, int M, int C, float eps, void* stream) {
   VTK_REQUIRE(x && out, "vtk_layernorm_fwd: null pointer");
@@ -503,6 +584,17 @@ int vtk_adamw_bf16(void* p, const void* g, void* m, void* v, int64_t n, float lr
   VTK_REQUIRE(p && g && m && v, "vtk_adamw_bf16: null pointer");
   return launch_adamw((bf16*)p, (const bf16*)g, (bf16*)m, (bf16*)v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                       (cudaStream_t)stream);
+}
+int vtk_adamw_multi(const vtk_adamw_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps, int step,
+                    float grad_scale, void* stream) {
+  VTK_REQUIRE(tensors || n_tensors == 0, "vtk_adamw_multi: null tensor table");
+  static_assert(sizeof(vtk_adamw_tensor) == sizeof(AdamwTensor), "vtk_adamw_tensor layout");
+  return launch_adamw_multi(reinterpret_cast<const AdamwTensor*>(tensors), n_tensors, lr, beta1, beta2, eps, step, grad_scale,
+                            (cudaStream_t)stream);
+}
+int vtk_scale_by_dev(void* x, const float* scale, int64_t n, void* stream) {
+  VTK_REQUIRE(x && scale, "vtk_scale_by_dev: null pointer");
+  return launch_scale_by_dev((bf16*)x, scale, n, (cudaStream_t)stream);
 }
 int vtk_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, int M, int heads, int d, void* stream) {
   VTK_REQUIRE(o && dout && delta, "vtk_attn_delta: null pointer");
@@ -628,9 +720,9 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
     }
     const bool f8 = !s.fp8.empty();     // AE.quantize: e4m3 operands for both block GEMMs (needs the fused norm)
     if (f8) {
-      { LaunchTimer t(h, st, CLS_MISC); r = launch_quant_rows_e4m3(w.x, D, w.x8, D, w.sx, M, D, m_dev, st); }
+      { LaunchTimer t(h, st, CLS_MISC); r = launch_quant_rows_e4m3(w.x, D, w.x8, D, w.sx, M, D, m_dev, st, h->fp8_per_tensor ? w.amax : nullptr); }
       if (r) return r;
-      ++launches;
+      launches += h->fp8_per_tensor ? 2 : 1;
     }
     GemmArgs g1 = f8 ? base_args(w.x8, D, s.fp8[i].w_in8, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D)
                      : base_args(fused ? w.x : w.h, D, b.w_in, D, (int64_t)qp + 2 * Hf, M, qp + 2 * Hf, D);
@@ -661,9 +753,9 @@ static int run_blocks(vtk_ae_s* h, const Side& s, const Workspace& w, const int6
     { LaunchTimer t(h, st, CLS_ATTENTION); r = launch_attention(a, st); }
     if (r) return r;
     if (f8) {
-      { LaunchTimer t(h, st, CLS_MISC); r = launch_quant_rows_e4m3(w.a2, kp, w.a28, kp, w.sa, M, D + Hf, m_dev, st); }
+      { LaunchTimer t(h, st, CLS_MISC); r = launch_quant_rows_e4m3(w.a2, kp, w.a28, kp, w.sa, M, D + Hf, m_dev, st, h->fp8_per_tensor ? w.amax + 1 : nullptr); }
       if (r) return r;
-      ++launches;
+      launches += h->fp8_per_tensor ? 2 : 1;
     }
     GemmArgs g2 = f8 ? base_args(w.a28, kp, s.fp8[i].w_out8, kp, D, M, D, D + Hf) : base_args(w.a2, kp, b.w_out, kp, D, M, D, D + Hf);
     if (f8) { g2.fp8 = 1; g2.epi.a_scale = w.sa; g2.epi.w_scale = s.fp8[i].w_out_scale; }
@@ -770,6 +862,12 @@ int vtk_ae_set_fp8_weights(vtk_ae_t h, int side, const vtk_block_fp8* blocks, in
     VTK_REQUIRE(blocks[i].w_in8 && blocks[i].w_out8 && blocks[i].w_in_scale > 0.f && blocks[i].w_out_scale > 0.f,
                 "vtk_ae_set_fp8_weights: null pointer / non-positive scale in block %d", i);
   s.fp8.assign(blocks, blocks + nblocks);
+  return VTK_OK;
+}
+
+int vtk_ae_set_fp8_granularity(vtk_ae_t h, int per_tensor) {
+  VTK_REQUIRE(h, "vtk_ae_set_fp8_granularity: null handle");
+  h->fp8_per_tensor = per_tensor != 0;
   return VTK_OK;
 }
 

@@ -226,9 +226,11 @@ __device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
   return (uint32_t)lo | ((uint32_t)hi << 16);
 }
 
+// amax_all != nullptr: PER-TENSOR dynamic scale (torchao's default granularity for Float8DynamicActivationFloat8WeightConfig): every row
+// uses the amax of the whole tensor, computed by amax_kernel below; scale[row] is still written (all equal) so the GEMM epilogue is the same.
 __global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const bf16* __restrict__ x, long long ldx, uint8_t* __restrict__ q,
                                                               long long ldq, float* __restrict__ scale, int M, int K,
-                                                              const int* __restrict__ m_dev) {
+                                                              const int* __restrict__ m_dev, const float* __restrict__ amax_all) {
   pdl_wait();      // PDL (vtk_common.cuh): this kernel may have been launched before its predecessor finished
   pdl_trigger();
   const int lane = threadIdx.x & 31;
@@ -237,14 +239,18 @@ __global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const bf16* __rest
   for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * 8) {
     const bf16* xr = x + row * ldx;
     float amax = 0.f;
-    for (int v = lane; v < nvec; v += 32) {
-      const uint4 u = ld_global_v4(xr + 8 * v);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    if (amax_all) {
+      amax = __ldg(amax_all);
+    } else {
+      for (int v = lane; v < nvec; v += 32) {
+        const uint4 u = ld_global_v4(xr + 8 * v);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fmaxf(fabsf(bf16_lo(w[i])), fabsf(bf16_hi(w[i]))));
+        for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fmaxf(fabsf(bf16_lo(w[i])), fabsf(bf16_hi(w[i]))));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     const float sc = amax > 0.f ? amax / 448.f : 1.f;
     const float inv = amax > 0.f ? 448.f / amax : 1.f;
     if (lane == 0) scale[row] = sc;
@@ -259,14 +265,41 @@ __global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const bf16* __rest
   }
 }
 
+// amax_out[0] = max |x| over the [M, K] tensor (non-negative floats order like their bit patterns: one atomicMax per warp); zero it first
+__global__ void __launch_bounds__(256) amax_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ amax_out, int M, int K,
+                                                   const int* __restrict__ m_dev) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int nvec = K >> 3;
+  if (m_dev) M = min(M, __ldg(m_dev));
+  float amax = 0.f;
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * 8) {
+    const bf16* xr = x + row * ldx;
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 u = ld_global_v4(xr + 8 * v);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fmaxf(fabsf(bf16_lo(w[i])), fabsf(bf16_hi(w[i]))));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(amax_out), __float_as_int(amax));
+}
+
 int launch_quant_rows_e4m3(const bf16* x, long long ldx, uint8_t* q, long long ldq, float* scale, int M, int K, const int* m_dev,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, float* amax_ws) {
   if (K % 8 || ldx % 8 || ldq % 8) { set_error("quant_rows: K and the row strides must be multiples of 8"); return -2; }
   if (M <= 0) return 0;
   long long blocks = ((long long)M + 7) / 8;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  (void)launch_k(quant_rows_e4m3_kernel, dim3((int)blocks), dim3(256), 0, stream, x, ldx, q, ldq, scale, M, K, m_dev);
+  if (amax_ws) {   // per-tensor scale: one more read of x for the global amax
+    if (check_cuda(cudaMemsetAsync(amax_ws, 0, sizeof(float), stream), "amax memset")) return -1;
+    (void)launch_k(amax_kernel, dim3((int)blocks), dim3(256), 0, stream, x, ldx, amax_ws, M, K, m_dev);
+  }
+  (void)launch_k(quant_rows_e4m3_kernel, dim3((int)blocks), dim3(256), 0, stream, x, ldx, q, ldq, scale, M, K, m_dev, (const float*)amax_ws);
   return check_cuda(cudaGetLastError(), "quant_rows launch");
 }
 

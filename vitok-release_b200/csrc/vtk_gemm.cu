@@ -172,6 +172,12 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
       b0 = ld_global_nc_v4(p.bias + col);
       if (second) b1 = ld_global_nc_v4(p.bias + col + 8);
     }
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);   // accumulate: what `out` already holds
+    if (p.accumulate && row_ok) {
+      const bf16* ap = p.out + (long long)row * p.ldo + col;
+      a0 = ld_global_v4(ap);
+      if (second) a1 = ld_global_v4(ap + 8);
+    }
     uint32_t r[16];
     tmem_ld16(taddr + cc, r);
     tmem_wait_ld();
@@ -179,8 +185,9 @@ __device__ __forceinline__ void epi_bias_unit(const EpiParams& p, uint32_t taddr
       uint32_t o[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        o[i] = pack_bf16x2(__uint_as_float(r[2 * i]) + u4_lo(b0, i), __uint_as_float(r[2 * i + 1]) + u4_hi(b0, i));
-        o[4 + i] = pack_bf16x2(__uint_as_float(r[8 + 2 * i]) + u4_lo(b1, i), __uint_as_float(r[8 + 2 * i + 1]) + u4_hi(b1, i));
+        o[i] = pack_bf16x2(__uint_as_float(r[2 * i]) + u4_lo(b0, i) + u4_lo(a0, i), __uint_as_float(r[2 * i + 1]) + u4_hi(b0, i) + u4_hi(a0, i));
+        o[4 + i] = pack_bf16x2(__uint_as_float(r[8 + 2 * i]) + u4_lo(b1, i) + u4_lo(a1, i),
+                               __uint_as_float(r[8 + 2 * i + 1]) + u4_hi(b1, i) + u4_hi(a1, i));
       }
       bf16* op = p.out + (long long)row * p.ldo + col;
       st_global_v4(op, o[0], o[1], o[2], o[3]);
@@ -826,6 +833,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI == EPI_BIAS && epi.k_split > 0) tma_prefetch_desc(&tmO1);
     for (int s = 0; s < G2_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], SK ? 1 : CL / 2);   // one MMA commit per pair that writes into this CTA's slot
@@ -887,14 +895,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           } else {
             tma_load_2d_2cta(sA + s * A_STAGE_BYTES, &tmA, fb, kb * BKE, m0 + (int)rrank * BM);
           }
+          // second weight matrix for the k-blocks at / beyond k_split (EPI_BIAS only: its output tensor maps are unused, tmO1 carries B2)
+          const bool second_b = EPI == EPI_BIAS && !TRANS && epi.k_split > 0 && kb * BKE >= epi.k_split;
+          const CUtensorMap* tb = second_b ? &tmO1 : &tmB;
+          const int kc = second_b ? kb * BKE - epi.k_split : kb * BKE;
           if (CL == 4 && !SK) {   // this CTA fetches half of its B share and multicasts it to its counterpart in the other pair
             const int nb = (int)pair * (hw >> 1);
-            tma_load_2d_2cta_mc(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb,
+            tma_load_2d_2cta_mc(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), tb, fb, kc, n0 + (int)rank * hw + nb,
                                 (uint16_t)((1u << rank) | (1u << (rank + 2))));
           } else {
             for (int nb = 0; nb < hw; nb += 64) {
               if (TRANS & 2) tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, n0 + (int)rank * hw + nb, kb * BK);
-              else tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, kb * BKE, n0 + (int)rank * hw + nb);
+              else tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), tb, fb, kc, n0 + (int)rank * hw + nb);
             }
           }
           if (++s == G2_STAGES) { s = 0; ph ^= 1; }
@@ -1122,6 +1134,8 @@ static int launch_gemm2_cl4(const GemmArgs& a, const CUtensorMap& tmA, const CUt
     if (encode_tmap_bf16(&tmO1, a.epi.act, (uint64_t)a.epi.Hf, (uint64_t)a.M, (uint64_t)a.epi.ld_act, 32, 32, 64)) return -1;
   } else if (EPI == EPI_RESID) {
     if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
+  } else if (EPI == EPI_BIAS && a.epi.k_split > 0) {
+    if (encode_tmap_bf16_sw128(&tmO1, a.B2, (uint64_t)(a.K - a.epi.k_split), (uint64_t)a.b_rows, (uint64_t)a.ldb2, 64)) return -1;
   }
   return check_cuda(launch_k(kern, dim3(4 * clusters), dim3(128 + 32 * NEPI), smem_bytes, stream, tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc,
                              a.epi), "gemm2 (4-CTA cluster) launch");
@@ -1141,7 +1155,7 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
     if (encode_tmap_u8_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.b_rows, (uint64_t)a.ldb, 64)) return -1;
   } else {
     if (encode_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda, BM)) return -1;
-    if (encode_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.b_rows, (uint64_t)a.ldb, 64)) return -1;
+    if (encode_tmap_bf16_sw128(&tmB, a.B, (uint64_t)(a.epi.k_split > 0 ? a.epi.k_split : a.K), (uint64_t)a.b_rows, (uint64_t)a.ldb, 64)) return -1;
   }
   TileSched sc;
   sc.bn = G2_BN;
@@ -1185,6 +1199,8 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
     if (encode_tmap_bf16(&tmO1, a.epi.act, (uint64_t)a.epi.Hf, (uint64_t)a.M, (uint64_t)a.epi.ld_act, 32, 32, 64)) return -1;
   } else if (EPI == EPI_RESID) {
     if (encode_tmap_bf16(&tmO0, a.epi.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.epi.ldo, 32, 32, 64)) return -1;
+  } else if (EPI == EPI_BIAS && a.epi.k_split > 0) {
+    if (encode_tmap_bf16_sw128(&tmO1, a.B2, (uint64_t)(a.K - a.epi.k_split), (uint64_t)a.b_rows, (uint64_t)a.ldb2, 64)) return -1;
   }
   const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
   auto kern = a.trans == 3 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 3>
@@ -1277,6 +1293,14 @@ int launch_gemm_inner(EpiKind kind, const GemmArgs& a, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) {
     set_error("gemm: operand pointers must be 16-byte aligned");
     return -2;
+  }
+  if (a.epi.k_split > 0) {   // two weight matrices, one accumulator: pair kernel only (the caller checks the shape)
+    if (kind != EPI_BIAS || a.trans || a.fp8 || !a.B2 || (a.epi.k_split % BK) || a.epi.k_split >= a.K || (a.ldb2 % 8) || a.M <= BM || a.N <= 128 ||
+        !gemm_pair_mode() || (reinterpret_cast<uintptr_t>(a.B2) & 15)) {
+      set_error("gemm(k_split): needs the bf16 pair kernel (M > 128, N > 128), k_split %% 64 == 0 inside K, a 16-byte aligned second matrix");
+      return -3;
+    }
+    return launch_gemm2_t<EPI_BIAS, 8>(a, stream);
   }
   if (a.trans) {   // transposed operands (weight gradients): CTA-pair kernel, plain epilogue
     if (kind != EPI_BIAS || a.fp8 || (a.trans != 2 && a.trans != 3)) {

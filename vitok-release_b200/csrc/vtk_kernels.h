@@ -78,6 +78,10 @@ struct EpiParams {
   // FP8 operands (GemmArgs::fp8): every accumulator row is multiplied by a_scale[row] * w_scale (per-row activation scale
   // of the dynamic quantisation x per-tensor weight scale) before anything else, on top of the fused-norm1 scale
   const float* a_scale; float w_scale;
+  int accumulate;       // EPI_BIAS: out = bf16(acc + bias + float(out)) -- the GEMM adds to what `out` already holds
+  int k_split;          // > 0 (pair kernel, EPI_BIAS, K-major operands): k-blocks at or beyond k_split read their B tile from the
+                        // SECOND weight matrix (GemmArgs::B2, k coordinate - k_split): out = A[:, :k_split] B^T + A[:, k_split:] B2^T
+                        // in one accumulator -- [out_proj | fc2] without a packed copy (training forward); a multiple of 64
   const int* m_dev;     // optional: number of rows to process, read on the device (<= GemmArgs::M, which is then the row
                         // capacity of the buffers); used by the packed NaFlex path where sum(n_i) is only known on the GPU
   unsigned long long* prof;  // perf experiments only (env VTK_GEMM_PROF): per-role clock64 accumulators, or null
@@ -88,6 +92,7 @@ struct GemmArgs {
   const bf16* A; long long lda;   // [M, K], row stride lda
   const bf16* B; long long ldb;   // [N_rows, K], row stride ldb (N_rows may be < N: OOB rows read as 0)
   long long b_rows;
+  const bf16* B2; long long ldb2;   // second weight matrix [N_rows, K - k_split] (EpiParams::k_split > 0), else null
   int M, N, K;                    // N = number of output (packed) columns to cover
   int trans;                      // 3: A is [K, M] and B is [K, N] row-major (out = A^T B); 2: only B is [K, N] (out = A B); CTA-pair kernel, EPI_BIAS
   int fp8;                        // 1: A and B hold e4m3 bytes (lda / ldb / K in elements = bytes); CTA-pair kernel only
@@ -173,8 +178,9 @@ int launch_unpack_rows(const bf16* packed, long long ld_p, const PackPlan& pl, b
 int launch_cast_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t stream);
 int launch_cast_bf16_f32(const bf16* in, float* out, long long n, cudaStream_t stream);
 // dynamic per-row FP8 (e4m3) quantisation: q[row, :K] = e4m3(x[row, :K] / scale[row]), scale[row] = amax(row) / 448
+// amax_ws (optional, one device float): per-TENSOR scale instead (amax of the whole tensor, torchao's default granularity)
 int launch_quant_rows_e4m3(const bf16* x, long long ldx, uint8_t* q, long long ldq, float* scale, int M, int K, const int* m_dev,
-                           cudaStream_t stream);
+                           cudaStream_t stream, float* amax_ws = nullptr);
 int launch_kv_len(const uint8_t* mask, int* kv_len, int* is_prefix, int B, int N, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
@@ -191,8 +197,11 @@ struct PatchifyArgs {
   int64_t* row_idx; int64_t* col_idx; int64_t* time_idx;  // [B, T]
   int64_t* meta;               // [4, B] = orig_height, orig_width, grid_rows, grid_cols
   int* status;                 // device int: set to 1 if any grid exceeds max_tokens
+  int max_h = 0, max_w = 0;    // optional: largest image height / width of the batch (host knowledge); > 0 selects the row-coalesced
+                               // uint8 kernel, which walks the batch's bounding box
 };
 int launch_patchify(const PatchifyArgs& a, cudaStream_t stream);
+int launch_patchify_selftest(int* mismatches, cudaStream_t stream);   // norm_u8_fast == norm_u8 for all 256 inputs
 
 struct UnpatchifyArgs {
   const void* patches;         // [B, N, 3 p^2]
@@ -215,9 +224,11 @@ int launch_grid_extent(const uint8_t* mask, const int64_t* row, const int64_t* c
 int launch_qk_norm_rope_fwd(const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk, const bf16* rope, bf16* qkv,
                             long long ldq, int M, int heads, int d, float eps, cudaStream_t st);
 int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long long lda, int M, int Hf, int layout, cudaStream_t st);
-int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st);
+int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st,
+                     const float* keep = nullptr, int rows_per_img = 0, float keep_prob = 1.f);
 int launch_ln_fwd(const bf16* x, bf16* out, int M, int C, float eps, cudaStream_t st);
-int launch_resid_bwd(const bf16* dx, const bf16* y, const bf16* gamma, bf16* dy, float* dgamma, int M, int D, cudaStream_t st);
+int launch_resid_bwd(const bf16* dx, const bf16* y, const bf16* gamma, bf16* dy, float* dgamma, int M, int D, cudaStream_t st,
+                     const float* keep = nullptr, int rows_per_img = 0, float keep_prob = 1.f);
 int launch_colsum(const bf16* in, long long ld, float* out, int M, int C, cudaStream_t st);
 int launch_swiglu_bwd(const bf16* dact, long long ldd, const bf16* zraw, long long ldz, int qp, bf16* dz, long long lddz, int M,
                       int Hf, int layout, cudaStream_t st);
@@ -233,5 +244,12 @@ int launch_adamw(bf16* p, const bf16* g, bf16* m, bf16* v, long long n, float lr
                  float grad_scale, cudaStream_t st);
 int launch_attn_delta(const bf16* o, long long ldo, const bf16* dob, long long lddo, float* delta, int M, int heads, int d,
                       cudaStream_t st);
+// one tensor of a multi-tensor AdamW step (mirrors vtk_adamw_tensor of include/vitok_b200.h)
+struct AdamwTensor {
+  float* master; void* p16; const void* g; float* m; float* v; long long n; float weight_decay; int g_is_f32;
+};
+int launch_adamw_multi(const AdamwTensor* tensors, int n_tensors, float lr, float b1, float b2, float eps, int step, float grad_scale,
+                       cudaStream_t st);
+int launch_scale_by_dev(bf16* x, const float* scale, long long n, cudaStream_t st);
 
 }  // namespace vtk

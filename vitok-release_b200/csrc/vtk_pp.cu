@@ -8,6 +8,8 @@
 //   unpatchify   vitok/pp/ops.py:295-335: scatter + fold restated as a gather through a cell->token map,
 //                with _convert_format (vitok/pp/io.py:91-121) optionally fused.
 // All integer/byte work is bit-exact against the reference.
+#include <stdlib.h>
+
 #include "vtk_common.cuh"
 #include "vtk_kernels.h"
 
@@ -16,6 +18,21 @@ namespace vtk {
 // ToTensor (u / 255, fp32 division) then Normalize(0.5, 0.5) ((t - 0.5) / 0.5 == (t - 0.5) * 2 exactly), ops.py:140-161
 __device__ __forceinline__ float norm_u8(uint32_t u) {
   return __fmul_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), 0.5f), 2.0f);
+}
+// The same value without the division sequence and without a table: q0 = u * RN(1/255), one FMA residual + one FMA correction is the
+// textbook correctly-rounded quotient, and for the 256 possible inputs it is bit-identical to __fdiv_rn (checked exhaustively against
+// norm_u8 by patchify_selftest_kernel / tests/test_gpu_pp.py).  3 FMA-pipe instructions instead of a shared-memory lookup whose
+// random bank conflicts bounded the uint8 front end at half of HBM bandwidth.
+__device__ __forceinline__ float norm_u8_fast(uint32_t u) {
+  const float uf = (float)u, rcp = 0.0039215688593685627f;   // RN(1 / 255)
+  const float q0 = __fmul_rn(uf, rcp);
+  const float rem = __fmaf_rn(-q0, 255.0f, uf);
+  const float q = __fmaf_rn(rem, rcp, q0);
+  return __fmul_rn(__fsub_rn(q, 0.5f), 2.0f);
+}
+__global__ void patchify_selftest_kernel(int* mismatches) {
+  const uint32_t u = threadIdx.x;
+  if (__float_as_uint(norm_u8(u)) != __float_as_uint(norm_u8_fast(u))) atomicAdd(mismatches, 1);
 }
 
 template <typename OutT>
@@ -58,6 +75,28 @@ __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyArgs a) {
     } else if (a.in_dtype == 0) {
       const float* img = reinterpret_cast<const float*>(a.images) + off;
       const bool al = ((reinterpret_cast<uintptr_t>(img) | ((uintptr_t)W << 2)) & 15) == 0;   // rows start 16-byte aligned
+      if (PT && al && (r + 1) * p <= H && (c + 1) * p <= W) {
+        // interior token of an aligned image (every token of the fixed-size configs): no bounds tests, and all of a lane's
+        // 16-byte loads are issued before the first store -- this kernel is latency-bound otherwise (two loads in flight per
+        // lane reached 3.3 TB/s), six to eight independent loads per lane keep enough bytes in flight for HBM
+        constexpr int NIT = PT ? (3 * PT * PT / 4) / 32 : 1;    // 6 (p = 16) / 24 (p = 32) chunks per lane
+        constexpr int UN = NIT % 8 == 0 ? 8 : 6;
+        const float* base = img + (long long)(r * p) * W + c * p;
+        const long long plane = (long long)H * W;
+#pragma unroll 1
+        for (int it0 = 0; it0 < NIT; it0 += UN) {
+          float4 v[UN];
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const int e4 = lane + 32 * (it0 + u);
+            const int ch = e4 / chunks, rem = e4 - ch * chunks;
+            const int dy = rem / p4, dx = (rem - dy * p4) << 2;
+            v[u] = __ldg(reinterpret_cast<const float4*>(base + ch * plane + (long long)dy * W + dx));
+          }
+#pragma unroll
+          for (int u = 0; u < UN; ++u) store4(dst + ((lane + 32 * (it0 + u)) << 2), v[u]);
+        }
+      } else
 #pragma unroll 2
       for (int e4 = lane; e4 < 3 * chunks; e4 += 32) {
         const int ch = e4 / chunks, rem = e4 - ch * chunks;
@@ -80,6 +119,34 @@ __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyArgs a) {
     } else {
       const uint8_t* img = reinterpret_cast<const uint8_t*>(a.images) + off;
       const bool al = (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+      if (PT && al && (W & 3) == 0 && (r + 1) * p <= H && (c + 1) * p <= W) {
+        // interior token, 4-byte aligned rows: a lane's 12-byte pixel groups are loaded up front (see the fp32 path)
+        constexpr int NQ = PT ? (PT * PT / 4) / 32 : 1;         // 2 (p = 16) / 8 (p = 32) 4-pixel groups per lane
+        const uint8_t* base = img + ((long long)(r * p) * W + c * p) * 3;
+#pragma unroll 1
+        for (int q0 = 0; q0 < NQ; q0 += 4) {
+          uint32_t w[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (q0 + u < NQ) {
+              const int q = lane + 32 * (q0 + u);
+              const int dy = q / p4, dx = (q - dy * p4) << 2;
+              const uint32_t* s32 = reinterpret_cast<const uint32_t*>(base + ((long long)dy * W + dx) * 3);
+              w[u][0] = __ldg(s32); w[u][1] = __ldg(s32 + 1); w[u][2] = __ldg(s32 + 2);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (q0 + u < NQ) {
+              const int q = lane + 32 * (q0 + u);
+              const uint32_t w0 = w[u][0], w1 = w[u][1], w2 = w[u][2];
+              store4(dst + (q << 2), make_float4(lut[w0 & 255], lut[w0 >> 24], lut[(w1 >> 16) & 255], lut[(w2 >> 8) & 255]));
+              store4(dst + pp + (q << 2), make_float4(lut[(w0 >> 8) & 255], lut[w1 & 255], lut[w1 >> 24], lut[(w2 >> 16) & 255]));
+              store4(dst + 2 * pp + (q << 2), make_float4(lut[(w0 >> 16) & 255], lut[(w1 >> 8) & 255], lut[w2 & 255], lut[w2 >> 24]));
+            }
+          }
+        }
+      } else
       for (int q = lane; q < chunks; q += 32) {
         const int dy = q / p4, dx = (q - dy * p4) << 2;
         const int y = r * p + dy, x = c * p + dx;
@@ -124,6 +191,81 @@ __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyArgs a) {
   }
 }
 
+// uint8 HWC input, row-coalesced: thread <-> 4 consecutive pixels of one image row (12 contiguous bytes; a warp reads 384 contiguous
+// bytes instead of eight 48-byte pieces), normalised arithmetically and written as three 4-element chunks (one per channel plane of the
+// token; the 4 lanes of a patch row fill one 32-byte sector).  Work item = (image, patch row r, 4-row group, x4); tokens beyond the
+// image's grid (padding tokens) and the index arrays are written by a second pass over tokens in the same kernel.
+template <typename OutT, int PT>
+__global__ void __launch_bounds__(256) patchify_u8_rows_kernel(const PatchifyArgs a, const int max_w4, const int max_rows) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int p = PT, pp = p * p, P = 3 * pp;
+  const int T = a.max_tokens;
+  // ---- pass 1: pixels.  idx -> (b, y, x4) over the bounding box [max_rows x max_w4] of the batch (threads outside an image idle)
+  const long long per_img = (long long)max_rows * max_w4;
+  const long long total = per_img * a.B;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / per_img);
+    const int rem = (int)(idx - (long long)b * per_img);
+    const int y = rem / max_w4, x = (rem - y * max_w4) << 2;
+    const int H = (int)a.img_table[3 * b + 1], W = (int)a.img_table[3 * b + 2];
+    const int gr = (H + p - 1) / p, gc = (W + p - 1) / p;
+    if (gr * gc > T || y >= gr * p || x >= gc * p) continue;        // outside this image's patch grid
+    const int r = y / p, dy = y - r * p, c = x / p, dx = x - c * p;
+    OutT* dst = reinterpret_cast<OutT*>(a.patches) + ((long long)b * T + r * gc + c) * P + dy * p + dx;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;   // zero padding to the patch boundary (applied AFTER normalize)
+    if (y < H && x < W) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.images) + a.img_table[3 * b] + ((long long)y * W + x) * 3;
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+      const int np = min(4, W - x);
+      if (np == 4 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+        w0 = __ldg(s32); w1 = __ldg(s32 + 1); w2 = __ldg(s32 + 2);
+      } else {
+        for (int k = 0; k < np * 3; ++k) {
+          const uint32_t u = src[k];
+          if (k < 4) w0 |= u << (8 * k); else if (k < 8) w1 |= u << (8 * (k - 4)); else w2 |= u << (8 * (k - 8));
+        }
+      }
+      v0.x = norm_u8_fast(w0 & 255); v1.x = norm_u8_fast((w0 >> 8) & 255); v2.x = norm_u8_fast((w0 >> 16) & 255);
+      if (np > 1) { v0.y = norm_u8_fast(w0 >> 24); v1.y = norm_u8_fast(w1 & 255); v2.y = norm_u8_fast((w1 >> 8) & 255); }
+      if (np > 2) { v0.z = norm_u8_fast((w1 >> 16) & 255); v1.z = norm_u8_fast(w1 >> 24); v2.z = norm_u8_fast(w2 & 255); }
+      if (np > 3) { v0.w = norm_u8_fast((w2 >> 8) & 255); v1.w = norm_u8_fast((w2 >> 16) & 255); v2.w = norm_u8_fast(w2 >> 24); }
+    }
+    store4(dst, v0);
+    store4(dst + pp, v1);
+    store4(dst + 2 * pp, v2);
+  }
+  // ---- pass 2: per token -- index arrays, metadata, and the zero rows of padding tokens (one warp per token)
+  const int lane = threadIdx.x & 31;
+  const unsigned ntok = (unsigned)a.B * (unsigned)T;
+  const unsigned nwarp = gridDim.x * (blockDim.x >> 5);
+  for (unsigned bt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bt < ntok; bt += nwarp) {
+    const int b = (int)(bt / (unsigned)T), t = (int)(bt - (unsigned)b * (unsigned)T);
+    const int H = (int)a.img_table[3 * b + 1], W = (int)a.img_table[3 * b + 2];
+    const int gr = (H + p - 1) / p, gc = (W + p - 1) / p;
+    const int n = gr * gc;
+    const bool valid = t < n && n <= T;
+    if (!valid) {
+      OutT* dst = reinterpret_cast<OutT*>(a.patches) + (long long)bt * P;
+      for (int e4 = lane; e4 < (P >> 2); e4 += 32) store4(dst + (e4 << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    if (lane == 0) {
+      a.patch_mask[bt] = valid ? 1 : 0;
+      a.row_idx[bt] = valid ? t / gc : 0;
+      a.col_idx[bt] = valid ? t - (t / gc) * gc : 0;
+      a.time_idx[bt] = 0;
+      if (t == 0) {
+        a.meta[0 * a.B + b] = H;
+        a.meta[1 * a.B + b] = W;
+        a.meta[2 * a.B + b] = gr;
+        a.meta[3 * a.B + b] = gc;
+        if (n > T && a.status) atomicExch(a.status, 1);
+      }
+    }
+  }
+}
+
 template <typename OutT>
 static void patchify_dispatch(const PatchifyArgs& a, int blocks, cudaStream_t stream) {
   if (a.patch == 16) (void)launch_k(patchify_kernel<OutT, 16>, dim3(blocks), dim3(256), 0, stream, a);
@@ -136,12 +278,37 @@ int launch_patchify(const PatchifyArgs& a, cudaStream_t stream) {
   if (a.B <= 0 || a.max_tokens <= 0) return 0;
   const long long ntok = (long long)a.B * a.max_tokens;
   if (ntok >= (1ll << 31)) { set_error("patchify: B * max_tokens too large"); return -2; }
-  long long blocks = (ntok + 7) / 8;                   // one warp per token, 8 warps per CTA
-  const long long cap = (long long)num_sms() * 8;     // a multiple of the SM count (8 resident CTAs per SM), warp-stride beyond
+  if (a.in_dtype == 1 && (a.patch == 16 || a.patch == 32) && a.max_h > 0 && a.max_w > 0) {
+    // uint8 HWC front end: the row-coalesced kernel over the batch's bounding box (the caller knows every image size)
+    const int p = a.patch;
+    const int max_rows = (a.max_h + p - 1) / p * p, max_w4 = ((a.max_w + p - 1) / p * p) >> 2;
+    const long long total = (long long)a.B * max_rows * max_w4;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < (ntok + 7) / 8 && (ntok + 7) / 8 <= cap) blocks = (ntok + 7) / 8;   // enough warps for the per-token pass
+    const dim3 g((unsigned)blocks), b(256);
+    if (a.out_dtype == 0) {
+      if (p == 16) (void)launch_k(patchify_u8_rows_kernel<float, 16>, g, b, 0, stream, a, max_w4, max_rows);
+      else (void)launch_k(patchify_u8_rows_kernel<float, 32>, g, b, 0, stream, a, max_w4, max_rows);
+    } else {
+      if (p == 16) (void)launch_k(patchify_u8_rows_kernel<bf16, 16>, g, b, 0, stream, a, max_w4, max_rows);
+      else (void)launch_k(patchify_u8_rows_kernel<bf16, 32>, g, b, 0, stream, a, max_w4, max_rows);
+    }
+    return check_cuda(cudaGetLastError(), "patchify (uint8 rows) launch");
+  }
+  long long blocks = (ntok + 7) / 8;                   // one warp per token, 8 warps per CTA: the block scheduler balances the tail
+  const long long cap = (long long)num_sms() * 8 * 16;  // (a fixed grid of one wave left the last tokens to a few warps); warp-stride beyond
   if (blocks > cap) blocks = cap;
   if (a.out_dtype == 0) patchify_dispatch<float>(a, (int)blocks, stream);
   else patchify_dispatch<bf16>(a, (int)blocks, stream);
   return check_cuda(cudaGetLastError(), "patchify launch");
+}
+
+int launch_patchify_selftest(int* mismatches, cudaStream_t stream) {
+  if (check_cuda(cudaMemsetAsync(mismatches, 0, sizeof(int), stream), "selftest memset")) return -1;
+  patchify_selftest_kernel<<<1, 256, 0, stream>>>(mismatches);
+  return check_cuda(cudaGetLastError(), "patchify selftest launch");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -165,20 +332,43 @@ __global__ void cellmap_kernel(const UnpatchifyArgs a) {
 }
 
 __device__ __forceinline__ float convert_px(float x, int fmt, bool bf16_math) {
-  // vitok/pp/io.py:91-121 from "minus_one_to_one"; each eager op rounds to the tensor dtype
+  // vitok/pp/io.py:91-121 from "minus_one_to_one"; each eager op rounds to the tensor dtype.  Halving is exact in both
+  // dtypes, so "/ 2" is a multiplication by 0.5 (no division sequence on the XU pipe)
   if (fmt == 1) {  // 0_255: ((clamp(x,-1,1) + 1) / 2 * 255).round()
     float t = fminf(fmaxf(x, -1.f), 1.f);
-    if (bf16_math) { t = bf16r(t + 1.f); t = bf16r(t / 2.f); t = bf16r(t * 255.f); }
-    else { t = __fadd_rn(t, 1.f); t = __fdiv_rn(t, 2.f); t = __fmul_rn(t, 255.f); }
+    if (bf16_math) { t = bf16r(t + 1.f); t = bf16r(t * 0.5f); t = bf16r(t * 255.f); }
+    else { t = __fadd_rn(t, 1.f); t = __fmul_rn(t, 0.5f); t = __fmul_rn(t, 255.f); }
     return rintf(t);
   }
   if (fmt == 2) {  // zero_to_one: ((x + 1) / 2).clamp(0, 1)
     float t;
-    if (bf16_math) { t = bf16r(x + 1.f); t = bf16r(t / 2.f); }
-    else { t = __fdiv_rn(__fadd_rn(x, 1.f), 2.f); }
+    if (bf16_math) { t = bf16r(x + 1.f); t = bf16r(t * 0.5f); }
+    else { t = __fmul_rn(__fadd_rn(x, 1.f), 0.5f); }
     return fminf(fmaxf(t, 0.f), 1.f);
   }
   return x;
+}
+
+// Four pixels of the "0_255" conversion -> packed uchar4, with no conversion-pipe (XU) instruction: the bf16 roundings are packed
+// cvt.rn.bf16x2.f32 (bf16(bf16(t * 0.5) * 255) == bf16(t * 127.5): halving is exact and an 8-bit x 8-bit significand product is exact
+// in fp32, so both round the same real number once), and round() + the cast to uint8 are one FADD with 1.5 * 2^23 (round to nearest
+// even in the low mantissa bits, what torch.round does) + a mask.  The first version (F2F / FRND / F2I per element) was XU-bound.
+__device__ __forceinline__ uint32_t to_u8x4(const float (&v)[4], bool bf16_math) {
+  float t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[k] = fminf(fmaxf(v[k], -1.f), 1.f);
+  if (bf16_math) {
+    const uint32_t a01 = bf2_cvt(t[0] + 1.f, t[1] + 1.f), a23 = bf2_cvt(t[2] + 1.f, t[3] + 1.f);
+    const uint32_t b01 = bf2_cvt(bf16_lo(a01) * 127.5f, bf16_hi(a01) * 127.5f), b23 = bf2_cvt(bf16_lo(a23) * 127.5f, bf16_hi(a23) * 127.5f);
+    t[0] = bf16_lo(b01); t[1] = bf16_hi(b01); t[2] = bf16_lo(b23); t[3] = bf16_hi(b23);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = __fmul_rn(__fmul_rn(__fadd_rn(t[k], 1.f), 0.5f), 255.f);
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r |= (__float_as_uint(__fadd_rn(t[k], 12582912.f)) & 255u) << (8 * k);
+  return r;
 }
 
 // One warp per canvas cell (b, r, c): the token that owns the cell is looked up once, its 3p^2 elements are read as
@@ -217,10 +407,7 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const UnpatchifyArgs a)
       }
       const long long o = (((long long)b * 3 + ch) * Hc + r * p + dy) * Wc + c * p + dx;
       if (a.out_format == 1) {
-        uchar4 u;
-        u.x = (unsigned char)convert_px(v[0], 1, bfm); u.y = (unsigned char)convert_px(v[1], 1, bfm);
-        u.z = (unsigned char)convert_px(v[2], 1, bfm); u.w = (unsigned char)convert_px(v[3], 1, bfm);
-        *reinterpret_cast<uchar4*>(reinterpret_cast<uint8_t*>(a.out) + o) = u;
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.out) + o) = to_u8x4(v, bfm);
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = convert_px(v[k], a.out_format, bfm);
@@ -234,8 +421,78 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const UnpatchifyArgs a)
   }
 }
 
+// Row-coalesced variant (compile-time patch size): thread <-> 4 consecutive pixels of FOUR consecutive canvas rows of one channel
+// plane.  A warp writes 128 contiguous pixels per row (128 B of uint8, 256 B of bf16, 512 B of fp32) -- the cell-per-warp kernel above
+// writes p-pixel pieces (16 bytes of uint8: half a sector) -- and reads the owning tokens' elements as 4-pixel chunks, four lanes per
+// 32-byte sector (bf16 patches, p = 16).  The four rows lie in the same patch row, so one cell-map lookup serves four loads that are
+// all issued before the first store.
+template <typename T, int PT>
+__global__ void __launch_bounds__(256) unpatchify_rows_kernel(const UnpatchifyArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int p = PT, pp = p * p, P = 3 * pp;
+  const int Hc = a.gy * p, Wc = a.gx * p, W4 = Wc >> 2, R4 = Hc >> 2;
+  const int cells_per_img = a.gy * a.gx;
+  const bool bfm = sizeof(T) == 2;
+  const long long total = (long long)a.B * 3 * R4 * W4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x4 = (int)(idx % W4);
+    const long long t1 = idx / W4;
+    const int yq = (int)(t1 % R4);
+    const int t2 = (int)(t1 / R4);
+    const int ch = t2 % 3, b = t2 / 3;
+    const int y0 = yq << 2, x = x4 << 2;
+    const int r = y0 / p, dy0 = y0 - r * p, c = x / p, dx = x - c * p;
+    const int cell = r * a.gx + c;
+    // token 0 is re-scattered into cell 0 after the main scatter (ops.py:332-333)
+    const int tok = (cell == 0) ? (a.patch_mask[(long long)b * a.N] ? 0 : -1) : a.cell_map[(long long)b * cells_per_img + cell];
+    float v[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+    if (tok >= 0) {
+      const T* src = reinterpret_cast<const T*>(a.patches) + ((long long)b * a.N + tok) * P + ch * pp + dy0 * p + dx;
+      if (sizeof(T) == 4) {
+        float4 f[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = __ldg(reinterpret_cast<const float4*>(src + k * p));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k][0] = f[k].x; v[k][1] = f[k].y; v[k][2] = f[k].z; v[k][3] = f[k].w; }
+      } else {
+        uint2 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint2*>(src + k * p));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k][0] = bf16_lo(u[k].x); v[k][1] = bf16_hi(u[k].x); v[k][2] = bf16_lo(u[k].y); v[k][3] = bf16_hi(u[k].y); }
+      }
+    }
+    const long long o = (((long long)b * 3 + ch) * Hc + y0) * Wc + x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (a.out_format == 1) {
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.out) + o + (long long)k * Wc) = to_u8x4(v[k], bfm);
+      } else {
+        float w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = convert_px(v[k][e], a.out_format, bfm);
+        if (sizeof(T) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o + (long long)k * Wc) = make_float4(w[0], w[1], w[2], w[3]);
+        else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.out) + o + (long long)k * Wc) = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
+      }
+    }
+  }
+}
+
 template <typename T>
 static void unpatchify_dispatch(const UnpatchifyArgs& a, int blocks, cudaStream_t stream) {
+  static const int rows_mode = getenv("VTK_UNPATCHIFY_ROWS") ? atoi(getenv("VTK_UNPATCHIFY_ROWS")) : 1;   // 0: cell-per-warp kernel (A/B)
+  if (rows_mode && (a.patch == 16 || a.patch == 32)) {
+    const long long total = (long long)a.B * 3 * (a.gy * a.patch / 4) * (a.gx * a.patch / 4);
+    long long rb = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 8 * 16;
+    if (rb > cap) rb = cap;
+    if (a.patch == 16) (void)launch_k(unpatchify_rows_kernel<T, 16>, dim3((unsigned)rb), dim3(256), 0, stream, a);
+    else (void)launch_k(unpatchify_rows_kernel<T, 32>, dim3((unsigned)rb), dim3(256), 0, stream, a);
+    return;
+  }
   if (a.patch == 16) (void)launch_k(unpatchify_kernel<T, 16>, dim3(blocks), dim3(256), 0, stream, a);
   else if (a.patch == 32) (void)launch_k(unpatchify_kernel<T, 32>, dim3(blocks), dim3(256), 0, stream, a);
   else (void)launch_k(unpatchify_kernel<T, 0>, dim3(blocks), dim3(256), 0, stream, a);
@@ -255,7 +512,7 @@ int launch_unpatchify(const UnpatchifyArgs& a, cudaStream_t stream) {
   }
   if (cells >= (1ll << 31)) { set_error("unpatchify: canvas too large"); return -2; }
   long long blocks = (cells + 7) / 8;                    // one warp per cell, 8 warps per CTA
-  const long long cap2 = (long long)num_sms() * 8;
+  const long long cap2 = (long long)num_sms() * 8 * 16;
   if (blocks > cap2) blocks = cap2;
   if (a.dtype == 0) unpatchify_dispatch<float>(a, (int)blocks, stream);
   else unpatchify_dispatch<bf16>(a, (int)blocks, stream);

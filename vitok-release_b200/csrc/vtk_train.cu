@@ -118,16 +118,32 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict_
 }
 
 // x_out = bf16(x + bf16(y * gamma))   (in place on x allowed)
+// Stochastic depth (drop_path, ae.py:15-30,65; decoder blocks in training): keep [B] holds the per-image 0/1 draw
+// floor(keep_prob + U[0,1)); the LayerScale output is divided by keep_prob (rounded to bf16, x.div) and multiplied by the
+// draw before it is added: x_out = x + bf16(bf16(y * gamma) / keep_prob) * keep[image].  keep == nullptr: no drop_path.
+__device__ __forceinline__ uint32_t drop_scale2(uint32_t t, float inv_keep_num, float keep_prob, float kp) {
+  // t = packed bf16x2 of the LayerScale output; returns bf16(t / keep_prob) * kp   (kp = 0 or 1)
+  const float a = bf16r(bf16_lo(t) / keep_prob) * kp, b = bf16r(bf16_hi(t) / keep_prob) * kp;
+  (void)inv_keep_num;
+  return bf2_cvt(a, b);
+}
 __global__ void __launch_bounds__(256) resid_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
-                                                        const bf16* __restrict__ gamma, bf16* __restrict__ out, int M, int D) {
+                                                        const bf16* __restrict__ gamma, bf16* __restrict__ out, int M, int D,
+                                                        const float* __restrict__ keep, int rows_per_img, float keep_prob) {
   const int vpr = D >> 3;
   const long long total = (long long)M * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % vpr) << 3;
     const uint4 xv = ld_global_v4(x + i * 8), yv = ld_global_nc_v4(y + i * 8), gv = ld_global_nc_v4(gamma + c);
+    uint4 t;
+    t.x = bf2_mul(yv.x, gv.x); t.y = bf2_mul(yv.y, gv.y); t.z = bf2_mul(yv.z, gv.z); t.w = bf2_mul(yv.w, gv.w);
+    if (keep) {
+      const float kp = __ldg(keep + (i / vpr) / rows_per_img);
+      t.x = drop_scale2(t.x, 0.f, keep_prob, kp); t.y = drop_scale2(t.y, 0.f, keep_prob, kp);
+      t.z = drop_scale2(t.z, 0.f, keep_prob, kp); t.w = drop_scale2(t.w, 0.f, keep_prob, kp);
+    }
     uint4 o;
-    o.x = bf2_add(xv.x, bf2_mul(yv.x, gv.x)); o.y = bf2_add(xv.y, bf2_mul(yv.y, gv.y));
-    o.z = bf2_add(xv.z, bf2_mul(yv.z, gv.z)); o.w = bf2_add(xv.w, bf2_mul(yv.w, gv.w));
+    o.x = bf2_add(xv.x, t.x); o.y = bf2_add(xv.y, t.y); o.z = bf2_add(xv.z, t.z); o.w = bf2_add(xv.w, t.w);
     *reinterpret_cast<uint4*>(out + i * 8) = o;
   }
 }
@@ -167,9 +183,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 
 // dy = bf16(dx * gamma);  dgamma[c] += sum_rows dx * y   (fp32 atomics, one per column and block)
 // block = 32 column groups (8 columns each) x 8 row lanes; grid = (ceil(D/256), row chunks)
+// drop_path (keep != nullptr): the gradient of the LayerScale output is bf16(dx * keep[image] / keep_prob) (autograd of x.div and
+// of the multiplication by the draw); dy and dgamma follow from it.
 __global__ void __launch_bounds__(256) resid_bwd_kernel(const bf16* __restrict__ dx, const bf16* __restrict__ y,
                                                         const bf16* __restrict__ gamma, bf16* __restrict__ dy,
-                                                        float* __restrict__ dgamma, int M, int D) {
+                                                        float* __restrict__ dgamma, int M, int D, const float* __restrict__ keep,
+                                                        int rows_per_img, float keep_prob) {
   __shared__ float red[8][256 + 8];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + cg * 8;
@@ -181,6 +200,11 @@ __global__ void __launch_bounds__(256) resid_bwd_kernel(const bf16* __restrict__
       float a[8], b[8], o[8];
       unpack8(ld_global_nc_v4(dx + m * D + c), a);
       unpack8(ld_global_nc_v4(y + m * D + c), b);
+      if (keep) {
+        const float kp = __ldg(keep + m / rows_per_img);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = bf16r(a[k] * kp / keep_prob);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         acc[k] += a[k] * b[k];
@@ -569,6 +593,105 @@ __global__ void __launch_bounds__(256) adamw_kernel(bf16* __restrict__ p, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-tensor AdamW with the reference's optimizer precision (scripts/train_vae.py:200-208 keeps fp32 parameters and fp32
+// Adam moments under autocast): per tensor an fp32 MASTER copy of the parameter and fp32 exp_avg / exp_avg_sq are updated
+// in fp32 and the bf16 model parameter is re-emitted from the master in the same pass -- an update smaller than half a bf16
+// ulp of the weight is therefore not lost (it accumulates in the master).  fp32 model parameters are their own master
+// (p16 == nullptr).  Up to ADAMW_MAX_T tensors per launch travel in the kernel parameters; work is cut into chunks of
+// ADAMW_CHUNK elements and dealt to the blocks round-robin, so one launch covers tensors of any size mix.
+// HBM traffic per parameter: 4 + 4 + 4 (master, m, v) + 2 (bf16 grad) read, 4 + 4 + 4 + 2 written = 28 bytes.
+// ------------------------------------------------------------------------------------------------
+static constexpr int ADAMW_MAX_T = 64;
+static constexpr int ADAMW_CHUNK = 8192;   // elements per (block, iteration): 256 threads x 4 vectors of 8
+struct AdamwBatch {
+  float* master[ADAMW_MAX_T];
+  bf16* p16[ADAMW_MAX_T];
+  const void* g[ADAMW_MAX_T];
+  float* m[ADAMW_MAX_T];
+  float* v[ADAMW_MAX_T];
+  long long n[ADAMW_MAX_T];
+  int chunk0[ADAMW_MAX_T + 1];   // first global chunk of every tensor
+  float wd[ADAMW_MAX_T];
+  unsigned char g_f32[ADAMW_MAX_T];
+  int nt;
+};
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant__ AdamwBatch b, float lr, float b1, float b2, float eps,
+                                                          float bc1, float bc2_sqrt, float grad_scale) {
+  const int total = b.chunk0[b.nt];
+  for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
+    int t = 0;   // tensor of this chunk: binary search in chunk0 (nt <= 64)
+    {
+      int lo = 0, hi = b.nt;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (b.chunk0[mid] <= ch) lo = mid; else hi = mid;
+      }
+      t = lo;
+    }
+    const long long e0 = (long long)(ch - b.chunk0[t]) * ADAMW_CHUNK;
+    const long long n = b.n[t];
+    const long long e1 = e0 + ADAMW_CHUNK < n ? e0 + ADAMW_CHUNK : n;
+    float* __restrict__ mp = b.master[t];
+    bf16* __restrict__ pp = b.p16[t];
+    float* __restrict__ mm = b.m[t];
+    float* __restrict__ vv = b.v[t];
+    const float wd = b.wd[t];
+    const bool gf32 = b.g_f32[t] != 0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(mp) | reinterpret_cast<uintptr_t>(mm) | reinterpret_cast<uintptr_t>(vv) |
+                       reinterpret_cast<uintptr_t>(b.g[t])) & 15) == 0 && (pp == nullptr || (reinterpret_cast<uintptr_t>(pp) & 7) == 0);
+    long long i = e0 + 4 * (long long)threadIdx.x;
+    if (vec) {
+      for (; i + 3 < e1; i += 4 * 256) {   // 4 elements per thread and iteration: 16-byte fp32 vectors, 8-byte bf16 vectors
+        float4 pf = *reinterpret_cast<const float4*>(mp + i), mf = *reinterpret_cast<const float4*>(mm + i), vf = *reinterpret_cast<const float4*>(vv + i);
+        float g4[4];
+        if (gf32) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(b.g[t]) + i));
+          g4[0] = q.x; g4[1] = q.y; g4[2] = q.z; g4[3] = q.w;
+        } else {
+          const uint2 q = __ldg(reinterpret_cast<const uint2*>(static_cast<const bf16*>(b.g[t]) + i));
+          g4[0] = bf16_lo(q.x); g4[1] = bf16_hi(q.x); g4[2] = bf16_lo(q.y); g4[3] = bf16_hi(q.y);
+        }
+        adamw_one(pf.x, g4[0] * grad_scale, mf.x, vf.x, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+        adamw_one(pf.y, g4[1] * grad_scale, mf.y, vf.y, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+        adamw_one(pf.z, g4[2] * grad_scale, mf.z, vf.z, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+        adamw_one(pf.w, g4[3] * grad_scale, mf.w, vf.w, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+        *reinterpret_cast<float4*>(mp + i) = pf;
+        *reinterpret_cast<float4*>(mm + i) = mf;
+        *reinterpret_cast<float4*>(vv + i) = vf;
+        if (pp) *reinterpret_cast<uint2*>(pp + i) = make_uint2(bf2_cvt(pf.x, pf.y), bf2_cvt(pf.z, pf.w));
+      }
+      // tail of the chunk (n % 4 elements of the last chunk)
+      i = e0 + ((e1 - e0) & ~3LL) + threadIdx.x;
+    } else {
+      i = e0 + threadIdx.x;
+    }
+    for (; i < e1; i += vec ? 256 * 1024 : 256) {
+      float pf = mp[i], mf = mm[i], vf = vv[i];
+      const float gf = (gf32 ? static_cast<const float*>(b.g[t])[i] : __bfloat162float(static_cast<const bf16*>(b.g[t])[i])) * grad_scale;
+      adamw_one(pf, gf, mf, vf, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+      mp[i] = pf; mm[i] = mf; vv[i] = vf;
+      if (pp) pp[i] = __float2bfloat16_rn(pf);
+    }
+  }
+}
+
+// x *= *scale (bf16 tensor, fp32 device scalar): the Charbonnier gradient times the incoming loss gradient
+__global__ void __launch_bounds__(256) scale_by_dev_kernel(bf16* __restrict__ x, const float* __restrict__ scale, long long n) {
+  const float s = __ldg(scale);
+  if (s == 1.f) return;
+  const long long nvec = n >> 3, stride = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = tid; i < nvec; i += stride) {
+    float f[8];
+    unpack8(ld_global_v4(x + 8 * i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] *= s;
+    *reinterpret_cast<uint4*>(x + 8 * i) = pack8(f);
+  }
+  for (long long i = (nvec << 3) + tid; i < n; i += stride) x[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * s);
+}
+
 // per attention row and head: delta = sum_d dO * O   (the softmax-backward row term), fp32 [M, heads]
 template <int DH>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ dob,
@@ -618,10 +741,12 @@ int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long l
   swiglu_fwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(zraw, ldz, qp, act, lda, M, Hf, layout);
   return check_cuda(cudaGetLastError(), "swiglu_fwd launch");
 }
-int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st) {
+int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st, const float* keep,
+                     int rows_per_img, float keep_prob) {
   VTK_TRAIN_CHECK(D % 8 == 0, "resid: D %% 8 required");
+  VTK_TRAIN_CHECK(!keep || (rows_per_img > 0 && keep_prob > 0.f), "resid: drop_path needs rows_per_img > 0 and keep_prob > 0");
   if (M <= 0) return 0;
-  resid_fwd_kernel<<<grid_for((long long)M * (D / 8), 256), 256, 0, st>>>(x, y, gamma, out, M, D);
+  resid_fwd_kernel<<<grid_for((long long)M * (D / 8), 256), 256, 0, st>>>(x, y, gamma, out, M, D, keep, rows_per_img, keep_prob);
   return check_cuda(cudaGetLastError(), "resid_fwd launch");
 }
 int launch_ln_fwd(const bf16* x, bf16* out, int M, int C, float eps, cudaStream_t st) {
@@ -630,11 +755,13 @@ int launch_ln_fwd(const bf16* x, bf16* out, int M, int C, float eps, cudaStream_
   ln_fwd_kernel<<<grid_for(M, 8), 256, 0, st>>>(x, out, M, C, eps);
   return check_cuda(cudaGetLastError(), "ln_fwd launch");
 }
-int launch_resid_bwd(const bf16* dx, const bf16* y, const bf16* gamma, bf16* dy, float* dgamma, int M, int D, cudaStream_t st) {
+int launch_resid_bwd(const bf16* dx, const bf16* y, const bf16* gamma, bf16* dy, float* dgamma, int M, int D, cudaStream_t st,
+                     const float* keep, int rows_per_img, float keep_prob) {
   VTK_TRAIN_CHECK(D % 8 == 0, "resid_bwd: D %% 8 required");
+  VTK_TRAIN_CHECK(!keep || (rows_per_img > 0 && keep_prob > 0.f), "resid_bwd: drop_path needs rows_per_img > 0 and keep_prob > 0");
   if (M <= 0) return 0;
   dim3 grid((D + 255) / 256, (unsigned)std::min<long long>(((long long)M + 7) / 8, 4LL * num_sms()));
-  resid_bwd_kernel<<<grid, 256, 0, st>>>(dx, y, gamma, dy, dgamma, M, D);
+  resid_bwd_kernel<<<grid, 256, 0, st>>>(dx, y, gamma, dy, dgamma, M, D, keep, rows_per_img, keep_prob);
   return check_cuda(cudaGetLastError(), "resid_bwd launch");
 }
 int launch_colsum(const bf16* in, long long ld, float* out, int M, int C, cudaStream_t st) {
@@ -705,6 +832,40 @@ int launch_adamw(bf16* p, const bf16* g, bf16* m, bf16* v, long long n, float lr
   if (vec) adamw_kernel<true><<<grid_for((n + 7) / 8, 256, 8), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
   else adamw_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2s, grad_scale);
   return check_cuda(cudaGetLastError(), "adamw launch");
+}
+int launch_adamw_multi(const AdamwTensor* tensors, int n_tensors, float lr, float b1, float b2, float eps, int step, float grad_scale,
+                       cudaStream_t st) {
+  VTK_TRAIN_CHECK(step >= 1, "adamw: step must be >= 1");
+  const float bc1 = 1.f - powf(b1, (float)step), bc2s = sqrtf(1.f - powf(b2, (float)step));
+  int i = 0;
+  while (i < n_tensors) {
+    AdamwBatch bt;
+    bt.nt = 0;
+    long long chunks = 0;
+    for (; i < n_tensors && bt.nt < ADAMW_MAX_T; ++i) {
+      const AdamwTensor& t = tensors[i];
+      if (t.n <= 0) continue;
+      VTK_TRAIN_CHECK(t.master && t.g && t.m && t.v, "adamw: null pointer in tensor %d", i);
+      const long long c = (t.n + ADAMW_CHUNK - 1) / ADAMW_CHUNK;
+      if (chunks + c >= (1ll << 30)) break;
+      const int k = bt.nt++;
+      bt.master[k] = t.master; bt.p16[k] = (bf16*)t.p16; bt.g[k] = t.g; bt.m[k] = t.m; bt.v[k] = t.v; bt.n[k] = t.n;
+      bt.wd[k] = t.weight_decay; bt.g_f32[k] = t.g_is_f32 ? 1 : 0;
+      bt.chunk0[k] = (int)chunks;
+      chunks += c;
+    }
+    if (bt.nt == 0) continue;
+    bt.chunk0[bt.nt] = (int)chunks;
+    const int grid = (int)std::min<long long>(chunks, (long long)num_sms() * 8);
+    adamw_multi_kernel<<<grid, 256, 0, st>>>(bt, lr, b1, b2, eps, bc1, bc2s, grad_scale);
+    if (check_cuda(cudaGetLastError(), "adamw_multi launch")) return -1;
+  }
+  return 0;
+}
+int launch_scale_by_dev(bf16* x, const float* scale, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  scale_by_dev_kernel<<<grid_for((n + 7) / 8, 256, 8), 256, 0, st>>>(x, scale, n);
+  return check_cuda(cudaGetLastError(), "scale_by_dev launch");
 }
 int launch_attn_delta(const bf16* o, long long ldo, const bf16* dob, long long lddo, float* delta, int M, int heads, int d,
                       cudaStream_t st) {

@@ -38,6 +38,11 @@ class BlockFp8(ctypes.Structure):
     _fields_ = [("w_in8", c_vp), ("w_out8", c_vp), ("w_in_scale", ctypes.c_float), ("w_out_scale", ctypes.c_float)]
 
 
+class AdamwTensor(ctypes.Structure):
+    _fields_ = [("master", c_vp), ("p16", c_vp), ("g", c_vp), ("m", c_vp), ("v", c_vp), ("n", ctypes.c_longlong),
+                ("weight_decay", ctypes.c_float), ("g_is_f32", ctypes.c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol include/vitok_b200.h declares
 SIGNATURES = {
     "vtk_last_error": (ctypes.c_char_p, []),
@@ -45,6 +50,8 @@ SIGNATURES = {
     "vtk_sm_count": (c_int, []),
     "vtk_set_flag": (c_int, [ctypes.c_char_p, c_int]),
     "vtk_patchify": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vtk_patchify_ex": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "vtk_patchify_selftest": (c_int, [c_vp, c_vp]),
     "vtk_grid_extent": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "vtk_unpatchify": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "vtk_rmsnorm_bf16": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_f32, c_vp]),
@@ -56,16 +63,25 @@ SIGNATURES = {
     "vtk_pack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_int, c_vp]),
     "vtk_unpack_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
     "vtk_quant_rows_e4m3": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp]),
+    "vtk_quant_tensor_e4m3": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp]),
     "vtk_proj_residual_fp8": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_linear_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_linear_tn_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_linear_nn_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    "vtk_linear_nn_acc_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
+    "vtk_linear2_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
+    "vtk_resid_fwd_dp": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_f32, c_vp]),
+    "vtk_resid_bwd_dp": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_f32, c_vp]),
+    "vtk_adamw_multi": (c_int, [ctypes.POINTER(AdamwTensor), c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_f32, c_vp]),
+    "vtk_scale_by_dev": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "vtk_linear_ln_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
     "vtk_qkv_swiglu_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                     c_f32, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "vtk_proj_residual_bf16": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_attention_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_vp, c_vp]),
+    "vtk_attention_packed_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                          c_i64, c_int, c_vp]),
     "vtk_qk_norm_rope_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp]),
     "vtk_swiglu_fwd": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "vtk_resid_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
@@ -93,6 +109,7 @@ SIGNATURES = {
     "vtk_ae_last_launch_count": (c_int, [c_vp]),
     "vtk_ae_set_timing": (c_int, [c_vp, c_int]),
     "vtk_ae_set_packing": (c_int, [c_vp, c_int]),
+    "vtk_ae_set_fp8_granularity": (c_int, [c_vp, c_int]),
     "vtk_ae_set_fp8_weights": (c_int, [c_vp, c_int, ctypes.POINTER(BlockFp8), c_int]),
     "vtk_ae_set_norm_folded": (c_int, [c_vp, c_int, c_int]),
     "vtk_ae_collect_timing": (c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_int)]),
@@ -339,6 +356,18 @@ def quant_rows_e4m3(x: torch.Tensor):
 
 
 @_on_device
+@_on_device
+def quant_tensor_e4m3(x: torch.Tensor):
+    """Dynamic per-TENSOR FP8 quantisation (torchao's default granularity): returns (q [M, K] float8_e4m3fn, scale [M] fp32, all equal)."""
+    _req(x, torch.bfloat16, "x")
+    M, K = x.shape
+    q = torch.empty(M, K, dtype=torch.uint8, device=x.device)
+    scale = torch.empty(M, dtype=torch.float32, device=x.device)
+    ws = torch.zeros(1, dtype=torch.float32, device=x.device)
+    check(load().vtk_quant_tensor_e4m3(ptr(x), x.stride(0), ptr(q), q.stride(0), ptr(scale), ptr(ws), M, K, stream_ptr()))
+    return q.view(torch.float8_e4m3fn), scale
+
+
 def proj_residual_fp8(a8, a_scale, w8, w_scale: float, gamma, x):
     """x += gamma * (a_scale[:, None] * w_scale * (a8 @ w8^T)) with e4m3 operands (tcgen05 kind::f8f6f4)."""
     M, K = a8.shape
@@ -390,3 +419,16 @@ def umma_probe(a: torch.Tensor, b: torch.Tensor, n: int, k: int, b_mn_major: boo
     d = torch.zeros(128, n, dtype=torch.float32, device=a.device)
     check(load().vtk_umma_probe(ptr(a), ptr(b), ptr(d), n, k, 1 if b_mn_major else 0, lbo, sbo, kstep, stream_ptr()))
     return d
+
+
+@_on_device
+def attention_packed(qkv: torch.Tensor, plan: dict, B: int, N: int, heads: int, d: int) -> torch.Tensor:
+    """Attention over the packed NaFlex layout of ``pack_plan`` (qkv [row capacity, 3*heads*d]; the plan's qrows must be 128 for
+    d = 64, 256 for d = 128)."""
+    D = heads * d
+    out = torch.empty(qkv.shape[0], D, dtype=torch.bfloat16, device=qkv.device)   # pad rows are never written
+    base = qkv.data_ptr()
+    check(load().vtk_attention_packed_bf16(base, base + 2 * D, base + 4 * D, qkv.stride(0), ptr(out), out.stride(0), ptr(plan["n_valid"]),
+                                           ptr(plan["cu"]), ptr(plan["cuq"]), ptr(plan["grp_img"]), ptr(plan["grp_order"]), B, N, heads, d,
+                                           qkv.shape[0], plan["grp_img"].numel(), stream_ptr()))
+    return out

@@ -50,7 +50,8 @@ class GraphedAE:
 
     def _state(self):
         m = self.model
-        return (m._signature(), bool(m.token_packing), bool(m.fuse_norm), bool(m._quantization_applied), m.attn_backend, m.sw)
+        return (m._signature(), bool(m.token_packing), bool(m.fuse_norm), bool(m._quantization_applied), m.fp8_activation_scale,
+                m.attn_backend, m.sw)
 
     def _forward(self, d):
         m = self.model

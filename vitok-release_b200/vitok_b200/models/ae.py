@@ -259,6 +259,9 @@ class AE(nn.Module):
         # Block.norm1 fused into the GEMM epilogues (widths that are multiples of 256): no RMSNorm kernel, no h buffer
         # round trip.  False keeps the separate RMSNorm kernel (rounds h to bf16 exactly where the reference does).
         self.fuse_norm = os.environ.get("VTK_NO_FUSE_NORM", "0") != "1"
+        # quantize(): dynamic FP8 activation scale per "row" (default: finer, no extra pass over the activations) or per "tensor"
+        # (torchao's default granularity for Float8DynamicActivationFloat8WeightConfig, the reference's numerics)
+        self.fp8_activation_scale = "row"
         # True: re-pack the weights on every call (for code that writes parameters through ``.data``; see invalidate_packed)
         self.always_repack = False
 
@@ -447,6 +450,7 @@ class AE(nn.Module):
         out = torch.empty(B, N, out_cols, dtype=torch.bfloat16, device=x.device)
         fn = lib.vtk_ae_encode if side == 0 else lib.vtk_ae_decode
         _lib.check(lib.vtk_ae_set_packing(h, 1 if self.token_packing else 0))
+        _lib.check(lib.vtk_ae_set_fp8_granularity(h, 1 if self.fp8_activation_scale == "tensor" else 0))
         _lib.check(fn(h, xin.data_ptr(), row.data_ptr(), col.data_ptr(), m8.data_ptr() if m8 is not None else None,
                       B, N, out.data_ptr(), ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()), _lib.stream_ptr()))
         self.last_launch_count = lib.vtk_ae_last_launch_count(h)

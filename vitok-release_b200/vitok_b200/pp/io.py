@@ -27,7 +27,13 @@ def preprocess(images, pp: str = "to_tensor|normalize(minus_one_to_one)|patchify
         images = [images]
     steps = parse_pipeline(pp)
     if not steps or steps[-1][0] != "patchify":
-        raise ValueError("preprocess: the pipeline must end with patchify(patch, max_tokens)")
+        # not a patchifying pipeline: exactly what the reference does (io.py:43-49) -- transform every image, collate, move the
+        # dict's tensors to the device (for tensor- or PIL-valued pipelines that last step raises AttributeError there too)
+        from ..data import patch_collate_fn
+        from .registry import build_transform
+        transform = build_transform(pp)
+        batched = patch_collate_fn([transform(img) for img in images])
+        return {k: v.to(device) if isinstance(v, torch.Tensor) else v for k, v in batched.items()}
     _, pargs, pkw = steps[-1]
     probe = OPS["patchify"](*pargs, **pkw)
     patch, max_tokens = probe.patch, probe.max_tokens

@@ -152,10 +152,10 @@ def _patchify_packed(packed, offsets, sizes, in_dtype, patch, max_tokens, out_dt
     idx = torch.empty(3, B, T, dtype=torch.int64, device=dev)
     meta = torch.empty(4, B, dtype=torch.int64, device=dev)
     with _lib.device_of(packed, patches):       # the launch and stream_ptr() follow the tensors' device, not the current one
-        _lib.check(_lib.load().vtk_patchify(packed.data_ptr(), table.data_ptr(), in_dtype, B, patch, T,
-                                            0 if out_dtype == torch.float32 else 1, patches.data_ptr(), mask.data_ptr(),
-                                            idx[0].data_ptr(), idx[1].data_ptr(), idx[2].data_ptr(), meta.data_ptr(), None,
-                                            _lib.stream_ptr()))
+        _lib.check(_lib.load().vtk_patchify_ex(packed.data_ptr(), table.data_ptr(), in_dtype, B, patch, T,
+                                               0 if out_dtype == torch.float32 else 1, patches.data_ptr(), mask.data_ptr(),
+                                               idx[0].data_ptr(), idx[1].data_ptr(), idx[2].data_ptr(), meta.data_ptr(), None,
+                                               max(h for h, _ in sizes), max(w for _, w in sizes), _lib.stream_ptr()))
     return {"patches": patches, "patch_mask": mask, "row_idx": idx[0], "col_idx": idx[1], "time_idx": idx[2],
             "orig_height": meta[0], "orig_width": meta[1], "grid_rows": meta[2], "grid_cols": meta[3]}
 
