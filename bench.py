@@ -75,13 +75,18 @@ def c3_sizes(n, seed):
     return [(int(rng.randint(128, 513)), int(rng.randint(128, 513))) for _ in range(n)]
 
 
-def flops_per_image(cfg, N):
-    """per layer 2N D (4D + 3Hf) + 4 N^2 D, plus the four projections."""
+def flops_per_image(cfg, N, window=0):
+    """per layer 2N D (4D + 3Hf) + 4 N^2 D, plus the four projections.  With a sliding window of radius
+    `window` tokens a query sees at most 2 * window + 1 keys (clipped at the sequence ends): sum_i |{j : |i - j| <= window}|."""
     def hf(D):
         return ((int(D * cfg["mlp_factor"]) + 8) // 16) * 16
+    pairs = float(N) * N
+    if window and window > 0 and window < N:
+        w = int(window)
+        pairs = float(N) * (2 * w + 1) - float(w) * (w + 1)      # full bands minus the two clipped triangles
     tot = 0.0
     for D, L in ((cfg["encoder_width"], cfg["encoder_depth"]), (cfg["decoder_width"], cfg["decoder_depth"])):
-        tot += L * (2.0 * N * D * (4 * D + 3 * hf(D)) + 4.0 * N * N * D)
+        tot += L * (2.0 * N * D * (4 * D + 3 * hf(D)) + 4.0 * pairs * D)
     P, C, De, Dd = cfg["pixels_per_token"], cfg["channels_per_token"], cfg["encoder_width"], cfg["decoder_width"]
     tot += 2.0 * N * (P * De + De * C + C * Dd + Dd * P)
     return tot
@@ -514,7 +519,7 @@ def run_ours(args, rank, world, local):
                  "e2e": {k: o_e2e[k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}}
     if rank != 0:
         return
-    gf = sum(flops_per_image(cfg, n) for n in inp.n_valid) / B / 1e9     # per image, valid tokens only
+    gf = sum(flops_per_image(cfg, n, args.sw) for n in inp.n_valid) / B / 1e9     # per image, valid tokens only
     pk = peaks()
     try:
         n_img = 4 if 0 < res <= 256 else 1
@@ -583,7 +588,7 @@ def run_train(args, rank, world, local):
         return loss
 
     for _ in range(max(args.warmup, 1)):
-        losses.append(float(step()))
+        losses.append(float(step().detach()))
     torch.cuda.synchronize()
     barrier(world)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -594,9 +599,33 @@ def run_train(args, rank, world, local):
     ev1.record()
     torch.cuda.synchronize()
     barrier(world)
-    losses.append(float(last))
+    losses.append(float(last.detach()))
     clocks = sampler.stop() if sampler else None
     ms = max_over_ranks(ev0.elapsed_time(ev1), world, dev)
+    # exposed (non-overlapped) all-reduce time: the same steps once more with the gradient exchange switched off (ranks drift apart from
+    # here on -- these are the last steps of the run); exposed = synchronised step - local-only step, both max over ranks
+    exposed = None
+    if world > 1:
+        import contextlib
+        grp = getattr(model, "_grad_sync_group", None)
+        if grp is not None:
+            del model._grad_sync_group
+        ctx = net.no_sync() if hasattr(net, "no_sync") else contextlib.nullcontext()
+        n_local = max(2, min(args.steps, 5))
+        with ctx:
+            step()
+            torch.cuda.synchronize()
+            barrier(world)
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for _ in range(n_local):
+                step()
+            l1.record()
+            torch.cuda.synchronize()
+        barrier(world)
+        local_ms = max_over_ranks(l0.elapsed_time(l1), world, dev) / n_local
+        exposed = {"local_only_ms_per_step": local_ms, "allreduce_exposed_ms_per_step": ms / args.steps - local_ms,
+                   "gradient_bytes_per_step": sum(p.numel() for p in model.parameters()) * 2}
     if rank != 0:
         return
     N = T
@@ -613,6 +642,8 @@ def run_train(args, rank, world, local):
                    "attn_backend": backend, "gflop_per_image_fwd_bwd": gf},
         "model_tflops": value * gf / 1e3 / world, "model_frac_of_peak": value * gf / 1e3 / world / pk["bf16_sustained"],
         "loss_first_last": [losses[0], losses[-1]], "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "clocks": clocks,
+        "optimizer": "FusedAdamW: fp32 master weights + fp32 moments (scripts/train_vae.py:200-208 precision), bf16 model weights / gradients",
+        "grad_sync": exposed,
     }
     print(json.dumps(line), flush=True)
 

@@ -42,7 +42,9 @@ int vtk_sm_count(void); /* of the current device; <0 when no CUDA device is usab
  * tail; default 1, env VTK_PDL).  "gemm_splitk": split-K over the two CTA pairs of a 4-CTA cluster for the out_proj+fc2 residual
  * GEMM of small batches (<= 37 output tiles; default 1, env VTK_GEMM_SPLITK) -- the two K-halves are summed in fp32, so results
  * differ from the un-split kernel in the last bit of the accumulator; set 0 where bit-identical results across batch sizes
- * matter.  Returns VTK_ERR_BAD_ARG for an unknown name. */
+ * matter.  "reserve_sms" = n: the persistent kernels (GEMMs, d = 64 attention) size their grids for n SMs fewer (default 0, env
+ * VTK_RESERVE_SMS) -- room for NCCL's all-reduce CTAs when the gradient exchange overlaps the backward pass.
+ * Returns VTK_ERR_BAD_ARG for an unknown name. */
 int vtk_set_flag(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -5,6 +5,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "../../include/vitok_b200.h"
@@ -37,7 +40,31 @@ int num_sms() {   // of the CURRENT device (cached per device: one process may d
   return n;
 }
 
-static int g_flag_pdl = -1, g_flag_splitk = -1;
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : 0;
+}
+
+int ensure_max_smem(const void* kern, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kern, dev})) return 0;
+  const int r = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), what);
+  if (r == 0) done.insert({kern, dev});
+  return r;
+}
+
+static int g_flag_pdl = -1, g_flag_splitk = -1, g_flag_reserve = -1;
+// SMs the persistent kernels (GEMMs, d = 64 attention) may occupy: all of them, minus the ones a concurrent communication kernel needs
+// ("reserve_sms": NCCL's all-reduce CTAs run next to the backward GEMMs of the data-parallel training step; a persistent grid sized for
+// every SM would leave some of its CTAs waiting for the whole collective to finish before they can start)
+int usable_sms() {
+  if (g_flag_reserve < 0) g_flag_reserve = getenv("VTK_RESERVE_SMS") ? atoi(getenv("VTK_RESERVE_SMS")) : 0;
+  const int n = num_sms() - g_flag_reserve;
+  return n < 2 ? 2 : n;
+}
 bool pdl_enabled() {
   if (g_flag_pdl < 0) g_flag_pdl = getenv("VTK_PDL") ? atoi(getenv("VTK_PDL")) : 1;
   return g_flag_pdl != 0;
@@ -243,7 +270,8 @@ int vtk_set_flag(const char* name, int value) {
   VTK_REQUIRE(name, "vtk_set_flag: null name");
   if (!strcmp(name, "pdl")) { g_flag_pdl = value ? 1 : 0; return VTK_OK; }
   if (!strcmp(name, "gemm_splitk")) { g_flag_splitk = value ? 1 : 0; return VTK_OK; }
-  set_error("vtk_set_flag: unknown flag '%s' (pdl, gemm_splitk)", name);
+  if (!strcmp(name, "reserve_sms")) { g_flag_reserve = value < 0 ? 0 : value; return VTK_OK; }
+  set_error("vtk_set_flag: unknown flag '%s' (pdl, gemm_splitk, reserve_sms)", name);
   return VTK_ERR_BAD_ARG;
 }
 

@@ -975,17 +975,11 @@ static int launch_attention_persist(const AttnArgs& a, cudaStream_t stream) {
   static const int ptmem = getenv("VTK_ATTN_PTMEM") ? atoi(getenv("VTK_ATTN_PTMEM")) : 1;
   auto kern = packed ? (ptmem ? attn_persist_kernel<64, true, true> : attn_persist_kernel<64, true, false>)
                      : (ptmem ? attn_persist_kernel<64, false, true> : attn_persist_kernel<64, false, false>);
-  static bool attr_set[4] = {false, false, false, false};
-  const int ai = (packed ? 1 : 0) + (ptmem ? 2 : 0);
-  if (!attr_set[ai]) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES), "cudaFuncSetAttribute(attn_persist)"))
-      return -1;
-    attr_set[ai] = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), S::SMEM_BYTES, "cudaFuncSetAttribute(attn_persist)")) return -1;
   const int qtiles = (a.N + ATT_BQ - 1) / ATT_BQ;
   const long long total = packed ? (long long)a.grp_cap * a.heads : (long long)a.B * a.heads * qtiles;
   if (total >= (1ll << 31)) { set_error("attention: too many work items"); return -2; }
-  const int grid = (int)std::min<long long>(total, 2ll * num_sms());
+  const int grid = (int)std::min<long long>(total, 2ll * usable_sms());
   const cudaError_t lerr = launch_k(kern, dim3(grid), dim3(192), S::SMEM_BYTES, stream, tmQ, tmK, tmV, tmO, p, (int)total, qtiles);
   if (lerr != cudaSuccess) return check_cuda(lerr, "attention (persistent) launch");
   if (prof_mode) {
@@ -1034,13 +1028,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t stream) {
     p.prof = d_prof;
   }
   auto kern = attn_kernel<DH, NQ>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES),
-                   "cudaFuncSetAttribute(attn)"))
-      return -1;
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), S::SMEM_BYTES, "cudaFuncSetAttribute(attn)")) return -1;
   dim3 grid((a.N + NQ * ATT_BQ - 1) / (NQ * ATT_BQ), a.heads, a.B);
   if (packed) grid = dim3((unsigned)a.grp_cap, a.heads, 1);
   const cudaError_t lerr = launch_k(kern, grid, dim3(S::THREADS), S::SMEM_BYTES, stream, tmQ, tmK, tmV, tmO, p);

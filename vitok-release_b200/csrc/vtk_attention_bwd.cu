@@ -357,12 +357,8 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t stream) {
   p.scale_log2 = (float)((1.0 / sqrt((double)a.d)) * 1.4426950408889634);
   auto k0 = attn_bwd_kernel<DH, 0>;
   auto k1 = attn_bwd_kernel<DH, 1>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES), "attr(attn_bwd0)")) return -1;
-    if (check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES), "attr(attn_bwd1)")) return -1;
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(k0), S::SMEM_BYTES, "attr(attn_bwd0)")) return -1;
+  if (ensure_max_smem(reinterpret_cast<const void*>(k1), S::SMEM_BYTES, "attr(attn_bwd1)")) return -1;
   dim3 grid((a.N + BWD_T - 1) / BWD_T, a.heads, a.B);
   k0<<<grid, 384, S::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, p);
   if (check_cuda(cudaGetLastError(), "attention bwd (dK/dV) launch")) return -1;

@@ -23,6 +23,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "vtk_common.cuh"
 #include "vtk_kernels.h"
 
@@ -725,7 +727,7 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
     sc.gm_cap = (int)(gm < 1 ? 1 : gm > (1 << 20) ? (1 << 20) : gm);
   }
   sc.split = (allow_split && BN >= 256) ? 1 : 0;
-  const int sms = num_sms();
+  const int sms = usable_sms();
   sc.setup(a.M, sms);   // a.M is the row capacity when a.m_dev is given (the kernel redoes this with the device value)
   const int grid = sc.workers;
   // output tensor maps for the TMA-store epilogues (box = 32 cols x 32 rows, SWIZZLE_64B)
@@ -739,13 +741,7 @@ static int launch_gemm_t(const GemmArgs& a, bool allow_split, cudaStream_t strea
   }
   const int smem_bytes = S::smem_bytes(kStaged ? NEPI : 0);
   auto kern = gemm_kernel<BN, EPI, NEPI>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
-                   "cudaFuncSetAttribute(gemm)"))
-      return -1;
-    attr_set = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), smem_bytes, "cudaFuncSetAttribute(gemm)")) return -1;
   return check_cuda(launch_k(kern, dim3(grid), dim3(128 + 32 * NEPI), smem_bytes, stream, tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc, a.epi),
                     "gemm launch");
 }
@@ -1081,9 +1077,10 @@ static int launch_gemm2_sk(const GemmArgs& a, const CUtensorMap& tmA, const CUte
   sc.split = 0;
   const int smem_bytes = g2_smem_bytes(G2_STAGES, NEPI);
   auto kern = gemm2_kernel<EPI_RESID, NEPI, G2_STAGES, false, false, 0, 4, true>;
-  static int max_clusters = 0;
+  static int max_clusters_dev[64] = {0};
+  int& max_clusters = max_clusters_dev[current_device() & 63];
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), smem_bytes, "cudaFuncSetAttribute(gemm2 split-K)")) return -1;
   if (max_clusters == 0) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute(gemm2 split-K)")) return -1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(128 + 32 * NEPI); cfg.dynamicSmemBytes = smem_bytes;
     cudaLaunchAttribute at;
@@ -1111,10 +1108,11 @@ static int launch_gemm2_cl4(const GemmArgs& a, const CUtensorMap& tmA, const CUt
   constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
   const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
   auto kern = a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true, 0, 4> : gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 0, 4>;
-  static int max_clusters[2] = {0, 0};
+  static int max_clusters_dev[64][2] = {{0, 0}};
+  int (&max_clusters)[2] = max_clusters_dev[current_device() & 63];
   const int vi = a.fp8 ? 1 : 0;
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), smem_bytes, "cudaFuncSetAttribute(gemm2 cl4)")) return -1;
   if (max_clusters[vi] == 0) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute(gemm2 cl4)")) return -1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(128 + 32 * NEPI); cfg.dynamicSmemBytes = smem_bytes;
     cudaLaunchAttribute at;
@@ -1125,9 +1123,10 @@ static int launch_gemm2_cl4(const GemmArgs& a, const CUtensorMap& tmA, const CUt
     if (n <= 0) { set_error("gemm2 cl4: no 4-CTA cluster fits on this device"); return -1; }
     max_clusters[vi] = n;
   }
-  sc.setup(a.M, max_clusters[vi]);
+  const int avail = std::min(max_clusters[vi], std::max(1, usable_sms() / 4));   // (reserve_sms: room for a concurrent collective)
+  sc.setup(a.M, avail);
   const int big = sc.num_m * sc.num_n;
-  const int clusters = big < max_clusters[vi] ? big : max_clusters[vi];
+  const int clusters = big < avail ? big : avail;
   CUtensorMap tmO0 = tmA, tmO1 = tmA;
   if (EPI == EPI_QKV_SWIGLU) {
     if (encode_tmap_bf16(&tmO0, a.epi.qkv, (uint64_t)3 * a.epi.D, (uint64_t)a.M, (uint64_t)a.epi.ld_qkv, 32, 32, 64)) return -1;
@@ -1189,7 +1188,7 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
   const bool cl4 = (cl4_mode == 1 || (cl4_mode == -1 && (EPI == EPI_RESID || EPI == EPI_BIAS) && tiles4 >= num_sms() / 4 - 4)) && !a.trans &&
                    !a.epi.prof && a.M > 2 * BM;
   if (cl4) return launch_gemm2_cl4<EPI, NEPI, G2_STAGES>(a, tmA, tmB, sc, stream);
-  const int pairs = num_sms() / 2;
+  const int pairs = usable_sms() / 2;
   sc.setup(a.M, pairs);
   const int clusters = sc.workers;
   CUtensorMap tmO0 = tmA, tmO1 = tmA;
@@ -1207,13 +1206,7 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
               : a.trans == 2 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 2>
               : a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true>
               : a.epi.prof ? gemm2_kernel<EPI, NEPI, G2_STAGES, true> : gemm2_kernel<EPI, NEPI, G2_STAGES, false>;
-  static bool attr_set[5] = {false, false, false, false, false};
-  if (!attr_set[a.trans == 3 ? 4 : a.trans ? 3 : a.fp8 ? 2 : a.epi.prof ? 1 : 0]) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
-                   "cudaFuncSetAttribute(gemm2)"))
-      return -1;
-    attr_set[a.trans == 3 ? 4 : a.trans ? 3 : a.fp8 ? 2 : a.epi.prof ? 1 : 0] = true;
-  }
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), smem_bytes, "cudaFuncSetAttribute(gemm2)")) return -1;
   return check_cuda(launch_k(kern, dim3(2 * clusters), dim3(128 + 32 * NEPI), smem_bytes, stream, tmA, tmB, tmO0, tmO1, a.M, a.N, a.K, sc,
                              a.epi), "gemm2 launch");
 }

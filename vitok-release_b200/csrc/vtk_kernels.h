@@ -15,11 +15,16 @@ typedef __nv_bfloat16 bf16;
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+int usable_sms();   // num_sms() minus the "reserve_sms" flag: grid size of the persistent kernels
 
 // Kernel launch with programmatic dependent launch (PDL, vtk_common.cuh: pdl_wait / pdl_trigger): the kernel's prologue
 // overlaps the tail of the previous kernel of the stream.  Works inside CUDA-graph capture (programmatic edges).  Only for
 // kernels that call pdl_wait() before their first access to global memory.  VTK_PDL=0 launches them fully serialised.
 bool pdl_enabled();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, and one process may drive
+// several GPUs (a model on cuda:1 while cuda:0 is current, torch DataParallel-style callers)
+int ensure_max_smem(const void* kern, int bytes, const char* what);
+int current_device();
 // runtime switches (include/vitok_b200.h: vtk_set_flag)
 int flag_gemm_splitk();
 template <typename... KArgs, typename... Args>

@@ -24,7 +24,8 @@ __device__ __forceinline__ float norm_u8(uint32_t u) {
 // norm_u8 by patchify_selftest_kernel / tests/test_gpu_pp.py).  3 FMA-pipe instructions instead of a shared-memory lookup whose
 // random bank conflicts bounded the uint8 front end at half of HBM bandwidth.
 __device__ __forceinline__ float norm_u8_fast(uint32_t u) {
-  const float uf = (float)u, rcp = 0.0039215688593685627f;   // RN(1 / 255)
+  // float(u) for u < 2^23 without the conversion pipe: 2^23 + u is exact in fp32, subtract 2^23 again
+  const float uf = __fsub_rn(__uint_as_float(0x4B000000u | u), 8388608.0f), rcp = 0.0039215688593685627f;   // RN(1 / 255)
   const float q0 = __fmul_rn(uf, rcp);
   const float rem = __fmaf_rn(-q0, 255.0f, uf);
   const float q = __fmaf_rn(rem, rcp, q0);
@@ -191,50 +192,62 @@ __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyArgs a) {
   }
 }
 
-// uint8 HWC input, row-coalesced: thread <-> 4 consecutive pixels of one image row (12 contiguous bytes; a warp reads 384 contiguous
-// bytes instead of eight 48-byte pieces), normalised arithmetically and written as three 4-element chunks (one per channel plane of the
-// token; the 4 lanes of a patch row fill one 32-byte sector).  Work item = (image, patch row r, 4-row group, x4); tokens beyond the
-// image's grid (padding tokens) and the index arrays are written by a second pass over tokens in the same kernel.
+// uint8 HWC input, row-coalesced: thread <-> 16 consecutive pixels of one image row (48 contiguous bytes = three 16-byte loads; a warp
+// reads 1.5 KB of a row instead of eight 48-byte pieces), normalised arithmetically and written as 16-element runs of the three channel
+// planes of the token (64 B of fp32 / 32 B of bf16 each: whole sectors).  Work item = (image, y, 16-pixel group) over the bounding box of
+// the batch; tokens beyond an image's grid (padding tokens) and the index arrays are written by a second pass over tokens.
 template <typename OutT, int PT>
-__global__ void __launch_bounds__(256) patchify_u8_rows_kernel(const PatchifyArgs a, const int max_w4, const int max_rows) {
+__global__ void __launch_bounds__(256) patchify_u8_rows_kernel(const PatchifyArgs a, const int max_w16, const int max_rows) {
   pdl_wait();
   pdl_trigger();
   constexpr int p = PT, pp = p * p, P = 3 * pp;
   const int T = a.max_tokens;
-  // ---- pass 1: pixels.  idx -> (b, y, x4) over the bounding box [max_rows x max_w4] of the batch (threads outside an image idle)
-  const long long per_img = (long long)max_rows * max_w4;
+  // ---- pass 1: pixels.  idx -> (b, y, x16) over the bounding box [max_rows x max_w16] of the batch (threads outside an image idle)
+  const long long per_img = (long long)max_rows * max_w16;
   const long long total = per_img * a.B;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(idx / per_img);
     const int rem = (int)(idx - (long long)b * per_img);
-    const int y = rem / max_w4, x = (rem - y * max_w4) << 2;
+    const int y = rem / max_w16, x = (rem - y * max_w16) << 4;
     const int H = (int)a.img_table[3 * b + 1], W = (int)a.img_table[3 * b + 2];
     const int gr = (H + p - 1) / p, gc = (W + p - 1) / p;
     if (gr * gc > T || y >= gr * p || x >= gc * p) continue;        // outside this image's patch grid
     const int r = y / p, dy = y - r * p, c = x / p, dx = x - c * p;
     OutT* dst = reinterpret_cast<OutT*>(a.patches) + ((long long)b * T + r * gc + c) * P + dy * p + dx;
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;   // zero padding to the patch boundary (applied AFTER normalize)
+    uint32_t w[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) w[k] = 0u;
+    int np = 0;                                                      // pixels of this run inside the image
     if (y < H && x < W) {
+      np = min(16, W - x);
       const uint8_t* src = reinterpret_cast<const uint8_t*>(a.images) + a.img_table[3 * b] + ((long long)y * W + x) * 3;
-      uint32_t w0 = 0, w1 = 0, w2 = 0;
-      const int np = min(4, W - x);
-      if (np == 4 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
-        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-        w0 = __ldg(s32); w1 = __ldg(s32 + 1); w2 = __ldg(s32 + 2);
+      if (np == 16 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(src)), q1 = __ldg(reinterpret_cast<const uint4*>(src) + 1),
+                    q2 = __ldg(reinterpret_cast<const uint4*>(src) + 2);
+        w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w; w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+        w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+      } else if (np == 16 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t*>(src) + k);
       } else {
-        for (int k = 0; k < np * 3; ++k) {
-          const uint32_t u = src[k];
-          if (k < 4) w0 |= u << (8 * k); else if (k < 8) w1 |= u << (8 * (k - 4)); else w2 |= u << (8 * (k - 8));
-        }
+#pragma unroll
+        for (int k = 0; k < 48; ++k)        // (fully unrolled: w[] must stay in registers)
+          if (k < np * 3) w[k >> 2] |= (uint32_t)src[k] << (8 * (k & 3));
       }
-      v0.x = norm_u8_fast(w0 & 255); v1.x = norm_u8_fast((w0 >> 8) & 255); v2.x = norm_u8_fast((w0 >> 16) & 255);
-      if (np > 1) { v0.y = norm_u8_fast(w0 >> 24); v1.y = norm_u8_fast(w1 & 255); v2.y = norm_u8_fast((w1 >> 8) & 255); }
-      if (np > 2) { v0.z = norm_u8_fast((w1 >> 16) & 255); v1.z = norm_u8_fast(w1 >> 24); v2.z = norm_u8_fast(w2 & 255); }
-      if (np > 3) { v0.w = norm_u8_fast((w2 >> 8) & 255); v1.w = norm_u8_fast((w2 >> 16) & 255); v2.w = norm_u8_fast(w2 >> 24); }
     }
-    store4(dst, v0);
-    store4(dst + pp, v1);
-    store4(dst + 2 * pp, v2);
+    // byte i of the run = pixel i / 3, channel i % 3; pixels at or beyond np stay 0.0 (zero padding is applied AFTER normalize)
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v[16];
+#pragma unroll
+      for (int px = 0; px < 16; ++px) {
+        const int i = 3 * px + ch;
+        const float f = norm_u8_fast((w[i >> 2] >> (8 * (i & 3))) & 255u);
+        v[px] = px < np ? f : 0.f;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) store4(dst + ch * pp + 4 * g, make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
+    }
   }
   // ---- pass 2: per token -- index arrays, metadata, and the zero rows of padding tokens (one warp per token)
   const int lane = threadIdx.x & 31;
@@ -281,7 +294,7 @@ int launch_patchify(const PatchifyArgs& a, cudaStream_t stream) {
   if (a.in_dtype == 1 && (a.patch == 16 || a.patch == 32) && a.max_h > 0 && a.max_w > 0) {
     // uint8 HWC front end: the row-coalesced kernel over the batch's bounding box (the caller knows every image size)
     const int p = a.patch;
-    const int max_rows = (a.max_h + p - 1) / p * p, max_w4 = ((a.max_w + p - 1) / p * p) >> 2;
+    const int max_rows = (a.max_h + p - 1) / p * p, max_w4 = ((a.max_w + p - 1) / p * p) >> 4;   // 16-pixel runs per bounding-box row
     const long long total = (long long)a.B * max_rows * max_w4;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 8 * 16;
@@ -421,76 +434,108 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const UnpatchifyArgs a)
   }
 }
 
-// Row-coalesced variant (compile-time patch size): thread <-> 4 consecutive pixels of FOUR consecutive canvas rows of one channel
-// plane.  A warp writes 128 contiguous pixels per row (128 B of uint8, 256 B of bf16, 512 B of fp32) -- the cell-per-warp kernel above
-// writes p-pixel pieces (16 bytes of uint8: half a sector) -- and reads the owning tokens' elements as 4-pixel chunks, four lanes per
-// 32-byte sector (bf16 patches, p = 16).  The four rows lie in the same patch row, so one cell-map lookup serves four loads that are
-// all issued before the first store.
-template <typename T, int PT>
+// Row-coalesced variant (compile-time patch size): thread <-> PXT consecutive pixels of FOUR consecutive canvas rows of one channel
+// plane, PXT chosen so that every store is 16 bytes (16 pixels of uint8, 8 of bf16, 4 of fp32).  A warp writes 512 contiguous bytes per
+// row -- the cell-per-warp kernel above writes p-pixel pieces (16 bytes of uint8: half a sector) -- and reads the owning tokens'
+// elements as 16-byte chunks.  The four rows lie in the same patch row, so one cell-map lookup serves all the loads, which are issued
+// before the first store.
+template <typename T, int PT, int PXT, bool U8OUT>
 __global__ void __launch_bounds__(256) unpatchify_rows_kernel(const UnpatchifyArgs a) {
   pdl_wait();
   pdl_trigger();
   constexpr int p = PT, pp = p * p, P = 3 * pp;
-  const int Hc = a.gy * p, Wc = a.gx * p, W4 = Wc >> 2, R4 = Hc >> 2;
+  constexpr int LV = PXT * (int)sizeof(T) / 16;     // 16-byte loads per row
+  static_assert(PT % PXT == 0 && LV >= 1, "unpatchify_rows: PXT must divide the patch size and fill a 16-byte load");
+  const int Hc = a.gy * p, Wc = a.gx * p, WX = Wc / PXT, R4 = Hc >> 2;
   const int cells_per_img = a.gy * a.gx;
   const bool bfm = sizeof(T) == 2;
-  const long long total = (long long)a.B * 3 * R4 * W4;
+  const long long total = (long long)a.B * 3 * R4 * WX;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int x4 = (int)(idx % W4);
-    const long long t1 = idx / W4;
+    const int xq = (int)(idx % WX);
+    const long long t1 = idx / WX;
     const int yq = (int)(t1 % R4);
     const int t2 = (int)(t1 / R4);
     const int ch = t2 % 3, b = t2 / 3;
-    const int y0 = yq << 2, x = x4 << 2;
+    const int y0 = yq << 2, x = xq * PXT;
     const int r = y0 / p, dy0 = y0 - r * p, c = x / p, dx = x - c * p;
     const int cell = r * a.gx + c;
     // token 0 is re-scattered into cell 0 after the main scatter (ops.py:332-333)
     const int tok = (cell == 0) ? (a.patch_mask[(long long)b * a.N] ? 0 : -1) : a.cell_map[(long long)b * cells_per_img + cell];
-    float v[4][4];
+    uint4 raw[4][LV];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int l = 0; l < LV; ++l) raw[k][l] = make_uint4(0u, 0u, 0u, 0u);     // (0.0 in both dtypes)
     if (tok >= 0) {
       const T* src = reinterpret_cast<const T*>(a.patches) + ((long long)b * a.N + tok) * P + ch * pp + dy0 * p + dx;
-      if (sizeof(T) == 4) {
-        float4 f[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) f[k] = __ldg(reinterpret_cast<const float4*>(src + k * p));
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { v[k][0] = f[k].x; v[k][1] = f[k].y; v[k][2] = f[k].z; v[k][3] = f[k].w; }
-      } else {
-        uint2 u[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint2*>(src + k * p));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { v[k][0] = bf16_lo(u[k].x); v[k][1] = bf16_hi(u[k].x); v[k][2] = bf16_lo(u[k].y); v[k][3] = bf16_hi(u[k].y); }
-      }
+        for (int l = 0; l < LV; ++l) raw[k][l] = __ldg(reinterpret_cast<const uint4*>(src + k * p) + l);
     }
     const long long o = (((long long)b * 3 + ch) * Hc + y0) * Wc + x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (a.out_format == 1) {
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.out) + o + (long long)k * Wc) = to_u8x4(v[k], bfm);
-      } else {
-        float w[4];
+      float v[PXT];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) w[e] = convert_px(v[k][e], a.out_format, bfm);
-        if (sizeof(T) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o + (long long)k * Wc) = make_float4(w[0], w[1], w[2], w[3]);
-        else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.out) + o + (long long)k * Wc) = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
+      for (int l = 0; l < LV; ++l) {
+        const uint32_t w[4] = {raw[k][l].x, raw[k][l].y, raw[k][l].z, raw[k][l].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (sizeof(T) == 4) v[4 * l + e] = __uint_as_float(w[e]);
+          else { v[8 * l + 2 * e] = bf16_lo(w[e]); v[8 * l + 2 * e + 1] = bf16_hi(w[e]); }
+        }
+      }
+      if (U8OUT) {
+        uint32_t q[PXT / 4];
+#pragma unroll
+        for (int g = 0; g < PXT / 4; ++g) {
+          const float f4[4] = {v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]};
+          q[g] = to_u8x4(f4, bfm);
+        }
+        uint8_t* op = reinterpret_cast<uint8_t*>(a.out) + o + (long long)k * Wc;
+        if (PXT == 16) *reinterpret_cast<uint4*>(op) = make_uint4(q[0], q[1], q[2 % (PXT / 4)], q[3 % (PXT / 4)]);
+        else
+#pragma unroll
+          for (int g = 0; g < PXT / 4; ++g) *reinterpret_cast<uint32_t*>(op + 4 * g) = q[g];
+      } else {
+#pragma unroll
+        for (int e = 0; e < PXT; ++e) v[e] = convert_px(v[e], a.out_format, bfm);
+        if (sizeof(T) == 4) {
+          float* op = reinterpret_cast<float*>(a.out) + o + (long long)k * Wc;
+#pragma unroll
+          for (int g = 0; g < PXT / 4; ++g) *reinterpret_cast<float4*>(op + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        } else {
+          bf16* op = reinterpret_cast<bf16*>(a.out) + o + (long long)k * Wc;
+#pragma unroll
+          for (int g = 0; g < PXT / 8; ++g)
+            *reinterpret_cast<uint4*>(op + 8 * g) = make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                                                               pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+        }
       }
     }
   }
+}
+
+template <typename T, int PT>
+static void unpatchify_rows_launch(const UnpatchifyArgs& a, cudaStream_t stream) {
+  constexpr int PX_SAME = 16 / (int)sizeof(T);     // same-dtype output: 16-byte stores
+  const bool u8 = a.out_format == 1;
+  const int pxt = u8 ? 16 : PX_SAME;
+  const long long total = (long long)a.B * 3 * (a.gy * PT / 4) * (a.gx * PT / pxt);
+  long long rb = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8 * 16;
+  if (rb > cap) rb = cap;
+  if (u8) (void)launch_k(unpatchify_rows_kernel<T, PT, 16, true>, dim3((unsigned)rb), dim3(256), 0, stream, a);
+  else (void)launch_k(unpatchify_rows_kernel<T, PT, PX_SAME, false>, dim3((unsigned)rb), dim3(256), 0, stream, a);
 }
 
 template <typename T>
 static void unpatchify_dispatch(const UnpatchifyArgs& a, int blocks, cudaStream_t stream) {
   static const int rows_mode = getenv("VTK_UNPATCHIFY_ROWS") ? atoi(getenv("VTK_UNPATCHIFY_ROWS")) : 1;   // 0: cell-per-warp kernel (A/B)
   if (rows_mode && (a.patch == 16 || a.patch == 32)) {
-    const long long total = (long long)a.B * 3 * (a.gy * a.patch / 4) * (a.gx * a.patch / 4);
-    long long rb = (total + 255) / 256;
-    const long long cap = (long long)num_sms() * 8 * 16;
-    if (rb > cap) rb = cap;
-    if (a.patch == 16) (void)launch_k(unpatchify_rows_kernel<T, 16>, dim3((unsigned)rb), dim3(256), 0, stream, a);
-    else (void)launch_k(unpatchify_rows_kernel<T, 32>, dim3((unsigned)rb), dim3(256), 0, stream, a);
+    if (a.patch == 16) unpatchify_rows_launch<T, 16>(a, stream);
+    else unpatchify_rows_launch<T, 32>(a, stream);
     return;
   }
   if (a.patch == 16) (void)launch_k(unpatchify_kernel<T, 16>, dim3(blocks), dim3(256), 0, stream, a);

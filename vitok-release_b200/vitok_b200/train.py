@@ -139,11 +139,15 @@ class _GradSync:
         self.pending, self.small = [], []
 
 
-def enable_grad_sync(model, process_group=None, broadcast_parameters: bool = True):
+def enable_grad_sync(model, process_group=None, broadcast_parameters: bool = True, reserve_sms: Optional[int] = None):
     """Turn on overlapped data-parallel gradient averaging for ``model`` (see _GradSync).  Call once after
     ``torch.distributed.init_process_group``; do NOT also wrap the model in DistributedDataParallel.  With
-    ``broadcast_parameters`` the parameters of rank 0 are copied to every rank first (what DDP's constructor does)."""
+    ``broadcast_parameters`` the parameters of rank 0 are copied to every rank first (what DDP's constructor does).
+    ``reserve_sms``: SMs the persistent GEMM / attention kernels leave free for NCCL's all-reduce CTAs, which run next to the
+    backward kernels (include/vitok_b200.h: vtk_set_flag "reserve_sms"); None keeps the process-wide setting."""
     import torch.distributed as dist
+    if reserve_sms is not None:
+        _lib.set_flag("reserve_sms", int(reserve_sms))
     if broadcast_parameters and dist.get_world_size(process_group) > 1:
         with torch.no_grad():
             for p in model.parameters():
