@@ -155,7 +155,7 @@ def test_bad_args_raise(L):
         L.linear(a.cpu(), w.cpu())
 
 
-@pytest.mark.parametrize("K,M,N", [(1000, 256, 512), (4096, 3072, 1024), (333, 776, 136), (64, 128, 64), (8192, 1024, 2736)])
+@pytest.mark.parametrize("K,M,N", [(1000, 256, 512), (4096, 3072, 1024), (333, 776, 136), (64, 128, 64), (8192, 1024, 2736), (2048, 4648, 1000)])
 def test_linear_tn_transposed_operands(K, M, N):
     """out = At^T Bt with both operands given transposed (the training step's weight gradient dW = dY^T X): the tensor core
     reads the [k, column] tiles MN-major, no transpose pass.  Operands are column slices of wider buffers (row pitch > width)."""
@@ -168,7 +168,7 @@ def test_linear_tn_transposed_operands(K, M, N):
     report(f"linear_tn K={K} M={M} N={N}", out, ref, rel_fro=4e-3)
 
 
-@pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (8192, 1024, 3760), (300, 136, 776), (4096, 11280, 3072)])
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (8192, 1024, 3760), (300, 136, 776), (4096, 11280, 3072), (4616, 1032, 1024)])
 def test_linear_nn_b_transposed(M, N, K):
     """out = A Bt with B given as [K, N] row-major (the data gradient dX = dY W, W used as stored)."""
     from vitok_b200 import _lib

@@ -467,8 +467,14 @@ def test_activation_checkpointing_is_bit_identical(ck):
         a, b = res[0][2][n], res[ck][2][n]
         if a.ndim >= 2:
             assert torch.equal(a, b), n                                          # GEMM-produced gradients: bit-identical
-        else:                                                                    # norm weights / gamma / biases: fp32 atomic column sums
-            assert _rel(a, b) <= 1e-4, (n, _rel(a, b))
+        else:
+            # norm weights / gamma / biases: fp32 atomic column sums whose order differs from run to run, then ONE rounding to the bf16
+            # gradient -- a sum that lands next to a rounding boundary may come out one bf16 ulp (2^-8 relative) away, so: every
+            # element within one ulp (+ a floor of 2^-8 of the vector's largest element, for sums that cancel to ~0), few of them
+            fa, fb = a.float(), b.float()
+            tol = 2.0 ** -7 * torch.maximum(fa.abs(), fb.abs()) + 2.0 ** -8 * fa.abs().max()
+            assert bool(((fa - fb).abs() <= tol).all()), (n, float((fa - fb).abs().max()))
+            assert _rel(a, b) <= 2e-3, (n, _rel(a, b))
     print(f"[parity] activations held after forward: checkpoint=0 {res[0][3] / 2**20:.1f} MiB, checkpoint={ck} {res[ck][3] / 2**20:.1f} MiB")
     assert res[ck][3] < (0.45 if ck == 1 else 0.8) * res[0][3]
 

@@ -897,8 +897,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int kc = second_b ? kb * BKE - epi.k_split : kb * BKE;
           if (CL == 4 && !SK) {   // this CTA fetches half of its B share and multicasts it to its counterpart in the other pair
             const int nb = (int)pair * (hw >> 1);
-            tma_load_2d_2cta_mc(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), tb, fb, kc, n0 + (int)rank * hw + nb,
-                                (uint16_t)((1u << rank) | (1u << (rank + 2))));
+            if (TRANS & 2) tma_load_2d_2cta_mc(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, n0 + (int)rank * hw + nb, kb * BK,
+                                               (uint16_t)((1u << rank) | (1u << (rank + 2))));   // one [64 k-rows x 64 columns] box
+            else tma_load_2d_2cta_mc(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), tb, fb, kc, n0 + (int)rank * hw + nb,
+                                     (uint16_t)((1u << rank) | (1u << (rank + 2))));
           } else {
             for (int nb = 0; nb < hw; nb += 64) {
               if (TRANS & 2) tma_load_2d_2cta(sB + s * G2_B_STAGE_BYTES + nb * (BK * 2), &tmB, fb, n0 + (int)rank * hw + nb, kb * BK);
@@ -1108,9 +1110,13 @@ static int launch_gemm2_cl4(const GemmArgs& a, const CUtensorMap& tmA, const CUt
   constexpr bool kStaged = (EPI == EPI_QKV_SWIGLU || EPI == EPI_RESID);
   const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
   auto kern = a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true, 0, 4> : gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 0, 4>;
-  static int max_clusters_dev[64][2] = {{0, 0}};
-  int (&max_clusters)[2] = max_clusters_dev[current_device() & 63];
-  const int vi = a.fp8 ? 1 : 0;
+  if constexpr (EPI == EPI_BIAS) {   // transposed-operand variants (the training step's data / weight gradients)
+    if (a.trans == 3) kern = gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 3, 4>;
+    else if (a.trans == 2) kern = gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 2, 4>;
+  }
+  static int max_clusters_dev[64][4] = {{0, 0, 0, 0}};
+  int (&max_clusters)[4] = max_clusters_dev[current_device() & 63];
+  const int vi = a.fp8 ? 1 : a.trans == 3 ? 3 : a.trans == 2 ? 2 : 0;
   if (ensure_max_smem(reinterpret_cast<const void*>(kern), smem_bytes, "cudaFuncSetAttribute(gemm2 cl4)")) return -1;
   if (max_clusters[vi] == 0) {
     cudaLaunchConfig_t cfg = {};
@@ -1185,8 +1191,11 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
   // ... and only when the 512-row super tiles fill the ~33 co-resident clusters at least once: below that (the small per-GPU
   // batches of a strong-scaled job) the pair kernel with half-width tiles keeps more SMs busy
   const long long tiles4 = (long long)((a.M + 4 * BM - 1) / (4 * BM)) * sc.num_n;
-  const bool cl4 = (cl4_mode == 1 || (cl4_mode == -1 && (EPI == EPI_RESID || EPI == EPI_BIAS) && tiles4 >= num_sms() / 4 - 4)) && !a.trans &&
-                   !a.epi.prof && a.M > 2 * BM;
+  // ... the transposed-operand variants (data / weight gradients of the training step) included: alone wgrad 1333-1365 -> 1414-1441 TF/s,
+  // dgrad 1395 -> 1439 TF/s, 5B step 302.8 -> 296.3 ms (VTK_GEMM_CL4_TRANS=0 keeps them on CTA pairs)
+  static const int cl4_trans = env_int("VTK_GEMM_CL4_TRANS", 1);
+  const bool cl4 = (cl4_mode == 1 || (cl4_mode == -1 && (EPI == EPI_RESID || EPI == EPI_BIAS) && tiles4 >= num_sms() / 4 - 4)) &&
+                   (!a.trans || (cl4_trans && EPI == EPI_BIAS)) && !a.epi.prof && a.M > 2 * BM;
   if (cl4) return launch_gemm2_cl4<EPI, NEPI, G2_STAGES>(a, tmA, tmB, sc, stream);
   const int pairs = usable_sms() / 2;
   sc.setup(a.M, pairs);
@@ -1202,8 +1211,8 @@ static int launch_gemm2_s(const GemmArgs& a, cudaStream_t stream) {
     if (encode_tmap_bf16_sw128(&tmO1, a.B2, (uint64_t)(a.K - a.epi.k_split), (uint64_t)a.b_rows, (uint64_t)a.ldb2, 64)) return -1;
   }
   const int smem_bytes = g2_smem_bytes(G2_STAGES, kStaged ? NEPI : 0);
-  auto kern = a.trans == 3 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 3>
-              : a.trans == 2 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 2>
+  auto kern = a.trans == 3 ? (a.epi.prof ? gemm2_kernel<EPI, NEPI, G2_STAGES, true, false, 3> : gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 3>)
+              : a.trans == 2 ? (a.epi.prof ? gemm2_kernel<EPI, NEPI, G2_STAGES, true, false, 2> : gemm2_kernel<EPI, NEPI, G2_STAGES, false, false, 2>)
               : a.fp8 ? gemm2_kernel<EPI, NEPI, G2_STAGES, false, true>
               : a.epi.prof ? gemm2_kernel<EPI, NEPI, G2_STAGES, true> : gemm2_kernel<EPI, NEPI, G2_STAGES, false>;
   if (ensure_max_smem(reinterpret_cast<const void*>(kern), smem_bytes, "cudaFuncSetAttribute(gemm2)")) return -1;

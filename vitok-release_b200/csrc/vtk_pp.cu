@@ -279,6 +279,208 @@ __global__ void __launch_bounds__(256) patchify_u8_rows_kernel(const PatchifyArg
   }
 }
 
+// uint8 HWC input, staged through shared memory (round 2, second rewrite).  The row kernel above reads coalesced but every one of its
+// store instructions touches 32 different 128-byte lines (a lane owns one image row of one token = 16 elements of a plane, the next lane
+// the next TOKEN), and the load/store unit needs one pass per line: ncu 1.8 TB/s, LSU wavefronts 71 % of peak.  Here a persistent CTA walks
+// STRIPS = the PT image rows of one token row x up to 256 pixels:
+//   phase 1: the strip's PT row segments (<= 768 contiguous bytes each) land in shared memory -- one cp.async.bulk per row, completing on
+//            an mbarrier, when every segment is 16-byte aligned (all fixed-size configs); otherwise 16-byte loads from the aligned-down
+//            address (edge vectors byte by byte, nothing outside [row start, row end) is ever read), the row's misalignment is kept;
+//   phase 2: a lane produces 16 output bytes (8 bf16 / 4 fp32 consecutive pixels of one plane row); lanes are ordered along the token's
+//            plane, so a warp-wide store writes 512 CONTIGUOUS bytes.  The 3 x PXT source bytes are read as 32-bit words (+ one funnel
+//            shift per word for unaligned rows) and normalised through a 256-entry table that is replicated PER LANE
+//            (lut[byte][lane]: every lane reads its own bank, so the random byte values cannot collide -- the single 1 KB table of the
+//            first uint8 kernel was bounded by exactly those conflicts, and the arithmetic form costs 6 FMA-pipe instructions per byte,
+//            which made a first version of this kernel issue-bound at 2.8 TB/s): shift + mask-or + LDS = 3 instructions per byte.
+//            The table holds norm_u8 = the reference's own operation order (ops.py:140-161), bit-exact by construction.
+// Pixels outside the image (patch padding) are 0.0, applied after normalisation as in the reference (ops.py:235-238).
+static constexpr int STRIP_CW = 256;                       // pixels per strip
+static constexpr int STRIP_ROW_BYTES = STRIP_CW * 3 + 16;  // 49 vectors: 768 bytes + up to 15 of misalignment
+template <int PT>
+static constexpr int strip_smem_bytes() { return 256 * 32 * 4 + PT * STRIP_ROW_BYTES + 16; }
+template <typename OutT, int PT>
+__global__ void __launch_bounds__(256) patchify_u8_strip_kernel(const PatchifyArgs a, const int max_gr, const int nchunk) {
+  constexpr int p = PT, pp = p * p, P = 3 * pp;
+  constexpr int PXT = 16 / (int)sizeof(OutT);            // pixels per lane
+  constexpr int SEG = PT / PXT;                          // lanes per plane row
+  constexpr int UPT = PT * SEG;                          // lanes (work units) per token: 32 .. 256, a multiple of 32
+  constexpr int NW = (3 * PXT) / 4;                      // source words per unit: 6 / 3
+  constexpr int NVEC = STRIP_ROW_BYTES / 16;             // 49
+  extern __shared__ __align__(128) uint8_t strip_smem[];
+  float* lut = reinterpret_cast<float*>(strip_smem);     // [256][32]
+  uint8_t* strip = strip_smem + 256 * 32 * 4;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int mis_s[PT];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  {
+    const float v = norm_u8((uint32_t)tid);   // this warp's 32 entries, one per lane; every lane then writes its own column (bank)
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) lut[((tid & ~31) + j) * 32 + lane] = __shfl_sync(0xffffffffu, v, j);
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  const int T = a.max_tokens;
+  uint32_t bar_ph = 0;
+  const unsigned per_img = (unsigned)max_gr * (unsigned)nchunk;
+  const unsigned items = (unsigned)a.B * per_img;
+  const uint8_t* lut_lane = reinterpret_cast<const uint8_t*>(lut) + lane * 4;
+  for (unsigned it = blockIdx.x; it < items; it += gridDim.x) {
+    const int b = (int)(it / per_img);
+    const int rem = (int)(it - (unsigned)b * per_img);
+    const int r = rem / nchunk, x0 = (rem - r * nchunk) * STRIP_CW;
+    const int H = (int)a.img_table[3 * b + 1], W = (int)a.img_table[3 * b + 2];
+    const int gr = (H + p - 1) / p, gc = (W + p - 1) / p;
+    if (gr * gc > T || r >= gr || x0 >= gc * p) continue;                      // block-uniform
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(a.images) + a.img_table[3 * b];
+    const int npx = min(STRIP_CW, W - x0);                                      // >= 1: x0 is a multiple of 256 below gc * p, hence below W
+    const int nbytes = npx * 3;
+    const int nrows = min(p, H - r * p);                                        // image rows in this strip (>= 1)
+    const long long rowb = (long long)W * 3;
+    const uint8_t* src0 = img + ((long long)(r * p) * W + x0) * 3;
+    const bool bulk = ((reinterpret_cast<uintptr_t>(src0) | (uintptr_t)rowb | (uintptr_t)nbytes) & 15) == 0;
+    if (bulk) {
+      if (tid < 32) {
+        fence_proxy_async_smem();   // this buffer was read / written through the generic proxy by the previous item
+        if (tid == 0) mbar_expect_tx(&bar, (uint32_t)(nrows * nbytes));
+        __syncwarp();
+        for (int dy = tid; dy < nrows; dy += 32)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(strip + dy * STRIP_ROW_BYTES)),
+                       "l"(src0 + dy * rowb), "r"((uint32_t)nbytes), "r"(smem_u32(&bar))
+                       : "memory");
+      }
+      if (tid < PT) mis_s[tid] = 0;
+      mbar_wait(&bar, bar_ph);
+      bar_ph ^= 1;
+      __syncthreads();   // mis_s
+    } else {
+      constexpr int NIT = (PT * NVEC + 255) / 256;
+      uint4 v[NIT];
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int u = tid + 256 * i;
+        const int dy = u / NVEC, k = u - dy * NVEC;
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (dy < nrows) {
+          const uint8_t* sp = src0 + dy * rowb;                                  // row segment [sp, sp + nbytes)
+          const int mis = (int)(reinterpret_cast<uintptr_t>(sp) & 15);
+          const int lo = 16 * k - mis;                                           // first byte of vector k relative to sp
+          if (lo >= 0 && lo + 16 <= nbytes) {
+            v[i] = __ldg(reinterpret_cast<const uint4*>(sp + lo));
+          } else if (lo + 16 > 0 && lo < nbytes) {                               // edge vector: only the bytes inside the row
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+            for (int j = max(0, -lo); j < min(16, nbytes - lo); ++j) {
+              const uint32_t by = (uint32_t)__ldg(sp + lo + j) << (8 * (j & 3));
+              if ((j >> 2) == 0) w[0] |= by; else if ((j >> 2) == 1) w[1] |= by; else if ((j >> 2) == 2) w[2] |= by; else w[3] |= by;
+            }
+            v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int u = tid + 256 * i;
+        const int dy = u / NVEC, k = u - dy * NVEC;
+        if (dy < PT) *reinterpret_cast<uint4*>(strip + dy * STRIP_ROW_BYTES + 16 * k) = v[i];
+      }
+      if (tid < PT) mis_s[tid] = (int)(reinterpret_cast<uintptr_t>(src0 + min(tid, nrows - 1) * rowb) & 15);
+      __syncthreads();
+    }
+    // ---- phase 2
+    const int c0 = x0 / p, ntok = min(gc - c0, STRIP_CW / p);
+    OutT* const dst_strip = reinterpret_cast<OutT*>(a.patches) + ((long long)b * T + r * gc + c0) * P;
+    for (int u = tid; u < ntok * UPT; u += 256) {
+      const int tok = u / UPT, q = u - tok * UPT;
+      const int dy = q / SEG, seg = q - dy * SEG;
+      const int xl = tok * p + seg * PXT;                                        // pixel offset inside the strip
+      const int o = mis_s[dy] + xl * 3;
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(strip + dy * STRIP_ROW_BYTES + (o & ~3));
+      const uint32_t sh = (uint32_t)(o & 3) * 8u;
+      uint32_t w[NW + 1];
+#pragma unroll
+      for (int k = 0; k <= NW; ++k) w[k] = wp[k];
+#pragma unroll
+      for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(w[k], w[k + 1], sh);
+      const int nin = (r * p + dy) < H ? min(PXT, W - (x0 + xl)) : 0;            // pixels of this run inside the image (may be <= 0)
+      OutT* dst = dst_strip + tok * P + dy * p + seg * PXT;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float f[PXT];
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+          const int i = 3 * j + ch, k = i & 3;
+          const uint32_t wv = w[i >> 2];
+          // byte k of wv, times 128 (= one table row of 32 lanes x 4 bytes), or'ed with this lane's column
+          const uint32_t off = (k == 0 ? (wv << 7) : (wv >> (8 * k - 7))) & 0x7F80u;
+          f[j] = *reinterpret_cast<const float*>(lut_lane + off);
+        }
+        if (nin < PXT) {
+#pragma unroll
+          for (int j = 0; j < PXT; ++j) f[j] = j < nin ? f[j] : 0.f;
+        }
+        if (sizeof(OutT) == 4) {
+          *reinterpret_cast<float4*>(dst + ch * pp) = make_float4(f[0], f[1], f[2], f[3]);
+        } else {
+          *reinterpret_cast<uint4*>(dst + ch * pp) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                                pack_bf16x2(f[PXT > 4 ? 4 : 0], f[PXT > 4 ? 5 : 1]),
+                                                                pack_bf16x2(f[PXT > 4 ? 6 : 2], f[PXT > 4 ? 7 : 3]));
+        }
+      }
+    }
+    __syncthreads();   // the strip buffer is reused by the next item
+  }
+  // ---- per token: index arrays, metadata, and the zero rows of padding tokens (one warp per token)
+  const unsigned ntokens = (unsigned)a.B * (unsigned)T;
+  const unsigned nwarp = gridDim.x * 8u;
+  for (unsigned bt = blockIdx.x * 8u + (unsigned)(tid >> 5); bt < ntokens; bt += nwarp) {
+    const int b = (int)(bt / (unsigned)T), t = (int)(bt - (unsigned)b * (unsigned)T);
+    const int H = (int)a.img_table[3 * b + 1], W = (int)a.img_table[3 * b + 2];
+    const int gr = (H + p - 1) / p, gc = (W + p - 1) / p;
+    const int n = gr * gc;
+    const bool valid = t < n && n <= T;
+    if (!valid) {
+      OutT* dst = reinterpret_cast<OutT*>(a.patches) + (long long)bt * P;
+      for (int e4 = lane; e4 < (P >> 2); e4 += 32) store4(dst + (e4 << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    if (lane == 0) {
+      a.patch_mask[bt] = valid ? 1 : 0;
+      a.row_idx[bt] = valid ? t / gc : 0;
+      a.col_idx[bt] = valid ? t - (t / gc) * gc : 0;
+      a.time_idx[bt] = 0;
+      if (t == 0) {
+        a.meta[0 * a.B + b] = H;
+        a.meta[1 * a.B + b] = W;
+        a.meta[2 * a.B + b] = gr;
+        a.meta[3 * a.B + b] = gc;
+        if (n > T && a.status) atomicExch(a.status, 1);
+      }
+    }
+  }
+}
+
+template <typename OutT, int PT>
+static int patchify_u8_strip_launch(const PatchifyArgs& a, cudaStream_t stream) {
+  const int max_gr = (a.max_h + PT - 1) / PT;
+  const int nchunk = ((a.max_w + PT - 1) / PT * PT + STRIP_CW - 1) / STRIP_CW;
+  const long long items = (long long)a.B * max_gr * nchunk;
+  if (items >= (1ll << 31)) { set_error("patchify: batch bounding box too large"); return -2; }
+  auto kern = patchify_u8_strip_kernel<OutT, PT>;
+  constexpr int smem = strip_smem_bytes<PT>();
+  if (ensure_max_smem(reinterpret_cast<const void*>(kern), smem, "cudaFuncSetAttribute(patchify strips)")) return -1;
+  // persistent CTAs (every one builds the 32 KB table once): 4 (p = 16: 45 KB) / 3 (p = 32: 57 KB) per SM
+  long long blocks = (long long)num_sms() * (PT == 16 ? 4 : 3);
+  if (blocks > items) blocks = items;
+  if (blocks < 1) blocks = 1;
+  (void)launch_k(kern, dim3((unsigned)blocks), dim3(256), smem, stream, a, max_gr, nchunk);
+  return 0;
+}
+
 template <typename OutT>
 static void patchify_dispatch(const PatchifyArgs& a, int blocks, cudaStream_t stream) {
   if (a.patch == 16) (void)launch_k(patchify_kernel<OutT, 16>, dim3(blocks), dim3(256), 0, stream, a);
@@ -292,7 +494,16 @@ int launch_patchify(const PatchifyArgs& a, cudaStream_t stream) {
   const long long ntok = (long long)a.B * a.max_tokens;
   if (ntok >= (1ll << 31)) { set_error("patchify: B * max_tokens too large"); return -2; }
   if (a.in_dtype == 1 && (a.patch == 16 || a.patch == 32) && a.max_h > 0 && a.max_w > 0) {
-    // uint8 HWC front end: the row-coalesced kernel over the batch's bounding box (the caller knows every image size)
+    // uint8 HWC front end over the batch's bounding box (the caller knows every image size): the shared-memory-staged strip kernel;
+    // VTK_PATCHIFY_U8=rows keeps the register-only row kernel for A/B (byte-identical output)
+    static const bool use_rows = getenv("VTK_PATCHIFY_U8") && getenv("VTK_PATCHIFY_U8")[0] == 'r';
+    if (!use_rows) {
+      int rc;
+      if (a.out_dtype == 0) rc = a.patch == 16 ? patchify_u8_strip_launch<float, 16>(a, stream) : patchify_u8_strip_launch<float, 32>(a, stream);
+      else rc = a.patch == 16 ? patchify_u8_strip_launch<bf16, 16>(a, stream) : patchify_u8_strip_launch<bf16, 32>(a, stream);
+      if (rc) return rc;
+      return check_cuda(cudaGetLastError(), "patchify (uint8 strips) launch");
+    }
     const int p = a.patch;
     const int max_rows = (a.max_h + p - 1) / p * p, max_w4 = ((a.max_w + p - 1) / p * p) >> 4;   // 16-pixel runs per bounding-box row
     const long long total = (long long)a.B * max_rows * max_w4;
