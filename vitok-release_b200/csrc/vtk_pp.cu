@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) patchify_u8_strip_kernel(const PatchifyAr
   uint32_t bar_ph = 0;
   const unsigned per_img = (unsigned)max_gr * (unsigned)nchunk;
   const unsigned items = (unsigned)a.B * per_img;
-  const uint8_t* lut_lane = reinterpret_cast<const uint8_t*>(lut) + lane * 4;
+  const uint32_t lut_lane = smem_u32(lut) + (uint32_t)lane * 4u;   // shared-window address of this lane's table column
   for (unsigned it = blockIdx.x; it < items; it += gridDim.x) {
     const int b = (int)(it / per_img);
     const int rem = (int)(it - (unsigned)b * per_img);
@@ -392,75 +392,84 @@ __global__ void __launch_bounds__(256) patchify_u8_strip_kernel(const PatchifyAr
       if (tid < PT) mis_s[tid] = (int)(reinterpret_cast<uintptr_t>(src0 + min(tid, nrows - 1) * rowb) & 15);
       __syncthreads();
     }
-    // ---- phase 2
+    // ---- phase 2: 256 / UPT tokens per pass; a thread keeps its (plane row, segment) and walks the tokens
     const int c0 = x0 / p, ntok = min(gc - c0, STRIP_CW / p);
     OutT* const dst_strip = reinterpret_cast<OutT*>(a.patches) + ((long long)b * T + r * gc + c0) * P;
-    for (int u = tid; u < ntok * UPT; u += 256) {
-      const int tok = u / UPT, q = u - tok * UPT;
-      const int dy = q / SEG, seg = q - dy * SEG;
-      const int xl = tok * p + seg * PXT;                                        // pixel offset inside the strip
-      const int o = mis_s[dy] + xl * 3;
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(strip + dy * STRIP_ROW_BYTES + (o & ~3));
-      const uint32_t sh = (uint32_t)(o & 3) * 8u;
-      uint32_t w[NW + 1];
+    {
+      constexpr int TPP = 256 / UPT;                                             // tokens per pass
+      const int q = tid % UPT, dy = q / SEG, seg = q - dy * SEG;
+      const int mis = mis_s[dy];
+      const bool row_in = (r * p + dy) < H;
+      const uint8_t* srow = strip + dy * STRIP_ROW_BYTES;
+      for (int tok = tid / UPT; tok < ntok; tok += TPP) {
+        const int xl = tok * p + seg * PXT;                                      // pixel offset inside the strip
+        const int o = mis + xl * 3;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(srow + (o & ~3));
+        uint32_t w[NW + 1];
 #pragma unroll
-      for (int k = 0; k <= NW; ++k) w[k] = wp[k];
+        for (int k = 0; k <= NW; ++k) w[k] = wp[k];
+        if (mis & 3) {                                                           // (block-uniform per row for the usual layouts)
+          const uint32_t sh = (uint32_t)(o & 3) * 8u;
 #pragma unroll
-      for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(w[k], w[k + 1], sh);
-      const int nin = (r * p + dy) < H ? min(PXT, W - (x0 + xl)) : 0;            // pixels of this run inside the image (may be <= 0)
-      OutT* dst = dst_strip + tok * P + dy * p + seg * PXT;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        float f[PXT];
-#pragma unroll
-        for (int j = 0; j < PXT; ++j) {
-          const int i = 3 * j + ch, k = i & 3;
-          const uint32_t wv = w[i >> 2];
-          // byte k of wv, times 128 (= one table row of 32 lanes x 4 bytes), or'ed with this lane's column
-          const uint32_t off = (k == 0 ? (wv << 7) : (wv >> (8 * k - 7))) & 0x7F80u;
-          f[j] = *reinterpret_cast<const float*>(lut_lane + off);
+          for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(w[k], w[k + 1], sh);
         }
-        if (nin < PXT) {
+        const int nin = row_in ? min(PXT, W - (x0 + xl)) : 0;                    // pixels of this run inside the image (may be <= 0)
+        OutT* dst = dst_strip + tok * P + dy * p + seg * PXT;
 #pragma unroll
-          for (int j = 0; j < PXT; ++j) f[j] = j < nin ? f[j] : 0.f;
-        }
-        if (sizeof(OutT) == 4) {
-          *reinterpret_cast<float4*>(dst + ch * pp) = make_float4(f[0], f[1], f[2], f[3]);
-        } else {
-          *reinterpret_cast<uint4*>(dst + ch * pp) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                                pack_bf16x2(f[PXT > 4 ? 4 : 0], f[PXT > 4 ? 5 : 1]),
-                                                                pack_bf16x2(f[PXT > 4 ? 6 : 2], f[PXT > 4 ? 7 : 3]));
+        for (int ch = 0; ch < 3; ++ch) {
+          float f[PXT];
+#pragma unroll
+          for (int j = 0; j < PXT; ++j) {
+            const int i = 3 * j + ch;
+            // byte (i & 3) of the word alone in a register (PRMT), times one table row (32 lanes x 4 bytes) plus this lane's column:
+            // one ALU-pipe and one FMA-pipe instruction per byte, then the conflict-free LDS
+            const uint32_t by = __byte_perm(w[i >> 2], 0u, 0x4440u + (uint32_t)(i & 3));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(f[j]) : "r"(by * 128u + lut_lane));
+          }
+          if (nin < PXT) {
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) f[j] = j < nin ? f[j] : 0.f;
+          }
+          if (sizeof(OutT) == 4) {
+            *reinterpret_cast<float4*>(dst + ch * pp) = make_float4(f[0], f[1], f[2], f[3]);
+          } else {
+            *reinterpret_cast<uint4*>(dst + ch * pp) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                                  pack_bf16x2(f[PXT > 4 ? 4 : 0], f[PXT > 4 ? 5 : 1]),
+                                                                  pack_bf16x2(f[PXT > 4 ? 6 : 2], f[PXT > 4 ? 7 : 3]));
+          }
         }
       }
     }
     __syncthreads();   // the strip buffer is reused by the next item
   }
-  // ---- per token: index arrays, metadata, and the zero rows of padding tokens (one warp per token)
+  // ---- per token (one THREAD per token): index arrays and metadata; then the zero rows of padding tokens, which are one contiguous
+  // range per image ([n_b, T), or all of it when the grid does not fit) written CTA-wide with 16-byte stores
   const unsigned ntokens = (unsigned)a.B * (unsigned)T;
-  const unsigned nwarp = gridDim.x * 8u;
-  for (unsigned bt = blockIdx.x * 8u + (unsigned)(tid >> 5); bt < ntokens; bt += nwarp) {
+  for (unsigned bt = blockIdx.x * 256u + (unsigned)tid; bt < ntokens; bt += gridDim.x * 256u) {
     const int b = (int)(bt / (unsigned)T), t = (int)(bt - (unsigned)b * (unsigned)T);
     const int H = (int)a.img_table[3 * b + 1], W = (int)a.img_table[3 * b + 2];
     const int gr = (H + p - 1) / p, gc = (W + p - 1) / p;
     const int n = gr * gc;
     const bool valid = t < n && n <= T;
-    if (!valid) {
-      OutT* dst = reinterpret_cast<OutT*>(a.patches) + (long long)bt * P;
-      for (int e4 = lane; e4 < (P >> 2); e4 += 32) store4(dst + (e4 << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+    a.patch_mask[bt] = valid ? 1 : 0;
+    a.row_idx[bt] = valid ? t / gc : 0;
+    a.col_idx[bt] = valid ? t - (t / gc) * gc : 0;
+    a.time_idx[bt] = 0;
+    if (t == 0) {
+      a.meta[0 * a.B + b] = H;
+      a.meta[1 * a.B + b] = W;
+      a.meta[2 * a.B + b] = gr;
+      a.meta[3 * a.B + b] = gc;
+      if (n > T && a.status) atomicExch(a.status, 1);
     }
-    if (lane == 0) {
-      a.patch_mask[bt] = valid ? 1 : 0;
-      a.row_idx[bt] = valid ? t / gc : 0;
-      a.col_idx[bt] = valid ? t - (t / gc) * gc : 0;
-      a.time_idx[bt] = 0;
-      if (t == 0) {
-        a.meta[0 * a.B + b] = H;
-        a.meta[1 * a.B + b] = W;
-        a.meta[2 * a.B + b] = gr;
-        a.meta[3 * a.B + b] = gc;
-        if (n > T && a.status) atomicExch(a.status, 1);
-      }
-    }
+  }
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    const int H = (int)a.img_table[3 * b + 1], W = (int)a.img_table[3 * b + 2];
+    const int n = ((H + p - 1) / p) * ((W + p - 1) / p);
+    const int first = n <= T ? n : 0;                                            // first padding token of this image
+    uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(a.patches) + ((long long)b * T + first) * P);   // (P * sizeof(OutT) is a multiple of 16)
+    const long long nv = (long long)(T - first) * P * (long long)sizeof(OutT) / 16;
+    for (long long i = tid; i < nv; i += 256) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
