@@ -56,7 +56,7 @@ def test_colsum_and_resid_bwd(L):
     assert torch.equal(o, x + (y * gamma))
 
 
-@pytest.mark.parametrize("M,heads,d", [(200, 2, 64), (96, 3, 128)])
+@pytest.mark.parametrize("M,heads,d", [(200, 2, 64), (96, 3, 128), (203, 4, 64), (97, 4, 128), (1001, 16, 64), (333, 24, 128)])
 def test_qk_norm_rope_fwd_bwd(L, M, heads, d):
     D = heads * d
     z = bf16_randn(M, 3 * D, seed=55)
@@ -124,7 +124,7 @@ def test_swiglu_fwd_bwd(L):
     assert torch.equal(dz1[:, qp:], du)
 
 
-@pytest.mark.parametrize("M,D", [(100, 256), (64, 1024), (40, 3072)])
+@pytest.mark.parametrize("M,D", [(100, 256), (64, 1024), (40, 3072), (4099, 3072), (77, 4096), (50, 768), (1500, 1024)])
 def test_rmsnorm_bwd(L, M, D):
     x, dh, dres = bf16_randn(M, D, seed=61, scale=2.0), bf16_randn(M, D, seed=62), bf16_randn(M, D, seed=63)
     w = (torch.rand(D, generator=torch.Generator().manual_seed(64)) + 0.5).to(BF).cuda()

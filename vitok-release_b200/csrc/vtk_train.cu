@@ -12,6 +12,8 @@
 //
 // GEMMs of the backward pass (dgrad / wgrad) run on the tcgen05 GEMM of vtk_gemm.cu: dgrad against transposed
 // weight copies, wgrad on activations transposed by transpose_kernel below (both operands K-major).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "vtk_common.cuh"
@@ -96,13 +98,14 @@ __device__ __forceinline__ void swiglu_cols(int o, int qp, int Hf, int layout, l
   if (layout == 0) { voff = qp + ((o >> 4) << 5) + (o & 8); goff = voff + 16; }
   else { voff = qp + o; goff = voff + Hf; }
 }
+template <typename IT>   // IT = unsigned when M * Hf / 8 < 2^32: a 32-bit division per vector instead of the 64-bit sequence
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ zraw, long long ldz, int qp,
                                                          bf16* __restrict__ act, long long lda, int M, int Hf, int layout) {
   const int vec_per_row = Hf >> 3;
-  const long long total = (long long)M * vec_per_row;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / vec_per_row);
-    const int o = (int)(i - (long long)m * vec_per_row) << 3;   // first of 8 output columns
+  const IT total = (IT)M * (IT)vec_per_row;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IT)gridDim.x * blockDim.x) {
+    const int m = (int)(i / (IT)vec_per_row);
+    const int o = (int)(i - (IT)m * (IT)vec_per_row) << 3;   // first of 8 output columns
     long long voff, goff;
     swiglu_cols(o, qp, Hf, layout, voff, goff);
     float v[8], g[8], r[8];
@@ -249,14 +252,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ in
 
 // SwiGLU backward: d_act [M, Hf] (row stride ldd), zraw (value16 | gate16 groups at column qp) ->
 // dz[:, qp:] in the same packed order:  d_val = d_act * silu(g),  d_gate = d_act * val * sig(g) * (1 + g * (1 - sig(g)))
+template <typename IT>
 __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dact, long long ldd,
                                                          const bf16* __restrict__ zraw, long long ldz, int qp,
                                                          bf16* __restrict__ dz, long long lddz, int M, int Hf, int layout) {
   const int vec_per_row = Hf >> 3;
-  const long long total = (long long)M * vec_per_row;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / vec_per_row);
-    const int o = (int)(i - (long long)m * vec_per_row) << 3;
+  const IT total = (IT)M * (IT)vec_per_row;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IT)gridDim.x * blockDim.x) {
+    const int m = (int)(i / (IT)vec_per_row);
+    const int o = (int)(i - (IT)m * (IT)vec_per_row) << 3;
     long long zoff, goff;
     swiglu_cols(o, qp, Hf, layout, zoff, goff);
     float v[8], g[8], d[8], dv[8], dg[8];
@@ -718,6 +722,281 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// round 2: 16-byte versions of the three kernels that sat furthest below the HBM roofline in the 5B step
+// (torch.profiler, 44 blocks: qk_norm_rope_fwd 132 us, qk_norm_rope_bwd 177 us, rmsnorm_bwd 207 us per launch for
+// 302 / 300 / 200 MB, i.e. 2.3 / 1.7 / 1.0 TB/s).  The versions above moved 4 bytes per lane and instruction with a
+// warp-wide reduction per 256 bytes (qk), or re-read every row three times with 128 accumulator registers (rmsnorm).
+// ------------------------------------------------------------------------------------------------
+
+// sum over the LPH (8 or 16) consecutive lanes that share a head
+template <int LPH>
+static __device__ __forceinline__ float head_sum(float v) {
+#pragma unroll
+  for (int o = LPH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// RoPE table chunks of row m for the lane's 8 columns (chunk j of C2, chunk DH/8 + j of S2); layout: vtk_gemm.cu rope_row_ptr
+template <int DH>
+static __device__ __forceinline__ void rope_chunks(const bf16* rope, int m, int j, uint4& c2, uint4& s2) {
+  const uint4* t = reinterpret_cast<const uint4*>(rope) + ((long long)(m >> 5) * (DH >> 2)) * 32 + (m & 31);
+  c2 = ld_global_nc_v4(reinterpret_cast<const bf16*>(t + j * 32));
+  s2 = ld_global_nc_v4(reinterpret_cast<const bf16*>(t + ((DH >> 3) + j) * 32));
+}
+
+// Forward: a lane owns 8 consecutive columns (4 RoPE pairs) of one head, LPH = DH / 8 lanes share a head, a warp covers 256 consecutive
+// columns of [q | k | v] per pass (heads % (32 / LPH) == 0, so a pass never straddles q / k / v) and UN passes are in flight.
+template <int DH, int UN>
+__global__ void __launch_bounds__(256) qk_norm_rope_fwd16_kernel(const bf16* __restrict__ zraw, long long ldz,
+                                                                 const bf16* __restrict__ wq, const bf16* __restrict__ wk,
+                                                                 const bf16* __restrict__ rope, bf16* __restrict__ qkv,
+                                                                 long long ldq, int M, int heads, float eps) {
+  constexpr int LPH = DH / 8, HPW = 32 / LPH;
+  const int lane = threadIdx.x & 31, sub = lane / LPH, j = lane - sub * LPH;
+  const unsigned upr = (unsigned)(3 * heads / HPW);                 // 256-column units per row
+  const unsigned total = (unsigned)M * upr;
+  const unsigned nwarps = gridDim.x * 8u;
+  float wqf[8], wkf[8];
+  unpack8(ld_global_nc_v4(wq + 8 * j), wqf);
+  unpack8(ld_global_nc_v4(wk + 8 * j), wkf);
+  for (unsigned u0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * UN; u0 < total; u0 += nwarps * UN) {
+    uint4 t[UN];
+    int mrow[UN], g[UN];
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      const unsigned u = u0 + k;
+      t[k] = make_uint4(0u, 0u, 0u, 0u);
+      mrow[k] = -1;
+      if (u < total) {
+        mrow[k] = (int)(u / upr);
+        g[k] = (int)(u - (unsigned)mrow[k] * upr);
+        t[k] = ld_global_nc_v4(zraw + (long long)mrow[k] * ldz + g[k] * 256 + lane * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      if (mrow[k] < 0) continue;
+      const int m = mrow[k];
+      bf16* dst = qkv + (long long)m * ldq + g[k] * 256 + lane * 8;
+      const int seg = (g[k] * HPW) / heads;                         // warp-uniform
+      if (seg == 2) {                                               // v: copy
+        *reinterpret_cast<uint4*>(dst) = t[k];
+        continue;
+      }
+      uint4 c2, s2;
+      rope_chunks<DH>(rope, m, j, c2, s2);
+      float x[8];
+      unpack8(t[k], x);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += x[i] * x[i];
+      ss = head_sum<LPH>(ss);
+      const float rstd = rsqrtf(ss / (float)DH + eps);
+      const float* w = seg == 0 ? wqf : wkf;
+      const uint32_t cw[4] = {c2.x, c2.y, c2.z, c2.w}, sw[4] = {s2.x, s2.y, s2.z, s2.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t Y = bf2_cvt(x[2 * i] * rstd * w[2 * i], x[2 * i + 1] * rstd * w[2 * i + 1]);
+        o[i] = bf2_add(bf2_mul(Y, cw[i]), bf2_mul(bf2_swap(Y), sw[i]));
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// Backward, in place on dz[:, 0:2D]: same lane <-> column mapping; the lane's dw accumulators (8 columns x {q, k}) are
+// reduced over the lanes that own the same columns, then per block and per grid.
+template <int DH, int UN>
+__global__ void __launch_bounds__(256) qk_norm_rope_bwd16_kernel(bf16* __restrict__ dz, long long lddz,
+                                                                 const bf16* __restrict__ zraw, long long ldz,
+                                                                 const bf16* __restrict__ wq, const bf16* __restrict__ wk,
+                                                                 const bf16* __restrict__ rope, float* __restrict__ dw,
+                                                                 int M, int heads, float eps) {
+  constexpr int LPH = DH / 8, HPW = 32 / LPH;
+  __shared__ float red[8][2][DH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPH, j = lane - sub * LPH;
+  const unsigned upr = (unsigned)(2 * heads / HPW);
+  const unsigned total = (unsigned)M * upr;
+  const unsigned nwarps = gridDim.x * 8u;
+  float wqf[8], wkf[8], accq[8], acck[8];
+  unpack8(ld_global_nc_v4(wq + 8 * j), wqf);
+  unpack8(ld_global_nc_v4(wk + 8 * j), wkf);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) accq[i] = acck[i] = 0.f;
+  for (unsigned u0 = (blockIdx.x * 8u + (unsigned)warp) * UN; u0 < total; u0 += nwarps * UN) {
+    uint4 tx[UN], td[UN];
+    int mrow[UN], g[UN];
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      const unsigned u = u0 + k;
+      mrow[k] = -1;
+      tx[k] = td[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (u < total) {
+        mrow[k] = (int)(u / upr);
+        g[k] = (int)(u - (unsigned)mrow[k] * upr);
+        tx[k] = ld_global_nc_v4(zraw + (long long)mrow[k] * ldz + g[k] * 256 + lane * 8);
+        td[k] = ld_global_v4(dz + (long long)mrow[k] * lddz + g[k] * 256 + lane * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      if (mrow[k] < 0) continue;
+      const int m = mrow[k];
+      const int seg = (g[k] * HPW) / heads;                         // 0 = q, 1 = k (warp-uniform)
+      uint4 c2, s2;
+      rope_chunks<DH>(rope, m, j, c2, s2);
+      float x[8], d[8], gr[8];
+      unpack8(tx[k], x);
+      unpack8(td[k], d);
+      const uint32_t cw[4] = {c2.x, c2.y, c2.z, c2.w}, sw[4] = {s2.x, s2.y, s2.z, s2.w};
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float c = bf16_lo(cw[i]), sn = bf16_hi(sw[i]);        // C2 = (c, c), S2 = (-s, +s)
+        gr[2 * i] = c * d[2 * i] + sn * d[2 * i + 1];               // un-rotate
+        gr[2 * i + 1] = -sn * d[2 * i] + c * d[2 * i + 1];
+        ss += x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1];
+      }
+      ss = head_sum<LPH>(ss);
+      const float rstd = rsqrtf(ss / (float)DH + eps);
+      const float* w = seg == 0 ? wqf : wkf;
+      float gw[8], dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] *= rstd;                                               // xh
+        gw[i] = gr[i] * w[i];
+        dot += gw[i] * x[i];
+      }
+      if (seg == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) accq[i] += gr[i] * x[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acck[i] += gr[i] * x[i];
+      }
+      dot = head_sum<LPH>(dot) / (float)DH;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rstd * (gw[i] - x[i] * dot);
+      *reinterpret_cast<uint4*>(dz + (long long)m * lddz + g[k] * 256 + lane * 8) = pack8(o);
+    }
+  }
+  // lanes sub = 0 .. HPW-1 own the same columns: fold them, then warps, then the grid
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = LPH; o < 32; o <<= 1) {
+      accq[i] += __shfl_xor_sync(0xffffffffu, accq[i], o);
+      acck[i] += __shfl_xor_sync(0xffffffffu, acck[i], o);
+    }
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[warp][0][8 * j + i] = accq[i];
+      red[warp][1][8 * j + i] = acck[i];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * DH; e += blockDim.x) {
+    float sum = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) sum += red[wp][e / DH][e % DH];
+    atomicAdd(&dw[e], sum);
+  }
+}
+
+// RMSNorm backward with column-owning threads: CTA = D / 8 threads (rounded up to whole warps), a thread keeps 8 fixed columns, so
+// dw needs 8 accumulators (not 128) and every operand is read ONCE: RB rows per pass, all 3 x RB 16-byte loads of a thread issued up
+// front, ONE block-wide reduction per pass for both row statistics -- sum x^2 and sum dh w x (mean(gw * xh) = rstd * that / D, so it
+// does not have to wait for rstd) --, through ping-pong shared-memory slots (one __syncthreads per pass).
+template <int RB, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) rmsnorm_bwd_cols_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dh,
+                                                                const bf16* __restrict__ w, const bf16* __restrict__ dx_res,
+                                                                bf16* __restrict__ dx_out, float* __restrict__ dw, int M, int D,
+                                                                float eps) {
+  __shared__ __align__(16) float red[2][32][2 * RB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const bool active = tid < (D >> 3);
+  const int c = tid * 8;
+  float wv[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wv[i] = acc[i] = 0.f;
+  if (active) unpack8(ld_global_nc_v4(w + c), wv);
+  const float inv_d = 1.f / (float)D;
+  int buf = 0;
+  for (long long m0 = (long long)blockIdx.x * RB; m0 < M; m0 += (long long)gridDim.x * RB) {
+    uint4 xr[RB], dr[RB], rr[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      xr[r] = dr[r] = rr[r] = make_uint4(0u, 0u, 0u, 0u);
+      if (active && m0 + r < M) {
+        const long long off = (m0 + r) * D + c;
+        xr[r] = ld_global_nc_v4(x + off);
+        dr[r] = ld_global_nc_v4(dh + off);
+        rr[r] = ld_global_v4(dx_res + off);
+      }
+    }
+    float part[2 * RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float xv[8], dv[8];
+      unpack8(xr[r], xv);
+      unpack8(dr[r], dv);
+      float ss = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ss += xv[i] * xv[i];
+        s2 += dv[i] * wv[i] * xv[i];
+      }
+      part[r] = warp_sum(ss);
+      part[RB + r] = warp_sum(s2);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 2 * RB; ++q) red[buf][warp][q] = part[q];
+    }
+    __syncthreads();
+    float tot[2 * RB];
+#pragma unroll
+    for (int q = 0; q < 2 * RB; ++q) tot[q] = 0.f;
+    for (int wp = 0; wp < nw; ++wp) {
+#pragma unroll
+      for (int q = 0; q < 2 * RB; q += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&red[buf][wp][q]);
+        tot[q] += v.x; tot[q + 1] += v.y; tot[q + 2] += v.z; tot[q + 3] += v.w;
+      }
+    }
+    buf ^= 1;
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (m0 + r >= M) break;
+        const float rstd = rsqrtf(tot[r] * inv_d + eps);
+        const float dot = rstd * tot[RB + r] * inv_d;               // mean(gw * xh)
+        float xv[8], dv[8], rv[8], o[8];
+        unpack8(xr[r], xv);
+        unpack8(dr[r], dv);
+        unpack8(rr[r], rv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = xv[i] * rstd;
+          acc[i] += dv[i] * xh;
+          o[i] = rv[i] + rstd * (dv[i] * wv[i] - xh * dot);
+        }
+        *reinterpret_cast<uint4*>(dx_out + (m0 + r) * D + c) = pack8(o);
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&dw[c + i], acc[i]);
+  }
+}
+
+
 #define VTK_TRAIN_CHECK(cond, ...) \
   do {                             \
     if (!(cond)) {                 \
@@ -730,6 +1009,15 @@ int launch_qk_norm_rope_fwd(const bf16* zraw, long long ldz, const bf16* wq, con
                             long long ldq, int M, int heads, int d, float eps, cudaStream_t st) {
   VTK_TRAIN_CHECK(d == 64 || d == 128, "qk_norm_rope: head_dim %d unsupported (64 or 128)", d);
   if (M <= 0) return 0;
+  static const int v1 = getenv("VTK_TRAIN_V1") ? atoi(getenv("VTK_TRAIN_V1")) : 0;   // 1: the round-1 kernels (A/B)
+  const int hpw = 32 / (d / 8);
+  if (!v1 && heads % hpw == 0 && ldz % 8 == 0 && ldq % 8 == 0 && (long long)M * (3 * heads / hpw) < (1ll << 31) &&
+      ((reinterpret_cast<uintptr_t>(zraw) | reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk)) & 15) == 0) {
+    const int g16 = grid_for(((long long)M * (3 * heads / hpw) + 3) / 4, 8, 8);
+    if (d == 64) qk_norm_rope_fwd16_kernel<64, 4><<<g16, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
+    else qk_norm_rope_fwd16_kernel<128, 4><<<g16, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
+    return check_cuda(cudaGetLastError(), "qk_norm_rope_fwd16 launch");
+  }
   const int grid = grid_for((long long)M * 3 * heads, 8);
   if (d == 64) qk_norm_rope_fwd_kernel<64><<<grid, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
   else qk_norm_rope_fwd_kernel<128><<<grid, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
@@ -738,7 +1026,9 @@ int launch_qk_norm_rope_fwd(const bf16* zraw, long long ldz, const bf16* wq, con
 int launch_swiglu_fwd(const bf16* zraw, long long ldz, int qp, bf16* act, long long lda, int M, int Hf, int layout, cudaStream_t st) {
   VTK_TRAIN_CHECK(Hf % 16 == 0 && lda % 8 == 0 && ldz % 8 == 0, "swiglu: Hf %% 16 and strides %% 8 required");
   if (M <= 0) return 0;
-  swiglu_fwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(zraw, ldz, qp, act, lda, M, Hf, layout);
+  if ((long long)M * (Hf / 8) + (long long)num_sms() * 16 * 256 < (1ll << 32))
+    swiglu_fwd_kernel<unsigned><<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(zraw, ldz, qp, act, lda, M, Hf, layout);
+  else swiglu_fwd_kernel<long long><<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(zraw, ldz, qp, act, lda, M, Hf, layout);
   return check_cuda(cudaGetLastError(), "swiglu_fwd launch");
 }
 int launch_resid_fwd(const bf16* x, const bf16* y, const bf16* gamma, bf16* out, int M, int D, cudaStream_t st, const float* keep,
@@ -775,13 +1065,24 @@ int launch_swiglu_bwd(const bf16* dact, long long ldd, const bf16* zraw, long lo
                       int Hf, int layout, cudaStream_t st) {
   VTK_TRAIN_CHECK(Hf % 16 == 0 && ldd % 8 == 0 && ldz % 8 == 0 && lddz % 8 == 0, "swiglu_bwd: Hf %% 16 and strides %% 8 required");
   if (M <= 0) return 0;
-  swiglu_bwd_kernel<<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(dact, ldd, zraw, ldz, qp, dz, lddz, M, Hf, layout);
+  if ((long long)M * (Hf / 8) + (long long)num_sms() * 16 * 256 < (1ll << 32))
+    swiglu_bwd_kernel<unsigned><<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(dact, ldd, zraw, ldz, qp, dz, lddz, M, Hf, layout);
+  else swiglu_bwd_kernel<long long><<<grid_for((long long)M * (Hf / 8), 256), 256, 0, st>>>(dact, ldd, zraw, ldz, qp, dz, lddz, M, Hf, layout);
   return check_cuda(cudaGetLastError(), "swiglu_bwd launch");
 }
 int launch_qk_norm_rope_bwd(bf16* dz, long long lddz, const bf16* zraw, long long ldz, const bf16* wq, const bf16* wk,
                             const bf16* rope, float* dw, int M, int heads, int d, float eps, cudaStream_t st) {
   VTK_TRAIN_CHECK(d == 64 || d == 128, "qk_norm_rope_bwd: head_dim %d unsupported (64 or 128)", d);
   if (M <= 0) return 0;
+  static const int v1 = getenv("VTK_TRAIN_V1") ? atoi(getenv("VTK_TRAIN_V1")) : 0;
+  const int hpw = 32 / (d / 8);
+  if (!v1 && heads % hpw == 0 && ldz % 8 == 0 && lddz % 8 == 0 && (long long)M * (2 * heads / hpw) < (1ll << 31) &&
+      ((reinterpret_cast<uintptr_t>(zraw) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk)) & 15) == 0) {
+    const int g16 = grid_for(((long long)M * (2 * heads / hpw) + 3) / 4, 8, 4);
+    if (d == 64) qk_norm_rope_bwd16_kernel<64, 4><<<g16, 256, 0, st>>>(dz, lddz, zraw, ldz, wq, wk, rope, dw, M, heads, eps);
+    else qk_norm_rope_bwd16_kernel<128, 4><<<g16, 256, 0, st>>>(dz, lddz, zraw, ldz, wq, wk, rope, dw, M, heads, eps);
+    return check_cuda(cudaGetLastError(), "qk_norm_rope_bwd16 launch");
+  }
   const int grid = grid_for((long long)M * 2 * heads, 8, 8);
   if (d == 64) qk_norm_rope_bwd_kernel<64><<<grid, 256, 0, st>>>(dz, lddz, zraw, ldz, wq, wk, rope, dw, M, heads, eps);
   else qk_norm_rope_bwd_kernel<128><<<grid, 256, 0, st>>>(dz, lddz, zraw, ldz, wq, wk, rope, dw, M, heads, eps);
@@ -791,6 +1092,18 @@ int launch_rmsnorm_bwd(const bf16* x, const bf16* dh, const bf16* w, const bf16*
                        float eps, cudaStream_t st) {
   VTK_TRAIN_CHECK(D % 8 == 0 && D <= 4096, "rmsnorm_bwd: D %% 8 == 0 and D <= 4096 required (D=%d)", D);
   if (M <= 0) return 0;
+  static const int v1 = getenv("VTK_TRAIN_V1") ? atoi(getenv("VTK_TRAIN_V1")) : 0;
+  if (!v1 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(w) |
+               reinterpret_cast<uintptr_t>(dx_res) | reinterpret_cast<uintptr_t>(dx_out)) & 15) == 0) {
+    const int threads = ((D / 8) + 31) / 32 * 32;                       // <= 512 for D <= 4096
+    const int per_sm = threads <= 192 ? 4 : threads <= 384 ? 2 : 1;
+    const int RB = threads <= 384 ? 2 : 4;   // rows per pass: 2 x 3 x 16 bytes per thread and two CTAs per SM, or 4 x 3 x 16 and one
+    long long g = ((long long)M + RB - 1) / RB;
+    if (g > (long long)num_sms() * per_sm) g = (long long)num_sms() * per_sm;
+    if (threads <= 384) rmsnorm_bwd_cols_kernel<2, 384, 2><<<(unsigned)g, threads, 0, st>>>(x, dh, w, dx_res, dx_out, dw, M, D, eps);
+    else rmsnorm_bwd_cols_kernel<4, 512, 1><<<(unsigned)g, threads, 0, st>>>(x, dh, w, dx_res, dx_out, dw, M, D, eps);
+    return check_cuda(cudaGetLastError(), "rmsnorm_bwd (columns) launch");
+  }
   const int grid = grid_for(M, 8, 4);
   const size_t smem = (size_t)8 * D * sizeof(float);
   auto run = [&](auto kern) {
