@@ -16,8 +16,9 @@ Contract (see DESIGN.md "Measurement"):
                 encode, decode, postprocess, uint8 reconstructions out (D2H), all inside the timed region;
   * `roofline`: the dominant kernel (QKV+SwiGLU tcgen05 GEMM): algorithmic FLOPs per launch / its mean launch
                 duration from CUDA events recorded around every launch inside a timed pass;
-  * `cpu_baseline` / `--impl reference`: the CPU oracle (oracle/, a restatement of the reference's PyTorch CPU
-                path; the only place bench.py touches oracle/) timed on the host cores on a bounded sample.
+  * `cpu_baseline` / `--impl reference`: the reference's own CPU path on the host cores -- the UNMODIFIED reference from
+                baseline/_ref (`kind: "reference"`) when it is installed, else the CPU oracle (oracle/, a restatement of it,
+                `kind: "port"`; the only place bench.py touches oracle/) -- on the arm's batch or a bounded sample of it.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -202,6 +203,45 @@ def cpu_oracle_rate(variant: str, n_images: int, res: int, steps: int, warmup: i
     return n_images * len(times) / total, cores, total / len(times)
 
 
+def cpu_reference_rate(variant: str, n_images: int, res: int, steps: int, warmup: int):
+    """The UNMODIFIED reference (vitok, installed into baseline/_ref -- git-ignored, shipped to the GPU box by gpurun) on the host
+    cores: AE(**decode_variant(variant)) in fp32, random init, encode -> decode of the same synthetic batch the port arm uses, through
+    the reference's own public API.  attn_backend="sdpa": flash-attn is CUDA-only; with every token valid the two backends compute the
+    same attention (attention.py:109-127).  Returns None when baseline/_ref is absent (the caller falls back to the oracle port)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "vitok")):
+        return None
+    import types
+    import numpy as np
+    from oracle import pp_oracle
+    from oracle.weights import synth_images
+    if "webdataset" not in sys.modules:          # the reference's only missing hard import (vitok/data.py), unused on this path
+        sys.modules["webdataset"] = types.ModuleType("webdataset")
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    from vitok.models.ae import AE as RefAE, decode_variant as ref_decode_variant
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ref_decode_variant(variant)
+    torch.manual_seed(0)
+    model = RefAE(**cfg, attn_backend="sdpa").eval()
+    if res > 0:
+        sizes, T = [(res, res)] * n_images, (res // cfg["spatial_stride"]) ** 2
+    else:
+        sizes, T = c3_sizes(n_images, 1234), 1024
+    b = pp_oracle.collate([pp_oracle.patchify(i, cfg["spatial_stride"], T) for i in synth_images(sizes, seed=1234)])
+    batch = {k: torch.from_numpy(np.asarray(v)) for k, v in b.items()}
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            model.decode(model.encode(batch))
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return n_images * len(times) / total, cores, total / len(times)
+
+
 def _res_name(res):
     return f"{res}px" if res > 0 else "128-512px mixed aspect (NaFlex, max_tokens 1024)"
 
@@ -246,9 +286,18 @@ def run_reference(args, rank, world):
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     if not full:            # bounded: the whole run must end within a few minutes; the line prints what was actually run
         steps, warmup = min(steps, 3 if est_gflop_img > 1e6 else 20), min(warmup, 1)
-    rate, cores, sec = cpu_oracle_rate(variant, n_img, res, steps, warmup)
+    kind, got = "reference", None
+    try:
+        got = cpu_reference_rate(variant, n_img, res, steps, warmup)
+    except Exception as ex:                                   # a broken install must not cost the arm: say so and use the port
+        sys.stderr.write(f"bench.py: baseline/_ref could not be run ({type(ex).__name__}: {ex}); using the oracle port\n")
+    if got is None:
+        kind, got = "port", cpu_oracle_rate(variant, n_img, res, steps, warmup)
+    rate, cores, sec = got
+    what = ("the unmodified reference from baseline/_ref: vitok.models.ae.AE, sdpa backend" if kind == "reference"
+            else "oracle port of vitok/models/ae.py")
     sample = (f"{n_img} x {_res_name(res)} images per step ({'the whole per-rank batch' if full else 'a bounded sample of the batch'}), "
-              f"fp32, torch CPU ops on {cores} threads (oracle port of vitok/models/ae.py), {steps} timed steps after {warmup} warm-up")
+              f"fp32, torch CPU ops on {cores} threads ({what}), {steps} timed steps after {warmup} warm-up")
     cfg = make_config(args, world, scaling, B)
     if not full:
         cfg["reference_sample"] = f"{n_img} of {B} images per step"
@@ -256,7 +305,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -524,8 +573,15 @@ def run_ours(args, rank, world, local):
     try:
         n_img = 4 if 0 < res <= 256 else 1
         c_res = res if res <= 512 else 512                                   # bounded sample: the CPU leg stops at 512 px
-        rate, cores, sec = cpu_oracle_rate(variant, n_img, c_res, 2, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        kind, got = "reference", None
+        try:                                                                 # the unmodified reference (baseline/_ref) when it is installed
+            got = cpu_reference_rate(variant, n_img, c_res, 2, 1)
+        except Exception as ex:
+            sys.stderr.write(f"bench.py: baseline/_ref could not be run ({type(ex).__name__}: {ex}); using the oracle port\n")
+        if got is None:
+            kind, got = "port", cpu_oracle_rate(variant, n_img, c_res, 2, 1)
+        rate, cores, sec = got
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{n_img} x {_res_name(c_res)} images, fp32, 2 timed iterations after 1 warm-up ({sec:.2f} s each)"}
     except Exception as ex:  # noqa: BLE001
         cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}

@@ -12,6 +12,8 @@ from bench import WORKLOADS  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 variant, B, res, T, backend = WORKLOADS[wl]
+if len(sys.argv) > 3:          # optional batch override (the per-GPU shards of a strong-scaled job: 8 / 16 / 32)
+    B = int(sys.argv[3])
 cfg = vb.decode_variant(variant)
 torch.manual_seed(0)
 model = vb.AE(**cfg, attn_backend=backend).eval().to("cuda", torch.bfloat16)
