@@ -13,7 +13,8 @@
 //   dV += P^T dO, dK += dS^T Q : A = the [query x key] tile read MN-major (transposed by the descriptor),
 //                                B = dO / Q read MN-major straight from their [row, d] layout
 //   dQ += dS K                 : A = dS K-major, B = K_j MN-major
-// The step loop is not software-pipelined (one tile pair in flight); S/dP recomputation makes it 7 MMAs per
+// The step loop itself is serial (S / dP -> P / dS -> second MMA group), but the TMA thread fetches ahead: both streamed tiles
+// of the next step in MODE 1, Q_i in MODE 0 (see the buffer comment in the kernel).  S/dP recomputation makes it 7 MMAs per
 // tile pair instead of the minimal 5.  Attention is ~5 % of the step's FLOPs at config 5.
 // Two compute warpgroups (warps 0-3 and 8-11) split every [128 x 128] S / dP tile by columns (64 keys each; a warp may
 // only read the TMEM lanes of its quarter, so both groups own the same rows), which halves the P / dS latency that
@@ -38,8 +39,10 @@ template <int DH> struct BwdShape {
   static constexpr int OFF_S1 = 3 * TILE;          // streamed tile 1 (MODE 0: dO_i, MODE 1: V_j)
   static constexpr int OFF_P = 4 * TILE;           // P  [128 q x 128 k] bf16 (2 blocks)
   static constexpr int OFF_DS = OFF_P + 2 * BWD_BLK;
-  static constexpr int OFF_BAR = OFF_DS + 2 * BWD_BLK;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int OFF_X = OFF_DS + 2 * BWD_BLK;   // one extra tile: MODE 0 second Q_i buffer; MODE 1 second V_j buffer (its second K_j
+                                                       // buffer is the P region, which MODE 1 does not write)
+  static constexpr int OFF_BAR = OFF_X + TILE;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;     // d = 128: 229 504 bytes (limit 232 448)
   // TMEM columns: S [0,128) dP [128,256) acc0 [256, 256+DH) acc1 [256+DH, 256+2DH)
 };
 
@@ -148,22 +151,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sS1 = smem + S::OFF_S1;
   uint8_t* sP = smem + S::OFF_P;
   uint8_t* sDS = smem + S::OFF_DS;
+  // The step loop is serial (load -> S / dP -> P / dS -> second MMA group), so whatever the TMA thread cannot fetch ahead is exposed:
+  // ~2 300 of the ~8 000 cycles of a step were the 64 KB of streamed tiles.  MODE 1 (dQ) does not write P, which leaves room for a
+  // SECOND pair of streamed tiles (K_j in the P region, V_j in the extra tile X): its loads run one step ahead.  MODE 0 needs K, V, Q, dO,
+  // P, dS = 192 KB at d = 128; the extra tile double-buffers Q_i only, so the S MMAs of the next step start at once and only the dO load
+  // (half the bytes, partly under those MMAs) stays exposed.  Each streamed tile has its own full / free barriers.
+  constexpr int NB0 = 2, NB1 = MODE == 1 ? 2 : 1;          // buffers of stream tile 0 / 1
+  uint8_t* sSb0[2] = {sS0, smem + (MODE == 1 ? S::OFF_P : S::OFF_X)};
+  uint8_t* sSb1[2] = {sS1, smem + S::OFF_X};               // (second entry used by MODE 1 only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* res_full = bars + 0;   // resident tiles landed
-  uint64_t* str_full = bars + 1;   // streamed tiles of this step landed
-  uint64_t* str_free = bars + 2;   // second MMA group of this step has read the streamed tiles (+ P / dS)
-  uint64_t* sdp_full = bars + 3;   // S and dP of this step are in TMEM
-  uint64_t* sdp_free = bars + 4;   // count 256: threads have pulled S / dP into registers
-  uint64_t* pds_full = bars + 5;   // count 256: P and dS of this step are in smem
-  uint64_t* acc_done = bars + 6;   // all MMAs finished (epilogue)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s0_full = bars + 1;    // [2] stream tile 0 of a step landed (buffer = step % NB0)
+  uint64_t* s0_free = bars + 3;    // [2] the second MMA group of that step has read it
+  uint64_t* s1_full = bars + 5;    // [2] stream tile 1 (buffer = step % NB1)
+  uint64_t* s1_free = bars + 7;    // [2]
+  uint64_t* sdp_full = bars + 9;   // S and dP of this step are in TMEM
+  uint64_t* sdp_free = bars + 10;  // count 256: threads have pulled S / dP into registers
+  uint64_t* pds_full = bars + 11;  // count 256: P and dS of this step are in smem
+  uint64_t* acc_done = bars + 12;  // all MMAs finished (epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   if (warp == 4) {
-    if (lane < 7) mbar_init(&bars[lane], (lane == 4 || lane == 5) ? 256u : 1u);
-    else if (lane == 8) tma_prefetch_desc(&tmQ);
-    else if (lane == 9) tma_prefetch_desc(&tmK);
-    else if (lane == 10) tma_prefetch_desc(&tmV);
-    else if (lane == 11) tma_prefetch_desc(&tmDO);
+    if (lane < 13) mbar_init(&bars[lane], (lane == 10 || lane == 11) ? 256u : 1u);
+    else if (lane == 16) tma_prefetch_desc(&tmQ);
+    else if (lane == 17) tma_prefetch_desc(&tmK);
+    else if (lane == 18) tma_prefetch_desc(&tmV);
+    else if (lane == 19) tma_prefetch_desc(&tmDO);
     fence_barrier_init();
     __syncwarp();
   }
@@ -188,14 +201,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_2d(sR0 + nb * BWD_BLK, mR0, res_full, head * DH + nb * 64, (int)(row0 + tile0));
         tma_load_2d(sR1 + nb * BWD_BLK, mR1, res_full, head * DH + nb * 64, (int)(row0 + tile0));
       }
+      // issue order: tile 0 of step t, then tile 1 of step t -- with NB1 = 1 the wait for tile 1's buffer (the previous step's second MMA
+      // group) comes AFTER tile 0 of this step has been requested, so tile 0 always runs a step ahead
       for (int t = 0; t < steps; ++t) {
-        if (t > 0) mbar_wait(str_free, (uint32_t)(t - 1) & 1u);
         const int other0 = (t_lo + t) * BWD_T;
-        mbar_expect_tx(str_full, 2 * S::TILE);
-        for (int nb = 0; nb < S::NB; ++nb) {
-          tma_load_2d(sS0 + nb * BWD_BLK, mS0, str_full, head * DH + nb * 64, (int)(row0 + other0));
-          tma_load_2d(sS1 + nb * BWD_BLK, mS1, str_full, head * DH + nb * 64, (int)(row0 + other0));
-        }
+        const int b0 = t % NB0, b1 = t % NB1;
+        if (t >= NB0) mbar_wait(&s0_free[b0], (uint32_t)(t / NB0 - 1) & 1u);   // the step that used this buffer last is done with it
+        mbar_expect_tx(&s0_full[b0], S::TILE);
+        for (int nb = 0; nb < S::NB; ++nb) tma_load_2d(sSb0[b0] + nb * BWD_BLK, mS0, &s0_full[b0], head * DH + nb * 64, (int)(row0 + other0));
+        if (t >= NB1) mbar_wait(&s1_free[b1], (uint32_t)(t / NB1 - 1) & 1u);
+        mbar_expect_tx(&s1_full[b1], S::TILE);
+        for (int nb = 0; nb < S::NB; ++nb) tma_load_2d(sSb1[b1] + nb * BWD_BLK, mS1, &s1_full[b1], head * DH + nb * 64, (int)(row0 + other0));
       }
     }
   } else if (warp == 5) {
@@ -204,13 +220,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t idesc_s = make_idesc_bf16(BWD_T, BWD_T, 0, 0);      // S, dP: both operands K-major
       const uint32_t idesc_tt = make_idesc_bf16(BWD_T, DH, 1, 1);        // dV, dK: A and B MN-major
       const uint32_t idesc_q = make_idesc_bf16(BWD_T, DH, 0, 1);         // dQ: A K-major, B MN-major
-      // operands by role
-      const uint32_t aQ = smem_u32(MODE == 0 ? sS0 : sR0), aK = smem_u32(MODE == 0 ? sR0 : sS0);
-      const uint32_t aDO = smem_u32(MODE == 0 ? sS1 : sR1), aV = smem_u32(MODE == 0 ? sR1 : sS1);
       const uint32_t aP = smem_u32(sP), aDS = smem_u32(sDS);
       mbar_wait(res_full, 0);
       for (int t = 0; t < steps; ++t) {
-        mbar_wait(str_full, (uint32_t)t & 1u);
+        const int b0 = t % NB0, b1 = t % NB1;
+        // operands by role
+        const uint32_t aQ = smem_u32(MODE == 0 ? sSb0[b0] : sR0), aK = smem_u32(MODE == 0 ? sR0 : sSb0[b0]);
+        const uint32_t aDO = smem_u32(MODE == 0 ? sSb1[b1] : sR1), aV = smem_u32(MODE == 0 ? sR1 : sSb1[b1]);
+        mbar_wait(&s0_full[b0], (uint32_t)(t / NB0) & 1u);
         if (t > 0) mbar_wait(sdp_free, (uint32_t)(t - 1) & 1u);
         tc_fence_after();
 #pragma unroll
@@ -218,6 +235,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t off = (kk >> 2) * BWD_BLK + (kk & 3) * 32;
           umma_bf16_ss(tmem_base + 0, make_desc_kmajor_sw128(aQ + off), make_desc_kmajor_sw128(aK + off), idesc_s, kk != 0);
         }
+        mbar_wait(&s1_full[b1], (uint32_t)(t / NB1) & 1u);
+        tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
           const uint32_t off = (kk >> 2) * BWD_BLK + (kk & 3) * 32;
@@ -246,7 +265,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_bf16_ss(tmem_base + 256, aD, bK, idesc_q, (t | kk) != 0);            // dQ += dS K
           }
         }
-        umma_commit(str_free);
+        umma_commit(&s0_free[b0]);
+        umma_commit(&s1_free[b1]);
       }
       umma_commit(acc_done);
     }
@@ -283,7 +303,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       tc_fence_after();
       if (t > 0) {   // P / dS buffers are free once the previous step's second MMA group has completed
-        mbar_wait(str_free, (uint32_t)(t - 1) & 1u);
+        mbar_wait(&s1_free[(t - 1) % NB1], (uint32_t)((t - 1) / NB1) & 1u);
         __syncwarp();
       }
       const bool need_mask = (k0 + BWD_T > kvlen) || W >= 0;   // warp-uniform
