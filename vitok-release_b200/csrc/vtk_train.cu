@@ -8,10 +8,10 @@
 //   SwiGLU                   modules/mlp.py:20-23
 //   LayerNorm (no affine)    modules/norm.py:28-39           the latent bottleneck's output_fn
 //   Charbonnier loss         scripts/train_vae.py:314-320    sqrt(diff^2 + eps^2), masked per-image mean
-//   AdamW (fused, bf16)      scripts/train_vae.py:185-208    torch.optim.AdamW semantics, decoupled weight decay
+//   AdamW (multi-tensor)     scripts/train_vae.py:185-208    torch.optim.AdamW semantics, fp32 master weights + fp32 moments
 //
-// GEMMs of the backward pass (dgrad / wgrad) run on the tcgen05 GEMM of vtk_gemm.cu: dgrad against transposed
-// weight copies, wgrad on activations transposed by transpose_kernel below (both operands K-major).
+// GEMMs of the backward pass (dgrad / wgrad) run on the tcgen05 GEMM of vtk_gemm.cu with transposed-operand variants (the
+// weights and activations are read MN-major as stored: no transposed copies; transpose_kernel below is kept for tests only).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -1012,7 +1012,8 @@ int launch_qk_norm_rope_fwd(const bf16* zraw, long long ldz, const bf16* wq, con
   static const int v1 = getenv("VTK_TRAIN_V1") ? atoi(getenv("VTK_TRAIN_V1")) : 0;   // 1: the round-1 kernels (A/B)
   const int hpw = 32 / (d / 8);
   if (!v1 && heads % hpw == 0 && ldz % 8 == 0 && ldq % 8 == 0 && (long long)M * (3 * heads / hpw) < (1ll << 31) &&
-      ((reinterpret_cast<uintptr_t>(zraw) | reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk)) & 15) == 0) {
+      ((reinterpret_cast<uintptr_t>(zraw) | reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk) |
+        reinterpret_cast<uintptr_t>(rope)) & 15) == 0) {
     const int g16 = grid_for(((long long)M * (3 * heads / hpw) + 3) / 4, 8, 8);
     if (d == 64) qk_norm_rope_fwd16_kernel<64, 4><<<g16, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
     else qk_norm_rope_fwd16_kernel<128, 4><<<g16, 256, 0, st>>>(zraw, ldz, wq, wk, rope, qkv, ldq, M, heads, eps);
@@ -1077,7 +1078,8 @@ int launch_qk_norm_rope_bwd(bf16* dz, long long lddz, const bf16* zraw, long lon
   static const int v1 = getenv("VTK_TRAIN_V1") ? atoi(getenv("VTK_TRAIN_V1")) : 0;
   const int hpw = 32 / (d / 8);
   if (!v1 && heads % hpw == 0 && ldz % 8 == 0 && lddz % 8 == 0 && (long long)M * (2 * heads / hpw) < (1ll << 31) &&
-      ((reinterpret_cast<uintptr_t>(zraw) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk)) & 15) == 0) {
+      ((reinterpret_cast<uintptr_t>(zraw) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(wk) |
+        reinterpret_cast<uintptr_t>(rope)) & 15) == 0) {
     const int g16 = grid_for(((long long)M * (2 * heads / hpw) + 3) / 4, 8, 4);
     if (d == 64) qk_norm_rope_bwd16_kernel<64, 4><<<g16, 256, 0, st>>>(dz, lddz, zraw, ldz, wq, wk, rope, dw, M, heads, eps);
     else qk_norm_rope_bwd16_kernel<128, 4><<<g16, 256, 0, st>>>(dz, lddz, zraw, ldz, wq, wk, rope, dw, M, heads, eps);
