@@ -59,16 +59,26 @@ def test_ragged_batch_matches_reference_golden(ppmeta):
     assert [sha(c.contiguous().cpu().numpy()) for c in crops] == m["crops_sha"]
 
 
-def test_uint8_fused_frontend_bit_exact():
-    """N1: uint8 HWC -> to_tensor|normalize|patchify in one kernel == oracle on the same pixels."""
+@pytest.mark.parametrize("patch,sizes", [
+    (16, [(256, 256), (130, 131), (37, 300)]),
+    # the strip kernel's other paths: p = 32 (32-row strips), widths beyond one 256-pixel strip with aligned (512, 272) and unaligned
+    # rows (517, 259), a one-pixel image, heights that are not multiples of the patch size
+    (32, [(512, 512), (100, 517), (33, 259), (1, 1), (64, 272)]),
+    (16, [(16, 512), (515, 16), (48, 272), (1, 700)]),
+])
+def test_uint8_fused_frontend_bit_exact(patch, sizes):
+    """N1: uint8 HWC -> to_tensor|normalize|patchify in one kernel == oracle on the same pixels (fp32 and bf16 outputs)."""
     import vitok_b200 as vb
     rng = np.random.default_rng(0)
-    sizes = [(256, 256), (130, 131), (37, 300)]
     u8 = [rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8) for h, w in sizes]
-    got = vb.patchify_batch(u8, 16, 512)
-    want = pp_oracle.collate([pp_oracle.patchify(pp_oracle.normalize_u8(a), 16, 512) for a in u8])
+    T = max(((h + patch - 1) // patch) * ((w + patch - 1) // patch) for h, w in sizes) + 3      # a few padding tokens per image too
+    got = vb.patchify_batch(u8, patch, T)
+    want = pp_oracle.collate([pp_oracle.patchify(pp_oracle.normalize_u8(a), patch, T) for a in u8])
     for k in want:
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    got16 = vb.patchify_batch(u8, patch, T, out_dtype=torch.bfloat16)
+    assert torch.equal(got16["patches"], got["patches"].to(torch.bfloat16))
+    assert torch.equal(got16["patch_mask"], got["patch_mask"]) and torch.equal(got16["row_idx"], got["row_idx"])
 
 
 def test_uint8_batched_tensor_frontend_and_u8_roundtrip():
