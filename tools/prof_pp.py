@@ -57,5 +57,10 @@ nv = int(mask.sum())
 packed = _lib.pack_rows(xx, plan)
 mask_d = mask.to(dev)
 line("pack_plan [64, 1024] mask (3 launches)", timed(lambda: _lib.pack_plan(mask_d)), B * 1024 * 9)
-line("pack_rows  (P = 768, half the tokens valid)", timed(lambda: _lib.pack_rows(xx, plan)) , nv * 768 * 4)
+# (the C entry point into a pre-allocated buffer: `_lib.pack_rows` also zero-fills a fresh output tensor, a second pass over it)
+cap = plan["src"].numel()
+packed_out = torch.zeros(cap, 768, dtype=torch.bfloat16, device=dev)
+line("pack_rows  (P = 768, half the tokens valid)",
+     timed(lambda: _lib.check(_lib.load().vtk_pack_rows(_lib.ptr(xx), 768, _lib.ptr(plan["src"]), _lib.ptr(plan["cu"]), B, cap, _lib.ptr(packed_out),
+                                                        768, 768, _lib.stream_ptr()))), nv * 768 * 4)
 line("unpack_rows (P = 768)", timed(lambda: _lib.unpack_rows(packed, plan, B, 1024)), nv * 768 * 2 + B * 1024 * 768 * 2)
