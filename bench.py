@@ -352,13 +352,34 @@ def time_resident(vb, model, inp, steps, warmup, world, dev, use_graph, sampler_
             return o, n + model.last_launch_count
 
     _, per_step = eager()
+    join = lambda: None                     # noqa: E731
     if use_graph:
-        graphed = vb.GraphedAE(model, inp.pd)
-        run = lambda: graphed(inp.pd)       # noqa: E731  (static inputs: no copies, one graph launch)
+        # Small per-rank batches: every kernel of the chain is about one wave and leaves SMs idle at its head and tail, so TWO steps are
+        # kept in flight -- two graphs of the same model with workspaces of their own, replayed alternately on two streams (each step is
+        # still one encode + decode of one batch; VTK_BENCH_DUAL_STREAM=0: one graph, one stream).
+        n_g = 2 if os.environ.get("VTK_BENCH_DUAL_STREAM", "1") != "0" else 1
+        graphs = [vb.GraphedAE(model, inp.pd, private_workspace=n_g > 1) for _ in range(n_g)]
+        main = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_g)] if n_g > 1 else [main]
+        turn = [0]
+
+        def run():
+            i = turn[0] % n_g
+            turn[0] += 1
+            if n_g > 1:
+                streams[i].wait_stream(main)                 # (orders the replay after the timing event recorded on `main`)
+            with torch.cuda.stream(streams[i]):
+                graphs[i](graphs[i].static_in)               # static inputs: no copies, one graph launch
+
+        def join():
+            for st in streams:
+                if st is not main:
+                    main.wait_stream(st)
     else:
         run = lambda: eager()[0]            # noqa: E731
     for _ in range(max(warmup, 3)):
         run()
+    join()
     torch.cuda.synchronize()
     barrier(world)
     torch.cuda.synchronize()
@@ -367,6 +388,7 @@ def time_resident(vb, model, inp, steps, warmup, world, dev, use_graph, sampler_
     ev0.record()
     for _ in range(steps):
         run()
+    join()
     ev1.record()
     torch.cuda.synchronize()
     barrier(world)
@@ -398,10 +420,12 @@ def time_e2e(vb, model, inp, steps, world, dev, use_graph):
     ev_done = [torch.cuda.Event() for _ in range(2)]
     ev_copied = [torch.cuda.Event() for _ in range(2)]
     diag = {"h2d": [], "d2h": [], "cpu": []}
+    dual = use_graph and os.environ.get("VTK_BENCH_DUAL_STREAM", "1") != "0"    # (see time_resident: two steps in flight)
+    s_comp = [torch.cuda.Stream(device=dev) for _ in range(2)] if dual else [s_main, s_main]
     if use_graph:
         first = host_u8.to(dev)
         codecs = [vb.GraphedCodec(model, (first, inp.offs, inp.szs) if inp.ragged else first, patch, T,
-                                  max_grid_size=canvas // patch, output_format="0_255") for _ in range(2)]
+                                  max_grid_size=canvas // patch, output_format="0_255", private_workspace=dual) for _ in range(2)]
         dev_in = [c.static_in for c in codecs]
     else:
         dev_in = [torch.empty_like(host_u8, device=dev) for _ in range(2)]
@@ -422,11 +446,13 @@ def time_e2e(vb, model, inp, steps, world, dev, use_graph):
                 h1.record(s_in)
                 diag["h2d"].append((h0, h1))
             ev_in[b].record(s_in)
-        s_main.wait_event(ev_in[b])
+        sc = s_comp[b]                                  # the compute stream of this step (dual: buffer b has its own)
+        sc.wait_event(ev_in[b])
         if use_graph:
-            s_main.wait_event(ev_copied[b])             # the D2H copy of step i-2 has read this codec's output buffer
-            img = codecs[b]()
-            ev_free[b].record(s_main)
+            sc.wait_event(ev_copied[b])                 # the D2H copy of step i-2 has read this codec's output buffer
+            with torch.cuda.stream(sc):
+                img = codecs[b]()
+            ev_free[b].record(sc)
         else:
             if inp.ragged:
                 d = vb.patchify_packed(dev_in[b], inp.offs, inp.szs, patch, T, out_dtype=torch.bfloat16)
@@ -439,7 +465,7 @@ def time_e2e(vb, model, inp, steps, world, dev, use_graph):
             # the D2H copy of step i-2 (it read keep[b]) has finished before that tensor's memory can be reused on s_main
             s_main.wait_event(ev_copied[b])
             keep[b] = img
-        ev_done[b].record(s_main)
+        ev_done[b].record(sc)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done[b])
             if timed:
@@ -454,6 +480,9 @@ def time_e2e(vb, model, inp, steps, world, dev, use_graph):
             diag["cpu"].append((time.perf_counter() - c0) * 1e3)
 
     def drain():
+        for st in s_comp:
+            if st is not s_main:
+                s_main.wait_stream(st)
         s_main.wait_stream(s_out)
         s_main.wait_stream(s_in)
 

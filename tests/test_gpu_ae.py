@@ -263,6 +263,37 @@ def test_cuda_graph_replay_equals_eager(backend):
         assert out["orig_height"] is b["orig_height"]
 
 
+def test_graphs_with_private_workspaces_replay_concurrently():
+    """GraphedAE(private_workspace=True): two graphs of ONE model, each with workspaces of its own, replayed at the same time on two
+    streams (two batches in flight: what bench.py does for the small per-rank batches of a strong-scaled job) give exactly the eager
+    results of their own batches, many times over; the model's own workspaces are back in place afterwards."""
+    import vitok_b200 as vb
+    cfg0 = ae_oracle.decode_variant(SMALL)
+    sd = make_state_dict(cfg0, seed=1, stress=True)
+    model, cfg = _model(SMALL, sd, "sdpa")
+    b1 = _to_cuda(_batch([(128, 128), (96, 64), (50, 120)], 16, 64, seed=5))
+    b2 = _to_cuda(_batch([(64, 100), (128, 128), (16, 16)], 16, 64, seed=6))
+    with torch.no_grad():
+        e1 = model.decode(model.encode(b1))["patches"].clone()
+        e2 = model.decode(model.encode(b2))["patches"].clone()
+    own = dict(model._ws)
+    g1 = vb.GraphedAE(model, b1, private_workspace=True)
+    g2 = vb.GraphedAE(model, b2, private_workspace=True)
+    assert set(model._ws) == set(own) and all(model._ws[k] is own[k] for k in own)
+    assert not {t.data_ptr() for t in g1._keep[0]} & {t.data_ptr() for t in g2._keep[0]}
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(20):
+        with torch.cuda.stream(s1):
+            o1 = g1(g1.static_in)["patches"]
+        with torch.cuda.stream(s2):
+            o2 = g2(g2.static_in)["patches"]
+    torch.cuda.synchronize()
+    assert torch.equal(o1, e1) and torch.equal(o2, e2)
+    with torch.no_grad():                                     # eager calls still work and still agree
+        assert torch.equal(model.decode(model.encode(b1))["patches"], e1)
+
+
 @pytest.mark.parametrize("backend", ["sdpa", "flash"])
 def test_reference_smoke_case_Bd2_Bd4(backend):
     """The reference's own AE smoke test (tests/cpu/test_ae.py:43-76,162-233): variant Bd2-Bd4/1x16x32, B = 2, N = 64 random

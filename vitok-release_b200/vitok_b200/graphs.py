@@ -22,7 +22,7 @@ class GraphedAE:
     be in eval mode; re-create the object after changing weights (``load_state_dict``, ``.to()``, ``quantize()``).
     """
 
-    def __init__(self, model, example_batch: Dict[str, torch.Tensor], warmup: int = 2):
+    def __init__(self, model, example_batch: Dict[str, torch.Tensor], warmup: int = 2, private_workspace: bool = False):
         if model.training:
             raise RuntimeError("GraphedAE: put the model in eval mode first (model.eval())")
         self.model = model
@@ -30,6 +30,19 @@ class GraphedAE:
         if dev.type != "cuda":
             raise RuntimeError("GraphedAE: the model must be on a CUDA device")
         self.static_in = {k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in example_batch.items()}
+        # private_workspace: capture with workspaces of its own instead of the model's (one per side, shared by every graph and eager call
+        # of that shape), so that several graphs of one model may be replayed CONCURRENTLY on different streams -- two batches in flight
+        # fill the SMs that the one-wave kernels of a small batch leave idle.  The model's own workspaces are put back afterwards.
+        saved_ws = None
+        if private_workspace:
+            saved_ws, model._ws = model._ws, {}
+        try:
+            self._capture(model, dev, warmup)
+        finally:
+            if saved_ws is not None:
+                model._ws = saved_ws
+
+    def _capture(self, model, dev, warmup):
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -94,7 +107,7 @@ class GraphedCodec:
     """
 
     def __init__(self, model, images, patch: int = 16, max_tokens: int = 256, max_grid_size: Optional[int] = None,
-                 output_format: str = "0_255", warmup: int = 2):
+                 output_format: str = "0_255", warmup: int = 2, private_workspace: bool = False):
         from .pp import patchify_batch, patchify_packed, unpatchify
         if model.training:
             raise RuntimeError("GraphedCodec: put the model in eval mode first (model.eval())")
@@ -132,19 +145,26 @@ class GraphedCodec:
             self.launches = n + 2                  # cell map + unpatchify
             return unpatchify(d, patch, max_grid_size=max_grid_size, output_format=output_format)
 
-        with torch.cuda.device(dev):
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side), torch.no_grad():
-                for _ in range(max(warmup, 1)):
-                    run()
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            self._sig = GraphedAE._state(self)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph), torch.no_grad():
-                self.static_out = run()
-        self._keep = (list(model._ws.values()), [t for lst in model._packed.values() for t in lst])
+        saved_ws = None
+        if private_workspace:                      # see GraphedAE: workspaces of its own, for concurrent replays on several streams
+            saved_ws, model._ws = model._ws, {}
+        try:
+            with torch.cuda.device(dev):
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side), torch.no_grad():
+                    for _ in range(max(warmup, 1)):
+                        run()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                self._sig = GraphedAE._state(self)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph), torch.no_grad():
+                    self.static_out = run()
+            self._keep = (list(model._ws.values()), [t for lst in model._packed.values() for t in lst])
+        finally:
+            if saved_ws is not None:
+                model._ws = saved_ws
         self._dev = dev
 
     def __call__(self, images: Optional[torch.Tensor] = None) -> torch.Tensor:
